@@ -1,0 +1,227 @@
+/*
+ * skgpu_batch.h -- batch C ABI of streamkit_b200 (libskgpu.so), version 1.
+ *
+ * This is the per-tick boundary a frame-batching layer in StreamKit's crates/engine binds over FFI
+ * (SURVEY.md 8b "Batch C ABI"; INTEGRATION.md shows the Rust `extern "C"` block). It does not exist in
+ * the reference: there every node is one tokio task fed one packet at a time
+ * (crates/engine/src/dynamic_actor.rs:393-495, crates/core/src/node.rs:191-226). Each entry point below
+ * names the reference code whose per-packet work it replaces.
+ *
+ * Conventions (mirroring the native plugin ABI, sdks/plugin-sdk/native/src/types.rs):
+ *   - plain C, POD structs, no exceptions cross the boundary;
+ *   - every call returns skgpu_rc (0 = ok, <0 = error); the message for the last error on the calling
+ *     thread is borrowed from skgpu_last_error() and stays valid until the next error on that thread
+ *     (same ownership rule as CResult.error_message, types.rs:42-48, conversions.rs:441-461);
+ *   - a context is thread-compatible: one submitting thread at a time per context; different contexts
+ *     (one per GPU) are independent. Sessions shard across GPUs by mix-group id, no collective.
+ *   - all audio is interleaved (crates/core/src/types.rs:210-211). Offsets are BYTE offsets into the
+ *     plan's device arena and must be 4-byte aligned (2 for s16); 16-byte alignment enables the
+ *     128-bit / TMA paths.
+ *   - there is NO CPU fallback: without a CUDA device skgpu_ctx_create fails.
+ */
+#ifndef SKGPU_BATCH_H
+#define SKGPU_BATCH_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SKGPU_ABI_VERSION 1u
+
+typedef int32_t skgpu_rc;
+#define SKGPU_OK 0
+#define SKGPU_ERR_INVALID (-1)   /* bad argument / configuration (StreamKitError::Configuration) */
+#define SKGPU_ERR_CUDA (-2)      /* CUDA runtime error (StreamKitError::Runtime, node -> Failed) */
+#define SKGPU_ERR_NOMEM (-3)
+#define SKGPU_ERR_STATE (-4)     /* call not valid in the current state */
+#define SKGPU_ERR_NODEVICE (-5)
+
+typedef struct skgpu_ctx skgpu_ctx;
+typedef struct skgpu_plan skgpu_plan;
+
+uint32_t skgpu_abi_version(void);
+const char *skgpu_last_error(void);
+
+/* ------------------------------------------------------------------ context */
+
+typedef struct skgpu_ctx_config {
+    uint32_t max_streams;     /* resampler stream slots (per-stream state in HBM) */
+    uint32_t max_channels;    /* 1..8; history is stored 16 frames x max_channels per slot */
+    uint32_t fifo_frames;     /* per-slot device re-framing ring (frames, power of two), 0 = none */
+    uint32_t flags;           /* reserved, 0 */
+} skgpu_ctx_config;
+
+skgpu_rc skgpu_ctx_create(int32_t device_ordinal, const skgpu_ctx_config *cfg, skgpu_ctx **out);
+void skgpu_ctx_destroy(skgpu_ctx *ctx);
+/* "NVIDIA B200" etc.; sm count; for logs */
+skgpu_rc skgpu_ctx_device_info(skgpu_ctx *ctx, char *name, size_t name_len, int32_t *sm_count, int32_t *cc_major,
+                               int32_t *cc_minor);
+
+/* Pinned (page-locked) host memory for the tick arenas the batching layer gathers frames into.
+ * Replaces AudioFramePool buckets (crates/core/src/frame_pool.rs:302-317) on the batched path. */
+skgpu_rc skgpu_pinned_alloc(skgpu_ctx *ctx, size_t bytes, void **out);
+skgpu_rc skgpu_pinned_free(skgpu_ctx *ctx, void *p);
+
+/* ------------------------------------------------------------------ resampler stream slots
+ * One slot = one rubato::FastFixedIn<f32>(Linear) instance (resampler.rs:232-238): last_index (f64) and
+ * a 16-frame history live in HBM for the lifetime of the stream. */
+
+typedef struct skgpu_stream_cfg {
+    uint32_t in_rate;           /* Hz, from the first packet (resampler.rs:206-209) */
+    uint32_t out_rate;          /* AudioResamplerConfig.target_sample_rate (resampler.rs:22-27) */
+    uint32_t chunk_frames;      /* AudioResamplerConfig.chunk_frames, input frames per process() */
+    uint16_t channels;          /* 1..max_channels */
+    uint16_t reserved;
+} skgpu_stream_cfg;
+
+skgpu_rc skgpu_stream_open(skgpu_ctx *ctx, const skgpu_stream_cfg *cfg, uint32_t *slot_out);
+/* bulk open of n identical streams (session ramp-up); slots_out[n] */
+skgpu_rc skgpu_stream_open_many(skgpu_ctx *ctx, const skgpu_stream_cfg *cfg, uint32_t n, uint32_t *slots_out);
+/* back to a fresh FastFixedIn: zero history, last_index = -4.0 */
+skgpu_rc skgpu_stream_reset(skgpu_ctx *ctx, uint32_t slot);
+skgpu_rc skgpu_stream_close(skgpu_ctx *ctx, uint32_t slot);
+/* read back state (tests, checkpointing): hist receives 16*channels floats (interleaved) */
+skgpu_rc skgpu_stream_get_state(skgpu_ctx *ctx, uint32_t slot, double *last_index, float *hist, uint64_t *fifo_written,
+                                uint64_t *fifo_read);
+/* upper bound of frames one chunk can produce for this configuration */
+uint32_t skgpu_stream_max_out_frames(const skgpu_stream_cfg *cfg);
+
+/* ------------------------------------------------------------------ descriptors */
+
+#define SKGPU_NO_GAIN 0xFFFFFFFFu /* gain_idx sentinel: no multiply */
+
+/* format-conversion / gain segments (one per frame). Replaces gain.rs:184-190 and the build-defined
+ * f32<->s16 conversion (types.rs:26-29 only declares SampleFormat::S16Le). */
+typedef enum skgpu_cvt_mode {
+    SKGPU_CVT_F32_TO_F32 = 0, /* y = x * g                                  (audio::gain)               */
+    SKGPU_CVT_F32_TO_S16 = 1, /* s = sat_s16(rint_even((x * g) * 32768))    (gain -> clip -> s16 pack)  */
+    SKGPU_CVT_S16_TO_F32 = 2  /* y = (s / 32768) * g                         (s16 ingest)                */
+} skgpu_cvt_mode;
+
+typedef struct skgpu_seg {
+    uint64_t in_off;
+    uint64_t out_off;    /* may equal in_off for F32_TO_F32 (in place, like make_samples_mut) */
+    uint32_t n_samples;  /* total samples (all channels) */
+    uint32_t gain_idx;   /* index into the plan's gain table, or SKGPU_NO_GAIN */
+} skgpu_seg;
+
+/* resampler work item: one chunk of one stream. Replaces resampler.rs:377-417 (+ rubato process). */
+#define SKGPU_RS_TO_FIFO 1u /* append output to the slot's device ring instead of out_off */
+typedef struct skgpu_rs_item {
+    uint64_t in_off;          /* chunk_frames * channels f32, interleaved */
+    uint64_t out_off;         /* receives out_frames * channels f32 (ignored with SKGPU_RS_TO_FIFO) */
+    uint32_t slot;
+    uint32_t out_cap_frames;  /* capacity at out_off, frames */
+    uint32_t flags;
+    uint32_t reserved;
+} skgpu_rs_item;
+
+typedef struct skgpu_rs_result { /* written per item at the op's results offset */
+    uint32_t out_frames;
+    uint32_t status;          /* 0 ok; 1 = output truncated (out_cap_frames too small); 2 = run table overflow */
+} skgpu_rs_result;
+
+/* mixer. Replaces mixer.rs:922-1019 / :1436-1492 (+ :1027-1078). Inputs are listed in PIN ORDER
+ * (in_0, in_1, ...); base-frame selection and swap_remove ordering (mixer.rs:960-980) run on the device
+ * every tick from the inputs that are present. */
+#define SKGPU_MIX_IN_UNIQUE 1u   /* AudioFrame::has_unique_samples() */
+#define SKGPU_MIX_IN_FIFO 2u     /* read one output_frame_size packet from slot's device ring */
+typedef struct skgpu_mix_input {
+    uint64_t in_off;
+    uint32_t n_frames;    /* frames per channel in this input frame */
+    uint16_t channels;
+    uint16_t flags;
+    uint32_t gain_idx;    /* per-input audio::gain applied before the sum (rounded separately), or NO_GAIN */
+    uint32_t slot;        /* for SKGPU_MIX_IN_FIFO */
+} skgpu_mix_input;
+
+#define SKGPU_MIX_OUT_S16 1u     /* epilogue: clip + pack s16 instead of storing f32 */
+typedef struct skgpu_mix_group {
+    uint64_t out_off;
+    uint32_t first_input;  /* index of the group's first skgpu_mix_input */
+    uint32_t n_inputs;
+    uint32_t out_frames;   /* frames per channel of the output (sync: longest input; clocked: fixed) */
+    uint16_t out_channels; /* sticky max channel count (mixer.rs:947-948), decided by the host */
+    uint16_t flags;
+    uint32_t gain_idx;     /* master audio::gain after the mix, or NO_GAIN */
+    uint32_t reserved;
+} skgpu_mix_group;
+
+/* ------------------------------------------------------------------ plan = one compiled tick
+ * A plan is the steady-state shape of a tick: an ordered list of ops whose descriptor tables live on the
+ * device, one H2D range and one D2H range. Built once, replayed every 20 ms; tables can be replaced
+ * when sessions come and go (same capacity), gains / presence change per tick. */
+
+skgpu_rc skgpu_plan_create(skgpu_ctx *ctx, size_t arena_bytes, skgpu_plan **out);
+void skgpu_plan_destroy(skgpu_plan *plan);
+
+/* each add_* returns the op index in *op_out (may be NULL) */
+skgpu_rc skgpu_plan_add_convert(skgpu_plan *plan, skgpu_cvt_mode mode, const skgpu_seg *segs, uint32_t n,
+                                uint32_t *op_out);
+skgpu_rc skgpu_plan_add_resample(skgpu_plan *plan, const skgpu_rs_item *items, uint32_t n, uint64_t results_off,
+                                 uint32_t *op_out);
+skgpu_rc skgpu_plan_add_mix(skgpu_plan *plan, const skgpu_mix_group *groups, uint32_t n_groups,
+                            const skgpu_mix_input *inputs, uint32_t n_inputs, uint32_t *op_out);
+
+/* replace an op's descriptor table in place (n <= capacity given at add time) */
+skgpu_rc skgpu_plan_update_convert(skgpu_plan *plan, uint32_t op, const skgpu_seg *segs, uint32_t n);
+skgpu_rc skgpu_plan_update_resample(skgpu_plan *plan, uint32_t op, const skgpu_rs_item *items, uint32_t n);
+skgpu_rc skgpu_plan_update_mix(skgpu_plan *plan, uint32_t op, const skgpu_mix_group *groups, uint32_t n_groups,
+                               const skgpu_mix_input *inputs, uint32_t n_inputs);
+
+/* tick I/O ranges: host_in[0..bytes) -> arena[h2d_off..), arena[d2h_off..) -> host_out[0..bytes) */
+skgpu_rc skgpu_plan_set_io(skgpu_plan *plan, uint64_t h2d_off, uint64_t h2d_bytes, uint64_t d2h_off, uint64_t d2h_bytes);
+
+/* per-tick dynamic parameters, snapshotted at submit (gain.rs:151: control messages are drained before
+ * each packet, so a new gain applies from the next frame on). present[i] != 0 <=> mix input i of op
+ * `mix_op` delivered a frame this tick; absent inputs are silence (mixer.rs:999-1009, :1354-1367). */
+skgpu_rc skgpu_plan_set_gains(skgpu_plan *plan, const float *gains, uint32_t n);
+skgpu_rc skgpu_plan_set_present(skgpu_plan *plan, uint32_t mix_op, const uint8_t *present, uint32_t n);
+
+/* validates, uploads tables, optionally captures the CUDA graph */
+skgpu_rc skgpu_plan_finalize(skgpu_plan *plan);
+
+#define SKGPU_SUBMIT_NO_H2D 1u   /* inputs already resident in the device arena */
+#define SKGPU_SUBMIT_NO_D2H 2u
+#define SKGPU_SUBMIT_GRAPH 4u    /* replay the captured CUDA graph instead of individual launches */
+#define SKGPU_SUBMIT_TIME_OPS 8u /* record a CUDA event pair around every op (stream mode only) */
+
+/* asynchronous: enqueues H2D, kernels, D2H on the context stream and returns */
+skgpu_rc skgpu_tick_submit(skgpu_plan *plan, const void *host_in, void *host_out, uint32_t flags);
+
+typedef struct skgpu_tick_timing { /* of the most recent submitted tick, CUDA events on the ctx stream */
+    float h2d_ms;
+    float kernels_ms;
+    float d2h_ms;
+    float total_ms;
+} skgpu_tick_timing;
+/* blocks until everything submitted so far has finished; timing may be NULL */
+skgpu_rc skgpu_tick_wait(skgpu_plan *plan, skgpu_tick_timing *timing);
+
+/* averaged device time of one op over the ticks submitted with SKGPU_SUBMIT_TIME_OPS since the last reset.
+ * For a resample op, sub = 0 is the phase-table kernel, sub = 1 the interpolation kernel. */
+skgpu_rc skgpu_plan_op_time(skgpu_plan *plan, uint32_t op, uint32_t sub, float *avg_ms, uint32_t *n_samples);
+skgpu_rc skgpu_plan_reset_op_times(skgpu_plan *plan);
+/* number of kernel launches one tick of this plan performs (for bench.py's gpu_launches) */
+uint32_t skgpu_plan_launches_per_tick(const skgpu_plan *plan);
+
+/* direct arena access (tests, device-resident benchmarking) */
+skgpu_rc skgpu_arena_upload(skgpu_plan *plan, uint64_t off, const void *host, size_t bytes);
+skgpu_rc skgpu_arena_download(skgpu_plan *plan, uint64_t off, void *host, size_t bytes);
+skgpu_rc skgpu_arena_fill(skgpu_plan *plan, uint64_t off, int byte_value, size_t bytes);
+
+/* CUDA-event stopwatch on the context stream (device time of a whole timed region) */
+skgpu_rc skgpu_timer_start(skgpu_ctx *ctx);
+skgpu_rc skgpu_timer_stop(skgpu_ctx *ctx);
+skgpu_rc skgpu_timer_elapsed_ms(skgpu_ctx *ctx, float *ms); /* synchronises on the stop event */
+skgpu_rc skgpu_ctx_sync(skgpu_ctx *ctx);
+/* writes a buffer larger than L2 (flush between timed iterations of L2-sized workloads) */
+skgpu_rc skgpu_ctx_flush_l2(skgpu_ctx *ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,230 @@
+"""ctypes wrapper of the C oracle (oracle/libsk_oracle.so). TEST INFRASTRUCTURE ONLY.
+
+Importers allowed: tests/, __graft_entry__.smoke(), bench.py's cpu_baseline / --impl reference legs.
+Nothing under streamkit_b200/ may import this module.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libsk_oracle.so")
+REF_GAIN_PLUGIN = os.path.join(_HERE, "_ref", "libgain_plugin_c.so")
+
+
+class Frame(C.Structure):
+    _fields_ = [("samples", C.POINTER(C.c_float)), ("n_samples", C.c_uint32), ("channels", C.c_uint16), ("unique", C.c_uint8),
+                ("_pad", C.c_uint8)]
+
+
+class PacketMeta(C.Structure):
+    _fields_ = [("timestamp_us", C.c_uint64), ("has_timestamp", C.c_uint8), ("duration_us", C.c_uint64), ("sequence", C.c_uint64)]
+
+
+EMIT_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_uint32, C.c_uint16, C.POINTER(C.c_float), C.c_size_t, C.POINTER(PacketMeta))
+
+_lib = None
+
+
+def build():
+    subprocess.check_call(["make", "-s", "-C", _HERE])
+
+
+def load() -> C.CDLL:
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        build()
+    lib = C.CDLL(LIB_PATH)
+    f32p, i16p, vp = C.POINTER(C.c_float), C.POINTER(C.c_int16), C.c_void_p
+    lib.sko_gain_validate.restype = C.c_int
+    lib.sko_gain_validate.argtypes = [C.c_float, C.c_char_p, C.c_size_t]
+    lib.sko_gain_apply.argtypes = [vp, C.c_size_t, C.c_float]
+    lib.sko_f32_to_s16_buf.argtypes = [vp, vp, C.c_size_t]
+    lib.sko_s16_to_f32_buf.argtypes = [vp, vp, C.c_size_t]
+    lib.sko_gain_f32_to_s16_buf.argtypes = [vp, vp, C.c_size_t, C.c_float]
+    lib.sko_mix_plan.argtypes = [C.POINTER(Frame), C.c_size_t, C.c_uint16, C.c_size_t, vp, C.POINTER(C.c_int)]
+    lib.sko_mix_sync.restype = C.c_int
+    lib.sko_mix_sync.argtypes = [C.POINTER(Frame), C.c_size_t, C.c_uint16, vp, C.c_size_t, C.POINTER(C.c_uint16), C.POINTER(C.c_size_t)]
+    lib.sko_mix_clocked.restype = C.c_int
+    lib.sko_mix_clocked.argtypes = [C.POINTER(Frame), C.c_size_t, C.c_uint16, C.c_size_t, vp, C.c_size_t]
+    lib.sko_ffi_new.restype = vp
+    lib.sko_ffi_new.argtypes = [C.c_double, C.c_size_t, C.c_size_t]
+    lib.sko_ffi_free.argtypes = [vp]
+    lib.sko_ffi_out_max.restype = C.c_size_t
+    lib.sko_ffi_out_max.argtypes = [vp]
+    lib.sko_ffi_process_interleaved.restype = C.c_size_t
+    lib.sko_ffi_process_interleaved.argtypes = [vp, vp, vp, C.c_size_t]
+    lib.sko_ffi_last_index.restype = C.c_double
+    lib.sko_ffi_last_index.argtypes = [vp]
+    lib.sko_ffi_history.argtypes = [vp, vp]
+    lib.sko_rsnode_new.restype = vp
+    lib.sko_rsnode_new.argtypes = [C.c_uint32, C.c_size_t, C.c_size_t, C.c_char_p, C.c_size_t]
+    lib.sko_rsnode_free.argtypes = [vp]
+    lib.sko_rsnode_push.restype = C.c_int
+    lib.sko_rsnode_push.argtypes = [vp, C.c_uint32, C.c_uint16, vp, C.c_size_t, C.c_int, C.c_uint64, EMIT_FN, vp, C.c_char_p, C.c_size_t]
+    lib.sko_rsnode_finish.restype = C.c_int
+    lib.sko_rsnode_finish.argtypes = [vp, EMIT_FN, vp]
+    lib.sko_duration_us_for_frames.restype = C.c_uint64
+    lib.sko_duration_us_for_frames.argtypes = [C.c_uint32, C.c_size_t]
+    _lib = lib
+    return lib
+
+
+def _p(a: np.ndarray):
+    return C.c_void_p(a.ctypes.data)
+
+
+# ---------------------------------------------------------------- gain / s16
+
+def gain_validate(gain: float):
+    err = C.create_string_buffer(256)
+    rc = load().sko_gain_validate(C.c_float(gain), err, 256)
+    return rc, err.value.decode()
+
+
+def gain(x: np.ndarray, g: float) -> np.ndarray:
+    y = np.array(x, dtype=np.float32, copy=True).ravel()
+    load().sko_gain_apply(_p(y), y.size, C.c_float(g))
+    return y
+
+
+def f32_to_s16(x: np.ndarray) -> np.ndarray:
+    x = np.ascontiguousarray(x, dtype=np.float32).ravel()
+    out = np.empty(x.size, dtype=np.int16)
+    load().sko_f32_to_s16_buf(_p(x), _p(out), x.size)
+    return out
+
+
+def s16_to_f32(s: np.ndarray) -> np.ndarray:
+    s = np.ascontiguousarray(s, dtype=np.int16).ravel()
+    out = np.empty(s.size, dtype=np.float32)
+    load().sko_s16_to_f32_buf(_p(s), _p(out), s.size)
+    return out
+
+
+def gain_f32_to_s16(x: np.ndarray, g: float) -> np.ndarray:
+    x = np.ascontiguousarray(x, dtype=np.float32).ravel()
+    out = np.empty(x.size, dtype=np.int16)
+    load().sko_gain_f32_to_s16_buf(_p(x), _p(out), x.size, C.c_float(g))
+    return out
+
+
+# ---------------------------------------------------------------- mixer
+
+def _frames(frames):
+    """frames: list of (samples f32 1-D, channels, unique)"""
+    keep = [np.ascontiguousarray(f[0], dtype=np.float32).ravel() for f in frames]
+    arr = (Frame * max(len(frames), 1))()
+    for i, (f, k) in enumerate(zip(frames, keep)):
+        arr[i].samples = k.ctypes.data_as(C.POINTER(C.c_float))
+        arr[i].n_samples = k.size
+        arr[i].channels = f[1]
+        arr[i].unique = 1 if (len(f) < 3 or f[2]) else 0
+    return arr, keep
+
+
+def mix_plan(frames, out_channels: int, out_size: int):
+    arr, _keep = _frames(frames)
+    order = np.zeros(max(len(frames), 1), dtype=np.uint32)
+    hb = C.c_int()
+    load().sko_mix_plan(arr, len(frames), out_channels, out_size, _p(order), C.byref(hb))
+    return order[: len(frames)].tolist(), bool(hb.value)
+
+
+def mix_sync(frames, max_channels_seen: int = 0):
+    arr, _keep = _frames(frames)
+    cap = max([k.size for k in _keep] + [1]) * 8 * max(max_channels_seen, 1)
+    out = np.zeros(cap, dtype=np.float32)
+    oc, ol = C.c_uint16(), C.c_size_t()
+    rc = load().sko_mix_sync(arr, len(frames), max_channels_seen, _p(out), cap, C.byref(oc), C.byref(ol))
+    assert rc == 0
+    return out[: ol.value].copy(), oc.value
+
+
+def mix_clocked(frames, out_channels: int, frame_samples_per_channel: int):
+    arr, _keep = _frames(frames)
+    out = np.zeros(out_channels * frame_samples_per_channel, dtype=np.float32)
+    rc = load().sko_mix_clocked(arr, len(frames), out_channels, frame_samples_per_channel, _p(out), out.size)
+    assert rc == 0
+    return out
+
+
+# ---------------------------------------------------------------- resampler
+
+class FastFixedIn:
+    """rubato::FastFixedIn<f32>, PolynomialDegree::Linear (restated)."""
+
+    def __init__(self, in_rate: int, out_rate: int, chunk_frames: int, channels: int):
+        self.lib = load()
+        self.channels = channels
+        self.chunk = chunk_frames
+        self.h = self.lib.sko_ffi_new(float(out_rate) / float(in_rate), chunk_frames, channels)
+        assert self.h
+        self.out_max = self.lib.sko_ffi_out_max(self.h)
+
+    def process(self, chunk: np.ndarray) -> np.ndarray:
+        chunk = np.ascontiguousarray(chunk, dtype=np.float32).ravel()
+        assert chunk.size == self.chunk * self.channels
+        out = np.empty(self.out_max * self.channels, dtype=np.float32)
+        n = self.lib.sko_ffi_process_interleaved(self.h, _p(chunk), _p(out), self.out_max)
+        return out[: n * self.channels].copy()
+
+    @property
+    def last_index(self) -> float:
+        return self.lib.sko_ffi_last_index(self.h)
+
+    def history(self) -> np.ndarray:
+        h = np.empty(16 * self.channels, dtype=np.float32)
+        self.lib.sko_ffi_history(self.h, _p(h))
+        return h
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.lib.sko_ffi_free(self.h)
+            self.h = None
+
+
+class ResamplerNode:
+    """AudioResamplerNode (resampler.rs:197-740) restated: push packets, collect emitted packets."""
+
+    def __init__(self, target_sample_rate: int, chunk_frames: int = 960, output_frame_size: int = 960):
+        self.lib = load()
+        err = C.create_string_buffer(256)
+        self.h = self.lib.sko_rsnode_new(target_sample_rate, chunk_frames, output_frame_size, err, 256)
+        if not self.h:
+            raise ValueError(err.value.decode())
+        self.out = []
+        self._cb = EMIT_FN(self._emit)
+
+    def _emit(self, ud, rate, ch, samples, n, meta):
+        arr = np.ctypeslib.as_array(samples, shape=(n,)).copy() if n else np.zeros(0, dtype=np.float32)
+        m = meta.contents
+        self.out.append(dict(sample_rate=rate, channels=ch, samples=arr,
+                             timestamp_us=(m.timestamp_us if m.has_timestamp else None), duration_us=m.duration_us,
+                             sequence=m.sequence))
+
+    def push(self, sample_rate: int, channels: int, samples: np.ndarray, timestamp_us=None):
+        s = np.ascontiguousarray(samples, dtype=np.float32).ravel()
+        err = C.create_string_buffer(256)
+        rc = self.lib.sko_rsnode_push(self.h, sample_rate, channels, _p(s), s.size, 0 if timestamp_us is None else 1,
+                                      0 if timestamp_us is None else timestamp_us, self._cb, None, err, 256)
+        if rc != 0:
+            raise RuntimeError(err.value.decode())
+
+    def finish(self):
+        self.lib.sko_rsnode_finish(self.h, self._cb, None)
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.lib.sko_rsnode_free(self.h)
+            self.h = None
+
+
+def duration_us_for_frames(rate: int, frames: int) -> int:
+    return load().sko_duration_us_for_frames(rate, frames)

@@ -1,0 +1,935 @@
+// skgpu.cu -- implementation of the batch C ABI (include/skgpu_batch.h) over the kernels in kernels.cuh.
+//
+// Shape of the runtime: one context per GPU (one CUDA stream, per-stream resampler state in HBM as SoA
+// tables), plans = compiled ticks (device-resident descriptor tables + one device arena + an optional
+// captured CUDA graph), and an asynchronous submit that enqueues H2D -> kernels -> D2H on the context
+// stream. Nothing here ever computes audio on the CPU: if CUDA is unavailable every entry point fails.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "kernels.cuh"
+
+using namespace skgpu;
+
+// ------------------------------------------------------------------ errors (borrowed TLS string, like
+// sdks/plugin-sdk/native/src/conversions.rs:441-461 error_to_c)
+
+static thread_local std::string g_err;
+
+static skgpu_rc fail(skgpu_rc rc, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return rc;
+}
+
+#define CU(expr)                                                                                     \
+    do {                                                                                             \
+        cudaError_t e__ = (expr);                                                                    \
+        if (e__ != cudaSuccess) return fail(SKGPU_ERR_CUDA, "%s failed: %s", #expr, cudaGetErrorString(e__)); \
+    } while (0)
+
+extern "C" uint32_t skgpu_abi_version(void) { return SKGPU_ABI_VERSION; }
+extern "C" const char *skgpu_last_error(void) { return g_err.c_str(); }
+
+// ------------------------------------------------------------------ context
+
+static constexpr int DYN_RING = 4;  // staging ring depth for per-tick dynamic tables
+
+struct skgpu_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t tm0 = nullptr, tm1 = nullptr;
+    skgpu_ctx_config cfg{};
+    SlotTables st{};
+    // host mirrors of slot configuration
+    std::vector<double> h_t;
+    std::vector<int32_t> h_end;
+    std::vector<uint32_t> h_chunk, h_ch;
+    std::vector<uint8_t> used;
+    std::vector<uint32_t> free_list;
+    uint32_t next_fresh = 0;
+    uint32_t dirty_lo = 0xFFFFFFFFu, dirty_hi = 0;
+    std::vector<uint32_t> reset_list;
+    uint32_t *d_reset = nullptr;
+    uint32_t d_reset_cap = 0;
+    uint4 *l2buf = nullptr;
+    size_t l2n = 0;
+    int sm_count = 0;
+};
+
+template <typename T>
+static cudaError_t dalloc(T **p, size_t n) {
+    return cudaMalloc((void **)p, n * sizeof(T));
+}
+
+static skgpu_rc ctx_flush(skgpu_ctx *c) {
+    // upload dirty slot configuration, then reset freshly opened / reset slots on the device
+    if (c->dirty_lo < c->dirty_hi) {
+        const uint32_t lo = c->dirty_lo, n = c->dirty_hi - c->dirty_lo;
+        CU(cudaMemcpyAsync(c->st.t_ratio + lo, c->h_t.data() + lo, n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+        CU(cudaMemcpyAsync(c->st.end_idx + lo, c->h_end.data() + lo, n * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+        CU(cudaMemcpyAsync(c->st.chunk + lo, c->h_chunk.data() + lo, n * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
+        CU(cudaMemcpyAsync(c->st.channels + lo, c->h_ch.data() + lo, n * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
+        CU(cudaStreamSynchronize(c->stream));  // pageable sources: make the copies complete before mirrors change
+        c->dirty_lo = 0xFFFFFFFFu;
+        c->dirty_hi = 0;
+    }
+    if (!c->reset_list.empty()) {
+        const uint32_t n = (uint32_t)c->reset_list.size();
+        if (n > c->d_reset_cap) {
+            if (c->d_reset) cudaFree(c->d_reset);
+            c->d_reset_cap = std::max<uint32_t>(n, 1024u);
+            CU(dalloc(&c->d_reset, c->d_reset_cap));
+        }
+        CU(cudaMemcpyAsync(c->d_reset, c->reset_list.data(), n * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
+        k_reset_slots<<<n, 128, 0, c->stream>>>(c->d_reset, n, c->st);
+        CU(cudaGetLastError());
+        CU(cudaStreamSynchronize(c->stream));
+        c->reset_list.clear();
+    }
+    return SKGPU_OK;
+}
+
+extern "C" skgpu_rc skgpu_ctx_create(int32_t device_ordinal, const skgpu_ctx_config *cfg, skgpu_ctx **out) {
+    if (!cfg || !out) return fail(SKGPU_ERR_INVALID, "skgpu_ctx_create: null argument");
+    if (cfg->max_streams == 0) return fail(SKGPU_ERR_INVALID, "max_streams must be > 0");
+    if (cfg->max_channels == 0 || cfg->max_channels > 8) return fail(SKGPU_ERR_INVALID, "max_channels must be in 1..8");
+    if (cfg->fifo_frames != 0 && (cfg->fifo_frames & (cfg->fifo_frames - 1)) != 0)
+        return fail(SKGPU_ERR_INVALID, "fifo_frames must be a power of two");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(SKGPU_ERR_NODEVICE, "no CUDA device available (%s); streamkit_b200 has no CPU fallback",
+                    e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+    if (device_ordinal < 0 || device_ordinal >= ndev) return fail(SKGPU_ERR_INVALID, "device ordinal %d out of range (have %d)", device_ordinal, ndev);
+    CU(cudaSetDevice(device_ordinal));
+    skgpu_ctx *c = new (std::nothrow) skgpu_ctx();
+    if (!c) return fail(SKGPU_ERR_NOMEM, "out of host memory");
+    c->device = device_ordinal;
+    c->cfg = *cfg;
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device_ordinal));
+    c->sm_count = prop.multiProcessorCount;
+    CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CU(cudaEventCreate(&c->tm0));
+    CU(cudaEventCreate(&c->tm1));
+    const size_t S = cfg->max_streams;
+    SlotTables &st = c->st;
+    st.max_channels = cfg->max_channels;
+    st.fifo_frames = cfg->fifo_frames;
+    CU(dalloc(&st.last_index, S));
+    CU(dalloc(&st.t_ratio, S));
+    CU(dalloc(&st.end_idx, S));
+    CU(dalloc(&st.chunk, S));
+    CU(dalloc(&st.channels, S));
+    CU(dalloc(&st.hist, S * 16 * cfg->max_channels));
+    CU(dalloc(&st.runs, S * SK_RUNS_MAX));
+    CU(dalloc(&st.n_runs, S));
+    CU(dalloc(&st.n_out, S));
+    CU(cudaMemset(st.hist, 0, S * 16 * cfg->max_channels * sizeof(float)));
+    CU(cudaMemset(st.n_runs, 0, S * sizeof(uint32_t)));
+    CU(cudaMemset(st.n_out, 0, S * sizeof(uint32_t)));
+    if (cfg->fifo_frames) {
+        CU(dalloc(&st.fifo, S * cfg->fifo_frames * cfg->max_channels));
+        CU(dalloc(&st.fifo_w, S));
+        CU(dalloc(&st.fifo_r, S));
+        CU(cudaMemset(st.fifo_w, 0, S * sizeof(unsigned long long)));
+        CU(cudaMemset(st.fifo_r, 0, S * sizeof(unsigned long long)));
+    }
+    c->h_t.assign(S, 1.0);
+    c->h_end.assign(S, 0);
+    c->h_chunk.assign(S, 0);
+    c->h_ch.assign(S, 0);
+    c->used.assign(S, 0);
+    *out = c;
+    return SKGPU_OK;
+}
+
+extern "C" void skgpu_ctx_destroy(skgpu_ctx *c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    SlotTables &st = c->st;
+    cudaFree(st.last_index); cudaFree(st.t_ratio); cudaFree(st.end_idx); cudaFree(st.chunk); cudaFree(st.channels);
+    cudaFree(st.hist); cudaFree(st.runs); cudaFree(st.n_runs); cudaFree(st.n_out);
+    if (st.fifo) { cudaFree(st.fifo); cudaFree(st.fifo_w); cudaFree(st.fifo_r); }
+    if (c->d_reset) cudaFree(c->d_reset);
+    if (c->l2buf) cudaFree(c->l2buf);
+    cudaEventDestroy(c->tm0); cudaEventDestroy(c->tm1);
+    cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+extern "C" skgpu_rc skgpu_ctx_device_info(skgpu_ctx *c, char *name, size_t name_len, int32_t *sm_count, int32_t *cc_major, int32_t *cc_minor) {
+    if (!c) return fail(SKGPU_ERR_INVALID, "null context");
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, c->device));
+    if (name && name_len) snprintf(name, name_len, "%s", prop.name);
+    if (sm_count) *sm_count = prop.multiProcessorCount;
+    if (cc_major) *cc_major = prop.major;
+    if (cc_minor) *cc_minor = prop.minor;
+    return SKGPU_OK;
+}
+
+extern "C" skgpu_rc skgpu_pinned_alloc(skgpu_ctx *c, size_t bytes, void **out) {
+    if (!c || !out) return fail(SKGPU_ERR_INVALID, "null argument");
+    CU(cudaSetDevice(c->device));
+    CU(cudaHostAlloc(out, bytes ? bytes : 16, cudaHostAllocDefault));
+    return SKGPU_OK;
+}
+extern "C" skgpu_rc skgpu_pinned_free(skgpu_ctx *c, void *p) {
+    if (!c) return fail(SKGPU_ERR_INVALID, "null context");
+    if (p) CU(cudaFreeHost(p));
+    return SKGPU_OK;
+}
+
+// ------------------------------------------------------------------ stream slots
+
+static skgpu_rc validate_stream_cfg(const skgpu_ctx *c, const skgpu_stream_cfg *s) {
+    if (!s) return fail(SKGPU_ERR_INVALID, "null stream config");
+    if (s->out_rate == 0) return fail(SKGPU_ERR_INVALID, "target_sample_rate must be greater than 0");  // resampler.rs:82-86
+    if (s->in_rate == 0) return fail(SKGPU_ERR_INVALID, "input sample rate must be greater than 0");
+    if (s->chunk_frames == 0) return fail(SKGPU_ERR_INVALID, "chunk_frames must be greater than 0");     // resampler.rs:88-92
+    if (s->chunk_frames > (1u << 20)) return fail(SKGPU_ERR_INVALID, "chunk_frames too large");
+    if (s->channels == 0 || s->channels > c->cfg.max_channels)
+        return fail(SKGPU_ERR_INVALID, "channels %u outside 1..%u", (unsigned)s->channels, c->cfg.max_channels);
+    const double ratio = (double)s->out_rate / (double)s->in_rate;
+    if (!(ratio >= 1.0 / 256.0 && ratio <= 256.0)) return fail(SKGPU_ERR_INVALID, "resample ratio %g outside [1/256, 256]", ratio);
+    return SKGPU_OK;
+}
+
+static void slot_configure(skgpu_ctx *c, uint32_t slot, const skgpu_stream_cfg *s) {
+    const double ratio = (double)s->out_rate / (double)s->in_rate;  // resampler.rs:233 f64::from(out) / f64::from(in)
+    const double t = 1.0 / ratio;                                    // rubato: t_ratio = 1.0 / resample_ratio
+    c->h_t[slot] = t;
+    c->h_end[slot] = (int32_t)s->chunk_frames - 9 - (int32_t)std::ceil(t);  // chunk - (POLYNOMIAL_LEN + 1) - ceil(t)
+    c->h_chunk[slot] = s->chunk_frames;
+    c->h_ch[slot] = s->channels;
+    c->used[slot] = 1;
+    c->dirty_lo = std::min(c->dirty_lo, slot);
+    c->dirty_hi = std::max(c->dirty_hi, slot + 1);
+    c->reset_list.push_back(slot);
+}
+
+extern "C" uint32_t skgpu_stream_max_out_frames(const skgpu_stream_cfg *s) {
+    if (!s || !s->in_rate) return 0;
+    const double ratio = (double)s->out_rate / (double)s->in_rate;
+    return (uint32_t)((double)s->chunk_frames * ratio + 10.0) + 8u;
+}
+
+extern "C" skgpu_rc skgpu_stream_open_many(skgpu_ctx *c, const skgpu_stream_cfg *s, uint32_t n, uint32_t *slots_out) {
+    if (!c || !slots_out) return fail(SKGPU_ERR_INVALID, "null argument");
+    skgpu_rc rc = validate_stream_cfg(c, s);
+    if (rc) return rc;
+    const size_t avail = c->free_list.size() + (c->cfg.max_streams - c->next_fresh);
+    if (n > avail) return fail(SKGPU_ERR_NOMEM, "out of stream slots (%u requested, %zu free of %u)", n, avail, c->cfg.max_streams);
+    for (uint32_t i = 0; i < n; ++i) {
+        uint32_t slot;
+        if (c->next_fresh < c->cfg.max_streams) slot = c->next_fresh++;  // fresh slots first: contiguous ranges
+        else { slot = c->free_list.back(); c->free_list.pop_back(); }
+        slot_configure(c, slot, s);
+        slots_out[i] = slot;
+    }
+    return SKGPU_OK;
+}
+extern "C" skgpu_rc skgpu_stream_open(skgpu_ctx *c, const skgpu_stream_cfg *s, uint32_t *slot_out) {
+    return skgpu_stream_open_many(c, s, 1, slot_out);
+}
+extern "C" skgpu_rc skgpu_stream_reset(skgpu_ctx *c, uint32_t slot) {
+    if (!c || slot >= c->cfg.max_streams || !c->used[slot]) return fail(SKGPU_ERR_INVALID, "invalid slot %u", slot);
+    c->reset_list.push_back(slot);
+    return SKGPU_OK;
+}
+extern "C" skgpu_rc skgpu_stream_close(skgpu_ctx *c, uint32_t slot) {
+    if (!c || slot >= c->cfg.max_streams || !c->used[slot]) return fail(SKGPU_ERR_INVALID, "invalid slot %u", slot);
+    c->used[slot] = 0;
+    c->free_list.push_back(slot);
+    return SKGPU_OK;
+}
+extern "C" skgpu_rc skgpu_stream_get_state(skgpu_ctx *c, uint32_t slot, double *last_index, float *hist, uint64_t *fifo_written, uint64_t *fifo_read) {
+    if (!c || slot >= c->cfg.max_streams || !c->used[slot]) return fail(SKGPU_ERR_INVALID, "invalid slot %u", slot);
+    CU(cudaSetDevice(c->device));
+    skgpu_rc rc = ctx_flush(c);
+    if (rc) return rc;
+    CU(cudaStreamSynchronize(c->stream));
+    if (last_index) CU(cudaMemcpy(last_index, c->st.last_index + slot, sizeof(double), cudaMemcpyDeviceToHost));
+    if (hist) CU(cudaMemcpy(hist, c->st.hist + (size_t)slot * 16 * c->cfg.max_channels, 16 * c->h_ch[slot] * sizeof(float), cudaMemcpyDeviceToHost));
+    if (fifo_written) { *fifo_written = 0; if (c->st.fifo_w) CU(cudaMemcpy(fifo_written, c->st.fifo_w + slot, 8, cudaMemcpyDeviceToHost)); }
+    if (fifo_read) { *fifo_read = 0; if (c->st.fifo_r) CU(cudaMemcpy(fifo_read, c->st.fifo_r + slot, 8, cudaMemcpyDeviceToHost)); }
+    return SKGPU_OK;
+}
+
+// ------------------------------------------------------------------ plan
+
+enum OpKind { OP_CONVERT = 0, OP_RESAMPLE = 1, OP_MIX = 2 };
+
+struct DynTable {  // small per-tick table with a ring of pinned staging buffers
+    void *dev = nullptr;
+    void *host[DYN_RING] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t done[DYN_RING] = {nullptr, nullptr, nullptr, nullptr};
+    bool used[DYN_RING] = {false, false, false, false};
+    size_t bytes = 0;
+    int cur = 0;
+    bool dirty = false;
+    bool valid = false;
+};
+
+struct Op {
+    OpKind kind;
+    int mode = 0;
+    uint32_t cap = 0, cap2 = 0;   // table capacities
+    uint32_t n = 0, n2 = 0;       // live entries
+    void *d_tab = nullptr, *d_tab2 = nullptr;
+    void *h_tab = nullptr, *h_tab2 = nullptr;  // pinned staging
+    OpHeader *d_hdr = nullptr;
+    OpHeader *h_hdr = nullptr;                 // pinned
+    bool dirty = true;
+    uint32_t tiles = 1;           // convert: tiles per segment; mix: tiles per group
+    uint32_t max_unit = 0;        // convert: max n_samples; mix: max out samples; resample: max chunk frames
+    uint32_t smem_frames = 0;     // resample: frames (history + chunk) the staged path can hold
+    uint32_t smem_bytes = 0;
+    int rs_channels = 0;          // resample: 1 / 2 specialisation, 0 = generic
+    uint64_t results_off = 0;
+    bool has_fifo_inputs = false;
+    DynTable present;             // mix: per-input presence
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev[2];
+    uint32_t ev_used[2] = {0, 0};
+};
+
+struct skgpu_plan {
+    skgpu_ctx *ctx = nullptr;
+    uint8_t *arena = nullptr;
+    size_t arena_bytes = 0;
+    std::vector<Op> ops;
+    DynTable gains;
+    uint32_t n_gains = 0;
+    uint64_t h2d_off = 0, h2d_bytes = 0, d2h_off = 0, d2h_bytes = 0;
+    bool finalized = false;
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t graph_exec = nullptr;
+    cudaEvent_t e0 = nullptr, e1 = nullptr, e2 = nullptr, e3 = nullptr;
+    bool timing_valid = false;
+};
+
+static skgpu_rc dyn_alloc(DynTable &t, size_t bytes) {
+    t.bytes = bytes;
+    CU(cudaMalloc(&t.dev, bytes ? bytes : 16));
+    for (int i = 0; i < DYN_RING; ++i) {
+        CU(cudaHostAlloc(&t.host[i], bytes ? bytes : 16, cudaHostAllocDefault));
+        CU(cudaEventCreateWithFlags(&t.done[i], cudaEventDisableTiming));
+    }
+    t.valid = true;
+    return SKGPU_OK;
+}
+static void dyn_free(DynTable &t) {
+    if (!t.valid) return;
+    cudaFree(t.dev);
+    for (int i = 0; i < DYN_RING; ++i) { cudaFreeHost(t.host[i]); cudaEventDestroy(t.done[i]); }
+    t.valid = false;
+}
+// host writes the next staging buffer (waiting for its previous upload if still in flight)
+static skgpu_rc dyn_write(DynTable &t, const void *src, size_t bytes) {
+    const int nxt = (t.cur + 1) % DYN_RING;
+    if (t.used[nxt]) CU(cudaEventSynchronize(t.done[nxt]));
+    memcpy(t.host[nxt], src, bytes);
+    t.cur = nxt;
+    t.dirty = true;
+    return SKGPU_OK;
+}
+static skgpu_rc dyn_upload(DynTable &t, cudaStream_t s) {
+    if (!t.valid || !t.dirty) return SKGPU_OK;
+    CU(cudaMemcpyAsync(t.dev, t.host[t.cur], t.bytes, cudaMemcpyHostToDevice, s));
+    CU(cudaEventRecord(t.done[t.cur], s));
+    t.used[t.cur] = true;
+    t.dirty = false;
+    return SKGPU_OK;
+}
+
+extern "C" skgpu_rc skgpu_plan_create(skgpu_ctx *c, size_t arena_bytes, skgpu_plan **out) {
+    if (!c || !out) return fail(SKGPU_ERR_INVALID, "null argument");
+    if (arena_bytes == 0) return fail(SKGPU_ERR_INVALID, "arena_bytes must be > 0");
+    CU(cudaSetDevice(c->device));
+    skgpu_plan *p = new (std::nothrow) skgpu_plan();
+    if (!p) return fail(SKGPU_ERR_NOMEM, "out of host memory");
+    p->ctx = c;
+    p->arena_bytes = arena_bytes;
+    cudaError_t e = cudaMalloc((void **)&p->arena, arena_bytes);
+    if (e != cudaSuccess) { delete p; return fail(SKGPU_ERR_NOMEM, "cudaMalloc(%zu) for the tick arena failed: %s", arena_bytes, cudaGetErrorString(e)); }
+    CU(cudaEventCreate(&p->e0)); CU(cudaEventCreate(&p->e1)); CU(cudaEventCreate(&p->e2)); CU(cudaEventCreate(&p->e3));
+    *out = p;
+    return SKGPU_OK;
+}
+
+static void op_free(Op &op) {
+    cudaFree(op.d_tab); cudaFree(op.d_tab2); cudaFree(op.d_hdr);
+    if (op.h_tab) cudaFreeHost(op.h_tab);
+    if (op.h_tab2) cudaFreeHost(op.h_tab2);
+    if (op.h_hdr) cudaFreeHost(op.h_hdr);
+    dyn_free(op.present);
+    for (int s = 0; s < 2; ++s)
+        for (auto &pr : op.ev[s]) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
+}
+
+extern "C" void skgpu_plan_destroy(skgpu_plan *p) {
+    if (!p) return;
+    cudaSetDevice(p->ctx->device);
+    cudaStreamSynchronize(p->ctx->stream);
+    for (auto &op : p->ops) op_free(op);
+    dyn_free(p->gains);
+    if (p->graph_exec) cudaGraphExecDestroy(p->graph_exec);
+    if (p->graph) cudaGraphDestroy(p->graph);
+    cudaFree(p->arena);
+    cudaEventDestroy(p->e0); cudaEventDestroy(p->e1); cudaEventDestroy(p->e2); cudaEventDestroy(p->e3);
+    delete p;
+}
+
+static skgpu_rc check_range(const skgpu_plan *p, uint64_t off, uint64_t bytes, const char *what) {
+    if (off > p->arena_bytes || bytes > p->arena_bytes - off)
+        return fail(SKGPU_ERR_INVALID, "%s: range [%llu, +%llu) outside the %zu-byte arena", what, (unsigned long long)off, (unsigned long long)bytes, p->arena_bytes);
+    return SKGPU_OK;
+}
+
+static skgpu_rc op_alloc_tables(Op &op, size_t entry, uint32_t cap, size_t entry2, uint32_t cap2) {
+    op.cap = cap;
+    op.cap2 = cap2;
+    CU(cudaMalloc(&op.d_tab, std::max<size_t>(entry * cap, 16)));
+    CU(cudaHostAlloc(&op.h_tab, std::max<size_t>(entry * cap, 16), cudaHostAllocDefault));
+    if (entry2) {
+        CU(cudaMalloc(&op.d_tab2, std::max<size_t>(entry2 * cap2, 16)));
+        CU(cudaHostAlloc(&op.h_tab2, std::max<size_t>(entry2 * cap2, 16), cudaHostAllocDefault));
+    }
+    CU(cudaMalloc((void **)&op.d_hdr, sizeof(OpHeader)));
+    CU(cudaHostAlloc((void **)&op.h_hdr, sizeof(OpHeader), cudaHostAllocDefault));
+    memset(op.h_hdr, 0, sizeof(OpHeader));
+    return SKGPU_OK;
+}
+
+// ---- convert
+
+static skgpu_rc validate_segs(const skgpu_plan *p, int mode, const skgpu_seg *segs, uint32_t n, uint32_t *max_n) {
+    const uint32_t in_b = mode == SKGPU_CVT_S16_TO_F32 ? 2 : 4, out_b = mode == SKGPU_CVT_F32_TO_S16 ? 2 : 4;
+    uint32_t mx = 0;
+    for (uint32_t i = 0; i < n; ++i) {
+        skgpu_rc rc = check_range(p, segs[i].in_off, (uint64_t)segs[i].n_samples * in_b, "convert input");
+        if (rc) return rc;
+        rc = check_range(p, segs[i].out_off, (uint64_t)segs[i].n_samples * out_b, "convert output");
+        if (rc) return rc;
+        if ((segs[i].in_off % in_b) || (segs[i].out_off % out_b)) return fail(SKGPU_ERR_INVALID, "convert segment %u: misaligned offset", i);
+        if (segs[i].gain_idx != SKGPU_NO_GAIN && segs[i].gain_idx >= p->n_gains)
+            return fail(SKGPU_ERR_INVALID, "convert segment %u: gain_idx %u >= gain table size %u (call skgpu_plan_set_gains first)", i, segs[i].gain_idx, p->n_gains);
+        mx = std::max(mx, segs[i].n_samples);
+    }
+    *max_n = mx;
+    return SKGPU_OK;
+}
+
+extern "C" skgpu_rc skgpu_plan_add_convert(skgpu_plan *p, skgpu_cvt_mode mode, const skgpu_seg *segs, uint32_t n, uint32_t *op_out) {
+    if (!p || (!segs && n)) return fail(SKGPU_ERR_INVALID, "null argument");
+    if (p->finalized) return fail(SKGPU_ERR_STATE, "plan already finalized");
+    if ((int)mode < 0 || (int)mode > 2) return fail(SKGPU_ERR_INVALID, "unknown convert mode %d", (int)mode);
+    CU(cudaSetDevice(p->ctx->device));
+    uint32_t mx = 0;
+    skgpu_rc rc = validate_segs(p, mode, segs, n, &mx);
+    if (rc) return rc;
+    Op op;
+    op.kind = OP_CONVERT;
+    op.mode = mode;
+    rc = op_alloc_tables(op, sizeof(skgpu_seg), std::max(n, 1u), 0, 0);
+    if (rc) return rc;
+    if (n) memcpy(op.h_tab, segs, n * sizeof(skgpu_seg));
+    op.n = n;
+    op.max_unit = std::max(mx, 1u);
+    op.tiles = (op.max_unit + CVT_TILE - 1) / CVT_TILE;
+    if (op_out) *op_out = (uint32_t)p->ops.size();
+    p->ops.push_back(op);
+    return SKGPU_OK;
+}
+
+extern "C" skgpu_rc skgpu_plan_update_convert(skgpu_plan *p, uint32_t opi, const skgpu_seg *segs, uint32_t n) {
+    if (!p || opi >= p->ops.size() || p->ops[opi].kind != OP_CONVERT) return fail(SKGPU_ERR_INVALID, "not a convert op");
+    Op &op = p->ops[opi];
+    if (n > op.cap) return fail(SKGPU_ERR_INVALID, "update exceeds capacity (%u > %u)", n, op.cap);
+    uint32_t mx = 0;
+    skgpu_rc rc = validate_segs(p, op.mode, segs, n, &mx);
+    if (rc) return rc;
+    if (mx > op.tiles * (uint32_t)CVT_TILE) return fail(SKGPU_ERR_INVALID, "segment longer (%u) than the op was sized for (%u)", mx, op.tiles * CVT_TILE);
+    CU(cudaStreamSynchronize(p->ctx->stream));
+    if (n) memcpy(op.h_tab, segs, n * sizeof(skgpu_seg));
+    op.n = n;
+    op.dirty = true;
+    return SKGPU_OK;
+}
+
+// ---- resample
+
+static skgpu_rc validate_rs(const skgpu_plan *p, const skgpu_rs_item *items, uint32_t n, uint32_t *max_chunk, int *chan, bool *any_fifo) {
+    const skgpu_ctx *c = p->ctx;
+    uint32_t mx = 0;
+    int ch = -1;
+    bool fifo = false;
+    for (uint32_t i = 0; i < n; ++i) {
+        const uint32_t slot = items[i].slot;
+        if (slot >= c->cfg.max_streams || !c->used[slot]) return fail(SKGPU_ERR_INVALID, "resample item %u: slot %u is not open", i, slot);
+        const uint32_t N = c->h_chunk[slot], C = c->h_ch[slot];
+        skgpu_rc rc = check_range(p, items[i].in_off, (uint64_t)N * C * 4, "resample input");
+        if (rc) return rc;
+        if (items[i].in_off % 4) return fail(SKGPU_ERR_INVALID, "resample item %u: misaligned input", i);
+        if (items[i].flags & SKGPU_RS_TO_FIFO) {
+            if (!c->cfg.fifo_frames) return fail(SKGPU_ERR_INVALID, "resample item %u: context has no device FIFO (fifo_frames = 0)", i);
+            fifo = true;
+        } else {
+            rc = check_range(p, items[i].out_off, (uint64_t)items[i].out_cap_frames * C * 4, "resample output");
+            if (rc) return rc;
+            if (items[i].out_off % (C == 2 ? 8 : 4)) return fail(SKGPU_ERR_INVALID, "resample item %u: misaligned output", i);
+        }
+        mx = std::max(mx, N);
+        if (ch == -1) ch = (int)C;
+        else if (ch != (int)C) ch = 0;
+    }
+    *max_chunk = mx;
+    *chan = (ch == 1 || ch == 2) ? ch : 0;
+    *any_fifo = fifo;
+    return SKGPU_OK;
+}
+
+static void rs_size_smem(const skgpu_ctx *c, Op &op) {
+    // staged path: (16 + chunk) frames x channels x 4 B of dynamic shared memory, capped at 96 KB so that
+    // at least two CTAs stay resident per SM; longer chunks take the direct-from-HBM path.
+    const uint32_t chmax = op.rs_channels ? (uint32_t)op.rs_channels : c->cfg.max_channels;
+    uint64_t need = (uint64_t)(op.max_unit + 16u) * chmax * 4u;
+    if (need <= 96u * 1024u) { op.smem_frames = op.max_unit + 16u; op.smem_bytes = (uint32_t)((need + 15u) & ~15ull); }
+    else { op.smem_frames = 0; op.smem_bytes = 0; }
+}
+
+extern "C" skgpu_rc skgpu_plan_add_resample(skgpu_plan *p, const skgpu_rs_item *items, uint32_t n, uint64_t results_off, uint32_t *op_out) {
+    if (!p || (!items && n)) return fail(SKGPU_ERR_INVALID, "null argument");
+    if (p->finalized) return fail(SKGPU_ERR_STATE, "plan already finalized");
+    CU(cudaSetDevice(p->ctx->device));
+    uint32_t mx = 0;
+    int ch = 0;
+    bool fifo = false;
+    skgpu_rc rc = validate_rs(p, items, n, &mx, &ch, &fifo);
+    if (rc) return rc;
+    rc = check_range(p, results_off, (uint64_t)std::max(n, 1u) * sizeof(skgpu_rs_result), "resample results");
+    if (rc) return rc;
+    if (results_off % 8) return fail(SKGPU_ERR_INVALID, "results_off must be 8-byte aligned");
+    Op op;
+    op.kind = OP_RESAMPLE;
+    rc = op_alloc_tables(op, sizeof(skgpu_rs_item), std::max(n, 1u), 0, 0);
+    if (rc) return rc;
+    if (n) memcpy(op.h_tab, items, n * sizeof(skgpu_rs_item));
+    op.n = n;
+    op.max_unit = std::max(mx, 1u);
+    op.rs_channels = ch;
+    op.results_off = results_off;
+    rs_size_smem(p->ctx, op);
+    if (op_out) *op_out = (uint32_t)p->ops.size();
+    p->ops.push_back(op);
+    return SKGPU_OK;
+}
+
+extern "C" skgpu_rc skgpu_plan_update_resample(skgpu_plan *p, uint32_t opi, const skgpu_rs_item *items, uint32_t n) {
+    if (!p || opi >= p->ops.size() || p->ops[opi].kind != OP_RESAMPLE) return fail(SKGPU_ERR_INVALID, "not a resample op");
+    Op &op = p->ops[opi];
+    if (n > op.cap) return fail(SKGPU_ERR_INVALID, "update exceeds capacity (%u > %u)", n, op.cap);
+    uint32_t mx = 0;
+    int ch = 0;
+    bool fifo = false;
+    skgpu_rc rc = validate_rs(p, items, n, &mx, &ch, &fifo);
+    if (rc) return rc;
+    if (n && ch != op.rs_channels && op.rs_channels != 0) return fail(SKGPU_ERR_INVALID, "update changes the op's channel specialisation (%d -> %d)", op.rs_channels, ch);
+    if (op.smem_frames && mx + 16u > op.smem_frames) return fail(SKGPU_ERR_INVALID, "update has a longer chunk (%u) than the op was sized for (%u)", mx, op.smem_frames - 16u);
+    CU(cudaStreamSynchronize(p->ctx->stream));
+    if (n) memcpy(op.h_tab, items, n * sizeof(skgpu_rs_item));
+    op.n = n;
+    op.dirty = true;
+    return SKGPU_OK;
+}
+
+// ---- mix
+
+static skgpu_rc validate_mix(const skgpu_plan *p, const skgpu_mix_group *g, uint32_t ng, const skgpu_mix_input *in, uint32_t ni, uint32_t *max_out, bool *any_fifo) {
+    const skgpu_ctx *c = p->ctx;
+    uint32_t mx = 0;
+    bool fifo = false;
+    for (uint32_t i = 0; i < ni; ++i) {
+        if (in[i].channels == 0) return fail(SKGPU_ERR_INVALID, "mix input %u: channels must be >= 1", i);
+        if (in[i].gain_idx != SKGPU_NO_GAIN && in[i].gain_idx >= p->n_gains) return fail(SKGPU_ERR_INVALID, "mix input %u: gain_idx out of range", i);
+        if (in[i].flags & SKGPU_MIX_IN_FIFO) {
+            if (!c->cfg.fifo_frames) return fail(SKGPU_ERR_INVALID, "mix input %u: context has no device FIFO", i);
+            if (in[i].slot >= c->cfg.max_streams || !c->used[in[i].slot]) return fail(SKGPU_ERR_INVALID, "mix input %u: slot %u is not open", i, in[i].slot);
+            if (in[i].channels != c->h_ch[in[i].slot]) return fail(SKGPU_ERR_INVALID, "mix input %u: channel count differs from its stream slot", i);
+            if (in[i].n_frames > c->cfg.fifo_frames) return fail(SKGPU_ERR_INVALID, "mix input %u: packet larger than the device FIFO", i);
+            fifo = true;
+        } else {
+            skgpu_rc rc = check_range(p, in[i].in_off, (uint64_t)in[i].n_frames * in[i].channels * 4, "mix input");
+            if (rc) return rc;
+            if (in[i].in_off % 4) return fail(SKGPU_ERR_INVALID, "mix input %u: misaligned offset", i);
+        }
+    }
+    for (uint32_t i = 0; i < ng; ++i) {
+        if (g[i].out_channels == 0) return fail(SKGPU_ERR_INVALID, "mix group %u: out_channels must be >= 1", i);
+        if ((uint64_t)g[i].first_input + g[i].n_inputs > ni) return fail(SKGPU_ERR_INVALID, "mix group %u: inputs [%u, +%u) outside the input table (%u)", i, g[i].first_input, g[i].n_inputs, ni);
+        if (g[i].n_inputs > (uint32_t)MIX_MAX_INPUTS) return fail(SKGPU_ERR_INVALID, "mix group %u: more than %d inputs", i, MIX_MAX_INPUTS);
+        if (g[i].gain_idx != SKGPU_NO_GAIN && g[i].gain_idx >= p->n_gains) return fail(SKGPU_ERR_INVALID, "mix group %u: gain_idx out of range", i);
+        const uint64_t osz = (uint64_t)g[i].out_frames * g[i].out_channels;
+        const uint32_t ob = (g[i].flags & SKGPU_MIX_OUT_S16) ? 2 : 4;
+        skgpu_rc rc = check_range(p, g[i].out_off, osz * ob, "mix output");
+        if (rc) return rc;
+        if (g[i].out_off % ob) return fail(SKGPU_ERR_INVALID, "mix group %u: misaligned output", i);
+        if (osz > 0xFFFFFFFFull) return fail(SKGPU_ERR_INVALID, "mix group %u: output too large", i);
+        mx = std::max<uint32_t>(mx, (uint32_t)osz);
+    }
+    *max_out = mx;
+    *any_fifo = fifo;
+    return SKGPU_OK;
+}
+
+extern "C" skgpu_rc skgpu_plan_add_mix(skgpu_plan *p, const skgpu_mix_group *groups, uint32_t ng, const skgpu_mix_input *inputs, uint32_t ni, uint32_t *op_out) {
+    if (!p || (!groups && ng) || (!inputs && ni)) return fail(SKGPU_ERR_INVALID, "null argument");
+    if (p->finalized) return fail(SKGPU_ERR_STATE, "plan already finalized");
+    CU(cudaSetDevice(p->ctx->device));
+    uint32_t mx = 0;
+    bool fifo = false;
+    skgpu_rc rc = validate_mix(p, groups, ng, inputs, ni, &mx, &fifo);
+    if (rc) return rc;
+    Op op;
+    op.kind = OP_MIX;
+    rc = op_alloc_tables(op, sizeof(skgpu_mix_group), std::max(ng, 1u), sizeof(skgpu_mix_input), std::max(ni, 1u));
+    if (rc) return rc;
+    if (ng) memcpy(op.h_tab, groups, ng * sizeof(skgpu_mix_group));
+    if (ni) memcpy(op.h_tab2, inputs, ni * sizeof(skgpu_mix_input));
+    op.n = ng;
+    op.n2 = ni;
+    op.max_unit = std::max(mx, 1u);
+    op.tiles = (op.max_unit + MIX_TILE - 1) / MIX_TILE;
+    op.has_fifo_inputs = fifo;
+    if (op_out) *op_out = (uint32_t)p->ops.size();
+    p->ops.push_back(op);
+    return SKGPU_OK;
+}
+
+extern "C" skgpu_rc skgpu_plan_update_mix(skgpu_plan *p, uint32_t opi, const skgpu_mix_group *groups, uint32_t ng, const skgpu_mix_input *inputs, uint32_t ni) {
+    if (!p || opi >= p->ops.size() || p->ops[opi].kind != OP_MIX) return fail(SKGPU_ERR_INVALID, "not a mix op");
+    Op &op = p->ops[opi];
+    if (ng > op.cap || ni > op.cap2) return fail(SKGPU_ERR_INVALID, "update exceeds capacity");
+    uint32_t mx = 0;
+    bool fifo = false;
+    skgpu_rc rc = validate_mix(p, groups, ng, inputs, ni, &mx, &fifo);
+    if (rc) return rc;
+    if (mx > op.tiles * (uint32_t)MIX_TILE) return fail(SKGPU_ERR_INVALID, "group output larger (%u) than the op was sized for (%u)", mx, op.tiles * MIX_TILE);
+    if (fifo && !op.has_fifo_inputs && p->finalized) return fail(SKGPU_ERR_INVALID, "update introduces FIFO inputs into an op finalized without them");
+    CU(cudaStreamSynchronize(p->ctx->stream));
+    if (ng) memcpy(op.h_tab, groups, ng * sizeof(skgpu_mix_group));
+    if (ni) memcpy(op.h_tab2, inputs, ni * sizeof(skgpu_mix_input));
+    op.n = ng;
+    op.n2 = ni;
+    op.has_fifo_inputs = op.has_fifo_inputs || fifo;
+    op.dirty = true;
+    return SKGPU_OK;
+}
+
+// ---- io / dynamic tables
+
+extern "C" skgpu_rc skgpu_plan_set_io(skgpu_plan *p, uint64_t h2d_off, uint64_t h2d_bytes, uint64_t d2h_off, uint64_t d2h_bytes) {
+    if (!p) return fail(SKGPU_ERR_INVALID, "null plan");
+    skgpu_rc rc = check_range(p, h2d_off, h2d_bytes, "h2d range");
+    if (rc) return rc;
+    rc = check_range(p, d2h_off, d2h_bytes, "d2h range");
+    if (rc) return rc;
+    p->h2d_off = h2d_off; p->h2d_bytes = h2d_bytes; p->d2h_off = d2h_off; p->d2h_bytes = d2h_bytes;
+    return SKGPU_OK;
+}
+
+extern "C" skgpu_rc skgpu_plan_set_gains(skgpu_plan *p, const float *gains, uint32_t n) {
+    if (!p || (!gains && n)) return fail(SKGPU_ERR_INVALID, "null argument");
+    CU(cudaSetDevice(p->ctx->device));
+    if (!p->gains.valid) {
+        if (p->finalized) return fail(SKGPU_ERR_STATE, "gain table must be created before finalize");
+        skgpu_rc rc = dyn_alloc(p->gains, std::max<size_t>(n, 1) * sizeof(float));
+        if (rc) return rc;
+        p->n_gains = n;
+    } else if (n != p->n_gains) {
+        return fail(SKGPU_ERR_INVALID, "gain table size is fixed at %u (got %u)", p->n_gains, n);
+    }
+    return dyn_write(p->gains, gains, n * sizeof(float));
+}
+
+extern "C" skgpu_rc skgpu_plan_set_present(skgpu_plan *p, uint32_t opi, const uint8_t *present, uint32_t n) {
+    if (!p || opi >= p->ops.size() || p->ops[opi].kind != OP_MIX) return fail(SKGPU_ERR_INVALID, "not a mix op");
+    Op &op = p->ops[opi];
+    CU(cudaSetDevice(p->ctx->device));
+    if (n > op.cap2) return fail(SKGPU_ERR_INVALID, "presence table larger than the input table capacity");
+    if (!op.present.valid) {
+        if (p->finalized) return fail(SKGPU_ERR_STATE, "presence table must be created before finalize");
+        skgpu_rc rc = dyn_alloc(op.present, op.cap2);
+        if (rc) return rc;
+    }
+    std::vector<uint8_t> full(op.cap2, 1);
+    if (n) memcpy(full.data(), present, n);
+    return dyn_write(op.present, full.data(), op.cap2);
+}
+
+// ---- launch
+
+static skgpu_rc upload_dirty(skgpu_plan *p) {
+    cudaStream_t s = p->ctx->stream;
+    for (auto &op : p->ops) {
+        if (op.dirty) {
+            const size_t esz = op.kind == OP_CONVERT ? sizeof(skgpu_seg) : op.kind == OP_RESAMPLE ? sizeof(skgpu_rs_item) : sizeof(skgpu_mix_group);
+            if (op.n) CU(cudaMemcpyAsync(op.d_tab, op.h_tab, esz * op.n, cudaMemcpyHostToDevice, s));
+            if (op.kind == OP_MIX && op.n2) CU(cudaMemcpyAsync(op.d_tab2, op.h_tab2, sizeof(skgpu_mix_input) * op.n2, cudaMemcpyHostToDevice, s));
+            op.h_hdr->count = op.n;
+            op.h_hdr->count2 = op.n2;
+            CU(cudaMemcpyAsync(op.d_hdr, op.h_hdr, sizeof(OpHeader), cudaMemcpyHostToDevice, s));
+            op.dirty = false;
+        }
+        if (op.kind == OP_MIX) { skgpu_rc rc = dyn_upload(op.present, s); if (rc) return rc; }
+    }
+    return dyn_upload(p->gains, s);
+}
+
+static skgpu_rc op_event(Op &op, int sub, bool second, cudaStream_t s) {
+    if (!second) {
+        if (op.ev_used[sub] >= op.ev[sub].size()) {
+            if (op.ev[sub].size() >= 8192) return SKGPU_OK;  // stop sampling, keep running
+            cudaEvent_t a, b;
+            CU(cudaEventCreate(&a));
+            CU(cudaEventCreate(&b));
+            op.ev[sub].push_back({a, b});
+        }
+        CU(cudaEventRecord(op.ev[sub][op.ev_used[sub]].first, s));
+    } else {
+        if (op.ev_used[sub] >= op.ev[sub].size()) return SKGPU_OK;
+        CU(cudaEventRecord(op.ev[sub][op.ev_used[sub]].second, s));
+        op.ev_used[sub]++;
+    }
+    return SKGPU_OK;
+}
+
+static skgpu_rc launch_ops(skgpu_plan *p, bool time_ops) {
+    skgpu_ctx *c = p->ctx;
+    cudaStream_t s = c->stream;
+    const float *gains = (const float *)p->gains.dev;
+    for (auto &op : p->ops) {
+        if (op.kind == OP_CONVERT) {
+            const uint32_t grid = op.cap * op.tiles;
+            if (time_ops) { skgpu_rc rc = op_event(op, 0, false, s); if (rc) return rc; }
+            switch (op.mode) {
+                case SKGPU_CVT_F32_TO_F32: k_convert<SKGPU_CVT_F32_TO_F32><<<grid, CVT_THREADS, 0, s>>>(op.d_hdr, (const skgpu_seg *)op.d_tab, gains, p->arena, op.tiles); break;
+                case SKGPU_CVT_F32_TO_S16: k_convert<SKGPU_CVT_F32_TO_S16><<<grid, CVT_THREADS, 0, s>>>(op.d_hdr, (const skgpu_seg *)op.d_tab, gains, p->arena, op.tiles); break;
+                default: k_convert<SKGPU_CVT_S16_TO_F32><<<grid, CVT_THREADS, 0, s>>>(op.d_hdr, (const skgpu_seg *)op.d_tab, gains, p->arena, op.tiles); break;
+            }
+            CU(cudaGetLastError());
+            if (time_ops) { skgpu_rc rc = op_event(op, 0, true, s); if (rc) return rc; }
+        } else if (op.kind == OP_RESAMPLE) {
+            const skgpu_rs_item *items = (const skgpu_rs_item *)op.d_tab;
+            if (time_ops) { skgpu_rc rc = op_event(op, 0, false, s); if (rc) return rc; }
+            k_phase<<<(op.cap + PHASE_THREADS - 1) / PHASE_THREADS, PHASE_THREADS, 0, s>>>(op.d_hdr, items, c->st, p->arena, op.results_off);
+            CU(cudaGetLastError());
+            if (time_ops) { skgpu_rc rc = op_event(op, 0, true, s); if (rc) return rc; rc = op_event(op, 1, false, s); if (rc) return rc; }
+            if (op.rs_channels == 2) k_resample<2><<<op.cap, RS_THREADS, op.smem_bytes, s>>>(op.d_hdr, items, c->st, p->arena, op.smem_frames);
+            else if (op.rs_channels == 1) k_resample<1><<<op.cap, RS_THREADS, op.smem_bytes, s>>>(op.d_hdr, items, c->st, p->arena, op.smem_frames);
+            else k_resample<0><<<op.cap, RS_THREADS, op.smem_bytes, s>>>(op.d_hdr, items, c->st, p->arena, op.smem_frames);
+            CU(cudaGetLastError());
+            if (time_ops) { skgpu_rc rc = op_event(op, 1, true, s); if (rc) return rc; }
+        } else {
+            const uint8_t *present = op.present.valid ? (const uint8_t *)op.present.dev : nullptr;
+            if (time_ops) { skgpu_rc rc = op_event(op, 0, false, s); if (rc) return rc; }
+            k_mix<<<op.cap * op.tiles, MIX_THREADS, 0, s>>>(op.d_hdr, (const skgpu_mix_group *)op.d_tab, (const skgpu_mix_input *)op.d_tab2, present, gains, c->st, p->arena, op.tiles);
+            CU(cudaGetLastError());
+            if (op.has_fifo_inputs) {
+                k_fifo_commit<<<(op.cap2 + 127) / 128, 128, 0, s>>>(op.d_hdr, (const skgpu_mix_input *)op.d_tab2, present, c->st);
+                CU(cudaGetLastError());
+            }
+            if (time_ops) { skgpu_rc rc = op_event(op, 0, true, s); if (rc) return rc; }
+        }
+    }
+    return SKGPU_OK;
+}
+
+extern "C" uint32_t skgpu_plan_launches_per_tick(const skgpu_plan *p) {
+    if (!p) return 0;
+    uint32_t n = 0;
+    for (auto &op : p->ops) n += op.kind == OP_RESAMPLE ? 2 : (op.kind == OP_MIX && op.has_fifo_inputs) ? 2 : 1;
+    return n;
+}
+
+extern "C" skgpu_rc skgpu_plan_finalize(skgpu_plan *p) {
+    if (!p) return fail(SKGPU_ERR_INVALID, "null plan");
+    if (p->finalized) return fail(SKGPU_ERR_STATE, "plan already finalized");
+    skgpu_ctx *c = p->ctx;
+    CU(cudaSetDevice(c->device));
+    if (!p->gains.valid) {  // an empty gain table keeps kernel arguments valid
+        float one = 1.0f;
+        skgpu_rc rc = skgpu_plan_set_gains(p, &one, 1);
+        if (rc) return rc;
+    }
+    for (auto &op : p->ops) {
+        if (op.kind == OP_RESAMPLE && op.smem_bytes > 48u * 1024u) {
+            if (op.rs_channels == 2) CU(cudaFuncSetAttribute(k_resample<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)op.smem_bytes));
+            else if (op.rs_channels == 1) CU(cudaFuncSetAttribute(k_resample<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)op.smem_bytes));
+            else CU(cudaFuncSetAttribute(k_resample<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)op.smem_bytes));
+        }
+    }
+    skgpu_rc rc = ctx_flush(c);
+    if (rc) return rc;
+    rc = upload_dirty(p);
+    if (rc) return rc;
+    CU(cudaStreamSynchronize(c->stream));
+    // capture the kernel sequence once: a tick becomes a single graph launch (hides per-kernel launch cost)
+    CU(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+    rc = launch_ops(p, false);
+    cudaError_t e = cudaStreamEndCapture(c->stream, &p->graph);
+    if (rc) return rc;
+    if (e != cudaSuccess) return fail(SKGPU_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(e));
+    if (!p->ops.empty()) CU(cudaGraphInstantiate(&p->graph_exec, p->graph, 0));
+    p->finalized = true;
+    return SKGPU_OK;
+}
+
+extern "C" skgpu_rc skgpu_tick_submit(skgpu_plan *p, const void *host_in, void *host_out, uint32_t flags) {
+    if (!p) return fail(SKGPU_ERR_INVALID, "null plan");
+    if (!p->finalized) return fail(SKGPU_ERR_STATE, "plan not finalized");
+    skgpu_ctx *c = p->ctx;
+    cudaStream_t s = c->stream;
+    CU(cudaSetDevice(c->device));
+    const bool do_h2d = !(flags & SKGPU_SUBMIT_NO_H2D) && p->h2d_bytes;
+    const bool do_d2h = !(flags & SKGPU_SUBMIT_NO_D2H) && p->d2h_bytes;
+    if (do_h2d && !host_in) return fail(SKGPU_ERR_INVALID, "host_in is null");
+    if (do_d2h && !host_out) return fail(SKGPU_ERR_INVALID, "host_out is null");
+    skgpu_rc rc = ctx_flush(c);
+    if (rc) return rc;
+    rc = upload_dirty(p);
+    if (rc) return rc;
+    CU(cudaEventRecord(p->e0, s));
+    if (do_h2d) CU(cudaMemcpyAsync(p->arena + p->h2d_off, host_in, p->h2d_bytes, cudaMemcpyHostToDevice, s));
+    CU(cudaEventRecord(p->e1, s));
+    if ((flags & SKGPU_SUBMIT_GRAPH) && p->graph_exec) {
+        CU(cudaGraphLaunch(p->graph_exec, s));
+    } else {
+        rc = launch_ops(p, (flags & SKGPU_SUBMIT_TIME_OPS) != 0);
+        if (rc) return rc;
+    }
+    CU(cudaEventRecord(p->e2, s));
+    if (do_d2h) CU(cudaMemcpyAsync(host_out, p->arena + p->d2h_off, p->d2h_bytes, cudaMemcpyDeviceToHost, s));
+    CU(cudaEventRecord(p->e3, s));
+    p->timing_valid = true;
+    return SKGPU_OK;
+}
+
+extern "C" skgpu_rc skgpu_tick_wait(skgpu_plan *p, skgpu_tick_timing *t) {
+    if (!p) return fail(SKGPU_ERR_INVALID, "null plan");
+    CU(cudaSetDevice(p->ctx->device));
+    CU(cudaStreamSynchronize(p->ctx->stream));
+    if (t) {
+        memset(t, 0, sizeof(*t));
+        if (p->timing_valid) {
+            CU(cudaEventElapsedTime(&t->h2d_ms, p->e0, p->e1));
+            CU(cudaEventElapsedTime(&t->kernels_ms, p->e1, p->e2));
+            CU(cudaEventElapsedTime(&t->d2h_ms, p->e2, p->e3));
+            CU(cudaEventElapsedTime(&t->total_ms, p->e0, p->e3));
+        }
+    }
+    return SKGPU_OK;
+}
+
+extern "C" skgpu_rc skgpu_plan_op_time(skgpu_plan *p, uint32_t opi, uint32_t sub, float *avg_ms, uint32_t *n_samples) {
+    if (!p || opi >= p->ops.size() || sub > 1) return fail(SKGPU_ERR_INVALID, "invalid op");
+    CU(cudaSetDevice(p->ctx->device));
+    CU(cudaStreamSynchronize(p->ctx->stream));
+    Op &op = p->ops[opi];
+    double sum = 0;
+    for (uint32_t i = 0; i < op.ev_used[sub]; ++i) {
+        float ms = 0;
+        CU(cudaEventElapsedTime(&ms, op.ev[sub][i].first, op.ev[sub][i].second));
+        sum += ms;
+    }
+    if (avg_ms) *avg_ms = op.ev_used[sub] ? (float)(sum / op.ev_used[sub]) : 0.0f;
+    if (n_samples) *n_samples = op.ev_used[sub];
+    return SKGPU_OK;
+}
+extern "C" skgpu_rc skgpu_plan_reset_op_times(skgpu_plan *p) {
+    if (!p) return fail(SKGPU_ERR_INVALID, "null plan");
+    CU(cudaStreamSynchronize(p->ctx->stream));
+    for (auto &op : p->ops) op.ev_used[0] = op.ev_used[1] = 0;
+    return SKGPU_OK;
+}
+
+// ---- arena access / stopwatch
+
+extern "C" skgpu_rc skgpu_arena_upload(skgpu_plan *p, uint64_t off, const void *host, size_t bytes) {
+    if (!p || !host) return fail(SKGPU_ERR_INVALID, "null argument");
+    skgpu_rc rc = check_range(p, off, bytes, "arena upload");
+    if (rc) return rc;
+    CU(cudaSetDevice(p->ctx->device));
+    CU(cudaMemcpyAsync(p->arena + off, host, bytes, cudaMemcpyHostToDevice, p->ctx->stream));
+    CU(cudaStreamSynchronize(p->ctx->stream));
+    return SKGPU_OK;
+}
+extern "C" skgpu_rc skgpu_arena_download(skgpu_plan *p, uint64_t off, void *host, size_t bytes) {
+    if (!p || !host) return fail(SKGPU_ERR_INVALID, "null argument");
+    skgpu_rc rc = check_range(p, off, bytes, "arena download");
+    if (rc) return rc;
+    CU(cudaSetDevice(p->ctx->device));
+    CU(cudaMemcpyAsync(host, p->arena + off, bytes, cudaMemcpyDeviceToHost, p->ctx->stream));
+    CU(cudaStreamSynchronize(p->ctx->stream));
+    return SKGPU_OK;
+}
+extern "C" skgpu_rc skgpu_arena_fill(skgpu_plan *p, uint64_t off, int byte_value, size_t bytes) {
+    if (!p) return fail(SKGPU_ERR_INVALID, "null plan");
+    skgpu_rc rc = check_range(p, off, bytes, "arena fill");
+    if (rc) return rc;
+    CU(cudaSetDevice(p->ctx->device));
+    CU(cudaMemsetAsync(p->arena + off, byte_value, bytes, p->ctx->stream));
+    return SKGPU_OK;
+}
+
+extern "C" skgpu_rc skgpu_timer_start(skgpu_ctx *c) {
+    if (!c) return fail(SKGPU_ERR_INVALID, "null context");
+    CU(cudaSetDevice(c->device));
+    CU(cudaEventRecord(c->tm0, c->stream));
+    return SKGPU_OK;
+}
+extern "C" skgpu_rc skgpu_timer_stop(skgpu_ctx *c) {
+    if (!c) return fail(SKGPU_ERR_INVALID, "null context");
+    CU(cudaSetDevice(c->device));
+    CU(cudaEventRecord(c->tm1, c->stream));
+    return SKGPU_OK;
+}
+extern "C" skgpu_rc skgpu_timer_elapsed_ms(skgpu_ctx *c, float *ms) {
+    if (!c || !ms) return fail(SKGPU_ERR_INVALID, "null argument");
+    CU(cudaSetDevice(c->device));
+    CU(cudaEventSynchronize(c->tm1));
+    CU(cudaEventElapsedTime(ms, c->tm0, c->tm1));
+    return SKGPU_OK;
+}
+extern "C" skgpu_rc skgpu_ctx_sync(skgpu_ctx *c) {
+    if (!c) return fail(SKGPU_ERR_INVALID, "null context");
+    CU(cudaSetDevice(c->device));
+    CU(cudaStreamSynchronize(c->stream));
+    return SKGPU_OK;
+}
+extern "C" skgpu_rc skgpu_ctx_flush_l2(skgpu_ctx *c) {
+    if (!c) return fail(SKGPU_ERR_INVALID, "null context");
+    CU(cudaSetDevice(c->device));
+    if (!c->l2buf) {
+        c->l2n = (size_t)256 * 1024 * 1024 / sizeof(uint4);  // 256 MB > 126 MB L2
+        CU(dalloc(&c->l2buf, c->l2n));
+    }
+    k_l2_flush<<<c->sm_count * 8, 256, 0, c->stream>>>(c->l2buf, c->l2n);
+    CU(cudaGetLastError());
+    return SKGPU_OK;
+}

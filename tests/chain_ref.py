@@ -1,0 +1,42 @@
+"""Oracle composition of the full chain (test infrastructure): the same pipeline streamkit_b200.chain
+builds on the GPU, expressed with the CPU restatement of the reference nodes (oracle/sko.py)."""
+from __future__ import annotations
+
+import collections
+
+import numpy as np
+
+from oracle import sko
+from streamkit_b200 import synth
+
+OUT_RATE = 48000
+OUT_FRAMES = 960
+
+
+def run_chain_oracle(n_sessions: int, k_inputs: int, ticks: int, seed: int, in_rate: int = 44100, channels: int = 2,
+                     inputs_fn=None):
+    chunk = in_rate // 50
+    n_streams = n_sessions * k_inputs
+    in_gains = synth.gains(seed, n_streams, 0.25, 1.5)
+    master = synth.gains(seed + 1, n_sessions, 0.5, 2.0)
+    nodes = [sko.ResamplerNode(OUT_RATE, chunk_frames=chunk, output_frame_size=OUT_FRAMES) for _ in range(n_streams)]
+    queues = [collections.deque() for _ in range(n_streams)]
+    outs = []
+    for t in range(ticks):
+        x = (inputs_fn or synth.tone_streams)(seed, t, n_streams, chunk, channels, in_rate) if inputs_fn is None else inputs_fn(t)
+        out = np.zeros((n_sessions, OUT_FRAMES * channels), dtype=np.int16)
+        for s in range(n_streams):
+            nodes[s].out.clear()
+            nodes[s].push(in_rate, channels, x[s])
+            for pkt in nodes[s].out:                     # audio::gain on every resampled packet (gain.rs:187-189)
+                queues[s].append(sko.gain(pkt["samples"], float(in_gains[s])))
+        for g in range(n_sessions):
+            frames = []
+            for i in range(k_inputs):
+                q = queues[g * k_inputs + i]
+                if q:                                     # clocked mixer pops <= 1 frame per input per tick (mixer.rs:1323-1353)
+                    frames.append((q.popleft(), channels, True))
+            mixed = sko.mix_clocked(frames, channels, OUT_FRAMES)      # zeros when nothing is present
+            out[g] = sko.gain_f32_to_s16(mixed, float(master[g]))     # master gain -> clip -> s16
+        outs.append(out)
+    return outs

@@ -1,0 +1,510 @@
+"""GPU parity tests: every CUDA kernel, called THROUGH the C ABI (ctypes -> libskgpu.so), against the
+oracle (oracle/libsk_oracle.so) on identical seeded inputs.
+
+Bars (BASELINE.json north_star): s16 conversion / clipping bit-exact; f32 gain / mix bit-exact (they
+are single IEEE operations in a defined order); f32 resample within 2e-6 max-abs -- in practice the
+kernels reproduce the oracle bit for bit, the tests assert the tolerance AND report exactness.
+"""
+import numpy as np
+import pytest
+
+from oracle import np_oracle, sko
+from streamkit_b200 import chain, lib as L, synth
+from tests import chain_ref
+
+pytestmark = pytest.mark.gpu
+
+RESAMPLE_TOL = 2e-6  # north_star: f32 resample within 2e-6 max-abs
+
+
+def bits(a):
+    return np.ascontiguousarray(a, dtype=np.float32).view(np.uint32)
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = L.Context(device=0, max_streams=4096, max_channels=8, fifo_frames=2048)
+    yield c
+    c.close()
+
+
+def _al(x, a=256):
+    return (x + a - 1) // a * a
+
+
+# ------------------------------------------------------------------ K1 / K2: gain + format conversion
+
+EDGE = np.array([0.0, -0.0, 1.0, -1.0, 0.999969482421875, 1.0000001, -1.0000001, 0.5 / 32768, 1.5 / 32768, 2.5 / 32768,
+                 -0.5 / 32768, -1.5 / 32768, 32766.5 / 32768, 32767.5 / 32768, -32768.5 / 32768, 3.9, -3.9, 1e-40, -1e-40,
+                 np.inf, -np.inf, np.nan, 1e30, -1e30, 1.17549435e-38], dtype=np.float32)
+
+
+def _run_convert(ctx, mode, frames, gains, offsets_in=None):
+    """frames: list of 1-D arrays (f32 or s16); returns list of outputs"""
+    in_b = 2 if mode == L.CVT_S16_TO_F32 else 4
+    out_b = 2 if mode == L.CVT_F32_TO_S16 else 4
+    segs = np.zeros(len(frames), dtype=L.SEG_DT)
+    off = 0
+    for i, f in enumerate(frames):
+        pad = 0 if offsets_in is None else offsets_in[i]
+        segs[i]["in_off"] = off + pad
+        segs[i]["n_samples"] = f.size
+        segs[i]["gain_idx"] = i if gains is not None else L.SKGPU_NO_GAIN
+        off = _al(off + pad + f.size * in_b)
+    in_bytes = off
+    for i, f in enumerate(frames):
+        pad = 0 if offsets_in is None else (offsets_in[i] // in_b) * out_b
+        segs[i]["out_off"] = off + pad
+        off = _al(off + pad + f.size * out_b)
+    plan = L.Plan(ctx, max(off, 256))
+    try:
+        if gains is not None:
+            plan.set_gains(gains)
+        plan.add_convert(mode, segs)
+        plan.set_io(0, in_bytes, in_bytes, off - in_bytes)
+        plan.finalize()
+        host_in = np.zeros(in_bytes, dtype=np.uint8)
+        for s, f in zip(segs, frames):
+            b = np.ascontiguousarray(f).view(np.uint8)
+            host_in[int(s["in_off"]): int(s["in_off"]) + b.size] = b
+        host_out = np.zeros(off - in_bytes, dtype=np.uint8)
+        plan.submit(host_in, host_out)
+        plan.wait()
+        outs = []
+        for s, f in zip(segs, frames):
+            o = int(s["out_off"]) - in_bytes
+            outs.append(host_out[o: o + f.size * out_b].view(np.int16 if out_b == 2 else np.float32).copy())
+        return outs
+    finally:
+        plan.destroy()
+
+
+@pytest.mark.parametrize("n", [0, 1, 3, 4, 7, 8, 100, 1919, 1920, 1921, 2048, 2049, 5000, 7680])
+def test_gain_f32_bit_exact(ctx, n):
+    x = synth.uniform_pcm(n + 11, n)
+    g = np.float32(1.7)
+    (y,) = _run_convert(ctx, L.CVT_F32_TO_F32, [x], np.array([g], np.float32))
+    assert np.array_equal(bits(y), bits(sko.gain(x, g)))
+
+
+def test_gain_reference_unit_test_constants(ctx):
+    # gain.rs:233-435: 0.5 * 2.0 -> 1.0 ; 0.5x on 3 packets ; zero gain -> exact 0.0 ; 4.0 * 0.5 -> 2.0
+    x = np.full(100, 0.5, np.float32)
+    (y,) = _run_convert(ctx, L.CVT_F32_TO_F32, [x], np.array([2.0], np.float32))
+    assert y.size == 100 and np.all(np.abs(y - 1.0) < 1e-3)
+    frames = [np.full(20, v, np.float32) for v in (0.2, 0.4, 0.6)]
+    outs = _run_convert(ctx, L.CVT_F32_TO_F32, frames, np.array([0.5, 0.5, 0.5], np.float32))
+    for o, v in zip(outs, (0.2, 0.4, 0.6)):
+        assert np.all(np.abs(o - v * 0.5) < 1e-3)
+    (z,) = _run_convert(ctx, L.CVT_F32_TO_F32, [np.ones(20, np.float32)], np.array([0.0], np.float32))
+    assert np.all(z == 0.0)
+    (m,) = _run_convert(ctx, L.CVT_F32_TO_F32, [np.full(20, 0.5, np.float32)], np.array([4.0], np.float32))
+    assert np.all(np.abs(m - 2.0) < 1e-3)
+
+
+def test_gain_many_sessions_ragged(ctx):
+    rng = np.random.default_rng(3)
+    frames = [synth.uniform_pcm(100 + i, int(n)) for i, n in enumerate(rng.integers(1, 4000, size=97))]
+    gains = synth.gains(5, len(frames))
+    outs = _run_convert(ctx, L.CVT_F32_TO_F32, frames, gains)
+    for x, g, y in zip(frames, gains, outs):
+        assert np.array_equal(bits(y), bits(sko.gain(x, g)))
+
+
+def test_gain_unaligned_offsets(ctx):
+    frames = [synth.uniform_pcm(200 + i, 501 + i) for i in range(8)]
+    gains = synth.gains(6, len(frames))
+    outs = _run_convert(ctx, L.CVT_F32_TO_F32, frames, gains, offsets_in=[4 * (i % 4) for i in range(8)])
+    for x, g, y in zip(frames, gains, outs):
+        assert np.array_equal(bits(y), bits(sko.gain(x, g)))
+
+
+def test_f32_to_s16_edge_vectors_bit_exact(ctx):
+    x = np.concatenate([EDGE, np.arange(-40000, 40000, 1, dtype=np.float32) / np.float32(32768.0) + np.float32(0.5 / 32768)])
+    (s,) = _run_convert(ctx, L.CVT_F32_TO_S16, [x], None)
+    assert np.array_equal(s, sko.f32_to_s16(x))
+    assert np.array_equal(s, np_oracle.f32_to_s16(x))
+
+
+@pytest.mark.parametrize("n", [1, 7, 8, 9, 1920, 4097])
+def test_gain_clip_s16_bit_exact(ctx, n):
+    x = synth.uniform_pcm(n, n, over_range_frac=0.05)
+    g = np.float32(2.3)
+    (s,) = _run_convert(ctx, L.CVT_F32_TO_S16, [x], np.array([g], np.float32))
+    assert np.array_equal(s, sko.gain_f32_to_s16(x, g))
+
+
+def test_s16_to_f32_all_values_and_roundtrip(ctx):
+    allv = np.arange(-32768, 32768, dtype=np.int16)
+    (f,) = _run_convert(ctx, L.CVT_S16_TO_F32, [allv], None)
+    assert np.array_equal(bits(f), bits(sko.s16_to_f32(allv)))
+    (back,) = _run_convert(ctx, L.CVT_F32_TO_S16, [f], None)
+    assert np.array_equal(back, allv)  # s16 -> f32 -> s16 is the identity
+
+
+def test_config2_shape_4096_sessions_property(ctx):
+    """BASELINE config #2 at full size: 4096 sessions x 1920 samples, fused gain -> s16.
+    Checked by oracle on a sample of sessions and by a checksum of all of them."""
+    S, N = 4096, 1920
+    x = synth.uniform_pcm(42, S * N).reshape(S, N)
+    gains = synth.gains(43, S)
+    outs = _run_convert(ctx, L.CVT_F32_TO_S16, [x[i] for i in range(S)], gains)
+    got = np.stack(outs)
+    want = np.empty_like(got)
+    for i in range(S):
+        want[i] = sko.gain_f32_to_s16(x[i], gains[i])
+    assert np.array_equal(got, want)
+
+
+# ------------------------------------------------------------------ K3: mixer
+
+def _run_mix(ctx, groups_frames, out_shapes, in_gains=None, master=None, s16=False, present=None):
+    """groups_frames: list of groups, each a list of (samples, channels, unique); out_shapes: [(oc, out_frames)]"""
+    n_in = sum(len(g) for g in groups_frames)
+    inputs = np.zeros(n_in, dtype=L.MIX_INPUT_DT)
+    groups = np.zeros(len(groups_frames), dtype=L.MIX_GROUP_DT)
+    off = 0
+    blobs = []
+    k = 0
+    for gi, g in enumerate(groups_frames):
+        groups[gi]["first_input"] = k
+        groups[gi]["n_inputs"] = len(g)
+        for (smp, ch, uniq) in g:
+            smp = np.ascontiguousarray(smp, dtype=np.float32)
+            inputs[k]["in_off"] = off
+            inputs[k]["n_frames"] = smp.size // ch
+            inputs[k]["channels"] = ch
+            inputs[k]["flags"] = L.MIX_IN_UNIQUE if uniq else 0
+            inputs[k]["gain_idx"] = k if in_gains is not None else L.SKGPU_NO_GAIN
+            blobs.append((off, smp))
+            off = _al(off + smp.size * 4, 16)
+            k += 1
+    in_bytes = _al(off)
+    off = in_bytes
+    ob = 2 if s16 else 4
+    for gi, (oc, of) in enumerate(out_shapes):
+        groups[gi]["out_off"] = off
+        groups[gi]["out_frames"] = of
+        groups[gi]["out_channels"] = oc
+        groups[gi]["flags"] = L.MIX_OUT_S16 if s16 else 0
+        groups[gi]["gain_idx"] = (n_in + gi) if master is not None else L.SKGPU_NO_GAIN
+        off = _al(off + oc * of * ob, 16)
+    plan = L.Plan(ctx, max(_al(off), 256))
+    try:
+        gt = []
+        if in_gains is not None:
+            gt = list(in_gains)
+        elif master is not None:
+            gt = [1.0] * n_in
+        if master is not None:
+            gt += list(master)
+        if gt:
+            plan.set_gains(np.array(gt, np.float32))
+        op = plan.add_mix(groups, inputs)
+        if present is not None:
+            plan.set_present(op, present)
+        plan.set_io(0, in_bytes, in_bytes, max(off - in_bytes, 0))
+        plan.finalize()
+        host_in = np.zeros(in_bytes, dtype=np.uint8)
+        for o, smp in blobs:
+            host_in[o:o + smp.size * 4] = smp.view(np.uint8)
+        host_out = np.zeros(max(off - in_bytes, 1), dtype=np.uint8)
+        plan.submit(host_in, host_out)
+        plan.wait()
+        res = []
+        for gi, (oc, of) in enumerate(out_shapes):
+            o = int(groups[gi]["out_off"]) - in_bytes
+            res.append(host_out[o:o + oc * of * ob].view(np.int16 if s16 else np.float32).copy())
+        return res
+    finally:
+        plan.destroy()
+
+
+def test_mixer_reference_scenarios(ctx):
+    f = lambda v, ch, n=10: (np.full(n * ch, v, np.float32), ch, True)
+    # mixer.rs:1698-1701  0.5 + 0.3 ~ 0.8
+    (o,) = _run_mix(ctx, [[f(0.5, 2), f(0.3, 2)]], [(2, 10)])
+    assert o.size == 20 and np.all(np.abs(o - 0.8) < 1e-3)
+    # three inputs 0.1 + 0.2 + 0.3 ~ 0.6 ; negative 0.5 + (-0.3) ~ 0.2
+    (o,) = _run_mix(ctx, [[f(0.1, 2), f(0.2, 2), f(0.3, 2)]], [(2, 10)])
+    assert np.all(np.abs(o - 0.6) < 1e-3)
+    (o,) = _run_mix(ctx, [[f(0.5, 2), f(-0.3, 2)]], [(2, 10)])
+    assert np.all(np.abs(o - 0.2) < 1e-3)
+    # single input is a pass-through (mixer.rs:1947-1984)
+    (o,) = _run_mix(ctx, [[f(0.75, 2)]], [(2, 10)])
+    assert np.all(o == np.float32(0.75))
+    # stereo + mono -> stereo upmix (mixer.rs:1728-1738), then sticky stereo with mono only (:1741-1754)
+    (o,) = _run_mix(ctx, [[f(0.5, 2), f(0.3, 1)]], [(2, 10)])
+    assert abs(o[0] - 0.8) < 1e-3 and abs(o[1] - 0.8) < 1e-3
+    (o,) = _run_mix(ctx, [[f(0.25, 1)]], [(2, 10)])
+    assert o.size == 20 and np.all(np.abs(o - 0.25) < 1e-3)
+    # clocked: missing input is silence (mixer.rs:2097-2102)
+    (o,) = _run_mix(ctx, [[f(0.75, 2), f(0.1, 2)]], [(2, 10)], present=[1, 0])
+    assert np.all(np.abs(o - 0.75) < 1e-3)
+
+
+def _rand_group(rng, n_inputs, oc, frames, full_scale, ragged=False, chans=(1, 2)):
+    g = []
+    for _ in range(n_inputs):
+        ch = int(rng.choice(chans))
+        fr = frames if not ragged else int(rng.integers(max(1, frames - 50), frames + 50))
+        amp = 1.0 if full_scale else 0.125
+        smp = ((rng.random(fr * ch, dtype=np.float32) * 2 - 1) * np.float32(amp)).astype(np.float32)
+        if rng.random() < 0.1:
+            smp[rng.integers(0, smp.size)] = -0.0
+        g.append((smp, ch, bool(rng.random() < 0.8)))
+    return g
+
+
+@pytest.mark.parametrize("full_scale", [False, True])
+def test_mixer_64_inputs_bit_exact_order(ctx, full_scale):
+    """config #3 shape: 64 stereo inputs per group. With full-scale inputs the partial sums reach |64| where one
+    ulp is 7.6e-6 > 2e-6, so only the reference's summation ORDER gives the right bits."""
+    rng = np.random.default_rng(11 + full_scale)
+    groups = [_rand_group(rng, 64, 2, 960, full_scale, chans=(2,)) for _ in range(6)]
+    outs = _run_mix(ctx, groups, [(2, 960)] * 6)
+    for g, o in zip(groups, outs):
+        want = sko.mix_clocked(g, 2, 960)
+        assert np.array_equal(bits(o), bits(want))
+        assert np.array_equal(bits(want), bits(np_oracle.mix(g, 2, 1920)))
+
+
+def test_mixer_mixed_channels_ragged_sync_mode(ctx):
+    rng = np.random.default_rng(5)
+    groups, shapes, wants = [], [], []
+    for gi in range(40):
+        n = int(rng.integers(1, 9))
+        g = _rand_group(rng, n, 2, int(rng.integers(5, 700)), False, ragged=True, chans=(1, 2, 3) if gi % 5 == 0 else (1, 2))
+        want, oc = sko.mix_sync(g, max_channels_seen=int(rng.choice([0, 1, 2])))
+        groups.append(g)
+        shapes.append((oc, want.size // oc))
+        wants.append(want)
+    outs = _run_mix(ctx, groups, shapes)
+    for o, w in zip(outs, wants):
+        assert np.array_equal(bits(o), bits(w))
+
+
+def test_mixer_stereo_to_mono_and_generic(ctx):
+    rng = np.random.default_rng(9)
+    g1 = _rand_group(rng, 5, 1, 333, False, chans=(1, 2))
+    w1 = sko.mix_clocked(g1, 1, 333)
+    g2 = _rand_group(rng, 4, 3, 200, False, chans=(1, 2, 3, 4))
+    w2 = sko.mix_clocked(g2, 3, 200)
+    o1, o2 = _run_mix(ctx, [g1, g2], [(1, 333), (3, 200)])
+    assert np.array_equal(bits(o1), bits(w1))
+    assert np.array_equal(bits(o2), bits(w2))
+
+
+def test_mixer_gain_clip_s16_epilogue(ctx):
+    rng = np.random.default_rng(21)
+    groups = [_rand_group(rng, 8, 2, 960, True, chans=(2,)) for _ in range(5)]
+    in_g = synth.gains(1, 40, 0.0, 2.0)
+    master = synth.gains(2, 5, 0.1, 1.5)
+    outs = _run_mix(ctx, groups, [(2, 960)] * 5, in_gains=in_g, master=master, s16=True)
+    for gi, (g, o) in enumerate(zip(groups, outs)):
+        scaled = [(sko.gain(s, in_g[gi * 8 + j]), ch, u) for j, (s, ch, u) in enumerate(g)]
+        want = sko.gain_f32_to_s16(sko.mix_clocked(scaled, 2, 960), master[gi])
+        assert np.array_equal(o, want)
+
+
+def test_mixer_presence_changes_base_and_order(ctx):
+    rng = np.random.default_rng(33)
+    g = _rand_group(rng, 12, 2, 480, True, chans=(2,))
+    for trial in range(6):
+        present = (rng.random(12) < 0.6).astype(np.uint8)
+        (o,) = _run_mix(ctx, [g], [(2, 480)], present=present)
+        sel = [f for f, p in zip(g, present) if p]
+        want = sko.mix_clocked(sel, 2, 480)
+        assert np.array_equal(bits(o), bits(want))
+
+
+# ------------------------------------------------------------------ K4: resampler
+
+def _run_resample_stream(ctx, in_rate, out_rate, chunk, channels, n_chunks, seed, n_streams=3):
+    """streams x chunks through the GPU with persistent state; returns per-stream list of per-chunk outputs"""
+    slots = [ctx.stream_open(in_rate, out_rate, chunk, channels) for _ in range(n_streams)]
+    cap = L.Context.max_out_frames(in_rate, out_rate, chunk, channels)
+    in_stride = _al(chunk * channels * 4, 16)
+    out_stride = _al(cap * channels * 4, 16)
+    in_bytes = _al(n_streams * in_stride)
+    res_off = in_bytes
+    out_off = _al(res_off + 8 * n_streams)
+    total = _al(out_off + n_streams * out_stride)
+    plan = L.Plan(ctx, total)
+    items = np.zeros(n_streams, dtype=L.RS_ITEM_DT)
+    items["in_off"] = np.arange(n_streams) * in_stride
+    items["out_off"] = out_off + np.arange(n_streams) * out_stride
+    items["slot"] = slots
+    items["out_cap_frames"] = cap
+    plan.add_resample(items, res_off)
+    plan.set_io(0, in_bytes, res_off, total - res_off)
+    plan.finalize()
+    outs = [[] for _ in range(n_streams)]
+    try:
+        for c in range(n_chunks):
+            x = synth.tone_streams(seed, c, n_streams, chunk, channels, in_rate)
+            host_in = np.zeros(in_bytes, np.uint8)
+            for s in range(n_streams):
+                host_in[s * in_stride: s * in_stride + chunk * channels * 4] = x[s].view(np.uint8)
+            host_out = np.zeros(total - res_off, np.uint8)
+            plan.submit(host_in, host_out, L.SUBMIT_GRAPH if c % 2 else 0)
+            plan.wait()
+            res = host_out[: 8 * n_streams].view(L.RS_RESULT_DT)
+            for s in range(n_streams):
+                assert res[s]["status"] == 0
+                n = int(res[s]["out_frames"])
+                o = (out_off - res_off) + s * out_stride
+                outs[s].append(host_out[o: o + n * channels * 4].view(np.float32).copy())
+        states = [ctx.stream_state(sl, channels) for sl in slots]
+    finally:
+        plan.destroy()
+        for sl in slots:
+            ctx.stream_close(sl)
+    return outs, states
+
+
+@pytest.mark.parametrize("in_rate,out_rate,chunk,channels", [
+    (44100, 48000, 882, 2), (48000, 16000, 960, 2), (48000, 16000, 960, 1), (44100, 48000, 882, 1),
+    (48000, 24000, 480, 2), (16000, 48000, 320, 2), (8000, 48000, 160, 1), (48000, 44100, 960, 2),
+    (44100, 16000, 441, 1), (22050, 48000, 441, 3), (48000, 8000, 960, 2), (32000, 48000, 7, 2), (48000, 16000, 20, 2),
+])
+def test_resampler_streaming_parity(ctx, in_rate, out_rate, chunk, channels):
+    n_chunks, n_streams = 12, 3
+    outs, states = _run_resample_stream(ctx, in_rate, out_rate, chunk, channels, n_chunks, seed=chunk + channels, n_streams=n_streams)
+    exact = True
+    for s in range(n_streams):
+        r = sko.FastFixedIn(in_rate, out_rate, chunk, channels)
+        for c in range(n_chunks):
+            x = synth.tone_streams(chunk + channels, c, n_streams, chunk, channels, in_rate)[s]
+            want = r.process(x)
+            got = outs[s][c]
+            assert got.size == want.size, (s, c, got.size, want.size)  # output COUNT is exact, not +-1
+            if got.size:
+                assert np.max(np.abs(got - want)) <= RESAMPLE_TOL
+                exact = exact and np.array_equal(bits(got), bits(want))
+        li, hist, _, _ = states[s]
+        assert li == r.last_index                      # f64 phase state bit-identical after 12 chunks
+        assert np.array_equal(bits(hist), bits(r.history()))
+    assert exact, "within tolerance but not bit-exact (unexpected: arithmetic is IEEE, uncontracted)"
+
+
+def test_resampler_known_answer_lengths(ctx):
+    # 48k->16k chunk 960: 318 frames first call, then 320
+    outs, _ = _run_resample_stream(ctx, 48000, 16000, 960, 2, 3, seed=1, n_streams=1)
+    assert [o.size // 2 for o in outs[0]] == [318, 320, 320]
+    # reference test resampler.rs:816-835 (remainder path): 48k->24k, fresh resampler with chunk 480 -> 237 frames = 474 samples
+    outs, _ = _run_resample_stream(ctx, 48000, 24000, 480, 2, 1, seed=2, n_streams=1)
+    assert outs[0][0].size == 474 and abs(outs[0][0].size - 480) < 10
+
+
+def test_resampler_long_run_count_exact(ctx):
+    """500 chunks of 44.1k->48k: accumulated f64 phase must track the sequential recurrence exactly
+    (a closed-form idx0 + k*t would drift and eventually flip an output count)."""
+    outs, states = _run_resample_stream(ctx, 44100, 48000, 882, 1, 500, seed=77, n_streams=1)
+    r = sko.FastFixedIn(44100, 48000, 882, 1)
+    for c in range(500):
+        want = r.process(synth.tone_streams(77, c, 1, 882, 1, 44100)[0])
+        assert outs[0][c].size == want.size
+        assert np.array_equal(bits(outs[0][c]), bits(want))
+    assert states[0][0] == r.last_index
+
+
+def test_resampler_reset_gives_fresh_state(ctx):
+    slot = ctx.stream_open(48000, 16000, 960, 2)
+    li, hist, _, _ = ctx.stream_state(slot, 2)
+    assert li == -4.0 and np.all(hist == 0)
+    ctx.stream_close(slot)
+
+
+def test_resampler_many_streams_16384_property(ctx):
+    """config #4 scale-down on shared ctx is limited to 4096 slots; full 16384 runs in a dedicated context.
+    Property: identical streams produce identical outputs and every stream matches the oracle's count."""
+    c2 = L.Context(device=0, max_streams=16384, max_channels=2, fifo_frames=0)
+    try:
+        S, N, C = 16384, 882, 2
+        slots = c2.stream_open_many(44100, 48000, N, C, S)
+        cap = L.Context.max_out_frames(44100, 48000, N, C)
+        in_stride, out_stride = N * C * 4, _al(cap * C * 4, 16)
+        in_bytes = _al(S * in_stride)
+        res_off = in_bytes
+        out_off = _al(res_off + 8 * S)
+        total = _al(out_off + S * out_stride)
+        plan = L.Plan(c2, total)
+        items = np.zeros(S, dtype=L.RS_ITEM_DT)
+        items["in_off"] = np.arange(S, dtype=np.uint64) * in_stride
+        items["out_off"] = out_off + np.arange(S, dtype=np.uint64) * out_stride
+        items["slot"] = slots
+        items["out_cap_frames"] = cap
+        plan.add_resample(items, res_off)
+        plan.set_io(0, in_bytes, res_off, total - res_off)
+        plan.finalize()
+        base = synth.tone_streams(5, 0, 64, N, C, 44100)          # 64 distinct streams tiled 256x
+        x = np.tile(base, (S // 64, 1))
+        host_in = np.zeros(in_bytes, np.uint8)
+        host_in[: S * in_stride] = x.reshape(-1).view(np.uint8)
+        host_out = np.zeros(total - res_off, np.uint8)
+        r = [sko.FastFixedIn(44100, 48000, N, C) for _ in range(64)]
+        for tick in range(3):
+            plan.submit(host_in, host_out)
+            plan.wait()
+            res = host_out[: 8 * S].view(L.RS_RESULT_DT)
+            want = [rr.process(base[i]) for i, rr in enumerate(r)]
+            assert np.all(res["status"] == 0)
+            for i in range(64):
+                assert np.all(res["out_frames"][i::64] == want[i].size // C)
+            o0 = out_off - res_off
+            outs = host_out[o0: o0 + S * out_stride].reshape(S, out_stride)
+            for i in (0, 17, 63):
+                n = want[i].size
+                blk = outs[i::64, : n * 4].copy().view(np.float32)
+                assert np.array_equal(blk.view(np.uint32), np.tile(bits(want[i]), (S // 64, 1)))
+        plan.destroy()
+    finally:
+        c2.close()
+
+
+# ------------------------------------------------------------------ full chain (config #5)
+
+@pytest.mark.parametrize("k_inputs,channels,in_rate", [(1, 2, 44100), (2, 2, 44100), (3, 1, 44100), (2, 2, 48000 * 2 // 3)])
+def test_full_chain_bit_exact(k_inputs, channels, in_rate):
+    S, T = 12, 6
+    got = chain.run_chain_gpu(S, k_inputs, T, seed=3, in_rate=in_rate, channels=channels)
+    want = chain_ref.run_chain_oracle(S, k_inputs, T, seed=3, in_rate=in_rate, channels=channels)
+    for t in range(T):
+        assert np.array_equal(got[t], want[t]), f"tick {t}: {(got[t] != want[t]).sum()} s16 samples differ"
+    assert any(np.any(g != 0) for g in got)
+
+
+def test_full_chain_graph_equals_stream_launch():
+    a = chain.run_chain_gpu(8, 2, 5, seed=9, graph=False)
+    b = chain.run_chain_gpu(8, 2, 5, seed=9, graph=True)
+    for x, y in zip(a, b):
+        assert np.array_equal(x, y)
+
+
+def test_smoke_entry():
+    import __graft_entry__ as g
+
+    g.smoke()
+
+
+# ------------------------------------------------------------------ error behaviour at the boundary
+
+def test_invalid_configs_are_rejected(ctx):
+    with pytest.raises(L.SkgpuError) as e:
+        ctx.stream_open(48000, 0, 960, 2)
+    assert "target_sample_rate must be greater than 0" in e.value.msg  # resampler.rs:82-86
+    with pytest.raises(L.SkgpuError) as e:
+        ctx.stream_open(48000, 16000, 0, 2)
+    assert "chunk_frames must be greater than 0" in e.value.msg        # resampler.rs:88-92
+    with pytest.raises(L.SkgpuError):
+        ctx.stream_open(48000, 16000, 960, 9)
+    plan = L.Plan(ctx, 4096)
+    segs = np.zeros(1, dtype=L.SEG_DT)
+    segs[0]["in_off"] = 4000
+    segs[0]["n_samples"] = 1000
+    segs[0]["gain_idx"] = L.SKGPU_NO_GAIN
+    with pytest.raises(L.SkgpuError) as e:
+        plan.add_convert(L.CVT_F32_TO_F32, segs)
+    assert "outside" in e.value.msg
+    plan.destroy()
