@@ -38,7 +38,8 @@ def load() -> C.CDLL:
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB_PATH):
+    srcs = [os.path.join(_HERE, f) for f in ("sk_oracle.c", "sk_chain.c", "sk_oracle.h")]
+    if not os.path.exists(LIB_PATH) or any(os.path.getmtime(f) > os.path.getmtime(LIB_PATH) for f in srcs):
         build()
     lib = C.CDLL(LIB_PATH)
     f32p, i16p, vp = C.POINTER(C.c_float), C.POINTER(C.c_int16), C.c_void_p
@@ -72,6 +73,9 @@ def load() -> C.CDLL:
     lib.sko_rsnode_finish.argtypes = [vp, EMIT_FN, vp]
     lib.sko_duration_us_for_frames.restype = C.c_uint64
     lib.sko_duration_us_for_frames.argtypes = [C.c_uint32, C.c_size_t]
+    lib.sko_chain_bench.restype = C.c_double
+    lib.sko_chain_bench.argtypes = [C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint16, vp, C.c_uint32, vp, vp, C.c_int, vp,
+                                    C.POINTER(C.c_uint64)]
     _lib = lib
     return lib
 
@@ -228,3 +232,17 @@ class ResamplerNode:
 
 def duration_us_for_frames(rate: int, frames: int) -> int:
     return load().sko_duration_us_for_frames(rate, frames)
+
+
+def chain_bench(n_sessions: int, k_inputs: int, ticks: int, in_rate: int, channels: int, input_pool: np.ndarray,
+                in_gains: np.ndarray, master_gains: np.ndarray, threads: int, want_last: bool = False):
+    """multi-threaded, reference-shaped CPU run of the full chain (sk_chain.c). Returns (seconds, checksum, last_out)."""
+    pool = np.ascontiguousarray(input_pool, dtype=np.float32)
+    ig = np.ascontiguousarray(in_gains, dtype=np.float32)
+    mg = np.ascontiguousarray(master_gains, dtype=np.float32)
+    assert ig.size >= n_sessions * k_inputs and mg.size >= n_sessions
+    last = np.zeros((n_sessions, 960 * channels), dtype=np.int16) if want_last else None
+    cs = C.c_uint64()
+    sec = load().sko_chain_bench(n_sessions, k_inputs, ticks, in_rate, channels, _p(pool), pool.shape[0], _p(ig), _p(mg), threads,
+                                 _p(last) if want_last else None, C.byref(cs))
+    return sec, cs.value, last
