@@ -150,6 +150,39 @@ typedef struct skgpu_mix_group {
     uint32_t reserved;
 } skgpu_mix_group;
 
+/* fused chain (BASELINE config #5): per session K x [audio::resampler{output_frame_size F} -> audio::gain] ->
+ * audio::mixer -> audio::gain -> (s16). One kernel, no f32 intermediate in HBM. Replaces, per tick and session,
+ * resampler.rs:377-470, gain.rs:187-189 (K + 1 times), mixer.rs:960-980 + :1027-1078.
+ *
+ * Protocol (what the frame-batching layer must do):
+ *  - the H2D range is DOUBLE-BANKED (skgpu_plan_set_banks): tick n uploads into bank n & 1; a stream keeps the
+ *    same in_off while it is alive, so its previous chunk is found at the same offset in the other bank;
+ *  - a stream that delivers no chunk in a tick is marked absent (skgpu_plan_set_present) and the host repeats
+ *    the stream's previous chunk bytes at in_off, so the other bank stays valid for the next tick;
+ *  - eligible streams: channels 1 or 2, chunk_frames >= 16, chunk_frames * out_rate / in_rate == F (a packet
+ *    never spans more than two chunks). Everything else uses the unfused resample + mix ops. */
+typedef struct skgpu_chain_input {
+    uint64_t in_off;      /* byte offset of the stream's chunk inside bank 0 (bank 1 = + bank_stride), 16-byte aligned */
+    uint32_t slot;        /* resampler stream slot (state in HBM) */
+    uint32_t gain_idx;    /* per-input audio::gain, or SKGPU_NO_GAIN */
+    uint32_t flags;       /* SKGPU_MIX_IN_UNIQUE */
+    uint32_t reserved;
+} skgpu_chain_input;
+
+typedef struct skgpu_chain_group {
+    uint64_t out_off;      /* F * out_channels samples (s16 with SKGPU_MIX_OUT_S16, else f32), 16-byte aligned */
+    uint32_t first_input;
+    uint32_t n_inputs;     /* <= 64 */
+    uint32_t gain_idx;     /* master audio::gain, or SKGPU_NO_GAIN */
+    uint16_t out_channels; /* 1 or 2 (sticky max, decided by the host) */
+    uint16_t flags;        /* SKGPU_MIX_OUT_S16 */
+} skgpu_chain_group;
+
+typedef struct skgpu_chain_result { /* per input, written at the op's results offset every tick */
+    uint32_t emitted;      /* 1 = this input contributed an F-frame packet to the mix this tick */
+    uint32_t status;       /* bit0 backlog (second packet pending), bit1 phase-table overflow, bit2 carry spans two chunks */
+} skgpu_chain_result;
+
 /* ------------------------------------------------------------------ plan = one compiled tick
  * A plan is the steady-state shape of a tick: an ordered list of ops whose descriptor tables live on the
  * device, one H2D range and one D2H range. Built once, replayed every 20 ms; tables can be replaced
@@ -165,18 +198,29 @@ skgpu_rc skgpu_plan_add_resample(skgpu_plan *plan, const skgpu_rs_item *items, u
                                  uint32_t *op_out);
 skgpu_rc skgpu_plan_add_mix(skgpu_plan *plan, const skgpu_mix_group *groups, uint32_t n_groups,
                             const skgpu_mix_input *inputs, uint32_t n_inputs, uint32_t *op_out);
+/* requires skgpu_plan_set_banks first; output_frame_size = AudioResamplerConfig.output_frame_size (resampler.rs:33-38) */
+skgpu_rc skgpu_plan_add_chain(skgpu_plan *plan, const skgpu_chain_group *groups, uint32_t n_groups,
+                              const skgpu_chain_input *inputs, uint32_t n_inputs, uint32_t output_frame_size,
+                              uint64_t results_off, uint32_t *op_out);
 
 /* replace an op's descriptor table in place (n <= capacity given at add time) */
 skgpu_rc skgpu_plan_update_convert(skgpu_plan *plan, uint32_t op, const skgpu_seg *segs, uint32_t n);
 skgpu_rc skgpu_plan_update_resample(skgpu_plan *plan, uint32_t op, const skgpu_rs_item *items, uint32_t n);
 skgpu_rc skgpu_plan_update_mix(skgpu_plan *plan, uint32_t op, const skgpu_mix_group *groups, uint32_t n_groups,
                                const skgpu_mix_input *inputs, uint32_t n_inputs);
+skgpu_rc skgpu_plan_update_chain(skgpu_plan *plan, uint32_t op, const skgpu_chain_group *groups, uint32_t n_groups,
+                                 const skgpu_chain_input *inputs, uint32_t n_inputs);
 
 /* tick I/O ranges: host_in[0..bytes) -> arena[h2d_off..), arena[d2h_off..) -> host_out[0..bytes) */
 skgpu_rc skgpu_plan_set_io(skgpu_plan *plan, uint64_t h2d_off, uint64_t h2d_bytes, uint64_t d2h_off, uint64_t d2h_bytes);
+/* double-bank the H2D range: tick n uploads host_in to h2d_off + (n & 1) * bank_stride (bank_stride >= h2d_bytes,
+ * 16-byte multiple). Offsets of chain inputs are relative to bank 0. Call before skgpu_plan_add_chain. */
+skgpu_rc skgpu_plan_set_banks(skgpu_plan *plan, uint64_t bank_stride);
+/* number of ticks submitted so far (bank of the NEXT tick = result & 1) */
+uint64_t skgpu_plan_tick_count(const skgpu_plan *plan);
 
 /* per-tick dynamic parameters, snapshotted at submit (gain.rs:151: control messages are drained before
- * each packet, so a new gain applies from the next frame on). present[i] != 0 <=> mix input i of op
+ * each packet, so a new gain applies from the next frame on). present[i] != 0 <=> input i of mix or chain op
  * `mix_op` delivered a frame this tick; absent inputs are silence (mixer.rs:999-1009, :1354-1367). */
 skgpu_rc skgpu_plan_set_gains(skgpu_plan *plan, const float *gains, uint32_t n);
 skgpu_rc skgpu_plan_set_present(skgpu_plan *plan, uint32_t mix_op, const uint8_t *present, uint32_t n);

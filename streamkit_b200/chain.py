@@ -25,16 +25,20 @@ def _align(x: int, a: int = 256) -> int:
 
 class ChainTick:
     def __init__(self, n_sessions: int, k_inputs: int, in_rate: int = 44100, channels: int = 2, device: int = 0,
-                 seed: int = 0, chunk_frames: int | None = None):
+                 seed: int = 0, chunk_frames: int | None = None, fused: bool = True):
+        """fused=True: one k_chain launch per tick (double-banked input, lagged recompute, no HBM intermediates);
+        fused=False: the general unfused ops (k_resample -> device re-framing ring -> k_mix)."""
+        self.fused = fused
         self.S, self.K, self.C = n_sessions, k_inputs, channels
         self.in_rate = in_rate
         self.chunk = chunk_frames if chunk_frames is not None else in_rate // 50  # frames per 20 ms tick
         self.n_streams = n_sessions * k_inputs
-        self.ctx = L.Context(device=device, max_streams=self.n_streams, max_channels=channels, fifo_frames=2048)
-        self.in_stride = self.chunk * channels * 4
+        self.ctx = L.Context(device=device, max_streams=self.n_streams, max_channels=channels, fifo_frames=0 if fused else 2048)
+        self.in_stride = _align(self.chunk * channels * 4, 16)
         self.out_stride = OUT_FRAMES * channels * 2
         self.in_bytes = self.n_streams * self.in_stride
-        self.res_off = _align(self.in_bytes)
+        self.bank_stride = _align(self.in_bytes) if fused else 0
+        self.res_off = _align(self.in_bytes) + self.bank_stride
         self.res_bytes = self.n_streams * 8
         self.out_off = _align(self.res_off + self.res_bytes)
         self.out_bytes = n_sessions * self.out_stride
@@ -46,6 +50,27 @@ class ChainTick:
         self.plan.set_gains(np.concatenate([self.in_gains, self.master_gains]))
         slots = self.ctx.stream_open_many(in_rate, OUT_RATE, self.chunk, channels, self.n_streams)
         self.slots = slots
+        if fused:
+            self.plan.set_io(0, self.in_bytes, self.out_off, self.out_bytes)
+            self.plan.set_banks(self.bank_stride)
+            cin = np.zeros(self.n_streams, dtype=L.CHAIN_INPUT_DT)
+            cin["in_off"] = np.arange(self.n_streams, dtype=np.uint64) * self.in_stride
+            cin["slot"] = slots
+            cin["gain_idx"] = np.arange(self.n_streams, dtype=np.uint32)
+            cin["flags"] = L.MIX_IN_UNIQUE
+            cg = np.zeros(n_sessions, dtype=L.CHAIN_GROUP_DT)
+            cg["out_off"] = self.out_off + np.arange(n_sessions, dtype=np.uint64) * self.out_stride
+            cg["first_input"] = np.arange(n_sessions, dtype=np.uint32) * k_inputs
+            cg["n_inputs"] = k_inputs
+            cg["gain_idx"] = self.n_streams + np.arange(n_sessions, dtype=np.uint32)
+            cg["out_channels"] = channels
+            cg["flags"] = L.MIX_OUT_S16
+            self.op_chain = self.plan.add_chain(cg, cin, OUT_FRAMES, self.res_off)
+            self.op_rs = self.op_mix = None
+            self.plan.finalize()
+            self.host_in = self.ctx.pinned(self.in_bytes, np.float32)
+            self.host_out = self.ctx.pinned(self.out_bytes, np.int16)
+            return
         items = np.zeros(self.n_streams, dtype=L.RS_ITEM_DT)
         items["in_off"] = np.arange(self.n_streams, dtype=np.uint64) * self.in_stride
         items["slot"] = slots
@@ -78,13 +103,14 @@ class ChainTick:
 
     def tick(self, inputs: np.ndarray, flags: int = 0) -> np.ndarray:
         """inputs: float32 [n_streams, chunk*channels]; returns int16 [n_sessions, 960*channels]"""
-        self.host_in[:] = np.ascontiguousarray(inputs, dtype=np.float32).reshape(-1)
+        x = np.ascontiguousarray(inputs, dtype=np.float32).reshape(self.n_streams, -1)
+        self.host_in.reshape(self.n_streams, self.in_stride // 4)[:, : x.shape[1]] = x
         self.plan.submit(self.host_in, self.host_out, flags)
         self.plan.wait()
         return self.host_out.reshape(self.S, OUT_FRAMES * self.C).copy()
 
     def results(self) -> np.ndarray:
-        return self.plan.download(self.res_off, self.res_bytes, L.RS_RESULT_DT)
+        return self.plan.download(self.res_off, self.res_bytes, L.CHAIN_RESULT_DT if self.fused else L.RS_RESULT_DT)
 
     def close(self):
         self.plan.destroy()
@@ -92,8 +118,8 @@ class ChainTick:
 
 
 def run_chain_gpu(n_sessions: int, k_inputs: int, ticks: int, seed: int, in_rate: int = 44100, channels: int = 2,
-                  graph: bool = False):
-    ct = ChainTick(n_sessions, k_inputs, in_rate=in_rate, channels=channels, seed=seed)
+                  graph: bool = False, fused: bool = True):
+    ct = ChainTick(n_sessions, k_inputs, in_rate=in_rate, channels=channels, seed=seed, fused=fused)
     try:
         outs = []
         for t in range(ticks):

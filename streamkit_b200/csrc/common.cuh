@@ -1,0 +1,178 @@
+// common.cuh -- device-side tables and small helpers shared by all streamkit_b200 kernels.
+//
+// All kernels are HBM-bound streaming kernels (<= 3 flop/byte): no tensor cores. What matters is 128-bit
+// coalesced access, enough bytes in flight per SM, shared-memory/TMA staging where the access pattern is
+// data dependent (resampler), and exact IEEE arithmetic: the TU is compiled with -fmad=false and the
+// parity-critical expressions additionally use __fmul_rn/__fadd_rn so nothing is ever contracted
+// (Rust, the reference's language, never contracts a*b+c).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/skgpu_batch.h"
+#include "phase_runs.h"
+
+namespace skgpu {
+
+// ------------------------------------------------------------------ device-side tables
+
+struct OpHeader {       // lives in device memory so a captured graph sees table-size updates
+    uint32_t count;     // live entries (<= capacity the grid was sized for)
+    uint32_t count2;    // second table (mix / chain inputs)
+    uint32_t pad[2];
+};
+
+struct SlotTables {     // SoA per-stream state + configuration, all device pointers
+    double *last_index;     // rubato self.last_index (for the NEXT chunk)
+    double *t_ratio;        // 1.0 / resample_ratio
+    int32_t *end_idx;       // chunk - 9 - ceil(t)
+    uint32_t *chunk;        // chunk_frames
+    uint32_t *channels;
+    float *hist;            // [slot][16 * max_channels]: the 16 frames before the oldest chunk that still has
+                            // unconsumed output (plain resample op: before the next chunk; chain op: before the previous one)
+    SkPhaseTable *tab;      // [slot][2]: phase tables of the two most recent chunks, indexed by (chunk number & 1)
+    uint32_t *chunk_count;  // chunks processed so far
+    uint32_t *carry;        // chain op: resampled frames produced but not yet emitted in a packet
+    float *fifo;            // [slot][fifo_frames * max_channels] (may be null): unfused re-framing ring
+    unsigned long long *fifo_w;  // total frames ever written
+    unsigned long long *fifo_r;  // total frames ever consumed
+    uint32_t max_channels;
+    uint32_t fifo_frames;   // power of two
+};
+
+// ------------------------------------------------------------------ small helpers
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// streaming 128-bit accesses: inputs are read once, outputs written once -> keep them out of L1
+__device__ __forceinline__ float4 ldg_stream_f4(const float4 *p) {
+    float4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ uint4 ldg_stream_u4(const uint4 *p) {
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ float2 ldg_stream_f2(const float2 *p) {
+    float2 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.f32 {%0,%1}, [%2];" : "=f"(r.x), "=f"(r.y) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ void stg_stream_f4(float4 *p, float4 v) {
+    asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ void stg_stream_f2(float2 *p, float2 v) {
+    asm volatile("st.global.L1::no_allocate.v2.f32 [%0], {%1,%2};" ::"l"(p), "f"(v.x), "f"(v.y) : "memory");
+}
+__device__ __forceinline__ void stg_stream_u4(uint4 *p, uint4 v) {
+    asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ void stg_stream_u2(uint2 *p, uint2 v) {
+    asm volatile("st.global.L1::no_allocate.v2.u32 [%0], {%1,%2};" ::"l"(p), "r"(v.x), "r"(v.y) : "memory");
+}
+
+// f32 -> s16: sat_s16(rint_half_even(x * 32768)), NaN -> 0  (SURVEY A5). cvt.rni.sat.s16.f32 is exactly
+// this: round-to-nearest-even, saturating, NaN converts to 0.
+__device__ __forceinline__ uint32_t f32_to_s16_bits(float x) {
+    float y = __fmul_rn(x, 32768.0f);
+    int r;
+    asm("cvt.rni.sat.s16.f32 %0, %1;" : "=r"(r) : "f"(y));  // 16-bit result sign-extended in a b32 reg
+    return (uint32_t)r & 0xFFFFu;
+}
+__device__ __forceinline__ uint32_t pack_s16x2(float a, float b) { return f32_to_s16_bits(a) | (f32_to_s16_bits(b) << 16); }
+__device__ __forceinline__ float s16_to_f32(int s) { return __fmul_rn((float)s, 1.0f / 32768.0f); }
+
+// ---- mbarrier + TMA bulk copy (cp.async.bulk, SASS UBLKCP): one instruction moves a whole chunk into smem
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+
+// rubato interp_lin: (1 - x) * y0 + x * y1, every operation rounded to f32
+__device__ __forceinline__ float interp_lin(float frac, float y0, float y1) {
+    return __fadd_rn(__fmul_rn(__fsub_rn(1.0f, frac), y0), __fmul_rn(frac, y1));
+}
+
+// ---- phase table staged in shared memory (only the used part is copied)
+struct SmemPhase {
+    double prefix[SK_PREFIX_MAX];
+    SkRun runs[SK_RUNS_MAX];
+    uint32_t n_out, n_prefix, n_runs, overflow;
+};
+
+// cooperative copy global -> smem by `nthreads` threads (tid in [0, nthreads)); caller syncs afterwards
+__device__ __forceinline__ void load_phase_table(SmemPhase *dst, const SkPhaseTable *src, uint32_t tid, uint32_t nthreads) {
+    const uint4 hdr = *reinterpret_cast<const uint4 *>(src);  // n_out, n_prefix, n_runs, overflow (broadcast load)
+    const uint32_t np = min(hdr.y, (uint32_t)SK_PREFIX_MAX), nr = min(hdr.z, (uint32_t)SK_RUNS_MAX);
+    if (tid == 0) { dst->n_out = hdr.x; dst->n_prefix = np; dst->n_runs = nr; dst->overflow = hdr.w; }
+    const uint2 *sp = reinterpret_cast<const uint2 *>(src->prefix);
+    uint2 *dp = reinterpret_cast<uint2 *>(dst->prefix);
+    for (uint32_t i = tid; i < np; i += nthreads) dp[i] = sp[i];
+    const uint2 *sr = reinterpret_cast<const uint2 *>(src->runs);
+    uint2 *dr = reinterpret_cast<uint2 *>(dst->runs);
+    for (uint32_t i = tid; i < nr * 3u; i += nthreads) dr[i] = sr[i];
+}
+
+// idx of output k from a staged table. Searches the run from the END: the upper binades hold most outputs
+// ([512,1024) alone half of them), so the expected number of steps is ~1.
+__device__ __forceinline__ double phase_eval_smem(const SmemPhase *T, double t, uint32_t k) {
+    if (k < T->n_prefix) return T->prefix[k];
+    uint32_t r = T->n_runs - 1u;
+    while (r > 0u && T->runs[r].k_a > k) --r;
+    const SkRun rn = T->runs[r];
+    if (k < rn.k_e) return __fma_rn((double)(k - rn.k_a), rn.delta, rn.x_a);
+    return __dadd_rn(__fma_rn((double)(rn.k_e - 1u - rn.k_a), rn.delta, rn.x_a), t);  // gap element
+}
+
+// split idx into buffer position (floor(idx) + 16 = start_idx + 2*POLYNOMIAL_LEN) and f32 fraction
+__device__ __forceinline__ void phase_split(double x, uint32_t &p, float &frac) {
+    const int fl = __double2int_rd(x);
+    frac = __double2float_rn(__dsub_rn(x, (double)fl));  // T::coerce(idx - floor(idx))
+    p = (uint32_t)(fl + 16);
+}
+
+// (re)initialises stream slots: fresh FastFixedIn = zero history, last_index = -4.0 (rubato new())
+__global__ void k_reset_slots(const uint32_t *__restrict__ slots, uint32_t n, SlotTables st) {
+    const uint32_t i = blockIdx.x;
+    if (i >= n) return;
+    const uint32_t slot = slots[i];
+    for (uint32_t s = threadIdx.x; s < 16u * st.max_channels; s += blockDim.x) st.hist[(size_t)slot * 16u * st.max_channels + s] = 0.0f;
+    if (threadIdx.x == 0) {
+        st.last_index[slot] = -4.0;
+        st.chunk_count[slot] = 0;
+        st.carry[slot] = 0;
+        st.tab[(size_t)slot * 2].n_out = 0;
+        st.tab[(size_t)slot * 2 + 1].n_out = 0;
+        if (st.fifo_w) { st.fifo_w[slot] = 0ull; st.fifo_r[slot] = 0ull; }
+    }
+}
+
+__global__ void k_l2_flush(uint4 *buf, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) buf[i] = make_uint4((uint32_t)i, 0u, 0u, 0u);
+}
+
+}  // namespace skgpu

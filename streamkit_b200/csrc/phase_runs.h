@@ -4,23 +4,24 @@
 // crates/nodes/src/audio/filters/resampler.rs:404-407) advances the read position by REPEATED f64
 // addition:   while idx < end_idx { idx += t; emit(floor(idx), frac(idx)) }
 // A parallel kernel cannot use idx_k = idx_0 + k*t: the roundings differ, and with them (rarely) the
-// output count per chunk. This header turns the recurrence into a short table of "runs" that thousands
-// of threads can evaluate independently and BIT-EXACTLY:
+// output count per chunk. This header turns the recurrence into a compact PHASE TABLE that thousands of
+// threads evaluate independently and BIT-EXACTLY:
 //
-//     for k in [k_a, next run's k_a):   idx_k == fma((double)(k - k_a), delta, x_a)      (exact)
+//   k <  n_prefix             : idx_k = prefix[k]                      (the first few elements, stored)
+//   k in [k_a, k_e) of run r  : idx_k = fma((double)(k - k_a), delta, x_a)        (exact, see below)
+//   k == k_e of run r (gap)   : idx_k = idx_{k-1} + t                  (one true addition)
 //
-// Why it is exact: inside one binade B = +-[2^e, 2^(e+1)) with unit u = 2^(e-52), every chain element y
-// is a multiple of u, so fl(y + t) = y + RN_u(t) as long as the result stays strictly inside B; the
+// Why a run is exact: inside one binade B = +-[2^e, 2^(e+1)) with unit u = 2^(e-52) every chain element y
+// is a multiple of u, so fl(y + t) = y + RN_u(t) as long as the result stays strictly inside B: the
 // increment is a constant multiple of u and the fma result is representable, hence unrounded. Ties
 // (t an odd multiple of u/2) settle after one step because round-half-even leaves an even mantissa.
-// A run is therefore opened only after three consecutive TRUE chain elements a, b, c in the same
-// binade (b, c not on the binade's lower boundary): anchor b, delta = c - b. Every other element is
-// stored as a singleton (delta = 0). Membership of later elements is decided on the TRUE chain value
-// (same sign/exponent word, mantissa != 0), which implies equality with the fma prediction.
-// tests/test_phase_runs.py checks this against the plain recurrence for millions of (t, last_index).
-//
-// The generator is the sequential chain itself (one thread per stream, data independent: it needs only
-// last_index, t and end_idx), so correctness never depends on the closed form being clever.
+// A run is therefore opened only after three consecutive TRUE chain elements a, b, c in the same binade
+// (b, c not on the binade's lower edge): anchor b, delta = c - b. Because the increment is constant, the
+// generator does not walk a long run element by element: it JUMPS to the last member below
+// min(end_idx, binade edge) with one division (+ exact fix-up), so one chunk costs O(#binades) ~ 50
+// dependent steps instead of ~960. Everything that is not provably inside a run is produced by the true
+// sequential addition. tests/test_phase_runs.py checks every element against the plain recurrence for
+// hundreds of millions of (t, last_index) pairs, including tie-prone ratios.
 #pragma once
 #include <stdint.h>
 
@@ -30,13 +31,23 @@
 #define SK_HD static inline
 #endif
 
-#define SK_RUNS_MAX 96u
+#define SK_PREFIX_MAX 40u
+#define SK_RUNS_MAX 40u
 
 struct SkRun {
     double x_a;    // chain value of the anchor element
-    double delta;  // constant increment inside the run (0 for a singleton)
-    uint32_t k_a;  // output index (within the chunk) of the anchor
-    uint32_t _pad;
+    double delta;  // constant increment inside the run (0 for a degenerate single-element entry)
+    uint32_t k_a;  // first output index covered
+    uint32_t k_e;  // one past the last output index covered; index k_e itself may be an uncovered "gap" element
+};
+
+struct SkPhaseTable {       // one process() call of one stream
+    uint32_t n_out;         // frames this call produces
+    uint32_t n_prefix;      // elements [0, n_prefix) are stored verbatim
+    uint32_t n_runs;
+    uint32_t overflow;      // 1 = table capacity exceeded (never seen for ratios in [1/256, 256])
+    double prefix[SK_PREFIX_MAX];
+    SkRun runs[SK_RUNS_MAX];
 };
 
 SK_HD uint64_t sk_d2bits(double x) {
@@ -48,7 +59,15 @@ SK_HD uint64_t sk_d2bits(double x) {
     return v.u;
 #endif
 }
-
+SK_HD double sk_bits2d(uint64_t b) {
+#if defined(__CUDA_ARCH__)
+    return __longlong_as_double((long long)b);
+#else
+    union { double d; uint64_t u; } v;
+    v.u = b;
+    return v.d;
+#endif
+}
 SK_HD double sk_dadd(double a, double b) {
 #if defined(__CUDA_ARCH__)
     return __dadd_rn(a, b);
@@ -56,31 +75,47 @@ SK_HD double sk_dadd(double a, double b) {
     return a + b;
 #endif
 }
+SK_HD double sk_dfma(double a, double b, double c) {
+#if defined(__CUDA_ARCH__)
+    return __fma_rn(a, b, c);
+#else
+    return __builtin_fma(a, b, c);
+#endif
+}
 
-// Generates the run table for one process() call.
-//   last_index : rubato's self.last_index on entry
-//   t          : 1.0 / resample_ratio (f64)
-//   end_idx    : chunk - 9 - ceil(t)
-// Returns the number of output frames n; *n_runs receives the table length (clamped to rmax and
-// *overflow set when more runs were needed); *idx_end receives the final idx (last_index' = idx_end - chunk).
-SK_HD uint32_t sk_phase_runs(double last_index, double t, int32_t end_idx, SkRun *runs, uint32_t rmax,
-                             uint32_t *n_runs, double *idx_end, int *overflow) {
+// Generates the phase table of one process() call.
+//   last_index : rubato's self.last_index on entry;  t : 1.0 / resample_ratio;  end_idx : chunk - 9 - ceil(t)
+// Returns n_out; *idx_end receives the final idx (the caller stores last_index' = idx_end - chunk).
+SK_HD uint32_t sk_phase_table(double last_index, double t, int32_t end_idx, SkPhaseTable *T, double *idx_end) {
     const double end = (double)end_idx;
     double x = last_index;
-    uint32_t k = 0, nr = 0;
-    bool have_run = false;
-    uint32_t run_key = 0;
-    uint32_t prev_key = 0xFFFFFFFFu, cnt = 0;
+    uint32_t k = 0, np = 0, nr = 0;
+    bool in_prefix = true, have_run = false;
+    uint32_t run_key = 0, prev_key = 0xFFFFFFFFu, cnt = 0;
     bool prev_strict = false;
-    int ovf = 0;
+    double xb = 0.0;              // value of the previous element
+    SkRun cur;                    // the open (last) entry, kept in registers; flushed to T->runs[nr-1]
+    cur.x_a = 0.0; cur.delta = 0.0; cur.k_a = 0; cur.k_e = 0;
+    bool cur_valid = false;
+    uint32_t ovf = 0;
+
+#define SK_FLUSH_CUR()                                              \
+    do {                                                            \
+        if (cur_valid) {                                            \
+            if (nr <= SK_RUNS_MAX && nr > 0) T->runs[nr - 1] = cur; \
+        }                                                           \
+    } while (0)
+
     while (x < end) {
         x = sk_dadd(x, t);
         const uint64_t bits = sk_d2bits(x);
         const uint32_t key = (uint32_t)(bits >> 52);                 // sign + exponent
         const bool strict = (bits & 0x000FFFFFFFFFFFFFull) != 0ull;  // not on the binade's lower edge
         if (have_run) {
-            if (key == run_key && strict) {
+            if (key == run_key && strict) {  // provably fma(k - k_a, delta, x_a): extend the open run
                 ++k;
+                cur.k_e = k;
+                xb = x;
                 continue;
             }
             have_run = false;
@@ -89,36 +124,97 @@ SK_HD uint32_t sk_phase_runs(double last_index, double t, int32_t end_idx, SkRun
         }
         cnt = (key == prev_key) ? cnt + 1 : 1;
         prev_key = key;
-        if (cnt >= 3 && strict && prev_strict && nr > 0 && nr <= rmax) {
-            // a = element k-2, b = element k-1 (entry nr-1), c = this element
-            runs[nr - 1].delta = x - runs[nr - 1].x_a;  // exact: same binade
+        const bool can_open = cnt >= 3 && strict && prev_strict && k >= 1;
+        if (can_open && !(in_prefix && !(xb > 0.0) && np < SK_PREFIX_MAX)) {
+            // a = element k-2, b = element k-1 (value xb), c = this element: open a run anchored at b
+            if (in_prefix) {  // b leaves the prefix and becomes the first table entry
+                in_prefix = false;
+                np = k - 1;
+            }
+            const bool b_has_entry = cur_valid && cur.k_a == k - 1 && cur.k_e == k;  // degenerate entry for b
+            if (!b_has_entry) {
+                SK_FLUSH_CUR();
+                ++nr;
+                if (nr > SK_RUNS_MAX) ovf = 1;
+            }
+            cur.x_a = xb;
+            cur.delta = x - xb;  // exact: same binade
+            cur.k_a = k - 1;
+            cur.k_e = k + 1;
+            cur_valid = true;
             have_run = true;
             run_key = key;
-        } else {
-            if (nr < rmax) {
-                runs[nr].x_a = x;
-                runs[nr].delta = 0.0;
-                runs[nr].k_a = k;
-                runs[nr]._pad = 0;
-            } else {
-                ovf = 1;
+            // ---- jump to the last member strictly below min(end, binade edge)
+            const uint32_t E = key & 0x7FFu;
+            if (E > 0u && E < 0x7FEu && cur.delta > 0.0) {
+                const bool neg = (key & 0x800u) != 0u;
+                const double lim = neg ? sk_bits2d((uint64_t)key << 52)            // -2^e (values below it are inside)
+                                       : sk_bits2d((uint64_t)(E + 1u) << 52);      // +2^(e+1)
+                const double M = lim < end ? lim : end;
+                const double q = (M - cur.x_a) / cur.delta;
+                if (q > 2.0 && q < 1048576.0) {
+                    uint32_t j = (uint32_t)q;
+                    while (j > 1u && !(sk_dfma((double)j, cur.delta, cur.x_a) < M)) --j;
+                    while (sk_dfma((double)(j + 1u), cur.delta, cur.x_a) < M) ++j;
+                    if (j > 1u) {
+                        x = sk_dfma((double)j, cur.delta, cur.x_a);
+                        k = cur.k_a + j;
+                        cur.k_e = k + 1;
+                    }
+                }
             }
+            xb = x;
+            prev_strict = true;
+            ++k;
+            continue;
+        }
+        // ---- element outside any run
+        if (in_prefix) {
+            if (np < SK_PREFIX_MAX) {
+                T->prefix[np++] = x;
+                prev_strict = strict;
+                xb = x;
+                ++k;
+                continue;
+            }
+            in_prefix = false;  // prefix full: continue with table entries
+        }
+        // allowed uncovered: exactly one element right after the end of the last entry (consumer adds t once)
+        const bool gap_ok = cur_valid && cur.k_e == k && cur.delta != 0.0;
+        if (!gap_ok) {
+            SK_FLUSH_CUR();
             ++nr;
+            if (nr > SK_RUNS_MAX) ovf = 1;
+            cur.x_a = x;
+            cur.delta = 0.0;
+            cur.k_a = k;
+            cur.k_e = k + 1;
+            cur_valid = true;
         }
         prev_strict = strict;
+        xb = x;
         ++k;
     }
-    *n_runs = nr < rmax ? nr : rmax;
+    SK_FLUSH_CUR();
+#undef SK_FLUSH_CUR
+    T->n_out = k;
+    T->n_prefix = np < k ? np : k;
+    T->n_runs = nr < SK_RUNS_MAX ? nr : SK_RUNS_MAX;
+    T->overflow = ovf;
     *idx_end = x;
-    *overflow = ovf;
     return k;
 }
 
-// Evaluate element k from its run (the consumer side; exact by construction).
-SK_HD double sk_phase_eval(const SkRun &r, uint32_t k) {
-#if defined(__CUDA_ARCH__)
-    return __fma_rn((double)(k - r.k_a), r.delta, r.x_a);
-#else
-    return __builtin_fma((double)(k - r.k_a), r.delta, r.x_a);
-#endif
+// Consumer side: idx of output k (k < n_out). `r` is a cursor the caller may carry between calls with
+// non-decreasing k (start it at 0).
+SK_HD double sk_phase_eval(const double *prefix, uint32_t n_prefix, const SkRun *runs, uint32_t n_runs, double t, uint32_t k,
+                           uint32_t *r_io) {
+    if (k < n_prefix) return prefix[k];
+    uint32_t r = *r_io;
+    while (r + 1u < n_runs && runs[r + 1u].k_a <= k) ++r;
+    *r_io = r;
+    const SkRun rn = runs[r];
+    if (k < rn.k_e) return sk_dfma((double)(k - rn.k_a), rn.delta, rn.x_a);
+    // gap element: one true addition after the run's last member
+    return sk_dadd(sk_dfma((double)(rn.k_e - 1u - rn.k_a), rn.delta, rn.x_a), t);
 }

@@ -135,12 +135,13 @@ extern "C" skgpu_rc skgpu_ctx_create(int32_t device_ordinal, const skgpu_ctx_con
     CU(dalloc(&st.chunk, S));
     CU(dalloc(&st.channels, S));
     CU(dalloc(&st.hist, S * 16 * cfg->max_channels));
-    CU(dalloc(&st.runs, S * SK_RUNS_MAX));
-    CU(dalloc(&st.n_runs, S));
-    CU(dalloc(&st.n_out, S));
+    CU(dalloc(&st.tab, S * 2));
+    CU(dalloc(&st.chunk_count, S));
+    CU(dalloc(&st.carry, S));
     CU(cudaMemset(st.hist, 0, S * 16 * cfg->max_channels * sizeof(float)));
-    CU(cudaMemset(st.n_runs, 0, S * sizeof(uint32_t)));
-    CU(cudaMemset(st.n_out, 0, S * sizeof(uint32_t)));
+    CU(cudaMemset(st.tab, 0, S * 2 * sizeof(SkPhaseTable)));
+    CU(cudaMemset(st.chunk_count, 0, S * sizeof(uint32_t)));
+    CU(cudaMemset(st.carry, 0, S * sizeof(uint32_t)));
     if (cfg->fifo_frames) {
         CU(dalloc(&st.fifo, S * cfg->fifo_frames * cfg->max_channels));
         CU(dalloc(&st.fifo_w, S));
@@ -163,7 +164,7 @@ extern "C" void skgpu_ctx_destroy(skgpu_ctx *c) {
     cudaStreamSynchronize(c->stream);
     SlotTables &st = c->st;
     cudaFree(st.last_index); cudaFree(st.t_ratio); cudaFree(st.end_idx); cudaFree(st.chunk); cudaFree(st.channels);
-    cudaFree(st.hist); cudaFree(st.runs); cudaFree(st.n_runs); cudaFree(st.n_out);
+    cudaFree(st.hist); cudaFree(st.tab); cudaFree(st.chunk_count); cudaFree(st.carry);
     if (st.fifo) { cudaFree(st.fifo); cudaFree(st.fifo_w); cudaFree(st.fifo_r); }
     if (c->d_reset) cudaFree(c->d_reset);
     if (c->l2buf) cudaFree(c->l2buf);
@@ -273,7 +274,7 @@ extern "C" skgpu_rc skgpu_stream_get_state(skgpu_ctx *c, uint32_t slot, double *
 
 // ------------------------------------------------------------------ plan
 
-enum OpKind { OP_CONVERT = 0, OP_RESAMPLE = 1, OP_MIX = 2 };
+enum OpKind { OP_CONVERT = 0, OP_RESAMPLE = 1, OP_MIX = 2, OP_CHAIN = 3 };
 
 struct DynTable {  // small per-tick table with a ring of pinned staging buffers
     void *dev = nullptr;
@@ -303,7 +304,11 @@ struct Op {
     int rs_channels = 0;          // resample: 1 / 2 specialisation, 0 = generic
     uint64_t results_off = 0;
     bool has_fifo_inputs = false;
-    DynTable present;             // mix: per-input presence
+    uint32_t chain_F = 0;         // chain: output_frame_size
+    uint32_t chain_kb = 0;        // chain: inputs staged per batch
+    uint32_t chain_buf_floats = 0;  // chain: floats per staging buffer
+    int chain_oc = 2;             // chain: output channels specialisation
+    DynTable present;             // mix / chain: per-input presence
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev[2];
     uint32_t ev_used[2] = {0, 0};
 };
@@ -316,6 +321,9 @@ struct skgpu_plan {
     DynTable gains;
     uint32_t n_gains = 0;
     uint64_t h2d_off = 0, h2d_bytes = 0, d2h_off = 0, d2h_bytes = 0;
+    uint64_t bank_stride = 0;     // 0 = single-banked H2D
+    uint64_t tick = 0;            // ticks submitted (host mirror of d_tick)
+    uint32_t *d_tick = nullptr;
     bool finalized = false;
     cudaGraph_t graph = nullptr;
     cudaGraphExec_t graph_exec = nullptr;
@@ -368,6 +376,8 @@ extern "C" skgpu_rc skgpu_plan_create(skgpu_ctx *c, size_t arena_bytes, skgpu_pl
     cudaError_t e = cudaMalloc((void **)&p->arena, arena_bytes);
     if (e != cudaSuccess) { delete p; return fail(SKGPU_ERR_NOMEM, "cudaMalloc(%zu) for the tick arena failed: %s", arena_bytes, cudaGetErrorString(e)); }
     CU(cudaEventCreate(&p->e0)); CU(cudaEventCreate(&p->e1)); CU(cudaEventCreate(&p->e2)); CU(cudaEventCreate(&p->e3));
+    CU(cudaMalloc((void **)&p->d_tick, 16));
+    CU(cudaMemset(p->d_tick, 0, 16));
     *out = p;
     return SKGPU_OK;
 }
@@ -391,6 +401,7 @@ extern "C" void skgpu_plan_destroy(skgpu_plan *p) {
     if (p->graph_exec) cudaGraphExecDestroy(p->graph_exec);
     if (p->graph) cudaGraphDestroy(p->graph);
     cudaFree(p->arena);
+    cudaFree(p->d_tick);
     cudaEventDestroy(p->e0); cudaEventDestroy(p->e1); cudaEventDestroy(p->e2); cudaEventDestroy(p->e3);
     delete p;
 }
@@ -616,6 +627,13 @@ extern "C" skgpu_rc skgpu_plan_add_mix(skgpu_plan *p, const skgpu_mix_group *gro
     op.max_unit = std::max(mx, 1u);
     op.tiles = (op.max_unit + MIX_TILE - 1) / MIX_TILE;
     op.has_fifo_inputs = fifo;
+    {   // presence table: every input present until skgpu_plan_set_present says otherwise
+        rc = dyn_alloc(op.present, op.cap2);
+        if (rc) return rc;
+        std::vector<uint8_t> ones(op.cap2, 1);
+        rc = dyn_write(op.present, ones.data(), op.cap2);
+        if (rc) return rc;
+    }
     if (op_out) *op_out = (uint32_t)p->ops.size();
     p->ops.push_back(op);
     return SKGPU_OK;
@@ -668,18 +686,141 @@ extern "C" skgpu_rc skgpu_plan_set_gains(skgpu_plan *p, const float *gains, uint
 }
 
 extern "C" skgpu_rc skgpu_plan_set_present(skgpu_plan *p, uint32_t opi, const uint8_t *present, uint32_t n) {
-    if (!p || opi >= p->ops.size() || p->ops[opi].kind != OP_MIX) return fail(SKGPU_ERR_INVALID, "not a mix op");
+    if (!p || opi >= p->ops.size() || (p->ops[opi].kind != OP_MIX && p->ops[opi].kind != OP_CHAIN)) return fail(SKGPU_ERR_INVALID, "not a mix or chain op");
     Op &op = p->ops[opi];
     CU(cudaSetDevice(p->ctx->device));
     if (n > op.cap2) return fail(SKGPU_ERR_INVALID, "presence table larger than the input table capacity");
-    if (!op.present.valid) {
-        if (p->finalized) return fail(SKGPU_ERR_STATE, "presence table must be created before finalize");
-        skgpu_rc rc = dyn_alloc(op.present, op.cap2);
-        if (rc) return rc;
-    }
     std::vector<uint8_t> full(op.cap2, 1);
     if (n) memcpy(full.data(), present, n);
     return dyn_write(op.present, full.data(), op.cap2);
+}
+
+extern "C" skgpu_rc skgpu_plan_set_banks(skgpu_plan *p, uint64_t bank_stride) {
+    if (!p) return fail(SKGPU_ERR_INVALID, "null plan");
+    if (p->finalized) return fail(SKGPU_ERR_STATE, "plan already finalized");
+    if (bank_stride % 16) return fail(SKGPU_ERR_INVALID, "bank_stride must be a multiple of 16 bytes");
+    if (bank_stride < p->h2d_bytes) return fail(SKGPU_ERR_INVALID, "bank_stride smaller than the H2D range (call skgpu_plan_set_io first)");
+    skgpu_rc rc = check_range(p, p->h2d_off + bank_stride, p->h2d_bytes, "second input bank");
+    if (rc) return rc;
+    p->bank_stride = bank_stride;
+    return SKGPU_OK;
+}
+extern "C" uint64_t skgpu_plan_tick_count(const skgpu_plan *p) { return p ? p->tick : 0; }
+
+// ---- chain
+
+static skgpu_rc validate_chain(const skgpu_plan *p, const skgpu_chain_group *g, uint32_t ng, const skgpu_chain_input *in, uint32_t ni,
+                               uint32_t F, uint32_t *max_k, uint32_t *max_buf_floats, int *oc_out) {
+    const skgpu_ctx *c = p->ctx;
+    uint32_t mk = 0, mb = 0;
+    int oc = -1;
+    for (uint32_t i = 0; i < ni; ++i) {
+        const uint32_t slot = in[i].slot;
+        if (slot >= c->cfg.max_streams || !c->used[slot]) return fail(SKGPU_ERR_INVALID, "chain input %u: slot %u is not open", i, slot);
+        const uint32_t N = c->h_chunk[slot], C = c->h_ch[slot];
+        if (C != 1 && C != 2) return fail(SKGPU_ERR_INVALID, "chain input %u: %u channels (the fused chain handles mono and stereo)", i, C);
+        if (N < 16) return fail(SKGPU_ERR_INVALID, "chain input %u: chunk_frames %u < 16", i, N);
+        // nominal frames per chunk must equal the packet size: a packet then never spans more than two chunks
+        const double nominal = (double)N / c->h_t[slot];
+        if (std::fabs(nominal - (double)F) > 0.5)
+            return fail(SKGPU_ERR_INVALID, "chain input %u: chunk of %u frames yields %.2f output frames, not output_frame_size %u (use the unfused ops)", i, N, nominal, F);
+        if (in[i].in_off % 16) return fail(SKGPU_ERR_INVALID, "chain input %u: in_off must be 16-byte aligned", i);
+        skgpu_rc rc = check_range(p, in[i].in_off + p->bank_stride, (uint64_t)N * C * 4, "chain input (bank 1)");
+        if (rc) return rc;
+        if (in[i].gain_idx != SKGPU_NO_GAIN && in[i].gain_idx >= p->n_gains) return fail(SKGPU_ERR_INVALID, "chain input %u: gain_idx out of range", i);
+        mb = std::max(mb, (16u + N) * C);
+    }
+    for (uint32_t i = 0; i < ng; ++i) {
+        if (g[i].out_channels != 1 && g[i].out_channels != 2) return fail(SKGPU_ERR_INVALID, "chain group %u: out_channels must be 1 or 2", i);
+        if (oc == -1) oc = g[i].out_channels;
+        else if (oc != g[i].out_channels) return fail(SKGPU_ERR_INVALID, "chain op: all groups must share out_channels (split into two ops)");
+        if ((uint64_t)g[i].first_input + g[i].n_inputs > ni) return fail(SKGPU_ERR_INVALID, "chain group %u: inputs outside the input table", i);
+        if (g[i].n_inputs > (uint32_t)CH_MAX_INPUTS) return fail(SKGPU_ERR_INVALID, "chain group %u: more than %d inputs", i, CH_MAX_INPUTS);
+        if (g[i].gain_idx != SKGPU_NO_GAIN && g[i].gain_idx >= p->n_gains) return fail(SKGPU_ERR_INVALID, "chain group %u: gain_idx out of range", i);
+        const uint32_t ob = (g[i].flags & SKGPU_MIX_OUT_S16) ? 2 : 4;
+        skgpu_rc rc = check_range(p, g[i].out_off, (uint64_t)F * g[i].out_channels * ob, "chain output");
+        if (rc) return rc;
+        if (g[i].out_off % 16) return fail(SKGPU_ERR_INVALID, "chain group %u: out_off must be 16-byte aligned", i);
+        for (uint32_t j = 0; j < g[i].n_inputs; ++j) {
+            const uint32_t C = c->h_ch[in[g[i].first_input + j].slot];
+            if (C > g[i].out_channels && !(C == 2 && g[i].out_channels == 1)) return fail(SKGPU_ERR_INVALID, "chain group %u: unsupported channel mapping", i);
+        }
+        mk = std::max(mk, g[i].n_inputs);
+    }
+    *max_k = mk;
+    *max_buf_floats = (mb + 3u) & ~3u;
+    *oc_out = oc < 0 ? 2 : oc;
+    return SKGPU_OK;
+}
+
+static void chain_size_smem(Op &op, uint32_t max_k, uint32_t buf_floats) {
+    // stage up to 4 inputs per batch, fewer if a batch would not leave room for >= 4 resident CTAs per SM
+    uint32_t kb = std::max(1u, std::min(max_k, 4u));
+    while (kb > 1 && (uint64_t)kb * (buf_floats * 4ull + 2 * sizeof(SmemPhase)) > 56u * 1024u) --kb;
+    op.chain_kb = kb;
+    op.chain_buf_floats = buf_floats;
+    op.smem_bytes = (uint32_t)((((uint64_t)kb * buf_floats * 4u + 15u) & ~15ull) + (uint64_t)kb * 2u * sizeof(SmemPhase));
+}
+
+extern "C" skgpu_rc skgpu_plan_add_chain(skgpu_plan *p, const skgpu_chain_group *groups, uint32_t ng, const skgpu_chain_input *inputs, uint32_t ni,
+                                         uint32_t output_frame_size, uint64_t results_off, uint32_t *op_out) {
+    if (!p || (!groups && ng) || (!inputs && ni)) return fail(SKGPU_ERR_INVALID, "null argument");
+    if (p->finalized) return fail(SKGPU_ERR_STATE, "plan already finalized");
+    if (!p->bank_stride) return fail(SKGPU_ERR_STATE, "the fused chain needs a double-banked input range: call skgpu_plan_set_banks first");
+    static const uint32_t valid[] = {120, 240, 480, 960, 1920, 2880};  // resampler.rs:95-102
+    bool okF = false;
+    for (uint32_t v : valid) okF |= (v == output_frame_size);
+    if (!okF) return fail(SKGPU_ERR_INVALID, "output_frame_size must be a valid Opus frame size: [120, 240, 480, 960, 1920, 2880]");
+    CU(cudaSetDevice(p->ctx->device));
+    uint32_t mk = 0, mb = 0;
+    int oc = 2;
+    skgpu_rc rc = validate_chain(p, groups, ng, inputs, ni, output_frame_size, &mk, &mb, &oc);
+    if (rc) return rc;
+    rc = check_range(p, results_off, (uint64_t)std::max(ni, 1u) * sizeof(skgpu_chain_result), "chain results");
+    if (rc) return rc;
+    if (results_off % 8) return fail(SKGPU_ERR_INVALID, "results_off must be 8-byte aligned");
+    Op op;
+    op.kind = OP_CHAIN;
+    rc = op_alloc_tables(op, sizeof(skgpu_chain_group), std::max(ng, 1u), sizeof(skgpu_chain_input), std::max(ni, 1u));
+    if (rc) return rc;
+    if (ng) memcpy(op.h_tab, groups, ng * sizeof(skgpu_chain_group));
+    if (ni) memcpy(op.h_tab2, inputs, ni * sizeof(skgpu_chain_input));
+    op.n = ng;
+    op.n2 = ni;
+    op.chain_F = output_frame_size;
+    op.chain_oc = oc;
+    op.results_off = results_off;
+    chain_size_smem(op, mk, std::max(mb, 64u));
+    if (op.smem_bytes > 200u * 1024u) return fail(SKGPU_ERR_INVALID, "chain op: chunk too large for shared-memory staging (%u bytes)", op.smem_bytes);
+    {
+        rc = dyn_alloc(op.present, op.cap2);
+        if (rc) return rc;
+        std::vector<uint8_t> ones(op.cap2, 1);
+        rc = dyn_write(op.present, ones.data(), op.cap2);
+        if (rc) return rc;
+    }
+    if (op_out) *op_out = (uint32_t)p->ops.size();
+    p->ops.push_back(op);
+    return SKGPU_OK;
+}
+
+extern "C" skgpu_rc skgpu_plan_update_chain(skgpu_plan *p, uint32_t opi, const skgpu_chain_group *groups, uint32_t ng, const skgpu_chain_input *inputs, uint32_t ni) {
+    if (!p || opi >= p->ops.size() || p->ops[opi].kind != OP_CHAIN) return fail(SKGPU_ERR_INVALID, "not a chain op");
+    Op &op = p->ops[opi];
+    if (ng > op.cap || ni > op.cap2) return fail(SKGPU_ERR_INVALID, "update exceeds capacity");
+    uint32_t mk = 0, mb = 0;
+    int oc = 2;
+    skgpu_rc rc = validate_chain(p, groups, ng, inputs, ni, op.chain_F, &mk, &mb, &oc);
+    if (rc) return rc;
+    if (ng && oc != op.chain_oc) return fail(SKGPU_ERR_INVALID, "update changes the op's output channel count");
+    if (mb > op.chain_buf_floats) return fail(SKGPU_ERR_INVALID, "update has a longer chunk than the op was sized for");
+    CU(cudaStreamSynchronize(p->ctx->stream));
+    if (ng) memcpy(op.h_tab, groups, ng * sizeof(skgpu_chain_group));
+    if (ni) memcpy(op.h_tab2, inputs, ni * sizeof(skgpu_chain_input));
+    op.n = ng;
+    op.n2 = ni;
+    op.dirty = true;
+    return SKGPU_OK;
 }
 
 // ---- launch
@@ -688,15 +829,17 @@ static skgpu_rc upload_dirty(skgpu_plan *p) {
     cudaStream_t s = p->ctx->stream;
     for (auto &op : p->ops) {
         if (op.dirty) {
-            const size_t esz = op.kind == OP_CONVERT ? sizeof(skgpu_seg) : op.kind == OP_RESAMPLE ? sizeof(skgpu_rs_item) : sizeof(skgpu_mix_group);
+            const size_t esz = op.kind == OP_CONVERT ? sizeof(skgpu_seg) : op.kind == OP_RESAMPLE ? sizeof(skgpu_rs_item)
+                               : op.kind == OP_MIX ? sizeof(skgpu_mix_group) : sizeof(skgpu_chain_group);
+            const size_t esz2 = op.kind == OP_MIX ? sizeof(skgpu_mix_input) : sizeof(skgpu_chain_input);
             if (op.n) CU(cudaMemcpyAsync(op.d_tab, op.h_tab, esz * op.n, cudaMemcpyHostToDevice, s));
-            if (op.kind == OP_MIX && op.n2) CU(cudaMemcpyAsync(op.d_tab2, op.h_tab2, sizeof(skgpu_mix_input) * op.n2, cudaMemcpyHostToDevice, s));
+            if ((op.kind == OP_MIX || op.kind == OP_CHAIN) && op.n2) CU(cudaMemcpyAsync(op.d_tab2, op.h_tab2, esz2 * op.n2, cudaMemcpyHostToDevice, s));
             op.h_hdr->count = op.n;
             op.h_hdr->count2 = op.n2;
             CU(cudaMemcpyAsync(op.d_hdr, op.h_hdr, sizeof(OpHeader), cudaMemcpyHostToDevice, s));
             op.dirty = false;
         }
-        if (op.kind == OP_MIX) { skgpu_rc rc = dyn_upload(op.present, s); if (rc) return rc; }
+        if (op.kind == OP_MIX || op.kind == OP_CHAIN) { skgpu_rc rc = dyn_upload(op.present, s); if (rc) return rc; }
     }
     return dyn_upload(p->gains, s);
 }
@@ -737,12 +880,27 @@ static skgpu_rc launch_ops(skgpu_plan *p, bool time_ops) {
         } else if (op.kind == OP_RESAMPLE) {
             const skgpu_rs_item *items = (const skgpu_rs_item *)op.d_tab;
             if (time_ops) { skgpu_rc rc = op_event(op, 0, false, s); if (rc) return rc; }
-            k_phase<<<(op.cap + PHASE_THREADS - 1) / PHASE_THREADS, PHASE_THREADS, 0, s>>>(op.d_hdr, items, c->st, p->arena, op.results_off);
+            k_phase<skgpu_rs_item, false><<<(op.cap + PHASE_THREADS - 1) / PHASE_THREADS, PHASE_THREADS, 0, s>>>(op.d_hdr, items, nullptr, c->st, p->arena, op.results_off);
             CU(cudaGetLastError());
             if (time_ops) { skgpu_rc rc = op_event(op, 0, true, s); if (rc) return rc; rc = op_event(op, 1, false, s); if (rc) return rc; }
             if (op.rs_channels == 2) k_resample<2><<<op.cap, RS_THREADS, op.smem_bytes, s>>>(op.d_hdr, items, c->st, p->arena, op.smem_frames);
             else if (op.rs_channels == 1) k_resample<1><<<op.cap, RS_THREADS, op.smem_bytes, s>>>(op.d_hdr, items, c->st, p->arena, op.smem_frames);
             else k_resample<0><<<op.cap, RS_THREADS, op.smem_bytes, s>>>(op.d_hdr, items, c->st, p->arena, op.smem_frames);
+            CU(cudaGetLastError());
+            if (time_ops) { skgpu_rc rc = op_event(op, 1, true, s); if (rc) return rc; }
+        } else if (op.kind == OP_CHAIN) {
+            const uint8_t *present = op.present.valid ? (const uint8_t *)op.present.dev : nullptr;
+            const skgpu_chain_input *cin = (const skgpu_chain_input *)op.d_tab2;
+            if (time_ops) { skgpu_rc rc = op_event(op, 0, false, s); if (rc) return rc; }
+            k_phase<skgpu_chain_input, true><<<(op.cap2 + PHASE_THREADS - 1) / PHASE_THREADS, PHASE_THREADS, 0, s>>>(op.d_hdr, cin, present, c->st, p->arena, 0);
+            CU(cudaGetLastError());
+            if (time_ops) { skgpu_rc rc = op_event(op, 0, true, s); if (rc) return rc; rc = op_event(op, 1, false, s); if (rc) return rc; }
+            if (op.chain_oc == 2)
+                k_chain<2><<<op.cap, CH_THREADS, op.smem_bytes, s>>>(op.d_hdr, (const skgpu_chain_group *)op.d_tab, cin, present, gains, c->st, p->arena,
+                                                                     p->d_tick, p->bank_stride, op.chain_F, op.results_off, op.chain_kb, op.chain_buf_floats);
+            else
+                k_chain<1><<<op.cap, CH_THREADS, op.smem_bytes, s>>>(op.d_hdr, (const skgpu_chain_group *)op.d_tab, cin, present, gains, c->st, p->arena,
+                                                                     p->d_tick, p->bank_stride, op.chain_F, op.results_off, op.chain_kb, op.chain_buf_floats);
             CU(cudaGetLastError());
             if (time_ops) { skgpu_rc rc = op_event(op, 1, true, s); if (rc) return rc; }
         } else {
@@ -757,13 +915,18 @@ static skgpu_rc launch_ops(skgpu_plan *p, bool time_ops) {
             if (time_ops) { skgpu_rc rc = op_event(op, 0, true, s); if (rc) return rc; }
         }
     }
+    if (p->bank_stride) {  // bank parity of the next tick
+        k_tick_advance<<<1, 1, 0, s>>>(p->d_tick);
+        CU(cudaGetLastError());
+    }
     return SKGPU_OK;
 }
 
 extern "C" uint32_t skgpu_plan_launches_per_tick(const skgpu_plan *p) {
     if (!p) return 0;
     uint32_t n = 0;
-    for (auto &op : p->ops) n += op.kind == OP_RESAMPLE ? 2 : (op.kind == OP_MIX && op.has_fifo_inputs) ? 2 : 1;
+    for (auto &op : p->ops) n += (op.kind == OP_RESAMPLE || op.kind == OP_CHAIN) ? 2 : (op.kind == OP_MIX && op.has_fifo_inputs) ? 2 : 1;
+    if (p->bank_stride) n += 1;
     return n;
 }
 
@@ -782,6 +945,12 @@ extern "C" skgpu_rc skgpu_plan_finalize(skgpu_plan *p) {
             if (op.rs_channels == 2) CU(cudaFuncSetAttribute(k_resample<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)op.smem_bytes));
             else if (op.rs_channels == 1) CU(cudaFuncSetAttribute(k_resample<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)op.smem_bytes));
             else CU(cudaFuncSetAttribute(k_resample<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)op.smem_bytes));
+        }
+    }
+    for (auto &op : p->ops) {
+        if (op.kind == OP_CHAIN && op.smem_bytes > 40u * 1024u) {
+            if (op.chain_oc == 2) CU(cudaFuncSetAttribute(k_chain<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)op.smem_bytes));
+            else CU(cudaFuncSetAttribute(k_chain<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)op.smem_bytes));
         }
     }
     skgpu_rc rc = ctx_flush(c);
@@ -815,7 +984,8 @@ extern "C" skgpu_rc skgpu_tick_submit(skgpu_plan *p, const void *host_in, void *
     rc = upload_dirty(p);
     if (rc) return rc;
     CU(cudaEventRecord(p->e0, s));
-    if (do_h2d) CU(cudaMemcpyAsync(p->arena + p->h2d_off, host_in, p->h2d_bytes, cudaMemcpyHostToDevice, s));
+    if (do_h2d) CU(cudaMemcpyAsync(p->arena + p->h2d_off + (p->tick & 1ull) * p->bank_stride, host_in, p->h2d_bytes, cudaMemcpyHostToDevice, s));
+    p->tick++;
     CU(cudaEventRecord(p->e1, s));
     if ((flags & SKGPU_SUBMIT_GRAPH) && p->graph_exec) {
         CU(cudaGraphLaunch(p->graph_exec, s));

@@ -44,14 +44,20 @@ MIX_INPUT_DT = np.dtype([("in_off", "<u8"), ("n_frames", "<u4"), ("channels", "<
                          ("slot", "<u4")], align=True)
 MIX_GROUP_DT = np.dtype([("out_off", "<u8"), ("first_input", "<u4"), ("n_inputs", "<u4"), ("out_frames", "<u4"),
                          ("out_channels", "<u2"), ("flags", "<u2"), ("gain_idx", "<u4"), ("reserved", "<u4")], align=True)
+CHAIN_INPUT_DT = np.dtype([("in_off", "<u8"), ("slot", "<u4"), ("gain_idx", "<u4"), ("flags", "<u4"), ("reserved", "<u4")], align=True)
+CHAIN_GROUP_DT = np.dtype([("out_off", "<u8"), ("first_input", "<u4"), ("n_inputs", "<u4"), ("gain_idx", "<u4"),
+                           ("out_channels", "<u2"), ("flags", "<u2")], align=True)
+CHAIN_RESULT_DT = np.dtype([("emitted", "<u4"), ("status", "<u4")], align=True)
+assert CHAIN_INPUT_DT.itemsize == 24 and CHAIN_GROUP_DT.itemsize == 24
 assert SEG_DT.itemsize == 24 and RS_ITEM_DT.itemsize == 32 and MIX_INPUT_DT.itemsize == 24 and MIX_GROUP_DT.itemsize == 32
 
 EXPORTS = [
     "skgpu_abi_version", "skgpu_last_error", "skgpu_ctx_create", "skgpu_ctx_destroy", "skgpu_ctx_device_info",
     "skgpu_pinned_alloc", "skgpu_pinned_free", "skgpu_stream_open", "skgpu_stream_open_many", "skgpu_stream_reset",
     "skgpu_stream_close", "skgpu_stream_get_state", "skgpu_stream_max_out_frames", "skgpu_plan_create",
-    "skgpu_plan_destroy", "skgpu_plan_add_convert", "skgpu_plan_add_resample", "skgpu_plan_add_mix",
-    "skgpu_plan_update_convert", "skgpu_plan_update_resample", "skgpu_plan_update_mix", "skgpu_plan_set_io",
+    "skgpu_plan_destroy", "skgpu_plan_add_convert", "skgpu_plan_add_resample", "skgpu_plan_add_mix", "skgpu_plan_add_chain",
+    "skgpu_plan_update_convert", "skgpu_plan_update_resample", "skgpu_plan_update_mix", "skgpu_plan_update_chain",
+    "skgpu_plan_set_io", "skgpu_plan_set_banks", "skgpu_plan_tick_count",
     "skgpu_plan_set_gains", "skgpu_plan_set_present", "skgpu_plan_finalize", "skgpu_tick_submit", "skgpu_tick_wait",
     "skgpu_plan_op_time", "skgpu_plan_reset_op_times", "skgpu_plan_launches_per_tick", "skgpu_arena_upload",
     "skgpu_arena_download", "skgpu_arena_fill", "skgpu_timer_start", "skgpu_timer_stop", "skgpu_timer_elapsed_ms",
@@ -90,6 +96,10 @@ def load() -> C.CDLL:
         "skgpu_plan_add_convert": (i32, [vp, C.c_int, vp, u32, C.POINTER(u32)]),
         "skgpu_plan_add_resample": (i32, [vp, vp, u32, u64, C.POINTER(u32)]),
         "skgpu_plan_add_mix": (i32, [vp, vp, u32, vp, u32, C.POINTER(u32)]),
+        "skgpu_plan_add_chain": (i32, [vp, vp, u32, vp, u32, u32, u64, C.POINTER(u32)]),
+        "skgpu_plan_update_chain": (i32, [vp, u32, vp, u32, vp, u32]),
+        "skgpu_plan_set_banks": (i32, [vp, u64]),
+        "skgpu_plan_tick_count": (u64, [vp]),
         "skgpu_plan_update_convert": (i32, [vp, u32, vp, u32]),
         "skgpu_plan_update_resample": (i32, [vp, u32, vp, u32]),
         "skgpu_plan_update_mix": (i32, [vp, u32, vp, u32, vp, u32]),
@@ -252,6 +262,25 @@ class Plan:
         op = C.c_uint32()
         _chk(self.lib.skgpu_plan_add_mix(self.h, _ptr(groups), groups.size, _ptr(inputs), inputs.size, C.byref(op)))
         return op.value
+
+    def add_chain(self, groups: np.ndarray, inputs: np.ndarray, output_frame_size: int, results_off: int) -> int:
+        groups = np.ascontiguousarray(groups, dtype=CHAIN_GROUP_DT)
+        inputs = np.ascontiguousarray(inputs, dtype=CHAIN_INPUT_DT)
+        op = C.c_uint32()
+        _chk(self.lib.skgpu_plan_add_chain(self.h, _ptr(groups), groups.size, _ptr(inputs), inputs.size, output_frame_size,
+                                           results_off, C.byref(op)))
+        return op.value
+
+    def update_chain(self, op: int, groups: np.ndarray, inputs: np.ndarray):
+        groups = np.ascontiguousarray(groups, dtype=CHAIN_GROUP_DT)
+        inputs = np.ascontiguousarray(inputs, dtype=CHAIN_INPUT_DT)
+        _chk(self.lib.skgpu_plan_update_chain(self.h, op, _ptr(groups), groups.size, _ptr(inputs), inputs.size))
+
+    def set_banks(self, bank_stride: int):
+        _chk(self.lib.skgpu_plan_set_banks(self.h, bank_stride))
+
+    def tick_count(self) -> int:
+        return self.lib.skgpu_plan_tick_count(self.h)
 
     def update_convert(self, op: int, segs: np.ndarray):
         segs = np.ascontiguousarray(segs, dtype=SEG_DT)

@@ -465,10 +465,13 @@ def test_resampler_many_streams_16384_property(ctx):
 
 # ------------------------------------------------------------------ full chain (config #5)
 
-@pytest.mark.parametrize("k_inputs,channels,in_rate", [(1, 2, 44100), (2, 2, 44100), (3, 1, 44100), (2, 2, 48000 * 2 // 3)])
-def test_full_chain_bit_exact(k_inputs, channels, in_rate):
-    S, T = 12, 6
-    got = chain.run_chain_gpu(S, k_inputs, T, seed=3, in_rate=in_rate, channels=channels)
+@pytest.mark.parametrize("fused", [True, False])
+@pytest.mark.parametrize("k_inputs,channels,in_rate", [(1, 2, 44100), (2, 2, 44100), (3, 1, 44100), (2, 2, 32000), (6, 2, 44100)])
+def test_full_chain_bit_exact(k_inputs, channels, in_rate, fused):
+    """fused k_chain (lagged recompute from the double-banked input arena) and the unfused ops
+    (k_resample -> device ring -> k_mix) must both reproduce the oracle's s16 bytes."""
+    S, T = 12, 7
+    got = chain.run_chain_gpu(S, k_inputs, T, seed=3, in_rate=in_rate, channels=channels, fused=fused)
     want = chain_ref.run_chain_oracle(S, k_inputs, T, seed=3, in_rate=in_rate, channels=channels)
     for t in range(T):
         assert np.array_equal(got[t], want[t]), f"tick {t}: {(got[t] != want[t]).sum()} s16 samples differ"
@@ -476,10 +479,92 @@ def test_full_chain_bit_exact(k_inputs, channels, in_rate):
 
 
 def test_full_chain_graph_equals_stream_launch():
-    a = chain.run_chain_gpu(8, 2, 5, seed=9, graph=False)
-    b = chain.run_chain_gpu(8, 2, 5, seed=9, graph=True)
+    a = chain.run_chain_gpu(8, 2, 6, seed=9, graph=False)
+    b = chain.run_chain_gpu(8, 2, 6, seed=9, graph=True)
     for x, y in zip(a, b):
         assert np.array_equal(x, y)
+
+
+def test_fused_chain_state_and_results():
+    """carry / emission bookkeeping of the fused kernel: 44.1k->48k, first chunk yields 954 < 960 frames (no packet),
+    afterwards one packet per tick with 954 carried frames recomputed from the previous bank."""
+    ct = chain.ChainTick(4, 2, seed=5)
+    try:
+        for t in range(4):
+            ct.tick(synth.tone_streams(5, t, ct.n_streams, ct.chunk, 2, 44100))
+            res = ct.results()
+            assert np.all(res["status"] == 0)
+            assert np.all(res["emitted"] == (0 if t == 0 else 1))
+        assert ct.plan.tick_count() == 4
+    finally:
+        ct.close()
+
+
+def test_fused_chain_absent_stream_protocol():
+    """A stream that delivers nothing in a tick is marked absent and its previous chunk is repeated by the host so
+    the other bank stays valid (include/skgpu_batch.h, chain protocol). The oracle session simply gets no packet."""
+    S, K, T = 6, 2, 8
+    ct = chain.ChainTick(S, K, seed=11)
+    rng = np.random.default_rng(4)
+    import collections
+    nodes = [sko.ResamplerNode(48000, chunk_frames=ct.chunk, output_frame_size=960) for _ in range(S * K)]
+    queues = [collections.deque() for _ in range(S * K)]
+    last = np.zeros((S * K, ct.chunk * 2), np.float32)
+    n_sent = np.zeros(S * K, dtype=int)
+    try:
+        for t in range(T):
+            present = (rng.random(S * K) < 0.75).astype(np.uint8) if t >= 2 else np.ones(S * K, np.uint8)
+            x = np.empty_like(last)
+            for s in range(S * K):
+                if present[s]:
+                    x[s] = synth.tone_streams(11 + s, n_sent[s], 1, ct.chunk, 2, 44100)[0]
+                    n_sent[s] += 1
+                    last[s] = x[s]
+                else:
+                    x[s] = last[s]                      # host repeats the previous chunk bytes
+            ct.plan.set_present(ct.op_chain, present)
+            got = ct.tick(x)
+            want = np.zeros_like(got)
+            for s in range(S * K):
+                if present[s]:
+                    nodes[s].out.clear()
+                    nodes[s].push(44100, 2, x[s])
+                    for pkt in nodes[s].out:
+                        queues[s].append(sko.gain(pkt["samples"], float(ct.in_gains[s])))
+            for g in range(S):
+                frames = []
+                for i in range(K):
+                    q = queues[g * K + i]
+                    if q:
+                        frames.append((q.popleft(), 2, True))
+                want[g] = sko.gain_f32_to_s16(sko.mix_clocked(frames, 2, 960), float(ct.master_gains[g]))
+            assert np.array_equal(got, want), f"tick {t}"
+            assert np.all(ct.results()["status"] == 0)
+    finally:
+        ct.close()
+
+
+def test_chain_rejects_ineligible_streams(ctx):
+    """48k -> 16k with chunk 960 yields 320 frames per chunk: a 960-frame packet would span 3 chunks -> unfused ops only"""
+    slot = ctx.stream_open(48000, 16000, 960, 2)
+    plan = L.Plan(ctx, 1 << 20)
+    try:
+        plan.set_io(0, 960 * 8, 65536, 4096)
+        plan.set_banks(32768)
+        cin = np.zeros(1, dtype=L.CHAIN_INPUT_DT)
+        cin["slot"] = slot
+        cin["gain_idx"] = L.SKGPU_NO_GAIN
+        cg = np.zeros(1, dtype=L.CHAIN_GROUP_DT)
+        cg["out_off"] = 65536
+        cg["n_inputs"] = 1
+        cg["gain_idx"] = L.SKGPU_NO_GAIN
+        cg["out_channels"] = 2
+        with pytest.raises(L.SkgpuError) as e:
+            plan.add_chain(cg, cin, 960, 131072)
+        assert "use the unfused ops" in e.value.msg
+    finally:
+        plan.destroy()
+        ctx.stream_close(slot)
 
 
 def test_smoke_entry():
