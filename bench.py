@@ -33,6 +33,8 @@ sys.path.insert(0, ROOT)
 
 IN_RATE, OUT_RATE, CHANNELS, K_INPUTS = 44100, 48000, 2, 2
 TICK_MS = 20.0
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture (profiles/), or None
+TRAFFIC_NCU: dict = {}
 METRIC = "concurrent real-time 48 kHz stereo sessions (resample->mix->gain->s16, 20 ms ticks)"
 UNIT = "sessions"
 
@@ -175,13 +177,15 @@ def run_gpu(args) -> None:
         return float(t.item())
 
     S = args.sessions
-    ct = chain.ChainTick(S, K_INPUTS, in_rate=IN_RATE, channels=CHANNELS, device=local_rank, seed=rank)
+    ct = chain.ChainTick(S, K_INPUTS, in_rate=IN_RATE, channels=CHANNELS, device=local_rank, seed=rank, fused=not args.unfused)
     plan, ctx = ct.plan, ct.ctx
     # synthetic input: a tick of noise for every stream of every session on this rank
     x = synth.noise_streams(1000 + rank, 0, ct.n_streams, ct.chunk, CHANNELS)
     ct.host_in[:] = x.reshape(-1)
     del x
     plan.upload(0, ct.host_in)  # resident in HBM for the device-timed region
+    if ct.fused:
+        plan.upload(ct.bank_stride, ct.host_in)  # both input banks (the fused kernel reads the previous tick's bank)
 
     # ---- device-resident region: W warm-up + K timed ticks, CUDA events on the library's stream
     dev_flags = L.SUBMIT_NO_H2D | L.SUBMIT_NO_D2H | L.SUBMIT_TIME_OPS
@@ -202,9 +206,15 @@ def run_gpu(args) -> None:
     barrier()
     dev_ms = max_over_ranks(dev_ms)
     ms_per_step = dev_ms / args.steps
-    phase_ms, _ = plan.op_time(ct.op_rs, 0)
-    rs_ms, n_rs = plan.op_time(ct.op_rs, 1)
-    mix_ms, _ = plan.op_time(ct.op_mix, 0)
+    if ct.fused:
+        phase_ms, _ = plan.op_time(ct.op_chain, 0)
+        main_ms, n_main = plan.op_time(ct.op_chain, 1)
+        kernels_ms = {"k_phase": phase_ms, "k_chain": main_ms}
+    else:
+        phase_ms, _ = plan.op_time(ct.op_rs, 0)
+        main_ms, n_main = plan.op_time(ct.op_rs, 1)
+        mix_ms, _ = plan.op_time(ct.op_mix, 0)
+        kernels_ms = {"k_phase": phase_ms, "k_resample": main_ms, "k_mix+k_fifo_commit": mix_ms}
 
     # ---- end-to-end region: every step copies its inputs from pinned host memory and reads the s16 result back
     for _ in range(max(1, min(args.warmup, 3))):
@@ -233,11 +243,15 @@ def run_gpu(args) -> None:
             peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (of measured)"
         else:
             peak, peak_src = 6650.0, "B200_PROFILING.md fallback 6.65 TB/s (of fallback)"
-        # dominant kernel = k_resample: in + out + state r/w per stream-tick (15,008 B for 44.1k->48k stereo)
-        n_out = 960
-        rs_bytes = ct.n_streams * (ct.in_stride + n_out * CHANNELS * 4 + 2 * (8 + 16 * CHANNELS * 4))
-        achieved = rs_bytes / (rs_ms * 1e-3) / 1e9 if rs_ms > 0 else 0.0
         chain_bytes = ct.algorithmic_bytes_per_tick()
+        if ct.fused:
+            # dominant kernel = k_chain: the fully fused algorithmic bytes of SURVEY 8(d) / BASELINE.md:
+            # per session-tick K x (7056 in + 272 state r/w) + 3840 s16 out = 18,496 B (K = 2)
+            dom_name, dom_bytes = "k_chain<2>", chain_bytes
+        else:
+            # dominant kernel = k_resample: in + out + state r/w per stream-tick (15,008 B for 44.1k->48k stereo)
+            dom_name, dom_bytes = "k_resample<2>", ct.n_streams * (ct.in_stride + 960 * CHANNELS * 4 + 2 * (8 + 16 * CHANNELS * 4))
+        achieved = dom_bytes / (main_ms * 1e-3) / 1e9 if main_ms > 0 else 0.0
         cores = len(os.sched_getaffinity(0))
         cpu_sessions, cpu_ticks = args.ref_sessions, 50
         cpu_chain(cpu_sessions, 2, cores)
@@ -247,17 +261,17 @@ def run_gpu(args) -> None:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-            "data": "synthetic", "config": workload_config(S, world),
+            "data": "synthetic", "config": dict(workload_config(S, world), path="fused k_chain" if ct.fused else "unfused k_resample + k_mix"),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": ct.in_bytes * world, "d2h_bytes_per_step": ct.out_bytes * world,
                     "ms_per_step": e2e_ms_per_step, "last_tick_ms": {"h2d": timing.h2d_ms, "kernels": timing.kernels_ms, "d2h": timing.d2h_ms},
                     "h2d_gbs_per_gpu": ct.in_bytes / (timing.h2d_ms * 1e-3) / 1e9 if timing.h2d_ms > 0 else None,
                     "d2h_gbs_per_gpu": ct.out_bytes / (timing.d2h_ms * 1e-3) / 1e9 if timing.d2h_ms > 0 else None},
             "gpu_launches": plan.launches_per_tick() * args.steps * 2,
             "clocks": clk,
-            "roofline": {"bound": "hbm", "kernel": "k_resample<2>", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None, "algorithmic_bytes_per_launch": rs_bytes,
-                         "avg_launch_ms": rs_ms, "launches_timed": n_rs, "peak_source": peak_src},
-            "kernels_ms": {"k_phase": phase_ms, "k_resample": rs_ms, "k_mix+k_fifo_commit": mix_ms},
+            "roofline": {"bound": "hbm", "kernel": dom_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": TRAFFIC_NCU.get(dom_name), "algorithmic_bytes_per_launch": dom_bytes,
+                         "avg_launch_ms": main_ms, "launches_timed": n_main, "peak_source": peak_src},
+            "kernels_ms": kernels_ms,
             "chain": {"algorithmic_bytes_per_tick": chain_bytes, "achieved_gbs": chain_bytes / (ms_per_step * 1e-3) / 1e9,
                       "frac_of_peak": chain_bytes / (ms_per_step * 1e-3) / 1e9 / peak,
                       "device_ms_per_tick": ms_per_step, "latency_budget_ms": 2.0},
@@ -278,6 +292,7 @@ def main() -> None:
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--sessions", type=int, default=65536, help="sessions per GPU (weak scaling)")
+    ap.add_argument("--unfused", action="store_true", help="use the general unfused ops (k_resample -> ring -> k_mix)")
     ap.add_argument("--ref-sessions", type=int, default=8192, help="bounded session sample of the CPU arm")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":

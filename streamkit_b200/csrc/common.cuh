@@ -22,17 +22,33 @@ struct OpHeader {       // lives in device memory so a captured graph sees table
     uint32_t pad[2];
 };
 
-struct SlotTables {     // SoA per-stream state + configuration, all device pointers
-    double *last_index;     // rubato self.last_index (for the NEXT chunk)
-    double *t_ratio;        // 1.0 / resample_ratio
-    int32_t *end_idx;       // chunk - 9 - ceil(t)
-    uint32_t *chunk;        // chunk_frames
-    uint32_t *channels;
+struct __align__(16) SlotRec {  // everything a kernel needs to know about one resampler stream: ONE 64-byte load
+    double t_ratio;        // 1.0 / resample_ratio                                  (host config)
+    double last_index;     // rubato self.last_index for the NEXT chunk             (k_phase)
+    uint32_t chunk;        // chunk_frames                                          (host config)
+    uint32_t channels;     //                                                       (host config)
+    uint32_t chunk_count;  // chunks processed so far                               (k_phase)
+    uint32_t carry;        // chain op: frames produced but not yet emitted in a packet (k_chain)
+    uint32_t n_out[2];     // frames produced by the two most recent chunks, by (chunk number & 1)
+    uint16_t n_prefix[2];  // phase-table sizes of those chunks
+    uint16_t n_runs[2];
+    int32_t end_idx;       // chunk - 9 - ceil(t)                                   (host config)
+    uint32_t overflow;     // bit (chunk number & 1): phase table overflowed
+    uint32_t pad;
+};
+static_assert(sizeof(SlotRec) == 64, "SlotRec must be one 64-byte record");
+
+struct SlotCfgUpload {     // host -> device (re)configuration of one slot (k_config_slots)
+    double t_ratio;
+    uint32_t slot, chunk, channels;
+    int32_t end_idx;
+};
+
+struct SlotTables {     // per-stream state + configuration, all device pointers
+    SlotRec *rec;           // [slot]
     float *hist;            // [slot][16 * max_channels]: the 16 frames before the oldest chunk that still has
                             // unconsumed output (plain resample op: before the next chunk; chain op: before the previous one)
     SkPhaseTable *tab;      // [slot][2]: phase tables of the two most recent chunks, indexed by (chunk number & 1)
-    uint32_t *chunk_count;  // chunks processed so far
-    uint32_t *carry;        // chain op: resampled frames produced but not yet emitted in a packet
     float *fifo;            // [slot][fifo_frames * max_channels] (may be null): unfused re-framing ring
     unsigned long long *fifo_w;  // total frames ever written
     unsigned long long *fifo_r;  // total frames ever consumed
@@ -122,11 +138,12 @@ struct SmemPhase {
     uint32_t n_out, n_prefix, n_runs, overflow;
 };
 
-// cooperative copy global -> smem by `nthreads` threads (tid in [0, nthreads)); caller syncs afterwards
-__device__ __forceinline__ void load_phase_table(SmemPhase *dst, const SkPhaseTable *src, uint32_t tid, uint32_t nthreads) {
-    const uint4 hdr = *reinterpret_cast<const uint4 *>(src);  // n_out, n_prefix, n_runs, overflow (broadcast load)
-    const uint32_t np = min(hdr.y, (uint32_t)SK_PREFIX_MAX), nr = min(hdr.z, (uint32_t)SK_RUNS_MAX);
-    if (tid == 0) { dst->n_out = hdr.x; dst->n_prefix = np; dst->n_runs = nr; dst->overflow = hdr.w; }
+// cooperative copy global -> smem by `nthreads` threads (tid in [0, nthreads)); sizes come from the slot record,
+// so no dependent header load is needed. Caller syncs afterwards.
+__device__ __forceinline__ void load_phase_table(SmemPhase *dst, const SkPhaseTable *src, uint32_t n_out, uint32_t n_prefix,
+                                                 uint32_t n_runs, uint32_t tid, uint32_t nthreads) {
+    const uint32_t np = min(n_prefix, (uint32_t)SK_PREFIX_MAX), nr = min(n_runs, (uint32_t)SK_RUNS_MAX);
+    if (tid == 0) { dst->n_out = n_out; dst->n_prefix = np; dst->n_runs = nr; dst->overflow = 0; }
     const uint2 *sp = reinterpret_cast<const uint2 *>(src->prefix);
     uint2 *dp = reinterpret_cast<uint2 *>(dst->prefix);
     for (uint32_t i = tid; i < np; i += nthreads) dp[i] = sp[i];
@@ -153,18 +170,47 @@ __device__ __forceinline__ void phase_split(double x, uint32_t &p, float &frac) 
     p = (uint32_t)(fl + 16);
 }
 
-// (re)initialises stream slots: fresh FastFixedIn = zero history, last_index = -4.0 (rubato new())
-__global__ void k_reset_slots(const uint32_t *__restrict__ slots, uint32_t n, SlotTables st) {
+// idx of 4 consecutive outputs k0..k0+3 (the caller uses the first n). Inside one run consecutive members differ by
+// exactly delta (all values are representable multiples of the binade's unit), so 1 fma + 3 adds; otherwise 4 lookups.
+__device__ __forceinline__ void phase_eval4(const SmemPhase *T, double t, uint32_t k0, uint32_t n, double *x) {
+    if (k0 >= T->n_prefix && T->n_runs > 0u) {
+        uint32_t r = T->n_runs - 1u;
+        while (r > 0u && T->runs[r].k_a > k0) --r;
+        const SkRun rn = T->runs[r];
+        if (k0 + 3u < rn.k_e) {
+            x[0] = __fma_rn((double)(k0 - rn.k_a), rn.delta, rn.x_a);
+            x[1] = __dadd_rn(x[0], rn.delta);
+            x[2] = __dadd_rn(x[1], rn.delta);
+            x[3] = __dadd_rn(x[2], rn.delta);
+            return;
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) x[i] = phase_eval_smem(T, t, k0 + min((uint32_t)i, n - 1u));
+}
+
+// (re)configures stream slots from the host: fresh FastFixedIn = zero history, last_index = -4.0 (rubato new())
+__global__ void k_config_slots(const SlotCfgUpload *__restrict__ cfgs, uint32_t n, SlotTables st) {
     const uint32_t i = blockIdx.x;
     if (i >= n) return;
-    const uint32_t slot = slots[i];
+    const SlotCfgUpload c = cfgs[i];
+    const uint32_t slot = c.slot;
     for (uint32_t s = threadIdx.x; s < 16u * st.max_channels; s += blockDim.x) st.hist[(size_t)slot * 16u * st.max_channels + s] = 0.0f;
     if (threadIdx.x == 0) {
-        st.last_index[slot] = -4.0;
-        st.chunk_count[slot] = 0;
-        st.carry[slot] = 0;
-        st.tab[(size_t)slot * 2].n_out = 0;
-        st.tab[(size_t)slot * 2 + 1].n_out = 0;
+        SlotRec r;
+        r.t_ratio = c.t_ratio;
+        r.last_index = -4.0;
+        r.chunk = c.chunk;
+        r.channels = c.channels;
+        r.chunk_count = 0;
+        r.carry = 0;
+        r.n_out[0] = r.n_out[1] = 0;
+        r.n_prefix[0] = r.n_prefix[1] = 0;
+        r.n_runs[0] = r.n_runs[1] = 0;
+        r.end_idx = c.end_idx;
+        r.overflow = 0;
+        r.pad = 0;
+        st.rec[slot] = r;
         if (st.fifo_w) { st.fifo_w[slot] = 0ull; st.fifo_r[slot] = 0ull; }
     }
 }

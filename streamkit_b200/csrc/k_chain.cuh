@@ -15,20 +15,28 @@
 // input arena. HBM traffic per stream-tick is one pass over one input chunk (+ 2 x 128 B history state and a
 // ~0.3 KB phase table), i.e. the "fully fused" algorithmic bytes of SURVEY 8(d).
 //
-// One CTA per session. Inputs are staged (history ++ previous chunk) by TMA bulk copies, up to `kb` inputs per
-// batch; each thread owns 4 consecutive output frames and adds the inputs sequentially in the reference's
-// summation order (f32 addition is not associative).
+// Shape: PERSISTENT, WARP-SPECIALISED CTAs (a few per SM, looping over sessions):
+//   warp 0  (producer)  resolves the next session (descriptors -> 64-byte slot records -> emission / carry
+//                       bookkeeping -> summation order) and issues TMA bulk copies (history, previous chunk,
+//                       phase tables) into a 2-stage shared-memory ring, signalling an mbarrier per stage;
+//   warps 1-8 (consumers) wait on the stage, interpolate 4 consecutive output frames per thread from shared
+//                       memory, add the inputs SEQUENTIALLY in the reference's order (f32 addition is not
+//                       associative), and store 16 bytes of s16 per thread.
+// The producer runs ahead, so the chain of dependent global loads that precedes every session's TMA is
+// hidden behind the previous session's arithmetic.
 #pragma once
 #include "common.cuh"
 
 namespace skgpu {
 
-constexpr int CH_THREADS = 256;
-constexpr int CH_MAX_INPUTS = 64;   // inputs per session
-constexpr int CH_FPT = 4;           // output frames per thread per iteration
-constexpr int CH_MAX_ITERS = 3;     // F <= 3072 (largest valid output_frame_size is 2880)
+constexpr int CH_CONSUMERS = 256;                 // 8 consumer warps
+constexpr int CH_THREADS = CH_CONSUMERS + 32;     // + producer warp (warp 0)
+constexpr int CH_STAGES = 2;
+constexpr int CH_MAX_INPUTS = 64;                 // inputs per session
+constexpr int CH_FPT = 4;                         // output frames per consumer thread per iteration
+constexpr int CH_MAX_KB = 4;                      // inputs staged per batch
 
-struct ChainIn {            // per-tick view of one input of the session (shared memory)
+struct ChainIn {            // per-tick view of one input of the session
     const float *prev_g;    // previous chunk (other bank)
     const float *cur_g;     // current chunk
     float *hist_g;          // st.hist of the slot: 16 frames before the previous chunk
@@ -37,7 +45,19 @@ struct ChainIn {            // per-tick view of one input of the session (shared
     uint32_t has_gain;
     uint32_t slot, N, ch;
     uint32_t carry, n_prev, n_cur, count;
-    uint32_t present, emit, unique, status, new_carry;
+    uint32_t emit, unique, par_prev, par_cur;
+};
+
+struct ChainStage {         // header of one pipeline stage (shared memory)
+    uint64_t out_off;
+    float master_gain;
+    uint32_t has_master;
+    uint32_t flags;
+    uint32_t nb;            // inputs in this batch
+    uint32_t first, last;   // first / last batch of the session
+    uint32_t has_base;      // the first input of the first batch is the base frame (mixer.rs:960-972)
+    uint32_t stop;          // no more work
+    ChainIn in[CH_MAX_KB];
 };
 
 template <int OC>
@@ -60,230 +80,322 @@ __device__ __forceinline__ void chain_accumulate(float *acc, const float *y, uin
     for (int c = 0; c < OC; ++c) acc[c] = is_base ? v[c] : __fadd_rn(acc[c], v[c]);
 }
 
-template <int OC>  // output channels: 1 or 2
+// one input of one session, 4 consecutive output frames j0..j0+3 of this thread
+template <int OC, int SC>
+__device__ __forceinline__ void chain_input(const ChainIn &in, const float *A, const SmemPhase *Tp, const SmemPhase *Tc, uint32_t F,
+                                            uint32_t j0, float *acc, bool is_base) {
+    const uint32_t NA = (in.count >= 2u) ? in.N : 0u;  // frames of the previous chunk present in A (after 16 history frames)
+    const bool has_gain = in.has_gain != 0;
+    if (j0 + CH_FPT <= in.carry && j0 + CH_FPT <= F) {
+        // all four frames were produced by the PREVIOUS chunk: recompute them from (history ++ previous chunk)
+        double x[4];
+        phase_eval4(Tp, in.t, in.n_prev - in.carry + j0, 4u, x);
+#pragma unroll
+        for (int f = 0; f < CH_FPT; ++f) {
+            uint32_t p;
+            float frac;
+            phase_split(x[f], p, frac);
+            float y[2];
+            if (SC == 2) {
+                const float2 y0 = *reinterpret_cast<const float2 *>(A + 2u * p);
+                const float2 y1 = *reinterpret_cast<const float2 *>(A + 2u * p + 2u);
+                y[0] = interp_lin(frac, y0.x, y1.x);
+                y[1] = interp_lin(frac, y0.y, y1.y);
+            } else {
+                y[0] = interp_lin(frac, A[p], A[p + 1u]);
+                y[1] = 0.0f;
+            }
+            chain_accumulate<OC>(acc + f * OC, y, SC, in.gain, has_gain, is_base);
+        }
+        return;
+    }
+    // boundary / tail threads: frame by frame
+#pragma unroll
+    for (int f = 0; f < CH_FPT; ++f) {
+        const uint32_t j = j0 + f;
+        if (j >= F) break;
+        uint32_t p;
+        float frac;
+        float y[2] = {0.0f, 0.0f};
+        if (j < in.carry) {
+            phase_split(phase_eval_smem(Tp, in.t, in.n_prev - in.carry + j), p, frac);
+#pragma unroll
+            for (int c = 0; c < SC; ++c) y[c] = interp_lin(frac, A[p * SC + c], A[(p + 1u) * SC + c]);
+        } else {
+            // produced by the CURRENT chunk: its history is the tail of the previous chunk (in A); positions beyond it
+            // are read from the current chunk in HBM (a handful of frames in steady state)
+            phase_split(phase_eval_smem(Tc, in.t, j - in.carry), p, frac);
+#pragma unroll
+            for (int c = 0; c < SC; ++c) {
+                const float y0 = (p < 16u) ? A[(NA + p) * SC + c] : in.cur_g[(size_t)(p - 16u) * SC + c];
+                const float y1 = (p + 1u < 16u) ? A[(NA + p + 1u) * SC + c] : in.cur_g[(size_t)(p + 1u - 16u) * SC + c];
+                y[c] = interp_lin(frac, y0, y1);
+            }
+        }
+        chain_accumulate<OC>(acc + f * OC, y, SC, in.gain, has_gain, is_base);
+    }
+}
+
+template <int OC, int ITERS>  // output channels (1 | 2); ITERS = ceil(F / 1024)
 __global__ void __launch_bounds__(CH_THREADS) k_chain(const OpHeader *__restrict__ hdr, const skgpu_chain_group *__restrict__ groups,
                                                       const skgpu_chain_input *__restrict__ inputs, const uint8_t *__restrict__ present,
                                                       const float *__restrict__ gains, SlotTables st, uint8_t *__restrict__ arena,
                                                       const uint32_t *__restrict__ tick, uint64_t bank_stride, uint32_t F,
                                                       uint64_t results_off, uint32_t kb, uint32_t buf_floats) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
-    __shared__ __align__(8) uint64_t bar;
-    __shared__ ChainIn s_in[CH_MAX_INPUTS];
+    __shared__ __align__(8) uint64_t bar_full[CH_STAGES], bar_empty[CH_STAGES];
+    __shared__ __align__(16) ChainStage s_stage[CH_STAGES];
+    __shared__ ChainIn s_res[CH_MAX_INPUTS];     // producer scratch: resolved inputs of the session being prepared
     __shared__ uint8_t s_order[CH_MAX_INPUTS];
-    __shared__ uint32_t s_m, s_has_base;
 
-    const uint32_t g_i = blockIdx.x;
-    if (g_i >= hdr->count) return;
-    const skgpu_chain_group grp = groups[g_i];
-    const uint32_t K = min(grp.n_inputs, (uint32_t)CH_MAX_INPUTS);
-    const uint32_t parity = tick[0] & 1u;
+    // dynamic smem per stage: kb staging buffers [(16 + N) * ch floats], then kb x 2 phase tables
+    const size_t buf_bytes = (((size_t)kb * buf_floats * 4u) + 15u) & ~(size_t)15u;
+    const size_t stage_bytes = buf_bytes + (size_t)kb * 2u * sizeof(SmemPhase);
+    const uint32_t n_groups = hdr->count;
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
 
-    // dynamic smem: kb staging buffers [(16 + N) * ch floats] then kb x 2 phase tables
-    float *s_buf = reinterpret_cast<float *>(smem_raw);
-    SmemPhase *s_tab = reinterpret_cast<SmemPhase *>(smem_raw + (((size_t)kb * buf_floats * 4u + 15u) & ~(size_t)15u));
-
-    // ---- resolve the session's inputs (one thread per input): slot state, emission decision, carry bookkeeping
-    if (threadIdx.x < K) {
-        const uint32_t gi = grp.first_input + threadIdx.x;
-        const skgpu_chain_input in = inputs[gi];
-        ChainIn r;
-        r.slot = in.slot;
-        r.N = st.chunk[in.slot];
-        r.ch = st.channels[in.slot];
-        r.t = st.t_ratio[in.slot];
-        r.count = st.chunk_count[in.slot];   // k_phase already counted the current chunk
-        r.carry = st.carry[in.slot];
-        r.present = present ? (present[gi] != 0) : 1u;
-        r.has_gain = in.gain_idx != SKGPU_NO_GAIN;
-        r.gain = r.has_gain ? gains[in.gain_idx] : 1.0f;
-        r.unique = (in.flags & SKGPU_MIX_IN_UNIQUE) ? 1u : 0u;
-        r.cur_g = reinterpret_cast<const float *>(arena + in.in_off + (uint64_t)parity * bank_stride);
-        r.prev_g = reinterpret_cast<const float *>(arena + in.in_off + (uint64_t)(1u - parity) * bank_stride);
-        r.hist_g = st.hist + (size_t)in.slot * 16u * st.max_channels;
-        const SkPhaseTable *tab = st.tab + (size_t)in.slot * 2u;
-        r.n_cur = (r.present && r.count >= 1u) ? tab[(r.count - 1u) & 1u].n_out : 0u;
-        r.n_prev = (r.count >= 2u) ? tab[(r.count - 2u) & 1u].n_out : 0u;
-        r.status = 0;
-        r.emit = 0;
-        r.new_carry = r.carry;
-        if (r.present) {
-            if (r.carry > r.n_prev) r.status |= 4u;                 // carried frames span more than one chunk: unsupported
-            const uint32_t avail = r.carry + r.n_cur;
-            r.emit = (avail >= F && !(r.status & 4u)) ? 1u : 0u;    // a whole F-frame packet is ready (resampler.rs:425-428)
-            r.new_carry = r.emit ? avail - F : avail;
-            if (r.new_carry > r.n_cur) r.status |= 1u;               // backlog: a second packet is pending / carry spans two chunks
-        }
-        s_in[threadIdx.x] = r;
-    }
-    __syncthreads();
-    // ---- summation order over the inputs that deliver a packet: base selection + swap_remove (mixer.rs:960-980)
     if (threadIdx.x == 0) {
-        uint32_t m = 0;
-        int base = -1, base_unique = -1;
-        for (uint32_t j = 0; j < K; ++j) {
-            if (!s_in[j].emit) continue;
-            if (s_in[j].ch == (uint32_t)OC) {  // packet already has the output shape (F frames x OC channels)
-                const int u = (int)s_in[j].unique;
-                if (u >= base_unique) { base = (int)m; base_unique = u; }
-            }
-            s_order[m++] = (uint8_t)j;
+        for (int s = 0; s < CH_STAGES; ++s) {
+            mbar_init(&bar_full[s], 1);
+            mbar_init(&bar_empty[s], CH_CONSUMERS / 32);
         }
-        if (base >= 0 && m > 0) {
-            const uint8_t b = s_order[base];
-            s_order[base] = s_order[m - 1];
-            for (uint32_t q = m - 1; q > 0; --q) s_order[q] = s_order[q - 1];
-            s_order[0] = b;
-        }
-        s_m = m;
-        s_has_base = (base >= 0) ? 1u : 0u;
-        mbar_init(&bar, 1);
         mbar_fence_init();
     }
     __syncthreads();
-    const uint32_t m = s_m;
-    const bool has_base = s_has_base != 0;
 
-    float acc[CH_MAX_ITERS][CH_FPT * OC];
-#pragma unroll
-    for (int it = 0; it < CH_MAX_ITERS; ++it)
-#pragma unroll
-        for (int e = 0; e < CH_FPT * OC; ++e) acc[it][e] = 0.0f;  // vec![0.0f32; output_size] when there is no base frame
-
-    uint32_t phase_bit = 0;
-    for (uint32_t b0 = 0; b0 < m; b0 += kb) {
-        const uint32_t nb = min(kb, m - b0);
-        if (b0 > 0) {
-            __syncthreads();  // previous batch fully consumed before its buffers are overwritten
-            if (threadIdx.x == 0) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic reads -> async writes
-        }
-        // ---- stage (history ++ previous chunk) of every input of the batch with TMA bulk copies
-        // (chunks whose byte size is not a multiple of 16, e.g. mono 882 frames, are copied cooperatively instead)
-        if (threadIdx.x == 0) {
-            uint32_t total = 0;
-            for (uint32_t q = 0; q < nb; ++q) {
-                const ChainIn &in = s_in[s_order[b0 + q]];
-                const uint32_t cb = (in.count >= 2u) ? in.N * in.ch * 4u : 0u;
-                total += 16u * in.ch * 4u + ((cb & 15u) ? 0u : cb);
+    if (warp == 0) {
+        // =============================================================== producer warp
+        const uint32_t parity = tick[0] & 1u;
+        uint32_t stage = 0, ephase = 1;  // waiting on parity 1 of a fresh mbarrier returns immediately
+        for (uint32_t g_i = blockIdx.x; g_i < n_groups; g_i += gridDim.x) {
+            const skgpu_chain_group grp = groups[g_i];
+            const uint32_t K = min(grp.n_inputs, (uint32_t)CH_MAX_INPUTS);
+            // ---- resolve inputs (one lane per input): slot record, emission decision, carry bookkeeping, results
+            for (uint32_t j = lane; j < K; j += 32u) {
+                const uint32_t gi = grp.first_input + j;
+                const skgpu_chain_input in = inputs[gi];
+                SlotRec *recp = st.rec + in.slot;
+                const SlotRec rec = *recp;
+                ChainIn r;
+                r.slot = in.slot;
+                r.N = rec.chunk;
+                r.ch = rec.channels;
+                r.t = rec.t_ratio;
+                r.count = rec.chunk_count;   // k_phase already counted the current chunk
+                r.carry = rec.carry;
+                const uint32_t pres = present ? (present[gi] != 0) : 1u;
+                r.has_gain = in.gain_idx != SKGPU_NO_GAIN;
+                r.gain = r.has_gain ? gains[in.gain_idx] : 1.0f;
+                r.unique = (in.flags & SKGPU_MIX_IN_UNIQUE) ? 1u : 0u;
+                r.cur_g = reinterpret_cast<const float *>(arena + in.in_off + (uint64_t)parity * bank_stride);
+                r.prev_g = reinterpret_cast<const float *>(arena + in.in_off + (uint64_t)(1u - parity) * bank_stride);
+                r.hist_g = st.hist + (size_t)in.slot * 16u * st.max_channels;
+                r.par_cur = (r.count - 1u) & 1u;
+                r.par_prev = r.count & 1u;   // == (count - 2) & 1
+                r.n_cur = (pres && r.count >= 1u) ? rec.n_out[r.par_cur] : 0u;
+                r.n_prev = (r.count >= 2u) ? rec.n_out[r.par_prev] : 0u;
+                uint32_t status = 0;
+                r.emit = 0;
+                uint32_t new_carry = r.carry;
+                if (pres) {
+                    if (r.carry > r.n_prev) status |= 4u;                   // carried frames span more than one chunk: unsupported
+                    const uint32_t avail = r.carry + r.n_cur;
+                    r.emit = (avail >= F && !(status & 4u)) ? 1u : 0u;      // a whole F-frame packet is ready (resampler.rs:425-428)
+                    new_carry = r.emit ? avail - F : avail;
+                    if (new_carry > r.n_cur) status |= 1u;                  // backlog: a second packet is pending
+                    if (r.count >= 1u && ((rec.overflow >> r.par_cur) & 1u)) status |= 2u;
+                    recp->carry = new_carry;
+                }
+                s_res[j] = r;
+                skgpu_chain_result res;
+                res.emitted = r.emit;
+                res.status = status;
+                reinterpret_cast<skgpu_chain_result *>(arena + results_off)[gi] = res;
+                // a present input that emits nothing still retires its previous chunk: advance the history here
+                // (emitting inputs are handled by the consumers, after the TMA read of the old history)
+                if (pres && !r.emit && r.count >= 2u) {
+                    for (uint32_t e = 0; e < 16u * r.ch; ++e) r.hist_g[e] = r.prev_g[(size_t)(r.N - 16u) * r.ch + e];
+                }
             }
-            mbar_expect_tx(&bar, total);
-            for (uint32_t q = 0; q < nb; ++q) {
-                const ChainIn &in = s_in[s_order[b0 + q]];
-                float *dst = s_buf + (size_t)q * buf_floats;
-                const uint32_t cb = (in.count >= 2u) ? in.N * in.ch * 4u : 0u;
-                tma_bulk_g2s(dst, in.hist_g, 16u * in.ch * 4u, &bar);
-                if (cb && !(cb & 15u)) tma_bulk_g2s(dst + 16u * in.ch, in.prev_g, cb, &bar);
-            }
-        }
-        for (uint32_t q = 0; q < nb; ++q) {
-            const ChainIn &in = s_in[s_order[b0 + q]];
-            const uint32_t cb = (in.count >= 2u) ? in.N * in.ch * 4u : 0u;
-            if (cb & 15u) {
-                float *dst = s_buf + (size_t)q * buf_floats + 16u * in.ch;
-                for (uint32_t e = threadIdx.x; e < in.N * in.ch; e += CH_THREADS) dst[e] = in.prev_g[e];
-            }
-        }
-        // ---- phase tables (previous and current chunk) of the batch -> smem, overlapping the bulk copies
-        for (uint32_t q = 0; q < nb; ++q) {
-            const ChainIn &in = s_in[s_order[b0 + q]];
-            const SkPhaseTable *tab = st.tab + (size_t)in.slot * 2u;
-            if (in.count >= 2u) load_phase_table(&s_tab[q * 2u], tab + ((in.count - 2u) & 1u), threadIdx.x, CH_THREADS);
-            load_phase_table(&s_tab[q * 2u + 1u], tab + ((in.count - 1u) & 1u), threadIdx.x, CH_THREADS);
-        }
-        __syncthreads();
-        mbar_wait(&bar, phase_bit);
-        phase_bit ^= 1u;
-
-        // ---- interpolate + gain + ordered accumulate
-        for (uint32_t q = 0; q < nb; ++q) {
-            const ChainIn in = s_in[s_order[b0 + q]];
-            const float *A = s_buf + (size_t)q * buf_floats;     // [16 history | previous chunk (N frames, if any)]
-            const uint32_t NA = (in.count >= 2u) ? in.N : 0u;    // frames of the previous chunk present in A
-            const SmemPhase *Tp = &s_tab[q * 2u], *Tc = &s_tab[q * 2u + 1u];
-            const bool is_base = has_base && (b0 + q == 0u);
-            const uint32_t sc = in.ch;
-#pragma unroll
-            for (int it = 0; it < CH_MAX_ITERS; ++it) {
-                const uint32_t j0 = (threadIdx.x + it * CH_THREADS) * CH_FPT;
-                if (j0 >= F) break;
-#pragma unroll
-                for (int f = 0; f < CH_FPT; ++f) {
-                    const uint32_t j = j0 + f;
-                    if (j >= F) break;
-                    float y[2];
-                    uint32_t p;
-                    float frac;
-                    if (j < in.carry) {
-                        // frame produced by the PREVIOUS chunk: recompute it from (history ++ previous chunk)
-                        const uint32_t k = in.n_prev - in.carry + j;
-                        phase_split(phase_eval_smem(Tp, in.t, k), p, frac);
-                        for (uint32_t c = 0; c < sc; ++c) y[c] = interp_lin(frac, A[p * sc + c], A[(p + 1u) * sc + c]);
-                    } else {
-                        // frame produced by the CURRENT chunk: its history is the tail of the previous chunk (in A),
-                        // positions beyond it are read from the current chunk in HBM (a handful in steady state)
-                        const uint32_t k = j - in.carry;
-                        phase_split(phase_eval_smem(Tc, in.t, k), p, frac);
-                        for (uint32_t c = 0; c < sc; ++c) {
-                            const float y0 = (p < 16u) ? A[(NA + p) * sc + c] : in.cur_g[(size_t)(p - 16u) * sc + c];
-                            const float y1 = (p + 1u < 16u) ? A[(NA + p + 1u) * sc + c] : in.cur_g[(size_t)(p + 1u - 16u) * sc + c];
-                            y[c] = interp_lin(frac, y0, y1);
-                        }
+            __syncwarp();
+            // ---- summation order over the inputs that deliver a packet: base selection + swap_remove (mixer.rs:960-980)
+            uint32_t m = 0, has_base = 0;
+            if (lane == 0) {
+                int base = -1, base_unique = -1;
+                for (uint32_t j = 0; j < K; ++j) {
+                    if (!s_res[j].emit) continue;
+                    if (s_res[j].ch == (uint32_t)OC) {  // packet already has the output shape (F frames x OC channels)
+                        const int u = (int)s_res[j].unique;
+                        if (u >= base_unique) { base = (int)m; base_unique = u; }
                     }
-                    chain_accumulate<OC>(&acc[it][f * OC], y, sc, in.gain, in.has_gain != 0, is_base);
+                    s_order[m++] = (uint8_t)j;
+                }
+                if (base >= 0 && m > 0) {
+                    const uint8_t b = s_order[base];
+                    s_order[base] = s_order[m - 1];
+                    for (uint32_t q = m - 1; q > 0; --q) s_order[q] = s_order[q - 1];
+                    s_order[0] = b;
+                }
+                has_base = (base >= 0) ? 1u : 0u;
+            }
+            m = __shfl_sync(0xffffffffu, m, 0);
+            has_base = __shfl_sync(0xffffffffu, has_base, 0);
+            __syncwarp();
+            // ---- one pipeline item per batch of <= kb inputs (an empty session still produces one item: silence)
+            const uint32_t n_batches = (m + kb - 1u) / kb + (m == 0u ? 1u : 0u);
+            for (uint32_t b = 0; b < n_batches; ++b) {
+                const uint32_t b0 = b * kb;
+                const uint32_t nb = min(kb, m - min(m, b0));
+                mbar_wait(&bar_empty[stage], ephase);
+                ChainStage *S = &s_stage[stage];
+                uint8_t *sm = smem_raw + (size_t)stage * stage_bytes;
+                float *s_buf = reinterpret_cast<float *>(sm);
+                SmemPhase *s_tab = reinterpret_cast<SmemPhase *>(sm + buf_bytes);
+                // chunks whose byte size is not a multiple of 16 (e.g. mono 882 frames) cannot use the bulk copy:
+                // the producer warp copies them itself
+                for (uint32_t q = 0; q < nb; ++q) {
+                    const ChainIn &in = s_res[s_order[b0 + q]];
+                    const uint32_t cb = (in.count >= 2u) ? in.N * in.ch * 4u : 0u;
+                    if (cb & 15u) {
+                        float *dst = s_buf + (size_t)q * buf_floats + 16u * in.ch;
+                        for (uint32_t e = lane; e < in.N * in.ch; e += 32u) dst[e] = in.prev_g[e];
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) {
+                    S->out_off = grp.out_off;
+                    S->has_master = grp.gain_idx != SKGPU_NO_GAIN;
+                    S->master_gain = S->has_master ? gains[grp.gain_idx] : 1.0f;
+                    S->flags = grp.flags;
+                    S->nb = nb;
+                    S->first = (b == 0u);
+                    S->last = (b + 1u == n_batches);
+                    S->has_base = has_base;
+                    S->stop = 0;
+                    uint32_t total = 0;
+                    for (uint32_t q = 0; q < nb; ++q) {
+                        const ChainIn in = s_res[s_order[b0 + q]];
+                        S->in[q] = in;
+                        const SlotRec *recp = st.rec + in.slot;
+                        SmemPhase *Tp = &s_tab[q * 2u], *Tc = &s_tab[q * 2u + 1u];
+                        const uint32_t npp = (in.count >= 2u) ? recp->n_prefix[in.par_prev] : 0u, nrp = (in.count >= 2u) ? recp->n_runs[in.par_prev] : 0u;
+                        const uint32_t npc = recp->n_prefix[in.par_cur], nrc = recp->n_runs[in.par_cur];
+                        Tp->n_out = in.n_prev; Tp->n_prefix = npp; Tp->n_runs = nrp; Tp->overflow = 0;
+                        Tc->n_out = in.n_cur; Tc->n_prefix = npc; Tc->n_runs = nrc; Tc->overflow = 0;
+                        const uint32_t cb = (in.count >= 2u) ? in.N * in.ch * 4u : 0u;
+                        const uint32_t b_hist = 16u * in.ch * 4u;
+                        const uint32_t b_chunk = (cb & 15u) ? 0u : cb;
+                        const uint32_t b_pp = (npp * 8u + 15u) & ~15u, b_pr = (nrp * 24u + 15u) & ~15u;
+                        const uint32_t b_cp = (npc * 8u + 15u) & ~15u, b_cr = (nrc * 24u + 15u) & ~15u;
+                        total += b_hist + b_chunk + b_pp + b_pr + b_cp + b_cr;
+                    }
+                    mbar_expect_tx(&bar_full[stage], total);
+                    for (uint32_t q = 0; q < nb; ++q) {
+                        const ChainIn &in = S->in[q];
+                        float *dst = s_buf + (size_t)q * buf_floats;
+                        const SkPhaseTable *tab = st.tab + (size_t)in.slot * 2u;
+                        SmemPhase *Tp = &s_tab[q * 2u], *Tc = &s_tab[q * 2u + 1u];
+                        const uint32_t cb = (in.count >= 2u) ? in.N * in.ch * 4u : 0u;
+                        tma_bulk_g2s(dst, in.hist_g, 16u * in.ch * 4u, &bar_full[stage]);
+                        if (cb && !(cb & 15u)) tma_bulk_g2s(dst + 16u * in.ch, in.prev_g, cb, &bar_full[stage]);
+                        const uint32_t b_pp = (Tp->n_prefix * 8u + 15u) & ~15u, b_pr = (Tp->n_runs * 24u + 15u) & ~15u;
+                        const uint32_t b_cp = (Tc->n_prefix * 8u + 15u) & ~15u, b_cr = (Tc->n_runs * 24u + 15u) & ~15u;
+                        if (b_pp) tma_bulk_g2s(Tp->prefix, tab[in.par_prev].prefix, b_pp, &bar_full[stage]);
+                        if (b_pr) tma_bulk_g2s(Tp->runs, tab[in.par_prev].runs, b_pr, &bar_full[stage]);
+                        if (b_cp) tma_bulk_g2s(Tc->prefix, tab[in.par_cur].prefix, b_cp, &bar_full[stage]);
+                        if (b_cr) tma_bulk_g2s(Tc->runs, tab[in.par_cur].runs, b_cr, &bar_full[stage]);
+                    }
+                }
+                __syncwarp();
+                if (++stage == CH_STAGES) { stage = 0; ephase ^= 1u; }
+            }
+        }
+        // ---- tell the consumers there is no more work
+        mbar_wait(&bar_empty[stage], ephase);
+        if (lane == 0) {
+            s_stage[stage].stop = 1;
+            mbar_expect_tx(&bar_full[stage], 0);
+        }
+        return;
+    }
+
+    // =================================================================== consumer warps
+    const uint32_t ct = threadIdx.x - 32u;  // 0..255
+    float acc[ITERS][CH_FPT * OC];
+    uint32_t stage = 0, fphase = 0;
+    for (;;) {
+        mbar_wait(&bar_full[stage], fphase);
+        const ChainStage *S = &s_stage[stage];
+        if (S->stop) break;
+        const uint8_t *sm = smem_raw + (size_t)stage * stage_bytes;
+        const float *s_buf = reinterpret_cast<const float *>(sm);
+        const SmemPhase *s_tab = reinterpret_cast<const SmemPhase *>(sm + buf_bytes);
+        if (S->first) {
+#pragma unroll
+            for (int it = 0; it < ITERS; ++it)
+#pragma unroll
+                for (int e = 0; e < CH_FPT * OC; ++e) acc[it][e] = 0.0f;  // vec![0.0f32; output_size] when there is no base frame
+        }
+        const uint32_t nb = S->nb;
+        for (uint32_t q = 0; q < nb; ++q) {
+            const ChainIn &in = S->in[q];
+            const float *A = s_buf + (size_t)q * buf_floats;
+            const SmemPhase *Tp = &s_tab[q * 2u], *Tc = &s_tab[q * 2u + 1u];
+            const bool is_base = S->has_base && S->first && q == 0u;
+#pragma unroll
+            for (int it = 0; it < ITERS; ++it) {
+                const uint32_t j0 = (ct + it * CH_CONSUMERS) * CH_FPT;
+                if (j0 < F) {
+                    if (in.ch == 2u) chain_input<OC, 2>(in, A, Tp, Tc, F, j0, acc[it], is_base);
+                    else chain_input<OC, 1>(in, A, Tp, Tc, F, j0, acc[it], is_base);
                 }
             }
         }
-    }
-
-    // ---- epilogue: master gain, then clip + s16 pack (or f32)
-    const bool has_master = grp.gain_idx != SKGPU_NO_GAIN;
-    const float mg = has_master ? gains[grp.gain_idx] : 1.0f;
+        if (S->last) {
+            // ---- epilogue: master gain, then clip + s16 pack (or f32)
+            const bool has_master = S->has_master != 0;
+            const float mg = S->master_gain;
 #pragma unroll
-    for (int it = 0; it < CH_MAX_ITERS; ++it) {
-        const uint32_t j0 = (threadIdx.x + it * CH_THREADS) * CH_FPT;
-        if (j0 >= F) break;
-        float *a = acc[it];
-        if (has_master) {
+            for (int it = 0; it < ITERS; ++it) {
+                const uint32_t j0 = (ct + it * CH_CONSUMERS) * CH_FPT;
+                if (j0 >= F) continue;
+                float *a = acc[it];
+                if (has_master) {
 #pragma unroll
-            for (int e = 0; e < CH_FPT * OC; ++e) a[e] = __fmul_rn(a[e], mg);
-        }
-        const uint32_t nfr = min((uint32_t)CH_FPT, F - j0);
-        if (grp.flags & SKGPU_MIX_OUT_S16) {
-            uint16_t *o = reinterpret_cast<uint16_t *>(arena + grp.out_off) + (size_t)j0 * OC;
-            if (nfr == CH_FPT && OC == 2 && ((((uintptr_t)o) & 15u) == 0)) {
-                stg_stream_u4(reinterpret_cast<uint4 *>(o), make_uint4(pack_s16x2(a[0], a[1]), pack_s16x2(a[2], a[3]),
-                                                                      pack_s16x2(a[4 % (CH_FPT * OC)], a[5 % (CH_FPT * OC)]),
-                                                                      pack_s16x2(a[6 % (CH_FPT * OC)], a[7 % (CH_FPT * OC)])));
-            } else if (nfr == CH_FPT && OC == 1 && ((((uintptr_t)o) & 7u) == 0)) {
-                stg_stream_u2(reinterpret_cast<uint2 *>(o), make_uint2(pack_s16x2(a[0], a[1]), pack_s16x2(a[2], a[3])));
-            } else {
-                for (uint32_t e = 0; e < nfr * OC; ++e) o[e] = (uint16_t)f32_to_s16_bits(a[e]);
+                    for (int e = 0; e < CH_FPT * OC; ++e) a[e] = __fmul_rn(a[e], mg);
+                }
+                const uint32_t nfr = min((uint32_t)CH_FPT, F - j0);
+                if (S->flags & SKGPU_MIX_OUT_S16) {
+                    uint16_t *o = reinterpret_cast<uint16_t *>(arena + S->out_off) + (size_t)j0 * OC;
+                    if (nfr == CH_FPT && OC == 2) {
+                        stg_stream_u4(reinterpret_cast<uint4 *>(o), make_uint4(pack_s16x2(a[0], a[1]), pack_s16x2(a[2], a[3]),
+                                                                              pack_s16x2(a[4 % (CH_FPT * OC)], a[5 % (CH_FPT * OC)]),
+                                                                              pack_s16x2(a[6 % (CH_FPT * OC)], a[7 % (CH_FPT * OC)])));
+                    } else if (nfr == CH_FPT && OC == 1) {
+                        stg_stream_u2(reinterpret_cast<uint2 *>(o), make_uint2(pack_s16x2(a[0], a[1]), pack_s16x2(a[2], a[3])));
+                    } else {
+                        for (uint32_t e = 0; e < nfr * OC; ++e) o[e] = (uint16_t)f32_to_s16_bits(a[e]);
+                    }
+                } else {
+                    float *o = reinterpret_cast<float *>(arena + S->out_off) + (size_t)j0 * OC;
+                    if (nfr == CH_FPT) {
+                        stg_stream_f4(reinterpret_cast<float4 *>(o), make_float4(a[0], a[1], a[2], a[3]));
+                        if (OC == 2) stg_stream_f4(reinterpret_cast<float4 *>(o) + 1, make_float4(a[4 % (CH_FPT * OC)], a[5 % (CH_FPT * OC)], a[6 % (CH_FPT * OC)], a[7 % (CH_FPT * OC)]));
+                    } else {
+                        for (uint32_t e = 0; e < nfr * OC; ++e) o[e] = a[e];
+                    }
+                }
             }
-        } else {
-            float *o = reinterpret_cast<float *>(arena + grp.out_off) + (size_t)j0 * OC;
-            for (uint32_t e = 0; e < nfr * OC; ++e) o[e] = a[e];
         }
-    }
-
-    // ---- state: carry, history (16 frames before the chunk that now becomes "previous"), per-input results
-    __syncthreads();  // all TMA reads of st.hist have completed (every thread passed the last mbar_wait)
-    for (uint32_t j = 0; j < K; ++j) {
-        const ChainIn &in = s_in[j];
-        if (in.present && in.count >= 2u) {
-            // new history = last 16 frames of the previous chunk (N >= 16 is validated by the host)
-            const uint32_t n = 16u * in.ch;
-            if (threadIdx.x < n) in.hist_g[threadIdx.x] = in.prev_g[(size_t)(in.N - 16u) * in.ch + threadIdx.x];
+        // ---- history of every input of the batch := last 16 frames of its previous chunk (now retired); the bulk
+        // read of the old history has completed (the full barrier flipped), so overwriting it is safe
+        for (uint32_t q = 0; q < nb; ++q) {
+            const ChainIn &in = S->in[q];
+            if (in.count >= 2u && ct < 16u * in.ch) in.hist_g[ct] = s_buf[(size_t)q * buf_floats + (size_t)in.N * in.ch + ct];
         }
-    }
-    if (threadIdx.x < K) {
-        const ChainIn &in = s_in[threadIdx.x];
-        if (in.present) st.carry[in.slot] = in.new_carry;
-        uint32_t status = in.status;
-        const SkPhaseTable *tab = st.tab + (size_t)in.slot * 2u;
-        if (in.present && in.count >= 1u && tab[(in.count - 1u) & 1u].overflow) status |= 2u;
-        skgpu_chain_result res;
-        res.emitted = in.emit;
-        res.status = status;
-        reinterpret_cast<skgpu_chain_result *>(arena + results_off)[grp.first_input + threadIdx.x] = res;
+        __syncwarp();
+        if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&bar_empty[stage])) : "memory");
+        if (++stage == CH_STAGES) { stage = 0; fphase ^= 1u; }
     }
 }
 

@@ -23,12 +23,18 @@ __global__ void __launch_bounds__(PHASE_THREADS) k_phase(const OpHeader *__restr
     if (i >= n_items) return;
     if (present && !present[i]) return;  // stream delivered no chunk this tick: state untouched
     const uint32_t slot = items[i].slot;
-    const uint32_t c = st.chunk_count[slot];
-    SkPhaseTable *T = st.tab + (size_t)slot * 2u + (c & 1u);
+    SlotRec *rec = st.rec + slot;
+    const uint32_t c = rec->chunk_count;
+    const uint32_t par = c & 1u;
+    SkPhaseTable *T = st.tab + (size_t)slot * 2u + par;
     double idx_end;
-    const uint32_t n = sk_phase_table(st.last_index[slot], st.t_ratio[slot], st.end_idx[slot], T, &idx_end);
-    st.last_index[slot] = __dsub_rn(idx_end, (double)st.chunk[slot]);  // self.last_index = idx - chunk_size as f64
-    st.chunk_count[slot] = c + 1u;
+    const uint32_t n = sk_phase_table(rec->last_index, rec->t_ratio, rec->end_idx, T, &idx_end);
+    rec->last_index = __dsub_rn(idx_end, (double)rec->chunk);  // self.last_index = idx - chunk_size as f64
+    rec->chunk_count = c + 1u;
+    rec->n_out[par] = n;
+    rec->n_prefix[par] = (uint16_t)T->n_prefix;
+    rec->n_runs[par] = (uint16_t)T->n_runs;
+    rec->overflow = (rec->overflow & ~(1u << par)) | ((T->overflow ? 1u : 0u) << par);
     if (!CHAIN) {
         const skgpu_rs_item *it = reinterpret_cast<const skgpu_rs_item *>(items) + i;
         skgpu_rs_result res;
@@ -72,9 +78,10 @@ __global__ void __launch_bounds__(RS_THREADS) k_resample(const OpHeader *__restr
     if (i >= hdr->count) return;
     const skgpu_rs_item it = items[i];
     const uint32_t slot = it.slot;
-    const uint32_t ch = (C > 0) ? (uint32_t)C : st.channels[slot];
-    const uint32_t N = st.chunk[slot];
-    const double t = st.t_ratio[slot];
+    const SlotRec rec = st.rec[slot];
+    const uint32_t ch = (C > 0) ? (uint32_t)C : rec.channels;
+    const uint32_t N = rec.chunk;
+    const double t = rec.t_ratio;
     const bool to_fifo = (it.flags & SKGPU_RS_TO_FIFO) != 0;
 
     float *buf = reinterpret_cast<float *>(smem_raw);  // [(16 + N) * ch]: history then chunk, interleaved
@@ -100,8 +107,8 @@ __global__ void __launch_bounds__(RS_THREADS) k_resample(const OpHeader *__restr
         }
     }
     // phase table of the chunk k_phase just processed (chunk_count was already advanced) -> smem, overlapping the bulk copy
-    const uint32_t c_idx = st.chunk_count[slot] - 1u;
-    load_phase_table(&s_tab, st.tab + (size_t)slot * 2u + (c_idx & 1u), threadIdx.x, RS_THREADS);
+    const uint32_t par = (rec.chunk_count - 1u) & 1u;
+    load_phase_table(&s_tab, st.tab + (size_t)slot * 2u + par, rec.n_out[par], rec.n_prefix[par], rec.n_runs[par], threadIdx.x, RS_THREADS);
     __syncthreads();
     if (staged && tma_ok) mbar_wait(&bar, 0);
 
@@ -121,15 +128,17 @@ __global__ void __launch_bounds__(RS_THREADS) k_resample(const OpHeader *__restr
 
     if (C == 1 || C == 2) {
         constexpr int CC = (C == 0) ? 1 : C;
-        constexpr int FPT = 4 / CC;  // frames per thread per iteration = 16 bytes of output
+        constexpr int FPT = 4;  // consecutive frames per thread per iteration: one phase-run lookup, 16*CC bytes of output
         for (uint32_t k0 = threadIdx.x * FPT; k0 < n_out; k0 += RS_THREADS * FPT) {
-            float o[4];
+            const uint32_t nfr = min((uint32_t)FPT, n_out - k0);
+            double x[4];
+            phase_eval4(&s_tab, t, k0, nfr, x);
+            float o[4 * CC];
 #pragma unroll
             for (int f = 0; f < FPT; ++f) {
-                const uint32_t k = min(k0 + f, n_out - 1u);
                 uint32_t p;
                 float frac;
-                phase_split(phase_eval_smem(&s_tab, t, k), p, frac);
+                phase_split(x[f], p, frac);
                 if (staged) {
                     interp_frame<CC>(buf, p, frac, o + f * CC);
                 } else {
@@ -143,13 +152,14 @@ __global__ void __launch_bounds__(RS_THREADS) k_resample(const OpHeader *__restr
             }
             const uint32_t of0 = to_fifo ? (uint32_t)((fifo_w + k0) & fifo_mask) : k0;
             float *dst = out_g + (size_t)of0 * CC;
-            const bool contiguous = (k0 + FPT <= n_out) && (!to_fifo || of0 + FPT <= st.fifo_frames);
+            const bool contiguous = (nfr == FPT) && (!to_fifo || of0 + FPT <= st.fifo_frames);
             if (contiguous && ((((uintptr_t)dst) & 15u) == 0)) {
                 stg_stream_f4(reinterpret_cast<float4 *>(dst), make_float4(o[0], o[1], o[2], o[3]));
+                if (CC == 2) stg_stream_f4(reinterpret_cast<float4 *>(dst) + 1, make_float4(o[4 % (4 * CC)], o[5 % (4 * CC)], o[6 % (4 * CC)], o[7 % (4 * CC)]));
             } else {
 #pragma unroll
                 for (int f = 0; f < FPT; ++f) {
-                    if (k0 + f < n_out) {
+                    if ((uint32_t)f < nfr) {
                         const uint32_t of = to_fifo ? (uint32_t)((fifo_w + k0 + f) & fifo_mask) : (k0 + f);
 #pragma unroll
                         for (int c = 0; c < CC; ++c) out_g[(size_t)of * CC + c] = o[f * CC + c];

@@ -60,9 +60,8 @@ struct skgpu_ctx {
     std::vector<uint8_t> used;
     std::vector<uint32_t> free_list;
     uint32_t next_fresh = 0;
-    uint32_t dirty_lo = 0xFFFFFFFFu, dirty_hi = 0;
-    std::vector<uint32_t> reset_list;
-    uint32_t *d_reset = nullptr;
+    std::vector<uint32_t> reset_list;   // slots to (re)configure + reset on the device before the next launch
+    SlotCfgUpload *d_reset = nullptr;
     uint32_t d_reset_cap = 0;
     uint4 *l2buf = nullptr;
     size_t l2n = 0;
@@ -75,28 +74,27 @@ static cudaError_t dalloc(T **p, size_t n) {
 }
 
 static skgpu_rc ctx_flush(skgpu_ctx *c) {
-    // upload dirty slot configuration, then reset freshly opened / reset slots on the device
-    if (c->dirty_lo < c->dirty_hi) {
-        const uint32_t lo = c->dirty_lo, n = c->dirty_hi - c->dirty_lo;
-        CU(cudaMemcpyAsync(c->st.t_ratio + lo, c->h_t.data() + lo, n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
-        CU(cudaMemcpyAsync(c->st.end_idx + lo, c->h_end.data() + lo, n * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
-        CU(cudaMemcpyAsync(c->st.chunk + lo, c->h_chunk.data() + lo, n * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
-        CU(cudaMemcpyAsync(c->st.channels + lo, c->h_ch.data() + lo, n * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
-        CU(cudaStreamSynchronize(c->stream));  // pageable sources: make the copies complete before mirrors change
-        c->dirty_lo = 0xFFFFFFFFu;
-        c->dirty_hi = 0;
-    }
+    // (re)configure freshly opened / reset slots on the device: one 24-byte record per slot, one small kernel
     if (!c->reset_list.empty()) {
         const uint32_t n = (uint32_t)c->reset_list.size();
+        std::vector<SlotCfgUpload> up(n);
+        for (uint32_t i = 0; i < n; ++i) {
+            const uint32_t slot = c->reset_list[i];
+            up[i].t_ratio = c->h_t[slot];
+            up[i].slot = slot;
+            up[i].chunk = c->h_chunk[slot];
+            up[i].channels = c->h_ch[slot];
+            up[i].end_idx = c->h_end[slot];
+        }
         if (n > c->d_reset_cap) {
             if (c->d_reset) cudaFree(c->d_reset);
             c->d_reset_cap = std::max<uint32_t>(n, 1024u);
             CU(dalloc(&c->d_reset, c->d_reset_cap));
         }
-        CU(cudaMemcpyAsync(c->d_reset, c->reset_list.data(), n * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
-        k_reset_slots<<<n, 128, 0, c->stream>>>(c->d_reset, n, c->st);
+        CU(cudaMemcpyAsync(c->d_reset, up.data(), n * sizeof(SlotCfgUpload), cudaMemcpyHostToDevice, c->stream));
+        k_config_slots<<<n, 128, 0, c->stream>>>(c->d_reset, n, c->st);
         CU(cudaGetLastError());
-        CU(cudaStreamSynchronize(c->stream));
+        CU(cudaStreamSynchronize(c->stream));  // `up` is pageable host memory
         c->reset_list.clear();
     }
     return SKGPU_OK;
@@ -129,19 +127,12 @@ extern "C" skgpu_rc skgpu_ctx_create(int32_t device_ordinal, const skgpu_ctx_con
     SlotTables &st = c->st;
     st.max_channels = cfg->max_channels;
     st.fifo_frames = cfg->fifo_frames;
-    CU(dalloc(&st.last_index, S));
-    CU(dalloc(&st.t_ratio, S));
-    CU(dalloc(&st.end_idx, S));
-    CU(dalloc(&st.chunk, S));
-    CU(dalloc(&st.channels, S));
+    CU(dalloc(&st.rec, S));
     CU(dalloc(&st.hist, S * 16 * cfg->max_channels));
     CU(dalloc(&st.tab, S * 2));
-    CU(dalloc(&st.chunk_count, S));
-    CU(dalloc(&st.carry, S));
+    CU(cudaMemset(st.rec, 0, S * sizeof(SlotRec)));
     CU(cudaMemset(st.hist, 0, S * 16 * cfg->max_channels * sizeof(float)));
     CU(cudaMemset(st.tab, 0, S * 2 * sizeof(SkPhaseTable)));
-    CU(cudaMemset(st.chunk_count, 0, S * sizeof(uint32_t)));
-    CU(cudaMemset(st.carry, 0, S * sizeof(uint32_t)));
     if (cfg->fifo_frames) {
         CU(dalloc(&st.fifo, S * cfg->fifo_frames * cfg->max_channels));
         CU(dalloc(&st.fifo_w, S));
@@ -163,8 +154,7 @@ extern "C" void skgpu_ctx_destroy(skgpu_ctx *c) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     SlotTables &st = c->st;
-    cudaFree(st.last_index); cudaFree(st.t_ratio); cudaFree(st.end_idx); cudaFree(st.chunk); cudaFree(st.channels);
-    cudaFree(st.hist); cudaFree(st.tab); cudaFree(st.chunk_count); cudaFree(st.carry);
+    cudaFree(st.rec); cudaFree(st.hist); cudaFree(st.tab);
     if (st.fifo) { cudaFree(st.fifo); cudaFree(st.fifo_w); cudaFree(st.fifo_r); }
     if (c->d_reset) cudaFree(c->d_reset);
     if (c->l2buf) cudaFree(c->l2buf);
@@ -219,8 +209,6 @@ static void slot_configure(skgpu_ctx *c, uint32_t slot, const skgpu_stream_cfg *
     c->h_chunk[slot] = s->chunk_frames;
     c->h_ch[slot] = s->channels;
     c->used[slot] = 1;
-    c->dirty_lo = std::min(c->dirty_lo, slot);
-    c->dirty_hi = std::max(c->dirty_hi, slot + 1);
     c->reset_list.push_back(slot);
 }
 
@@ -265,7 +253,11 @@ extern "C" skgpu_rc skgpu_stream_get_state(skgpu_ctx *c, uint32_t slot, double *
     skgpu_rc rc = ctx_flush(c);
     if (rc) return rc;
     CU(cudaStreamSynchronize(c->stream));
-    if (last_index) CU(cudaMemcpy(last_index, c->st.last_index + slot, sizeof(double), cudaMemcpyDeviceToHost));
+    if (last_index) {
+        SlotRec rec;
+        CU(cudaMemcpy(&rec, c->st.rec + slot, sizeof(SlotRec), cudaMemcpyDeviceToHost));
+        *last_index = rec.last_index;
+    }
     if (hist) CU(cudaMemcpy(hist, c->st.hist + (size_t)slot * 16 * c->cfg.max_channels, 16 * c->h_ch[slot] * sizeof(float), cudaMemcpyDeviceToHost));
     if (fifo_written) { *fifo_written = 0; if (c->st.fifo_w) CU(cudaMemcpy(fifo_written, c->st.fifo_w + slot, 8, cudaMemcpyDeviceToHost)); }
     if (fifo_read) { *fifo_read = 0; if (c->st.fifo_r) CU(cudaMemcpy(fifo_read, c->st.fifo_r + slot, 8, cudaMemcpyDeviceToHost)); }
@@ -308,6 +300,8 @@ struct Op {
     uint32_t chain_kb = 0;        // chain: inputs staged per batch
     uint32_t chain_buf_floats = 0;  // chain: floats per staging buffer
     int chain_oc = 2;             // chain: output channels specialisation
+    int chain_iters = 1;          // chain: ceil(F / 1024)
+    uint32_t chain_grid = 0;      // chain: persistent grid size (CTAs per SM x SMs)
     DynTable present;             // mix / chain: per-input presence
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev[2];
     uint32_t ev_used[2] = {0, 0};
@@ -754,12 +748,14 @@ static skgpu_rc validate_chain(const skgpu_plan *p, const skgpu_chain_group *g, 
 }
 
 static void chain_size_smem(Op &op, uint32_t max_k, uint32_t buf_floats) {
-    // stage up to 4 inputs per batch, fewer if a batch would not leave room for >= 4 resident CTAs per SM
-    uint32_t kb = std::max(1u, std::min(max_k, 4u));
-    while (kb > 1 && (uint64_t)kb * (buf_floats * 4ull + 2 * sizeof(SmemPhase)) > 56u * 1024u) --kb;
+    // CH_STAGES pipeline stages, each staging up to kb inputs (buffer + two phase tables). Fewer inputs per batch
+    // when a stage would get so large that fewer than ~3 CTAs fit on an SM.
+    uint32_t kb = std::max(1u, std::min<uint32_t>(max_k, CH_MAX_KB));
+    while (kb > 1 && (uint64_t)CH_STAGES * kb * (buf_floats * 4ull + 2 * sizeof(SmemPhase)) > 64u * 1024u) --kb;
     op.chain_kb = kb;
     op.chain_buf_floats = buf_floats;
-    op.smem_bytes = (uint32_t)((((uint64_t)kb * buf_floats * 4u + 15u) & ~15ull) + (uint64_t)kb * 2u * sizeof(SmemPhase));
+    const uint64_t stage = (((uint64_t)kb * buf_floats * 4u + 15u) & ~15ull) + (uint64_t)kb * 2u * sizeof(SmemPhase);
+    op.smem_bytes = (uint32_t)(stage * CH_STAGES);
 }
 
 extern "C" skgpu_rc skgpu_plan_add_chain(skgpu_plan *p, const skgpu_chain_group *groups, uint32_t ng, const skgpu_chain_input *inputs, uint32_t ni,
@@ -789,6 +785,7 @@ extern "C" skgpu_rc skgpu_plan_add_chain(skgpu_plan *p, const skgpu_chain_group 
     op.n2 = ni;
     op.chain_F = output_frame_size;
     op.chain_oc = oc;
+    op.chain_iters = (int)((output_frame_size + 1023u) / 1024u);
     op.results_off = results_off;
     chain_size_smem(op, mk, std::max(mb, 64u));
     if (op.smem_bytes > 200u * 1024u) return fail(SKGPU_ERR_INVALID, "chain op: chunk too large for shared-memory staging (%u bytes)", op.smem_bytes);
@@ -862,6 +859,13 @@ static skgpu_rc op_event(Op &op, int sub, bool second, cudaStream_t s) {
     return SKGPU_OK;
 }
 
+typedef void (*chain_kernel_t)(const OpHeader *, const skgpu_chain_group *, const skgpu_chain_input *, const uint8_t *, const float *, SlotTables,
+                               uint8_t *, const uint32_t *, uint64_t, uint32_t, uint64_t, uint32_t, uint32_t);
+static chain_kernel_t chain_kernel(int oc, int iters) {
+    if (oc == 2) return iters == 1 ? k_chain<2, 1> : iters == 2 ? k_chain<2, 2> : k_chain<2, 3>;
+    return iters == 1 ? k_chain<1, 1> : iters == 2 ? k_chain<1, 2> : k_chain<1, 3>;
+}
+
 static skgpu_rc launch_ops(skgpu_plan *p, bool time_ops) {
     skgpu_ctx *c = p->ctx;
     cudaStream_t s = c->stream;
@@ -895,12 +899,12 @@ static skgpu_rc launch_ops(skgpu_plan *p, bool time_ops) {
             k_phase<skgpu_chain_input, true><<<(op.cap2 + PHASE_THREADS - 1) / PHASE_THREADS, PHASE_THREADS, 0, s>>>(op.d_hdr, cin, present, c->st, p->arena, 0);
             CU(cudaGetLastError());
             if (time_ops) { skgpu_rc rc = op_event(op, 0, true, s); if (rc) return rc; rc = op_event(op, 1, false, s); if (rc) return rc; }
-            if (op.chain_oc == 2)
-                k_chain<2><<<op.cap, CH_THREADS, op.smem_bytes, s>>>(op.d_hdr, (const skgpu_chain_group *)op.d_tab, cin, present, gains, c->st, p->arena,
-                                                                     p->d_tick, p->bank_stride, op.chain_F, op.results_off, op.chain_kb, op.chain_buf_floats);
-            else
-                k_chain<1><<<op.cap, CH_THREADS, op.smem_bytes, s>>>(op.d_hdr, (const skgpu_chain_group *)op.d_tab, cin, present, gains, c->st, p->arena,
-                                                                     p->d_tick, p->bank_stride, op.chain_F, op.results_off, op.chain_kb, op.chain_buf_floats);
+            {
+                const uint32_t grid = std::min<uint32_t>(op.cap, op.chain_grid);
+                auto kfn = chain_kernel(op.chain_oc, op.chain_iters);
+                kfn<<<grid, CH_THREADS, op.smem_bytes, s>>>(op.d_hdr, (const skgpu_chain_group *)op.d_tab, cin, present, gains, c->st, p->arena,
+                                                             p->d_tick, p->bank_stride, op.chain_F, op.results_off, op.chain_kb, op.chain_buf_floats);
+            }
             CU(cudaGetLastError());
             if (time_ops) { skgpu_rc rc = op_event(op, 1, true, s); if (rc) return rc; }
         } else {
@@ -948,9 +952,13 @@ extern "C" skgpu_rc skgpu_plan_finalize(skgpu_plan *p) {
         }
     }
     for (auto &op : p->ops) {
-        if (op.kind == OP_CHAIN && op.smem_bytes > 40u * 1024u) {
-            if (op.chain_oc == 2) CU(cudaFuncSetAttribute(k_chain<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)op.smem_bytes));
-            else CU(cudaFuncSetAttribute(k_chain<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)op.smem_bytes));
+        if (op.kind == OP_CHAIN) {
+            auto kfn = chain_kernel(op.chain_oc, op.chain_iters);
+            CU(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)op.smem_bytes));
+            int per_sm = 0;
+            CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kfn, CH_THREADS, op.smem_bytes));
+            if (per_sm < 1) return fail(SKGPU_ERR_INVALID, "chain op: kernel does not fit on an SM (%u bytes of shared memory)", op.smem_bytes);
+            op.chain_grid = (uint32_t)per_sm * (uint32_t)c->sm_count;  // persistent CTAs: every SM fully occupied, each loops over sessions
         }
     }
     skgpu_rc rc = ctx_flush(c);
