@@ -31,7 +31,8 @@ namespace skgpu {
 
 constexpr int CH_CONSUMERS = 256;                 // 8 consumer warps
 constexpr int CH_THREADS = CH_CONSUMERS + 32;     // + producer warp (warp 0)
-constexpr int CH_STAGES = 2;
+constexpr int CH_MAX_STAGES = 4;                // pipeline depth is a launch parameter (2..4)
+constexpr int CH_HEAD = 32;                     // frames of the CURRENT chunk staged behind the previous one
 constexpr int CH_MAX_INPUTS = 64;                 // inputs per session
 constexpr int CH_FPT = 4;                         // output frames per consumer thread per iteration
 constexpr int CH_MAX_KB = 4;                      // inputs staged per batch
@@ -46,6 +47,7 @@ struct ChainIn {            // per-tick view of one input of the session
     uint32_t slot, N, ch;
     uint32_t carry, n_prev, n_cur, count;
     uint32_t emit, unique, par_prev, par_cur;
+    uint16_t np_prev, nr_prev, np_cur, nr_cur;   // phase-table sizes (from the slot record)
 };
 
 struct ChainStage {         // header of one pipeline stage (shared memory)
@@ -60,91 +62,127 @@ struct ChainStage {         // header of one pipeline stage (shared memory)
     ChainIn in[CH_MAX_KB];
 };
 
-template <int OC>
-__device__ __forceinline__ void chain_accumulate(float *acc, const float *y, uint32_t sc, float gain, bool has_gain, bool is_base) {
-    // y: one input frame (sc channels) -> one output frame (OC channels); channel conversion as mixer.rs:1027-1078,
-    // upstream audio::gain applied per sample first (rounded separately, gain.rs:187-189)
-    float v[2];
-    if (sc == (uint32_t)OC) {
-#pragma unroll
-        for (int c = 0; c < OC; ++c) v[c] = has_gain ? __fmul_rn(y[c], gain) : y[c];
-    } else if (sc == 1 && OC == 2) {
-        const float m = has_gain ? __fmul_rn(y[0], gain) : y[0];
-        v[0] = m; v[1] = m;
-    } else {  // sc == 2 && OC == 1
-        const float l = has_gain ? __fmul_rn(y[0], gain) : y[0];
-        const float r = has_gain ? __fmul_rn(y[1], gain) : y[1];
-        v[0] = __fmul_rn(__fadd_rn(l, r), 0.5f);
-    }
-#pragma unroll
-    for (int c = 0; c < OC; ++c) acc[c] = is_base ? v[c] : __fadd_rn(acc[c], v[c]);
+// packed f32x2 multiply (Blackwell FMUL2): two IEEE-rounded products per instruction. Additions stay scalar
+// FADDs on purpose: ptxas contracts mul.f32x2 + add.f32x2 into FFMA2 (one rounding less than the reference).
+__device__ __forceinline__ unsigned long long mul2(unsigned long long a, float b) {
+    unsigned long long d, bb;
+    asm("mov.b64 %0, {%1, %1};" : "=l"(bb) : "f"(b));
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(bb));
+    return d;
+}
+__device__ __forceinline__ void unpack2(unsigned long long v, float &a, float &b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ unsigned long long pack2(float a, float b) {
+    unsigned long long d;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "f"(a), "f"(b));
+    return d;
 }
 
-// one input of one session, 4 consecutive output frames j0..j0+3 of this thread
+struct ChainInRegs {        // the fields of ChainIn the inner loop needs, in registers
+    const float *cur_g;
+    double t;
+    float gain;
+    uint32_t has_gain, sc, carry, n_prev, n_cur, NA;
+};
+
+// one input of one session, 4 consecutive output frames j0..j0+3 of this thread (frames >= F are computed on clamped
+// indices and never stored). A = [16 history | previous chunk (NA frames) | CH_HEAD frames of the current chunk].
 template <int OC, int SC>
-__device__ __forceinline__ void chain_input(const ChainIn &in, const float *A, const SmemPhase *Tp, const SmemPhase *Tc, uint32_t F,
+__device__ __forceinline__ void chain_input(const ChainInRegs &in, const float *A, const SmemPhase *Tp, const SmemPhase *Tc, uint32_t F,
                                             uint32_t j0, float *acc, bool is_base) {
-    const uint32_t NA = (in.count >= 2u) ? in.N : 0u;  // frames of the previous chunk present in A (after 16 history frames)
-    const bool has_gain = in.has_gain != 0;
-    if (j0 + CH_FPT <= in.carry && j0 + CH_FPT <= F) {
-        // all four frames were produced by the PREVIOUS chunk: recompute them from (history ++ previous chunk)
-        double x[4];
+    double x[4];
+    if (j0 + CH_FPT <= in.carry) {
+        // FAST PATH (954 of 960 frames in steady state): all four frames were produced by the PREVIOUS chunk;
+        // recompute them from (history ++ previous chunk), everything in shared memory, no selects.
         phase_eval4(Tp, in.t, in.n_prev - in.carry + j0, 4u, x);
+        if (SC == 2 && OC == 2) {
+#pragma unroll
+            for (int f = 0; f < CH_FPT; ++f) {
+                uint32_t p;
+                float frac;
+                phase_split(x[f], p, frac);
+                const unsigned long long y0 = *reinterpret_cast<const unsigned long long *>(A + 2u * p);
+                const unsigned long long y1 = *reinterpret_cast<const unsigned long long *>(A + 2u * p + 2u);
+                float a0, a1, b0, b1;
+                unpack2(mul2(y0, __fsub_rn(1.0f, frac)), a0, a1);   // rubato interp_lin: (1 - frac) * y0 + frac * y1
+                unpack2(mul2(y1, frac), b0, b1);
+                float r0 = __fadd_rn(a0, b0), r1 = __fadd_rn(a1, b1);
+                if (in.has_gain) unpack2(mul2(pack2(r0, r1), in.gain), r0, r1);   // the input's audio::gain
+                acc[f * 2] = is_base ? r0 : __fadd_rn(acc[f * 2], r0);
+                acc[f * 2 + 1] = is_base ? r1 : __fadd_rn(acc[f * 2 + 1], r1);
+            }
+            return;
+        }
+    } else if (j0 >= in.carry) {
+        // all four from the CURRENT chunk (its history is the tail of the previous chunk, which precedes it in A)
+        const uint32_t k0 = j0 - in.carry;
+        phase_eval4(Tc, in.t, min(k0, in.n_cur - 1u), min(4u, in.n_cur - min(k0, in.n_cur - 1u)), x);
+    } else {
 #pragma unroll
         for (int f = 0; f < CH_FPT; ++f) {
-            uint32_t p;
-            float frac;
-            phase_split(x[f], p, frac);
-            float y[2];
-            if (SC == 2) {
-                const float2 y0 = *reinterpret_cast<const float2 *>(A + 2u * p);
-                const float2 y1 = *reinterpret_cast<const float2 *>(A + 2u * p + 2u);
-                y[0] = interp_lin(frac, y0.x, y1.x);
-                y[1] = interp_lin(frac, y0.y, y1.y);
-            } else {
-                y[0] = interp_lin(frac, A[p], A[p + 1u]);
-                y[1] = 0.0f;
-            }
-            chain_accumulate<OC>(acc + f * OC, y, SC, in.gain, has_gain, is_base);
+            const uint32_t j = j0 + f;
+            x[f] = (j < in.carry) ? phase_eval_smem(Tp, in.t, in.n_prev - in.carry + j)
+                                  : phase_eval_smem(Tc, in.t, min(j - in.carry, in.n_cur - 1u));
         }
-        return;
     }
-    // boundary / tail threads: frame by frame
 #pragma unroll
     for (int f = 0; f < CH_FPT; ++f) {
-        const uint32_t j = j0 + f;
-        if (j >= F) break;
         uint32_t p;
         float frac;
-        float y[2] = {0.0f, 0.0f};
-        if (j < in.carry) {
-            phase_split(phase_eval_smem(Tp, in.t, in.n_prev - in.carry + j), p, frac);
-#pragma unroll
-            for (int c = 0; c < SC; ++c) y[c] = interp_lin(frac, A[p * SC + c], A[(p + 1u) * SC + c]);
+        phase_split(x[f], p, frac);
+        const bool from_cur = (j0 + f) >= in.carry;
+        const uint32_t idx = (from_cur ? in.NA : 0u) + p;   // frame index into A
+        if (SC == 2 && OC == 2) {
+            unsigned long long y0, y1;
+            if (from_cur && p + 1u >= 16u + CH_HEAD) {       // beyond the staged head (only right after a stream starts)
+                y0 = *reinterpret_cast<const unsigned long long *>(in.cur_g + 2u * (size_t)(p - 16u));
+                y1 = *reinterpret_cast<const unsigned long long *>(in.cur_g + 2u * (size_t)(p - 16u) + 2u);
+            } else {
+                y0 = *reinterpret_cast<const unsigned long long *>(A + 2u * idx);
+                y1 = *reinterpret_cast<const unsigned long long *>(A + 2u * idx + 2u);
+            }
+            // rubato interp_lin per channel: (1 - frac) * y0 + frac * y1, then the input's audio::gain, then the sum
+            float a0, a1, b0, b1;
+            unpack2(mul2(y0, __fsub_rn(1.0f, frac)), a0, a1);
+            unpack2(mul2(y1, frac), b0, b1);
+            float r0 = __fadd_rn(a0, b0), r1 = __fadd_rn(a1, b1);
+            if (in.has_gain) unpack2(mul2(pack2(r0, r1), in.gain), r0, r1);
+            acc[f * 2] = is_base ? r0 : __fadd_rn(acc[f * 2], r0);
+            acc[f * 2 + 1] = is_base ? r1 : __fadd_rn(acc[f * 2 + 1], r1);
         } else {
-            // produced by the CURRENT chunk: its history is the tail of the previous chunk (in A); positions beyond it
-            // are read from the current chunk in HBM (a handful of frames in steady state)
-            phase_split(phase_eval_smem(Tc, in.t, j - in.carry), p, frac);
+            float y[2] = {0.0f, 0.0f};
 #pragma unroll
             for (int c = 0; c < SC; ++c) {
-                const float y0 = (p < 16u) ? A[(NA + p) * SC + c] : in.cur_g[(size_t)(p - 16u) * SC + c];
-                const float y1 = (p + 1u < 16u) ? A[(NA + p + 1u) * SC + c] : in.cur_g[(size_t)(p + 1u - 16u) * SC + c];
+                float y0, y1;
+                if (from_cur && p + 1u >= 16u + CH_HEAD) {
+                    y0 = in.cur_g[(size_t)(p - 16u) * SC + c];
+                    y1 = in.cur_g[(size_t)(p + 1u - 16u) * SC + c];
+                } else {
+                    y0 = A[idx * SC + c];
+                    y1 = A[(idx + 1u) * SC + c];
+                }
                 y[c] = interp_lin(frac, y0, y1);
+                if (in.has_gain) y[c] = __fmul_rn(y[c], in.gain);   // upstream audio::gain, rounded separately (gain.rs:187-189)
             }
+            // channel conversion as mixer.rs:1027-1078
+            float v[2];
+            if (SC == OC) { v[0] = y[0]; v[1] = y[1]; }
+            else if (SC == 1 && OC == 2) { v[0] = y[0]; v[1] = y[0]; }
+            else { v[0] = __fmul_rn(__fadd_rn(y[0], y[1]), 0.5f); v[1] = 0.0f; }
+#pragma unroll
+            for (int c = 0; c < OC; ++c) acc[f * OC + c] = is_base ? v[c] : __fadd_rn(acc[f * OC + c], v[c]);
         }
-        chain_accumulate<OC>(acc + f * OC, y, SC, in.gain, has_gain, is_base);
     }
 }
 
 template <int OC, int ITERS>  // output channels (1 | 2); ITERS = ceil(F / 1024)
-__global__ void __launch_bounds__(CH_THREADS) k_chain(const OpHeader *__restrict__ hdr, const skgpu_chain_group *__restrict__ groups,
+__global__ void __launch_bounds__(CH_THREADS, 4) k_chain(const OpHeader *__restrict__ hdr, const skgpu_chain_group *__restrict__ groups,
                                                       const skgpu_chain_input *__restrict__ inputs, const uint8_t *__restrict__ present,
                                                       const float *__restrict__ gains, SlotTables st, uint8_t *__restrict__ arena,
                                                       const uint32_t *__restrict__ tick, uint64_t bank_stride, uint32_t F,
-                                                      uint64_t results_off, uint32_t kb, uint32_t buf_floats) {
+                                                      uint64_t results_off, uint32_t kb, uint32_t buf_floats, uint32_t nstages) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
-    __shared__ __align__(8) uint64_t bar_full[CH_STAGES], bar_empty[CH_STAGES];
-    __shared__ __align__(16) ChainStage s_stage[CH_STAGES];
+    __shared__ __align__(8) uint64_t bar_full[CH_MAX_STAGES], bar_empty[CH_MAX_STAGES];
+    __shared__ __align__(16) ChainStage s_stage[CH_MAX_STAGES];
     __shared__ ChainIn s_res[CH_MAX_INPUTS];     // producer scratch: resolved inputs of the session being prepared
     __shared__ uint8_t s_order[CH_MAX_INPUTS];
 
@@ -155,7 +193,7 @@ __global__ void __launch_bounds__(CH_THREADS) k_chain(const OpHeader *__restrict
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < CH_STAGES; ++s) {
+        for (uint32_t s = 0; s < nstages; ++s) {
             mbar_init(&bar_full[s], 1);
             mbar_init(&bar_empty[s], CH_CONSUMERS / 32);
         }
@@ -167,15 +205,49 @@ __global__ void __launch_bounds__(CH_THREADS) k_chain(const OpHeader *__restrict
         // =============================================================== producer warp
         const uint32_t parity = tick[0] & 1u;
         uint32_t stage = 0, ephase = 1;  // waiting on parity 1 of a fresh mbarrier returns immediately
-        for (uint32_t g_i = blockIdx.x; g_i < n_groups; g_i += gridDim.x) {
-            const skgpu_chain_group grp = groups[g_i];
+        // The descriptors of a session hang off each other (group -> inputs -> slot records / gains / presence): three
+        // dependent global round trips. They are software-pipelined three sessions deep in registers, so by the time a
+        // session is processed everything it needs was requested a full iteration earlier.
+        struct InPre { skgpu_chain_input in; SlotRec rec; float gain; uint32_t pres; };
+        const skgpu_chain_group grp_none = {0, 0, 0, SKGPU_NO_GAIN, (uint16_t)OC, 0};
+        auto load_grp = [&](uint32_t g) -> skgpu_chain_group { return (g < n_groups) ? groups[g] : grp_none; };
+        auto load_in = [&](const skgpu_chain_group &g, uint32_t j) -> skgpu_chain_input {
+            skgpu_chain_input z = {0, 0, SKGPU_NO_GAIN, 0, 0};
+            return (j < min(g.n_inputs, (uint32_t)CH_MAX_INPUTS)) ? inputs[g.first_input + j] : z;
+        };
+        auto load_pre = [&](const skgpu_chain_group &g, const skgpu_chain_input &in, uint32_t j, InPre &o) {
+            o.in = in;
+            if (j < min(g.n_inputs, (uint32_t)CH_MAX_INPUTS)) {
+                o.rec = st.rec[in.slot];
+                o.gain = (in.gain_idx != SKGPU_NO_GAIN) ? gains[in.gain_idx] : 1.0f;
+                o.pres = present ? (uint32_t)(present[g.first_input + j] != 0) : 1u;
+            }
+        };
+        const uint32_t gstep = gridDim.x;
+        skgpu_chain_group grp0 = load_grp(blockIdx.x), grp1 = load_grp(blockIdx.x + gstep), grp2 = load_grp(blockIdx.x + 2u * gstep);
+        skgpu_chain_input in0 = load_in(grp0, lane), in1 = load_in(grp1, lane);
+        InPre pre0;
+        load_pre(grp0, in0, lane, pre0);
+        for (uint32_t g_i = blockIdx.x; g_i < n_groups; g_i += gstep) {
+            const skgpu_chain_group grp = grp0;
+            const InPre pre = pre0;
+            // prefetch for the next three sessions
+            const skgpu_chain_group grp3 = load_grp(g_i + 3u * gstep);
+            const skgpu_chain_input in2 = load_in(grp2, lane);
+            InPre pre1;
+            load_pre(grp1, in1, lane, pre1);
             const uint32_t K = min(grp.n_inputs, (uint32_t)CH_MAX_INPUTS);
             // ---- resolve inputs (one lane per input): slot record, emission decision, carry bookkeeping, results
             for (uint32_t j = lane; j < K; j += 32u) {
                 const uint32_t gi = grp.first_input + j;
-                const skgpu_chain_input in = inputs[gi];
+                InPre cur = pre;
+                if (j >= 32u) {  // sessions with more than 32 inputs: the rest is fetched on demand
+                    cur.in = inputs[gi];
+                    load_pre(grp, cur.in, j, cur);
+                }
+                const skgpu_chain_input in = cur.in;
                 SlotRec *recp = st.rec + in.slot;
-                const SlotRec rec = *recp;
+                const SlotRec rec = cur.rec;
                 ChainIn r;
                 r.slot = in.slot;
                 r.N = rec.chunk;
@@ -183,9 +255,9 @@ __global__ void __launch_bounds__(CH_THREADS) k_chain(const OpHeader *__restrict
                 r.t = rec.t_ratio;
                 r.count = rec.chunk_count;   // k_phase already counted the current chunk
                 r.carry = rec.carry;
-                const uint32_t pres = present ? (present[gi] != 0) : 1u;
+                const uint32_t pres = cur.pres;
                 r.has_gain = in.gain_idx != SKGPU_NO_GAIN;
-                r.gain = r.has_gain ? gains[in.gain_idx] : 1.0f;
+                r.gain = cur.gain;
                 r.unique = (in.flags & SKGPU_MIX_IN_UNIQUE) ? 1u : 0u;
                 r.cur_g = reinterpret_cast<const float *>(arena + in.in_off + (uint64_t)parity * bank_stride);
                 r.prev_g = reinterpret_cast<const float *>(arena + in.in_off + (uint64_t)(1u - parity) * bank_stride);
@@ -194,6 +266,10 @@ __global__ void __launch_bounds__(CH_THREADS) k_chain(const OpHeader *__restrict
                 r.par_prev = r.count & 1u;   // == (count - 2) & 1
                 r.n_cur = (pres && r.count >= 1u) ? rec.n_out[r.par_cur] : 0u;
                 r.n_prev = (r.count >= 2u) ? rec.n_out[r.par_prev] : 0u;
+                r.np_prev = (r.count >= 2u) ? rec.n_prefix[r.par_prev] : (uint16_t)0;
+                r.nr_prev = (r.count >= 2u) ? rec.n_runs[r.par_prev] : (uint16_t)0;
+                r.np_cur = rec.n_prefix[r.par_cur];
+                r.nr_cur = rec.n_runs[r.par_cur];
                 uint32_t status = 0;
                 r.emit = 0;
                 uint32_t new_carry = r.carry;
@@ -217,6 +293,9 @@ __global__ void __launch_bounds__(CH_THREADS) k_chain(const OpHeader *__restrict
                     for (uint32_t e = 0; e < 16u * r.ch; ++e) r.hist_g[e] = r.prev_g[(size_t)(r.N - 16u) * r.ch + e];
                 }
             }
+            grp0 = grp1; grp1 = grp2; grp2 = grp3;
+            in0 = in1; in1 = in2;
+            pre0 = pre1;
             __syncwarp();
             // ---- summation order over the inputs that deliver a packet: base selection + swap_remove (mixer.rs:960-980)
             uint32_t m = 0, has_base = 0;
@@ -259,6 +338,8 @@ __global__ void __launch_bounds__(CH_THREADS) k_chain(const OpHeader *__restrict
                     if (cb & 15u) {
                         float *dst = s_buf + (size_t)q * buf_floats + 16u * in.ch;
                         for (uint32_t e = lane; e < in.N * in.ch; e += 32u) dst[e] = in.prev_g[e];
+                        const uint32_t head = min((uint32_t)CH_HEAD, in.N) * in.ch;
+                        for (uint32_t e = lane; e < head; e += 32u) dst[in.N * in.ch + e] = in.cur_g[e];
                     }
                 }
                 __syncwarp();
@@ -276,15 +357,13 @@ __global__ void __launch_bounds__(CH_THREADS) k_chain(const OpHeader *__restrict
                     for (uint32_t q = 0; q < nb; ++q) {
                         const ChainIn in = s_res[s_order[b0 + q]];
                         S->in[q] = in;
-                        const SlotRec *recp = st.rec + in.slot;
                         SmemPhase *Tp = &s_tab[q * 2u], *Tc = &s_tab[q * 2u + 1u];
-                        const uint32_t npp = (in.count >= 2u) ? recp->n_prefix[in.par_prev] : 0u, nrp = (in.count >= 2u) ? recp->n_runs[in.par_prev] : 0u;
-                        const uint32_t npc = recp->n_prefix[in.par_cur], nrc = recp->n_runs[in.par_cur];
+                        const uint32_t npp = in.np_prev, nrp = in.nr_prev, npc = in.np_cur, nrc = in.nr_cur;
                         Tp->n_out = in.n_prev; Tp->n_prefix = npp; Tp->n_runs = nrp; Tp->overflow = 0;
                         Tc->n_out = in.n_cur; Tc->n_prefix = npc; Tc->n_runs = nrc; Tc->overflow = 0;
                         const uint32_t cb = (in.count >= 2u) ? in.N * in.ch * 4u : 0u;
                         const uint32_t b_hist = 16u * in.ch * 4u;
-                        const uint32_t b_chunk = (cb & 15u) ? 0u : cb;
+                        const uint32_t b_chunk = (cb & 15u) ? 0u : cb + min((uint32_t)CH_HEAD, in.N) * in.ch * 4u;  // + head of the current chunk
                         const uint32_t b_pp = (npp * 8u + 15u) & ~15u, b_pr = (nrp * 24u + 15u) & ~15u;
                         const uint32_t b_cp = (npc * 8u + 15u) & ~15u, b_cr = (nrc * 24u + 15u) & ~15u;
                         total += b_hist + b_chunk + b_pp + b_pr + b_cp + b_cr;
@@ -298,6 +377,7 @@ __global__ void __launch_bounds__(CH_THREADS) k_chain(const OpHeader *__restrict
                         const uint32_t cb = (in.count >= 2u) ? in.N * in.ch * 4u : 0u;
                         tma_bulk_g2s(dst, in.hist_g, 16u * in.ch * 4u, &bar_full[stage]);
                         if (cb && !(cb & 15u)) tma_bulk_g2s(dst + 16u * in.ch, in.prev_g, cb, &bar_full[stage]);
+                        if (!(cb & 15u)) tma_bulk_g2s(dst + (16u + (cb ? in.N : 0u)) * in.ch, in.cur_g, min((uint32_t)CH_HEAD, in.N) * in.ch * 4u, &bar_full[stage]);
                         const uint32_t b_pp = (Tp->n_prefix * 8u + 15u) & ~15u, b_pr = (Tp->n_runs * 24u + 15u) & ~15u;
                         const uint32_t b_cp = (Tc->n_prefix * 8u + 15u) & ~15u, b_cr = (Tc->n_runs * 24u + 15u) & ~15u;
                         if (b_pp) tma_bulk_g2s(Tp->prefix, tab[in.par_prev].prefix, b_pp, &bar_full[stage]);
@@ -307,7 +387,7 @@ __global__ void __launch_bounds__(CH_THREADS) k_chain(const OpHeader *__restrict
                     }
                 }
                 __syncwarp();
-                if (++stage == CH_STAGES) { stage = 0; ephase ^= 1u; }
+                if (++stage == nstages) { stage = 0; ephase ^= 1u; }
             }
         }
         // ---- tell the consumers there is no more work
@@ -337,16 +417,27 @@ __global__ void __launch_bounds__(CH_THREADS) k_chain(const OpHeader *__restrict
                 for (int e = 0; e < CH_FPT * OC; ++e) acc[it][e] = 0.0f;  // vec![0.0f32; output_size] when there is no base frame
         }
         const uint32_t nb = S->nb;
+        const bool first_base = S->has_base && S->first;
         for (uint32_t q = 0; q < nb; ++q) {
-            const ChainIn &in = S->in[q];
+            const ChainIn *ip = &S->in[q];
+            ChainInRegs in;
+            in.cur_g = ip->cur_g;
+            in.t = ip->t;
+            in.gain = ip->gain;
+            in.has_gain = ip->has_gain;
+            in.sc = ip->ch;
+            in.carry = ip->carry;
+            in.n_prev = ip->n_prev;
+            in.n_cur = max(ip->n_cur, 1u);
+            in.NA = (ip->count >= 2u) ? ip->N : 0u;
             const float *A = s_buf + (size_t)q * buf_floats;
             const SmemPhase *Tp = &s_tab[q * 2u], *Tc = &s_tab[q * 2u + 1u];
-            const bool is_base = S->has_base && S->first && q == 0u;
+            const bool is_base = first_base && q == 0u;
 #pragma unroll
             for (int it = 0; it < ITERS; ++it) {
                 const uint32_t j0 = (ct + it * CH_CONSUMERS) * CH_FPT;
                 if (j0 < F) {
-                    if (in.ch == 2u) chain_input<OC, 2>(in, A, Tp, Tc, F, j0, acc[it], is_base);
+                    if (in.sc == 2u) chain_input<OC, 2>(in, A, Tp, Tc, F, j0, acc[it], is_base);
                     else chain_input<OC, 1>(in, A, Tp, Tc, F, j0, acc[it], is_base);
                 }
             }
@@ -395,7 +486,7 @@ __global__ void __launch_bounds__(CH_THREADS) k_chain(const OpHeader *__restrict
         }
         __syncwarp();
         if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&bar_empty[stage])) : "memory");
-        if (++stage == CH_STAGES) { stage = 0; fphase ^= 1u; }
+        if (++stage == nstages) { stage = 0; fphase ^= 1u; }
     }
 }
 

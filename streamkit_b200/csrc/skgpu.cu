@@ -301,6 +301,7 @@ struct Op {
     uint32_t chain_buf_floats = 0;  // chain: floats per staging buffer
     int chain_oc = 2;             // chain: output channels specialisation
     int chain_iters = 1;          // chain: ceil(F / 1024)
+    uint32_t chain_stages = 2;    // chain: pipeline depth
     uint32_t chain_grid = 0;      // chain: persistent grid size (CTAs per SM x SMs)
     DynTable present;             // mix / chain: per-input presence
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev[2];
@@ -722,7 +723,7 @@ static skgpu_rc validate_chain(const skgpu_plan *p, const skgpu_chain_group *g, 
         skgpu_rc rc = check_range(p, in[i].in_off + p->bank_stride, (uint64_t)N * C * 4, "chain input (bank 1)");
         if (rc) return rc;
         if (in[i].gain_idx != SKGPU_NO_GAIN && in[i].gain_idx >= p->n_gains) return fail(SKGPU_ERR_INVALID, "chain input %u: gain_idx out of range", i);
-        mb = std::max(mb, (16u + N) * C);
+        mb = std::max(mb, (16u + N + (uint32_t)CH_HEAD) * C);
     }
     for (uint32_t i = 0; i < ng; ++i) {
         if (g[i].out_channels != 1 && g[i].out_channels != 2) return fail(SKGPU_ERR_INVALID, "chain group %u: out_channels must be 1 or 2", i);
@@ -748,14 +749,25 @@ static skgpu_rc validate_chain(const skgpu_plan *p, const skgpu_chain_group *g, 
 }
 
 static void chain_size_smem(Op &op, uint32_t max_k, uint32_t buf_floats) {
-    // CH_STAGES pipeline stages, each staging up to kb inputs (buffer + two phase tables). Fewer inputs per batch
-    // when a stage would get so large that fewer than ~3 CTAs fit on an SM.
+    // nstages pipeline stages, each staging up to kb inputs (buffer + two phase tables). Pick (kb, nstages) so that the
+    // number of sessions being loaded at any time per SM -- CTAs/SM x (nstages - 1) -- is as large as shared memory
+    // (227 KB/SM) and threads (2048/SM) allow: that is what hides HBM latency for a streaming kernel.
     uint32_t kb = std::max(1u, std::min<uint32_t>(max_k, CH_MAX_KB));
-    while (kb > 1 && (uint64_t)CH_STAGES * kb * (buf_floats * 4ull + 2 * sizeof(SmemPhase)) > 64u * 1024u) --kb;
+    while (kb > 1 && (uint64_t)2 * kb * (buf_floats * 4ull + 2 * sizeof(SmemPhase)) > 72u * 1024u) --kb;
+    const uint64_t stage = (((uint64_t)kb * buf_floats * 4u + 15u) & ~15ull) + (uint64_t)kb * 2u * sizeof(SmemPhase);
+    const uint64_t static_smem = 9u * 1024u, sm_smem = 227u * 1024u;
+    uint32_t best_ns = 2, best_inflight = 0;
+    for (uint32_t ns = 2; ns <= 2u; ++ns) {  // measured on B200: the kernel is issue-bound, more resident consumer warps beat deeper rings
+        const uint64_t per_cta = stage * ns + static_smem;
+        uint32_t ctas = (uint32_t)std::min<uint64_t>(sm_smem / per_cta, 2048u / CH_THREADS);
+        if (ctas < 1) continue;
+        const uint32_t inflight = ctas * (ns - 1);
+        if (inflight > best_inflight) { best_inflight = inflight; best_ns = ns; }
+    }
     op.chain_kb = kb;
     op.chain_buf_floats = buf_floats;
-    const uint64_t stage = (((uint64_t)kb * buf_floats * 4u + 15u) & ~15ull) + (uint64_t)kb * 2u * sizeof(SmemPhase);
-    op.smem_bytes = (uint32_t)(stage * CH_STAGES);
+    op.chain_stages = best_ns;
+    op.smem_bytes = (uint32_t)(stage * best_ns);
 }
 
 extern "C" skgpu_rc skgpu_plan_add_chain(skgpu_plan *p, const skgpu_chain_group *groups, uint32_t ng, const skgpu_chain_input *inputs, uint32_t ni,
@@ -860,7 +872,7 @@ static skgpu_rc op_event(Op &op, int sub, bool second, cudaStream_t s) {
 }
 
 typedef void (*chain_kernel_t)(const OpHeader *, const skgpu_chain_group *, const skgpu_chain_input *, const uint8_t *, const float *, SlotTables,
-                               uint8_t *, const uint32_t *, uint64_t, uint32_t, uint64_t, uint32_t, uint32_t);
+                               uint8_t *, const uint32_t *, uint64_t, uint32_t, uint64_t, uint32_t, uint32_t, uint32_t);
 static chain_kernel_t chain_kernel(int oc, int iters) {
     if (oc == 2) return iters == 1 ? k_chain<2, 1> : iters == 2 ? k_chain<2, 2> : k_chain<2, 3>;
     return iters == 1 ? k_chain<1, 1> : iters == 2 ? k_chain<1, 2> : k_chain<1, 3>;
@@ -903,7 +915,7 @@ static skgpu_rc launch_ops(skgpu_plan *p, bool time_ops) {
                 const uint32_t grid = std::min<uint32_t>(op.cap, op.chain_grid);
                 auto kfn = chain_kernel(op.chain_oc, op.chain_iters);
                 kfn<<<grid, CH_THREADS, op.smem_bytes, s>>>(op.d_hdr, (const skgpu_chain_group *)op.d_tab, cin, present, gains, c->st, p->arena,
-                                                             p->d_tick, p->bank_stride, op.chain_F, op.results_off, op.chain_kb, op.chain_buf_floats);
+                                                             p->d_tick, p->bank_stride, op.chain_F, op.results_off, op.chain_kb, op.chain_buf_floats, op.chain_stages);
             }
             CU(cudaGetLastError());
             if (time_ops) { skgpu_rc rc = op_event(op, 1, true, s); if (rc) return rc; }
