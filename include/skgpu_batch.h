@@ -232,6 +232,8 @@ skgpu_rc skgpu_plan_finalize(skgpu_plan *plan);
 #define SKGPU_SUBMIT_NO_D2H 2u
 #define SKGPU_SUBMIT_GRAPH 4u    /* replay the captured CUDA graph instead of individual launches */
 #define SKGPU_SUBMIT_TIME_OPS 8u /* record a CUDA event pair around every op (stream mode only) */
+#define SKGPU_SUBMIT_OVERLAP_D2H 16u /* read results back on a second stream so the copy overlaps the NEXT tick's upload
+                                      * (host_out must stay untouched until the next skgpu_tick_wait) */
 
 /* asynchronous: enqueues H2D, kernels, D2H on the context stream and returns */
 skgpu_rc skgpu_tick_submit(skgpu_plan *plan, const void *host_in, void *host_out, uint32_t flags);

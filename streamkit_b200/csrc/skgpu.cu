@@ -50,6 +50,7 @@ static constexpr int DYN_RING = 4;  // staging ring depth for per-tick dynamic t
 struct skgpu_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t stream_d2h = nullptr;   // result read-back runs here so it overlaps the next tick's upload (PCIe is full duplex)
     cudaEvent_t tm0 = nullptr, tm1 = nullptr;
     skgpu_ctx_config cfg{};
     SlotTables st{};
@@ -121,6 +122,7 @@ extern "C" skgpu_rc skgpu_ctx_create(int32_t device_ordinal, const skgpu_ctx_con
     CU(cudaGetDeviceProperties(&prop, device_ordinal));
     c->sm_count = prop.multiProcessorCount;
     CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&c->stream_d2h, cudaStreamNonBlocking));
     CU(cudaEventCreate(&c->tm0));
     CU(cudaEventCreate(&c->tm1));
     const size_t S = cfg->max_streams;
@@ -159,6 +161,7 @@ extern "C" void skgpu_ctx_destroy(skgpu_ctx *c) {
     if (c->d_reset) cudaFree(c->d_reset);
     if (c->l2buf) cudaFree(c->l2buf);
     cudaEventDestroy(c->tm0); cudaEventDestroy(c->tm1);
+    cudaStreamDestroy(c->stream_d2h);
     cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -323,6 +326,8 @@ struct skgpu_plan {
     cudaGraph_t graph = nullptr;
     cudaGraphExec_t graph_exec = nullptr;
     cudaEvent_t e0 = nullptr, e1 = nullptr, e2 = nullptr, e3 = nullptr;
+    cudaEvent_t ev_kernels_done = nullptr, ev_d2h_done = nullptr;  // cross-stream ordering for overlapped read-back
+    bool d2h_pending = false;
     bool timing_valid = false;
 };
 
@@ -371,6 +376,8 @@ extern "C" skgpu_rc skgpu_plan_create(skgpu_ctx *c, size_t arena_bytes, skgpu_pl
     cudaError_t e = cudaMalloc((void **)&p->arena, arena_bytes);
     if (e != cudaSuccess) { delete p; return fail(SKGPU_ERR_NOMEM, "cudaMalloc(%zu) for the tick arena failed: %s", arena_bytes, cudaGetErrorString(e)); }
     CU(cudaEventCreate(&p->e0)); CU(cudaEventCreate(&p->e1)); CU(cudaEventCreate(&p->e2)); CU(cudaEventCreate(&p->e3));
+    CU(cudaEventCreateWithFlags(&p->ev_kernels_done, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&p->ev_d2h_done, cudaEventDisableTiming));
     CU(cudaMalloc((void **)&p->d_tick, 16));
     CU(cudaMemset(p->d_tick, 0, 16));
     *out = p;
@@ -397,6 +404,7 @@ extern "C" void skgpu_plan_destroy(skgpu_plan *p) {
     if (p->graph) cudaGraphDestroy(p->graph);
     cudaFree(p->arena);
     cudaFree(p->d_tick);
+    cudaEventDestroy(p->ev_kernels_done); cudaEventDestroy(p->ev_d2h_done);
     cudaEventDestroy(p->e0); cudaEventDestroy(p->e1); cudaEventDestroy(p->e2); cudaEventDestroy(p->e3);
     delete p;
 }
@@ -1003,10 +1011,13 @@ extern "C" skgpu_rc skgpu_tick_submit(skgpu_plan *p, const void *host_in, void *
     if (rc) return rc;
     rc = upload_dirty(p);
     if (rc) return rc;
+    const bool overlap = (flags & SKGPU_SUBMIT_OVERLAP_D2H) != 0 && do_d2h;
     CU(cudaEventRecord(p->e0, s));
     if (do_h2d) CU(cudaMemcpyAsync(p->arena + p->h2d_off + (p->tick & 1ull) * p->bank_stride, host_in, p->h2d_bytes, cudaMemcpyHostToDevice, s));
     p->tick++;
     CU(cudaEventRecord(p->e1, s));
+    // the kernels overwrite the output range: they must not start before the previous tick's read-back has finished
+    if (p->d2h_pending) CU(cudaStreamWaitEvent(s, p->ev_d2h_done, 0));
     if ((flags & SKGPU_SUBMIT_GRAPH) && p->graph_exec) {
         CU(cudaGraphLaunch(p->graph_exec, s));
     } else {
@@ -1014,8 +1025,18 @@ extern "C" skgpu_rc skgpu_tick_submit(skgpu_plan *p, const void *host_in, void *
         if (rc) return rc;
     }
     CU(cudaEventRecord(p->e2, s));
-    if (do_d2h) CU(cudaMemcpyAsync(host_out, p->arena + p->d2h_off, p->d2h_bytes, cudaMemcpyDeviceToHost, s));
-    CU(cudaEventRecord(p->e3, s));
+    if (overlap) {
+        // read-back on the second stream: overlaps the NEXT tick's upload (H2D and D2H use opposite PCIe directions)
+        CU(cudaEventRecord(p->ev_kernels_done, s));
+        CU(cudaStreamWaitEvent(c->stream_d2h, p->ev_kernels_done, 0));
+        CU(cudaMemcpyAsync(host_out, p->arena + p->d2h_off, p->d2h_bytes, cudaMemcpyDeviceToHost, c->stream_d2h));
+        CU(cudaEventRecord(p->ev_d2h_done, c->stream_d2h));
+        CU(cudaEventRecord(p->e3, c->stream_d2h));
+        p->d2h_pending = true;
+    } else {
+        if (do_d2h) CU(cudaMemcpyAsync(host_out, p->arena + p->d2h_off, p->d2h_bytes, cudaMemcpyDeviceToHost, s));
+        CU(cudaEventRecord(p->e3, s));
+    }
     p->timing_valid = true;
     return SKGPU_OK;
 }
@@ -1024,6 +1045,8 @@ extern "C" skgpu_rc skgpu_tick_wait(skgpu_plan *p, skgpu_tick_timing *t) {
     if (!p) return fail(SKGPU_ERR_INVALID, "null plan");
     CU(cudaSetDevice(p->ctx->device));
     CU(cudaStreamSynchronize(p->ctx->stream));
+    CU(cudaStreamSynchronize(p->ctx->stream_d2h));
+    p->d2h_pending = false;
     if (t) {
         memset(t, 0, sizeof(*t));
         if (p->timing_valid) {
@@ -1096,6 +1119,9 @@ extern "C" skgpu_rc skgpu_timer_start(skgpu_ctx *c) {
 extern "C" skgpu_rc skgpu_timer_stop(skgpu_ctx *c) {
     if (!c) return fail(SKGPU_ERR_INVALID, "null context");
     CU(cudaSetDevice(c->device));
+    // the stop mark covers the read-back stream too
+    CU(cudaEventRecord(c->tm1, c->stream_d2h));
+    CU(cudaStreamWaitEvent(c->stream, c->tm1, 0));
     CU(cudaEventRecord(c->tm1, c->stream));
     return SKGPU_OK;
 }
@@ -1110,6 +1136,7 @@ extern "C" skgpu_rc skgpu_ctx_sync(skgpu_ctx *c) {
     if (!c) return fail(SKGPU_ERR_INVALID, "null context");
     CU(cudaSetDevice(c->device));
     CU(cudaStreamSynchronize(c->stream));
+    CU(cudaStreamSynchronize(c->stream_d2h));
     return SKGPU_OK;
 }
 extern "C" skgpu_rc skgpu_ctx_flush_l2(skgpu_ctx *c) {

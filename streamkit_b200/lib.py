@@ -19,7 +19,7 @@ CVT_F32_TO_F32, CVT_F32_TO_S16, CVT_S16_TO_F32 = 0, 1, 2
 RS_TO_FIFO = 1
 MIX_IN_UNIQUE, MIX_IN_FIFO = 1, 2
 MIX_OUT_S16 = 1
-SUBMIT_NO_H2D, SUBMIT_NO_D2H, SUBMIT_GRAPH, SUBMIT_TIME_OPS = 1, 2, 4, 8
+SUBMIT_NO_H2D, SUBMIT_NO_D2H, SUBMIT_GRAPH, SUBMIT_TIME_OPS, SUBMIT_OVERLAP_D2H = 1, 2, 4, 8, 16
 
 
 class CtxConfig(C.Structure):

@@ -104,3 +104,20 @@ int main(void){ printf("%zu %zu %zu %zu %zu %zu %zu %zu\n", sizeof(sk_result), s
         subprocess.check_call(["gcc", "-std=c11", "-I", os.path.join(ROOT, "include"), "-o", os.path.join(d, "t"), os.path.join(d, "t.c")])
         got = [int(v) for v in subprocess.check_output([os.path.join(d, "t")], text=True).split()]
     assert got == [16, 24, 24, 12, 24, 72, 56, 48]
+
+
+def test_plugin_libraries_export_the_entry_point_and_metadata_without_a_gpu():
+    """the host reads plugin metadata before any instance exists (plugin-native/src/lib.rs:107): that must work on a box
+    without a GPU; creating an instance there must fail (NULL handle), never fall back to the CPU"""
+    from tests import plugin_host as ph
+    csrc = os.path.join(ROOT, "streamkit_b200", "csrc")
+    for so, kind in (("libskgpu_plugin_gain.so", "gpu_gain"), ("libskgpu_plugin_resampler.so", "gpu_resampler"),
+                     ("libskgpu_plugin_pcm16.so", "gpu_pcm16")):
+        p = ph.NativePlugin(os.path.join(csrc, so))           # checks version == 2 like lib.rs:90-95
+        assert p.kind == kind and p.inputs == ["in"] and p.outputs == ["out"]
+        assert "::" not in p.kind and not p.kind.startswith("core")   # plugin kind rules (lib.rs:307-333)
+        import json
+        json.loads(p.param_schema)
+        if not _gpu_present():
+            with pytest.raises(ph.PluginError, match="failed to create instance"):
+                p.create('{"gain": 1.0, "target_sample_rate": 48000}')

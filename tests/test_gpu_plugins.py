@@ -1,0 +1,185 @@
+"""GPU tests of the drop-in boundary: the native plugin ABI v2 libraries (libskgpu_plugin_*.so) driven by the same
+host shim that drives the reference's own C plugin, and the C++ node mirror (libskgpu_nodes.so)."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+from oracle import sko
+from streamkit_b200 import synth
+from tests import plugin_host as ph
+
+pytestmark = pytest.mark.gpu
+CSRC = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "streamkit_b200", "csrc")
+
+
+def bits(a):
+    return np.ascontiguousarray(a, dtype=np.float32).view(np.uint32)
+
+
+def test_gpu_gain_plugin_is_a_drop_in_for_the_reference_c_plugin():
+    gpu = ph.NativePlugin(os.path.join(CSRC, "libskgpu_plugin_gain.so"))
+    assert gpu.kind == "gpu_gain" and gpu.inputs == ["in"] and gpu.outputs == ["out"]
+    assert gpu.input_formats == [(0, (0, 0, 0))]            # RawAudio{0, 0, F32}: same wildcard pin as gain.rs:89-101
+    ref = ph.NativePlugin(sko.REF_GAIN_PLUGIN) if os.path.exists(sko.REF_GAIN_PLUGIN) else None
+    gi = gpu.create('{"gain": 2.0}')
+    ri = ref.create('{"gain": 2.0}') if ref else None
+    # reference unit test gain.rs:233-286: 50 stereo frames of 0.5 at gain 2.0 -> 100 samples of ~1.0
+    out = gi.process_audio(48000, 2, np.full(100, 0.5, np.float32))
+    assert len(out) == 1 and out[0][0] == "out"
+    pkt = out[0][1]
+    assert pkt["sample_rate"] == 48000 and pkt["channels"] == 2 and pkt["samples"].size == 100
+    assert np.all(np.abs(pkt["samples"] - 1.0) < 1e-3)
+    x = synth.uniform_pcm(9, 1920)
+    for g in (0.0, 0.37, 1.0, 3.999, 4.0):
+        ok, _ = gi.update_params('{"gain": %r}' % g)
+        assert ok
+        y = gi.process_audio(48000, 2, x)[0][1]["samples"]
+        assert np.array_equal(bits(y), bits(sko.gain(x, np.float32(g))))
+        if ri:
+            ri.update_params('{"gain": %r}' % g)
+            assert np.array_equal(bits(y), bits(ri.process_audio(48000, 2, x)[0][1]["samples"]))
+    # invalid live update: rejected, old gain stays (gain.rs:157-171)
+    ok, msg = gi.update_params('{"gain": 4.5}')
+    assert not ok and "must be between" in msg
+    ok, msg = gi.update_params('{"gain": "loud"}')
+    assert not ok
+    y = gi.process_audio(48000, 2, x)[0][1]["samples"]
+    assert np.array_equal(bits(y), bits(sko.gain(x, np.float32(4.0))))
+    # variable packet sizes, empty packet
+    for n in (1, 7, 960, 5000):
+        xx = synth.uniform_pcm(n, n)
+        assert np.array_equal(bits(gi.process_audio(16000, 1, xx)[0][1]["samples"]), bits(sko.gain(xx, np.float32(4.0))))
+    assert gi.flush() == []
+    gi.destroy()
+    if ri:
+        ri.destroy()
+    # construction with an out-of-range gain fails (gain.rs:81-84 -> StreamKitError::Configuration)
+    with pytest.raises(ph.PluginError):
+        gpu.create('{"gain": 9.0}')
+    # missing / empty params fall back to the default gain 1.0 (gain.rs:29,38-42)
+    d = gpu.create(None)
+    assert np.array_equal(bits(d.process_audio(48000, 2, x)[0][1]["samples"]), bits(x))
+    d.destroy()
+
+
+@pytest.mark.parametrize("in_rate,target,chunk,ofs,ch,pkt_frames", [
+    (48000, 16000, 960, 960, 1, 960), (44100, 48000, 960, 960, 2, 882), (48000, 24000, 960, 0, 2, 480), (16000, 48000, 320, 480, 1, 320),
+])
+def test_gpu_resampler_plugin_matches_reference_node_semantics(in_rate, target, chunk, ofs, ch, pkt_frames):
+    plug = ph.NativePlugin(os.path.join(CSRC, "libskgpu_plugin_resampler.so"))
+    assert plug.kind == "gpu_resampler"
+    inst = plug.create('{"target_sample_rate": %d, "chunk_frames": %d, "output_frame_size": %d}' % (target, chunk, ofs))
+    node = sko.ResamplerNode(target, chunk, ofs)
+    got = []
+    for c in range(9):
+        x = synth.tone_streams(17, c, 1, pkt_frames, ch, in_rate)[0]
+        got += [p for _, p in inst.process_audio(in_rate, ch, x)]
+        node.push(in_rate, ch, x)
+    got += [p for _, p in inst.flush()]
+    node.finish()
+    assert len(got) == len(node.out) and len(got) > 0
+    for a, b in zip(got, node.out):
+        assert a["sample_rate"] == b["sample_rate"] == target and a["channels"] == b["channels"] == ch
+        assert a["samples"].size == b["samples"].size
+        assert np.array_equal(bits(a["samples"]), bits(b["samples"]))
+    inst.destroy()
+
+
+def test_gpu_resampler_plugin_errors():
+    plug = ph.NativePlugin(os.path.join(CSRC, "libskgpu_plugin_resampler.so"))
+    for bad in ('{"target_sample_rate": 0}', '{"target_sample_rate": 48000, "chunk_frames": 0}',
+                '{"target_sample_rate": 48000, "output_frame_size": 1000}', '{"chunk_frames": 960}'):
+        with pytest.raises(ph.PluginError):
+            plug.create(bad)                                   # resampler.rs:81-102, parse_config_required
+    inst = plug.create('{"target_sample_rate": 48000}')
+    inst.process_audio(44100, 2, np.zeros(882 * 2, np.float32))
+    with pytest.raises(ph.PluginError, match="Audio format changed mid-stream: expected 44100Hz/2ch, got 48000Hz/2ch"):
+        inst.process_audio(48000, 2, np.zeros(960 * 2, np.float32))   # fatal for the node (resampler.rs:253-279)
+    inst.destroy()
+    # equal rates: pure re-framing, no DSP (resampler.rs:299-373)
+    inst = plug.create('{"target_sample_rate": 48000, "output_frame_size": 480}')
+    x = synth.uniform_pcm(1, 700)
+    out = inst.process_audio(48000, 1, x) + inst.flush()
+    assert [p["samples"].size for _, p in out] == [480, 220]
+    assert np.array_equal(bits(np.concatenate([p["samples"] for _, p in out])), bits(x))
+    inst.destroy()
+
+
+def test_gpu_pcm16_plugin_bit_exact():
+    plug = ph.NativePlugin(os.path.join(CSRC, "libskgpu_plugin_pcm16.so"))
+    assert plug.kind == "gpu_pcm16"
+    inst = plug.create('{"gain": 1.5}')
+    x = synth.uniform_pcm(5, 1920, over_range_frac=0.05)
+    out = inst.process_audio(48000, 2, x)
+    assert out[0][1]["kind"] == "binary"
+    s = np.frombuffer(out[0][1]["data"], dtype="<i2")
+    assert np.array_equal(s, sko.gain_f32_to_s16(x, np.float32(1.5)))
+    inst.destroy()
+
+
+def _nodes():
+    lib = C.CDLL(os.path.join(CSRC, "libskgpu_nodes.so"))
+    lib.skn_mixer_create.restype = C.c_void_p
+    lib.skn_mixer_create.argtypes = [C.c_char_p]
+    lib.skn_mixer_destroy.argtypes = [C.c_void_p]
+    lib.skn_mixer_num_input_pins.restype = C.c_uint32
+    lib.skn_mixer_num_input_pins.argtypes = [C.c_void_p]
+    lib.skn_mixer_pin_name.argtypes = [C.c_void_p, C.c_uint32, C.c_char_p, C.c_size_t]
+    lib.skn_last_error.restype = C.c_char_p
+    return lib
+
+
+class SknFrame(C.Structure):
+    _fields_ = [("samples", C.POINTER(C.c_float)), ("n_samples", C.c_uint32), ("sample_rate", C.c_uint32), ("channels", C.c_uint16),
+                ("unique", C.c_uint16)]
+
+
+def _mix(lib, h, clocked, frames, rate=48000):
+    keep = [np.ascontiguousarray(f[0], np.float32) for f in frames]
+    arr = (SknFrame * max(len(frames), 1))()
+    for i, (f, k) in enumerate(zip(frames, keep)):
+        arr[i] = SknFrame(k.ctypes.data_as(C.POINTER(C.c_float)), k.size, rate, f[1], 1 if f[2] else 0)
+    out = np.zeros(65536, np.float32)
+    ol, oc, orate = C.c_size_t(), C.c_uint16(), C.c_uint32()
+    rc = lib.skn_mixer_mix(C.c_void_p(h), clocked, arr, len(frames), out.ctypes.data_as(C.POINTER(C.c_float)), out.size, C.byref(ol), C.byref(oc), C.byref(orate))
+    assert rc == 0, lib.skn_last_error()
+    return out[: ol.value].copy(), oc.value
+
+
+def test_mixer_node_mirror_reference_scenarios():
+    lib = _nodes()
+    h = lib.skn_mixer_create(b'{"sync_timeout_ms": 100, "num_inputs": 2}')
+    assert lib.skn_mixer_num_input_pins(C.c_void_p(h)) == 2            # in_0, in_1 (mixer.rs:128-143)
+    buf = C.create_string_buffer(16)
+    lib.skn_mixer_pin_name(C.c_void_p(h), 1, buf, 16)
+    assert buf.value == b"in_1"
+    F = lambda v, ch, n=10: (np.full(n * ch, v, np.float32), ch, True)
+    # test_mixer_continues_after_eof_with_sticky_channels (mixer.rs:1705-1760)
+    o, oc = _mix(lib, h, 0, [F(0.5, 2), F(0.3, 1)])
+    assert oc == 2 and abs(o[0] - 0.8) < 1e-3
+    o, oc = _mix(lib, h, 0, [F(0.25, 1)])
+    assert oc == 2 and o.size == 20 and abs(o[0] - 0.25) < 1e-3 and abs(o[1] - 0.25) < 1e-3
+    lib.skn_mixer_destroy(C.c_void_p(h))
+    # random cross-check against the oracle incl. sticky state
+    rng = np.random.default_rng(8)
+    h = lib.skn_mixer_create(None)
+    seen = 0
+    for _ in range(25):
+        frames = []
+        for _ in range(int(rng.integers(1, 6))):
+            ch = int(rng.choice([1, 2]))
+            frames.append((rng.standard_normal(int(rng.integers(1, 300)) * ch).astype(np.float32), ch, bool(rng.random() < 0.7)))
+        want, oc_w = sko.mix_sync(frames, seen)
+        seen = max(seen, oc_w)
+        got, oc = _mix(lib, h, 0, frames)
+        assert oc == oc_w and np.array_equal(bits(got), bits(want))
+    lib.skn_mixer_destroy(C.c_void_p(h))
+    # clocked (mixer.rs:2047-2052, :2097-2102)
+    h = lib.skn_mixer_create(b'{"clocked": {"sample_rate": 48000, "frame_samples_per_channel": 10, "jitter_buffer_frames": 2, "generate_silence": false}}')
+    o, oc = _mix(lib, h, 1, [F(0.5, 2), F(0.3, 2)])
+    assert oc == 2 and o.size == 20 and np.all(np.abs(o - 0.8) < 1e-3)
+    o, oc = _mix(lib, h, 1, [F(0.75, 2)])
+    assert np.all(np.abs(o - 0.75) < 1e-3)
+    lib.skn_mixer_destroy(C.c_void_p(h))
