@@ -34,7 +34,7 @@ def _run(cmd: list[str]) -> None:
 
 
 def build_all(force: bool = False) -> None:
-    hdrs = [os.path.join(CSRC, h) for h in ("kernels.cuh", "phase_runs.h")] + [os.path.join(ROOT, "include", "skgpu_batch.h")]
+    hdrs = sorted(os.path.join(CSRC, h) for h in os.listdir(CSRC) if h.endswith((".cuh", ".h"))) + [os.path.join(ROOT, "include", "skgpu_batch.h")]
     # 1. the product: libskgpu.so (CUDA kernels + batch C ABI)
     tgt = os.path.join(CSRC, "libskgpu.so")
     src = os.path.join(CSRC, "skgpu.cu")

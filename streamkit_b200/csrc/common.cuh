@@ -44,11 +44,15 @@ struct SlotCfgUpload {     // host -> device (re)configuration of one slot (k_co
     int32_t end_idx;
 };
 
+constexpr uint32_t SK_SIDE_STRIDE = 1408u;   // >= sizeof(SkPhaseTable) and >= 40*8 + 40*24 + 128
+constexpr uint32_t SK_SIDE_HIST = 128u;      // 16 frames x 2 channels x 4 bytes
+
 struct SlotTables {     // per-stream state + configuration, all device pointers
     SlotRec *rec;           // [slot]
     float *hist;            // [slot][16 * max_channels]: the 16 frames before the oldest chunk that still has
                             // unconsumed output (plain resample op: before the next chunk; chain op: before the previous one)
-    SkPhaseTable *tab;      // [slot][2]: phase tables of the two most recent chunks, indexed by (chunk number & 1)
+    uint8_t *side;          // [slot][2][SK_SIDE_STRIDE]: per (slot, chunk number & 1) record. Plain resample op: a SkPhaseTable.
+                            // Fused chain: compact [prefix cap_np | runs cap_nr | 128 B history before that chunk] (one TMA copy)
     float *fifo;            // [slot][fifo_frames * max_channels] (may be null): unfused re-framing ring
     unsigned long long *fifo_w;  // total frames ever written
     unsigned long long *fifo_r;  // total frames ever consumed
@@ -57,6 +61,13 @@ struct SlotTables {     // per-stream state + configuration, all device pointers
 };
 
 // ------------------------------------------------------------------ small helpers
+
+__device__ __forceinline__ uint8_t *slot_side(const SlotTables &st, uint32_t slot, uint32_t par) {
+    return st.side + ((size_t)slot * 2u + par) * SK_SIDE_STRIDE;
+}
+__device__ __forceinline__ SkPhaseTable *slot_tab(const SlotTables &st, uint32_t slot, uint32_t par) {
+    return reinterpret_cast<SkPhaseTable *>(slot_side(st, slot, par));
+}
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -126,6 +137,18 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
         "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
 
+// ---- cp.async (LDGSTS): asynchronous global -> shared copies that need no destination registers
+__device__ __forceinline__ void cp_async4(void *dst_smem, const void *src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async8(void *dst_smem, const void *src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async16(void *dst_smem, const void *src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
 // rubato interp_lin: (1 - x) * y0 + x * y1, every operation rounded to f32
 __device__ __forceinline__ float interp_lin(float frac, float y0, float y1) {
     return __fadd_rn(__fmul_rn(__fsub_rn(1.0f, frac), y0), __fmul_rn(frac, y1));
@@ -163,6 +186,42 @@ __device__ __forceinline__ double phase_eval_smem(const SmemPhase *T, double t, 
     return __dadd_rn(__fma_rn((double)(rn.k_e - 1u - rn.k_a), rn.delta, rn.x_a), t);  // gap element
 }
 
+// ---- pointer-based view of a staged phase table (k_chain sizes the staging area per op, not for the worst case)
+struct PhaseView {
+    const double *prefix;
+    const SkRun *runs;
+    uint32_t n_out, n_prefix, n_runs;
+};
+
+__device__ __forceinline__ double pv_eval(const PhaseView &T, double t, uint32_t k) {
+    if (k < T.n_prefix) return T.prefix[k];
+    if (T.n_runs == 0u) return 0.0;   // empty table (a stream's first chunk has no predecessor): value is never used
+    uint32_t r = T.n_runs - 1u;
+    while (r > 0u && T.runs[r].k_a > k) --r;
+    const SkRun rn = T.runs[r];
+    if (k < rn.k_e) return __fma_rn((double)(k - rn.k_a), rn.delta, rn.x_a);
+    return __dadd_rn(__fma_rn((double)(rn.k_e - 1u - rn.k_a), rn.delta, rn.x_a), t);  // gap element
+}
+
+// idx of 4 consecutive outputs k0..k0+3, each index clamped to n_out - 1 (callers discard the clamped ones)
+__device__ __forceinline__ void pv_eval4(const PhaseView &T, double t, uint32_t k0, double *x) {
+    if (k0 >= T.n_prefix && T.n_runs > 0u) {
+        uint32_t r = T.n_runs - 1u;
+        while (r > 0u && T.runs[r].k_a > k0) --r;
+        const SkRun rn = T.runs[r];
+        if (k0 + 3u < rn.k_e) {   // all four inside one run: consecutive members differ by exactly delta
+            x[0] = __fma_rn((double)(k0 - rn.k_a), rn.delta, rn.x_a);
+            x[1] = __dadd_rn(x[0], rn.delta);
+            x[2] = __dadd_rn(x[1], rn.delta);
+            x[3] = __dadd_rn(x[2], rn.delta);
+            return;
+        }
+    }
+    const uint32_t last = T.n_out - 1u;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) x[i] = pv_eval(T, t, min(k0 + (uint32_t)i, last));
+}
+
 // split idx into buffer position (floor(idx) + 16 = start_idx + 2*POLYNOMIAL_LEN) and f32 fraction
 __device__ __forceinline__ void phase_split(double x, uint32_t &p, float &frac) {
     const int fl = __double2int_rd(x);
@@ -196,6 +255,10 @@ __global__ void k_config_slots(const SlotCfgUpload *__restrict__ cfgs, uint32_t 
     const SlotCfgUpload c = cfgs[i];
     const uint32_t slot = c.slot;
     for (uint32_t s = threadIdx.x; s < 16u * st.max_channels; s += blockDim.x) st.hist[(size_t)slot * 16u * st.max_channels + s] = 0.0f;
+    {   // both side records (phase tables / chain history) start zeroed
+        uint4 *sd = reinterpret_cast<uint4 *>(slot_side(st, slot, 0));
+        for (uint32_t s = threadIdx.x; s < 2u * SK_SIDE_STRIDE / 16u; s += blockDim.x) sd[s] = make_uint4(0u, 0u, 0u, 0u);
+    }
     if (threadIdx.x == 0) {
         SlotRec r;
         r.t_ratio = c.t_ratio;

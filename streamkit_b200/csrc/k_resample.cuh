@@ -26,7 +26,7 @@ __global__ void __launch_bounds__(PHASE_THREADS) k_phase(const OpHeader *__restr
     SlotRec *rec = st.rec + slot;
     const uint32_t c = rec->chunk_count;
     const uint32_t par = c & 1u;
-    SkPhaseTable *T = st.tab + (size_t)slot * 2u + par;
+    SkPhaseTable *T = slot_tab(st, slot, par);
     double idx_end;
     const uint32_t n = sk_phase_table(rec->last_index, rec->t_ratio, rec->end_idx, T, &idx_end);
     rec->last_index = __dsub_rn(idx_end, (double)rec->chunk);  // self.last_index = idx - chunk_size as f64
@@ -108,7 +108,7 @@ __global__ void __launch_bounds__(RS_THREADS) k_resample(const OpHeader *__restr
     }
     // phase table of the chunk k_phase just processed (chunk_count was already advanced) -> smem, overlapping the bulk copy
     const uint32_t par = (rec.chunk_count - 1u) & 1u;
-    load_phase_table(&s_tab, st.tab + (size_t)slot * 2u + par, rec.n_out[par], rec.n_prefix[par], rec.n_runs[par], threadIdx.x, RS_THREADS);
+    load_phase_table(&s_tab, slot_tab(st, slot, par), rec.n_out[par], rec.n_prefix[par], rec.n_runs[par], threadIdx.x, RS_THREADS);
     __syncthreads();
     if (staged && tma_ok) mbar_wait(&bar, 0);
 

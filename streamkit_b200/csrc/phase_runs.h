@@ -86,7 +86,10 @@ SK_HD double sk_dfma(double a, double b, double c) {
 // Generates the phase table of one process() call.
 //   last_index : rubato's self.last_index on entry;  t : 1.0 / resample_ratio;  end_idx : chunk - 9 - ceil(t)
 // Returns n_out; *idx_end receives the final idx (the caller stores last_index' = idx_end - chunk).
-SK_HD uint32_t sk_phase_table(double last_index, double t, int32_t end_idx, SkPhaseTable *T, double *idx_end) {
+// Pointer-based form: prefix[] (capacity cap_np) and runs[] (capacity cap_nr) may live anywhere (a compact per-op layout
+// in HBM for the fused chain). Sizes and the overflow flag are returned through out-parameters.
+SK_HD uint32_t sk_phase_table_ex(double last_index, double t, int32_t end_idx, double *prefix_out, uint32_t cap_np, SkRun *runs_out,
+                                 uint32_t cap_nr, uint32_t *n_prefix_out, uint32_t *n_runs_out, uint32_t *overflow_out, double *idx_end) {
     const double end = (double)end_idx;
     double x = last_index;
     uint32_t k = 0, np = 0, nr = 0;
@@ -102,7 +105,7 @@ SK_HD uint32_t sk_phase_table(double last_index, double t, int32_t end_idx, SkPh
 #define SK_FLUSH_CUR()                                              \
     do {                                                            \
         if (cur_valid) {                                            \
-            if (nr <= SK_RUNS_MAX && nr > 0) T->runs[nr - 1] = cur; \
+            if (nr <= cap_nr && nr > 0) runs_out[nr - 1] = cur;     \
         }                                                           \
     } while (0)
 
@@ -125,7 +128,7 @@ SK_HD uint32_t sk_phase_table(double last_index, double t, int32_t end_idx, SkPh
         cnt = (key == prev_key) ? cnt + 1 : 1;
         prev_key = key;
         const bool can_open = cnt >= 3 && strict && prev_strict && k >= 1;
-        if (can_open && !(in_prefix && !(xb > 0.0) && np < SK_PREFIX_MAX)) {
+        if (can_open && !(in_prefix && !(xb > 0.0) && np < cap_np)) {
             // a = element k-2, b = element k-1 (value xb), c = this element: open a run anchored at b
             if (in_prefix) {  // b leaves the prefix and becomes the first table entry
                 in_prefix = false;
@@ -135,7 +138,7 @@ SK_HD uint32_t sk_phase_table(double last_index, double t, int32_t end_idx, SkPh
             if (!b_has_entry) {
                 SK_FLUSH_CUR();
                 ++nr;
-                if (nr > SK_RUNS_MAX) ovf = 1;
+                if (nr > cap_nr) ovf = 1;
             }
             cur.x_a = xb;
             cur.delta = x - xb;  // exact: same binade
@@ -170,8 +173,8 @@ SK_HD uint32_t sk_phase_table(double last_index, double t, int32_t end_idx, SkPh
         }
         // ---- element outside any run
         if (in_prefix) {
-            if (np < SK_PREFIX_MAX) {
-                T->prefix[np++] = x;
+            if (np < cap_np) {
+                prefix_out[np++] = x;
                 prev_strict = strict;
                 xb = x;
                 ++k;
@@ -184,7 +187,7 @@ SK_HD uint32_t sk_phase_table(double last_index, double t, int32_t end_idx, SkPh
         if (!gap_ok) {
             SK_FLUSH_CUR();
             ++nr;
-            if (nr > SK_RUNS_MAX) ovf = 1;
+            if (nr > cap_nr) ovf = 1;
             cur.x_a = x;
             cur.delta = 0.0;
             cur.k_a = k;
@@ -197,12 +200,24 @@ SK_HD uint32_t sk_phase_table(double last_index, double t, int32_t end_idx, SkPh
     }
     SK_FLUSH_CUR();
 #undef SK_FLUSH_CUR
-    T->n_out = k;
-    T->n_prefix = np < k ? np : k;
-    T->n_runs = nr < SK_RUNS_MAX ? nr : SK_RUNS_MAX;
-    T->overflow = ovf;
+    *n_prefix_out = np < k ? np : k;
+    *n_runs_out = nr < cap_nr ? nr : cap_nr;
+    *overflow_out = ovf;
     *idx_end = x;
     return k;
+}
+
+// Generates the phase table of one process() call into a SkPhaseTable.
+//   last_index : rubato's self.last_index on entry;  t : 1.0 / resample_ratio;  end_idx : chunk - 9 - ceil(t)
+// Returns n_out; *idx_end receives the final idx (the caller stores last_index' = idx_end - chunk).
+SK_HD uint32_t sk_phase_table(double last_index, double t, int32_t end_idx, SkPhaseTable *T, double *idx_end) {
+    uint32_t np, nr, ovf;
+    const uint32_t n = sk_phase_table_ex(last_index, t, end_idx, T->prefix, SK_PREFIX_MAX, T->runs, SK_RUNS_MAX, &np, &nr, &ovf, idx_end);
+    T->n_out = n;
+    T->n_prefix = np;
+    T->n_runs = nr;
+    T->overflow = ovf;
+    return n;
 }
 
 // Consumer side: idx of output k (k < n_out). `r` is a cursor the caller may carry between calls with

@@ -10,6 +10,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -131,10 +132,10 @@ extern "C" skgpu_rc skgpu_ctx_create(int32_t device_ordinal, const skgpu_ctx_con
     st.fifo_frames = cfg->fifo_frames;
     CU(dalloc(&st.rec, S));
     CU(dalloc(&st.hist, S * 16 * cfg->max_channels));
-    CU(dalloc(&st.tab, S * 2));
+    CU(dalloc(&st.side, S * 2 * SK_SIDE_STRIDE));
     CU(cudaMemset(st.rec, 0, S * sizeof(SlotRec)));
     CU(cudaMemset(st.hist, 0, S * 16 * cfg->max_channels * sizeof(float)));
-    CU(cudaMemset(st.tab, 0, S * 2 * sizeof(SkPhaseTable)));
+    CU(cudaMemset(st.side, 0, S * 2 * SK_SIDE_STRIDE));
     if (cfg->fifo_frames) {
         CU(dalloc(&st.fifo, S * cfg->fifo_frames * cfg->max_channels));
         CU(dalloc(&st.fifo_w, S));
@@ -156,7 +157,7 @@ extern "C" void skgpu_ctx_destroy(skgpu_ctx *c) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     SlotTables &st = c->st;
-    cudaFree(st.rec); cudaFree(st.hist); cudaFree(st.tab);
+    cudaFree(st.rec); cudaFree(st.hist); cudaFree(st.side);
     if (st.fifo) { cudaFree(st.fifo); cudaFree(st.fifo_w); cudaFree(st.fifo_r); }
     if (c->d_reset) cudaFree(c->d_reset);
     if (c->l2buf) cudaFree(c->l2buf);
@@ -304,7 +305,8 @@ struct Op {
     uint32_t chain_buf_floats = 0;  // chain: floats per staging buffer
     int chain_oc = 2;             // chain: output channels specialisation
     int chain_iters = 1;          // chain: ceil(F / 1024)
-    uint32_t chain_stages = 2;    // chain: pipeline depth
+    ChainDims chain_dm{};         // chain: staging-ring geometry passed to the kernel
+    ChainRec *d_rec = nullptr;    // chain: per-input records written by k_phase_chain every tick
     uint32_t chain_grid = 0;      // chain: persistent grid size (CTAs per SM x SMs)
     DynTable present;             // mix / chain: per-input presence
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev[2];
@@ -385,7 +387,7 @@ extern "C" skgpu_rc skgpu_plan_create(skgpu_ctx *c, size_t arena_bytes, skgpu_pl
 }
 
 static void op_free(Op &op) {
-    cudaFree(op.d_tab); cudaFree(op.d_tab2); cudaFree(op.d_hdr);
+    cudaFree(op.d_tab); cudaFree(op.d_tab2); cudaFree(op.d_hdr); cudaFree(op.d_rec);
     if (op.h_tab) cudaFreeHost(op.h_tab);
     if (op.h_tab2) cudaFreeHost(op.h_tab2);
     if (op.h_hdr) cudaFreeHost(op.h_hdr);
@@ -712,8 +714,27 @@ extern "C" uint64_t skgpu_plan_tick_count(const skgpu_plan *p) { return p ? p->t
 
 // ---- chain
 
+// Upper bounds of the phase-table sizes a stream configuration can produce: run the (host-compiled) generator for the
+// first chunk and for a spread of steady-state phases. The kernel re-checks at run time (status bit1).
+static void phase_table_bounds(double t, int32_t end_idx, uint32_t *np, uint32_t *nr) {
+    SkPhaseTable T;
+    double idx_end;
+    uint32_t mp = 0, mr = 0;
+    sk_phase_table(-4.0, t, end_idx, &T, &idx_end);
+    mp = std::max(mp, T.n_prefix); mr = std::max(mr, T.n_runs);
+    const double lo = -(9.0 + std::ceil(t));
+    for (int i = 0; i < 64; ++i) {
+        sk_phase_table(lo + t * (i + 0.37) / 64.0, t, end_idx, &T, &idx_end);
+        mp = std::max(mp, T.n_prefix); mr = std::max(mr, T.n_runs);
+    }
+    *np = mp; *nr = mr;
+}
+
 static skgpu_rc validate_chain(const skgpu_plan *p, const skgpu_chain_group *g, uint32_t ng, const skgpu_chain_input *in, uint32_t ni,
-                               uint32_t F, uint32_t *max_k, uint32_t *max_buf_floats, int *oc_out) {
+                               uint32_t F, uint32_t *max_k, uint32_t *max_buf_floats, int *oc_out, uint32_t *cap_np, uint32_t *cap_nr) {
+    uint32_t need_np = 0, need_nr = 0;
+    double last_t = -1.0;
+    int32_t last_end = 0;
     const skgpu_ctx *c = p->ctx;
     uint32_t mk = 0, mb = 0;
     int oc = -1;
@@ -731,7 +752,13 @@ static skgpu_rc validate_chain(const skgpu_plan *p, const skgpu_chain_group *g, 
         skgpu_rc rc = check_range(p, in[i].in_off + p->bank_stride, (uint64_t)N * C * 4, "chain input (bank 1)");
         if (rc) return rc;
         if (in[i].gain_idx != SKGPU_NO_GAIN && in[i].gain_idx >= p->n_gains) return fail(SKGPU_ERR_INVALID, "chain input %u: gain_idx out of range", i);
-        mb = std::max(mb, (16u + N + (uint32_t)CH_HEAD) * C);
+        mb = std::max(mb, (N + (uint32_t)CH_HEAD) * C * 4u);   // bytes: previous chunk + staged head of the current one
+        if (c->h_t[slot] != last_t || c->h_end[slot] != last_end) {   // streams of one op usually share a handful of configurations
+            uint32_t a = 0, b = 0;
+            phase_table_bounds(c->h_t[slot], c->h_end[slot], &a, &b);
+            need_np = std::max(need_np, a); need_nr = std::max(need_nr, b);
+            last_t = c->h_t[slot]; last_end = c->h_end[slot];
+        }
     }
     for (uint32_t i = 0; i < ng; ++i) {
         if (g[i].out_channels != 1 && g[i].out_channels != 2) return fail(SKGPU_ERR_INVALID, "chain group %u: out_channels must be 1 or 2", i);
@@ -751,31 +778,44 @@ static skgpu_rc validate_chain(const skgpu_plan *p, const skgpu_chain_group *g, 
         mk = std::max(mk, g[i].n_inputs);
     }
     *max_k = mk;
-    *max_buf_floats = (mb + 3u) & ~3u;
+    *max_buf_floats = (mb + 15u) & ~15u;
     *oc_out = oc < 0 ? 2 : oc;
+    // margin for phases the sampling did not hit; even counts keep every staged array a multiple of 16 bytes
+    *cap_np = std::min<uint32_t>(SK_PREFIX_MAX, (need_np + 5u) & ~1u);
+    *cap_nr = std::min<uint32_t>(SK_RUNS_MAX, (need_nr + 3u) & ~1u);
     return SKGPU_OK;
 }
 
-static void chain_size_smem(Op &op, uint32_t max_k, uint32_t buf_floats) {
-    // nstages pipeline stages, each staging up to kb inputs (buffer + two phase tables). Pick (kb, nstages) so that the
-    // number of sessions being loaded at any time per SM -- CTAs/SM x (nstages - 1) -- is as large as shared memory
-    // (227 KB/SM) and threads (2048/SM) allow: that is what hides HBM latency for a streaming kernel.
+static void chain_size_smem(Op &op, uint32_t max_k, uint32_t chunk_cap, uint32_t cap_np, uint32_t cap_nr) {
+    // nstages pipeline stages, each staging up to kb inputs: [table prev | history 128 B | previous chunk + head | table cur].
+    // 4 CTAs per SM is the register limit (56 regs x 288 threads); pick the deepest ring that keeps 4 CTAs in 227 KB.
+    ChainDims dm{};
+    dm.chunk_cap = chunk_cap;
+    dm.cap_np = cap_np;
+    dm.cap_nr = cap_nr;
+    dm.max_k = std::max(max_k, 1u);
+    const uint64_t in_bytes = chain_in_bytes(dm);
     uint32_t kb = std::max(1u, std::min<uint32_t>(max_k, CH_MAX_KB));
-    while (kb > 1 && (uint64_t)2 * kb * (buf_floats * 4ull + 2 * sizeof(SmemPhase)) > 72u * 1024u) --kb;
-    const uint64_t stage = (((uint64_t)kb * buf_floats * 4u + 15u) & ~15ull) + (uint64_t)kb * 2u * sizeof(SmemPhase);
-    const uint64_t static_smem = 9u * 1024u, sm_smem = 227u * 1024u;
-    uint32_t best_ns = 2, best_inflight = 0;
-    for (uint32_t ns = 2; ns <= 2u; ++ns) {  // measured on B200: the kernel is issue-bound, more resident consumer warps beat deeper rings
-        const uint64_t per_cta = stage * ns + static_smem;
-        uint32_t ctas = (uint32_t)std::min<uint64_t>(sm_smem / per_cta, 2048u / CH_THREADS);
-        if (ctas < 1) continue;
-        const uint32_t inflight = ctas * (ns - 1);
-        if (inflight > best_inflight) { best_inflight = inflight; best_ns = ns; }
+    while (kb > 1 && 2ull * kb * in_bytes > 100u * 1024u) --kb;
+    const uint64_t stage = (uint64_t)kb * in_bytes;
+    const uint64_t scratch = (uint64_t)dm.max_k * sizeof(ChainRec);
+    const uint64_t static_smem = sizeof(ChainStage) * CH_MAX_STAGES + 5u * 1024u, sm_smem = 227u * 1024u, cta_overhead = 1024u;   // stage headers + prefetch slots
+    uint32_t best_ns = 2;
+    for (uint32_t ns = 2; ns <= 2u; ++ns) {   // measured on B200: deeper rings do not help (the kernel is issue bound), keep 2
+        const uint64_t per_cta = stage * ns + scratch + static_smem + cta_overhead;
+        if (per_cta * 4u <= sm_smem) best_ns = ns;
     }
+    if (const char *e = std::getenv("SKGPU_CHAIN_STAGES")) {   // tuning knob (profiling only)
+        const int v = std::atoi(e);
+        if (v >= 2 && v <= CH_MAX_STAGES) best_ns = (uint32_t)v;
+    }
+    dm.kb = kb;
+    dm.nstages = best_ns;
+    dm.debug = std::getenv("SKGPU_CHAIN_DEBUG") ? (uint32_t)std::atoi(std::getenv("SKGPU_CHAIN_DEBUG")) : 0u;
     op.chain_kb = kb;
-    op.chain_buf_floats = buf_floats;
-    op.chain_stages = best_ns;
-    op.smem_bytes = (uint32_t)(stage * best_ns);
+    op.chain_buf_floats = chunk_cap;
+    op.chain_dm = dm;
+    op.smem_bytes = (uint32_t)(stage * best_ns + scratch);
 }
 
 extern "C" skgpu_rc skgpu_plan_add_chain(skgpu_plan *p, const skgpu_chain_group *groups, uint32_t ng, const skgpu_chain_input *inputs, uint32_t ni,
@@ -788,9 +828,9 @@ extern "C" skgpu_rc skgpu_plan_add_chain(skgpu_plan *p, const skgpu_chain_group 
     for (uint32_t v : valid) okF |= (v == output_frame_size);
     if (!okF) return fail(SKGPU_ERR_INVALID, "output_frame_size must be a valid Opus frame size: [120, 240, 480, 960, 1920, 2880]");
     CU(cudaSetDevice(p->ctx->device));
-    uint32_t mk = 0, mb = 0;
+    uint32_t mk = 0, mb = 0, cnp = 0, cnr = 0;
     int oc = 2;
-    skgpu_rc rc = validate_chain(p, groups, ng, inputs, ni, output_frame_size, &mk, &mb, &oc);
+    skgpu_rc rc = validate_chain(p, groups, ng, inputs, ni, output_frame_size, &mk, &mb, &oc, &cnp, &cnr);
     if (rc) return rc;
     rc = check_range(p, results_off, (uint64_t)std::max(ni, 1u) * sizeof(skgpu_chain_result), "chain results");
     if (rc) return rc;
@@ -807,7 +847,9 @@ extern "C" skgpu_rc skgpu_plan_add_chain(skgpu_plan *p, const skgpu_chain_group 
     op.chain_oc = oc;
     op.chain_iters = (int)((output_frame_size + 1023u) / 1024u);
     op.results_off = results_off;
-    chain_size_smem(op, mk, std::max(mb, 64u));
+    chain_size_smem(op, mk, std::max(mb, 64u), cnp, cnr);
+    CU(cudaMalloc((void **)&op.d_rec, (size_t)op.cap2 * sizeof(ChainRec)));
+    CU(cudaMemset(op.d_rec, 0, (size_t)op.cap2 * sizeof(ChainRec)));
     if (op.smem_bytes > 200u * 1024u) return fail(SKGPU_ERR_INVALID, "chain op: chunk too large for shared-memory staging (%u bytes)", op.smem_bytes);
     {
         rc = dyn_alloc(op.present, op.cap2);
@@ -825,12 +867,14 @@ extern "C" skgpu_rc skgpu_plan_update_chain(skgpu_plan *p, uint32_t opi, const s
     if (!p || opi >= p->ops.size() || p->ops[opi].kind != OP_CHAIN) return fail(SKGPU_ERR_INVALID, "not a chain op");
     Op &op = p->ops[opi];
     if (ng > op.cap || ni > op.cap2) return fail(SKGPU_ERR_INVALID, "update exceeds capacity");
-    uint32_t mk = 0, mb = 0;
+    uint32_t mk = 0, mb = 0, cnp = 0, cnr = 0;
     int oc = 2;
-    skgpu_rc rc = validate_chain(p, groups, ng, inputs, ni, op.chain_F, &mk, &mb, &oc);
+    skgpu_rc rc = validate_chain(p, groups, ng, inputs, ni, op.chain_F, &mk, &mb, &oc, &cnp, &cnr);
     if (rc) return rc;
     if (ng && oc != op.chain_oc) return fail(SKGPU_ERR_INVALID, "update changes the op's output channel count");
     if (mb > op.chain_buf_floats) return fail(SKGPU_ERR_INVALID, "update has a longer chunk than the op was sized for");
+    if (mk > op.chain_dm.max_k) return fail(SKGPU_ERR_INVALID, "update has a session with more inputs (%u) than the op was sized for (%u)", mk, op.chain_dm.max_k);
+    if (cnp > op.chain_dm.cap_np || cnr > op.chain_dm.cap_nr) return fail(SKGPU_ERR_INVALID, "update adds a resampling ratio whose phase tables exceed the op's staging capacity");
     CU(cudaStreamSynchronize(p->ctx->stream));
     if (ng) memcpy(op.h_tab, groups, ng * sizeof(skgpu_chain_group));
     if (ni) memcpy(op.h_tab2, inputs, ni * sizeof(skgpu_chain_input));
@@ -879,8 +923,7 @@ static skgpu_rc op_event(Op &op, int sub, bool second, cudaStream_t s) {
     return SKGPU_OK;
 }
 
-typedef void (*chain_kernel_t)(const OpHeader *, const skgpu_chain_group *, const skgpu_chain_input *, const uint8_t *, const float *, SlotTables,
-                               uint8_t *, const uint32_t *, uint64_t, uint32_t, uint64_t, uint32_t, uint32_t, uint32_t);
+typedef void (*chain_kernel_t)(const OpHeader *, const skgpu_chain_group *, const ChainRec *, const float *, SlotTables, uint8_t *, uint32_t, ChainDims);
 static chain_kernel_t chain_kernel(int oc, int iters) {
     if (oc == 2) return iters == 1 ? k_chain<2, 1> : iters == 2 ? k_chain<2, 2> : k_chain<2, 3>;
     return iters == 1 ? k_chain<1, 1> : iters == 2 ? k_chain<1, 2> : k_chain<1, 3>;
@@ -916,14 +959,14 @@ static skgpu_rc launch_ops(skgpu_plan *p, bool time_ops) {
             const uint8_t *present = op.present.valid ? (const uint8_t *)op.present.dev : nullptr;
             const skgpu_chain_input *cin = (const skgpu_chain_input *)op.d_tab2;
             if (time_ops) { skgpu_rc rc = op_event(op, 0, false, s); if (rc) return rc; }
-            k_phase<skgpu_chain_input, true><<<(op.cap2 + PHASE_THREADS - 1) / PHASE_THREADS, PHASE_THREADS, 0, s>>>(op.d_hdr, cin, present, c->st, p->arena, 0);
+            k_phase_chain<<<(op.cap2 + PHASE_CHAIN_THREADS - 1) / PHASE_CHAIN_THREADS, PHASE_CHAIN_THREADS, 0, s>>>(
+                op.d_hdr, cin, present, gains, c->st, p->arena, p->d_tick, p->bank_stride, op.chain_F, op.results_off, op.chain_dm, op.d_rec);
             CU(cudaGetLastError());
             if (time_ops) { skgpu_rc rc = op_event(op, 0, true, s); if (rc) return rc; rc = op_event(op, 1, false, s); if (rc) return rc; }
             {
                 const uint32_t grid = std::min<uint32_t>(op.cap, op.chain_grid);
                 auto kfn = chain_kernel(op.chain_oc, op.chain_iters);
-                kfn<<<grid, CH_THREADS, op.smem_bytes, s>>>(op.d_hdr, (const skgpu_chain_group *)op.d_tab, cin, present, gains, c->st, p->arena,
-                                                             p->d_tick, p->bank_stride, op.chain_F, op.results_off, op.chain_kb, op.chain_buf_floats, op.chain_stages);
+                kfn<<<grid, CH_THREADS, op.smem_bytes, s>>>(op.d_hdr, (const skgpu_chain_group *)op.d_tab, op.d_rec, gains, c->st, p->arena, op.chain_F, op.chain_dm);
             }
             CU(cudaGetLastError());
             if (time_ops) { skgpu_rc rc = op_event(op, 1, true, s); if (rc) return rc; }
