@@ -44,7 +44,7 @@ struct SlotCfgUpload {     // host -> device (re)configuration of one slot (k_co
     int32_t end_idx;
 };
 
-constexpr uint32_t SK_SIDE_STRIDE = 1408u;   // >= sizeof(SkPhaseTable) and >= 40*8 + 40*24 + 128
+constexpr uint32_t SK_SIDE_STRIDE = 2048u;   // >= sizeof(SkPhaseTable); fused chain: frame program (<= 1920 B) + 128 B history
 constexpr uint32_t SK_SIDE_HIST = 128u;      // 16 frames x 2 channels x 4 bytes
 
 struct SlotTables {     // per-stream state + configuration, all device pointers
@@ -52,7 +52,7 @@ struct SlotTables {     // per-stream state + configuration, all device pointers
     float *hist;            // [slot][16 * max_channels]: the 16 frames before the oldest chunk that still has
                             // unconsumed output (plain resample op: before the next chunk; chain op: before the previous one)
     uint8_t *side;          // [slot][2][SK_SIDE_STRIDE]: per (slot, chunk number & 1) record. Plain resample op: a SkPhaseTable.
-                            // Fused chain: compact [prefix cap_np | runs cap_nr | 128 B history before that chunk] (one TMA copy)
+                            // Fused chain: [frame program of the next packet (chain_prog.h) ... | 128 B history before that chunk]
     float *fifo;            // [slot][fifo_frames * max_channels] (may be null): unfused re-framing ring
     unsigned long long *fifo_w;  // total frames ever written
     unsigned long long *fifo_r;  // total frames ever consumed
@@ -98,6 +98,9 @@ __device__ __forceinline__ void stg_stream_f2(float2 *p, float2 v) {
 __device__ __forceinline__ void stg_stream_u4(uint4 *p, uint4 v) {
     asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
+__device__ __forceinline__ void stg_stream_u32(uint32_t *p, uint32_t v) {
+    asm volatile("st.global.L1::no_allocate.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
 __device__ __forceinline__ void stg_stream_u2(uint2 *p, uint2 v) {
     asm volatile("st.global.L1::no_allocate.v2.u32 [%0], {%1,%2};" ::"l"(p), "r"(v.x), "r"(v.y) : "memory");
 }
@@ -130,11 +133,11 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
         "{\n"
         ".reg .pred p;\n"
         "WAIT_LOOP:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"   // suspends the thread (no issue slots) up to the hint
         "@p bra DONE;\n"
         "bra WAIT_LOOP;\n"
         "DONE:\n"
-        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity), "r"(20000u) : "memory");
 }
 
 // ---- cp.async (LDGSTS): asynchronous global -> shared copies that need no destination registers

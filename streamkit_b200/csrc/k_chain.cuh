@@ -12,22 +12,26 @@
 // a packet, plus the first F - carry frames of the current chunk (steady state 44.1k->48k: 954 + 6). Instead
 // of parking those carry frames in an HBM ring (write + read of 7.6 KB per stream-tick), the kernel RECOMPUTES
 // them from the previous tick's input chunk, which is still resident in the other half of the double-banked
-// input arena. HBM traffic per stream-tick is one pass over one input chunk plus a ~0.5 KB "side record"
-// (phase table + 16-frame history), i.e. the "fully fused" algorithmic bytes of SURVEY 8(d).
+// input arena. HBM traffic per stream-tick is one pass over one input chunk plus a ~0.7 KB frame program
+// (chain_prog.h) and a 16-frame history.
 //
 // Two kernels per tick:
 //   k_phase_chain  one THREAD per input stream (massively parallel, data independent): rubato's f64 phase recurrence
-//                  -> compact phase table in the stream's side record; emission / carry / status bookkeeping
-//                  (resampler.rs:425-428 re-framing); writes a ready-made 64-byte ChainRec per input.
-//   k_chain        PERSISTENT, WARP-SPECIALISED CTAs (4 per SM, looping over sessions):
+//                  (phase_runs.h) -> the packet's frame program (chain_prog.h): run segments, explicit frames and a
+//                  per-32-frame block map; emission / carry / status bookkeeping (resampler.rs:425-428 re-framing);
+//                  a ready-made 64-byte ChainRec per input for k_chain's producer.
+//   k_chain        PERSISTENT, WARP-SPECIALISED CTAs (looping over sessions):
 //       warp 0  (producer)   prefetches ChainRecs with cp.async, derives the summation order (base selection +
-//                            swap_remove, mixer.rs:960-980) from warp ballots, and issues 3 TMA bulk copies per
-//                            input (side record of the previous chunk, the previous chunk, table of the current
-//                            chunk) into a 2-stage shared-memory ring guarded by full/empty mbarriers;
-//       warps 1-8 (consumers) interpolate 4 consecutive output frames per thread from shared memory, add the inputs
-//                            SEQUENTIALLY in the reference's order (f32 addition is not associative),
-//                            apply the master gain, clip + pack s16 and store 16 bytes per thread.
+//                            swap_remove, mixer.rs:960-980) from warp ballots, and issues 4 TMA bulk copies per
+//                            input (frame program, history, previous chunk, head of the current chunk) into a
+//                            shared-memory ring guarded by full/empty mbarriers;
+//       warps 1-8 (consumers) execute the frame programs: a warp owns 32-frame blocks in which lane l owns frame
+//                            (block start + l) -- neighbouring lanes read neighbouring input frames, so the two
+//                            shared-memory loads of a frame are conflict free. Inputs are added SEQUENTIALLY in the
+//                            reference's order (f32 addition is not associative); master gain, clip +
+//                            s16 pack, one coalesced store per block.
 #pragma once
+#include "chain_prog.h"
 #include "common.cuh"
 
 namespace skgpu {
@@ -35,38 +39,35 @@ namespace skgpu {
 constexpr int CH_CONSUMERS = 256;                 // 8 consumer warps
 constexpr int CH_THREADS = CH_CONSUMERS + 32;     // + producer warp (warp 0)
 constexpr int CH_MAX_STAGES = 4;                  // pipeline depth is a launch parameter (2..4)
-constexpr int CH_HEAD = 32;                       // frames of the CURRENT chunk staged behind the previous one (rarely needed)
+constexpr int CH_HEAD = 32;                       // frames of the CURRENT chunk staged behind the previous one
 constexpr int CH_MAX_INPUTS = 64;                 // inputs per session
-constexpr int CH_FPT = 4;                         // output frames per consumer thread per iteration
 constexpr int CH_MAX_KB = 4;                      // inputs staged per batch
+constexpr uint32_t CH_HIST_OFF = SK_SIDE_STRIDE - SK_SIDE_HIST;   // history field at the end of every side record
 
-struct __align__(16) ChainCons {   // what a consumer thread needs per input: 32 bytes = two broadcast 16-byte loads
-    double t;               // 1 / resample_ratio
-    float gain;
-    uint32_t carry;
-    uint32_t kdelta;        // n_prev - carry: chunk-output index of packet frame j (j < carry) is kdelta + j
-    uint32_t n_cur;         // >= 1
-    uint32_t np_nr;         // np_prev | nr_prev << 8 | np_cur << 16 | nr_cur << 24
-    uint32_t na_flags;      // NA (24 bits) | channels << 24 | has_gain << 26 | needs_global << 27
+struct __align__(8) ChainCons {   // what a consumer needs per input
+    float gain;             // 1.0 when the input has no audio::gain in front of the mixer (x * 1.0 == x)
+    uint32_t sc;            // source channels
 };
 
 // per-input record written by k_phase_chain every tick, consumed by k_chain's producer (64 bytes, one per chain input)
-constexpr uint32_t CR_EMIT = 1u, CR_UNIQUE = 2u, CR_NEEDS_HEAD = 4u, CR_PAR_PREV = 8u, CR_HAS_PREV = 16u;
+constexpr uint32_t CR_EMIT = 1u, CR_UNIQUE = 2u, CR_PAR_PREV = 8u;
 struct __align__(16) ChainRec {
     ChainCons cons;
     const float *prev_g;    // previous chunk (other input bank)
     const float *cur_g;     // current chunk
     uint32_t slot;
     uint32_t chunk_bytes;   // N * channels * 4
+    uint32_t head_bytes;    // staged frames of the current chunk, bytes
+    uint32_t prog_bytes;    // used bytes of the frame program (multiple of 16)
     uint32_t flags;         // CR_*
     uint32_t N;
+    uint32_t pad[4];
 };
 static_assert(sizeof(ChainRec) == 64, "ChainRec is one 64-byte record");
 
-struct ChainTail {          // per staged input: what the end-of-batch history update and the rare HBM path need
+struct ChainTail {          // per staged input: what the end-of-batch history update needs
     uint8_t *side_cur;      // side record of the current chunk (its history field is written here)
-    const float *cur_g;
-    uint32_t N, ch, has_prev, pad;
+    uint32_t N, ch;
 };
 
 struct __align__(16) ChainStage {   // header of one pipeline stage (shared memory)
@@ -74,11 +75,10 @@ struct __align__(16) ChainStage {   // header of one pipeline stage (shared memo
     uint32_t first, last;   // first / last batch of the session
     uint32_t has_base;      // the first input of the first batch is the base frame (mixer.rs:960-972)
     uint64_t out_off;
-    float master_gain;
-    uint32_t has_master;
+    float master_gain;      // 1.0 when the session has no master audio::gain
     uint32_t flags;
     uint32_t stop;          // no more work
-    uint32_t pad[2];
+    uint32_t pad[3];
     ChainCons cons[CH_MAX_KB];
     ChainTail tail[CH_MAX_KB];
 };
@@ -86,21 +86,25 @@ struct __align__(16) ChainStage {   // header of one pipeline stage (shared memo
 struct ChainDims {          // launch-time geometry of the staging ring (host: chain_size_smem)
     uint32_t kb;            // inputs per batch
     uint32_t chunk_cap;     // bytes reserved per input for [previous chunk | CH_HEAD frames of the current one], 16-aligned
-    uint32_t cap_np, cap_nr;   // phase-table capacity: prefix doubles / runs (both even) -> tab_bytes = cap_np*8 + cap_nr*24
+    ChainProgDims prog;     // frame-program capacities
     uint32_t nstages;
     uint32_t max_k;         // largest n_inputs of any session (sizes the producer scratch)
     uint32_t debug;         // profiling only: bit0 = consumers skip the arithmetic (isolates the load pipeline)
+    float one;              // 1.0f, deliberately a run-time value (see add2)
 };
-// shared-memory slot of one staged input:  [table prev | history field 128 B | previous chunk | head of current] [table cur]
-__host__ __device__ __forceinline__ uint32_t chain_tab_bytes(const ChainDims &dm) { return dm.cap_np * 8u + dm.cap_nr * (uint32_t)sizeof(SkRun); }
-__host__ __device__ __forceinline__ uint32_t chain_in_bytes(const ChainDims &dm) { return 2u * chain_tab_bytes(dm) + SK_SIDE_HIST + dm.chunk_cap; }
+// shared-memory slot of one staged input:  [frame program | history field 128 B | previous chunk | head of current]
+__host__ __device__ __forceinline__ uint32_t chain_in_bytes(const ChainDims &dm) { return skc_prog_cap(dm.prog) + SK_SIDE_HIST + dm.chunk_cap; }
 
-// packed f32x2 multiply (Blackwell FMUL2): two IEEE-rounded products per instruction. Additions stay scalar
-// FADDs on purpose: ptxas contracts mul.f32x2 + add.f32x2 into FFMA2 (one rounding less than the reference).
+// packed f32x2 arithmetic (Blackwell FMUL2 / FFMA2): two IEEE-rounded results per instruction
 __device__ __forceinline__ unsigned long long mul2(unsigned long long a, float b) {
     unsigned long long d, bb;
     asm("mov.b64 %0, {%1, %1};" : "=l"(bb) : "f"(b));
     asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(bb));
+    return d;
+}
+__device__ __forceinline__ unsigned long long mul2v(unsigned long long a, unsigned long long b) {
+    unsigned long long d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
     return d;
 }
 __device__ __forceinline__ void unpack2(unsigned long long v, float &a, float &b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
@@ -109,124 +113,93 @@ __device__ __forceinline__ unsigned long long pack2(float a, float b) {
     asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "f"(a), "f"(b));
     return d;
 }
-
-struct ChainInRegs {        // what the inner loop needs, in registers
-    const float *cur_g;     // only set on the rare HBM path
-    double t;
-    float gain;
-    uint32_t has_gain, carry, kdelta, n_cur, NA;
-};
-
-// one (input frame -> output frame) accumulate step for the non-stereo/stereo combinations (mixer.rs:1027-1078)
-template <int OC, int SC, bool IS_BASE>
-__device__ __forceinline__ void chain_accumulate(float *acc, const float *y) {
-    float v[2];
-    if (SC == OC) { v[0] = y[0]; v[1] = y[1]; }
-    else if (SC == 1 && OC == 2) { v[0] = y[0]; v[1] = y[0]; }
-    else { v[0] = __fmul_rn(__fadd_rn(y[0], y[1]), 0.5f); v[1] = 0.0f; }
-#pragma unroll
-    for (int c = 0; c < OC; ++c) acc[c] = IS_BASE ? v[c] : __fadd_rn(acc[c], v[c]);
+// packed add. ptxas contracts mul.rn.f32x2 + add.rn.f32x2 into one FFMA2 (one rounding less than the reference) even
+// though both carry .rn, so the add is written as fma(a, 1.0, b) with the 1.0 taken from a kernel parameter: ptxas
+// cannot fold a multiplier it does not know, and fl(a * 1 + b) == fl(a + b) for every a, b.
+__device__ __forceinline__ unsigned long long add2(unsigned long long a, unsigned long long b, unsigned long long one2) {
+    unsigned long long d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(one2), "l"(b));
+    return d;
+}
+__device__ __forceinline__ float lds_f32(uint32_t addr) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+    return v;
 }
 
-// interpolate + gain + accumulate one frame at phase x; `idx_base` selects history++previous (0) or the current chunk (NA)
-template <int OC, int SC, bool IS_BASE>
-__device__ __forceinline__ void chain_frame(const ChainInRegs &in, const float *A, double x, uint32_t idx_base, float *acc) {
-    uint32_t p;
-    float frac;
-    phase_split(x, p, frac);
-    const uint32_t idx = idx_base + p;   // frame index into A
-    if (SC == 2 && OC == 2) {
-        const unsigned long long y0 = *reinterpret_cast<const unsigned long long *>(A + 2u * idx);
-        const unsigned long long y1 = *reinterpret_cast<const unsigned long long *>(A + 2u * idx + 2u);
-        float a0, a1, b0, b1;
-        unpack2(mul2(y0, __fsub_rn(1.0f, frac)), a0, a1);   // rubato interp_lin: (1 - frac) * y0 + frac * y1
-        unpack2(mul2(y1, frac), b0, b1);
-        float r0 = __fadd_rn(a0, b0), r1 = __fadd_rn(a1, b1);
-        if (in.has_gain) unpack2(mul2(pack2(r0, r1), in.gain), r0, r1);   // the input's audio::gain (gain.rs:187-189)
-        acc[0] = IS_BASE ? r0 : __fadd_rn(acc[0], r0);
-        acc[1] = IS_BASE ? r1 : __fadd_rn(acc[1], r1);
-    } else {
-        float y[2] = {0.0f, 0.0f};
-#pragma unroll
-        for (int c = 0; c < SC; ++c) {
-            y[c] = interp_lin(frac, A[idx * SC + c], A[(idx + 1u) * SC + c]);
-            if (in.has_gain) y[c] = __fmul_rn(y[c], in.gain);
-        }
-        chain_accumulate<OC, SC, IS_BASE>(acc, y);
-    }
-}
-
-// rare path (right after a stream starts, or odd ratios): frames of the current chunk beyond the staged head are read from HBM
+// one frame of one input: rubato interp_lin between the buffer frames at `addr` and the next one, the input's
+// audio::gain (gain.rs:187-189), the mixer's channel mapping (mixer.rs:1027-1078); returns the value to ADD
 template <int OC, int SC>
-__device__ __noinline__ void chain_input_global(const ChainInRegs &in, const float *A, const PhaseView &Tp, const PhaseView &Tc, uint32_t F,
-                                                uint32_t j0, float *acc, bool is_base) {
-    for (int f = 0; f < CH_FPT; ++f) {
-        const uint32_t j = j0 + f;
-        if (j >= F) break;
-        uint32_t p;
-        float frac;
-        float y[2] = {0.0f, 0.0f};
-        if (j < in.carry) {
-            phase_split(pv_eval(Tp, in.t, in.kdelta + j), p, frac);
-            for (int c = 0; c < SC; ++c) y[c] = interp_lin(frac, A[p * SC + c], A[(p + 1u) * SC + c]);
-        } else {
-            phase_split(pv_eval(Tc, in.t, min(j - in.carry, in.n_cur - 1u)), p, frac);
-            for (int c = 0; c < SC; ++c) {
-                const float y0 = (p < 16u) ? A[(in.NA + p) * SC + c] : in.cur_g[(size_t)(p - 16u) * SC + c];
-                const float y1 = (p + 1u < 16u) ? A[(in.NA + p + 1u) * SC + c] : in.cur_g[(size_t)(p + 1u - 16u) * SC + c];
-                y[c] = interp_lin(frac, y0, y1);
-            }
-        }
-        for (int c = 0; c < SC; ++c)
-            if (in.has_gain) y[c] = __fmul_rn(y[c], in.gain);
-        if (is_base) chain_accumulate<OC, SC, true>(acc + f * OC, y);
-        else chain_accumulate<OC, SC, false>(acc + f * OC, y);
+__device__ __forceinline__ unsigned long long chain_frame(uint32_t addr, float frac, float gain, unsigned long long one2) {
+    if (SC == 2) {
+        unsigned long long y0, y1;
+        asm volatile("ld.shared.b64 %0, [%1];" : "=l"(y0) : "r"(addr));
+        asm volatile("ld.shared.b64 %0, [%1+8];" : "=l"(y1) : "r"(addr));
+        const unsigned long long r = mul2(add2(mul2(y0, __fsub_rn(1.0f, frac)), mul2(y1, frac), one2), gain);
+        if (OC == 2) return r;
+        float a, b;
+        unpack2(r, a, b);
+        return pack2(__fmul_rn(__fadd_rn(a, b), 0.5f), 0.0f);   // stereo -> mono: average
+    } else {
+        const float v = __fmul_rn(interp_lin(frac, lds_f32(addr), lds_f32(addr + 4u)), gain);
+        return pack2(v, OC == 2 ? v : 0.0f);                    // mono -> stereo: duplicate
     }
 }
 
-// one input of one session, 4 consecutive output frames j0..j0+3 of this thread (frames >= F are computed on clamped
-// indices and never stored). A = [16 history | previous chunk (NA frames) | CH_HEAD frames of the current chunk].
-template <int OC, int SC, bool IS_BASE>
-__device__ __forceinline__ void chain_input(const ChainInRegs &in, const float *A, const PhaseView &Tp, const PhaseView &Tc, uint32_t j0,
-                                            float *acc) {
-    if (j0 + CH_FPT <= in.carry) {
-        // FAST PATH (954 of 960 frames in steady state, 7 of 8 warps entirely): all four frames were produced by the
-        // PREVIOUS chunk; one run lookup, then x, x+d, x+2d, x+3d (exact inside a run)
-        const uint32_t k0 = in.kdelta + j0;
-        double x[4];
-        bool in_run = false;
-        if (k0 >= Tp.n_prefix) {
-            uint32_t r = Tp.n_runs - 1u;
-            while (r > 0u && Tp.runs[r].k_a > k0) --r;
-            const SkRun rn = Tp.runs[r];
-            if (k0 + 3u < rn.k_e) {
-                x[0] = __fma_rn((double)(k0 - rn.k_a), rn.delta, rn.x_a);
-                x[1] = __dadd_rn(x[0], rn.delta);
-                x[2] = __dadd_rn(x[1], rn.delta);
-                x[3] = __dadd_rn(x[2], rn.delta);
-                in_run = true;
+// Executes the frame program of one staged input for the blocks this warp owns (ITERS x 4 blocks of 32 frames).
+//   prog    shared-memory address of the program record; a_hist: of the 16-frame history (buffer position 0)
+template <int OC, int SC, int ITERS>
+__device__ __forceinline__ void chain_consume(unsigned long long (&acc)[ITERS][4], uint32_t prog, uint32_t a_hist, const ChainProgDims &pd,
+                                              uint32_t F, uint32_t cw, uint32_t lane, float gain, unsigned long long one2) {
+    const uint32_t segx = prog + skc_segx_off(pd), segj = prog + skc_segj_off(pd), exps = prog + skc_exp_off(pd);
+    const uint32_t a_chunk = a_hist + 16u * SC * 4u;   // buffer position 16: floor(idx) == 0
+#pragma unroll
+    for (int it = 0; it < ITERS; ++it) {
+#pragma unroll
+        for (int f = 0; f < 4; ++f) {
+            const uint32_t b = ((uint32_t)it * 8u + cw) * 4u + (uint32_t)f;   // warp-uniform block index
+            const uint32_t jf = b * 32u;
+            if (jf >= F) continue;
+            const uint32_t j = min(jf + lane, F - 1u);   // lanes past the packet recompute its last frame (never stored)
+            uint32_t ent;
+            asm volatile("ld.shared.u16 %0, [%1];" : "=r"(ent) : "r"(prog + b * 2u));
+            const uint32_t s_last = ent >> 8;
+            for (uint32_t s = ent & 0xFFu; s <= s_last; ++s) {
+                uint32_t jj, info;
+                asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(jj), "=r"(info) : "r"(segj + s * 8u));
+                const uint32_t j0 = jj & 0xFFFFu, len = (jj >> 16) - j0;
+                const uint32_t rel_raw = j - j0;
+                const bool active = rel_raw < len;                 // unsigned: also false for j < j0
+                const uint32_t rel = min(rel_raw, len - 1u);        // inactive lanes compute a valid frame and drop it
+                uint32_t addr;
+                float frac;
+                if (info & SKC_SEG_E) {
+                    uint32_t aoff;
+                    asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(aoff), "=f"(frac) : "r"(exps + ((info & 0xFFFFu) + rel) * 8u));
+                    addr = a_hist + aoff;
+                } else {
+                    double x0, dl;
+                    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(x0), "=d"(dl) : "r"(segx + s * 16u));
+                    const double x = __fma_rn((double)rel, dl, x0);    // exact inside a run (phase_runs.h)
+                    if (info & SKC_SEG_FAST) {
+                        const uint32_t sh = (info >> 16) & 31u;
+                        const uint32_t hi = (uint32_t)__double2hiint(x);
+                        const uint32_t fl = ((hi & 0xFFFFFu) | 0x100000u) >> sh;                     // floor(x), x in [1, 2^21)
+                        const double fl_d = __hiloint2double((int)(hi & (0xFFFFFFFFu << sh)), 0);    // the same as a double
+                        frac = __double2float_rn(__dsub_rn(x, fl_d));                                // T::coerce(idx - idx.floor())
+                        addr = a_chunk + fl * (SC * 4u);
+                    } else {
+                        int32_t fl;
+                        skc_split(x, &fl, &frac);
+                        addr = a_chunk + (uint32_t)(fl * (int32_t)(SC * 4));
+                    }
+                }
+                const unsigned long long v = chain_frame<OC, SC>(addr, frac, gain, one2);
+                if (active) acc[it][f] = add2(acc[it][f], v, one2);
             }
         }
-        if (!in_run) {
-#pragma unroll
-            for (int f = 0; f < CH_FPT; ++f) x[f] = pv_eval(Tp, in.t, k0 + (uint32_t)f);
-        }
-#pragma unroll
-        for (int f = 0; f < CH_FPT; ++f) chain_frame<OC, SC, IS_BASE>(in, A, x[f], 0u, acc + f * OC);
-        return;
-    }
-    // the thread that straddles the prev/cur boundary and the few behind it (one warp per session): frame by frame.
-    // Frames produced by the CURRENT chunk use its own table; their history is the tail of the previous chunk, which
-    // precedes the staged head of the current chunk in A.
-#pragma unroll
-    for (int f = 0; f < CH_FPT; ++f) {
-        const uint32_t j = j0 + f;
-        const bool from_cur = j >= in.carry;
-        const double x = from_cur ? pv_eval(Tc, in.t, min(j - in.carry, in.n_cur - 1u)) : pv_eval(Tp, in.t, in.kdelta + j);
-        chain_frame<OC, SC, IS_BASE>(in, A, x, from_cur ? in.NA : 0u, acc + f * OC);
     }
 }
-
 
 // ------------------------------------------------------------------ k_phase_chain
 constexpr int PHASE_CHAIN_THREADS = 64;
@@ -242,38 +215,46 @@ __global__ void __launch_bounds__(PHASE_CHAIN_THREADS) k_phase_chain(const OpHea
     SlotRec *recp = st.rec + slot;
     SlotRec rec = *recp;
     const bool pres = present ? (present[i] != 0) : true;
-    const uint32_t tab_bytes = chain_tab_bytes(dm);
-    uint32_t status = 0;
+    const uint32_t ch = rec.channels, N = rec.chunk, fb = ch * 4u;
+    const uint32_t head = min((uint32_t)CH_HEAD, N);
+    // slot record fields reused by the chain op: n_prefix[par] = explicit entries of the record's part 1, n_runs[par] = segments
+    const uint32_t count0 = rec.chunk_count;
+    const uint32_t par_new = count0 & 1u, par_old = par_new ^ 1u;   // record of the chunk processed now / of the previous chunk
+    const uint32_t carry = rec.carry;
+    uint32_t status = 0, emit = 0, prog_bytes = 0;
     if (pres) {
-        // ---- rubato's phase recurrence for this chunk -> compact table in the side record of (chunk number & 1)
-        const uint32_t par = rec.chunk_count & 1u;
-        uint8_t *side = slot_side(st, slot, par);
+        // ---- rubato's phase recurrence for this chunk (thread-private table)
+        double prefix[SK_PREFIX_MAX];
+        SkRun runs[SK_RUNS_MAX];
         uint32_t np, nr, ovf;
         double idx_end;
-        const uint32_t n = sk_phase_table_ex(rec.last_index, rec.t_ratio, rec.end_idx, reinterpret_cast<double *>(side), dm.cap_np,
-                                             reinterpret_cast<SkRun *>(side + dm.cap_np * 8u), dm.cap_nr, &np, &nr, &ovf, &idx_end);
+        const uint32_t n_cur = sk_phase_table_ex(rec.last_index, rec.t_ratio, rec.end_idx, prefix, SK_PREFIX_MAX, runs, SK_RUNS_MAX, &np, &nr, &ovf, &idx_end);
         rec.last_index = __dsub_rn(idx_end, (double)rec.chunk);   // self.last_index = idx - chunk_size as f64
-        rec.chunk_count += 1u;
-        rec.n_out[par] = n;
-        rec.n_prefix[par] = (uint16_t)np;
-        rec.n_runs[par] = (uint16_t)nr;
-        rec.overflow = (rec.overflow & ~(1u << par)) | ((ovf ? 1u : 0u) << par);
-        if (ovf) status |= 2u;
-    }
-    // ---- re-framing bookkeeping (resampler.rs:425-428): a packet is emitted when carry + n_cur >= F
-    const uint32_t count = rec.chunk_count;
-    const uint32_t par_cur = (count - 1u) & 1u, par_prev = count & 1u;
-    const uint32_t n_cur = (pres && count >= 1u) ? rec.n_out[par_cur] : 0u;
-    const uint32_t n_prev = (count >= 2u) ? rec.n_out[par_prev] : 0u;
-    const uint32_t carry = rec.carry;
-    uint32_t emit = 0;
-    if (pres) {
-        if (carry > n_prev) status |= 4u;                     // carried frames span more than one chunk: unsupported
-        if ((rec.overflow >> par_prev) & 1u) status |= 2u;
+        rec.chunk_count = count0 + 1u;
+        if (ovf) status |= SKC_ST_OVERFLOW;
+        const uint32_t n_prev = count0 >= 1u ? rec.n_out[par_old] : 0u;
+        if (carry > n_prev) status |= SKC_ST_UNSUPPORTED;                 // carried frames span more than one chunk
+        if ((rec.overflow >> par_old) & 1u) status |= SKC_ST_OVERFLOW;    // the record the packet would execute is incomplete
+        // ---- re-framing (resampler.rs:425-428): a packet is emitted when carry + n_cur >= F
         const uint32_t avail = carry + n_cur;
-        emit = (avail >= F && !(status & 6u)) ? 1u : 0u;
         const uint32_t new_carry = (avail >= F) ? avail - F : avail;
-        if (new_carry > n_cur) status |= 1u;                  // backlog: a second packet is pending
+        if (avail >= F && !(status & (SKC_ST_OVERFLOW | SKC_ST_UNSUPPORTED)) && count0 >= 1u) {
+            // part 2 of the packet's program: its tail comes from this chunk
+            uint8_t *rec_old = slot_side(st, slot, par_old);
+            const uint32_t ne_old = rec.n_prefix[par_old];
+            status |= skc_fill_tail(prefix, np, runs, nr, rec.t_ratio, n_cur, carry, F, N, head, fb,
+                                    reinterpret_cast<ChainExp *>(rec_old + skc_exp_off(dm.prog)) + ne_old, dm.prog.cap_exp - min(ne_old, dm.prog.cap_exp));
+            prog_bytes = (skc_exp_off(dm.prog) + (ne_old + (F - min(carry, F))) * 8u + 15u) & ~15u;
+            emit = (status & (SKC_ST_OVERFLOW | SKC_ST_UNSUPPORTED)) ? 0u : 1u;
+        }
+        if (new_carry > n_cur) status |= 1u;                              // backlog: a second packet is pending
+        // ---- part 1 of the NEXT packet's program: the frames this chunk carries over
+        uint32_t n_seg = 0, n_exp = 0;
+        const uint32_t st_new = skc_build(prefix, np, runs, nr, rec.t_ratio, n_cur, min(new_carry, n_cur), F, fb, dm.prog, slot_side(st, slot, par_new), &n_seg, &n_exp);
+        rec.n_out[par_new] = n_cur;
+        rec.n_prefix[par_new] = (uint16_t)n_exp;
+        rec.n_runs[par_new] = (uint16_t)n_seg;
+        rec.overflow = (rec.overflow & ~(1u << par_new)) | (((st_new | (ovf ? SKC_ST_OVERFLOW : 0u)) ? 1u : 0u) << par_new);
         rec.carry = new_carry;
         *recp = rec;
     }
@@ -283,35 +264,27 @@ __global__ void __launch_bounds__(PHASE_CHAIN_THREADS) k_phase_chain(const OpHea
     reinterpret_cast<skgpu_chain_result *>(arena + results_off)[i] = res;
 
     const uint32_t parity = tick[0] & 1u;
-    const uint32_t ch = rec.channels, N = rec.chunk;
     const float *cur_g = reinterpret_cast<const float *>(arena + in.in_off + (uint64_t)parity * bank_stride);
     const float *prev_g = reinterpret_cast<const float *>(arena + in.in_off + (uint64_t)(1u - parity) * bank_stride);
     // a present input that emits nothing still retires its previous chunk: the history before the current chunk
     // (= last 16 frames of the previous one) goes into the current chunk's side record. Emitting inputs get it from
     // k_chain's consumers, which have the previous chunk in shared memory anyway.
-    if (pres && !emit && count >= 2u) {
-        float *h = reinterpret_cast<float *>(slot_side(st, slot, par_cur) + tab_bytes + SK_SIDE_HIST) - 16u * ch;
+    if (pres && !emit && count0 >= 1u) {
+        float *h = reinterpret_cast<float *>(slot_side(st, slot, par_new) + CH_HIST_OFF + SK_SIDE_HIST) - 16u * ch;
         for (uint32_t e = 0; e < 16u * ch; ++e) h[e] = prev_g[(size_t)(N - 16u) * ch + e];
     }
     ChainRec r;
-    const bool has_gain = in.gain_idx != SKGPU_NO_GAIN;
-    r.cons.t = rec.t_ratio;
-    r.cons.gain = has_gain ? gains[in.gain_idx] : 1.0f;
-    r.cons.carry = carry;
-    r.cons.kdelta = n_prev - min(carry, n_prev);
-    r.cons.n_cur = max(n_cur, 1u);
-    r.cons.np_nr = (count >= 2u ? ((uint32_t)rec.n_prefix[par_prev] | ((uint32_t)rec.n_runs[par_prev] << 8)) : 0u) |
-                   ((uint32_t)rec.n_prefix[par_cur] << 16) | ((uint32_t)rec.n_runs[par_cur] << 24);
-    // positions the current-chunk frames can reach: idx < -9 + (F - carry) * t  (last_index < -9 after the first chunk)
-    const float reach = (emit && carry < F) ? (float)(F - carry) * (float)rec.t_ratio : 0.0f;
-    r.cons.na_flags = ((count >= 2u) ? N : 0u) | (ch << 24) | ((has_gain ? 1u : 0u) << 26) | ((reach > (float)(CH_HEAD + 6) ? 1u : 0u) << 27);
+    r.cons.gain = in.gain_idx != SKGPU_NO_GAIN ? gains[in.gain_idx] : 1.0f;
+    r.cons.sc = ch;
     r.prev_g = prev_g;
     r.cur_g = cur_g;
     r.slot = slot;
-    r.chunk_bytes = N * ch * 4u;
-    r.flags = (emit ? CR_EMIT : 0u) | ((in.flags & SKGPU_MIX_IN_UNIQUE) ? CR_UNIQUE : 0u) | (reach >= 7.0f ? CR_NEEDS_HEAD : 0u) |
-              (par_prev ? CR_PAR_PREV : 0u) | (count >= 2u ? CR_HAS_PREV : 0u);
+    r.chunk_bytes = N * fb;
+    r.head_bytes = head * fb;
+    r.prog_bytes = prog_bytes;
+    r.flags = (emit ? CR_EMIT : 0u) | ((in.flags & SKGPU_MIX_IN_UNIQUE) ? CR_UNIQUE : 0u) | (par_old ? CR_PAR_PREV : 0u);
     r.N = N;
+    r.pad[0] = r.pad[1] = r.pad[2] = r.pad[3] = 0u;
     recs[i] = r;
 }
 
@@ -326,7 +299,7 @@ __global__ void __launch_bounds__(CH_THREADS, 4) k_chain(const OpHeader *__restr
 
     // dynamic smem: nstages x kb input slots, then the producer's scratch for sessions that need several batches
     const uint32_t kb = dm.kb, nstages = dm.nstages;
-    const uint32_t tab_bytes = chain_tab_bytes(dm);
+    const uint32_t prog_cap = skc_prog_cap(dm.prog);
     const uint32_t in_bytes = chain_in_bytes(dm);
     const uint32_t stage_bytes = kb * in_bytes;
     ChainRec *s_res = reinterpret_cast<ChainRec *>(smem_raw + (size_t)stage_bytes * nstages);
@@ -359,29 +332,28 @@ __global__ void __launch_bounds__(CH_THREADS, 4) k_chain(const OpHeader *__restr
                 const uint8_t *src = reinterpret_cast<const uint8_t *>(recs + g.first_input + lane);
                 uint8_t *dst = reinterpret_cast<uint8_t *>(&pf_rec[n & 1u][lane]);
 #pragma unroll
-                for (int w = 0; w < 4; ++w) cp_async16(dst + w * 16, src + w * 16);
+                for (int w = 0; w < 3; ++w) cp_async16(dst + w * 16, src + w * 16);   // the last 16 bytes are padding
             }
         };
         // one input: copy its consumer record into the stage and issue its bulk copies; returns the bytes the barrier must expect
         auto stage_input = [&](const ChainRec &r, uint32_t q, ChainStage *S, uint8_t *sm, uint64_t *bar) -> uint32_t {
             S->cons[q] = r.cons;
-            const uint32_t ch = (r.cons.na_flags >> 24) & 3u;
             const uint32_t par_prev = (r.flags & CR_PAR_PREV) ? 1u : 0u;
             ChainTail tl;
             tl.side_cur = slot_side(st, r.slot, par_prev ^ 1u);
-            tl.cur_g = r.cur_g;
-            tl.N = r.N; tl.ch = ch; tl.has_prev = (r.flags & CR_HAS_PREV) ? 1u : 0u; tl.pad = 0;
+            tl.N = r.N; tl.ch = r.cons.sc;
             S->tail[q] = tl;
             uint8_t *slot_sm = sm + (size_t)q * in_bytes;
-            uint8_t *chunk_sm = slot_sm + tab_bytes + SK_SIDE_HIST;
-            const uint32_t cb = (r.flags & CR_HAS_PREV) ? r.chunk_bytes : 0u;
-            const uint32_t hb = (r.flags & CR_NEEDS_HEAD) ? min((uint32_t)CH_HEAD, r.N) * ch * 4u : 0u;
-            uint32_t bytes = 2u * tab_bytes + SK_SIDE_HIST;
-            tma_bulk_g2s(slot_sm, slot_side(st, r.slot, par_prev), tab_bytes + SK_SIDE_HIST, bar);              // table + history of the previous chunk
-            tma_bulk_g2s(chunk_sm + dm.chunk_cap, slot_side(st, r.slot, par_prev ^ 1u), tab_bytes, bar);       // table of the current chunk
-            if (!(cb & 15u)) {
-                if (cb) { tma_bulk_g2s(chunk_sm, r.prev_g, cb, bar); bytes += cb; }
-                if (hb) { tma_bulk_g2s(chunk_sm + cb, r.cur_g, hb, bar); bytes += hb; }
+            uint8_t *chunk_sm = slot_sm + prog_cap + SK_SIDE_HIST;
+            const uint8_t *side_prev = slot_side(st, r.slot, par_prev);
+            const uint32_t cb = r.chunk_bytes, hb = r.head_bytes;
+            uint32_t bytes = r.prog_bytes + SK_SIDE_HIST;
+            tma_bulk_g2s(slot_sm, side_prev, r.prog_bytes, bar);                                  // frame program of the packet
+            tma_bulk_g2s(slot_sm + prog_cap, side_prev + CH_HIST_OFF, SK_SIDE_HIST, bar);         // 16 frames before the previous chunk
+            if (!(cb & 15u) && !(hb & 15u)) {
+                tma_bulk_g2s(chunk_sm, r.prev_g, cb, bar);
+                tma_bulk_g2s(chunk_sm + cb, r.cur_g, hb, bar);
+                bytes += cb + hb;
             } else {   // chunk size not a multiple of 16 bytes (e.g. mono 882 frames): no bulk copy, this lane copies
                 float *dst = reinterpret_cast<float *>(chunk_sm);
                 for (uint32_t e = 0; e < cb / 4u; ++e) dst[e] = r.prev_g[e];
@@ -395,8 +367,7 @@ __global__ void __launch_bounds__(CH_THREADS, 4) k_chain(const OpHeader *__restr
             S->last = last;
             S->has_base = has_base;
             S->out_off = grp.out_off;
-            S->has_master = grp.gain_idx != SKGPU_NO_GAIN;
-            S->master_gain = S->has_master ? gains[grp.gain_idx] : 1.0f;
+            S->master_gain = grp.gain_idx != SKGPU_NO_GAIN ? gains[grp.gain_idx] : 1.0f;
             S->flags = grp.flags;
             S->stop = 0;
         };
@@ -412,10 +383,10 @@ __global__ void __launch_bounds__(CH_THREADS, 4) k_chain(const OpHeader *__restr
             const uint32_t K = min(grp.n_inputs, (uint32_t)CH_MAX_INPUTS);
             ChainRec r;
             r.flags = 0;
-            r.cons.na_flags = 0;
+            r.cons.sc = 0;
             if (lane < min(K, 32u)) r = pf_rec[n & 1u][lane];
             const bool emit = (r.flags & CR_EMIT) != 0;
-            const bool elig = emit && ((r.cons.na_flags >> 24) & 3u) == (uint32_t)OC;   // packet already has the output shape
+            const bool elig = emit && r.cons.sc == (uint32_t)OC;   // packet already has the output shape
             // ---- summation order over the inputs that deliver a packet: base selection + swap_remove (mixer.rs:960-980),
             // computed by every lane from three ballots
             const uint32_t emit_mask = __ballot_sync(0xffffffffu, emit);
@@ -453,7 +424,7 @@ __global__ void __launch_bounds__(CH_THREADS, 4) k_chain(const OpHeader *__restr
                     int base = -1, base_unique = -1;
                     for (uint32_t j = 0; j < K; ++j) {
                         if (!(s_res[j].flags & CR_EMIT)) continue;
-                        if (((s_res[j].cons.na_flags >> 24) & 3u) == (uint32_t)OC) {
+                        if (s_res[j].cons.sc == (uint32_t)OC) {
                             const int u = (s_res[j].flags & CR_UNIQUE) ? 1 : 0;
                             if (u >= base_unique) { base = (int)m; base_unique = u; }
                         }
@@ -503,124 +474,63 @@ __global__ void __launch_bounds__(CH_THREADS, 4) k_chain(const OpHeader *__restr
     }
 
     // =================================================================== consumer warps
-    const uint32_t ct = threadIdx.x - 32u;  // 0..255
-    float acc[ITERS][CH_FPT * OC];
+    const uint32_t cw = warp - 1u, ct = threadIdx.x - 32u;
+    unsigned long long acc[ITERS][4];   // (left, right) packed f32x2 per owned frame (mono: low half)
+    const unsigned long long one2 = pack2(dm.one, dm.one);   // 1.0f the compiler cannot see (add2)
     uint32_t stage = 0, fphase = 0;
     for (;;) {
         mbar_wait(&bar_full[stage], fphase);
         const ChainStage *S = &s_stage[stage];
         const uint4 hd = *reinterpret_cast<const uint4 *>(&S->nb);   // nb, first, last, has_base (one broadcast load)
         if (S->stop) break;
-        const uint8_t *sm = smem_raw + (size_t)stage * stage_bytes;
+        const uint32_t sm = smem_u32(smem_raw) + stage * stage_bytes;
         const uint32_t nb = (dm.debug & 1u) ? 0u : hd.x;
-        const bool first = hd.y != 0;
-        if (first) {
+        if (hd.y != 0) {
+            // the base frame IS the accumulator (mixer.rs:969-972): start from -0.0, the additive identity of every f32
+            // (-0.0 + v == v bit for bit, also for v == -0.0); without a base frame the mix starts from vec![0.0; n]
+            const unsigned long long init = hd.w != 0 ? 0x8000000080000000ull : 0ull;
 #pragma unroll
             for (int it = 0; it < ITERS; ++it)
 #pragma unroll
-                for (int e = 0; e < CH_FPT * OC; ++e) acc[it][e] = 0.0f;  // vec![0.0f32; output_size] when there is no base frame
+                for (int f = 0; f < 4; ++f) acc[it][f] = init;
         }
         for (uint32_t q = 0; q < nb; ++q) {
-            // everything the inner loop needs about this input: two broadcast 16-byte loads
-            const uint4 c0 = *reinterpret_cast<const uint4 *>(&S->cons[q]);
-            const uint4 c1 = *(reinterpret_cast<const uint4 *>(&S->cons[q]) + 1);
-            ChainInRegs in;
-            in.t = __hiloint2double((int)c0.y, (int)c0.x);
-            in.gain = __uint_as_float(c0.z);
-            in.carry = c0.w;
-            in.kdelta = c1.x;
-            in.n_cur = c1.y;
-            in.NA = c1.w & 0xFFFFFFu;
-            in.has_gain = (c1.w >> 26) & 1u;
-            in.cur_g = nullptr;
-            const uint32_t sc = (c1.w >> 24) & 3u;
-            const bool needs_global = ((c1.w >> 27) & 1u) != 0;
-            const uint8_t *slot_sm = sm + (size_t)q * in_bytes;
-            const uint8_t *chunk_sm = slot_sm + tab_bytes + SK_SIDE_HIST;
-            // A = [16 history frames | previous chunk | head of the current chunk]; the history field ends where the chunk begins
-            const float *A = reinterpret_cast<const float *>(chunk_sm) - 16u * sc;
-            const uint8_t *tc = chunk_sm + dm.chunk_cap;
-            PhaseView Tp, Tc;
-            Tp.prefix = reinterpret_cast<const double *>(slot_sm);
-            Tp.runs = reinterpret_cast<const SkRun *>(slot_sm + dm.cap_np * 8u);
-            Tp.n_prefix = c1.z & 0xFFu; Tp.n_runs = (c1.z >> 8) & 0xFFu; Tp.n_out = max(in.kdelta + in.carry, 1u);
-            Tc.prefix = reinterpret_cast<const double *>(tc);
-            Tc.runs = reinterpret_cast<const SkRun *>(tc + dm.cap_np * 8u);
-            Tc.n_prefix = (c1.z >> 16) & 0xFFu; Tc.n_runs = (c1.z >> 24) & 0xFFu; Tc.n_out = in.n_cur;
-            const bool is_base = first && hd.w != 0 && q == 0u;
-#pragma unroll
-            for (int it = 0; it < ITERS; ++it) {
-                const uint32_t j0 = (ct + it * CH_CONSUMERS) * CH_FPT;
-                const uint32_t j0_warp_first = (ct - lane + it * CH_CONSUMERS) * CH_FPT;   // warp-uniform
-                if (j0_warp_first >= F) continue;                                            // whole warp past the packet
-                if (needs_global) {
-                    if (j0 < F) {
-                        // rare path, out of line: it works on a copy so that `acc` itself never has its address taken
-                        // (an escaping pointer would push the accumulators into local memory for the hot path too)
-                        float tmp[CH_FPT * OC];
-#pragma unroll
-                        for (int e = 0; e < CH_FPT * OC; ++e) tmp[e] = acc[it][e];
-                        in.cur_g = S->tail[q].cur_g;
-                        if (sc == 2u) chain_input_global<OC, 2>(in, A, Tp, Tc, F, j0, tmp, is_base);
-                        else chain_input_global<OC, 1>(in, A, Tp, Tc, F, j0, tmp, is_base);
-#pragma unroll
-                        for (int e = 0; e < CH_FPT * OC; ++e) acc[it][e] = tmp[e];
-                    }
-                } else if (is_base) {   // uniform: the base frame IS the accumulator (no add), mixer.rs:969-972
-                    if (sc == 2u) chain_input<OC, 2, true>(in, A, Tp, Tc, j0, acc[it]);
-                    else chain_input<OC, 1, true>(in, A, Tp, Tc, j0, acc[it]);
-                } else {
-                    if (sc == 2u) chain_input<OC, 2, false>(in, A, Tp, Tc, j0, acc[it]);
-                    else chain_input<OC, 1, false>(in, A, Tp, Tc, j0, acc[it]);
-                }
-            }
+            const ChainCons c = S->cons[q];
+            const uint32_t prog = sm + q * in_bytes;
+            if (c.sc == 2u) chain_consume<OC, 2, ITERS>(acc, prog, prog + prog_cap, dm.prog, F, cw, lane, c.gain, one2);
+            else chain_consume<OC, 1, ITERS>(acc, prog, prog + prog_cap + SK_SIDE_HIST - 64u, dm.prog, F, cw, lane, c.gain, one2);
         }
         if (hd.z != 0) {
-            // ---- epilogue: master gain, then clip + s16 pack (or f32)
-            const bool has_master = S->has_master != 0;
-            const float mg = S->master_gain;
+            // ---- epilogue: master gain, then clip + s16 pack (or f32); a warp stores 32 consecutive frames per instruction
+            const unsigned long long mg2 = pack2(S->master_gain, S->master_gain);   // audio::gain after the mixer (x * 1.0 == x when there is none)
             const uint32_t flags = S->flags;
             uint8_t *out_base = arena + S->out_off;
 #pragma unroll
             for (int it = 0; it < ITERS; ++it) {
-                const uint32_t j0 = (ct + it * CH_CONSUMERS) * CH_FPT;
-                if (j0 >= F) continue;
-                float *a = acc[it];
-                if (has_master) {
 #pragma unroll
-                    for (int e = 0; e < CH_FPT * OC; ++e) a[e] = __fmul_rn(a[e], mg);
-                }
-                const uint32_t nfr = min((uint32_t)CH_FPT, F - j0);
-                if (flags & SKGPU_MIX_OUT_S16) {
-                    uint16_t *o = reinterpret_cast<uint16_t *>(out_base) + (size_t)j0 * OC;
-                    if (nfr == CH_FPT && OC == 2) {
-                        stg_stream_u4(reinterpret_cast<uint4 *>(o), make_uint4(pack_s16x2(a[0], a[1]), pack_s16x2(a[2], a[3]),
-                                                                              pack_s16x2(a[4 % (CH_FPT * OC)], a[5 % (CH_FPT * OC)]),
-                                                                              pack_s16x2(a[6 % (CH_FPT * OC)], a[7 % (CH_FPT * OC)])));
-                    } else if (nfr == CH_FPT && OC == 1) {
-                        stg_stream_u2(reinterpret_cast<uint2 *>(o), make_uint2(pack_s16x2(a[0], a[1]), pack_s16x2(a[2], a[3])));
+                for (int f = 0; f < 4; ++f) {
+                    const uint32_t j = (((uint32_t)it * 8u + cw) * 4u + (uint32_t)f) * 32u + lane;
+                    if (j >= F) continue;
+                    float a0, a1;
+                    unpack2(mul2v(acc[it][f], mg2), a0, a1);
+                    if (flags & SKGPU_MIX_OUT_S16) {
+                        if (OC == 2) stg_stream_u32(reinterpret_cast<uint32_t *>(out_base) + j, pack_s16x2(a0, a1));
+                        else reinterpret_cast<uint16_t *>(out_base)[j] = (uint16_t)f32_to_s16_bits(a0);
                     } else {
-                        for (uint32_t e = 0; e < nfr * OC; ++e) o[e] = (uint16_t)f32_to_s16_bits(a[e]);
-                    }
-                } else {
-                    float *o = reinterpret_cast<float *>(out_base) + (size_t)j0 * OC;
-                    if (nfr == CH_FPT) {
-                        stg_stream_f4(reinterpret_cast<float4 *>(o), make_float4(a[0], a[1], a[2], a[3]));
-                        if (OC == 2) stg_stream_f4(reinterpret_cast<float4 *>(o) + 1, make_float4(a[4 % (CH_FPT * OC)], a[5 % (CH_FPT * OC)], a[6 % (CH_FPT * OC)], a[7 % (CH_FPT * OC)]));
-                    } else {
-                        for (uint32_t e = 0; e < nfr * OC; ++e) o[e] = a[e];
+                        if (OC == 2) stg_stream_f2(reinterpret_cast<float2 *>(out_base) + j, make_float2(a0, a1));
+                        else reinterpret_cast<float *>(out_base)[j] = a0;
                     }
                 }
             }
         }
         // ---- history before the current chunk := last 16 frames of the previous chunk (now retired), written into the
-        // current chunk's side record (next tick it is the "previous" one and travels with its table in one bulk copy)
+        // current chunk's side record (next tick it is the "previous" one)
         if (ct < 16u * 2u) {
             for (uint32_t q = 0; q < hd.x; ++q) {
                 const ChainTail tl = S->tail[q];
-                if (tl.has_prev && ct < 16u * tl.ch) {
-                    const float *chunk_f = reinterpret_cast<const float *>(sm + (size_t)q * in_bytes + tab_bytes + SK_SIDE_HIST);
-                    float *h = reinterpret_cast<float *>(tl.side_cur + tab_bytes + SK_SIDE_HIST) - 16u * tl.ch;
+                if (ct < 16u * tl.ch) {
+                    const float *chunk_f = reinterpret_cast<const float *>(smem_raw + (size_t)stage * stage_bytes + (size_t)q * in_bytes + prog_cap + SK_SIDE_HIST);
+                    float *h = reinterpret_cast<float *>(tl.side_cur + CH_HIST_OFF + SK_SIDE_HIST) - 16u * tl.ch;
                     h[ct] = chunk_f[(size_t)(tl.N - 16u) * tl.ch + ct];
                 }
             }

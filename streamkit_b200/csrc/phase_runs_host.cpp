@@ -1,7 +1,9 @@
 // Host-side test shim for phase_runs.h (the SAME source the CUDA kernels compile): lets the CPU test
 // suite verify the phase-table representation against the plain sequential recurrence.
 #include "phase_runs.h"
+#include <algorithm>
 #include <cmath>
+#include <cstring>
 #include <vector>
 
 extern "C" {
@@ -59,4 +61,114 @@ void skp_table_sizes(uint32_t *table_bytes, uint32_t *prefix_max, uint32_t *runs
     *prefix_max = SK_PREFIX_MAX;
     *runs_max = SK_RUNS_MAX;
 }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Frame programs of the fused chain (chain_prog.h): simulate `calls` ticks of one stream exactly as k_phase_chain does
+// (generator -> tail of the pending packet -> part 1 of the next), execute every emitted packet's program the way
+// k_chain's consumers do (block map -> segments -> lanes, including the integer floor/fraction split of fast run
+// segments) and compare each frame's (buffer offset, fraction) with the plain sequential recurrence.
+#include "chain_prog.h"
+
+extern "C" uint64_t skc_check_stream(double ratio, uint32_t chunk, uint32_t F, uint32_t channels, uint32_t calls, uint32_t cap_seg,
+                                     uint32_t cap_exp, uint32_t *packets_out, uint32_t *max_seg, uint32_t *max_exp, uint32_t *status_or) {
+    const double t = 1.0 / ratio;
+    const int32_t end_idx = (int32_t)chunk - 9 - (int32_t)std::ceil(t);
+    const uint32_t fb = channels * 4u, head = std::min(32u, chunk);
+    ChainProgDims d;
+    d.nblk = (F + 31u) / 32u;
+    d.map_bytes = (d.nblk * 2u + 15u) & ~15u;
+    d.cap_seg = cap_seg;
+    d.cap_exp = cap_exp;
+    std::vector<uint8_t> rec[2] = {std::vector<uint8_t>(skc_prog_cap(d) + 64), std::vector<uint8_t>(skc_prog_cap(d) + 64)};
+    uint32_t n_exp_rec[2] = {0, 0}, n_out_rec[2] = {0, 0};
+    std::vector<double> seq_prev, seq_cur;   // the true chain of the previous / current chunk
+    SkPhaseTable T;
+    uint64_t bad = 0;
+    uint32_t packets = 0, ms = 0, me = 0, st_or = 0;
+    double L = -4.0;
+    uint32_t carry = 0;
+    for (uint32_t c = 0; c < calls; ++c) {
+        const uint32_t par_new = c & 1u, par_old = par_new ^ 1u;
+        double idx_end = 0;
+        const uint32_t n_cur = sk_phase_table(L, t, end_idx, &T, &idx_end);
+        seq_cur.clear();
+        for (double idx = L; idx < (double)end_idx;) { idx += t; seq_cur.push_back(idx); }
+        if (seq_cur.size() != n_cur) ++bad;
+        const uint32_t avail = carry + n_cur;
+        const uint32_t new_carry = avail >= F ? avail - F : avail;
+        if (avail >= F && c >= 1 && carry <= n_out_rec[par_old]) {
+            uint8_t *ro = rec[par_old].data();
+            const uint32_t ne_old = n_exp_rec[par_old];
+            const uint32_t st = skc_fill_tail(T.prefix, T.n_prefix, T.runs, T.n_runs, t, n_cur, carry, F, chunk, head, fb,
+                                              reinterpret_cast<ChainExp *>(ro + skc_exp_off(d)) + ne_old, d.cap_exp - std::min(ne_old, d.cap_exp));
+            st_or |= st;
+            if (!st) {
+                ++packets;
+                me = std::max(me, ne_old + (F - std::min(carry, F)));
+                // ---- execute the program like the consumers
+                const uint16_t *map = reinterpret_cast<const uint16_t *>(ro);
+                const ChainSegX *segx = reinterpret_cast<const ChainSegX *>(ro + skc_segx_off(d));
+                const ChainSegJ *segj = reinterpret_cast<const ChainSegJ *>(ro + skc_segj_off(d));
+                const ChainExp *exps = reinterpret_cast<const ChainExp *>(ro + skc_exp_off(d));
+                std::vector<int> hits(F, 0);
+                const uint32_t kd = n_out_rec[par_old] - carry;
+                for (uint32_t b = 0; b < d.nblk; ++b) {
+                    const uint32_t ent = map[b];
+                    for (uint32_t s = ent & 0xFFu; s <= (ent >> 8); ++s) {
+                        const uint32_t j0 = segj[s].jj & 0xFFFFu, len = (segj[s].jj >> 16) - j0, info = segj[s].info;
+                        for (uint32_t lane = 0; lane < 32; ++lane) {
+                            if (b * 32u + lane >= F) continue;
+                            const uint32_t j = b * 32u + lane, rel = j - j0;
+                            if (!(rel < len)) continue;
+                            uint32_t off;
+                            float frac;
+                            if (info & SKC_SEG_E) {
+                                const ChainExp e = exps[(info & 0xFFFFu) + rel];
+                                off = e.aoff; frac = e.frac;
+                            } else {
+                                const double x = __builtin_fma((double)rel, segx[s].delta, segx[s].x0);
+                                if (info & SKC_SEG_FAST) {
+                                    const uint32_t sh = (info >> 16) & 31u;
+                                    const uint64_t bits = sk_d2bits(x);
+                                    const uint32_t hi = (uint32_t)(bits >> 32);
+                                    const uint32_t fl = ((hi & 0xFFFFFu) | 0x100000u) >> sh;
+                                    const double fl_d = sk_bits2d((uint64_t)(hi & (0xFFFFFFFFu << sh)) << 32);
+                                    frac = (float)(x - fl_d);
+                                    off = (16u + fl) * fb;
+                                } else {
+                                    int32_t fl;
+                                    skc_split(x, &fl, &frac);
+                                    off = (uint32_t)(16 + fl) * fb;
+                                }
+                            }
+                            // expectation from the true chain
+                            const bool from_cur = j >= carry;
+                            const double xt = from_cur ? seq_cur[j - carry] : seq_prev[kd + j];
+                            const double fl_t = std::floor(xt);
+                            const uint32_t off_t = (uint32_t)((from_cur ? (int)chunk : 0) + 16 + (int)fl_t) * fb;
+                            const float frac_t = (float)(xt - fl_t);
+                            if (off != off_t || memcmp(&frac, &frac_t, 4) != 0) ++bad;
+                            ++hits[j];
+                        }
+                    }
+                }
+                for (uint32_t j = 0; j < F; ++j) if (hits[j] != 1) ++bad;
+            }
+        }
+        uint32_t ns = 0, ne = 0;
+        const uint32_t stb = skc_build(T.prefix, T.n_prefix, T.runs, T.n_runs, t, n_cur, std::min(new_carry, n_cur), F, fb, d, rec[par_new].data(), &ns, &ne);
+        st_or |= stb;
+        ms = std::max(ms, ns);
+        n_exp_rec[par_new] = ne;
+        n_out_rec[par_new] = n_cur;
+        carry = new_carry;
+        seq_prev.swap(seq_cur);
+        L = idx_end - (double)chunk;
+    }
+    *packets_out = packets;
+    *max_seg = ms;
+    *max_exp = me;
+    *status_or = st_or;
+    return bad;
 }

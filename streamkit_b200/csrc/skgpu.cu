@@ -714,27 +714,44 @@ extern "C" uint64_t skgpu_plan_tick_count(const skgpu_plan *p) { return p ? p->t
 
 // ---- chain
 
-// Upper bounds of the phase-table sizes a stream configuration can produce: run the (host-compiled) generator for the
-// first chunk and for a spread of steady-state phases. The kernel re-checks at run time (status bit1).
-static void phase_table_bounds(double t, int32_t end_idx, uint32_t *np, uint32_t *nr) {
+// Upper bounds of the frame-program sizes (chain_prog.h) a stream configuration can produce: run the host-compiled
+// generator + builder over the first chunks of a stream and over a spread of steady-state phases. The kernel
+// re-checks at run time (status bit1).
+static void prog_bounds(double t, int32_t end_idx, uint32_t N, uint32_t F, uint32_t *need_seg, uint32_t *need_exp) {
+    ChainProgDims big{};
+    big.nblk = (F + 31u) / 32u;
+    big.map_bytes = (big.nblk * 2u + 15u) & ~15u;
+    big.cap_seg = 254u;
+    big.cap_exp = 8192u;
+    std::vector<uint8_t> scratch(skc_prog_cap(big));
     SkPhaseTable T;
-    double idx_end;
-    uint32_t mp = 0, mr = 0;
-    sk_phase_table(-4.0, t, end_idx, &T, &idx_end);
-    mp = std::max(mp, T.n_prefix); mr = std::max(mr, T.n_runs);
+    uint32_t ms = 0, me = 0;
+    auto one_chunk = [&](double last_index, uint32_t carry, double *next_index, uint32_t *next_carry) {
+        double idx_end;
+        const uint32_t n_cur = sk_phase_table(last_index, t, end_idx, &T, &idx_end);
+        const uint32_t avail = carry + n_cur;
+        const uint32_t nc = avail >= F ? avail - F : avail;
+        uint32_t ns = 0, ne = 0;
+        skc_build(T.prefix, T.n_prefix, T.runs, T.n_runs, t, n_cur, std::min(nc, n_cur), F, 8u, big, scratch.data(), &ns, &ne);
+        ms = std::max(ms, ns);
+        me = std::max(me, ne + (F - std::min(nc, F)));
+        *next_index = idx_end - (double)N;
+        *next_carry = nc;
+    };
+    double li = -4.0, nli;
+    uint32_t carry = 0, ncarry, steady = 0;
+    for (int c = 0; c < 8; ++c) { one_chunk(li, carry, &nli, &ncarry); li = nli; carry = ncarry; steady = carry; }
     const double lo = -(9.0 + std::ceil(t));
-    for (int i = 0; i < 64; ++i) {
-        sk_phase_table(lo + t * (i + 0.37) / 64.0, t, end_idx, &T, &idx_end);
-        mp = std::max(mp, T.n_prefix); mr = std::max(mr, T.n_runs);
-    }
-    *np = mp; *nr = mr;
+    for (int i = 0; i < 64; ++i) one_chunk(lo + t * (i + 0.37) / 64.0, steady, &nli, &ncarry);
+    *need_seg = ms; *need_exp = me;
 }
 
 static skgpu_rc validate_chain(const skgpu_plan *p, const skgpu_chain_group *g, uint32_t ng, const skgpu_chain_input *in, uint32_t ni,
-                               uint32_t F, uint32_t *max_k, uint32_t *max_buf_floats, int *oc_out, uint32_t *cap_np, uint32_t *cap_nr) {
-    uint32_t need_np = 0, need_nr = 0;
+                               uint32_t F, uint32_t *max_k, uint32_t *max_buf_floats, int *oc_out, uint32_t *cap_seg, uint32_t *cap_exp) {
+    uint32_t need_seg = 0, need_exp = 0;
     double last_t = -1.0;
     int32_t last_end = 0;
+    uint32_t last_N = 0;
     const skgpu_ctx *c = p->ctx;
     uint32_t mk = 0, mb = 0;
     int oc = -1;
@@ -753,11 +770,11 @@ static skgpu_rc validate_chain(const skgpu_plan *p, const skgpu_chain_group *g, 
         if (rc) return rc;
         if (in[i].gain_idx != SKGPU_NO_GAIN && in[i].gain_idx >= p->n_gains) return fail(SKGPU_ERR_INVALID, "chain input %u: gain_idx out of range", i);
         mb = std::max(mb, (N + (uint32_t)CH_HEAD) * C * 4u);   // bytes: previous chunk + staged head of the current one
-        if (c->h_t[slot] != last_t || c->h_end[slot] != last_end) {   // streams of one op usually share a handful of configurations
+        if (c->h_t[slot] != last_t || c->h_end[slot] != last_end || N != last_N) {   // streams of one op usually share a handful of configurations
             uint32_t a = 0, b = 0;
-            phase_table_bounds(c->h_t[slot], c->h_end[slot], &a, &b);
-            need_np = std::max(need_np, a); need_nr = std::max(need_nr, b);
-            last_t = c->h_t[slot]; last_end = c->h_end[slot];
+            prog_bounds(c->h_t[slot], c->h_end[slot], N, F, &a, &b);
+            need_seg = std::max(need_seg, a); need_exp = std::max(need_exp, b);
+            last_t = c->h_t[slot]; last_end = c->h_end[slot]; last_N = N;
         }
     }
     for (uint32_t i = 0; i < ng; ++i) {
@@ -781,18 +798,29 @@ static skgpu_rc validate_chain(const skgpu_plan *p, const skgpu_chain_group *g, 
     *max_buf_floats = (mb + 15u) & ~15u;
     *oc_out = oc < 0 ? 2 : oc;
     // margin for phases the sampling did not hit; even counts keep every staged array a multiple of 16 bytes
-    *cap_np = std::min<uint32_t>(SK_PREFIX_MAX, (need_np + 5u) & ~1u);
-    *cap_nr = std::min<uint32_t>(SK_RUNS_MAX, (need_nr + 3u) & ~1u);
+    *cap_seg = (need_seg + 5u) & ~1u;
+    *cap_exp = (need_exp + 9u) & ~1u;
+    {
+        ChainProgDims d{};
+        d.nblk = (F + 31u) / 32u;
+        d.map_bytes = (d.nblk * 2u + 15u) & ~15u;
+        d.cap_seg = *cap_seg;
+        d.cap_exp = *cap_exp;
+        if (*cap_seg > 254u || skc_prog_cap(d) > CH_HIST_OFF)
+            return fail(SKGPU_ERR_INVALID, "chain op: frame program of %u segments + %u explicit frames does not fit a stream's side record (use the unfused ops)", *cap_seg, *cap_exp);
+    }
     return SKGPU_OK;
 }
 
-static void chain_size_smem(Op &op, uint32_t max_k, uint32_t chunk_cap, uint32_t cap_np, uint32_t cap_nr) {
-    // nstages pipeline stages, each staging up to kb inputs: [table prev | history 128 B | previous chunk + head | table cur].
+static void chain_size_smem(Op &op, uint32_t max_k, uint32_t chunk_cap, uint32_t cap_seg, uint32_t cap_exp) {
+    // nstages pipeline stages, each staging up to kb inputs: [frame program | history 128 B | previous chunk + head].
     // 4 CTAs per SM is the register limit (56 regs x 288 threads); pick the deepest ring that keeps 4 CTAs in 227 KB.
     ChainDims dm{};
     dm.chunk_cap = chunk_cap;
-    dm.cap_np = cap_np;
-    dm.cap_nr = cap_nr;
+    dm.prog.nblk = (op.chain_F + 31u) / 32u;
+    dm.prog.map_bytes = (dm.prog.nblk * 2u + 15u) & ~15u;
+    dm.prog.cap_seg = cap_seg;
+    dm.prog.cap_exp = cap_exp;
     dm.max_k = std::max(max_k, 1u);
     const uint64_t in_bytes = chain_in_bytes(dm);
     uint32_t kb = std::max(1u, std::min<uint32_t>(max_k, CH_MAX_KB));
@@ -810,6 +838,7 @@ static void chain_size_smem(Op &op, uint32_t max_k, uint32_t chunk_cap, uint32_t
         if (v >= 2 && v <= CH_MAX_STAGES) best_ns = (uint32_t)v;
     }
     dm.kb = kb;
+    dm.one = 1.0f;
     dm.nstages = best_ns;
     dm.debug = std::getenv("SKGPU_CHAIN_DEBUG") ? (uint32_t)std::atoi(std::getenv("SKGPU_CHAIN_DEBUG")) : 0u;
     op.chain_kb = kb;
@@ -874,7 +903,7 @@ extern "C" skgpu_rc skgpu_plan_update_chain(skgpu_plan *p, uint32_t opi, const s
     if (ng && oc != op.chain_oc) return fail(SKGPU_ERR_INVALID, "update changes the op's output channel count");
     if (mb > op.chain_buf_floats) return fail(SKGPU_ERR_INVALID, "update has a longer chunk than the op was sized for");
     if (mk > op.chain_dm.max_k) return fail(SKGPU_ERR_INVALID, "update has a session with more inputs (%u) than the op was sized for (%u)", mk, op.chain_dm.max_k);
-    if (cnp > op.chain_dm.cap_np || cnr > op.chain_dm.cap_nr) return fail(SKGPU_ERR_INVALID, "update adds a resampling ratio whose phase tables exceed the op's staging capacity");
+    if (cnp > op.chain_dm.prog.cap_seg || cnr > op.chain_dm.prog.cap_exp) return fail(SKGPU_ERR_INVALID, "update adds a resampling ratio whose phase tables exceed the op's staging capacity");
     CU(cudaStreamSynchronize(p->ctx->stream));
     if (ng) memcpy(op.h_tab, groups, ng * sizeof(skgpu_chain_group));
     if (ni) memcpy(op.h_tab2, inputs, ni * sizeof(skgpu_chain_input));
