@@ -6,39 +6,49 @@
 // packet's frame index j in [0, F) that the mixing kernel can execute without searching anything:
 //
 //   run segment       x_j = fma((double)(j - j0), delta, x0)         exact (all values in one binade, see phase_runs.h);
-//                     SKC_SEG_FAST: the binade is [2^e, 2^(e+1)) with 0 <= e <= 20, so floor(x) and x - floor(x) come
-//                     from integer operations on the high word of the double (info carries 20 - e)
+//                     FAST: the binade is [2^e, 2^(e+1)) with 0 <= e <= 17, so floor(x) and x - floor(x) come from
+//                     integer operations on the high word of the double (mask, shift and offset precomputed)
 //   explicit segment  (buffer offset, f32 fraction) stored per frame: prefix / gap / tiny-run elements and the packet's
 //                     tail, whose frames are produced by the CURRENT chunk (appended one tick later)
 //   block map         for every 32-frame block of the packet: first and last segment touching it
 //
 // Record layout (one per stream and chunk parity, in HBM; copied to shared memory by ONE bulk copy of the used bytes):
-//   [ map: nblk x u16, padded to 16 B | segx: cap_seg x {x0, delta} | segj: cap_seg x {j0 | j1 << 16, info} | exps ... ]
+//   [ map: nblk x u16, padded to 16 B | segs: cap_seg x ChainSeg (32 B) | exps: ChainExp (8 B) ... ]
 #pragma once
 #include <stdint.h>
 
 #include "phase_runs.h"
 
-#define SKC_SEG_E 0x80000000u     // explicit segment; info & 0xFFFF = index of its first ChainExp
-#define SKC_SEG_FAST 0x40000000u  // run segment inside [2^e, 2^(e+1)), 0 <= e <= 20; (info >> 16) & 31 = 20 - e
+#define SKC_TAB_PREFIX 24u        // capacities of the thread-private phase table the program is built from (host and
+#define SKC_TAB_RUNS 24u          // device must use the same ones: they shape the table, hence the program)
 #define SKC_MIN_RUN 8u            // shorter run pieces are stored explicitly (one pass of the consumer costs ~25 instructions)
 #define SKC_ST_OVERFLOW 2u        // status bit1: a table of the record overflowed
 #define SKC_ST_UNSUPPORTED 4u     // status bit2: the packet needs frames the kernel does not stage
+#define SKC_KIND_E 0u             // ChainSeg.himask: explicit segment
+#define SKC_KIND_SLOW 1u          // ChainSeg.himask: run segment outside [1, 2^18): floor / fraction by real conversions
+                                  // any other value: FAST run segment, the mask that clears the fraction bits of the high word
 
-struct ChainSegX { double x0, delta; };
-struct ChainSegJ { uint32_t jj, info; };        // jj = j0 | j1 << 16
+// One segment = two 16-byte shared-memory loads in the consumer. FAST run segments lie in one binade [2^e, 2^(e+1)),
+// 0 <= e <= 17, so with hi = high word of x:  floor(x) as a double = {hi & himask, 0}  and the byte offset of buffer
+// frame floor(x) is ((hi & himask) >> sh) - cs   (sh = 20 - e - log2(frame_bytes), cs = (1022 + e) << (20 - sh)).
+struct ChainSeg {
+    double x0, delta;   // run: x_j = fma((double)(j - j0), delta, x0)
+    uint32_t jj;        // j0 | j1 << 16
+    uint32_t himask;    // SKC_KIND_E, SKC_KIND_SLOW, or the FAST mask
+    uint32_t aux;       // E: byte offset of its first ChainExp from the record start; FAST: cs
+    uint32_t sh;        // FAST: shift
+};
 struct ChainExp { uint32_t aoff; float frac; };  // byte offset of frame y0 from the start of the 16-frame history
 
 struct ChainProgDims {
     uint32_t nblk;       // ceil(F / 32)
     uint32_t map_bytes;  // nblk * 2 rounded up to 16
-    uint32_t cap_seg;    // even
+    uint32_t cap_seg;
     uint32_t cap_exp;    // even
 };
-SK_HD uint32_t skc_segx_off(const ChainProgDims &d) { return d.map_bytes; }
-SK_HD uint32_t skc_segj_off(const ChainProgDims &d) { return d.map_bytes + d.cap_seg * 16u; }
-SK_HD uint32_t skc_exp_off(const ChainProgDims &d) { return d.map_bytes + d.cap_seg * 24u; }
-SK_HD uint32_t skc_prog_cap(const ChainProgDims &d) { return d.map_bytes + d.cap_seg * 24u + d.cap_exp * 8u; }
+SK_HD uint32_t skc_seg_off(const ChainProgDims &d) { return d.map_bytes; }
+SK_HD uint32_t skc_exp_off(const ChainProgDims &d) { return d.map_bytes + d.cap_seg * 32u; }
+SK_HD uint32_t skc_prog_cap(const ChainProgDims &d) { return d.map_bytes + d.cap_seg * 32u + d.cap_exp * 8u; }
 
 // T::coerce(idx - idx.floor()) and floor(idx) of rubato's interpolation loop
 SK_HD void skc_split(double x, int32_t *fl, float *frac) {
@@ -55,37 +65,43 @@ SK_HD void skc_split(double x, int32_t *fl, float *frac) {
 
 struct SkcBuilder {   // appends segments in increasing j and completes the block map on the fly
     uint16_t *map;
-    ChainSegX *segx;
-    ChainSegJ *segj;
+    ChainSeg *segs;
     ChainExp *exps;
     ChainProgDims d;
     uint32_t F, frame_bytes;
     uint32_t n_seg, n_exp, bcur, first_cur, status;
+    uint64_t map_acc;       // four map entries are collected and stored as one 8-byte word
     // the open explicit segment (consecutive explicit frames share one segment)
     uint32_t e_j0, e_first;
     bool e_open;
 };
 
-SK_HD void skc_append(SkcBuilder &b, uint32_t j0, uint32_t j1, double x0, double delta, uint32_t info) {
+SK_HD void skc_append(SkcBuilder &b, uint32_t j0, uint32_t j1, double x0, double delta, uint32_t himask, uint32_t aux, uint32_t sh) {
     if (b.n_seg >= b.d.cap_seg || b.n_seg >= 255u) { b.status |= SKC_ST_OVERFLOW; return; }
     const uint32_t s = b.n_seg++;
-    ChainSegX sx; sx.x0 = x0; sx.delta = delta;
-    ChainSegJ sj; sj.jj = j0 | (j1 << 16); sj.info = info;
-    b.segx[s] = sx;
-    b.segj[s] = sj;
+    ChainSeg sg;
+    sg.x0 = x0; sg.delta = delta; sg.jj = j0 | (j1 << 16); sg.himask = himask; sg.aux = aux; sg.sh = sh;
+    b.segs[s] = sg;
     while (b.bcur < b.d.nblk) {
         const uint32_t bs = 32u * b.bcur;
         const uint32_t be = (bs + 31u < b.F - 1u) ? bs + 31u : b.F - 1u;
         if (bs >= j0 && bs < j1) b.first_cur = s;
         if (be >= j1) break;
-        b.map[b.bcur] = (uint16_t)(b.first_cur | (s << 8));
+        b.map_acc |= (uint64_t)(b.first_cur | (s << 8)) << (16u * (b.bcur & 3u));
+        if ((b.bcur & 3u) == 3u) {
+            reinterpret_cast<uint64_t *>(b.map)[b.bcur >> 2] = b.map_acc;
+            b.map_acc = 0;
+        }
         ++b.bcur;
     }
+}
+SK_HD void skc_flush_map(SkcBuilder &b) {
+    if (b.bcur & 3u) reinterpret_cast<uint64_t *>(b.map)[b.bcur >> 2] = b.map_acc;
 }
 SK_HD void skc_close_exp(SkcBuilder &b, uint32_t j_end) {
     if (!b.e_open) return;
     b.e_open = false;
-    skc_append(b, b.e_j0, j_end, 0.0, 0.0, SKC_SEG_E | (b.e_first & 0xFFFFu));
+    skc_append(b, b.e_j0, j_end, 0.0, 0.0, SKC_KIND_E, skc_exp_off(b.d) + b.e_first * 8u, 0u);
 }
 // one explicit frame at packet index j reading buffer frame a_idx (index into [16 history | previous chunk | head of current])
 SK_HD void skc_push_exp(SkcBuilder &b, uint32_t j, uint32_t a_idx, float frac) {
@@ -103,11 +119,10 @@ SK_HD uint32_t skc_build(const double *prefix, uint32_t np, const SkRun *runs, u
                          uint32_t F, uint32_t frame_bytes, const ChainProgDims &d, uint8_t *rec, uint32_t *n_seg_out, uint32_t *n_exp_out) {
     SkcBuilder b;
     b.map = reinterpret_cast<uint16_t *>(rec);
-    b.segx = reinterpret_cast<ChainSegX *>(rec + skc_segx_off(d));
-    b.segj = reinterpret_cast<ChainSegJ *>(rec + skc_segj_off(d));
+    b.segs = reinterpret_cast<ChainSeg *>(rec + skc_seg_off(d));
     b.exps = reinterpret_cast<ChainExp *>(rec + skc_exp_off(d));
     b.d = d; b.F = F; b.frame_bytes = frame_bytes;
-    b.n_seg = 0; b.n_exp = 0; b.bcur = 0; b.first_cur = 0; b.status = 0;
+    b.n_seg = 0; b.n_exp = 0; b.bcur = 0; b.first_cur = 0; b.status = 0; b.map_acc = 0;
     b.e_j0 = 0; b.e_first = 0; b.e_open = false;
     const uint32_t c = carry < F ? carry : F;          // frames beyond F belong to a later packet (backlog, reported by the caller)
     const uint32_t kd = n_out - (carry < n_out ? carry : n_out);
@@ -149,9 +164,15 @@ SK_HD uint32_t skc_build(const double *prefix, uint32_t np, const SkRun *runs, u
         if (delta > 0.0 && ke - k >= SKC_MIN_RUN) {
             skc_close_exp(b, j);
             const uint32_t hi = (uint32_t)(sk_d2bits(x0) >> 32);
-            uint32_t info = 0;
-            if ((hi - 0x3FF00000u) < (21u << 20)) info = SKC_SEG_FAST | ((20u - ((hi >> 20) - 1023u)) << 16);
-            skc_append(b, j, ke - kd, x0, delta, info);
+            uint32_t himask = SKC_KIND_SLOW, cs = 0, sh = 0;
+            if ((hi - 0x3FF00000u) < (18u << 20)) {   // positive, exponent e in 0..17, shared by the whole run
+                const uint32_t e = (hi >> 20) - 1023u;
+                const uint32_t lfb = frame_bytes == 8u ? 3u : 2u;
+                himask = 0xFFFFFFFFu << (20u - e);
+                sh = 20u - e - lfb;
+                cs = (1022u + e) << (e + lfb);
+            }
+            skc_append(b, j, ke - kd, x0, delta, himask, cs, sh);
             k = ke;
         } else {
             const uint32_t k0 = k;   // short piece: explicit frames (x0 + i * delta is exact inside a run; delta == 0 for a lone element)
@@ -166,14 +187,15 @@ SK_HD uint32_t skc_build(const double *prefix, uint32_t np, const SkRun *runs, u
         if (b.e_open) {
             // the tail simply extends an open explicit segment
             b.e_open = false;
-            skc_append(b, b.e_j0, F, 0.0, 0.0, SKC_SEG_E | (b.e_first & 0xFFFFu));
+            skc_append(b, b.e_j0, F, 0.0, 0.0, SKC_KIND_E, skc_exp_off(d) + b.e_first * 8u, 0u);
         } else {
-            skc_append(b, c, F, 0.0, 0.0, SKC_SEG_E | (b.n_exp & 0xFFFFu));
+            skc_append(b, c, F, 0.0, 0.0, SKC_KIND_E, skc_exp_off(d) + b.n_exp * 8u, 0u);
         }
         if (b.n_exp + (F - c) > d.cap_exp) b.status |= SKC_ST_OVERFLOW;
     } else {
         skc_close_exp(b, c);
     }
+    skc_flush_map(b);
     *n_seg_out = b.n_seg;
     return b.status;
 }

@@ -151,7 +151,7 @@ __device__ __forceinline__ unsigned long long chain_frame(uint32_t addr, float f
 template <int OC, int SC, int ITERS>
 __device__ __forceinline__ void chain_consume(unsigned long long (&acc)[ITERS][4], uint32_t prog, uint32_t a_hist, const ChainProgDims &pd,
                                               uint32_t F, uint32_t cw, uint32_t lane, float gain, unsigned long long one2) {
-    const uint32_t segx = prog + skc_segx_off(pd), segj = prog + skc_segj_off(pd), exps = prog + skc_exp_off(pd);
+    const uint32_t segs = prog + skc_seg_off(pd);
     const uint32_t a_chunk = a_hist + 16u * SC * 4u;   // buffer position 16: floor(idx) == 0
 #pragma unroll
     for (int it = 0; it < ITERS; ++it) {
@@ -164,30 +164,29 @@ __device__ __forceinline__ void chain_consume(unsigned long long (&acc)[ITERS][4
             uint32_t ent;
             asm volatile("ld.shared.u16 %0, [%1];" : "=r"(ent) : "r"(prog + b * 2u));
             const uint32_t s_last = ent >> 8;
+#pragma unroll 1
             for (uint32_t s = ent & 0xFFu; s <= s_last; ++s) {
-                uint32_t jj, info;
-                asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(jj), "=r"(info) : "r"(segj + s * 8u));
+                const uint32_t sa = segs + s * 32u;
+                uint32_t jj, himask, aux, sh;
+                asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4+16];" : "=r"(jj), "=r"(himask), "=r"(aux), "=r"(sh) : "r"(sa));
                 const uint32_t j0 = jj & 0xFFFFu, len = (jj >> 16) - j0;
                 const uint32_t rel_raw = j - j0;
                 const bool active = rel_raw < len;                 // unsigned: also false for j < j0
                 const uint32_t rel = min(rel_raw, len - 1u);        // inactive lanes compute a valid frame and drop it
                 uint32_t addr;
                 float frac;
-                if (info & SKC_SEG_E) {
+                if (himask == SKC_KIND_E) {
                     uint32_t aoff;
-                    asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(aoff), "=f"(frac) : "r"(exps + ((info & 0xFFFFu) + rel) * 8u));
+                    asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(aoff), "=f"(frac) : "r"(prog + aux + rel * 8u));
                     addr = a_hist + aoff;
                 } else {
                     double x0, dl;
-                    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(x0), "=d"(dl) : "r"(segx + s * 16u));
+                    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(x0), "=d"(dl) : "r"(sa));
                     const double x = __fma_rn((double)rel, dl, x0);    // exact inside a run (phase_runs.h)
-                    if (info & SKC_SEG_FAST) {
-                        const uint32_t sh = (info >> 16) & 31u;
-                        const uint32_t hi = (uint32_t)__double2hiint(x);
-                        const uint32_t fl = ((hi & 0xFFFFFu) | 0x100000u) >> sh;                     // floor(x), x in [1, 2^21)
-                        const double fl_d = __hiloint2double((int)(hi & (0xFFFFFFFFu << sh)), 0);    // the same as a double
-                        frac = __double2float_rn(__dsub_rn(x, fl_d));                                // T::coerce(idx - idx.floor())
-                        addr = a_chunk + fl * (SC * 4u);
+                    if (himask != SKC_KIND_SLOW) {
+                        const uint32_t flh = (uint32_t)__double2hiint(x) & himask;                  // floor(x) as a double = {flh, 0}
+                        frac = __double2float_rn(__dsub_rn(x, __hiloint2double((int)flh, 0)));      // T::coerce(idx - idx.floor())
+                        addr = (flh >> sh) + (a_chunk - aux);                                       // a_chunk + floor(x) * frame bytes
                     } else {
                         int32_t fl;
                         skc_split(x, &fl, &frac);
@@ -202,12 +201,16 @@ __device__ __forceinline__ void chain_consume(unsigned long long (&acc)[ITERS][4
 }
 
 // ------------------------------------------------------------------ k_phase_chain
-constexpr int PHASE_CHAIN_THREADS = 64;
+constexpr int PHASE_CHAIN_THREADS = 32;
+// thread-private phase table in shared memory; 194 words between threads: 8-byte accesses of a warp are conflict free
+constexpr uint32_t PHASE_TAB_STRIDE = SKC_TAB_PREFIX * 8u + SKC_TAB_RUNS * (uint32_t)sizeof(SkRun) + 8u;
+static_assert((PHASE_TAB_STRIDE / 4u) % 32u == 2u, "phase-table stride must keep 8-byte accesses conflict free");
 
 __global__ void __launch_bounds__(PHASE_CHAIN_THREADS) k_phase_chain(const OpHeader *__restrict__ hdr, const skgpu_chain_input *__restrict__ inputs,
                                                                      const uint8_t *__restrict__ present, const float *__restrict__ gains, SlotTables st,
                                                                      uint8_t *__restrict__ arena, const uint32_t *__restrict__ tick, uint64_t bank_stride,
                                                                      uint32_t F, uint64_t results_off, ChainDims dm, ChainRec *__restrict__ recs) {
+    __shared__ __align__(8) uint8_t s_tab[PHASE_CHAIN_THREADS * PHASE_TAB_STRIDE];
     const uint32_t i = blockIdx.x * PHASE_CHAIN_THREADS + threadIdx.x;
     if (i >= hdr->count2) return;
     const skgpu_chain_input in = inputs[i];
@@ -224,11 +227,11 @@ __global__ void __launch_bounds__(PHASE_CHAIN_THREADS) k_phase_chain(const OpHea
     uint32_t status = 0, emit = 0, prog_bytes = 0;
     if (pres) {
         // ---- rubato's phase recurrence for this chunk (thread-private table)
-        double prefix[SK_PREFIX_MAX];
-        SkRun runs[SK_RUNS_MAX];
+        double *prefix = reinterpret_cast<double *>(s_tab + threadIdx.x * PHASE_TAB_STRIDE);
+        SkRun *runs = reinterpret_cast<SkRun *>(prefix + SKC_TAB_PREFIX);
         uint32_t np, nr, ovf;
         double idx_end;
-        const uint32_t n_cur = sk_phase_table_ex(rec.last_index, rec.t_ratio, rec.end_idx, prefix, SK_PREFIX_MAX, runs, SK_RUNS_MAX, &np, &nr, &ovf, &idx_end);
+        const uint32_t n_cur = sk_phase_table_ex(rec.last_index, rec.t_ratio, rec.end_idx, prefix, SKC_TAB_PREFIX, runs, SKC_TAB_RUNS, &np, &nr, &ovf, &idx_end);
         rec.last_index = __dsub_rn(idx_end, (double)rec.chunk);   // self.last_index = idx - chunk_size as f64
         rec.chunk_count = count0 + 1u;
         if (ovf) status |= SKC_ST_OVERFLOW;

@@ -83,7 +83,7 @@ extern "C" uint64_t skc_check_stream(double ratio, uint32_t chunk, uint32_t F, u
     std::vector<uint8_t> rec[2] = {std::vector<uint8_t>(skc_prog_cap(d) + 64), std::vector<uint8_t>(skc_prog_cap(d) + 64)};
     uint32_t n_exp_rec[2] = {0, 0}, n_out_rec[2] = {0, 0};
     std::vector<double> seq_prev, seq_cur;   // the true chain of the previous / current chunk
-    SkPhaseTable T;
+    struct { double prefix[SKC_TAB_PREFIX]; SkRun runs[SKC_TAB_RUNS]; uint32_t n_prefix, n_runs, overflow; } T;
     uint64_t bad = 0;
     uint32_t packets = 0, ms = 0, me = 0, st_or = 0;
     double L = -4.0;
@@ -91,7 +91,8 @@ extern "C" uint64_t skc_check_stream(double ratio, uint32_t chunk, uint32_t F, u
     for (uint32_t c = 0; c < calls; ++c) {
         const uint32_t par_new = c & 1u, par_old = par_new ^ 1u;
         double idx_end = 0;
-        const uint32_t n_cur = sk_phase_table(L, t, end_idx, &T, &idx_end);
+        const uint32_t n_cur = sk_phase_table_ex(L, t, end_idx, T.prefix, SKC_TAB_PREFIX, T.runs, SKC_TAB_RUNS, &T.n_prefix, &T.n_runs, &T.overflow, &idx_end);
+        if (T.overflow) st_or |= SKC_ST_OVERFLOW;
         seq_cur.clear();
         for (double idx = L; idx < (double)end_idx;) { idx += t; seq_cur.push_back(idx); }
         if (seq_cur.size() != n_cur) ++bad;
@@ -108,34 +109,29 @@ extern "C" uint64_t skc_check_stream(double ratio, uint32_t chunk, uint32_t F, u
                 me = std::max(me, ne_old + (F - std::min(carry, F)));
                 // ---- execute the program like the consumers
                 const uint16_t *map = reinterpret_cast<const uint16_t *>(ro);
-                const ChainSegX *segx = reinterpret_cast<const ChainSegX *>(ro + skc_segx_off(d));
-                const ChainSegJ *segj = reinterpret_cast<const ChainSegJ *>(ro + skc_segj_off(d));
-                const ChainExp *exps = reinterpret_cast<const ChainExp *>(ro + skc_exp_off(d));
+                const ChainSeg *segs = reinterpret_cast<const ChainSeg *>(ro + skc_seg_off(d));
                 std::vector<int> hits(F, 0);
                 const uint32_t kd = n_out_rec[par_old] - carry;
                 for (uint32_t b = 0; b < d.nblk; ++b) {
                     const uint32_t ent = map[b];
                     for (uint32_t s = ent & 0xFFu; s <= (ent >> 8); ++s) {
-                        const uint32_t j0 = segj[s].jj & 0xFFFFu, len = (segj[s].jj >> 16) - j0, info = segj[s].info;
+                        const ChainSeg sg = segs[s];
+                        const uint32_t j0 = sg.jj & 0xFFFFu, len = (sg.jj >> 16) - j0;
                         for (uint32_t lane = 0; lane < 32; ++lane) {
                             if (b * 32u + lane >= F) continue;
                             const uint32_t j = b * 32u + lane, rel = j - j0;
                             if (!(rel < len)) continue;
                             uint32_t off;
                             float frac;
-                            if (info & SKC_SEG_E) {
-                                const ChainExp e = exps[(info & 0xFFFFu) + rel];
+                            if (sg.himask == SKC_KIND_E) {
+                                const ChainExp e = *reinterpret_cast<const ChainExp *>(ro + sg.aux + rel * 8u);
                                 off = e.aoff; frac = e.frac;
                             } else {
-                                const double x = __builtin_fma((double)rel, segx[s].delta, segx[s].x0);
-                                if (info & SKC_SEG_FAST) {
-                                    const uint32_t sh = (info >> 16) & 31u;
-                                    const uint64_t bits = sk_d2bits(x);
-                                    const uint32_t hi = (uint32_t)(bits >> 32);
-                                    const uint32_t fl = ((hi & 0xFFFFFu) | 0x100000u) >> sh;
-                                    const double fl_d = sk_bits2d((uint64_t)(hi & (0xFFFFFFFFu << sh)) << 32);
-                                    frac = (float)(x - fl_d);
-                                    off = (16u + fl) * fb;
+                                const double x = __builtin_fma((double)rel, sg.delta, sg.x0);
+                                if (sg.himask != SKC_KIND_SLOW) {
+                                    const uint32_t flh = (uint32_t)(sk_d2bits(x) >> 32) & sg.himask;
+                                    frac = (float)(x - sk_bits2d((uint64_t)flh << 32));
+                                    off = 16u * fb + (flh >> sg.sh) - sg.aux;
                                 } else {
                                     int32_t fl;
                                     skc_split(x, &fl, &frac);

@@ -724,11 +724,11 @@ static void prog_bounds(double t, int32_t end_idx, uint32_t N, uint32_t F, uint3
     big.cap_seg = 254u;
     big.cap_exp = 8192u;
     std::vector<uint8_t> scratch(skc_prog_cap(big));
-    SkPhaseTable T;
+    struct { double prefix[SKC_TAB_PREFIX]; SkRun runs[SKC_TAB_RUNS]; uint32_t n_prefix, n_runs, overflow; } T;
     uint32_t ms = 0, me = 0;
     auto one_chunk = [&](double last_index, uint32_t carry, double *next_index, uint32_t *next_carry) {
         double idx_end;
-        const uint32_t n_cur = sk_phase_table(last_index, t, end_idx, &T, &idx_end);
+        const uint32_t n_cur = sk_phase_table_ex(last_index, t, end_idx, T.prefix, SKC_TAB_PREFIX, T.runs, SKC_TAB_RUNS, &T.n_prefix, &T.n_runs, &T.overflow, &idx_end);
         const uint32_t avail = carry + n_cur;
         const uint32_t nc = avail >= F ? avail - F : avail;
         uint32_t ns = 0, ne = 0;
