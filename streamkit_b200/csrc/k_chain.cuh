@@ -146,55 +146,90 @@ __device__ __forceinline__ unsigned long long chain_frame(uint32_t addr, float f
     }
 }
 
-// Executes the frame program of one staged input for the blocks this warp owns (ITERS x 4 blocks of 32 frames).
+// rare run segments outside [1, 2^18) (negative positions right after a stream starts, very long chunks): real conversions.
+// Out of line so that the hot loop carries none of its instructions; returns (byte offset from buffer position 16, fraction).
+__device__ __noinline__ unsigned long long chain_split_slow(double x, uint32_t frame_bytes) {
+    int32_t fl;
+    float frac;
+    skc_split(x, &fl, &frac);
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"((uint32_t)(fl * (int32_t)frame_bytes)), "f"(frac));
+    return r;
+}
+
+// acc += v where `active` (packed f32x2, in place; see add2 for the fma-with-one form)
+__device__ __forceinline__ void acc_add2(unsigned long long &acc, unsigned long long v, unsigned long long one2, bool active) {
+    asm("{\n.reg .pred p;\nsetp.ne.u32 p, %2, 0;\n@p fma.rn.f32x2 %0, %1, %3, %0;\n}" : "+l"(acc) : "l"(v), "r"((uint32_t)active), "l"(one2));
+}
+
+// Executes the frame program of one staged input for the 128 frames (4 blocks of 32) this warp owns per iteration:
+// segment-major -- a segment is decoded once (two 16-byte loads) and applied to every owned block it touches.
 //   prog    shared-memory address of the program record; a_hist: of the 16-frame history (buffer position 0)
 template <int OC, int SC, int ITERS>
 __device__ __forceinline__ void chain_consume(unsigned long long (&acc)[ITERS][4], uint32_t prog, uint32_t a_hist, const ChainProgDims &pd,
-                                              uint32_t F, uint32_t cw, uint32_t lane, float gain, unsigned long long one2) {
+                                              uint32_t cw, uint32_t lane, float gain, unsigned long long one2) {
     const uint32_t segs = prog + skc_seg_off(pd);
     const uint32_t a_chunk = a_hist + 16u * SC * 4u;   // buffer position 16: floor(idx) == 0
 #pragma unroll
     for (int it = 0; it < ITERS; ++it) {
-#pragma unroll
-        for (int f = 0; f < 4; ++f) {
-            const uint32_t b = ((uint32_t)it * 8u + cw) * 4u + (uint32_t)f;   // warp-uniform block index
-            const uint32_t jf = b * 32u;
-            if (jf >= F) continue;
-            const uint32_t j = min(jf + lane, F - 1u);   // lanes past the packet recompute its last frame (never stored)
-            uint32_t ent;
-            asm volatile("ld.shared.u16 %0, [%1];" : "=r"(ent) : "r"(prog + b * 2u));
-            const uint32_t s_last = ent >> 8;
+        const uint32_t b0 = ((uint32_t)it * 8u + cw) * 4u;   // warp-uniform: first owned block
+        if (b0 >= pd.nblk) continue;
+        uint32_t e_first, e_last;
+        asm volatile("ld.shared.u16 %0, [%1];" : "=r"(e_first) : "r"(prog + b0 * 2u));
+        asm volatile("ld.shared.u16 %0, [%1];" : "=r"(e_last) : "r"(prog + min(b0 + 3u, pd.nblk - 1u) * 2u));
+        const uint32_t s_last = e_last >> 8;
+        const uint32_t jb = b0 * 32u, jw = jb + lane;
 #pragma unroll 1
-            for (uint32_t s = ent & 0xFFu; s <= s_last; ++s) {
-                const uint32_t sa = segs + s * 32u;
-                uint32_t jj, himask, aux, sh;
-                asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4+16];" : "=r"(jj), "=r"(himask), "=r"(aux), "=r"(sh) : "r"(sa));
-                const uint32_t j0 = jj & 0xFFFFu, len = (jj >> 16) - j0;
-                const uint32_t rel_raw = j - j0;
-                const bool active = rel_raw < len;                 // unsigned: also false for j < j0
-                const uint32_t rel = min(rel_raw, len - 1u);        // inactive lanes compute a valid frame and drop it
-                uint32_t addr;
-                float frac;
-                if (himask == SKC_KIND_E) {
-                    uint32_t aoff;
-                    asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(aoff), "=f"(frac) : "r"(prog + aux + rel * 8u));
-                    addr = a_hist + aoff;
-                } else {
-                    double x0, dl;
-                    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(x0), "=d"(dl) : "r"(sa));
-                    const double x = __fma_rn((double)rel, dl, x0);    // exact inside a run (phase_runs.h)
-                    if (himask != SKC_KIND_SLOW) {
-                        const uint32_t flh = (uint32_t)__double2hiint(x) & himask;                  // floor(x) as a double = {flh, 0}
-                        frac = __double2float_rn(__dsub_rn(x, __hiloint2double((int)flh, 0)));      // T::coerce(idx - idx.floor())
-                        addr = (flh >> sh) + (a_chunk - aux);                                       // a_chunk + floor(x) * frame bytes
-                    } else {
-                        int32_t fl;
-                        skc_split(x, &fl, &frac);
-                        addr = a_chunk + (uint32_t)(fl * (int32_t)(SC * 4));
+        for (uint32_t s = e_first & 0xFFu; s <= s_last; ++s) {
+            const uint32_t sa = segs + s * 32u;
+            uint32_t jj, himask, aux, sh;
+            asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4+16];" : "=r"(jj), "=r"(himask), "=r"(aux), "=r"(sh) : "r"(sa));
+            const uint32_t j0 = jj & 0xFFFFu, j1 = jj >> 16, lenm1 = j1 - j0 - 1u;
+            const uint32_t relw = jw - j0;   // frame f of this lane is element relw + 32 f of the segment (lanes outside are dropped)
+            if (himask > SKC_KIND_SLOW) {
+                // ---- FAST run segment (almost everything)
+                double x0, dl;
+                asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(x0), "=d"(dl) : "r"(sa));
+                const uint32_t k_chunk = a_chunk - aux;
+#pragma unroll
+                for (int f = 0; f < 4; ++f) {
+                    const uint32_t jf = jb + (uint32_t)f * 32u;
+                    if (jf < j1 && jf + 32u > j0) {                     // warp-uniform: block f touches this segment
+                        const uint32_t rel_raw = relw + (uint32_t)f * 32u;
+                        const uint32_t rel = min(rel_raw, lenm1);       // lanes outside compute a valid frame and drop it
+                        const double x = __fma_rn((double)rel, dl, x0);    // exact inside a run (phase_runs.h)
+                        const uint32_t flh = (uint32_t)__double2hiint(x) & himask;                       // floor(x) as a double = {flh, 0}
+                        const float frac = __double2float_rn(__dsub_rn(x, __hiloint2double((int)flh, 0)));   // T::coerce(idx - idx.floor())
+                        const unsigned long long v = chain_frame<OC, SC>((flh >> sh) + k_chunk, frac, gain, one2);   // a_chunk + floor(x) * frame bytes
+                        acc_add2(acc[it][f], v, one2, rel_raw <= lenm1);
                     }
                 }
-                const unsigned long long v = chain_frame<OC, SC>(addr, frac, gain, one2);
-                if (active) acc[it][f] = add2(acc[it][f], v, one2);
+            } else {
+                // ---- explicit frames / slow run segments
+                double x0 = 0.0, dl = 0.0;
+                if (himask == SKC_KIND_SLOW) asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(x0), "=d"(dl) : "r"(sa));
+#pragma unroll
+                for (int f = 0; f < 4; ++f) {
+                    const uint32_t jf = jb + (uint32_t)f * 32u;
+                    if (jf < j1 && jf + 32u > j0) {
+                        const uint32_t rel_raw = relw + (uint32_t)f * 32u;
+                        const uint32_t rel = min(rel_raw, lenm1);
+                        uint32_t addr;
+                        float frac;
+                        if (himask == SKC_KIND_E) {
+                            uint32_t aoff;
+                            asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(aoff), "=f"(frac) : "r"(prog + aux + rel * 8u));
+                            addr = a_hist + aoff;
+                        } else {
+                            const unsigned long long pf = chain_split_slow(__fma_rn((double)rel, dl, x0), SC * 4u);
+                            uint32_t off;
+                            asm("mov.b64 {%0, %1}, %2;" : "=r"(off), "=f"(frac) : "l"(pf));
+                            addr = a_chunk + off;
+                        }
+                        const unsigned long long v = chain_frame<OC, SC>(addr, frac, gain, one2);
+                        acc_add2(acc[it][f], v, one2, rel_raw <= lenm1);
+                    }
+                }
             }
         }
     }
@@ -500,8 +535,8 @@ __global__ void __launch_bounds__(CH_THREADS, 4) k_chain(const OpHeader *__restr
         for (uint32_t q = 0; q < nb; ++q) {
             const ChainCons c = S->cons[q];
             const uint32_t prog = sm + q * in_bytes;
-            if (c.sc == 2u) chain_consume<OC, 2, ITERS>(acc, prog, prog + prog_cap, dm.prog, F, cw, lane, c.gain, one2);
-            else chain_consume<OC, 1, ITERS>(acc, prog, prog + prog_cap + SK_SIDE_HIST - 64u, dm.prog, F, cw, lane, c.gain, one2);
+            if (c.sc == 2u) chain_consume<OC, 2, ITERS>(acc, prog, prog + prog_cap, dm.prog, cw, lane, c.gain, one2);
+            else chain_consume<OC, 1, ITERS>(acc, prog, prog + prog_cap + SK_SIDE_HIST - 64u, dm.prog, cw, lane, c.gain, one2);
         }
         if (hd.z != 0) {
             // ---- epilogue: master gain, then clip + s16 pack (or f32); a warp stores 32 consecutive frames per instruction
