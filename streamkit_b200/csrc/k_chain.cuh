@@ -42,38 +42,40 @@ constexpr int CH_MAX_STAGES = 4;                  // pipeline depth is a launch 
 constexpr int CH_HEAD = 32;                       // frames of the CURRENT chunk staged behind the previous one
 constexpr int CH_MAX_INPUTS = 64;                 // inputs per session
 constexpr int CH_MAX_KB = 4;                      // inputs staged per batch
-constexpr uint32_t CH_HIST_OFF = SK_SIDE_STRIDE - SK_SIDE_HIST;   // history field at the end of every side record
+constexpr uint32_t CH_PROG_MAX = SK_SIDE_STRIDE - SK_SIDE_HIST;   // side record = [frame program (prog_cap bytes) | 128-byte history field]
 
 struct __align__(8) ChainCons {   // what a consumer needs per input
     float gain;             // 1.0 when the input has no audio::gain in front of the mixer (x * 1.0 == x)
     uint32_t sc;            // source channels
 };
 
-// per-input record written by k_phase_chain every tick, consumed by k_chain's producer (64 bytes, one per chain input)
-constexpr uint32_t CR_EMIT = 1u, CR_UNIQUE = 2u, CR_PAR_PREV = 8u;
+// per-input record written by k_phase_chain every tick, consumed by k_chain's producer (64 bytes, one per chain input):
+// every address the producer needs is final, so staging an input is three bulk copies and two small stores
+constexpr uint32_t CR_EMIT = 1u, CR_UNIQUE = 2u, CR_UNALIGNED = 4u;
 struct __align__(16) ChainRec {
     ChainCons cons;
-    const float *prev_g;    // previous chunk (other input bank)
-    const float *cur_g;     // current chunk
-    uint32_t slot;
-    uint32_t chunk_bytes;   // N * channels * 4
-    uint32_t head_bytes;    // staged frames of the current chunk, bytes
-    uint32_t prog_bytes;    // used bytes of the frame program (multiple of 16)
-    uint32_t flags;         // CR_*
-    uint32_t N;
-    uint32_t pad[4];
+    const uint8_t *prog_src;  // side record of the packet: [frame program (prog_cap bytes) | 128-byte history field]
+    const float *prev_g;      // previous chunk (other input bank)
+    const float *cur_g;       // current chunk
+    float *hist_dst;          // where the last 16 frames of the previous chunk go (history field of the current chunk's record)
+    uint32_t chunk_bytes;     // N * channels * 4
+    uint32_t head_bytes;      // staged frames of the current chunk, bytes
+    uint32_t flags;           // CR_*
+    uint32_t tail_off;        // (N - 16) * channels: float offset of those 16 frames inside the chunk
+    uint32_t pad[2];
 };
 static_assert(sizeof(ChainRec) == 64, "ChainRec is one 64-byte record");
 
-struct ChainTail {          // per staged input: what the end-of-batch history update needs
-    uint8_t *side_cur;      // side record of the current chunk (its history field is written here)
-    uint32_t N, ch;
+struct __align__(16) ChainTail {   // per staged input: what the end-of-batch history update needs
+    float *hist_dst;
+    uint32_t tail_off, n;   // n = 16 * channels floats
 };
 
 struct __align__(16) ChainStage {   // header of one pipeline stage (shared memory)
     uint32_t nb;            // inputs in this batch           } one 16-byte load
     uint32_t first, last;   // first / last batch of the session
-    uint32_t has_base;      // the first input of the first batch is the base frame (mixer.rs:960-972)
+    uint32_t has_base;      // bit0: the first input of the first batch is the base frame (mixer.rs:960-972);
+                            // bits 8-10: block-ownership rotation of this session (load balance, see the consumers)
     uint64_t out_off;
     float master_gain;      // 1.0 when the session has no master audio::gain
     uint32_t flags;
@@ -259,7 +261,7 @@ __global__ void __launch_bounds__(PHASE_CHAIN_THREADS) k_phase_chain(const OpHea
     const uint32_t count0 = rec.chunk_count;
     const uint32_t par_new = count0 & 1u, par_old = par_new ^ 1u;   // record of the chunk processed now / of the previous chunk
     const uint32_t carry = rec.carry;
-    uint32_t status = 0, emit = 0, prog_bytes = 0;
+    uint32_t status = 0, emit = 0;
     if (pres) {
         // ---- rubato's phase recurrence for this chunk (thread-private table)
         double *prefix = reinterpret_cast<double *>(s_tab + threadIdx.x * PHASE_TAB_STRIDE);
@@ -282,7 +284,6 @@ __global__ void __launch_bounds__(PHASE_CHAIN_THREADS) k_phase_chain(const OpHea
             const uint32_t ne_old = rec.n_prefix[par_old];
             status |= skc_fill_tail(prefix, np, runs, nr, rec.t_ratio, n_cur, carry, F, N, head, fb,
                                     reinterpret_cast<ChainExp *>(rec_old + skc_exp_off(dm.prog)) + ne_old, dm.prog.cap_exp - min(ne_old, dm.prog.cap_exp));
-            prog_bytes = (skc_exp_off(dm.prog) + (ne_old + (F - min(carry, F))) * 8u + 15u) & ~15u;
             emit = (status & (SKC_ST_OVERFLOW | SKC_ST_UNSUPPORTED)) ? 0u : 1u;
         }
         if (new_carry > n_cur) status |= 1u;                              // backlog: a second packet is pending
@@ -307,22 +308,23 @@ __global__ void __launch_bounds__(PHASE_CHAIN_THREADS) k_phase_chain(const OpHea
     // a present input that emits nothing still retires its previous chunk: the history before the current chunk
     // (= last 16 frames of the previous one) goes into the current chunk's side record. Emitting inputs get it from
     // k_chain's consumers, which have the previous chunk in shared memory anyway.
+    const uint32_t prog_cap = skc_prog_cap(dm.prog);
+    float *hist_dst = reinterpret_cast<float *>(slot_side(st, slot, par_new) + prog_cap + SK_SIDE_HIST) - 16u * ch;
     if (pres && !emit && count0 >= 1u) {
-        float *h = reinterpret_cast<float *>(slot_side(st, slot, par_new) + CH_HIST_OFF + SK_SIDE_HIST) - 16u * ch;
-        for (uint32_t e = 0; e < 16u * ch; ++e) h[e] = prev_g[(size_t)(N - 16u) * ch + e];
+        for (uint32_t e = 0; e < 16u * ch; ++e) hist_dst[e] = prev_g[(size_t)(N - 16u) * ch + e];
     }
     ChainRec r;
     r.cons.gain = in.gain_idx != SKGPU_NO_GAIN ? gains[in.gain_idx] : 1.0f;
     r.cons.sc = ch;
+    r.prog_src = slot_side(st, slot, par_old);
     r.prev_g = prev_g;
     r.cur_g = cur_g;
-    r.slot = slot;
+    r.hist_dst = hist_dst;
     r.chunk_bytes = N * fb;
     r.head_bytes = head * fb;
-    r.prog_bytes = prog_bytes;
-    r.flags = (emit ? CR_EMIT : 0u) | ((in.flags & SKGPU_MIX_IN_UNIQUE) ? CR_UNIQUE : 0u) | (par_old ? CR_PAR_PREV : 0u);
-    r.N = N;
-    r.pad[0] = r.pad[1] = r.pad[2] = r.pad[3] = 0u;
+    r.flags = (emit ? CR_EMIT : 0u) | ((in.flags & SKGPU_MIX_IN_UNIQUE) ? CR_UNIQUE : 0u) | ((((N * fb) | (head * fb)) & 15u) ? CR_UNALIGNED : 0u);
+    r.tail_off = (N - 16u) * ch;
+    r.pad[0] = r.pad[1] = 0u;
     recs[i] = r;
 }
 
@@ -370,25 +372,21 @@ __global__ void __launch_bounds__(CH_THREADS, 4) k_chain(const OpHeader *__restr
                 const uint8_t *src = reinterpret_cast<const uint8_t *>(recs + g.first_input + lane);
                 uint8_t *dst = reinterpret_cast<uint8_t *>(&pf_rec[n & 1u][lane]);
 #pragma unroll
-                for (int w = 0; w < 3; ++w) cp_async16(dst + w * 16, src + w * 16);   // the last 16 bytes are padding
+                for (int w = 0; w < 4; ++w) cp_async16(dst + w * 16, src + w * 16);
             }
         };
-        // one input: copy its consumer record into the stage and issue its bulk copies; returns the bytes the barrier must expect
+        // one input (general path): copy its consumer record into the stage and issue its bulk copies; returns the bytes the barrier must expect
         auto stage_input = [&](const ChainRec &r, uint32_t q, ChainStage *S, uint8_t *sm, uint64_t *bar) -> uint32_t {
             S->cons[q] = r.cons;
-            const uint32_t par_prev = (r.flags & CR_PAR_PREV) ? 1u : 0u;
             ChainTail tl;
-            tl.side_cur = slot_side(st, r.slot, par_prev ^ 1u);
-            tl.N = r.N; tl.ch = r.cons.sc;
+            tl.hist_dst = r.hist_dst; tl.tail_off = r.tail_off; tl.n = 16u * r.cons.sc;
             S->tail[q] = tl;
             uint8_t *slot_sm = sm + (size_t)q * in_bytes;
             uint8_t *chunk_sm = slot_sm + prog_cap + SK_SIDE_HIST;
-            const uint8_t *side_prev = slot_side(st, r.slot, par_prev);
             const uint32_t cb = r.chunk_bytes, hb = r.head_bytes;
-            uint32_t bytes = r.prog_bytes + SK_SIDE_HIST;
-            tma_bulk_g2s(slot_sm, side_prev, r.prog_bytes, bar);                                  // frame program of the packet
-            tma_bulk_g2s(slot_sm + prog_cap, side_prev + CH_HIST_OFF, SK_SIDE_HIST, bar);         // 16 frames before the previous chunk
-            if (!(cb & 15u) && !(hb & 15u)) {
+            uint32_t bytes = prog_cap + SK_SIDE_HIST;
+            tma_bulk_g2s(slot_sm, r.prog_src, prog_cap + SK_SIDE_HIST, bar);   // frame program + the 16 frames before the previous chunk
+            if (!(r.flags & CR_UNALIGNED)) {
                 tma_bulk_g2s(chunk_sm, r.prev_g, cb, bar);
                 tma_bulk_g2s(chunk_sm + cb, r.cur_g, hb, bar);
                 bytes += cb + hb;
@@ -399,11 +397,11 @@ __global__ void __launch_bounds__(CH_THREADS, 4) k_chain(const OpHeader *__restr
             }
             return bytes;
         };
-        auto stage_header = [&](ChainStage *S, const skgpu_chain_group &grp, uint32_t nb, bool first, bool last, uint32_t has_base) {
+        auto stage_header = [&](ChainStage *S, const skgpu_chain_group &grp, uint32_t nb, bool first, bool last, uint32_t has_base, uint32_t rot) {
             S->nb = nb;
             S->first = first;
             S->last = last;
-            S->has_base = has_base;
+            S->has_base = has_base | (rot << 8);
             S->out_off = grp.out_off;
             S->master_gain = grp.gain_idx != SKGPU_NO_GAIN ? gains[grp.gain_idx] : 1.0f;
             S->flags = grp.flags;
@@ -430,9 +428,10 @@ __global__ void __launch_bounds__(CH_THREADS, 4) k_chain(const OpHeader *__restr
             const uint32_t emit_mask = __ballot_sync(0xffffffffu, emit);
             const uint32_t elig_mask = __ballot_sync(0xffffffffu, elig);
             const uint32_t uniq_mask = __ballot_sync(0xffffffffu, elig && (r.flags & CR_UNIQUE));
+            const uint32_t unal_mask = __ballot_sync(0xffffffffu, emit && (r.flags & CR_UNALIGNED));
             uint32_t m = __popc(emit_mask);
-            if (K <= 32u && m <= kb) {
-                // max_by_key((unique, idx)): the last unique full-shape frame, else the last full-shape frame
+            if (K <= 32u && m <= kb && unal_mask == 0u) {
+                // ---- common path. max_by_key((unique, idx)): the last unique full-shape frame, else the last full-shape frame
                 const int base_lane = uniq_mask ? 31 - __clz(uniq_mask) : (elig_mask ? 31 - __clz(elig_mask) : -1);
                 const uint32_t rank = __popc(emit_mask & ((1u << lane) - 1u));
                 uint32_t pos = rank;
@@ -443,13 +442,29 @@ __global__ void __launch_bounds__(CH_THREADS, 4) k_chain(const OpHeader *__restr
                 }
                 mbar_wait(&bar_empty[stage], ephase);
                 ChainStage *S = &s_stage[stage];
-                uint8_t *sm = smem_raw + (size_t)stage * stage_bytes;
-                uint32_t bytes = emit ? stage_input(r, pos, S, sm, &bar_full[stage]) : 0u;
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) bytes += __shfl_xor_sync(0xffffffffu, bytes, o);
-                if (lane == 0) stage_header(S, grp, m, true, true, base_lane >= 0 ? 1u : 0u);
+                if (emit) {   // the lanes fill the consumer-side records of their inputs in parallel
+                    S->cons[pos] = r.cons;
+                    ChainTail tl;
+                    tl.hist_dst = r.hist_dst; tl.tail_off = r.tail_off; tl.n = 16u * r.cons.sc;
+                    S->tail[pos] = tl;
+                    s_order[pos] = (uint8_t)lane;
+                }
                 __syncwarp();
-                if (lane == 0) mbar_expect_tx(&bar_full[stage], bytes);   // arrive: the lanes' smem writes are ordered before it
+                if (lane == 0) {
+                    stage_header(S, grp, m, true, true, base_lane >= 0 ? 1u : 0u, n & 7u);
+                    // one thread issues the 3 bulk copies of every input, in summation order, from the prefetched records
+                    uint8_t *dst = smem_raw + (size_t)stage * stage_bytes;
+                    uint32_t bytes = 0;
+                    for (uint32_t q = 0; q < m; ++q, dst += in_bytes) {
+                        const ChainRec *rr = &pf_rec[n & 1u][s_order[q]];
+                        const uint32_t cb = rr->chunk_bytes, hb = rr->head_bytes;
+                        tma_bulk_g2s(dst, rr->prog_src, prog_cap + SK_SIDE_HIST, &bar_full[stage]);
+                        tma_bulk_g2s(dst + prog_cap + SK_SIDE_HIST, rr->prev_g, cb, &bar_full[stage]);
+                        tma_bulk_g2s(dst + prog_cap + SK_SIDE_HIST + cb, rr->cur_g, hb, &bar_full[stage]);
+                        bytes += prog_cap + SK_SIDE_HIST + cb + hb;
+                    }
+                    mbar_expect_tx(&bar_full[stage], bytes);   // arrive: the smem writes above are ordered before it
+                }
                 if (++stage == nstages) { stage = 0; ephase ^= 1u; }
             } else {
                 // ---- general path: more emitting inputs than fit one batch, or more than 32 inputs: serial order, several batches
@@ -493,7 +508,7 @@ __global__ void __launch_bounds__(CH_THREADS, 4) k_chain(const OpHeader *__restr
                     }
 #pragma unroll
                     for (int o = 16; o > 0; o >>= 1) bytes += __shfl_xor_sync(0xffffffffu, bytes, o);
-                    if (lane == 0) stage_header(S, grp, nb, b == 0u, b + 1u == n_batches, has_base);
+                    if (lane == 0) stage_header(S, grp, nb, b == 0u, b + 1u == n_batches, has_base, n & 7u);
                     __syncwarp();
                     if (lane == 0) mbar_expect_tx(&bar_full[stage], bytes);
                     if (++stage == nstages) { stage = 0; ephase ^= 1u; }
@@ -512,7 +527,10 @@ __global__ void __launch_bounds__(CH_THREADS, 4) k_chain(const OpHeader *__restr
     }
 
     // =================================================================== consumer warps
-    const uint32_t cw = warp - 1u, ct = threadIdx.x - 32u;
+    // Block ownership ROTATES from session to session: the first 128 frames of a packet hold most of the program's
+    // segments (the binades below 128) and the last ones its explicit tail, so a fixed assignment would make the same
+    // warp the slowest of every session while a stage is only released when all eight are done.
+    const uint32_t ct = threadIdx.x - 32u;
     unsigned long long acc[ITERS][4];   // (left, right) packed f32x2 per owned frame (mono: low half)
     const unsigned long long one2 = pack2(dm.one, dm.one);   // 1.0f the compiler cannot see (add2)
     uint32_t stage = 0, fphase = 0;
@@ -523,10 +541,11 @@ __global__ void __launch_bounds__(CH_THREADS, 4) k_chain(const OpHeader *__restr
         if (S->stop) break;
         const uint32_t sm = smem_u32(smem_raw) + stage * stage_bytes;
         const uint32_t nb = (dm.debug & 1u) ? 0u : hd.x;
+        const uint32_t cw = (warp - 1u + (hd.w >> 8)) & 7u;   // this session's block group of the warp
         if (hd.y != 0) {
             // the base frame IS the accumulator (mixer.rs:969-972): start from -0.0, the additive identity of every f32
             // (-0.0 + v == v bit for bit, also for v == -0.0); without a base frame the mix starts from vec![0.0; n]
-            const unsigned long long init = hd.w != 0 ? 0x8000000080000000ull : 0ull;
+            const unsigned long long init = (hd.w & 1u) != 0 ? 0x8000000080000000ull : 0ull;
 #pragma unroll
             for (int it = 0; it < ITERS; ++it)
 #pragma unroll
@@ -566,10 +585,9 @@ __global__ void __launch_bounds__(CH_THREADS, 4) k_chain(const OpHeader *__restr
         if (ct < 16u * 2u) {
             for (uint32_t q = 0; q < hd.x; ++q) {
                 const ChainTail tl = S->tail[q];
-                if (ct < 16u * tl.ch) {
+                if (ct < tl.n) {
                     const float *chunk_f = reinterpret_cast<const float *>(smem_raw + (size_t)stage * stage_bytes + (size_t)q * in_bytes + prog_cap + SK_SIDE_HIST);
-                    float *h = reinterpret_cast<float *>(tl.side_cur + CH_HIST_OFF + SK_SIDE_HIST) - 16u * tl.ch;
-                    h[ct] = chunk_f[(size_t)(tl.N - 16u) * tl.ch + ct];
+                    tl.hist_dst[ct] = chunk_f[tl.tail_off + ct];
                 }
             }
         }

@@ -806,7 +806,7 @@ static skgpu_rc validate_chain(const skgpu_plan *p, const skgpu_chain_group *g, 
         d.map_bytes = (d.nblk * 2u + 15u) & ~15u;
         d.cap_seg = *cap_seg;
         d.cap_exp = *cap_exp;
-        if (*cap_seg > 254u || skc_prog_cap(d) > CH_HIST_OFF)
+        if (*cap_seg > 254u || skc_prog_cap(d) > CH_PROG_MAX)
             return fail(SKGPU_ERR_INVALID, "chain op: frame program of %u segments + %u explicit frames does not fit a stream's side record (use the unfused ops)", *cap_seg, *cap_exp);
     }
     return SKGPU_OK;
