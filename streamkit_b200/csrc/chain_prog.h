@@ -19,8 +19,10 @@
 
 #include "phase_runs.h"
 
+#ifndef SKC_TAB_PREFIX
 #define SKC_TAB_PREFIX 24u        // capacities of the thread-private phase table the program is built from (host and
 #define SKC_TAB_RUNS 24u          // device must use the same ones: they shape the table, hence the program)
+#endif
 #define SKC_MIN_RUN 8u            // shorter run pieces are stored explicitly (one pass of the consumer costs ~25 instructions)
 #define SKC_ST_OVERFLOW 2u        // status bit1: a table of the record overflowed
 #define SKC_ST_UNSUPPORTED 4u     // status bit2: the packet needs frames the kernel does not stage
@@ -31,7 +33,7 @@
 // One segment = two 16-byte shared-memory loads in the consumer. FAST run segments lie in one binade [2^e, 2^(e+1)),
 // 0 <= e <= 17, so with hi = high word of x:  floor(x) as a double = {hi & himask, 0}  and the byte offset of buffer
 // frame floor(x) is ((hi & himask) >> sh) - cs   (sh = 20 - e - log2(frame_bytes), cs = (1022 + e) << (20 - sh)).
-struct ChainSeg {
+struct alignas(16) ChainSeg {
     double x0, delta;   // run: x_j = fma((double)(j - j0), delta, x0)
     uint32_t jj;        // j0 | j1 << 16
     uint32_t himask;    // SKC_KIND_E, SKC_KIND_SLOW, or the FAST mask
@@ -39,6 +41,9 @@ struct ChainSeg {
     uint32_t sh;        // FAST: shift
 };
 struct ChainExp { uint32_t aoff; float frac; };  // byte offset of frame y0 from the start of the 16-frame history
+struct alignas(16) ChainExp2 { ChainExp a, b; };  // the builder stores explicit entries in aligned pairs: one thread per stream
+                                                   // writes its own record, so every store is a scattered request and wide
+                                                   // stores halve their number (k_phase_chain is bound by them)
 
 struct ChainProgDims {
     uint32_t nblk;       // ceil(F / 32)
@@ -63,6 +68,12 @@ SK_HD void skc_split(double x, int32_t *fl, float *frac) {
 #endif
 }
 
+SK_HD void skc_store16(uint8_t *dst, uint64_t lo, uint64_t hi) {
+    struct alignas(16) U2 { uint64_t lo, hi; } v;
+    v.lo = lo; v.hi = hi;
+    *reinterpret_cast<U2 *>(dst) = v;
+}
+
 struct SkcBuilder {   // appends segments in increasing j and completes the block map on the fly
     uint16_t *map;
     ChainSeg *segs;
@@ -70,7 +81,8 @@ struct SkcBuilder {   // appends segments in increasing j and completes the bloc
     ChainProgDims d;
     uint32_t F, frame_bytes;
     uint32_t n_seg, n_exp, bcur, first_cur, status;
-    uint64_t map_acc;       // four map entries are collected and stored as one 8-byte word
+    uint64_t map_lo, map_hi; // eight map entries are collected and stored as one 16-byte word
+    ChainExp exp_pend;       // first entry of an aligned pair of explicit entries (stored with the second one)
     // the open explicit segment (consecutive explicit frames share one segment)
     uint32_t e_j0, e_first;
     bool e_open;
@@ -87,16 +99,18 @@ SK_HD void skc_append(SkcBuilder &b, uint32_t j0, uint32_t j1, double x0, double
         const uint32_t be = (bs + 31u < b.F - 1u) ? bs + 31u : b.F - 1u;
         if (bs >= j0 && bs < j1) b.first_cur = s;
         if (be >= j1) break;
-        b.map_acc |= (uint64_t)(b.first_cur | (s << 8)) << (16u * (b.bcur & 3u));
-        if ((b.bcur & 3u) == 3u) {
-            reinterpret_cast<uint64_t *>(b.map)[b.bcur >> 2] = b.map_acc;
-            b.map_acc = 0;
+        const uint64_t ent = (uint64_t)(b.first_cur | (s << 8)) << (16u * (b.bcur & 3u));
+        if (b.bcur & 4u) b.map_hi |= ent; else b.map_lo |= ent;
+        if ((b.bcur & 7u) == 7u) {
+            skc_store16(reinterpret_cast<uint8_t *>(b.map) + (b.bcur >> 3) * 16u, b.map_lo, b.map_hi);
+            b.map_lo = 0; b.map_hi = 0;
         }
         ++b.bcur;
     }
 }
 SK_HD void skc_flush_map(SkcBuilder &b) {
-    if (b.bcur & 3u) reinterpret_cast<uint64_t *>(b.map)[b.bcur >> 2] = b.map_acc;
+    if (b.bcur & 7u) skc_store16(reinterpret_cast<uint8_t *>(b.map) + (b.bcur >> 3) * 16u, b.map_lo, b.map_hi);
+    if (b.n_exp & 1u) b.exps[b.n_exp - 1u] = b.exp_pend;   // an unpaired last explicit entry
 }
 SK_HD void skc_close_exp(SkcBuilder &b, uint32_t j_end) {
     if (!b.e_open) return;
@@ -108,116 +122,136 @@ SK_HD void skc_push_exp(SkcBuilder &b, uint32_t j, uint32_t a_idx, float frac) {
     if (b.n_exp >= b.d.cap_exp) { b.status |= SKC_ST_OVERFLOW; return; }
     if (!b.e_open) { b.e_open = true; b.e_j0 = j; b.e_first = b.n_exp; }
     ChainExp e; e.aoff = a_idx * b.frame_bytes; e.frac = frac;
-    b.exps[b.n_exp++] = e;
-}
-
-// PART 1 (written when chunk n is processed, consumed one tick later): the `carry` frames chunk n contributes to the
-// NEXT packet, i.e. chunk outputs k in [n_out - carry, n_out) -> packet frames j = k - (n_out - carry); then the
-// (still empty) explicit tail segment [carry, F) whose entries skc_fill_tail() appends when chunk n + 1 is known.
-// Returns status bits; *n_seg_out / *n_exp_out receive the table sizes (n_exp WITHOUT the tail).
-SK_HD uint32_t skc_build(const double *prefix, uint32_t np, const SkRun *runs, uint32_t nr, double t, uint32_t n_out, uint32_t carry,
-                         uint32_t F, uint32_t frame_bytes, const ChainProgDims &d, uint8_t *rec, uint32_t *n_seg_out, uint32_t *n_exp_out) {
-    SkcBuilder b;
-    b.map = reinterpret_cast<uint16_t *>(rec);
-    b.segs = reinterpret_cast<ChainSeg *>(rec + skc_seg_off(d));
-    b.exps = reinterpret_cast<ChainExp *>(rec + skc_exp_off(d));
-    b.d = d; b.F = F; b.frame_bytes = frame_bytes;
-    b.n_seg = 0; b.n_exp = 0; b.bcur = 0; b.first_cur = 0; b.status = 0; b.map_acc = 0;
-    b.e_j0 = 0; b.e_first = 0; b.e_open = false;
-    const uint32_t c = carry < F ? carry : F;          // frames beyond F belong to a later packet (backlog, reported by the caller)
-    const uint32_t kd = n_out - (carry < n_out ? carry : n_out);
-    uint32_t k = kd, r = 0;
-    const uint32_t k_end = kd + c;
-    while (k < k_end) {
-        const uint32_t j = k - kd;
-        int32_t fl;
-        float frac;
-        if (k < np || nr == 0u) {
-            skc_split(k < np ? prefix[k] : 0.0, &fl, &frac);
-            skc_push_exp(b, j, (uint32_t)(fl + 16), frac);
-            ++k;
-            continue;
-        }
-        while (r + 1u < nr && runs[r + 1u].k_a <= k) ++r;
-        const SkRun rn = runs[r];
-        double x0, delta = rn.delta;
-        uint32_t ke;
-        if (k < rn.k_e) {
-            x0 = sk_dfma((double)(k - rn.k_a), rn.delta, rn.x_a);
-            ke = rn.k_e;
-        } else {
-            // gap element: one true addition after the run's last member. It usually lies on the NEXT run's lattice
-            // (x_a' - delta' exactly, same binade): then it becomes the first member of that run's segment.
-            x0 = sk_dadd(sk_dfma((double)(rn.k_e - 1u - rn.k_a), rn.delta, rn.x_a), t);
-            ke = k + 1u;
-            delta = 0.0;
-            if (r + 1u < nr) {
-                const SkRun nx = runs[r + 1u];
-                if (nx.k_a == k + 1u && nx.delta > 0.0 && (sk_d2bits(x0) >> 52) == (sk_d2bits(nx.x_a) >> 52) &&
-                    sk_dfma(-1.0, nx.delta, nx.x_a) == x0) {
-                    delta = nx.delta;
-                    ke = nx.k_e;
-                }
-            }
-        }
-        if (ke > k_end) ke = k_end;
-        if (delta > 0.0 && ke - k >= SKC_MIN_RUN) {
-            skc_close_exp(b, j);
-            const uint32_t hi = (uint32_t)(sk_d2bits(x0) >> 32);
-            uint32_t himask = SKC_KIND_SLOW, cs = 0, sh = 0;
-            if ((hi - 0x3FF00000u) < (18u << 20)) {   // positive, exponent e in 0..17, shared by the whole run
-                const uint32_t e = (hi >> 20) - 1023u;
-                const uint32_t lfb = frame_bytes == 8u ? 3u : 2u;
-                himask = 0xFFFFFFFFu << (20u - e);
-                sh = 20u - e - lfb;
-                cs = (1022u + e) << (e + lfb);
-            }
-            skc_append(b, j, ke - kd, x0, delta, himask, cs, sh);
-            k = ke;
-        } else {
-            const uint32_t k0 = k;   // short piece: explicit frames (x0 + i * delta is exact inside a run; delta == 0 for a lone element)
-            for (; k < ke; ++k) {
-                skc_split(sk_dfma((double)(k - k0), delta, x0), &fl, &frac);
-                skc_push_exp(b, k - kd, (uint32_t)(fl + 16), frac);
-            }
-        }
-    }
-    *n_exp_out = b.n_exp;
-    if (c < F) {   // the tail: frames produced by the next chunk; entries follow the explicit entries of part 1
-        if (b.e_open) {
-            // the tail simply extends an open explicit segment
-            b.e_open = false;
-            skc_append(b, b.e_j0, F, 0.0, 0.0, SKC_KIND_E, skc_exp_off(d) + b.e_first * 8u, 0u);
-        } else {
-            skc_append(b, c, F, 0.0, 0.0, SKC_KIND_E, skc_exp_off(d) + b.n_exp * 8u, 0u);
-        }
-        if (b.n_exp + (F - c) > d.cap_exp) b.status |= SKC_ST_OVERFLOW;
+    if (b.n_exp & 1u) {
+        ChainExp2 pr; pr.a = b.exp_pend; pr.b = e;
+        *reinterpret_cast<ChainExp2 *>(b.exps + (b.n_exp - 1u)) = pr;
     } else {
-        skc_close_exp(b, c);
+        b.exp_pend = e;
     }
-    skc_flush_map(b);
-    *n_seg_out = b.n_seg;
-    return b.status;
+    ++b.n_exp;
 }
 
-// PART 2 (written when chunk n + 1 is processed): the packet's tail, frames j in [carry, F) = outputs 0 .. F - carry - 1 of
-// the current chunk, whose buffer is [.. tail of the previous chunk | head_frames of the current chunk]. `n_frames_prev`
-// is the previous chunk's length N: buffer frame of position p (= floor + 16) is N + p.
-SK_HD uint32_t skc_fill_tail(const double *prefix, uint32_t np, const SkRun *runs, uint32_t nr, double t, uint32_t n_cur, uint32_t carry,
-                             uint32_t F, uint32_t n_frames_prev, uint32_t head_frames, uint32_t frame_bytes, ChainExp *tail, uint32_t cap) {
-    uint32_t r = 0, status = 0;
-    if (carry >= F) return 0;
-    const uint32_t n = F - carry;
-    if (n > n_cur || n > cap) return SKC_ST_UNSUPPORTED;
-    for (uint32_t k = 0; k < n; ++k) {
-        const double x = sk_phase_eval(prefix, np, runs, nr, t, k, &r);
+// ---------------------------------------------------------------------------------------------------------------
+// Streaming builder: a sink of sk_phase_stream (phase_runs.h). While the generator walks chunk n it receives the chunk's
+// outputs k = 0, 1, .. in order (prefix elements one by one, run entries as soon as they are complete) and writes
+//   PART 2 of the pending packet  its tail, frames j in [carry, F) = outputs k < n_tail of this chunk, explicit entries
+//                                 appended to the OLD record (buffer = [.. previous chunk | head_frames of this chunk]:
+//                                 position p = floor + 16 of this chunk is buffer frame n_frames_prev + p);
+//   PART 1 of the next packet     outputs k >= kd of this chunk -> packet frames j = k - kd of the NEW record, then the
+//                                 (still empty) explicit tail segment that the next chunk will fill.
+// Both boundaries are F - carry when this chunk completes the pending packet (kd == n_tail); the caller re-runs the
+// generator with kd = n_tail = 0 in the rare case that it does not (right after a stream starts).
+struct SkcStream {
+    SkcBuilder b;
+    ChainExp *tail;          // old record: where the tail's explicit entries go
+    uint32_t n_tail, tail_cap, n_frames_prev, head_frames;
+    uint32_t tail_status;    // problems of the PENDING packet's tail (the builder's own status concerns the new record)
+    double t;
+    uint32_t kd;
+    uint32_t k_next;         // outputs below k_next have been consumed
+    bool have_last;
+    SkRun last;              // the previous run entry (a gap element may follow it)
+
+    SK_HD_MEMBER void begin(uint8_t *rec_new, const ChainProgDims &d, uint32_t F, uint32_t frame_bytes, uint32_t kd_, ChainExp *tail_, uint32_t n_tail_,
+                            uint32_t tail_cap_, uint32_t n_frames_prev_, uint32_t head_frames_, double t_) {
+        b.map = reinterpret_cast<uint16_t *>(rec_new);
+        b.segs = reinterpret_cast<ChainSeg *>(rec_new + skc_seg_off(d));
+        b.exps = reinterpret_cast<ChainExp *>(rec_new + skc_exp_off(d));
+        b.d = d; b.F = F; b.frame_bytes = frame_bytes;
+        b.n_seg = 0; b.n_exp = 0; b.bcur = 0; b.first_cur = 0; b.status = 0; b.map_lo = 0; b.map_hi = 0;
+        b.exp_pend.aoff = 0; b.exp_pend.frac = 0.0f;
+        b.e_j0 = 0; b.e_first = 0; b.e_open = false;
+        tail = tail_; n_tail = n_tail_; tail_cap = tail_cap_; n_frames_prev = n_frames_prev_; head_frames = head_frames_;
+        t = t_; kd = kd_; k_next = 0; have_last = false;
+        last.x_a = 0.0; last.delta = 0.0; last.k_a = 0; last.k_e = 0;
+        tail_status = n_tail > tail_cap ? SKC_ST_UNSUPPORTED : 0u;
+    }
+    // one output whose value is known explicitly
+    SK_HD_MEMBER void element(uint32_t k, double x) {
         int32_t fl;
         float frac;
         skc_split(x, &fl, &frac);
         const uint32_t p = (uint32_t)(fl + 16);
-        if (p + 1u >= 16u + head_frames) { status |= SKC_ST_UNSUPPORTED; break; }
-        ChainExp e; e.aoff = (n_frames_prev + p) * frame_bytes; e.frac = frac;
-        tail[k] = e;
+        if (k < n_tail && k < tail_cap) {
+            if (p + 1u >= 16u + head_frames) tail_status |= SKC_ST_UNSUPPORTED;   // needs frames of this chunk the kernel does not stage
+            ChainExp e; e.aoff = (n_frames_prev + p) * b.frame_bytes; e.frac = frac;
+            tail[k] = e;
+        }
+        if (k >= kd && k - kd < b.F) skc_push_exp(b, k - kd, p, frac);
     }
-    return status;
-}
+    // members kfirst .. ke-1 of a run anchored at k0: x = x0 + (k - k0) * delta (exact)
+    SK_HD_MEMBER void members(uint32_t kfirst, uint32_t ke, uint32_t k0, double x0, double delta) {
+        uint32_t k = kfirst;
+        const uint32_t lo_end = ke < kd ? ke : kd;   // part below kd: only the tail may want it
+        for (; k < lo_end; ++k) {
+            if (k >= n_tail) { k = lo_end; break; }
+            element(k, sk_dfma((double)(k - k0), delta, x0));
+        }
+        if (k >= ke) return;
+        uint32_t ke_c = ke;                           // clip to the packet
+        if (ke_c - kd > b.F) ke_c = kd + b.F;
+        if (k >= ke_c) return;
+        if (delta > 0.0 && ke_c - k >= SKC_MIN_RUN && k >= n_tail) {
+            skc_close_exp(b, k - kd);
+            const double xs = sk_dfma((double)(k - k0), delta, x0);
+            const uint32_t hi = (uint32_t)(sk_d2bits(xs) >> 32);
+            uint32_t himask = SKC_KIND_SLOW, cs = 0, sh = 0;
+            if ((hi - 0x3FF00000u) < (18u << 20)) {   // positive, exponent e in 0..17, shared by the whole run
+                const uint32_t e = (hi >> 20) - 1023u;
+                const uint32_t lfb = b.frame_bytes == 8u ? 3u : 2u;
+                himask = 0xFFFFFFFFu << (20u - e);
+                sh = 20u - e - lfb;
+                cs = (1022u + e) << (e + lfb);
+            }
+            skc_append(b, k - kd, ke_c - kd, xs, delta, himask, cs, sh);
+        } else {
+            for (; k < ke_c; ++k) element(k, sk_dfma((double)(k - k0), delta, x0));   // short piece: explicit frames
+        }
+    }
+    SK_HD_MEMBER double gap_value() const { return sk_dadd(sk_dfma((double)(last.k_e - 1u - last.k_a), last.delta, last.x_a), t); }
+    SK_HD_MEMBER void prefix(uint32_t k, double x) {
+        element(k, x);
+        k_next = k + 1u;
+    }
+    SK_HD_MEMBER void run(uint32_t, const SkRun &rn) {
+        uint32_t k0 = rn.k_a;
+        double x0 = rn.x_a;
+        if (have_last && k_next < rn.k_a) {
+            // the one uncovered element after the previous run: a true addition. It usually lies on THIS run's lattice
+            // (x_a - delta exactly, same binade): then it simply becomes the run's first member.
+            const double xg = gap_value();
+            if (rn.k_a == k_next + 1u && rn.delta > 0.0 && (sk_d2bits(xg) >> 52) == (sk_d2bits(rn.x_a) >> 52) && sk_dfma(-1.0, rn.delta, rn.x_a) == xg) {
+                k0 = k_next;
+                x0 = xg;
+            } else {
+                element(k_next, xg);
+            }
+        }
+        // the generator may re-issue the last prefix element as the anchor of the first run: it has been consumed already
+        members(k0 < k_next ? k_next : k0, rn.k_e, k0, x0, rn.delta);
+        last = rn;
+        have_last = true;
+        k_next = rn.k_e;
+    }
+    // after the generator: n_out outputs in total. Returns status bits; sizes of the new record in *n_seg_out / *n_exp_out
+    // (n_exp WITHOUT the tail the next chunk will append).
+    SK_HD_MEMBER uint32_t finish(uint32_t n_out, uint32_t *n_seg_out, uint32_t *n_exp_out) {
+        if (have_last && k_next < n_out) element(k_next, gap_value());   // trailing gap element
+        const uint32_t c = n_out > kd ? (n_out - kd < b.F ? n_out - kd : b.F) : 0u;   // frames carried into the next packet
+        *n_exp_out = b.n_exp;
+        if (c < b.F) {   // the tail: frames produced by the next chunk; its entries follow the explicit entries of part 1
+            if (b.e_open) {
+                b.e_open = false;   // the tail simply extends an open explicit segment
+                skc_append(b, b.e_j0, b.F, 0.0, 0.0, SKC_KIND_E, skc_exp_off(b.d) + b.e_first * 8u, 0u);
+            } else {
+                skc_append(b, c, b.F, 0.0, 0.0, SKC_KIND_E, skc_exp_off(b.d) + b.n_exp * 8u, 0u);
+            }
+            if (b.n_exp + (b.F - c) > b.d.cap_exp) b.status |= SKC_ST_OVERFLOW;
+        } else {
+            skc_close_exp(b, c);
+        }
+        skc_flush_map(b);
+        *n_seg_out = b.n_seg;
+        return b.status;
+    }
+};

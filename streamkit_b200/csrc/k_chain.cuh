@@ -238,16 +238,12 @@ __device__ __forceinline__ void chain_consume(unsigned long long (&acc)[ITERS][4
 }
 
 // ------------------------------------------------------------------ k_phase_chain
-constexpr int PHASE_CHAIN_THREADS = 32;
-// thread-private phase table in shared memory; 194 words between threads: 8-byte accesses of a warp are conflict free
-constexpr uint32_t PHASE_TAB_STRIDE = SKC_TAB_PREFIX * 8u + SKC_TAB_RUNS * (uint32_t)sizeof(SkRun) + 8u;
-static_assert((PHASE_TAB_STRIDE / 4u) % 32u == 2u, "phase-table stride must keep 8-byte accesses conflict free");
+constexpr int PHASE_CHAIN_THREADS = 64;
 
-__global__ void __launch_bounds__(PHASE_CHAIN_THREADS) k_phase_chain(const OpHeader *__restrict__ hdr, const skgpu_chain_input *__restrict__ inputs,
+__global__ void __launch_bounds__(PHASE_CHAIN_THREADS, 14) k_phase_chain(const OpHeader *__restrict__ hdr, const skgpu_chain_input *__restrict__ inputs,
                                                                      const uint8_t *__restrict__ present, const float *__restrict__ gains, SlotTables st,
                                                                      uint8_t *__restrict__ arena, const uint32_t *__restrict__ tick, uint64_t bank_stride,
                                                                      uint32_t F, uint64_t results_off, ChainDims dm, ChainRec *__restrict__ recs) {
-    __shared__ __align__(8) uint8_t s_tab[PHASE_CHAIN_THREADS * PHASE_TAB_STRIDE];
     const uint32_t i = blockIdx.x * PHASE_CHAIN_THREADS + threadIdx.x;
     if (i >= hdr->count2) return;
     const skgpu_chain_input in = inputs[i];
@@ -263,37 +259,42 @@ __global__ void __launch_bounds__(PHASE_CHAIN_THREADS) k_phase_chain(const OpHea
     const uint32_t carry = rec.carry;
     uint32_t status = 0, emit = 0;
     if (pres) {
-        // ---- rubato's phase recurrence for this chunk (thread-private table)
-        double *prefix = reinterpret_cast<double *>(s_tab + threadIdx.x * PHASE_TAB_STRIDE);
-        SkRun *runs = reinterpret_cast<SkRun *>(prefix + SKC_TAB_PREFIX);
-        uint32_t np, nr, ovf;
-        double idx_end;
-        const uint32_t n_cur = sk_phase_table_ex(rec.last_index, rec.t_ratio, rec.end_idx, prefix, SKC_TAB_PREFIX, runs, SKC_TAB_RUNS, &np, &nr, &ovf, &idx_end);
-        rec.last_index = __dsub_rn(idx_end, (double)rec.chunk);   // self.last_index = idx - chunk_size as f64
-        rec.chunk_count = count0 + 1u;
-        if (ovf) status |= SKC_ST_OVERFLOW;
+        // ---- rubato's phase recurrence for this chunk, streamed into the frame programs (chain_prog.h): the tail of the
+        // pending packet (old record) and part 1 of the next packet (new record). A packet is emitted when
+        // carry + n_cur >= F (resampler.rs:425-428), i.e. when this chunk has at least kd = F - carry outputs.
         const uint32_t n_prev = count0 >= 1u ? rec.n_out[par_old] : 0u;
         if (carry > n_prev) status |= SKC_ST_UNSUPPORTED;                 // carried frames span more than one chunk
         if ((rec.overflow >> par_old) & 1u) status |= SKC_ST_OVERFLOW;    // the record the packet would execute is incomplete
-        // ---- re-framing (resampler.rs:425-428): a packet is emitted when carry + n_cur >= F
-        const uint32_t avail = carry + n_cur;
-        const uint32_t new_carry = (avail >= F) ? avail - F : avail;
-        if (avail >= F && !(status & (SKC_ST_OVERFLOW | SKC_ST_UNSUPPORTED)) && count0 >= 1u) {
-            // part 2 of the packet's program: its tail comes from this chunk
-            uint8_t *rec_old = slot_side(st, slot, par_old);
-            const uint32_t ne_old = rec.n_prefix[par_old];
-            status |= skc_fill_tail(prefix, np, runs, nr, rec.t_ratio, n_cur, carry, F, N, head, fb,
-                                    reinterpret_cast<ChainExp *>(rec_old + skc_exp_off(dm.prog)) + ne_old, dm.prog.cap_exp - min(ne_old, dm.prog.cap_exp));
+        const bool pending = count0 >= 1u;
+        uint32_t kd = pending ? F - min(carry, F) : 0u;
+        const uint32_t ne_old = rec.n_prefix[par_old];
+        ChainExp *tail = reinterpret_cast<ChainExp *>(slot_side(st, slot, par_old) + skc_exp_off(dm.prog)) + ne_old;
+        uint8_t *rec_new = slot_side(st, slot, par_new);
+        SkcStream sb;
+        uint32_t np, nr, ovf;
+        double idx_end;
+        sb.begin(rec_new, dm.prog, F, fb, kd, tail, kd, dm.prog.cap_exp - min(ne_old, dm.prog.cap_exp), N, head, rec.t_ratio);
+        uint32_t n_cur = sk_phase_stream(rec.last_index, rec.t_ratio, rec.end_idx, SKC_TAB_PREFIX, 255u, sb, &np, &nr, &ovf, &idx_end);
+        if (n_cur < kd) {
+            // the chunk does not complete the packet (only right after a stream starts): everything is carried
+            kd = 0u;
+            sb.begin(rec_new, dm.prog, F, fb, 0u, tail, 0u, 0u, N, head, rec.t_ratio);
+            n_cur = sk_phase_stream(rec.last_index, rec.t_ratio, rec.end_idx, SKC_TAB_PREFIX, 255u, sb, &np, &nr, &ovf, &idx_end);
+        } else if (pending) {
+            status |= sb.tail_status;
             emit = (status & (SKC_ST_OVERFLOW | SKC_ST_UNSUPPORTED)) ? 0u : 1u;
         }
-        if (new_carry > n_cur) status |= 1u;                              // backlog: a second packet is pending
-        // ---- part 1 of the NEXT packet's program: the frames this chunk carries over
         uint32_t n_seg = 0, n_exp = 0;
-        const uint32_t st_new = skc_build(prefix, np, runs, nr, rec.t_ratio, n_cur, min(new_carry, n_cur), F, fb, dm.prog, slot_side(st, slot, par_new), &n_seg, &n_exp);
+        const uint32_t st_new = sb.finish(n_cur, &n_seg, &n_exp);
+        const uint32_t avail = carry + n_cur;
+        const uint32_t new_carry = (avail >= F) ? avail - F : avail;
+        if (new_carry > n_cur) status |= 1u;                              // backlog: a second packet is pending
+        rec.last_index = __dsub_rn(idx_end, (double)rec.chunk);           // self.last_index = idx - chunk_size as f64
+        rec.chunk_count = count0 + 1u;
         rec.n_out[par_new] = n_cur;
         rec.n_prefix[par_new] = (uint16_t)n_exp;
         rec.n_runs[par_new] = (uint16_t)n_seg;
-        rec.overflow = (rec.overflow & ~(1u << par_new)) | (((st_new | (ovf ? SKC_ST_OVERFLOW : 0u)) ? 1u : 0u) << par_new);
+        rec.overflow = (rec.overflow & ~(1u << par_new)) | ((st_new ? 1u : 0u) << par_new);
         rec.carry = new_carry;
         *recp = rec;
     }

@@ -27,8 +27,10 @@
 
 #if defined(__CUDACC__)
 #define SK_HD __host__ __device__ __forceinline__
+#define SK_HD_MEMBER __host__ __device__ __forceinline__
 #else
 #define SK_HD static inline
+#define SK_HD_MEMBER inline
 #endif
 
 #define SK_PREFIX_MAX 40u
@@ -88,8 +90,11 @@ SK_HD double sk_dfma(double a, double b, double c) {
 // Returns n_out; *idx_end receives the final idx (the caller stores last_index' = idx_end - chunk).
 // Pointer-based form: prefix[] (capacity cap_np) and runs[] (capacity cap_nr) may live anywhere (a compact per-op layout
 // in HBM for the fused chain). Sizes and the overflow flag are returned through out-parameters.
-SK_HD uint32_t sk_phase_table_ex(double last_index, double t, int32_t end_idx, double *prefix_out, uint32_t cap_np, SkRun *runs_out,
-                                 uint32_t cap_nr, uint32_t *n_prefix_out, uint32_t *n_runs_out, uint32_t *overflow_out, double *idx_end) {
+// Streaming form: every prefix element goes to sink.prefix(k, x) and every COMPLETED table entry to sink.run(index, entry),
+// both in increasing k, so a consumer (chain_prog.h) can build on the fly without a stored table.
+template <class Sink>
+SK_HD uint32_t sk_phase_stream(double last_index, double t, int32_t end_idx, uint32_t cap_np, uint32_t cap_nr, Sink &sink,
+                               uint32_t *n_prefix_out, uint32_t *n_runs_out, uint32_t *overflow_out, double *idx_end) {
     const double end = (double)end_idx;
     double x = last_index;
     uint32_t k = 0, np = 0, nr = 0;
@@ -105,7 +110,7 @@ SK_HD uint32_t sk_phase_table_ex(double last_index, double t, int32_t end_idx, d
 #define SK_FLUSH_CUR()                                              \
     do {                                                            \
         if (cur_valid) {                                            \
-            if (nr <= cap_nr && nr > 0) runs_out[nr - 1] = cur;     \
+            if (nr <= cap_nr && nr > 0) sink.run(nr - 1, cur);      \
         }                                                           \
     } while (0)
 
@@ -174,7 +179,7 @@ SK_HD uint32_t sk_phase_table_ex(double last_index, double t, int32_t end_idx, d
         // ---- element outside any run
         if (in_prefix) {
             if (np < cap_np) {
-                prefix_out[np++] = x;
+                sink.prefix(np++, x);
                 prev_strict = strict;
                 xb = x;
                 ++k;
@@ -205,6 +210,20 @@ SK_HD uint32_t sk_phase_table_ex(double last_index, double t, int32_t end_idx, d
     *overflow_out = ovf;
     *idx_end = x;
     return k;
+}
+
+struct SkArraySink {   // stores the table (prefix[] / runs[] may live anywhere)
+    double *prefix_out;
+    SkRun *runs_out;
+    SK_HD_MEMBER void prefix(uint32_t i, double x) { prefix_out[i] = x; }
+    SK_HD_MEMBER void run(uint32_t i, const SkRun &r) { runs_out[i] = r; }
+};
+SK_HD uint32_t sk_phase_table_ex(double last_index, double t, int32_t end_idx, double *prefix_out, uint32_t cap_np, SkRun *runs_out,
+                                 uint32_t cap_nr, uint32_t *n_prefix_out, uint32_t *n_runs_out, uint32_t *overflow_out, double *idx_end) {
+    SkArraySink sink;
+    sink.prefix_out = prefix_out;
+    sink.runs_out = runs_out;
+    return sk_phase_stream(last_index, t, end_idx, cap_np, cap_nr, sink, n_prefix_out, n_runs_out, overflow_out, idx_end);
 }
 
 // Generates the phase table of one process() call into a SkPhaseTable.

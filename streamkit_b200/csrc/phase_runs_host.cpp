@@ -82,27 +82,41 @@ extern "C" uint64_t skc_check_stream(double ratio, uint32_t chunk, uint32_t F, u
     d.cap_exp = cap_exp;
     std::vector<uint8_t> rec[2] = {std::vector<uint8_t>(skc_prog_cap(d) + 64), std::vector<uint8_t>(skc_prog_cap(d) + 64)};
     uint32_t n_exp_rec[2] = {0, 0}, n_out_rec[2] = {0, 0};
+    bool rec_bad[2] = {false, false};
     std::vector<double> seq_prev, seq_cur;   // the true chain of the previous / current chunk
-    struct { double prefix[SKC_TAB_PREFIX]; SkRun runs[SKC_TAB_RUNS]; uint32_t n_prefix, n_runs, overflow; } T;
     uint64_t bad = 0;
     uint32_t packets = 0, ms = 0, me = 0, st_or = 0;
     double L = -4.0;
     uint32_t carry = 0;
     for (uint32_t c = 0; c < calls; ++c) {
         const uint32_t par_new = c & 1u, par_old = par_new ^ 1u;
+        // ---- exactly what k_phase_chain does: stream the generator into the tail of the old record + part 1 of the new one
         double idx_end = 0;
-        const uint32_t n_cur = sk_phase_table_ex(L, t, end_idx, T.prefix, SKC_TAB_PREFIX, T.runs, SKC_TAB_RUNS, &T.n_prefix, &T.n_runs, &T.overflow, &idx_end);
-        if (T.overflow) st_or |= SKC_ST_OVERFLOW;
+        uint32_t np, nr, ovf, ns = 0, ne = 0;
+        const bool pending = c >= 1;
+        uint32_t kd = pending ? F - std::min(carry, F) : 0u;
+        const uint32_t ne_old = n_exp_rec[par_old];
+        ChainExp *tailp = reinterpret_cast<ChainExp *>(rec[par_old].data() + skc_exp_off(d)) + ne_old;
+        SkcStream sb;
+        sb.begin(rec[par_new].data(), d, F, fb, kd, tailp, kd, d.cap_exp - std::min(ne_old, d.cap_exp), chunk, head, t);
+        uint32_t n_cur = sk_phase_stream(L, t, end_idx, SKC_TAB_PREFIX, 255u, sb, &np, &nr, &ovf, &idx_end);
+        bool completes = pending;
+        if (n_cur < kd) {
+            completes = false;
+            sb.begin(rec[par_new].data(), d, F, fb, 0u, tailp, 0u, 0u, chunk, head, t);
+            n_cur = sk_phase_stream(L, t, end_idx, SKC_TAB_PREFIX, 255u, sb, &np, &nr, &ovf, &idx_end);
+        }
+        const uint32_t tail_status = completes ? sb.tail_status : 0u;
+        const uint32_t stb = sb.finish(n_cur, &ns, &ne);
+        if (ovf) st_or |= SKC_ST_OVERFLOW;
         seq_cur.clear();
         for (double idx = L; idx < (double)end_idx;) { idx += t; seq_cur.push_back(idx); }
         if (seq_cur.size() != n_cur) ++bad;
         const uint32_t avail = carry + n_cur;
         const uint32_t new_carry = avail >= F ? avail - F : avail;
-        if (avail >= F && c >= 1 && carry <= n_out_rec[par_old]) {
+        if (completes && carry <= n_out_rec[par_old] && !rec_bad[par_old]) {
             uint8_t *ro = rec[par_old].data();
-            const uint32_t ne_old = n_exp_rec[par_old];
-            const uint32_t st = skc_fill_tail(T.prefix, T.n_prefix, T.runs, T.n_runs, t, n_cur, carry, F, chunk, head, fb,
-                                              reinterpret_cast<ChainExp *>(ro + skc_exp_off(d)) + ne_old, d.cap_exp - std::min(ne_old, d.cap_exp));
+            const uint32_t st = tail_status;
             st_or |= st;
             if (!st) {
                 ++packets;
@@ -152,9 +166,8 @@ extern "C" uint64_t skc_check_stream(double ratio, uint32_t chunk, uint32_t F, u
                 for (uint32_t j = 0; j < F; ++j) if (hits[j] != 1) ++bad;
             }
         }
-        uint32_t ns = 0, ne = 0;
-        const uint32_t stb = skc_build(T.prefix, T.n_prefix, T.runs, T.n_runs, t, n_cur, std::min(new_carry, n_cur), F, fb, d, rec[par_new].data(), &ns, &ne);
         st_or |= stb;
+        rec_bad[par_new] = stb != 0;
         ms = std::max(ms, ns);
         n_exp_rec[par_new] = ne;
         n_out_rec[par_new] = n_cur;

@@ -717,22 +717,31 @@ extern "C" uint64_t skgpu_plan_tick_count(const skgpu_plan *p) { return p ? p->t
 // Upper bounds of the frame-program sizes (chain_prog.h) a stream configuration can produce: run the host-compiled
 // generator + builder over the first chunks of a stream and over a spread of steady-state phases. The kernel
 // re-checks at run time (status bit1).
-static void prog_bounds(double t, int32_t end_idx, uint32_t N, uint32_t F, uint32_t *need_seg, uint32_t *need_exp) {
+static bool prog_bounds(double t, int32_t end_idx, uint32_t N, uint32_t F, uint32_t *need_seg, uint32_t *need_exp) {
     ChainProgDims big{};
     big.nblk = (F + 31u) / 32u;
     big.map_bytes = (big.nblk * 2u + 15u) & ~15u;
     big.cap_seg = 254u;
     big.cap_exp = 8192u;
     std::vector<uint8_t> scratch(skc_prog_cap(big));
-    struct { double prefix[SKC_TAB_PREFIX]; SkRun runs[SKC_TAB_RUNS]; uint32_t n_prefix, n_runs, overflow; } T;
     uint32_t ms = 0, me = 0;
-    auto one_chunk = [&](double last_index, uint32_t carry, double *next_index, uint32_t *next_carry) {
+    bool overflow = false;
+    auto one_chunk = [&](double last_index, uint32_t carry, bool pending, double *next_index, uint32_t *next_carry) {
+        // the same sequence k_phase_chain runs (k_chain.cuh)
+        SkcStream sb;
+        uint32_t np, nr, ovf, ns = 0, ne = 0;
         double idx_end;
-        const uint32_t n_cur = sk_phase_table_ex(last_index, t, end_idx, T.prefix, SKC_TAB_PREFIX, T.runs, SKC_TAB_RUNS, &T.n_prefix, &T.n_runs, &T.overflow, &idx_end);
+        uint32_t kd = pending ? F - std::min(carry, F) : 0u;
+        std::vector<ChainExp> tail(F + 1u);
+        sb.begin(scratch.data(), big, F, 8u, kd, tail.data(), kd, F, N, 32u, t);
+        uint32_t n_cur = sk_phase_stream(last_index, t, end_idx, SKC_TAB_PREFIX, 255u, sb, &np, &nr, &ovf, &idx_end);
+        if (n_cur < kd) {
+            sb.begin(scratch.data(), big, F, 8u, 0u, tail.data(), 0u, 0u, N, 32u, t);
+            n_cur = sk_phase_stream(last_index, t, end_idx, SKC_TAB_PREFIX, 255u, sb, &np, &nr, &ovf, &idx_end);
+        }
+        overflow |= sb.finish(n_cur, &ns, &ne) != 0;
         const uint32_t avail = carry + n_cur;
         const uint32_t nc = avail >= F ? avail - F : avail;
-        uint32_t ns = 0, ne = 0;
-        skc_build(T.prefix, T.n_prefix, T.runs, T.n_runs, t, n_cur, std::min(nc, n_cur), F, 8u, big, scratch.data(), &ns, &ne);
         ms = std::max(ms, ns);
         me = std::max(me, ne + (F - std::min(nc, F)));
         *next_index = idx_end - (double)N;
@@ -740,10 +749,11 @@ static void prog_bounds(double t, int32_t end_idx, uint32_t N, uint32_t F, uint3
     };
     double li = -4.0, nli;
     uint32_t carry = 0, ncarry, steady = 0;
-    for (int c = 0; c < 8; ++c) { one_chunk(li, carry, &nli, &ncarry); li = nli; carry = ncarry; steady = carry; }
+    for (int c = 0; c < 8; ++c) { one_chunk(li, carry, c > 0, &nli, &ncarry); li = nli; carry = ncarry; steady = carry; }
     const double lo = -(9.0 + std::ceil(t));
-    for (int i = 0; i < 64; ++i) one_chunk(lo + t * (i + 0.37) / 64.0, steady, &nli, &ncarry);
+    for (int i = 0; i < 64; ++i) one_chunk(lo + t * (i + 0.37) / 64.0, steady, true, &nli, &ncarry);
     *need_seg = ms; *need_exp = me;
+    return !overflow;
 }
 
 static skgpu_rc validate_chain(const skgpu_plan *p, const skgpu_chain_group *g, uint32_t ng, const skgpu_chain_input *in, uint32_t ni,
@@ -772,7 +782,8 @@ static skgpu_rc validate_chain(const skgpu_plan *p, const skgpu_chain_group *g, 
         mb = std::max(mb, (N + (uint32_t)CH_HEAD) * C * 4u);   // bytes: previous chunk + staged head of the current one
         if (c->h_t[slot] != last_t || c->h_end[slot] != last_end || N != last_N) {   // streams of one op usually share a handful of configurations
             uint32_t a = 0, b = 0;
-            prog_bounds(c->h_t[slot], c->h_end[slot], N, F, &a, &b);
+            if (!prog_bounds(c->h_t[slot], c->h_end[slot], N, F, &a, &b))
+                return fail(SKGPU_ERR_INVALID, "chain input %u: the phase table of ratio %g does not fit the fused kernel (use the unfused ops)", i, 1.0 / c->h_t[slot]);
             need_seg = std::max(need_seg, a); need_exp = std::max(need_exp, b);
             last_t = c->h_t[slot]; last_end = c->h_end[slot]; last_N = N;
         }
