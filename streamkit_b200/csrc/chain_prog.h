@@ -40,7 +40,7 @@ struct alignas(16) ChainSeg {
     uint32_t aux;       // E: byte offset of its first ChainExp from the record start; FAST: cs
     uint32_t sh;        // FAST: shift
 };
-struct ChainExp { uint32_t aoff; float frac; };  // byte offset of frame y0 from the start of the 16-frame history
+struct alignas(8) ChainExp { uint32_t aoff; float frac; };  // byte offset of frame y0 from the start of the 16-frame history
 struct alignas(16) ChainExp2 { ChainExp a, b; };  // the builder stores explicit entries in aligned pairs: one thread per stream
                                                    // writes its own record, so every store is a scattered request and wide
                                                    // stores halve their number (k_phase_chain is bound by them)
@@ -146,14 +146,18 @@ struct SkcStream {
     ChainExp *tail;          // old record: where the tail's explicit entries go
     uint32_t n_tail, tail_cap, n_frames_prev, head_frames;
     uint32_t tail_status;    // problems of the PENDING packet's tail (the builder's own status concerns the new record)
+    uint32_t tail_odd;       // parity of the absolute index of tail[0]: entries are stored in 16-byte aligned pairs
+    ChainExp tail_pend;
     double t;
     uint32_t kd;
     uint32_t k_next;         // outputs below k_next have been consumed
     bool have_last;
     SkRun last;              // the previous run entry (a gap element may follow it)
 
-    SK_HD_MEMBER void begin(uint8_t *rec_new, const ChainProgDims &d, uint32_t F, uint32_t frame_bytes, uint32_t kd_, ChainExp *tail_, uint32_t n_tail_,
-                            uint32_t tail_cap_, uint32_t n_frames_prev_, uint32_t head_frames_, double t_) {
+    SK_HD_MEMBER void begin(uint8_t *rec_new, const ChainProgDims &d, uint32_t F, uint32_t frame_bytes, uint32_t kd_, ChainExp *tail_, uint32_t tail_index0,
+                            uint32_t n_tail_, uint32_t tail_cap_, uint32_t n_frames_prev_, uint32_t head_frames_, double t_) {
+        tail_odd = tail_index0 & 1u;
+        tail_pend.aoff = 0; tail_pend.frac = 0.0f;
         b.map = reinterpret_cast<uint16_t *>(rec_new);
         b.segs = reinterpret_cast<ChainSeg *>(rec_new + skc_seg_off(d));
         b.exps = reinterpret_cast<ChainExp *>(rec_new + skc_exp_off(d));
@@ -175,7 +179,14 @@ struct SkcStream {
         if (k < n_tail && k < tail_cap) {
             if (p + 1u >= 16u + head_frames) tail_status |= SKC_ST_UNSUPPORTED;   // needs frames of this chunk the kernel does not stage
             ChainExp e; e.aoff = (n_frames_prev + p) * b.frame_bytes; e.frac = frac;
-            tail[k] = e;
+            if (((k + tail_odd) & 1u) && k > 0u) {          // second entry of an aligned pair
+                ChainExp2 pr; pr.a = tail_pend; pr.b = e;
+                *reinterpret_cast<ChainExp2 *>(tail + (k - 1u)) = pr;
+            } else if (k + 1u == n_tail || ((k + tail_odd) & 1u)) {
+                tail[k] = e;                                // last entry, or an unaligned first one
+            } else {
+                tail_pend = e;
+            }
         }
         if (k >= kd && k - kd < b.F) skc_push_exp(b, k - kd, p, frac);
     }

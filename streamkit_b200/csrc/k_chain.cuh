@@ -273,12 +273,12 @@ __global__ void __launch_bounds__(PHASE_CHAIN_THREADS, 14) k_phase_chain(const O
         SkcStream sb;
         uint32_t np, nr, ovf;
         double idx_end;
-        sb.begin(rec_new, dm.prog, F, fb, kd, tail, kd, dm.prog.cap_exp - min(ne_old, dm.prog.cap_exp), N, head, rec.t_ratio);
+        sb.begin(rec_new, dm.prog, F, fb, kd, tail, ne_old, kd, dm.prog.cap_exp - min(ne_old, dm.prog.cap_exp), N, head, rec.t_ratio);
         uint32_t n_cur = sk_phase_stream(rec.last_index, rec.t_ratio, rec.end_idx, SKC_TAB_PREFIX, 255u, sb, &np, &nr, &ovf, &idx_end);
         if (n_cur < kd) {
             // the chunk does not complete the packet (only right after a stream starts): everything is carried
             kd = 0u;
-            sb.begin(rec_new, dm.prog, F, fb, 0u, tail, 0u, 0u, N, head, rec.t_ratio);
+            sb.begin(rec_new, dm.prog, F, fb, 0u, tail, ne_old, 0u, 0u, N, head, rec.t_ratio);
             n_cur = sk_phase_stream(rec.last_index, rec.t_ratio, rec.end_idx, SKC_TAB_PREFIX, 255u, sb, &np, &nr, &ovf, &idx_end);
         } else if (pending) {
             status |= sb.tail_status;

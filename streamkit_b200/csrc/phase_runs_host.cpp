@@ -98,12 +98,12 @@ extern "C" uint64_t skc_check_stream(double ratio, uint32_t chunk, uint32_t F, u
         const uint32_t ne_old = n_exp_rec[par_old];
         ChainExp *tailp = reinterpret_cast<ChainExp *>(rec[par_old].data() + skc_exp_off(d)) + ne_old;
         SkcStream sb;
-        sb.begin(rec[par_new].data(), d, F, fb, kd, tailp, kd, d.cap_exp - std::min(ne_old, d.cap_exp), chunk, head, t);
+        sb.begin(rec[par_new].data(), d, F, fb, kd, tailp, ne_old, kd, d.cap_exp - std::min(ne_old, d.cap_exp), chunk, head, t);
         uint32_t n_cur = sk_phase_stream(L, t, end_idx, SKC_TAB_PREFIX, 255u, sb, &np, &nr, &ovf, &idx_end);
         bool completes = pending;
         if (n_cur < kd) {
             completes = false;
-            sb.begin(rec[par_new].data(), d, F, fb, 0u, tailp, 0u, 0u, chunk, head, t);
+            sb.begin(rec[par_new].data(), d, F, fb, 0u, tailp, ne_old, 0u, 0u, chunk, head, t);
             n_cur = sk_phase_stream(L, t, end_idx, SKC_TAB_PREFIX, 255u, sb, &np, &nr, &ovf, &idx_end);
         }
         const uint32_t tail_status = completes ? sb.tail_status : 0u;

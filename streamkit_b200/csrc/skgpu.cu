@@ -732,11 +732,12 @@ static bool prog_bounds(double t, int32_t end_idx, uint32_t N, uint32_t F, uint3
         uint32_t np, nr, ovf, ns = 0, ne = 0;
         double idx_end;
         uint32_t kd = pending ? F - std::min(carry, F) : 0u;
-        std::vector<ChainExp> tail(F + 1u);
-        sb.begin(scratch.data(), big, F, 8u, kd, tail.data(), kd, F, N, 32u, t);
+        std::vector<ChainExp2> tail2(F / 2u + 2u);   // 16-byte aligned: the builder stores entries in pairs
+        ChainExp *tail_p = reinterpret_cast<ChainExp *>(tail2.data());
+        sb.begin(scratch.data(), big, F, 8u, kd, tail_p, 0u, kd, F, N, 32u, t);
         uint32_t n_cur = sk_phase_stream(last_index, t, end_idx, SKC_TAB_PREFIX, 255u, sb, &np, &nr, &ovf, &idx_end);
         if (n_cur < kd) {
-            sb.begin(scratch.data(), big, F, 8u, 0u, tail.data(), 0u, 0u, N, 32u, t);
+            sb.begin(scratch.data(), big, F, 8u, 0u, tail_p, 0u, 0u, 0u, N, 32u, t);
             n_cur = sk_phase_stream(last_index, t, end_idx, SKC_TAB_PREFIX, 255u, sb, &np, &nr, &ovf, &idx_end);
         }
         overflow |= sb.finish(n_cur, &ns, &ne) != 0;
