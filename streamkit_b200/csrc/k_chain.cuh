@@ -560,21 +560,40 @@ __global__ void __launch_bounds__(CH_THREADS, 4) k_chain(const OpHeader *__restr
         }
         if (hd.z != 0) {
             // ---- epilogue: master gain, then clip + s16 pack (or f32); a warp stores 32 consecutive frames per instruction
-            const unsigned long long mg2 = pack2(S->master_gain, S->master_gain);   // audio::gain after the mixer (x * 1.0 == x when there is none)
+            const float mg = S->master_gain;   // audio::gain after the mixer (1.0 when there is none: x * 1.0 == x)
             const uint32_t flags = S->flags;
             uint8_t *out_base = arena + S->out_off;
+            const uint32_t jw = cw * 128u + lane;
+            if (flags & SKGPU_MIX_OUT_S16) {
+                // s16 = cvt.rni.sat(fl(a * g) * 32768). The power-of-two scale commutes with the rounding of a * g, so one
+                // multiply by g * 32768 gives the same integer (a subnormal a * g rounds to 0 either way, overflow saturates).
+                const float mgs = __fmul_rn(mg, 32768.0f);
+                const unsigned long long mgs2 = pack2(mgs, mgs);
 #pragma unroll
-            for (int it = 0; it < ITERS; ++it) {
+                for (int it = 0; it < ITERS; ++it) {
 #pragma unroll
-                for (int f = 0; f < 4; ++f) {
-                    const uint32_t j = (((uint32_t)it * 8u + cw) * 4u + (uint32_t)f) * 32u + lane;
-                    if (j >= F) continue;
-                    float a0, a1;
-                    unpack2(mul2v(acc[it][f], mg2), a0, a1);
-                    if (flags & SKGPU_MIX_OUT_S16) {
-                        if (OC == 2) stg_stream_u32(reinterpret_cast<uint32_t *>(out_base) + j, pack_s16x2(a0, a1));
-                        else reinterpret_cast<uint16_t *>(out_base)[j] = (uint16_t)f32_to_s16_bits(a0);
-                    } else {
+                    for (int f = 0; f < 4; ++f) {
+                        const uint32_t j = jw + (uint32_t)it * 1024u + (uint32_t)f * 32u;
+                        if (j >= F) continue;
+                        float a0, a1;
+                        unpack2(mul2v(acc[it][f], mgs2), a0, a1);
+                        int r0, r1;
+                        asm("cvt.rni.sat.s16.f32 %0, %1;" : "=r"(r0) : "f"(a0));
+                        asm("cvt.rni.sat.s16.f32 %0, %1;" : "=r"(r1) : "f"(a1));
+                        if (OC == 2) stg_stream_u32(reinterpret_cast<uint32_t *>(out_base) + j, __byte_perm((uint32_t)r0, (uint32_t)r1, 0x5410));
+                        else reinterpret_cast<uint16_t *>(out_base)[j] = (uint16_t)r0;
+                    }
+                }
+            } else {
+                const unsigned long long mg2 = pack2(mg, mg);
+#pragma unroll
+                for (int it = 0; it < ITERS; ++it) {
+#pragma unroll
+                    for (int f = 0; f < 4; ++f) {
+                        const uint32_t j = jw + (uint32_t)it * 1024u + (uint32_t)f * 32u;
+                        if (j >= F) continue;
+                        float a0, a1;
+                        unpack2(mul2v(acc[it][f], mg2), a0, a1);
                         if (OC == 2) stg_stream_f2(reinterpret_cast<float2 *>(out_base) + j, make_float2(a0, a1));
                         else reinterpret_cast<float *>(out_base)[j] = a0;
                     }
