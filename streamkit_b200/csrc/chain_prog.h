@@ -265,4 +265,29 @@ struct SkcStream {
         *n_seg_out = b.n_seg;
         return b.status;
     }
+    // variant for a record WITHOUT a tail (plain resample op: the record covers exactly the n_out outputs of one chunk,
+    // begin() was called with kd = n_tail = 0 and F = the record's frame capacity)
+    SK_HD_MEMBER uint32_t finish_open(uint32_t n_out, uint32_t *n_seg_out, uint32_t *n_exp_out) {
+        if (have_last && k_next < n_out) element(k_next, gap_value());
+        const uint32_t c = n_out < b.F ? n_out : b.F;
+        if (n_out > b.F) b.status |= SKC_ST_OVERFLOW;
+        skc_close_exp(b, c);
+        if (b.n_seg > 0u) {   // the block the last segment left open ends with the record
+            const uint32_t s = b.n_seg - 1u;
+            while (b.bcur < b.d.nblk && b.bcur * 32u < c) {
+                const uint64_t ent = (uint64_t)(b.first_cur | (s << 8)) << (16u * (b.bcur & 3u));
+                if (b.bcur & 4u) b.map_hi |= ent; else b.map_lo |= ent;
+                if ((b.bcur & 7u) == 7u) {
+                    skc_store16(reinterpret_cast<uint8_t *>(b.map) + (b.bcur >> 3) * 16u, b.map_lo, b.map_hi);
+                    b.map_lo = 0; b.map_hi = 0;
+                }
+                ++b.bcur;
+                b.first_cur = s;
+            }
+        }
+        skc_flush_map(b);
+        *n_seg_out = b.n_seg;
+        *n_exp_out = b.n_exp;
+        return b.status;
+    }
 };

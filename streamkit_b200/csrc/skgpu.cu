@@ -298,6 +298,8 @@ struct Op {
     uint32_t smem_frames = 0;     // resample: frames (history + chunk) the staged path can hold
     uint32_t smem_bytes = 0;
     int rs_channels = 0;          // resample: 1 / 2 specialisation, 0 = generic
+    bool rs_prog = false;         // resample: program-driven kernels (k_phase_prog + k_resample_prog)
+    ChainProgDims rs_pd{};        // resample: frame-program capacities of the op
     uint64_t results_off = 0;
     bool has_fifo_inputs = false;
     uint32_t chain_F = 0;         // chain: output_frame_size
@@ -520,6 +522,57 @@ static skgpu_rc validate_rs(const skgpu_plan *p, const skgpu_rs_item *items, uin
     return SKGPU_OK;
 }
 
+// Frame-program capacities of a resample op (k_resample_prog): the same generator + builder the phase kernel runs,
+// over the first chunks of every distinct stream configuration and a spread of steady-state phases. Returns false when
+// a program cannot be represented (the op then uses the table-driven kernels).
+static bool rs_prog_dims(const skgpu_ctx *c, const skgpu_rs_item *items, uint32_t n, ChainProgDims *out) {
+    uint32_t max_frames = 0, need_seg = 0, need_exp = 0;
+    double last_t = -1.0;
+    int32_t last_end = 0;
+    uint32_t last_N = 0;
+    for (uint32_t i = 0; i < n; ++i) {
+        const uint32_t slot = items[i].slot;
+        const double t = c->h_t[slot];
+        const int32_t end_idx = c->h_end[slot];
+        const uint32_t N = c->h_chunk[slot];
+        if (t == last_t && end_idx == last_end && N == last_N) continue;
+        last_t = t; last_end = end_idx; last_N = N;
+        const uint32_t fcap = (uint32_t)((double)N / t + 10.0) + 8u;
+        if (fcap > 60000u) return false;   // segment bounds are 16-bit
+        ChainProgDims big{};
+        big.nblk = (fcap + 31u) / 32u;
+        big.map_bytes = (big.nblk * 2u + 15u) & ~15u;
+        big.cap_seg = 254u;
+        big.cap_exp = 8192u;
+        std::vector<uint8_t> scratch(skc_prog_cap(big) + 16u);
+        auto one_chunk = [&](double last_index, double *next_index) -> bool {
+            SkcStream sb;
+            uint32_t np, nr, ovf, ns = 0, ne = 0;
+            double idx_end;
+            sb.begin(scratch.data(), big, big.nblk * 32u, 8u, 0u, nullptr, 0u, 0u, 0u, N, 0u, t);
+            const uint32_t n_out = sk_phase_stream(last_index, t, end_idx, SKC_TAB_PREFIX, 255u, sb, &np, &nr, &ovf, &idx_end);
+            const uint32_t st = sb.finish_open(n_out, &ns, &ne);
+            need_seg = std::max(need_seg, ns);
+            need_exp = std::max(need_exp, ne);
+            *next_index = idx_end - (double)N;
+            return st == 0 && !ovf;
+        };
+        double li = -4.0, nli;
+        for (int k = 0; k < 6; ++k) { if (!one_chunk(li, &nli)) return false; li = nli; }
+        const double lo = -(9.0 + std::ceil(t));
+        for (int k = 0; k < 64; ++k) if (!one_chunk(lo + t * (k + 0.37) / 64.0, &nli)) return false;
+        max_frames = std::max(max_frames, fcap);
+    }
+    ChainProgDims d{};
+    d.nblk = (std::max(max_frames, 32u) + 31u) / 32u;
+    d.map_bytes = (d.nblk * 2u + 15u) & ~15u;
+    d.cap_seg = (need_seg + 5u) & ~1u;
+    d.cap_exp = (need_exp + 9u) & ~1u;
+    if (d.cap_seg > 254u || skc_prog_cap(d) > SK_SIDE_STRIDE) return false;
+    *out = d;
+    return true;
+}
+
 static void rs_size_smem(const skgpu_ctx *c, Op &op) {
     // staged path: (16 + chunk) frames x channels x 4 B of dynamic shared memory, capped at 96 KB so that
     // at least two CTAs stay resident per SM; longer chunks take the direct-from-HBM path.
@@ -527,6 +580,10 @@ static void rs_size_smem(const skgpu_ctx *c, Op &op) {
     uint64_t need = (uint64_t)(op.max_unit + 16u) * chmax * 4u;
     if (need <= 96u * 1024u) { op.smem_frames = op.max_unit + 16u; op.smem_bytes = (uint32_t)((need + 15u) & ~15ull); }
     else { op.smem_frames = 0; op.smem_bytes = 0; }
+    // the program-driven kernels need the staged path and mono / stereo streams
+    if (op.rs_prog && (op.smem_frames == 0 || (op.rs_channels != 1 && op.rs_channels != 2))) op.rs_prog = false;
+    if (op.rs_prog) op.smem_bytes += skc_prog_cap(op.rs_pd);
+    if (std::getenv("SKGPU_RS_TABLE")) op.rs_prog = false;   // profiling knob: force the table-driven kernels
 }
 
 extern "C" skgpu_rc skgpu_plan_add_resample(skgpu_plan *p, const skgpu_rs_item *items, uint32_t n, uint64_t results_off, uint32_t *op_out) {
@@ -550,6 +607,7 @@ extern "C" skgpu_rc skgpu_plan_add_resample(skgpu_plan *p, const skgpu_rs_item *
     op.max_unit = std::max(mx, 1u);
     op.rs_channels = ch;
     op.results_off = results_off;
+    op.rs_prog = n > 0 && rs_prog_dims(p->ctx, items, n, &op.rs_pd);
     rs_size_smem(p->ctx, op);
     if (op_out) *op_out = (uint32_t)p->ops.size();
     p->ops.push_back(op);
@@ -567,6 +625,11 @@ extern "C" skgpu_rc skgpu_plan_update_resample(skgpu_plan *p, uint32_t opi, cons
     if (rc) return rc;
     if (n && ch != op.rs_channels && op.rs_channels != 0) return fail(SKGPU_ERR_INVALID, "update changes the op's channel specialisation (%d -> %d)", op.rs_channels, ch);
     if (op.smem_frames && mx + 16u > op.smem_frames) return fail(SKGPU_ERR_INVALID, "update has a longer chunk (%u) than the op was sized for (%u)", mx, op.smem_frames - 16u);
+    if (op.rs_prog && n) {
+        ChainProgDims d{};
+        if (!rs_prog_dims(p->ctx, items, n, &d) || d.nblk > op.rs_pd.nblk || d.cap_seg > op.rs_pd.cap_seg || d.cap_exp > op.rs_pd.cap_exp)
+            return fail(SKGPU_ERR_INVALID, "update adds a stream configuration whose frame program exceeds what the op was sized for");
+    }
     CU(cudaStreamSynchronize(p->ctx->stream));
     if (n) memcpy(op.h_tab, items, n * sizeof(skgpu_rs_item));
     op.n = n;
@@ -988,10 +1051,13 @@ static skgpu_rc launch_ops(skgpu_plan *p, bool time_ops) {
         } else if (op.kind == OP_RESAMPLE) {
             const skgpu_rs_item *items = (const skgpu_rs_item *)op.d_tab;
             if (time_ops) { skgpu_rc rc = op_event(op, 0, false, s); if (rc) return rc; }
-            k_phase<skgpu_rs_item, false><<<(op.cap + PHASE_THREADS - 1) / PHASE_THREADS, PHASE_THREADS, 0, s>>>(op.d_hdr, items, nullptr, c->st, p->arena, op.results_off);
+            if (op.rs_prog) k_phase_prog<<<(op.cap + PHASE_THREADS - 1) / PHASE_THREADS, PHASE_THREADS, 0, s>>>(op.d_hdr, items, c->st, p->arena, op.results_off, op.rs_pd);
+            else k_phase<skgpu_rs_item, false><<<(op.cap + PHASE_THREADS - 1) / PHASE_THREADS, PHASE_THREADS, 0, s>>>(op.d_hdr, items, nullptr, c->st, p->arena, op.results_off);
             CU(cudaGetLastError());
             if (time_ops) { skgpu_rc rc = op_event(op, 0, true, s); if (rc) return rc; rc = op_event(op, 1, false, s); if (rc) return rc; }
-            if (op.rs_channels == 2) k_resample<2><<<op.cap, RS_THREADS, op.smem_bytes, s>>>(op.d_hdr, items, c->st, p->arena, op.smem_frames);
+            if (op.rs_prog && op.rs_channels == 2) k_resample_prog<2><<<op.cap, RS_THREADS, op.smem_bytes, s>>>(op.d_hdr, items, c->st, p->arena, op.smem_frames, op.rs_pd);
+            else if (op.rs_prog) k_resample_prog<1><<<op.cap, RS_THREADS, op.smem_bytes, s>>>(op.d_hdr, items, c->st, p->arena, op.smem_frames, op.rs_pd);
+            else if (op.rs_channels == 2) k_resample<2><<<op.cap, RS_THREADS, op.smem_bytes, s>>>(op.d_hdr, items, c->st, p->arena, op.smem_frames);
             else if (op.rs_channels == 1) k_resample<1><<<op.cap, RS_THREADS, op.smem_bytes, s>>>(op.d_hdr, items, c->st, p->arena, op.smem_frames);
             else k_resample<0><<<op.cap, RS_THREADS, op.smem_bytes, s>>>(op.d_hdr, items, c->st, p->arena, op.smem_frames);
             CU(cudaGetLastError());
@@ -1050,7 +1116,9 @@ extern "C" skgpu_rc skgpu_plan_finalize(skgpu_plan *p) {
     }
     for (auto &op : p->ops) {
         if (op.kind == OP_RESAMPLE && op.smem_bytes > 48u * 1024u) {
-            if (op.rs_channels == 2) CU(cudaFuncSetAttribute(k_resample<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)op.smem_bytes));
+            if (op.rs_prog && op.rs_channels == 2) CU(cudaFuncSetAttribute(k_resample_prog<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)op.smem_bytes));
+            else if (op.rs_prog) CU(cudaFuncSetAttribute(k_resample_prog<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)op.smem_bytes));
+            else if (op.rs_channels == 2) CU(cudaFuncSetAttribute(k_resample<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)op.smem_bytes));
             else if (op.rs_channels == 1) CU(cudaFuncSetAttribute(k_resample<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)op.smem_bytes));
             else CU(cudaFuncSetAttribute(k_resample<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)op.smem_bytes));
         }
