@@ -9,7 +9,7 @@ Metric: concurrent real-time 48 kHz stereo sessions = session-ticks processed pe
   value : device-resident (inputs already in HBM when the timed region starts), CUDA events, max over ranks
   e2e   : the same tick submitted through the C ABI with HOST (pinned) buffers: H2D of every input frame and
           D2H of every s16 result inside the timed region
-  roofline     : dominant kernel (k_resample), algorithmic bytes / CUDA-event time vs measured HBM peak
+  roofline     : dominant kernel (k_chain; k_resample with --unfused), algorithmic bytes / CUDA-event time vs measured HBM peak
   cpu_baseline : the oracle's reference-shaped CPU chain (oracle/sk_chain.c) on the box's host cores
 
 `--impl reference` times that CPU chain as the reference arm (the reference is Rust and cannot be built in this
@@ -33,8 +33,9 @@ sys.path.insert(0, ROOT)
 
 IN_RATE, OUT_RATE, CHANNELS, K_INPUTS = 44100, 48000, 2, 2
 TICK_MS = 20.0
-# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture (profiles/), or None
-TRAFFIC_NCU: dict = {}
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture
+# (profiles/r1_ncu_full_summary.csv: 1.100975 GB read + 252.58 MB written at 65,536 sessions x 2 inputs), or None
+TRAFFIC_NCU: dict = {"k_chain<2>": 1100975000 + 252580608}
 METRIC = "concurrent real-time 48 kHz stereo sessions (resample->mix->gain->s16, 20 ms ticks)"
 UNIT = "sessions"
 
@@ -269,7 +270,9 @@ def run_gpu(args) -> None:
             "gpu_launches": plan.launches_per_tick() * args.steps * 2,
             "clocks": clk,
             "roofline": {"bound": "hbm", "kernel": dom_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": TRAFFIC_NCU.get(dom_name), "algorithmic_bytes_per_launch": dom_bytes,
+                         "frac": achieved / peak,
+                         "traffic": TRAFFIC_NCU.get(dom_name) if (S == 65536 and K_INPUTS == 2) else None,
+                         "algorithmic_bytes_per_launch": dom_bytes,
                          "avg_launch_ms": main_ms, "launches_timed": n_main, "peak_source": peak_src},
             "kernels_ms": kernels_ms,
             "chain": {"algorithmic_bytes_per_tick": chain_bytes, "achieved_gbs": chain_bytes / (ms_per_step * 1e-3) / 1e9,
