@@ -25,17 +25,18 @@ def _align(x: int, a: int = 256) -> int:
 
 class ChainTick:
     def __init__(self, n_sessions: int, k_inputs: int, in_rate: int = 44100, channels: int = 2, device: int = 0,
-                 seed: int = 0, chunk_frames: int | None = None, fused: bool = True):
+                 seed: int = 0, chunk_frames: int | None = None, fused: bool = True, out_frames: int = OUT_FRAMES):
         """fused=True: one k_chain launch per tick (double-banked input, lagged recompute, no HBM intermediates);
         fused=False: the general unfused ops (k_resample -> device re-framing ring -> k_mix)."""
         self.fused = fused
+        self.F = out_frames   # output_frame_size of the resampler nodes = frame_samples_per_channel of the clocked mixer
         self.S, self.K, self.C = n_sessions, k_inputs, channels
         self.in_rate = in_rate
         self.chunk = chunk_frames if chunk_frames is not None else in_rate // 50  # frames per 20 ms tick
         self.n_streams = n_sessions * k_inputs
         self.ctx = L.Context(device=device, max_streams=self.n_streams, max_channels=channels, fifo_frames=0 if fused else 2048)
         self.in_stride = _align(self.chunk * channels * 4, 16)
-        self.out_stride = OUT_FRAMES * channels * 2
+        self.out_stride = self.F * channels * 2
         self.in_bytes = self.n_streams * self.in_stride
         self.bank_stride = _align(self.in_bytes) if fused else 0
         self.res_off = _align(self.in_bytes) + self.bank_stride
@@ -65,7 +66,7 @@ class ChainTick:
             cg["gain_idx"] = self.n_streams + np.arange(n_sessions, dtype=np.uint32)
             cg["out_channels"] = channels
             cg["flags"] = L.MIX_OUT_S16
-            self.op_chain = self.plan.add_chain(cg, cin, OUT_FRAMES, self.res_off)
+            self.op_chain = self.plan.add_chain(cg, cin, self.F, self.res_off)
             self.op_rs = self.op_mix = None
             self.plan.finalize()
             self.host_in = self.ctx.pinned(self.in_bytes, np.float32)
@@ -77,7 +78,7 @@ class ChainTick:
         items["flags"] = L.RS_TO_FIFO
         self.op_rs = self.plan.add_resample(items, self.res_off)
         inputs = np.zeros(self.n_streams, dtype=L.MIX_INPUT_DT)
-        inputs["n_frames"] = OUT_FRAMES
+        inputs["n_frames"] = self.F
         inputs["channels"] = channels
         inputs["flags"] = L.MIX_IN_UNIQUE | L.MIX_IN_FIFO
         inputs["gain_idx"] = np.arange(self.n_streams, dtype=np.uint32)
@@ -86,7 +87,7 @@ class ChainTick:
         groups["out_off"] = self.out_off + np.arange(n_sessions, dtype=np.uint64) * self.out_stride
         groups["first_input"] = np.arange(n_sessions, dtype=np.uint32) * k_inputs
         groups["n_inputs"] = k_inputs
-        groups["out_frames"] = OUT_FRAMES
+        groups["out_frames"] = self.F
         groups["out_channels"] = channels
         groups["flags"] = L.MIX_OUT_S16
         groups["gain_idx"] = self.n_streams + np.arange(n_sessions, dtype=np.uint32)
@@ -107,7 +108,7 @@ class ChainTick:
         self.host_in.reshape(self.n_streams, self.in_stride // 4)[:, : x.shape[1]] = x
         self.plan.submit(self.host_in, self.host_out, flags)
         self.plan.wait()
-        return self.host_out.reshape(self.S, OUT_FRAMES * self.C).copy()
+        return self.host_out.reshape(self.S, self.F * self.C).copy()
 
     def results(self) -> np.ndarray:
         return self.plan.download(self.res_off, self.res_bytes, L.CHAIN_RESULT_DT if self.fused else L.RS_RESULT_DT)
@@ -118,8 +119,9 @@ class ChainTick:
 
 
 def run_chain_gpu(n_sessions: int, k_inputs: int, ticks: int, seed: int, in_rate: int = 44100, channels: int = 2,
-                  graph: bool = False, fused: bool = True):
-    ct = ChainTick(n_sessions, k_inputs, in_rate=in_rate, channels=channels, seed=seed, fused=fused)
+                  graph: bool = False, fused: bool = True, chunk_frames: int | None = None, out_frames: int = OUT_FRAMES):
+    ct = ChainTick(n_sessions, k_inputs, in_rate=in_rate, channels=channels, seed=seed, fused=fused, chunk_frames=chunk_frames,
+                   out_frames=out_frames)
     try:
         outs = []
         for t in range(ticks):

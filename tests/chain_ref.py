@@ -14,8 +14,9 @@ OUT_FRAMES = 960
 
 
 def run_chain_oracle(n_sessions: int, k_inputs: int, ticks: int, seed: int, in_rate: int = 44100, channels: int = 2,
-                     inputs_fn=None):
-    chunk = in_rate // 50
+                     inputs_fn=None, chunk_frames: int | None = None, out_frames: int = OUT_FRAMES):
+    chunk = chunk_frames if chunk_frames is not None else in_rate // 50
+    OUT_FRAMES = out_frames
     n_streams = n_sessions * k_inputs
     in_gains = synth.gains(seed, n_streams, 0.25, 1.5)
     master = synth.gains(seed + 1, n_sessions, 0.5, 2.0)

@@ -478,6 +478,23 @@ def test_full_chain_bit_exact(k_inputs, channels, in_rate, fused):
     assert any(np.any(g != 0) for g in got)
 
 
+@pytest.mark.parametrize("in_rate,chunk,out_frames,channels,k_inputs", [
+    (44100, 441, 480, 2, 2), (44100, 1764, 1920, 2, 2), (44100, 2646, 2880, 2, 3), (22050, 441, 960, 1, 2),
+    (16000, 320, 960, 2, 2), (8000, 160, 960, 2, 1), (11025, 441, 1920, 2, 2), (44100, 2646, 2880, 1, 2), (96000, 1920, 960, 2, 2),
+    (44100, 882, 960, 2, 33),
+])
+def test_fused_chain_other_packet_sizes_and_ratios(in_rate, chunk, out_frames, channels, k_inputs):
+    """every valid output_frame_size with more than one kernel iteration per packet (F > 1024), up- and down-sampling
+    ratios whose programs contain slow (negative-position) run segments, and a session with more inputs than fit one
+    staging batch: s16 bytes identical to the oracle."""
+    S, T = 5, 6
+    got = chain.run_chain_gpu(S, k_inputs, T, seed=21, in_rate=in_rate, channels=channels, chunk_frames=chunk, out_frames=out_frames)
+    want = chain_ref.run_chain_oracle(S, k_inputs, T, seed=21, in_rate=in_rate, channels=channels, chunk_frames=chunk, out_frames=out_frames)
+    for t in range(T):
+        assert np.array_equal(got[t], want[t]), f"tick {t}: {(got[t] != want[t]).sum()} s16 samples differ"
+    assert any(np.any(g != 0) for g in got)
+
+
 def test_full_chain_graph_equals_stream_launch():
     a = chain.run_chain_gpu(8, 2, 6, seed=9, graph=False)
     b = chain.run_chain_gpu(8, 2, 6, seed=9, graph=True)
