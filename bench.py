@@ -163,6 +163,9 @@ def run_gpu(args) -> None:
     if world > 1:
         import torch.distributed as dist  # plumbing only: barrier + max-reduce of the timings (no data-path collective)
 
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"   # keep NCCL's version banner off stdout: rank 0 prints exactly one JSON line
+
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     def barrier():
