@@ -452,7 +452,7 @@ __global__ void __launch_bounds__(CH_THREADS, 4) k_chain(const OpHeader *__restr
                 }
                 __syncwarp();
                 if (lane == 0) {
-                    stage_header(S, grp, m, true, true, base_lane >= 0 ? 1u : 0u, n & 7u);
+                    stage_header(S, grp, m, true, true, base_lane >= 0 ? 1u : 0u, (n * 3u) & 7u);
                     // one thread issues the 3 bulk copies of every input, in summation order, from the prefetched records
                     uint8_t *dst = smem_raw + (size_t)stage * stage_bytes;
                     uint32_t bytes = 0;
@@ -509,7 +509,7 @@ __global__ void __launch_bounds__(CH_THREADS, 4) k_chain(const OpHeader *__restr
                     }
 #pragma unroll
                     for (int o = 16; o > 0; o >>= 1) bytes += __shfl_xor_sync(0xffffffffu, bytes, o);
-                    if (lane == 0) stage_header(S, grp, nb, b == 0u, b + 1u == n_batches, has_base, n & 7u);
+                    if (lane == 0) stage_header(S, grp, nb, b == 0u, b + 1u == n_batches, has_base, (n * 3u) & 7u);
                     __syncwarp();
                     if (lane == 0) mbar_expect_tx(&bar_full[stage], bytes);
                     if (++stage == nstages) { stage = 0; ephase ^= 1u; }
