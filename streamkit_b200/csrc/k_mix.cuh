@@ -9,7 +9,7 @@ namespace skgpu {
 // inputs would not be bit-exact). Coalescing comes from adjacent threads owning adjacent samples;
 // memory-level parallelism from the (unrolled) independent loads of successive inputs.
 
-constexpr int MIX_THREADS = 128;
+constexpr int MIX_THREADS = 96;    // tile = 384 samples: a 20 ms 48 kHz stereo frame (1920 samples) is exactly five full tiles
 constexpr int MIX_TILE = MIX_THREADS * 4;
 constexpr int MIX_MAX_INPUTS = 1024;
 
@@ -202,9 +202,18 @@ __global__ void __launch_bounds__(MIX_THREADS) k_mix(const OpHeader *__restrict_
         bool ok[4];
         if (sc == oc) {
             const uint32_t mix_len = mix_frames * oc;
-            const bool vec = !in.fifo && (s0 + 4u <= mix_len) && ((((uintptr_t)(in.ptr + s0)) & 15u) == 0);
+            // four consecutive samples of the packet: contiguous in a plain frame; in a ring when they do not wrap
+            // (ring sizes and packet sizes are multiples of 4 samples, so an aligned quad never straddles the end)
+            const float *src = in.ptr + s0;
+            if (in.fifo) {
+                const uint32_t ring_samples = (in.ring_mask + 1u) * oc;
+                const uint32_t pos = (in.ring_start * oc + s0) & (ring_samples - 1u);   // ring_mask + 1 is a power of two; oc is 1 or 2 here
+                src = in.ptr + pos;
+            }
+            const bool pow2_oc = (oc & (oc - 1u)) == 0u;
+            const bool vec = (!in.fifo || pow2_oc) && (s0 + 4u <= mix_len) && ((((uintptr_t)src) & 15u) == 0);
             if (vec) {
-                const float4 t = ldg_stream_f4(reinterpret_cast<const float4 *>(in.ptr + s0));
+                const float4 t = ldg_stream_f4(reinterpret_cast<const float4 *>(src));
                 v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
                 ok[0] = ok[1] = ok[2] = ok[3] = true;
             } else {
