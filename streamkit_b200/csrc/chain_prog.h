@@ -33,7 +33,7 @@
 // One segment = two 16-byte shared-memory loads in the consumer. FAST run segments lie in one binade [2^e, 2^(e+1)),
 // 0 <= e <= 17, so with hi = high word of x:  floor(x) as a double = {hi & himask, 0}  and the byte offset of buffer
 // frame floor(x) is ((hi & himask) >> sh) - cs   (sh = 20 - e - log2(frame_bytes), cs = (1022 + e) << (20 - sh)).
-struct alignas(16) ChainSeg {
+struct alignas(32) ChainSeg {
     double x0, delta;   // run: x_j = fma((double)(j - j0), delta, x0)
     uint32_t jj;        // j0 | j1 << 16
     uint32_t himask;    // SKC_KIND_E, SKC_KIND_SLOW, or the FAST mask
@@ -45,9 +45,10 @@ struct alignas(16) ChainExp2 { ChainExp a, b; };  // the builder stores explicit
                                                    // writes its own record, so every store is a scattered request and wide
                                                    // stores halve their number (k_phase_chain is bound by them)
 
+SK_HD uint32_t skc_map_bytes(uint32_t nblk) { return (nblk * 2u + 31u) & ~31u; }   // segments stay 32-byte aligned
 struct ChainProgDims {
     uint32_t nblk;       // ceil(F / 32)
-    uint32_t map_bytes;  // nblk * 2 rounded up to 16
+    uint32_t map_bytes;  // skc_map_bytes(nblk)
     uint32_t cap_seg;
     uint32_t cap_exp;    // even
 };
@@ -91,9 +92,15 @@ struct SkcBuilder {   // appends segments in increasing j and completes the bloc
 SK_HD void skc_append(SkcBuilder &b, uint32_t j0, uint32_t j1, double x0, double delta, uint32_t himask, uint32_t aux, uint32_t sh) {
     if (b.n_seg >= b.d.cap_seg || b.n_seg >= 255u) { b.status |= SKC_ST_OVERFLOW; return; }
     const uint32_t s = b.n_seg++;
+#if defined(__CUDA_ARCH__)
+    // one 256-bit store (STG.256, sm_100): k_phase_chain is bound by the number of scattered store requests
+    asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(b.segs + s), "r"(__double2loint(x0)), "r"(__double2hiint(x0)),
+                 "r"(__double2loint(delta)), "r"(__double2hiint(delta)), "r"(j0 | (j1 << 16)), "r"(himask), "r"(aux), "r"(sh) : "memory");
+#else
     ChainSeg sg;
     sg.x0 = x0; sg.delta = delta; sg.jj = j0 | (j1 << 16); sg.himask = himask; sg.aux = aux; sg.sh = sh;
     b.segs[s] = sg;
+#endif
     while (b.bcur < b.d.nblk) {
         const uint32_t bs = 32u * b.bcur;
         const uint32_t be = (bs + 31u < b.F - 1u) ? bs + 31u : b.F - 1u;

@@ -314,19 +314,16 @@ __global__ void __launch_bounds__(PHASE_CHAIN_THREADS, 14) k_phase_chain(const O
     if (pres && !emit && count0 >= 1u) {
         for (uint32_t e = 0; e < 16u * ch; ++e) hist_dst[e] = prev_g[(size_t)(N - 16u) * ch + e];
     }
-    ChainRec r;
-    r.cons.gain = in.gain_idx != SKGPU_NO_GAIN ? gains[in.gain_idx] : 1.0f;
-    r.cons.sc = ch;
-    r.prog_src = slot_side(st, slot, par_old);
-    r.prev_g = prev_g;
-    r.cur_g = cur_g;
-    r.hist_dst = hist_dst;
-    r.chunk_bytes = N * fb;
-    r.head_bytes = head * fb;
-    r.flags = (emit ? CR_EMIT : 0u) | ((in.flags & SKGPU_MIX_IN_UNIQUE) ? CR_UNIQUE : 0u) | ((((N * fb) | (head * fb)) & 15u) ? CR_UNALIGNED : 0u);
-    r.tail_off = (N - 16u) * ch;
-    r.pad[0] = r.pad[1] = 0u;
-    recs[i] = r;
+    // the 64-byte ChainRec, written with two 256-bit stores (the kernel is bound by scattered store requests)
+    const float gain = in.gain_idx != SKGPU_NO_GAIN ? gains[in.gain_idx] : 1.0f;
+    const uint64_t a_prog = (uint64_t)(uintptr_t)slot_side(st, slot, par_old), a_prev = (uint64_t)(uintptr_t)prev_g,
+                   a_cur = (uint64_t)(uintptr_t)cur_g, a_hist = (uint64_t)(uintptr_t)hist_dst;
+    const uint32_t flags = (emit ? CR_EMIT : 0u) | ((in.flags & SKGPU_MIX_IN_UNIQUE) ? CR_UNIQUE : 0u) | ((((N * fb) | (head * fb)) & 15u) ? CR_UNALIGNED : 0u);
+    uint32_t *dst = reinterpret_cast<uint32_t *>(recs + i);
+    asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(dst), "r"(__float_as_uint(gain)), "r"(ch), "r"((uint32_t)a_prog),
+                 "r"((uint32_t)(a_prog >> 32)), "r"((uint32_t)a_prev), "r"((uint32_t)(a_prev >> 32)), "r"((uint32_t)a_cur), "r"((uint32_t)(a_cur >> 32)) : "memory");
+    asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(dst + 8), "r"((uint32_t)a_hist), "r"((uint32_t)(a_hist >> 32)), "r"(N * fb),
+                 "r"(head * fb), "r"(flags), "r"((N - 16u) * ch), "r"(0u), "r"(0u) : "memory");
 }
 
 template <int OC, int ITERS>  // output channels (1 | 2); ITERS = ceil(F / 1024)

@@ -77,7 +77,7 @@ extern "C" uint64_t skc_check_stream(double ratio, uint32_t chunk, uint32_t F, u
     const uint32_t fb = channels * 4u, head = std::min(32u, chunk);
     ChainProgDims d;
     d.nblk = (F + 31u) / 32u;
-    d.map_bytes = (d.nblk * 2u + 15u) & ~15u;
+    d.map_bytes = skc_map_bytes(d.nblk);
     d.cap_seg = cap_seg;
     d.cap_exp = cap_exp;
     std::vector<uint8_t> rec[2] = {std::vector<uint8_t>(skc_prog_cap(d) + 64), std::vector<uint8_t>(skc_prog_cap(d) + 64)};

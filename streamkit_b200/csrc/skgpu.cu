@@ -541,7 +541,7 @@ static bool rs_prog_dims(const skgpu_ctx *c, const skgpu_rs_item *items, uint32_
         if (fcap > 60000u) return false;   // segment bounds are 16-bit
         ChainProgDims big{};
         big.nblk = (fcap + 31u) / 32u;
-        big.map_bytes = (big.nblk * 2u + 15u) & ~15u;
+        big.map_bytes = skc_map_bytes(big.nblk);
         big.cap_seg = 254u;
         big.cap_exp = 8192u;
         std::vector<uint8_t> scratch(skc_prog_cap(big) + 16u);
@@ -565,7 +565,7 @@ static bool rs_prog_dims(const skgpu_ctx *c, const skgpu_rs_item *items, uint32_
     }
     ChainProgDims d{};
     d.nblk = (std::max(max_frames, 32u) + 31u) / 32u;
-    d.map_bytes = (d.nblk * 2u + 15u) & ~15u;
+    d.map_bytes = skc_map_bytes(d.nblk);
     d.cap_seg = (need_seg + 5u) & ~1u;
     d.cap_exp = (need_exp + 9u) & ~1u;
     if (d.cap_seg > 254u || skc_prog_cap(d) > SK_SIDE_STRIDE) return false;
@@ -783,7 +783,7 @@ extern "C" uint64_t skgpu_plan_tick_count(const skgpu_plan *p) { return p ? p->t
 static bool prog_bounds(double t, int32_t end_idx, uint32_t N, uint32_t F, uint32_t *need_seg, uint32_t *need_exp) {
     ChainProgDims big{};
     big.nblk = (F + 31u) / 32u;
-    big.map_bytes = (big.nblk * 2u + 15u) & ~15u;
+    big.map_bytes = skc_map_bytes(big.nblk);
     big.cap_seg = 254u;
     big.cap_exp = 8192u;
     std::vector<uint8_t> scratch(skc_prog_cap(big));
@@ -878,7 +878,7 @@ static skgpu_rc validate_chain(const skgpu_plan *p, const skgpu_chain_group *g, 
     {
         ChainProgDims d{};
         d.nblk = (F + 31u) / 32u;
-        d.map_bytes = (d.nblk * 2u + 15u) & ~15u;
+        d.map_bytes = skc_map_bytes(d.nblk);
         d.cap_seg = *cap_seg;
         d.cap_exp = *cap_exp;
         if (*cap_seg > 254u || skc_prog_cap(d) > CH_PROG_MAX)
@@ -893,7 +893,7 @@ static void chain_size_smem(Op &op, uint32_t max_k, uint32_t chunk_cap, uint32_t
     ChainDims dm{};
     dm.chunk_cap = chunk_cap;
     dm.prog.nblk = (op.chain_F + 31u) / 32u;
-    dm.prog.map_bytes = (dm.prog.nblk * 2u + 15u) & ~15u;
+    dm.prog.map_bytes = skc_map_bytes(dm.prog.nblk);
     dm.prog.cap_seg = cap_seg;
     dm.prog.cap_exp = cap_exp;
     dm.max_k = std::max(max_k, 1u);
