@@ -69,10 +69,13 @@ SK_HD void skc_split(double x, int32_t *fl, float *frac) {
 #endif
 }
 
-SK_HD void skc_store16(uint8_t *dst, uint64_t lo, uint64_t hi) {
-    struct alignas(16) U2 { uint64_t lo, hi; } v;
-    v.lo = lo; v.hi = hi;
-    *reinterpret_cast<U2 *>(dst) = v;
+SK_HD void skc_store32(uint8_t *dst, const uint64_t (&w)[4]) {   // one 256-bit store on the device (STG.256, sm_100)
+#if defined(__CUDA_ARCH__)
+    asm volatile("st.global.v4.b64 [%0], {%1, %2, %3, %4};" ::"l"(dst), "l"(w[0]), "l"(w[1]), "l"(w[2]), "l"(w[3]) : "memory");
+#else
+    uint64_t *d = reinterpret_cast<uint64_t *>(dst);
+    d[0] = w[0]; d[1] = w[1]; d[2] = w[2]; d[3] = w[3];
+#endif
 }
 
 struct SkcBuilder {   // appends segments in increasing j and completes the block map on the fly
@@ -82,13 +85,23 @@ struct SkcBuilder {   // appends segments in increasing j and completes the bloc
     ChainProgDims d;
     uint32_t F, frame_bytes;
     uint32_t n_seg, n_exp, bcur, first_cur, status;
-    uint64_t map_lo, map_hi; // eight map entries are collected and stored as one 16-byte word
+    uint64_t map_w[4];       // sixteen map entries are collected and stored as one 32-byte word
     ChainExp exp_pend;       // first entry of an aligned pair of explicit entries (stored with the second one)
     // the open explicit segment (consecutive explicit frames share one segment)
     uint32_t e_j0, e_first;
     bool e_open;
 };
 
+SK_HD void skc_map_put(SkcBuilder &b, uint32_t s) {   // entry of block b.bcur: (first_cur, s); advances bcur
+    const uint64_t ent = (uint64_t)(b.first_cur | (s << 8)) << (16u * (b.bcur & 3u));
+    const uint32_t w = (b.bcur >> 2) & 3u;
+    if (w == 0u) b.map_w[0] |= ent; else if (w == 1u) b.map_w[1] |= ent; else if (w == 2u) b.map_w[2] |= ent; else b.map_w[3] |= ent;
+    if ((b.bcur & 15u) == 15u) {
+        skc_store32(reinterpret_cast<uint8_t *>(b.map) + (b.bcur >> 4) * 32u, b.map_w);
+        b.map_w[0] = b.map_w[1] = b.map_w[2] = b.map_w[3] = 0;
+    }
+    ++b.bcur;
+}
 SK_HD void skc_append(SkcBuilder &b, uint32_t j0, uint32_t j1, double x0, double delta, uint32_t himask, uint32_t aux, uint32_t sh) {
     if (b.n_seg >= b.d.cap_seg || b.n_seg >= 255u) { b.status |= SKC_ST_OVERFLOW; return; }
     const uint32_t s = b.n_seg++;
@@ -106,17 +119,11 @@ SK_HD void skc_append(SkcBuilder &b, uint32_t j0, uint32_t j1, double x0, double
         const uint32_t be = (bs + 31u < b.F - 1u) ? bs + 31u : b.F - 1u;
         if (bs >= j0 && bs < j1) b.first_cur = s;
         if (be >= j1) break;
-        const uint64_t ent = (uint64_t)(b.first_cur | (s << 8)) << (16u * (b.bcur & 3u));
-        if (b.bcur & 4u) b.map_hi |= ent; else b.map_lo |= ent;
-        if ((b.bcur & 7u) == 7u) {
-            skc_store16(reinterpret_cast<uint8_t *>(b.map) + (b.bcur >> 3) * 16u, b.map_lo, b.map_hi);
-            b.map_lo = 0; b.map_hi = 0;
-        }
-        ++b.bcur;
+        skc_map_put(b, s);
     }
 }
 SK_HD void skc_flush_map(SkcBuilder &b) {
-    if (b.bcur & 7u) skc_store16(reinterpret_cast<uint8_t *>(b.map) + (b.bcur >> 3) * 16u, b.map_lo, b.map_hi);
+    if (b.bcur & 15u) skc_store32(reinterpret_cast<uint8_t *>(b.map) + (b.bcur >> 4) * 32u, b.map_w);
     if (b.n_exp & 1u) b.exps[b.n_exp - 1u] = b.exp_pend;   // an unpaired last explicit entry
 }
 SK_HD void skc_close_exp(SkcBuilder &b, uint32_t j_end) {
@@ -169,7 +176,7 @@ struct SkcStream {
         b.segs = reinterpret_cast<ChainSeg *>(rec_new + skc_seg_off(d));
         b.exps = reinterpret_cast<ChainExp *>(rec_new + skc_exp_off(d));
         b.d = d; b.F = F; b.frame_bytes = frame_bytes;
-        b.n_seg = 0; b.n_exp = 0; b.bcur = 0; b.first_cur = 0; b.status = 0; b.map_lo = 0; b.map_hi = 0;
+        b.n_seg = 0; b.n_exp = 0; b.bcur = 0; b.first_cur = 0; b.status = 0; b.map_w[0] = b.map_w[1] = b.map_w[2] = b.map_w[3] = 0;
         b.exp_pend.aoff = 0; b.exp_pend.frac = 0.0f;
         b.e_j0 = 0; b.e_first = 0; b.e_open = false;
         tail = tail_; n_tail = n_tail_; tail_cap = tail_cap_; n_frames_prev = n_frames_prev_; head_frames = head_frames_;
@@ -282,13 +289,7 @@ struct SkcStream {
         if (b.n_seg > 0u) {   // the block the last segment left open ends with the record
             const uint32_t s = b.n_seg - 1u;
             while (b.bcur < b.d.nblk && b.bcur * 32u < c) {
-                const uint64_t ent = (uint64_t)(b.first_cur | (s << 8)) << (16u * (b.bcur & 3u));
-                if (b.bcur & 4u) b.map_hi |= ent; else b.map_lo |= ent;
-                if ((b.bcur & 7u) == 7u) {
-                    skc_store16(reinterpret_cast<uint8_t *>(b.map) + (b.bcur >> 3) * 16u, b.map_lo, b.map_hi);
-                    b.map_lo = 0; b.map_hi = 0;
-                }
-                ++b.bcur;
+                skc_map_put(b, s);
                 b.first_cur = s;
             }
         }
