@@ -129,8 +129,15 @@ __global__ void __launch_bounds__(CVT_THREADS) k_convert(const OpHeader *__restr
 #pragma unroll
                         for (int q = 0; q < 8; ++q) f[q] = __fmul_rn(f[q], g);
                     }
-                    stg_stream_f4(out4 + 2 * vi, make_float4(f[0], f[1], f[2], f[3]));
-                    stg_stream_f4(out4 + 2 * vi + 1, make_float4(f[4], f[5], f[6], f[7]));
+                    // 8 floats = one 32-byte sector per thread: a single 256-bit store (STG.256, sm_100) instead of two
+                    // half-sector stores
+                    if ((((uintptr_t)(out4 + 2 * vi)) & 31u) == 0) {
+                        asm volatile("st.global.L1::no_allocate.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(out4 + 2 * vi), "f"(f[0]), "f"(f[1]),
+                                     "f"(f[2]), "f"(f[3]), "f"(f[4]), "f"(f[5]), "f"(f[6]), "f"(f[7]) : "memory");
+                    } else {
+                        stg_stream_f4(out4 + 2 * vi, make_float4(f[0], f[1], f[2], f[3]));
+                        stg_stream_f4(out4 + 2 * vi + 1, make_float4(f[4], f[5], f[6], f[7]));
+                    }
                 }
             }
             const uint32_t t0 = v_end * 8;

@@ -495,6 +495,16 @@ def test_fused_chain_other_packet_sizes_and_ratios(in_rate, chunk, out_frames, c
     assert any(np.any(g != 0) for g in got)
 
 
+def test_fused_chain_long_run_stays_bit_exact():
+    """400 ticks (8 s of audio): the f64 phase state, the carry bookkeeping and the alternating side records of the
+    fused path must track the oracle tick for tick (a drifting phase would flip a packet boundary sooner or later)."""
+    S, K, T = 2, 2, 400
+    got = chain.run_chain_gpu(S, K, T, seed=31)
+    want = chain_ref.run_chain_oracle(S, K, T, seed=31)
+    bad = [t for t in range(T) if not np.array_equal(got[t], want[t])]
+    assert not bad, f"first differing ticks: {bad[:5]}"
+
+
 def test_full_chain_graph_equals_stream_launch():
     a = chain.run_chain_gpu(8, 2, 6, seed=9, graph=False)
     b = chain.run_chain_gpu(8, 2, 6, seed=9, graph=True)
