@@ -23,7 +23,7 @@
 #define SKC_TAB_PREFIX 24u        // capacities of the thread-private phase table the program is built from (host and
 #define SKC_TAB_RUNS 24u          // device must use the same ones: they shape the table, hence the program)
 #endif
-#define SKC_MIN_RUN 8u            // shorter run pieces are stored explicitly (one pass of the consumer costs ~25 instructions)
+#define SKC_MIN_RUN 16u           // shorter run pieces are stored explicitly (one pass of the consumer costs ~25 instructions)
 #define SKC_ST_OVERFLOW 2u        // status bit1: a table of the record overflowed
 #define SKC_ST_UNSUPPORTED 4u     // status bit2: the packet needs frames the kernel does not stage
 #define SKC_KIND_E 0u             // ChainSeg.himask: explicit segment
