@@ -262,12 +262,13 @@ __global__ void __launch_bounds__(PHASE_CHAIN_THREADS, 14) k_phase_chain(const O
         // ---- rubato's phase recurrence for this chunk, streamed into the frame programs (chain_prog.h): the tail of the
         // pending packet (old record) and part 1 of the next packet (new record). A packet is emitted when
         // carry + n_cur >= F (resampler.rs:425-428), i.e. when this chunk has at least kd = F - carry outputs.
-        const uint32_t n_prev = count0 >= 1u ? rec.n_out[par_old] : 0u;
+        // (static field accesses only: the record stays in registers and is written back with two 256-bit stores)
+        const uint32_t n_prev = count0 >= 1u ? (par_old ? rec.n_out[1] : rec.n_out[0]) : 0u;
         if (carry > n_prev) status |= SKC_ST_UNSUPPORTED;                 // carried frames span more than one chunk
         if ((rec.overflow >> par_old) & 1u) status |= SKC_ST_OVERFLOW;    // the record the packet would execute is incomplete
         const bool pending = count0 >= 1u;
         uint32_t kd = pending ? F - min(carry, F) : 0u;
-        const uint32_t ne_old = rec.n_prefix[par_old];
+        const uint32_t ne_old = par_old ? rec.n_prefix[1] : rec.n_prefix[0];
         ChainExp *tail = reinterpret_cast<ChainExp *>(slot_side(st, slot, par_old) + skc_exp_off(dm.prog)) + ne_old;
         uint8_t *rec_new = slot_side(st, slot, par_new);
         SkcStream sb;
@@ -289,14 +290,16 @@ __global__ void __launch_bounds__(PHASE_CHAIN_THREADS, 14) k_phase_chain(const O
         const uint32_t avail = carry + n_cur;
         const uint32_t new_carry = (avail >= F) ? avail - F : avail;
         if (new_carry > n_cur) status |= 1u;                              // backlog: a second packet is pending
-        rec.last_index = __dsub_rn(idx_end, (double)rec.chunk);           // self.last_index = idx - chunk_size as f64
-        rec.chunk_count = count0 + 1u;
-        rec.n_out[par_new] = n_cur;
-        rec.n_prefix[par_new] = (uint16_t)n_exp;
-        rec.n_runs[par_new] = (uint16_t)n_seg;
-        rec.overflow = (rec.overflow & ~(1u << par_new)) | ((st_new ? 1u : 0u) << par_new);
-        rec.carry = new_carry;
-        *recp = rec;
+        const double li = __dsub_rn(idx_end, (double)rec.chunk);           // self.last_index = idx - chunk_size as f64
+        const uint32_t n_out0 = par_new ? rec.n_out[0] : n_cur, n_out1 = par_new ? n_cur : rec.n_out[1];
+        const uint32_t np01 = par_new ? ((uint32_t)rec.n_prefix[0] | (n_exp << 16)) : ((n_exp & 0xFFFFu) | ((uint32_t)rec.n_prefix[1] << 16));
+        const uint32_t nr01 = par_new ? ((uint32_t)rec.n_runs[0] | (n_seg << 16)) : ((n_seg & 0xFFFFu) | ((uint32_t)rec.n_runs[1] << 16));
+        const uint32_t ovfl = (rec.overflow & ~(1u << par_new)) | ((st_new ? 1u : 0u) << par_new);
+        uint32_t *rw = reinterpret_cast<uint32_t *>(recp);
+        asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(rw), "r"(__double2loint(rec.t_ratio)), "r"(__double2hiint(rec.t_ratio)),
+                     "r"(__double2loint(li)), "r"(__double2hiint(li)), "r"(rec.chunk), "r"(rec.channels), "r"(count0 + 1u), "r"(new_carry) : "memory");
+        asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(rw + 8), "r"(n_out0), "r"(n_out1), "r"(np01), "r"(nr01),
+                     "r"((uint32_t)rec.end_idx), "r"(ovfl), "r"(0u), "r"(0u) : "memory");
     }
     skgpu_chain_result res;
     res.emitted = emit;
