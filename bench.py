@@ -220,6 +220,16 @@ def run_gpu(args) -> None:
         mix_ms, _ = plan.op_time(ct.op_mix, 0)
         kernels_ms = {"k_phase": phase_ms, "k_resample": main_ms, "k_mix+k_fifo_commit": mix_ms}
 
+    # ---- per-tick device latency (added latency per 20 ms tick, p99 over >= 500 ticks): one tick at a time,
+    # kernels only (upload-done -> results ready for the read-back), CUDA events inside the library
+    lat = []
+    for _ in range(args.latency_ticks):
+        plan.submit(None, None, L.SUBMIT_NO_H2D | L.SUBMIT_NO_D2H)
+        lat.append(plan.wait().kernels_ms)
+    lat.sort()
+    latency = {"ticks": len(lat), "p50_ms": lat[len(lat) // 2], "p99_ms": lat[min(len(lat) - 1, int(len(lat) * 0.99))], "max_ms": lat[-1],
+               "what": "device time of one tick's kernels at sessions_per_gpu sessions, submitted and awaited tick by tick"} if lat else None
+
     # ---- end-to-end region: every step copies its inputs from pinned host memory and reads the s16 result back
     for _ in range(max(1, min(args.warmup, 3))):
         plan.submit(ct.host_in, ct.host_out, 0)
@@ -280,7 +290,7 @@ def run_gpu(args) -> None:
             "kernels_ms": kernels_ms,
             "chain": {"algorithmic_bytes_per_tick": chain_bytes, "achieved_gbs": chain_bytes / (ms_per_step * 1e-3) / 1e9,
                       "frac_of_peak": chain_bytes / (ms_per_step * 1e-3) / 1e9 / peak,
-                      "device_ms_per_tick": ms_per_step, "latency_budget_ms": 2.0},
+                      "device_ms_per_tick": ms_per_step, "latency_budget_ms": 2.0, "latency": latency},
             "cpu_baseline": {"value": cpu_value, "unit": UNIT, "cores": cores, "kind": "port",
                              "sample": "%d sessions x %d ticks on %d host threads (oracle/sk_chain.c)" % (cpu_sessions, cpu_ticks, cores)},
             "device": {"name": name, "sms": sms, "cc": "%d.%d" % (cc_ma, cc_mi)},
@@ -300,6 +310,7 @@ def main() -> None:
     ap.add_argument("--sessions", type=int, default=65536, help="sessions per GPU (weak scaling)")
     ap.add_argument("--unfused", action="store_true", help="use the general unfused ops (k_resample -> ring -> k_mix)")
     ap.add_argument("--ref-sessions", type=int, default=8192, help="bounded session sample of the CPU arm")
+    ap.add_argument("--latency-ticks", type=int, default=500, help="ticks of the per-tick latency measurement (0 = skip)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
