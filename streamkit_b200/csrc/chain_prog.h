@@ -20,9 +20,8 @@
 #include "phase_runs.h"
 
 #ifndef SKC_TAB_PREFIX
-#define SKC_TAB_PREFIX 24u        // capacities of the thread-private phase table the program is built from (host and
-#define SKC_TAB_RUNS 24u          // device must use the same ones: they shape the table, hence the program)
-#endif
+#define SKC_TAB_PREFIX 24u        // prefix capacity handed to the phase generator (host and device must use the same
+#endif                            // value: it decides where the generator switches from prefix elements to run entries)
 #define SKC_MIN_RUN 16u           // shorter run pieces are stored explicitly (one pass of the consumer costs ~25 instructions)
 #define SKC_ST_OVERFLOW 2u        // status bit1: a table of the record overflowed
 #define SKC_ST_UNSUPPORTED 4u     // status bit2: the packet needs frames the kernel does not stage

@@ -84,11 +84,6 @@ __device__ __forceinline__ uint4 ldg_stream_u4(const uint4 *p) {
                  : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
     return r;
 }
-__device__ __forceinline__ float2 ldg_stream_f2(const float2 *p) {
-    float2 r;
-    asm volatile("ld.global.nc.L1::no_allocate.v2.f32 {%0,%1}, [%2];" : "=f"(r.x), "=f"(r.y) : "l"(p));
-    return r;
-}
 __device__ __forceinline__ void stg_stream_f4(float4 *p, float4 v) {
     asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
@@ -141,9 +136,6 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
 }
 
 // ---- cp.async (LDGSTS): asynchronous global -> shared copies that need no destination registers
-__device__ __forceinline__ void cp_async4(void *dst_smem, const void *src) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory");
-}
 __device__ __forceinline__ void cp_async8(void *dst_smem, const void *src) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory");
 }
@@ -187,42 +179,6 @@ __device__ __forceinline__ double phase_eval_smem(const SmemPhase *T, double t, 
     const SkRun rn = T->runs[r];
     if (k < rn.k_e) return __fma_rn((double)(k - rn.k_a), rn.delta, rn.x_a);
     return __dadd_rn(__fma_rn((double)(rn.k_e - 1u - rn.k_a), rn.delta, rn.x_a), t);  // gap element
-}
-
-// ---- pointer-based view of a staged phase table (k_chain sizes the staging area per op, not for the worst case)
-struct PhaseView {
-    const double *prefix;
-    const SkRun *runs;
-    uint32_t n_out, n_prefix, n_runs;
-};
-
-__device__ __forceinline__ double pv_eval(const PhaseView &T, double t, uint32_t k) {
-    if (k < T.n_prefix) return T.prefix[k];
-    if (T.n_runs == 0u) return 0.0;   // empty table (a stream's first chunk has no predecessor): value is never used
-    uint32_t r = T.n_runs - 1u;
-    while (r > 0u && T.runs[r].k_a > k) --r;
-    const SkRun rn = T.runs[r];
-    if (k < rn.k_e) return __fma_rn((double)(k - rn.k_a), rn.delta, rn.x_a);
-    return __dadd_rn(__fma_rn((double)(rn.k_e - 1u - rn.k_a), rn.delta, rn.x_a), t);  // gap element
-}
-
-// idx of 4 consecutive outputs k0..k0+3, each index clamped to n_out - 1 (callers discard the clamped ones)
-__device__ __forceinline__ void pv_eval4(const PhaseView &T, double t, uint32_t k0, double *x) {
-    if (k0 >= T.n_prefix && T.n_runs > 0u) {
-        uint32_t r = T.n_runs - 1u;
-        while (r > 0u && T.runs[r].k_a > k0) --r;
-        const SkRun rn = T.runs[r];
-        if (k0 + 3u < rn.k_e) {   // all four inside one run: consecutive members differ by exactly delta
-            x[0] = __fma_rn((double)(k0 - rn.k_a), rn.delta, rn.x_a);
-            x[1] = __dadd_rn(x[0], rn.delta);
-            x[2] = __dadd_rn(x[1], rn.delta);
-            x[3] = __dadd_rn(x[2], rn.delta);
-            return;
-        }
-    }
-    const uint32_t last = T.n_out - 1u;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) x[i] = pv_eval(T, t, min(k0 + (uint32_t)i, last));
 }
 
 // split idx into buffer position (floor(idx) + 16 = start_idx + 2*POLYNOMIAL_LEN) and f32 fraction

@@ -14,15 +14,10 @@ namespace skgpu {
 
 constexpr int PHASE_THREADS = 64;
 
-// Item is skgpu_rs_item (resample op; one result per item) or skgpu_chain_input (chain op; no result here)
-template <class Item, bool CHAIN>
-__global__ void __launch_bounds__(PHASE_THREADS) k_phase(const OpHeader *__restrict__ hdr, const Item *__restrict__ items,
-                                                         const uint8_t *__restrict__ present, SlotTables st,
+__global__ void __launch_bounds__(PHASE_THREADS) k_phase(const OpHeader *__restrict__ hdr, const skgpu_rs_item *__restrict__ items, SlotTables st,
                                                          uint8_t *__restrict__ arena, uint64_t results_off) {
     const uint32_t i = blockIdx.x * PHASE_THREADS + threadIdx.x;
-    const uint32_t n_items = CHAIN ? hdr->count2 : hdr->count;
-    if (i >= n_items) return;
-    if (present && !present[i]) return;  // stream delivered no chunk this tick: state untouched
+    if (i >= hdr->count) return;
     const uint32_t slot = items[i].slot;
     SlotRec *rec = st.rec + slot;
     const uint32_t c = rec->chunk_count;
@@ -36,18 +31,16 @@ __global__ void __launch_bounds__(PHASE_THREADS) k_phase(const OpHeader *__restr
     rec->n_prefix[par] = (uint16_t)T->n_prefix;
     rec->n_runs[par] = (uint16_t)T->n_runs;
     rec->overflow = (rec->overflow & ~(1u << par)) | ((T->overflow ? 1u : 0u) << par);
-    if (!CHAIN) {
-        const skgpu_rs_item *it = reinterpret_cast<const skgpu_rs_item *>(items) + i;
-        skgpu_rs_result res;
-        res.out_frames = n;
-        res.status = 0;
-        if (!(it->flags & SKGPU_RS_TO_FIFO) && n > it->out_cap_frames) {
-            res.out_frames = it->out_cap_frames;
-            res.status = 1;
-        }
-        if (T->overflow) res.status = 2;
-        reinterpret_cast<skgpu_rs_result *>(arena + results_off)[i] = res;
+    const skgpu_rs_item *it = items + i;
+    skgpu_rs_result res;
+    res.out_frames = n;
+    res.status = 0;
+    if (!(it->flags & SKGPU_RS_TO_FIFO) && n > it->out_cap_frames) {
+        res.out_frames = it->out_cap_frames;
+        res.status = 1;
     }
+    if (T->overflow) res.status = 2;
+    reinterpret_cast<skgpu_rs_result *>(arena + results_off)[i] = res;
 }
 
 // ------------------------------------------------------------------ interpolation

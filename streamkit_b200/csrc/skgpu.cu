@@ -1052,7 +1052,7 @@ static skgpu_rc launch_ops(skgpu_plan *p, bool time_ops) {
             const skgpu_rs_item *items = (const skgpu_rs_item *)op.d_tab;
             if (time_ops) { skgpu_rc rc = op_event(op, 0, false, s); if (rc) return rc; }
             if (op.rs_prog) k_phase_prog<<<(op.cap + PHASE_THREADS - 1) / PHASE_THREADS, PHASE_THREADS, 0, s>>>(op.d_hdr, items, c->st, p->arena, op.results_off, op.rs_pd);
-            else k_phase<skgpu_rs_item, false><<<(op.cap + PHASE_THREADS - 1) / PHASE_THREADS, PHASE_THREADS, 0, s>>>(op.d_hdr, items, nullptr, c->st, p->arena, op.results_off);
+            else k_phase<<<(op.cap + PHASE_THREADS - 1) / PHASE_THREADS, PHASE_THREADS, 0, s>>>(op.d_hdr, items, c->st, p->arena, op.results_off);
             CU(cudaGetLastError());
             if (time_ops) { skgpu_rc rc = op_event(op, 0, true, s); if (rc) return rc; rc = op_event(op, 1, false, s); if (rc) return rc; }
             if (op.rs_prog && op.rs_channels == 2) k_resample_prog<2><<<op.cap, RS_THREADS, op.smem_bytes, s>>>(op.d_hdr, items, c->st, p->arena, op.smem_frames, op.rs_pd);

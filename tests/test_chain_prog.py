@@ -52,7 +52,7 @@ def test_steady_state_44k1_program_is_small(check):
     """BASELINE config #5: the record the mixing kernel stages per stream-tick stays below 1 KB."""
     bad, packets, max_seg, max_exp, status = check(48000 / 44100, 882, 960, 2, 2000)
     assert (bad, status) == (0, 0) and packets == 1999
-    assert max_seg <= 10 and max_exp <= 24
+    assert max_seg <= 10 and max_exp <= 32      # runs shorter than SKC_MIN_RUN (16) frames are explicit
     assert 64 + 32 * (max_seg + 4) + 8 * (max_exp + 8) <= 1024
 
 
