@@ -180,7 +180,9 @@ typedef struct skgpu_chain_group {
 
 typedef struct skgpu_chain_result { /* per input, written at the op's results offset every tick */
     uint32_t emitted;      /* 1 = this input contributed an F-frame packet to the mix this tick */
-    uint32_t status;       /* bit0 backlog (second packet pending), bit1 phase-table overflow, bit2 carry spans two chunks */
+    uint32_t status;       /* bit0 backlog (second packet pending), bit1 frame-program overflow (record incomplete),
+                            * bit2 unsupported packet (carry spans two chunks, or its tail needs more than the 32 staged
+                            * frames of the current chunk); with bit1 or bit2 set nothing is emitted */
 } skgpu_chain_result;
 
 /* ------------------------------------------------------------------ plan = one compiled tick
