@@ -201,6 +201,8 @@ __global__ void __launch_bounds__(RS_THREADS) k_resample(const OpHeader *__restr
 // loads) and a warp stores 32 consecutive output frames per instruction.
 // Used when the op's streams are mono / stereo, fit the staging buffer and their programs fit a side record.
 
+constexpr int RSP_THREADS = 64;   // small CTAs: more stream-chunks in flight per SM (the kernel is bound by bytes in flight)
+
 __global__ void __launch_bounds__(PHASE_THREADS, 14) k_phase_prog(const OpHeader *__restrict__ hdr, const skgpu_rs_item *__restrict__ items,
                                                                   SlotTables st, uint8_t *__restrict__ arena, uint64_t results_off, ChainProgDims pd) {
     const uint32_t i = blockIdx.x * PHASE_THREADS + threadIdx.x;
@@ -234,7 +236,7 @@ __global__ void __launch_bounds__(PHASE_THREADS, 14) k_phase_prog(const OpHeader
 }
 
 template <int C>  // 1 | 2
-__global__ void __launch_bounds__(RS_THREADS) k_resample_prog(const OpHeader *__restrict__ hdr, const skgpu_rs_item *__restrict__ items,
+__global__ void __launch_bounds__(RSP_THREADS) k_resample_prog(const OpHeader *__restrict__ hdr, const skgpu_rs_item *__restrict__ items,
                                                               SlotTables st, uint8_t *__restrict__ arena, uint32_t smem_frames, ChainProgDims pd) {
     extern __shared__ __align__(16) uint8_t smem_raw[];   // [program (prog_cap) | 16 history frames | chunk]
     __shared__ __align__(8) uint64_t bar;
@@ -268,7 +270,7 @@ __global__ void __launch_bounds__(RS_THREADS) k_resample_prog(const OpHeader *__
         if (tma_ok) tma_bulk_g2s(buf + 16u * C, in_g, in_bytes, &bar);
     }
     if (!tma_ok)
-        for (uint32_t s = threadIdx.x; s < N * C; s += RS_THREADS) buf[16u * C + s] = in_g[s];
+        for (uint32_t s = threadIdx.x; s < N * C; s += RSP_THREADS) buf[16u * C + s] = in_g[s];
     __syncthreads();
     mbar_wait(&bar, 0);
 
@@ -287,7 +289,7 @@ __global__ void __launch_bounds__(RS_THREADS) k_resample_prog(const OpHeader *__
     const uint32_t prog = smem_u32(smem_raw), segs = prog + skc_seg_off(pd);
     const uint32_t a_hist = smem_u32(buf), a_chunk = a_hist + 16u * C * 4u;
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
-    for (uint32_t b = warp; b * 32u < n_out; b += RS_THREADS / 32) {
+    for (uint32_t b = warp; b * 32u < n_out; b += RSP_THREADS / 32) {
         const uint32_t j = b * 32u + lane;
         uint32_t ent;
         asm volatile("ld.shared.u16 %0, [%1];" : "=r"(ent) : "r"(prog + b * 2u));
