@@ -34,8 +34,8 @@ sys.path.insert(0, ROOT)
 IN_RATE, OUT_RATE, CHANNELS, K_INPUTS = 44100, 48000, 2, 2
 TICK_MS = 20.0
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture
-# (profiles/r1_ncu_full_summary.csv: 1.100975 GB read + 252.58 MB written at 65,536 sessions x 2 inputs), or None
-TRAFFIC_NCU: dict = {"k_chain<2>": 1100975000 + 252580608}
+# (profiles/r1_ncu_full_summary.csv: 1.100923 GB read + 252.77 MB written at 65,536 sessions x 2 inputs), or None
+TRAFFIC_NCU: dict = {"k_chain<2>": 1100923000 + 252765952}
 METRIC = "concurrent real-time 48 kHz stereo sessions (resample->mix->gain->s16, 20 ms ticks)"
 UNIT = "sessions"
 
