@@ -205,6 +205,13 @@ skgpu_rc skgpu_plan_add_chain(skgpu_plan *plan, const skgpu_chain_group *groups,
                               const skgpu_chain_input *inputs, uint32_t n_inputs, uint32_t output_frame_size,
                               uint64_t results_off, uint32_t *op_out);
 
+/* same, with explicit table capacities (sessions come and go: skgpu_plan_update_chain may grow the tables up to these)
+ * and the largest n_inputs any later group will have (0 = the initial tables' maximum). The initial inputs must cover
+ * every stream configuration (rate pair, chunk size, channels) later updates will use: staging is sized from them. */
+skgpu_rc skgpu_plan_add_chain_cap(skgpu_plan *plan, const skgpu_chain_group *groups, uint32_t n_groups,
+                                  const skgpu_chain_input *inputs, uint32_t n_inputs, uint32_t cap_groups, uint32_t cap_inputs,
+                                  uint32_t max_inputs_per_group, uint32_t output_frame_size, uint64_t results_off, uint32_t *op_out);
+
 /* replace an op's descriptor table in place (n <= capacity given at add time) */
 skgpu_rc skgpu_plan_update_convert(skgpu_plan *plan, uint32_t op, const skgpu_seg *segs, uint32_t n);
 skgpu_rc skgpu_plan_update_resample(skgpu_plan *plan, uint32_t op, const skgpu_rs_item *items, uint32_t n);

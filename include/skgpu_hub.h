@@ -1,0 +1,92 @@
+/*
+ * skgpu_hub.h -- the frame-batching layer (libskgpu_hub.so), C ABI.
+ *
+ * BASELINE.json's north star puts a frame-batching layer into StreamKit's crates/engine: "gathers each tick's
+ * 10-20 ms frames from all live sessions into pinned host buffers and sends them to the device through a thin
+ * C-ABI FFI". In the reference nothing is batched across sessions: every node of every session is its own tokio
+ * task with its own channels (crates/engine/src/dynamic_actor.rs:393-495, crates/engine/src/graph_builder.rs:378-422),
+ * one DynamicEngine actor per session (apps/skit/src/session.rs:173-200). The reference is Rust and this image has
+ * no Rust toolchain, so the layer is written in C++ above include/skgpu_batch.h; a Rust engine binds THIS header
+ *  and keeps only the node shims (forward a frame, await the result).
+ *
+ * One hub = one GPU. A SESSION is one instance of the chain
+ *     n x [ audio::resampler{target 48 kHz, chunk = 20 ms, output_frame_size F} -> audio::gain ]
+ *       -> audio::mixer{clocked, F frames} -> audio::gain -> f32->s16
+ * (samples/pipelines/dynamic/moq_mixing.yml:63-74 is this shape with n = 2). Per 20 ms tick the engine pushes at most
+ * one chunk per input, calls skgpu_hub_tick (asynchronous: upload, one fused kernel pass, read-back) and collects
+ * every session's mixed packet after skgpu_hub_wait.
+ *
+ * Semantics kept from the reference nodes:
+ *   - an input that delivers nothing in a tick contributes silence to that tick's mix and keeps its resampler state
+ *     (clocked mixer: mixer.rs:1354-1367; the hub marks the stream absent and repeats its previous chunk bytes as the
+ *     fused kernel's protocol requires);
+ *   - gains are validated like AudioGainConfig (finite, 0.0 ..= 4.0, gain.rs:50-66); an invalid update is rejected and
+ *     the old gain stays (gain.rs:153-173); an accepted update applies from the next tick (gain.rs:151);
+ *   - a new stream starts from a fresh FastFixedIn (zero history, last_index = -4, resampler.rs:232-238) and emits its
+ *     first packet once F frames are available (resampler.rs:425-428): the first tick of a 44.1 kHz input mixes silence.
+ *
+ * Threading: skgpu_hub_push may be called concurrently from any number of threads for DISTINCT (session, input)
+ * pairs (the engine's node tasks); every other call belongs to the hub's tick thread.
+ */
+#ifndef SKGPU_HUB_H
+#define SKGPU_HUB_H
+
+#include "skgpu_batch.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct skgpu_hub skgpu_hub;
+
+#define SKGPU_HUB_OUT_S16 1u /* sessions deliver s16 (clip + pack); without it f32 */
+
+typedef struct skgpu_hub_config {
+    uint32_t max_sessions;           /* capacity: concurrently open sessions */
+    uint32_t max_streams;            /* capacity: resampled inputs over all sessions */
+    uint32_t max_inputs_per_session; /* 1..64 */
+    uint32_t out_rate;               /* mixer / resampler target rate, e.g. 48000 */
+    uint32_t out_frames;             /* F: output_frame_size = frame_samples_per_channel, e.g. 960 */
+    uint16_t channels;               /* 1 | 2, inputs and output */
+    uint16_t flags;                  /* SKGPU_HUB_OUT_S16 */
+    const uint32_t *in_rates;        /* every input sample rate sessions may use; a chunk is in_rate * F / out_rate frames */
+    uint32_t n_in_rates;
+} skgpu_hub_config;
+
+/* message of the last error on the calling thread (borrowed, like skgpu_last_error) */
+const char *skgpu_hub_last_error(void);
+
+skgpu_rc skgpu_hub_create(int32_t device_ordinal, const skgpu_hub_config *cfg, skgpu_hub **out);
+void skgpu_hub_destroy(skgpu_hub *hub);
+
+/* in_rates[n_inputs]: sample rate of every input (each must be one of cfg.in_rates). Gains start at 1.0. */
+skgpu_rc skgpu_hub_session_open(skgpu_hub *hub, uint32_t n_inputs, const uint32_t *in_rates, uint32_t *session_out);
+skgpu_rc skgpu_hub_session_close(skgpu_hub *hub, uint32_t session);
+skgpu_rc skgpu_hub_set_input_gain(skgpu_hub *hub, uint32_t session, uint32_t input, float gain);
+skgpu_rc skgpu_hub_set_master_gain(skgpu_hub *hub, uint32_t session, float gain);
+/* frames a chunk of this input must have (in_rate * F / out_rate) */
+skgpu_rc skgpu_hub_chunk_frames(skgpu_hub *hub, uint32_t session, uint32_t input, uint32_t *frames_out);
+
+/* one chunk (interleaved f32, n_frames == chunk frames of the input) for the NEXT tick; copied into the pinned arena.
+ * A second push for the same input before the tick replaces the first (the clocked mixer's overwrite-oldest ring,
+ * mixer.rs:1195-1201, with depth 1). */
+skgpu_rc skgpu_hub_push(skgpu_hub *hub, uint32_t session, uint32_t input, const float *samples, uint32_t n_frames);
+
+/* asynchronous: table updates after session churn, presence + gains, upload, kernels, read-back */
+skgpu_rc skgpu_hub_tick(skgpu_hub *hub);
+/* blocks until the last tick has finished; timing may be NULL */
+skgpu_rc skgpu_hub_wait(skgpu_hub *hub, skgpu_tick_timing *timing);
+/* the session's packet of the last waited tick: F * channels samples (s16 or f32) inside the hub's pinned output arena,
+ * valid until the next skgpu_hub_wait. *n_mixed = inputs that contributed a packet (0 = silence), *status = OR of the
+ * inputs' chain status bits (skgpu_chain_result.status). Sessions opened after that tick was submitted report 0 / NULL. */
+skgpu_rc skgpu_hub_session_output(skgpu_hub *hub, uint32_t session, const void **samples, uint32_t *n_mixed, uint32_t *status);
+
+/* counters for logs / tests */
+uint32_t skgpu_hub_live_sessions(const skgpu_hub *hub);
+uint32_t skgpu_hub_live_streams(const skgpu_hub *hub);
+uint64_t skgpu_hub_ticks(const skgpu_hub *hub);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SKGPU_HUB_H */

@@ -1,0 +1,396 @@
+// hub.cpp -- the frame-batching layer (include/skgpu_hub.h) above the batch C ABI (include/skgpu_batch.h).
+//
+// C++ stand-in for the layer BASELINE.json's north star adds to StreamKit's crates/engine (the reference is Rust and this
+// image has no Rust toolchain): it owns the pinned tick arenas, assigns every stream a fixed offset in the double-banked
+// input range, keeps the fused chain's descriptor tables in step with session churn (skgpu_plan_update_chain), gathers
+// the frames node tasks push, and runs one asynchronous tick per 20 ms. Reference behaviour it preserves is cited in
+// the header.
+#include "../../../include/skgpu_hub.h"
+
+#include <algorithm>
+#include <atomic>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+namespace {
+
+thread_local std::string g_err;
+
+skgpu_rc hub_fail(skgpu_rc rc, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return rc;
+}
+// propagate an error of the batch layer (its message lives in libskgpu's thread-local slot)
+skgpu_rc hub_pass(skgpu_rc rc) {
+    const char *m = skgpu_last_error();
+    g_err = m ? m : "batch layer error";
+    return rc;
+}
+#define PASS(call)                          \
+    do {                                    \
+        skgpu_rc rc__ = (call);             \
+        if (rc__ != SKGPU_OK) return hub_pass(rc__); \
+    } while (0)
+
+uint64_t align_up(uint64_t x, uint64_t a) { return (x + a - 1) / a * a; }
+
+struct Stream {
+    uint32_t slot = 0;         // resampler slot of the batch context
+    uint32_t chunk = 0;        // frames per pushed chunk
+    uint32_t in_rate = 0;
+    bool live = false;
+    bool ever_pushed = false;
+};
+
+struct Session {
+    bool live = false;
+    std::vector<uint32_t> streams;   // hub stream ids, pin order
+    int64_t tab_first = -1;          // index of its first input in the submitted tables (-1: not in the tables yet)
+};
+
+}  // namespace
+
+struct skgpu_hub {
+    skgpu_hub_config cfg{};
+    std::vector<uint32_t> rates;
+    skgpu_ctx *ctx = nullptr;
+    skgpu_plan *plan = nullptr;
+    uint32_t op = 0;
+    uint32_t C = 2, F = 960, ob = 2;
+    uint64_t in_stride = 0, in_bytes = 0, bank_stride = 0, res_off = 0, res_bytes = 0, out_off = 0, out_stride = 0, d2h_bytes = 0;
+    uint8_t *host_in[2] = {nullptr, nullptr};
+    uint8_t *host_out[2] = {nullptr, nullptr};
+    std::vector<Stream> streams;
+    std::vector<Session> sessions;
+    std::vector<uint32_t> free_streams, free_sessions;
+    std::vector<std::atomic<uint8_t>> pushed;   // per stream: a chunk for the NEXT tick sits in host_in[cur]
+    std::vector<float> gains;                   // [stream gains | master gains]
+    bool gains_dirty = true, tables_dirty = true;
+    std::vector<skgpu_chain_group> groups;
+    std::vector<skgpu_chain_input> inputs;
+    std::vector<uint32_t> tab_stream;           // table input index -> hub stream id
+    std::vector<uint8_t> present;
+    uint32_t cur = 0;                           // arena the next tick uploads
+    int last = -1;                              // arena of the last submitted tick
+    bool in_flight = false;
+    uint64_t ticks = 0;
+    uint32_t n_live_sessions = 0, n_live_streams = 0;
+    explicit skgpu_hub(uint32_t n_streams) : pushed(n_streams) {}
+};
+
+static bool valid_gain(float g) { return std::isfinite(g) && g >= 0.0f && g <= 4.0f; }   // gain.rs:50-66
+
+static skgpu_rc rebuild_tables(skgpu_hub *h) {
+    h->groups.clear();
+    h->inputs.clear();
+    h->tab_stream.clear();
+    for (uint32_t si = 0; si < h->sessions.size(); ++si) {
+        Session &s = h->sessions[si];
+        if (!s.live) continue;
+        skgpu_chain_group g{};
+        g.out_off = h->out_off + (uint64_t)si * h->out_stride;
+        g.first_input = (uint32_t)h->inputs.size();
+        g.n_inputs = (uint32_t)s.streams.size();
+        g.gain_idx = h->cfg.max_streams + si;
+        g.out_channels = (uint16_t)h->C;
+        g.flags = (h->cfg.flags & SKGPU_HUB_OUT_S16) ? 1u : 0u;   // SKGPU_MIX_OUT_S16
+        s.tab_first = (int64_t)h->inputs.size();
+        for (uint32_t sid : s.streams) {
+            skgpu_chain_input in{};
+            in.in_off = (uint64_t)sid * h->in_stride;
+            in.slot = h->streams[sid].slot;
+            in.gain_idx = sid;
+            in.flags = 1u;   // SKGPU_MIX_IN_UNIQUE: every stream owns its samples
+            h->inputs.push_back(in);
+            h->tab_stream.push_back(sid);
+        }
+        h->groups.push_back(g);
+    }
+    PASS(skgpu_plan_update_chain(h->plan, h->op, h->groups.data(), (uint32_t)h->groups.size(), h->inputs.data(), (uint32_t)h->inputs.size()));
+    h->tables_dirty = false;
+    return SKGPU_OK;
+}
+
+extern "C" const char *skgpu_hub_last_error(void) { return g_err.c_str(); }
+
+extern "C" skgpu_rc skgpu_hub_create(int32_t device, const skgpu_hub_config *cfg, skgpu_hub **out) {
+    if (!cfg || !out) return hub_fail(SKGPU_ERR_INVALID, "null argument");
+    if (!cfg->max_sessions || !cfg->max_streams || !cfg->n_in_rates || !cfg->in_rates) return hub_fail(SKGPU_ERR_INVALID, "empty capacity or rate list");
+    if (cfg->channels != 1 && cfg->channels != 2) return hub_fail(SKGPU_ERR_INVALID, "channels must be 1 or 2");
+    if (cfg->max_inputs_per_session < 1 || cfg->max_inputs_per_session > 64) return hub_fail(SKGPU_ERR_INVALID, "max_inputs_per_session must be 1..64");
+    if (cfg->n_in_rates > 64) return hub_fail(SKGPU_ERR_INVALID, "at most 64 distinct input rates");
+    uint32_t max_chunk = 0;
+    for (uint32_t i = 0; i < cfg->n_in_rates; ++i) {
+        const uint64_t num = (uint64_t)cfg->in_rates[i] * cfg->out_frames;
+        if (cfg->in_rates[i] == cfg->out_rate)
+            return hub_fail(SKGPU_ERR_INVALID, "input rate %u equals the output rate: the reference bypasses the resampler for such inputs (resampler.rs:299-373); "
+                            "mix them with the unfused ops", cfg->in_rates[i]);
+        if (!cfg->in_rates[i] || num % cfg->out_rate) return hub_fail(SKGPU_ERR_INVALID, "input rate %u does not give whole chunks of %u output frames at %u Hz", cfg->in_rates[i], cfg->out_frames, cfg->out_rate);
+        max_chunk = std::max<uint32_t>(max_chunk, (uint32_t)(num / cfg->out_rate));
+    }
+    skgpu_hub *h = new skgpu_hub(cfg->max_streams);
+    h->cfg = *cfg;
+    h->rates.assign(cfg->in_rates, cfg->in_rates + cfg->n_in_rates);
+    h->cfg.in_rates = h->rates.data();
+    h->C = cfg->channels;
+    h->F = cfg->out_frames;
+    h->ob = (cfg->flags & SKGPU_HUB_OUT_S16) ? 2u : 4u;
+    h->in_stride = align_up((uint64_t)max_chunk * h->C * 4u, 16);
+    h->in_bytes = (uint64_t)cfg->max_streams * h->in_stride;
+    h->bank_stride = align_up(h->in_bytes, 256);
+    h->res_off = 2 * h->bank_stride;
+    h->res_bytes = align_up((uint64_t)cfg->max_streams * sizeof(skgpu_chain_result), 256);
+    h->out_off = h->res_off + h->res_bytes;
+    h->out_stride = align_up((uint64_t)h->F * h->C * h->ob, 16);
+    h->d2h_bytes = h->res_bytes + (uint64_t)cfg->max_sessions * h->out_stride;
+    const uint64_t arena = align_up(h->res_off + h->d2h_bytes, 256);
+    auto bail = [&](skgpu_rc rc) { skgpu_hub_destroy(h); return rc; };
+
+    skgpu_ctx_config cc{};
+    cc.max_streams = cfg->max_streams + cfg->n_in_rates;   // + the probe streams that size the op
+    cc.max_channels = h->C;
+    cc.fifo_frames = 0;
+    skgpu_rc rc0 = skgpu_ctx_create(device, &cc, &h->ctx);
+    if (rc0 != SKGPU_OK) return bail(hub_pass(rc0));   // no CUDA device: SKGPU_ERR_NODEVICE, there is no CPU fallback
+    rc0 = skgpu_plan_create(h->ctx, arena, &h->plan);
+    if (rc0 != SKGPU_OK) return bail(hub_pass(rc0));
+    for (int b = 0; b < 2; ++b) {
+        void *p = nullptr;
+        if (skgpu_pinned_alloc(h->ctx, h->in_bytes, &p) != SKGPU_OK) return bail(hub_pass(SKGPU_ERR_NOMEM));
+        h->host_in[b] = (uint8_t *)p;
+        memset(p, 0, h->in_bytes);
+        if (skgpu_pinned_alloc(h->ctx, h->d2h_bytes, &p) != SKGPU_OK) return bail(hub_pass(SKGPU_ERR_NOMEM));
+        h->host_out[b] = (uint8_t *)p;
+        memset(p, 0, h->d2h_bytes);
+    }
+    h->streams.resize(cfg->max_streams);
+    h->sessions.resize(cfg->max_sessions);
+    for (uint32_t i = cfg->max_streams; i-- > 0;) h->free_streams.push_back(i);
+    for (uint32_t i = cfg->max_sessions; i-- > 0;) h->free_sessions.push_back(i);
+    h->gains.assign((size_t)cfg->max_streams + cfg->max_sessions, 1.0f);
+    h->present.assign(cfg->max_streams, 0);
+
+    // ---- the op is sized from one probe stream per allowed rate (staging buffers, frame-program capacities), with the
+    // table capacities of the whole hub; afterwards the tables are emptied and the probe streams closed
+    std::vector<uint32_t> probe_slots(cfg->n_in_rates);
+    std::vector<skgpu_chain_input> pin(cfg->n_in_rates);
+    for (uint32_t i = 0; i < cfg->n_in_rates; ++i) {
+        skgpu_stream_cfg sc{};
+        sc.in_rate = cfg->in_rates[i];
+        sc.out_rate = cfg->out_rate;
+        sc.chunk_frames = (uint32_t)((uint64_t)cfg->in_rates[i] * cfg->out_frames / cfg->out_rate);
+        sc.channels = (uint16_t)h->C;
+        if (skgpu_stream_open(h->ctx, &sc, &probe_slots[i]) != SKGPU_OK) return bail(hub_pass(SKGPU_ERR_INVALID));
+        pin[i] = skgpu_chain_input{};
+        pin[i].in_off = 0;
+        pin[i].slot = probe_slots[i];
+        pin[i].gain_idx = SKGPU_NO_GAIN;
+        pin[i].flags = 1u;
+    }
+    skgpu_chain_group pg{};
+    pg.out_off = h->out_off;
+    pg.first_input = 0;
+    pg.n_inputs = cfg->n_in_rates;
+    pg.gain_idx = SKGPU_NO_GAIN;
+    pg.out_channels = (uint16_t)h->C;
+    pg.flags = (cfg->flags & SKGPU_HUB_OUT_S16) ? 1u : 0u;
+    skgpu_rc rc = skgpu_plan_set_io(h->plan, 0, h->in_bytes, h->res_off, h->d2h_bytes);
+    if (rc == SKGPU_OK) rc = skgpu_plan_set_banks(h->plan, h->bank_stride);
+    if (rc == SKGPU_OK) rc = skgpu_plan_set_gains(h->plan, h->gains.data(), (uint32_t)h->gains.size());
+    if (rc == SKGPU_OK)
+        rc = skgpu_plan_add_chain_cap(h->plan, &pg, 1, pin.data(), cfg->n_in_rates, cfg->max_sessions, cfg->max_streams, cfg->max_inputs_per_session,
+                                      cfg->out_frames, h->res_off, &h->op);
+    if (rc == SKGPU_OK) rc = skgpu_plan_finalize(h->plan);
+    if (rc == SKGPU_OK) rc = skgpu_plan_update_chain(h->plan, h->op, nullptr, 0, nullptr, 0);
+    if (rc != SKGPU_OK) return bail(hub_pass(rc));
+    for (uint32_t s : probe_slots) skgpu_stream_close(h->ctx, s);
+    h->tables_dirty = false;
+    *out = h;
+    return SKGPU_OK;
+}
+
+extern "C" void skgpu_hub_destroy(skgpu_hub *h) {
+    if (!h) return;
+    if (h->plan && h->in_flight) skgpu_tick_wait(h->plan, nullptr);
+    if (h->ctx) {
+        for (int b = 0; b < 2; ++b) {
+            if (h->host_in[b]) skgpu_pinned_free(h->ctx, h->host_in[b]);
+            if (h->host_out[b]) skgpu_pinned_free(h->ctx, h->host_out[b]);
+        }
+    }
+    if (h->plan) skgpu_plan_destroy(h->plan);
+    if (h->ctx) skgpu_ctx_destroy(h->ctx);
+    delete h;
+}
+
+extern "C" skgpu_rc skgpu_hub_session_open(skgpu_hub *h, uint32_t n_inputs, const uint32_t *in_rates, uint32_t *session_out) {
+    if (!h || !in_rates || !session_out) return hub_fail(SKGPU_ERR_INVALID, "null argument");
+    if (n_inputs < 1 || n_inputs > h->cfg.max_inputs_per_session) return hub_fail(SKGPU_ERR_INVALID, "n_inputs %u outside 1..%u", n_inputs, h->cfg.max_inputs_per_session);
+    if (h->free_sessions.empty()) return hub_fail(SKGPU_ERR_NOMEM, "out of session slots (%u)", h->cfg.max_sessions);
+    if (h->free_streams.size() < n_inputs) return hub_fail(SKGPU_ERR_NOMEM, "out of stream slots (%u requested, %zu free)", n_inputs, h->free_streams.size());
+    for (uint32_t i = 0; i < n_inputs; ++i) {
+        bool ok = false;
+        for (uint32_t r : h->rates) ok |= (r == in_rates[i]);
+        if (!ok) return hub_fail(SKGPU_ERR_INVALID, "input %u: sample rate %u is not in the hub's rate list", i, in_rates[i]);
+    }
+    const uint32_t si = h->free_sessions.back();
+    Session s;
+    s.live = true;
+    for (uint32_t i = 0; i < n_inputs; ++i) {
+        skgpu_stream_cfg sc{};
+        sc.in_rate = in_rates[i];
+        sc.out_rate = h->cfg.out_rate;
+        sc.chunk_frames = (uint32_t)((uint64_t)in_rates[i] * h->F / h->cfg.out_rate);
+        sc.channels = (uint16_t)h->C;
+        uint32_t slot = 0;
+        const skgpu_rc rc = skgpu_stream_open(h->ctx, &sc, &slot);
+        if (rc != SKGPU_OK) {
+            for (uint32_t sid : s.streams) { skgpu_stream_close(h->ctx, h->streams[sid].slot); h->streams[sid] = Stream{}; h->free_streams.push_back(sid); }
+            return hub_pass(rc);
+        }
+        const uint32_t sid = h->free_streams.back();
+        h->free_streams.pop_back();
+        Stream st;
+        st.slot = slot; st.chunk = sc.chunk_frames; st.in_rate = in_rates[i]; st.live = true;
+        h->streams[sid] = st;
+        h->pushed[sid].store(0, std::memory_order_relaxed);
+        h->gains[sid] = 1.0f;
+        s.streams.push_back(sid);
+    }
+    h->free_sessions.pop_back();
+    h->gains[h->cfg.max_streams + si] = 1.0f;
+    h->sessions[si] = std::move(s);
+    h->n_live_sessions += 1;
+    h->n_live_streams += n_inputs;
+    h->gains_dirty = h->tables_dirty = true;
+    *session_out = si;
+    return SKGPU_OK;
+}
+
+static Session *live_session(skgpu_hub *h, uint32_t si) { return (h && si < h->sessions.size() && h->sessions[si].live) ? &h->sessions[si] : nullptr; }
+
+extern "C" skgpu_rc skgpu_hub_session_close(skgpu_hub *h, uint32_t si) {
+    Session *s = live_session(h, si);
+    if (!s) return hub_fail(SKGPU_ERR_INVALID, "session %u is not open", si);
+    if (h->in_flight) { PASS(skgpu_tick_wait(h->plan, nullptr)); h->in_flight = false; }   // its slots may be in use by the tick in flight
+    for (uint32_t sid : s->streams) {
+        skgpu_stream_close(h->ctx, h->streams[sid].slot);
+        h->streams[sid] = Stream{};
+        h->pushed[sid].store(0, std::memory_order_relaxed);
+        h->free_streams.push_back(sid);
+    }
+    h->n_live_streams -= (uint32_t)s->streams.size();
+    h->n_live_sessions -= 1;
+    *s = Session{};
+    h->free_sessions.push_back(si);
+    h->tables_dirty = true;
+    return SKGPU_OK;
+}
+
+extern "C" skgpu_rc skgpu_hub_set_input_gain(skgpu_hub *h, uint32_t si, uint32_t input, float gain) {
+    Session *s = live_session(h, si);
+    if (!s || input >= s->streams.size()) return hub_fail(SKGPU_ERR_INVALID, "no such session / input");
+    if (!valid_gain(gain)) return hub_fail(SKGPU_ERR_INVALID, "gain must be a finite number between 0.0 and 4.0");   // gain.rs:50-66; the old gain stays
+    h->gains[s->streams[input]] = gain;
+    h->gains_dirty = true;
+    return SKGPU_OK;
+}
+
+extern "C" skgpu_rc skgpu_hub_set_master_gain(skgpu_hub *h, uint32_t si, float gain) {
+    if (!live_session(h, si)) return hub_fail(SKGPU_ERR_INVALID, "session %u is not open", si);
+    if (!valid_gain(gain)) return hub_fail(SKGPU_ERR_INVALID, "gain must be a finite number between 0.0 and 4.0");
+    h->gains[h->cfg.max_streams + si] = gain;
+    h->gains_dirty = true;
+    return SKGPU_OK;
+}
+
+extern "C" skgpu_rc skgpu_hub_chunk_frames(skgpu_hub *h, uint32_t si, uint32_t input, uint32_t *frames_out) {
+    Session *s = live_session(h, si);
+    if (!s || input >= s->streams.size() || !frames_out) return hub_fail(SKGPU_ERR_INVALID, "no such session / input");
+    *frames_out = h->streams[s->streams[input]].chunk;
+    return SKGPU_OK;
+}
+
+extern "C" skgpu_rc skgpu_hub_push(skgpu_hub *h, uint32_t si, uint32_t input, const float *samples, uint32_t n_frames) {
+    Session *s = live_session(h, si);
+    if (!s || input >= s->streams.size() || !samples) return hub_fail(SKGPU_ERR_INVALID, "no such session / input");
+    const uint32_t sid = s->streams[input];
+    const Stream &st = h->streams[sid];
+    if (n_frames != st.chunk) return hub_fail(SKGPU_ERR_INVALID, "chunk of %u frames, the stream delivers %u per tick", n_frames, st.chunk);
+    memcpy(h->host_in[h->cur] + (uint64_t)sid * h->in_stride, samples, (size_t)n_frames * h->C * 4u);
+    h->pushed[sid].store(1, std::memory_order_release);
+    return SKGPU_OK;
+}
+
+extern "C" skgpu_rc skgpu_hub_tick(skgpu_hub *h) {
+    if (!h) return hub_fail(SKGPU_ERR_INVALID, "null hub");
+    if (h->tables_dirty) {
+        if (h->in_flight) { PASS(skgpu_tick_wait(h->plan, nullptr)); h->in_flight = false; }
+        skgpu_rc rc = rebuild_tables(h);
+        if (rc != SKGPU_OK) return rc;
+    }
+    const uint32_t n_in = (uint32_t)h->tab_stream.size();
+    uint8_t *in_cur = h->host_in[h->cur], *in_prev = h->host_in[h->cur ^ 1u];
+    for (uint32_t i = 0; i < n_in; ++i) {
+        const uint32_t sid = h->tab_stream[i];
+        Stream &st = h->streams[sid];
+        const bool got = h->pushed[sid].exchange(0, std::memory_order_acquire) != 0;
+        h->present[i] = got ? 1 : 0;
+        if (got) {
+            st.ever_pushed = true;
+        } else if (st.ever_pushed) {
+            // absent this tick: the other input bank must keep holding the stream's previous chunk (skgpu_batch.h, chain protocol)
+            const uint64_t off = (uint64_t)sid * h->in_stride;
+            memcpy(in_cur + off, in_prev + off, (size_t)st.chunk * h->C * 4u);
+        }
+    }
+    PASS(skgpu_plan_set_present(h->plan, h->op, h->present.data(), n_in));
+    if (h->gains_dirty) {
+        PASS(skgpu_plan_set_gains(h->plan, h->gains.data(), (uint32_t)h->gains.size()));
+        h->gains_dirty = false;
+    }
+    PASS(skgpu_tick_submit(h->plan, in_cur, h->host_out[h->cur], SKGPU_SUBMIT_GRAPH | SKGPU_SUBMIT_OVERLAP_D2H));
+    h->last = (int)h->cur;
+    h->cur ^= 1u;
+    h->in_flight = true;
+    h->ticks += 1;
+    return SKGPU_OK;
+}
+
+extern "C" skgpu_rc skgpu_hub_wait(skgpu_hub *h, skgpu_tick_timing *timing) {
+    if (!h) return hub_fail(SKGPU_ERR_INVALID, "null hub");
+    PASS(skgpu_tick_wait(h->plan, timing));
+    h->in_flight = false;
+    return SKGPU_OK;
+}
+
+extern "C" skgpu_rc skgpu_hub_session_output(skgpu_hub *h, uint32_t si, const void **samples, uint32_t *n_mixed, uint32_t *status) {
+    Session *s = live_session(h, si);
+    if (!s) return hub_fail(SKGPU_ERR_INVALID, "session %u is not open", si);
+    if (h->in_flight) return hub_fail(SKGPU_ERR_STATE, "a tick is in flight: call skgpu_hub_wait first");
+    if (samples) *samples = nullptr;
+    if (n_mixed) *n_mixed = 0;
+    if (status) *status = 0;
+    if (h->last < 0 || s->tab_first < 0) return SKGPU_OK;   // opened after the last tick was submitted
+    const uint8_t *o = h->host_out[h->last];
+    const skgpu_chain_result *res = reinterpret_cast<const skgpu_chain_result *>(o) + s->tab_first;
+    uint32_t nm = 0, stt = 0;
+    for (size_t i = 0; i < s->streams.size(); ++i) { nm += res[i].emitted; stt |= res[i].status; }
+    if (samples) *samples = o + (h->out_off - h->res_off) + (uint64_t)si * h->out_stride;
+    if (n_mixed) *n_mixed = nm;
+    if (status) *status = stt;
+    return SKGPU_OK;
+}
+
+extern "C" uint32_t skgpu_hub_live_sessions(const skgpu_hub *h) { return h ? h->n_live_sessions : 0; }
+extern "C" uint32_t skgpu_hub_live_streams(const skgpu_hub *h) { return h ? h->n_live_streams : 0; }
+extern "C" uint64_t skgpu_hub_ticks(const skgpu_hub *h) { return h ? h->ticks : 0; }

@@ -924,6 +924,14 @@ static void chain_size_smem(Op &op, uint32_t max_k, uint32_t chunk_cap, uint32_t
 
 extern "C" skgpu_rc skgpu_plan_add_chain(skgpu_plan *p, const skgpu_chain_group *groups, uint32_t ng, const skgpu_chain_input *inputs, uint32_t ni,
                                          uint32_t output_frame_size, uint64_t results_off, uint32_t *op_out) {
+    return skgpu_plan_add_chain_cap(p, groups, ng, inputs, ni, ng, ni, 0, output_frame_size, results_off, op_out);
+}
+
+extern "C" skgpu_rc skgpu_plan_add_chain_cap(skgpu_plan *p, const skgpu_chain_group *groups, uint32_t ng, const skgpu_chain_input *inputs, uint32_t ni,
+                                             uint32_t cap_groups, uint32_t cap_inputs, uint32_t max_inputs_per_group, uint32_t output_frame_size,
+                                             uint64_t results_off, uint32_t *op_out) {
+    if (cap_groups < ng || cap_inputs < ni) return fail(SKGPU_ERR_INVALID, "table capacities smaller than the initial tables");
+    if (max_inputs_per_group > (uint32_t)CH_MAX_INPUTS) return fail(SKGPU_ERR_INVALID, "more than %d inputs per group", CH_MAX_INPUTS);
     if (!p || (!groups && ng) || (!inputs && ni)) return fail(SKGPU_ERR_INVALID, "null argument");
     if (p->finalized) return fail(SKGPU_ERR_STATE, "plan already finalized");
     if (!p->bank_stride) return fail(SKGPU_ERR_STATE, "the fused chain needs a double-banked input range: call skgpu_plan_set_banks first");
@@ -936,12 +944,13 @@ extern "C" skgpu_rc skgpu_plan_add_chain(skgpu_plan *p, const skgpu_chain_group 
     int oc = 2;
     skgpu_rc rc = validate_chain(p, groups, ng, inputs, ni, output_frame_size, &mk, &mb, &oc, &cnp, &cnr);
     if (rc) return rc;
-    rc = check_range(p, results_off, (uint64_t)std::max(ni, 1u) * sizeof(skgpu_chain_result), "chain results");
+    mk = std::max(mk, max_inputs_per_group);
+    rc = check_range(p, results_off, (uint64_t)std::max(cap_inputs, 1u) * sizeof(skgpu_chain_result), "chain results");
     if (rc) return rc;
     if (results_off % 8) return fail(SKGPU_ERR_INVALID, "results_off must be 8-byte aligned");
     Op op;
     op.kind = OP_CHAIN;
-    rc = op_alloc_tables(op, sizeof(skgpu_chain_group), std::max(ng, 1u), sizeof(skgpu_chain_input), std::max(ni, 1u));
+    rc = op_alloc_tables(op, sizeof(skgpu_chain_group), std::max(cap_groups, 1u), sizeof(skgpu_chain_input), std::max(cap_inputs, 1u));
     if (rc) return rc;
     if (ng) memcpy(op.h_tab, groups, ng * sizeof(skgpu_chain_group));
     if (ni) memcpy(op.h_tab2, inputs, ni * sizeof(skgpu_chain_input));

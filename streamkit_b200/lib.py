@@ -56,6 +56,7 @@ EXPORTS = [
     "skgpu_pinned_alloc", "skgpu_pinned_free", "skgpu_stream_open", "skgpu_stream_open_many", "skgpu_stream_reset",
     "skgpu_stream_close", "skgpu_stream_get_state", "skgpu_stream_max_out_frames", "skgpu_plan_create",
     "skgpu_plan_destroy", "skgpu_plan_add_convert", "skgpu_plan_add_resample", "skgpu_plan_add_mix", "skgpu_plan_add_chain",
+    "skgpu_plan_add_chain_cap",
     "skgpu_plan_update_convert", "skgpu_plan_update_resample", "skgpu_plan_update_mix", "skgpu_plan_update_chain",
     "skgpu_plan_set_io", "skgpu_plan_set_banks", "skgpu_plan_tick_count",
     "skgpu_plan_set_gains", "skgpu_plan_set_present", "skgpu_plan_finalize", "skgpu_tick_submit", "skgpu_tick_wait",
@@ -97,6 +98,7 @@ def load() -> C.CDLL:
         "skgpu_plan_add_resample": (i32, [vp, vp, u32, u64, C.POINTER(u32)]),
         "skgpu_plan_add_mix": (i32, [vp, vp, u32, vp, u32, C.POINTER(u32)]),
         "skgpu_plan_add_chain": (i32, [vp, vp, u32, vp, u32, u32, u64, C.POINTER(u32)]),
+        "skgpu_plan_add_chain_cap": (i32, [vp, vp, u32, vp, u32, u32, u32, u32, u32, u64, C.POINTER(u32)]),
         "skgpu_plan_update_chain": (i32, [vp, u32, vp, u32, vp, u32]),
         "skgpu_plan_set_banks": (i32, [vp, u64]),
         "skgpu_plan_tick_count": (u64, [vp]),
