@@ -146,6 +146,54 @@ def run_reference(args) -> None:
     print(json.dumps(line), flush=True)
 
 
+# ---------------------------------------------------------------------------------------------- frame-batching layer
+
+def run_hub_e2e(S: int, steps: int, warmup: int, device: int, threads: int) -> dict:
+    """The same workload driven through the frame-batching layer (include/skgpu_hub.h): per tick the chunks of all
+    S x K streams are gathered from separate host buffers into the hub's pinned arena by `threads` worker threads
+    (skgpu_hub_push_batch), then one asynchronous tick; the gather of tick n + 1 overlaps tick n on the GPU.
+    Wall-clock time (it includes host work), results read back every tick."""
+    from streamkit_b200 import hub as H, synth
+
+    chunk = IN_RATE // 50
+    hub = H.Hub(max_sessions=S, max_streams=S * K_INPUTS, in_rates=[IN_RATE], max_inputs_per_session=K_INPUTS, channels=CHANNELS, device=device)
+    try:
+        pool = np.ascontiguousarray(synth.noise_streams(4242, 0, 256, chunk, CHANNELS))   # 256 distinct chunks, reused round-robin
+        frames = np.zeros(S * K_INPUTS, dtype=H.FRAME_DT)
+        for s in range(S):
+            sid = hub.session_open([IN_RATE] * K_INPUTS)
+            for i in range(K_INPUTS):
+                f = frames[s * K_INPUTS + i]
+                f["session"], f["input"], f["n_frames"] = sid, i, chunk
+        frames["samples"] = pool.ctypes.data + (np.arange(frames.size, dtype=np.uint64) % 256) * np.uint64(pool.strides[0])
+        for _ in range(max(2, warmup)):
+            hub.push_batch(frames, threads)
+            hub.tick()
+            hub.wait()
+        t_push = t_tick = t_wait = 0.0
+        t0 = time.perf_counter()
+        hub.push_batch(frames, threads)
+        hub.tick()
+        for _ in range(steps - 1):
+            a = time.perf_counter()
+            hub.push_batch(frames, threads)   # gather of the next tick while the GPU works on the current one
+            b = time.perf_counter()
+            hub.wait()
+            c = time.perf_counter()
+            hub.tick()
+            d = time.perf_counter()
+            t_push += b - a; t_wait += c - b; t_tick += d - c
+        hub.wait()
+        ms = (time.perf_counter() - t0) * 1e3 / steps
+        out, n_mixed, status = hub.output(0)
+        return {"value": S * TICK_MS / ms, "unit": UNIT, "ms_per_step": ms, "gather_threads": threads, "sessions": S,
+                "host_ms": {"gather": t_push * 1e3 / max(steps - 1, 1), "wait": t_wait * 1e3 / max(steps - 1, 1), "tick_call": t_tick * 1e3 / max(steps - 1, 1)},
+                "what": "skgpu_hub: multi-threaded gather into pinned arena + H2D + kernels + D2H per tick, wall clock",
+                "check": {"n_mixed": int(n_mixed), "status": int(status), "nonzero": bool(out is not None and np.any(out != 0))}}
+    finally:
+        hub.close()
+
+
 # ---------------------------------------------------------------------------------------------- GPU arm
 
 def run_gpu(args) -> None:
@@ -247,6 +295,19 @@ def run_gpu(args) -> None:
     e2e_ms_per_step = e2e_ms / args.steps
     clk = clocks.stop(t_wall0, t_wall1)
 
+    launches_per_tick = plan.launches_per_tick()
+    dev_name, dev_sms, dev_cc_ma, dev_cc_mi = ctx.device_info()
+    ct.close()   # frees the arenas before the frame-batching layer allocates its own
+    hub_e2e = None
+    if args.hub:
+        try:
+            hub_e2e = run_hub_e2e(S, max(5, min(args.steps, 20)), 2, local_rank, max(1, len(os.sched_getaffinity(0)) // max(world, 1)))
+            if dist is not None:
+                hub_e2e["ms_per_step"] = max_over_ranks(hub_e2e["ms_per_step"])
+                hub_e2e["value"] = S * world * TICK_MS / hub_e2e["ms_per_step"]
+        except Exception as e:  # the layer is an extra: never lose the main line
+            hub_e2e = {"error": str(e)[:200]}
+
     total_sessions = S * world
     value = total_sessions * TICK_MS / ms_per_step
     e2e_value = total_sessions * TICK_MS / e2e_ms_per_step
@@ -271,7 +332,7 @@ def run_gpu(args) -> None:
         cpu_chain(cpu_sessions, 2, cores)
         cpu_sec = cpu_chain(cpu_sessions, cpu_ticks, cores)
         cpu_value = cpu_sessions * TICK_MS / (cpu_sec * 1e3 / cpu_ticks)
-        name, sms, cc_ma, cc_mi = ctx.device_info()
+        name, sms, cc_ma, cc_mi = dev_name, dev_sms, dev_cc_ma, dev_cc_mi
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
@@ -280,7 +341,8 @@ def run_gpu(args) -> None:
                     "ms_per_step": e2e_ms_per_step, "last_tick_ms": {"h2d": timing.h2d_ms, "kernels": timing.kernels_ms, "d2h": timing.d2h_ms},
                     "h2d_gbs_per_gpu": ct.in_bytes / (timing.h2d_ms * 1e-3) / 1e9 if timing.h2d_ms > 0 else None,
                     "d2h_gbs_per_gpu": ct.out_bytes / (timing.d2h_ms * 1e-3) / 1e9 if timing.d2h_ms > 0 else None},
-            "gpu_launches": plan.launches_per_tick() * args.steps * 2,
+            "e2e_hub": hub_e2e,
+            "gpu_launches": launches_per_tick * args.steps * 2,
             "clocks": clk,
             "roofline": {"bound": "hbm", "kernel": dom_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak,
@@ -296,7 +358,6 @@ def run_gpu(args) -> None:
             "device": {"name": name, "sms": sms, "cc": "%d.%d" % (cc_ma, cc_mi)},
         }
         print(json.dumps(line), flush=True)
-    ct.close()
     if dist is not None:
         dist.destroy_process_group()
 
@@ -310,6 +371,7 @@ def main() -> None:
     ap.add_argument("--sessions", type=int, default=65536, help="sessions per GPU (weak scaling)")
     ap.add_argument("--unfused", action="store_true", help="use the general unfused ops (k_resample -> ring -> k_mix)")
     ap.add_argument("--ref-sessions", type=int, default=8192, help="bounded session sample of the CPU arm")
+    ap.add_argument("--no-hub", dest="hub", action="store_false", help="skip the frame-batching-layer end-to-end measurement")
     ap.add_argument("--latency-ticks", type=int, default=500, help="ticks of the per-tick latency measurement (0 = skip)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":

@@ -72,6 +72,14 @@ skgpu_rc skgpu_hub_chunk_frames(skgpu_hub *hub, uint32_t session, uint32_t input
  * mixer.rs:1195-1201, with depth 1). */
 skgpu_rc skgpu_hub_push(skgpu_hub *hub, uint32_t session, uint32_t input, const float *samples, uint32_t n_frames);
 
+/* many chunks at once, copied by n_threads worker threads (the gather of a whole tick is ~1 GB at 65 k sessions:
+ * one thread cannot keep up with PCIe). frames[i] must name distinct (session, input) pairs. */
+typedef struct skgpu_hub_frame {
+    const float *samples;
+    uint32_t session, input, n_frames, reserved;
+} skgpu_hub_frame;
+skgpu_rc skgpu_hub_push_batch(skgpu_hub *hub, const skgpu_hub_frame *frames, uint32_t n, uint32_t n_threads);
+
 /* asynchronous: table updates after session churn, presence + gains, upload, kernels, read-back */
 skgpu_rc skgpu_hub_tick(skgpu_hub *hub);
 /* blocks until the last tick has finished; timing may be NULL */

@@ -7,6 +7,9 @@
 // the header.
 #include "../../../include/skgpu_hub.h"
 
+#if defined(__SSE2__)
+#include <emmintrin.h>
+#endif
 #include <algorithm>
 #include <atomic>
 #include <cmath>
@@ -14,6 +17,7 @@
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 namespace {
@@ -42,6 +46,35 @@ skgpu_rc hub_pass(skgpu_rc rc) {
     } while (0)
 
 uint64_t align_up(uint64_t x, uint64_t a) { return (x + a - 1) / a * a; }
+
+// Copy of one chunk into the pinned arena with NON-TEMPORAL stores: the destination is read next by the PCIe DMA engine,
+// not by a CPU, so allocating it in the caches (and reading the lines first) only costs host memory bandwidth -- the
+// resource the gather of ~1 GB per tick competes for with the upload itself. dst is 16-byte aligned (arena offsets are).
+void stream_copy(uint8_t *dst, const uint8_t *src, size_t bytes) {
+#if defined(__SSE2__)
+    size_t i = 0;
+    if ((reinterpret_cast<uintptr_t>(dst) & 15u) == 0) {
+        for (; i + 64 <= bytes; i += 64) {
+            const __m128i a = _mm_loadu_si128(reinterpret_cast<const __m128i *>(src + i));
+            const __m128i b = _mm_loadu_si128(reinterpret_cast<const __m128i *>(src + i + 16));
+            const __m128i c = _mm_loadu_si128(reinterpret_cast<const __m128i *>(src + i + 32));
+            const __m128i d = _mm_loadu_si128(reinterpret_cast<const __m128i *>(src + i + 48));
+            _mm_stream_si128(reinterpret_cast<__m128i *>(dst + i), a);
+            _mm_stream_si128(reinterpret_cast<__m128i *>(dst + i + 16), b);
+            _mm_stream_si128(reinterpret_cast<__m128i *>(dst + i + 32), c);
+            _mm_stream_si128(reinterpret_cast<__m128i *>(dst + i + 48), d);
+        }
+    }
+    if (i < bytes) memcpy(dst + i, src + i, bytes - i);
+#else
+    memcpy(dst, src, bytes);
+#endif
+}
+void stream_fence() {
+#if defined(__SSE2__)
+    _mm_sfence();
+#endif
+}
 
 struct Stream {
     uint32_t slot = 0;         // resampler slot of the batch context
@@ -326,8 +359,36 @@ extern "C" skgpu_rc skgpu_hub_push(skgpu_hub *h, uint32_t si, uint32_t input, co
     const uint32_t sid = s->streams[input];
     const Stream &st = h->streams[sid];
     if (n_frames != st.chunk) return hub_fail(SKGPU_ERR_INVALID, "chunk of %u frames, the stream delivers %u per tick", n_frames, st.chunk);
-    memcpy(h->host_in[h->cur] + (uint64_t)sid * h->in_stride, samples, (size_t)n_frames * h->C * 4u);
+    stream_copy(h->host_in[h->cur] + (uint64_t)sid * h->in_stride, reinterpret_cast<const uint8_t *>(samples), (size_t)n_frames * h->C * 4u);
+    stream_fence();
     h->pushed[sid].store(1, std::memory_order_release);
+    return SKGPU_OK;
+}
+
+extern "C" skgpu_rc skgpu_hub_push_batch(skgpu_hub *h, const skgpu_hub_frame *frames, uint32_t n, uint32_t n_threads) {
+    if (!h || (!frames && n)) return hub_fail(SKGPU_ERR_INVALID, "null argument");
+    // validate on the calling thread (errors are thread-local), copy on the workers
+    for (uint32_t i = 0; i < n; ++i) {
+        Session *s = live_session(h, frames[i].session);
+        if (!s || frames[i].input >= s->streams.size() || !frames[i].samples) return hub_fail(SKGPU_ERR_INVALID, "frame %u: no such session / input", i);
+        if (frames[i].n_frames != h->streams[s->streams[frames[i].input]].chunk)
+            return hub_fail(SKGPU_ERR_INVALID, "frame %u: chunk of %u frames, the stream delivers %u per tick", i, frames[i].n_frames, h->streams[s->streams[frames[i].input]].chunk);
+    }
+    uint8_t *dst = h->host_in[h->cur];
+    auto work = [&](uint32_t lo, uint32_t hi) {
+        for (uint32_t i = lo; i < hi; ++i) {
+            const uint32_t sid = h->sessions[frames[i].session].streams[frames[i].input];
+            stream_copy(dst + (uint64_t)sid * h->in_stride, reinterpret_cast<const uint8_t *>(frames[i].samples), (size_t)frames[i].n_frames * h->C * 4u);
+            h->pushed[sid].store(1, std::memory_order_relaxed);
+        }
+        stream_fence();
+    };
+    const uint32_t T = std::max(1u, std::min(n_threads, n / 256u + 1u));
+    if (T == 1) { work(0, n); return SKGPU_OK; }
+    std::vector<std::thread> pool;
+    const uint32_t per = (n + T - 1) / T;
+    for (uint32_t t = 0; t < T; ++t) pool.emplace_back(work, std::min(n, t * per), std::min(n, (t + 1) * per));
+    for (auto &th : pool) th.join();
     return SKGPU_OK;
 }
 
@@ -343,7 +404,9 @@ extern "C" skgpu_rc skgpu_hub_tick(skgpu_hub *h) {
     for (uint32_t i = 0; i < n_in; ++i) {
         const uint32_t sid = h->tab_stream[i];
         Stream &st = h->streams[sid];
-        const bool got = h->pushed[sid].exchange(0, std::memory_order_acquire) != 0;
+        // pushes for this tick happened-before this call (the engine's tick thread decides the cut): plain load + store
+        const bool got = h->pushed[sid].load(std::memory_order_acquire) != 0;
+        if (got) h->pushed[sid].store(0, std::memory_order_relaxed);
         h->present[i] = got ? 1 : 0;
         if (got) {
             st.ever_pushed = true;

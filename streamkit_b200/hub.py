@@ -14,7 +14,8 @@ OUT_S16 = 1
 
 EXPORTS = [
     "skgpu_hub_last_error", "skgpu_hub_create", "skgpu_hub_destroy", "skgpu_hub_session_open", "skgpu_hub_session_close",
-    "skgpu_hub_set_input_gain", "skgpu_hub_set_master_gain", "skgpu_hub_chunk_frames", "skgpu_hub_push", "skgpu_hub_tick",
+    "skgpu_hub_set_input_gain", "skgpu_hub_set_master_gain", "skgpu_hub_chunk_frames", "skgpu_hub_push", "skgpu_hub_push_batch",
+    "skgpu_hub_tick",
     "skgpu_hub_wait", "skgpu_hub_session_output", "skgpu_hub_live_sessions", "skgpu_hub_live_streams", "skgpu_hub_ticks",
 ]
 
@@ -24,6 +25,13 @@ class HubConfig(C.Structure):
                 ("out_rate", C.c_uint32), ("out_frames", C.c_uint32), ("channels", C.c_uint16), ("flags", C.c_uint16),
                 ("in_rates", C.POINTER(C.c_uint32)), ("n_in_rates", C.c_uint32)]
 
+
+class HubFrame(C.Structure):
+    _fields_ = [("samples", C.c_void_p), ("session", C.c_uint32), ("input", C.c_uint32), ("n_frames", C.c_uint32), ("reserved", C.c_uint32)]
+
+
+FRAME_DT = np.dtype([("samples", "<u8"), ("session", "<u4"), ("input", "<u4"), ("n_frames", "<u4"), ("reserved", "<u4")], align=True)
+assert FRAME_DT.itemsize == C.sizeof(HubFrame) == 24
 
 _lib = None
 
@@ -47,6 +55,7 @@ def load() -> C.CDLL:
     lib.skgpu_hub_set_master_gain.argtypes = [vp, u32, C.c_float]
     lib.skgpu_hub_chunk_frames.argtypes = [vp, u32, u32, C.POINTER(u32)]
     lib.skgpu_hub_push.argtypes = [vp, u32, u32, vp, u32]
+    lib.skgpu_hub_push_batch.argtypes = [vp, vp, u32, u32]
     lib.skgpu_hub_tick.argtypes = [vp]
     lib.skgpu_hub_wait.argtypes = [vp, C.POINTER(L.TickTiming)]
     lib.skgpu_hub_session_output.argtypes = [vp, u32, C.POINTER(vp), C.POINTER(u32), C.POINTER(u32)]
@@ -112,6 +121,11 @@ class Hub:
     def push(self, session: int, inp: int, samples: np.ndarray):
         x = np.ascontiguousarray(samples, dtype=np.float32).reshape(-1)
         _chk(self.lib.skgpu_hub_push(self.h, session, inp, x.ctypes.data_as(C.c_void_p), x.size // self.C))
+
+    def push_batch(self, frames: np.ndarray, n_threads: int = 1):
+        """frames: FRAME_DT array (samples = host addresses of interleaved f32 chunks that stay alive during the call)"""
+        assert frames.dtype == FRAME_DT
+        _chk(self.lib.skgpu_hub_push_batch(self.h, frames.ctypes.data_as(C.c_void_p), frames.size, n_threads))
 
     def tick(self):
         _chk(self.lib.skgpu_hub_tick(self.h))
