@@ -113,7 +113,7 @@ sk_plugin_handle create_instance(const char *params_json, sk_log_callback log_cb
     }
 }
 
-sk_result emit_audio(const AudioFrame &f, sk_output_callback cb, void *ud) {
+[[maybe_unused]] sk_result emit_audio(const AudioFrame &f, sk_output_callback cb, void *ud) {
     sk_audio_frame af{f.sample_rate, f.channels, f.samples.data(), f.samples.size()};
     sk_packet pkt{SK_PACKET_RAW_AUDIO, &af, sizeof(sk_audio_frame)};
     return cb("out", &pkt, ud);
