@@ -57,67 +57,28 @@ __device__ __forceinline__ void mix_epilogue(const skgpu_mix_group &grp, const f
 __global__ void __launch_bounds__(MIX_THREADS) k_mix(const OpHeader *__restrict__ hdr, const skgpu_mix_group *__restrict__ groups,
                                                      const skgpu_mix_input *__restrict__ inputs, const uint8_t *__restrict__ present,
                                                      const float *__restrict__ gains, SlotTables st, uint8_t *__restrict__ arena,
-                                                     uint32_t tiles_per_group) {
+                                                     uint32_t tiles_per_group, uint32_t tiles_per_cta) {
     __shared__ MixIn s_in[MIX_MAX_INPUTS > 64 ? 64 : MIX_MAX_INPUTS];  // first 64 inputs cached in smem
     __shared__ uint16_t s_order[MIX_MAX_INPUTS];
     __shared__ uint8_t s_flag[MIX_MAX_INPUTS];
     __shared__ uint32_t s_n, s_has_base;
 
-    const uint32_t g_i = blockIdx.x / tiles_per_group;
-    const uint32_t tile = blockIdx.x - g_i * tiles_per_group;
+    // a CTA owns tiles_per_cta consecutive tiles of one group: small groups (few inputs) are handled whole by one CTA so
+    // that the prologue is paid once per group, large ones one tile per CTA for parallelism
+    const uint32_t ctas_per_group = (tiles_per_group + tiles_per_cta - 1u) / tiles_per_cta;
+    const uint32_t g_i = blockIdx.x / ctas_per_group;
+    const uint32_t tile0 = (blockIdx.x - g_i * ctas_per_group) * tiles_per_cta;
     if (g_i >= hdr->count) return;
     const skgpu_mix_group grp = groups[g_i];
     const uint32_t oc = grp.out_channels;
     const uint32_t out_size = grp.out_frames * oc;
-    const uint32_t s0 = tile * MIX_TILE + threadIdx.x * 4u;
-    if (tile * MIX_TILE >= out_size) return;
+    if (tile0 * MIX_TILE >= out_size) return;
     const uint32_t n_in = min(grp.n_inputs, (uint32_t)MIX_MAX_INPUTS);
 
     // ---- prologue: which inputs are present, base-frame selection, swap_remove order (mixer.rs:960-980)
-    // flags are computed by all threads in parallel (one global round trip), the tiny ordered compaction
-    // runs on thread 0 out of shared memory.
-    for (uint32_t j = threadIdx.x; j < n_in; j += MIX_THREADS) {
-        const uint32_t gi = grp.first_input + j;
-        const skgpu_mix_input in = inputs[gi];
-        bool pres = present ? (present[gi] != 0) : true;
-        if (pres && (in.flags & SKGPU_MIX_IN_FIFO)) {
-            const unsigned long long avail = st.fifo_w[in.slot] - st.fifo_r[in.slot];
-            pres = avail >= (unsigned long long)in.n_frames;  // a whole re-framed packet is ready
-        }
-        // frame.channels == output_channels && frame.samples.len() == output_size
-        const bool elig = in.channels == oc && in.n_frames * in.channels == out_size;
-        s_flag[j] = (uint8_t)((pres ? 1u : 0u) | (elig ? 2u : 0u) | ((in.flags & SKGPU_MIX_IN_UNIQUE) ? 4u : 0u));
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        uint32_t m = 0;
-        int base = -1, base_unique = -1;
-        for (uint32_t j = 0; j < n_in; ++j) {
-            const uint32_t fl = s_flag[j];
-            if (!(fl & 1u)) continue;
-            if (fl & 2u) {
-                const int u = (fl & 4u) ? 1 : 0;
-                if (u >= base_unique) { base = (int)m; base_unique = u; }  // max_by_key((unique, idx)): last max
-            }
-            s_order[m++] = (uint16_t)j;
-        }
-        if (base >= 0 && m > 0) {
-            // Vec::swap_remove(base): the last element takes the slot; the base goes first in our order and
-            // order[1..] is vec[0..m-1] after the swap_remove.
-            const uint16_t b = s_order[base];
-            s_order[base] = s_order[m - 1];
-            for (uint32_t q = m - 1; q > 0; --q) s_order[q] = s_order[q - 1];
-            s_order[0] = b;
-        }
-        s_n = m;
-        s_has_base = (base >= 0) ? 1u : 0u;
-    }
-    __syncthreads();
-    const uint32_t m = s_n;
-    // resolve inputs (in summation order) into smem
     bool simple = true;
-    for (uint32_t q = threadIdx.x; q < m && q < 64u; q += MIX_THREADS) {
-        const skgpu_mix_input in = inputs[grp.first_input + s_order[q]];
+    uint32_t m;
+    auto resolve = [&](const skgpu_mix_input &in) -> MixIn {
         MixIn r;
         r.n_frames = in.n_frames;
         r.channels = in.channels;
@@ -133,12 +94,101 @@ __global__ void __launch_bounds__(MIX_THREADS) k_mix(const OpHeader *__restrict_
             r.ptr = reinterpret_cast<const float *>(arena + in.in_off);
             r.ring_mask = 0; r.ring_start = 0;
         }
-        simple = simple && !r.fifo && r.channels == oc && r.n_frames >= grp.out_frames && ((((uintptr_t)r.ptr) & 15u) == 0);
-        s_in[q] = r;
+        return r;
+    };
+    auto is_simple = [&](const MixIn &r) { return !r.fifo && r.channels == oc && r.n_frames >= grp.out_frames && ((((uintptr_t)r.ptr) & 15u) == 0); };
+    if (n_in <= 32u) {
+        // small groups (the common 2..8-input mixers): warp 0 does everything with three ballots -- lane j owns input j,
+        // its position in the summation order follows from popcounts, and it resolves its own input straight into
+        // shared memory: one global round trip, one barrier, no serial loop.
+        if (threadIdx.x < 32u) {
+            const uint32_t lane = threadIdx.x;
+            skgpu_mix_input in{};
+            bool pres = false, elig = false;
+            if (lane < n_in) {
+                const uint32_t gi = grp.first_input + lane;
+                in = inputs[gi];
+                pres = present ? (present[gi] != 0) : true;
+                if (pres && (in.flags & SKGPU_MIX_IN_FIFO)) {
+                    const unsigned long long avail = st.fifo_w[in.slot] - st.fifo_r[in.slot];
+                    pres = avail >= (unsigned long long)in.n_frames;  // a whole re-framed packet is ready
+                }
+                elig = pres && in.channels == oc && in.n_frames * in.channels == out_size;   // already has the output's shape
+            }
+            const uint32_t pres_mask = __ballot_sync(0xffffffffu, pres);
+            const uint32_t elig_mask = __ballot_sync(0xffffffffu, elig);
+            const uint32_t uniq_mask = __ballot_sync(0xffffffffu, elig && (in.flags & SKGPU_MIX_IN_UNIQUE));
+            const uint32_t mm = __popc(pres_mask);
+            // max_by_key((unique, idx)): the last unique full-shape frame, else the last full-shape frame
+            const int base_lane = uniq_mask ? 31 - __clz(uniq_mask) : (elig_mask ? 31 - __clz(elig_mask) : -1);
+            if (pres) {
+                const uint32_t rank = __popc(pres_mask & ((1u << lane) - 1u));
+                uint32_t pos = rank;
+                if (base_lane >= 0) {
+                    const uint32_t base_rank = __popc(pres_mask & ((1u << base_lane) - 1u));
+                    pos = ((int)lane == base_lane) ? 0u : 1u + ((rank == mm - 1u) ? base_rank : rank);   // Vec::swap_remove
+                }
+                const MixIn r = resolve(in);
+                s_in[pos] = r;
+                s_order[pos] = (uint16_t)lane;
+                simple = is_simple(r);
+            }
+            if (lane == 0) { s_n = mm; s_has_base = base_lane >= 0 ? 1u : 0u; }
+        }
+    } else {
+        // flags are computed by all threads in parallel (one global round trip), the ordered compaction
+        // runs on thread 0 out of shared memory.
+        for (uint32_t j = threadIdx.x; j < n_in; j += MIX_THREADS) {
+            const uint32_t gi = grp.first_input + j;
+            const skgpu_mix_input in = inputs[gi];
+            bool pres = present ? (present[gi] != 0) : true;
+            if (pres && (in.flags & SKGPU_MIX_IN_FIFO)) {
+                const unsigned long long avail = st.fifo_w[in.slot] - st.fifo_r[in.slot];
+                pres = avail >= (unsigned long long)in.n_frames;  // a whole re-framed packet is ready
+            }
+            // frame.channels == output_channels && frame.samples.len() == output_size
+            const bool elig = in.channels == oc && in.n_frames * in.channels == out_size;
+            s_flag[j] = (uint8_t)((pres ? 1u : 0u) | (elig ? 2u : 0u) | ((in.flags & SKGPU_MIX_IN_UNIQUE) ? 4u : 0u));
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            uint32_t mm = 0;
+            int base = -1, base_unique = -1;
+            for (uint32_t j = 0; j < n_in; ++j) {
+                const uint32_t fl = s_flag[j];
+                if (!(fl & 1u)) continue;
+                if (fl & 2u) {
+                    const int u = (fl & 4u) ? 1 : 0;
+                    if (u >= base_unique) { base = (int)mm; base_unique = u; }  // max_by_key((unique, idx)): last max
+                }
+                s_order[mm++] = (uint16_t)j;
+            }
+            if (base >= 0 && mm > 0) {
+                // Vec::swap_remove(base): the last element takes the slot; the base goes first in our order and
+                // order[1..] is vec[0..m-1] after the swap_remove.
+                const uint16_t b = s_order[base];
+                s_order[base] = s_order[mm - 1];
+                for (uint32_t q = mm - 1; q > 0; --q) s_order[q] = s_order[q - 1];
+                s_order[0] = b;
+            }
+            s_n = mm;
+            s_has_base = (base >= 0) ? 1u : 0u;
+        }
+        __syncthreads();
+        // resolve inputs (in summation order) into smem
+        for (uint32_t q = threadIdx.x; q < s_n && q < 64u; q += MIX_THREADS) {
+            const MixIn r = resolve(inputs[grp.first_input + s_order[q]]);
+            simple = simple && is_simple(r);
+            s_in[q] = r;
+        }
     }
-    const bool all_simple = __syncthreads_and(simple ? 1 : 0) && m <= 64u && (out_size % 4u == 0);
-    if (s0 >= out_size) return;
+    const bool all_simple_v = __syncthreads_and(simple ? 1 : 0) != 0;
+    m = s_n;
+    const bool all_simple = all_simple_v && m <= 64u && (out_size % 4u == 0);
     const bool has_base = s_has_base != 0;
+    for (uint32_t tile = tile0; tile < tile0 + tiles_per_cta; ++tile) {
+    const uint32_t s0 = tile * MIX_TILE + threadIdx.x * 4u;
+    if (s0 >= out_size) break;
 
     if (all_simple) {
         // fast path: every present input has the output's shape -> pure 128-bit streaming, 8 loads in flight,
@@ -176,7 +226,7 @@ __global__ void __launch_bounds__(MIX_THREADS) k_mix(const OpHeader *__restrict_
         }
         float accf[4] = {a.x, a.y, a.z, a.w};
         mix_epilogue(grp, gains, arena, s0, 4u, accf);
-        return;
+        continue;
     }
 
     float acc[4] = {0.0f, 0.0f, 0.0f, 0.0f};  // vec![0.0f32; output_size] when there is no base frame
@@ -261,6 +311,7 @@ __global__ void __launch_bounds__(MIX_THREADS) k_mix(const OpHeader *__restrict_
     }
 
     mix_epilogue(grp, gains, arena, s0, nvalid, acc);
+    }   // tiles of this CTA
 }
 // advances ring read cursors of FIFO-sourced mix inputs that delivered a packet this tick
 __global__ void k_fifo_commit(const OpHeader *__restrict__ hdr, const skgpu_mix_input *__restrict__ inputs,

@@ -298,6 +298,7 @@ struct Op {
     uint32_t smem_frames = 0;     // resample: frames (history + chunk) the staged path can hold
     uint32_t smem_bytes = 0;
     int rs_channels = 0;          // resample: 1 / 2 specialisation, 0 = generic
+    uint32_t mix_tpc = 1;         // mix: tiles one CTA handles (whole group for small groups)
     bool rs_prog = false;         // resample: program-driven kernels (k_phase_prog + k_resample_prog)
     ChainProgDims rs_pd{};        // resample: frame-program capacities of the op
     uint64_t results_off = 0;
@@ -694,6 +695,11 @@ extern "C" skgpu_rc skgpu_plan_add_mix(skgpu_plan *p, const skgpu_mix_group *gro
     op.n2 = ni;
     op.max_unit = std::max(mx, 1u);
     op.tiles = (op.max_unit + MIX_TILE - 1) / MIX_TILE;
+    {   // groups with few inputs: one CTA per group (the prologue costs more than the tile's loads); fixed at add time
+        uint32_t max_k = 0;
+        for (uint32_t i = 0; i < ng; ++i) max_k = std::max(max_k, groups[i].n_inputs);
+        op.mix_tpc = (ng >= 4096u && max_k <= 8u) ? std::min(op.tiles, 8u) : 1u;
+    }
     op.has_fifo_inputs = fifo;
     {   // presence table: every input present until skgpu_plan_set_present says otherwise
         rc = dyn_alloc(op.present, op.cap2);
@@ -1089,7 +1095,7 @@ static skgpu_rc launch_ops(skgpu_plan *p, bool time_ops) {
         } else {
             const uint8_t *present = op.present.valid ? (const uint8_t *)op.present.dev : nullptr;
             if (time_ops) { skgpu_rc rc = op_event(op, 0, false, s); if (rc) return rc; }
-            k_mix<<<op.cap * op.tiles, MIX_THREADS, 0, s>>>(op.d_hdr, (const skgpu_mix_group *)op.d_tab, (const skgpu_mix_input *)op.d_tab2, present, gains, c->st, p->arena, op.tiles);
+            k_mix<<<op.cap * ((op.tiles + op.mix_tpc - 1) / op.mix_tpc), MIX_THREADS, 0, s>>>(op.d_hdr, (const skgpu_mix_group *)op.d_tab, (const skgpu_mix_input *)op.d_tab2, present, gains, c->st, p->arena, op.tiles, op.mix_tpc);
             CU(cudaGetLastError());
             if (op.has_fifo_inputs) {
                 k_fifo_commit<<<(op.cap2 + 127) / 128, 128, 0, s>>>(op.d_hdr, (const skgpu_mix_input *)op.d_tab2, present, c->st);
