@@ -345,7 +345,7 @@ def run_gpu(args) -> None:
             "gpu_launches": launches_per_tick * args.steps * 2,
             "clocks": clk,
             "roofline": {"bound": "hbm", "kernel": dom_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak,
+                         "frac": achieved / peak, "frac_of_nominal_8000_gbs": achieved / 8000.0,
                          "traffic": TRAFFIC_NCU.get(dom_name) if (S == 65536 and K_INPUTS == 2) else None,
                          "algorithmic_bytes_per_launch": dom_bytes,
                          "avg_launch_ms": main_ms, "launches_timed": n_main, "peak_source": peak_src},
