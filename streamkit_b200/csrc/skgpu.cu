@@ -380,6 +380,7 @@ extern "C" skgpu_rc skgpu_plan_create(skgpu_ctx *c, size_t arena_bytes, skgpu_pl
     p->arena_bytes = arena_bytes;
     cudaError_t e = cudaMalloc((void **)&p->arena, arena_bytes);
     if (e != cudaSuccess) { delete p; return fail(SKGPU_ERR_NOMEM, "cudaMalloc(%zu) for the tick arena failed: %s", arena_bytes, cudaGetErrorString(e)); }
+    CU(cudaMemset(p->arena, 0, arena_bytes));   // padding between frames and never-written capacity read back as zeros, not garbage
     CU(cudaEventCreate(&p->e0)); CU(cudaEventCreate(&p->e1)); CU(cudaEventCreate(&p->e2)); CU(cudaEventCreate(&p->e3));
     CU(cudaEventCreateWithFlags(&p->ev_kernels_done, cudaEventDisableTiming));
     CU(cudaEventCreateWithFlags(&p->ev_d2h_done, cudaEventDisableTiming));
