@@ -72,6 +72,15 @@ skgpu_rc skgpu_hub_chunk_frames(skgpu_hub *hub, uint32_t session, uint32_t input
  * mixer.rs:1195-1201, with depth 1). */
 skgpu_rc skgpu_hub_push(skgpu_hub *hub, uint32_t session, uint32_t input, const float *samples, uint32_t n_frames);
 
+/* zero-copy variant: *dst_out is the stream's slot in the pinned arena of the NEXT tick (chunk frames x channels f32);
+ * the producer (e.g. a decoder) writes its samples there and calls skgpu_hub_commit. This is how the pinned arenas
+ * replace AudioFramePool buffers (crates/core/src/frame_pool.rs:302-317) on the batched path: no gather copy at all.
+ * The pointer is valid until the next skgpu_hub_tick. */
+skgpu_rc skgpu_hub_acquire(skgpu_hub *hub, uint32_t session, uint32_t input, float **dst_out, uint32_t *n_frames_out);
+skgpu_rc skgpu_hub_commit(skgpu_hub *hub, uint32_t session, uint32_t input);
+/* every live stream delivered its chunk in place (producers that always write their slot) */
+skgpu_rc skgpu_hub_commit_all(skgpu_hub *hub);
+
 /* many chunks at once, copied by n_threads worker threads (the gather of a whole tick is ~1 GB at 65 k sessions:
  * one thread cannot keep up with PCIe). frames[i] must name distinct (session, input) pairs. */
 typedef struct skgpu_hub_frame {

@@ -365,6 +365,29 @@ extern "C" skgpu_rc skgpu_hub_push(skgpu_hub *h, uint32_t si, uint32_t input, co
     return SKGPU_OK;
 }
 
+extern "C" skgpu_rc skgpu_hub_acquire(skgpu_hub *h, uint32_t si, uint32_t input, float **dst_out, uint32_t *n_frames_out) {
+    Session *s = live_session(h, si);
+    if (!s || input >= s->streams.size() || !dst_out) return hub_fail(SKGPU_ERR_INVALID, "no such session / input");
+    const uint32_t sid = s->streams[input];
+    *dst_out = reinterpret_cast<float *>(h->host_in[h->cur] + (uint64_t)sid * h->in_stride);
+    if (n_frames_out) *n_frames_out = h->streams[sid].chunk;
+    return SKGPU_OK;
+}
+
+extern "C" skgpu_rc skgpu_hub_commit(skgpu_hub *h, uint32_t si, uint32_t input) {
+    Session *s = live_session(h, si);
+    if (!s || input >= s->streams.size()) return hub_fail(SKGPU_ERR_INVALID, "no such session / input");
+    h->pushed[s->streams[input]].store(1, std::memory_order_release);
+    return SKGPU_OK;
+}
+
+extern "C" skgpu_rc skgpu_hub_commit_all(skgpu_hub *h) {
+    if (!h) return hub_fail(SKGPU_ERR_INVALID, "null hub");
+    for (uint32_t sid = 0; sid < h->streams.size(); ++sid)
+        if (h->streams[sid].live) h->pushed[sid].store(1, std::memory_order_relaxed);
+    return SKGPU_OK;
+}
+
 extern "C" skgpu_rc skgpu_hub_push_batch(skgpu_hub *h, const skgpu_hub_frame *frames, uint32_t n, uint32_t n_threads) {
     if (!h || (!frames && n)) return hub_fail(SKGPU_ERR_INVALID, "null argument");
     // validate on the calling thread (errors are thread-local), copy on the workers

@@ -15,6 +15,7 @@ OUT_S16 = 1
 EXPORTS = [
     "skgpu_hub_last_error", "skgpu_hub_create", "skgpu_hub_destroy", "skgpu_hub_session_open", "skgpu_hub_session_close",
     "skgpu_hub_set_input_gain", "skgpu_hub_set_master_gain", "skgpu_hub_chunk_frames", "skgpu_hub_push", "skgpu_hub_push_batch",
+    "skgpu_hub_acquire", "skgpu_hub_commit", "skgpu_hub_commit_all",
     "skgpu_hub_tick",
     "skgpu_hub_wait", "skgpu_hub_session_output", "skgpu_hub_live_sessions", "skgpu_hub_live_streams", "skgpu_hub_ticks",
 ]
@@ -56,6 +57,9 @@ def load() -> C.CDLL:
     lib.skgpu_hub_chunk_frames.argtypes = [vp, u32, u32, C.POINTER(u32)]
     lib.skgpu_hub_push.argtypes = [vp, u32, u32, vp, u32]
     lib.skgpu_hub_push_batch.argtypes = [vp, vp, u32, u32]
+    lib.skgpu_hub_acquire.argtypes = [vp, u32, u32, C.POINTER(vp), C.POINTER(u32)]
+    lib.skgpu_hub_commit.argtypes = [vp, u32, u32]
+    lib.skgpu_hub_commit_all.argtypes = [vp]
     lib.skgpu_hub_tick.argtypes = [vp]
     lib.skgpu_hub_wait.argtypes = [vp, C.POINTER(L.TickTiming)]
     lib.skgpu_hub_session_output.argtypes = [vp, u32, C.POINTER(vp), C.POINTER(u32), C.POINTER(u32)]
@@ -121,6 +125,18 @@ class Hub:
     def push(self, session: int, inp: int, samples: np.ndarray):
         x = np.ascontiguousarray(samples, dtype=np.float32).reshape(-1)
         _chk(self.lib.skgpu_hub_push(self.h, session, inp, x.ctypes.data_as(C.c_void_p), x.size // self.C))
+
+    def acquire(self, session: int, inp: int) -> np.ndarray:
+        """zero-copy: a writable float32 view of the stream's pinned slot for the next tick; fill it, then commit()"""
+        p, n = C.c_void_p(), C.c_uint32()
+        _chk(self.lib.skgpu_hub_acquire(self.h, session, inp, C.byref(p), C.byref(n)))
+        return np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_float)), shape=(n.value * self.C,))
+
+    def commit(self, session: int, inp: int):
+        _chk(self.lib.skgpu_hub_commit(self.h, session, inp))
+
+    def commit_all(self):
+        _chk(self.lib.skgpu_hub_commit_all(self.h))
 
     def push_batch(self, frames: np.ndarray, n_threads: int = 1):
         """frames: FRAME_DT array (samples = host addresses of interleaved f32 chunks that stay alive during the call)"""

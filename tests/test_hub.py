@@ -27,7 +27,7 @@ def test_hub_library_exports_every_declared_symbol():
     src = open(os.path.join(ROOT, "include", "skgpu_hub.h")).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
     names = sorted(set(re.findall(r"\b(skgpu_hub_[a-z0-9_]+)\s*\(", src)))
-    assert len(names) >= 15
+    assert len(names) >= 19
     out = subprocess.check_output(["nm", "-D", "--defined-only", H.HUB_LIB_PATH], text=True)
     exported = {ln.split()[-1] for ln in out.splitlines() if " T " in ln}
     assert not [n for n in names if n not in exported]
@@ -118,7 +118,13 @@ def test_hub_sessions_match_oracle_with_churn_absences_and_gain_updates():
                     assert n == r * 960 // 48000
                     x = _chunk(seed * 10 + i, sent[i], r, n, 2)
                     sent[i] += 1
-                    hub.push(sid, i, x)
+                    if (t + i) % 3 == 0:                              # zero-copy path: write straight into the pinned slot
+                        dst = hub.acquire(sid, i)
+                        assert dst.size == n * 2
+                        dst[:] = x
+                        hub.commit(sid, i)
+                    else:
+                        hub.push(sid, i, x)
                     osess.push(i, x)
                 want[sid] = osess.tick()
             hub.tick()
