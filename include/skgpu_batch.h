@@ -256,6 +256,11 @@ typedef struct skgpu_tick_timing { /* of the most recent submitted tick, CUDA ev
 /* blocks until everything submitted so far has finished; timing may be NULL */
 skgpu_rc skgpu_tick_wait(skgpu_plan *plan, skgpu_tick_timing *timing);
 
+/* blocks until tick number `tick` (1-based: the value of skgpu_plan_tick_count right after its submit) has finished,
+ * read-back included, WITHOUT waiting for a later tick that is already submitted: with SKGPU_SUBMIT_OVERLAP_D2H and two
+ * host_out buffers the caller collects tick n while tick n + 1 uploads. Only the two most recent ticks can be waited for. */
+skgpu_rc skgpu_tick_wait_for(skgpu_plan *plan, uint64_t tick);
+
 /* averaged device time of one op over the ticks submitted with SKGPU_SUBMIT_TIME_OPS since the last reset.
  * For a resample op, sub = 0 is the phase-table kernel, sub = 1 the interpolation kernel. */
 skgpu_rc skgpu_plan_op_time(skgpu_plan *plan, uint32_t op, uint32_t sub, float *avg_ms, uint32_t *n_samples);

@@ -93,6 +93,11 @@ skgpu_rc skgpu_hub_push_batch(skgpu_hub *hub, const skgpu_hub_frame *frames, uin
 skgpu_rc skgpu_hub_tick(skgpu_hub *hub);
 /* blocks until the last tick has finished; timing may be NULL */
 skgpu_rc skgpu_hub_wait(skgpu_hub *hub, skgpu_tick_timing *timing);
+/* pipelined collection: blocks until tick number `tick` (1-based, = skgpu_hub_ticks() right after its skgpu_hub_tick)
+ * has finished without waiting for the next tick if that one is already submitted; skgpu_hub_session_output then
+ * reports tick `tick`. Lets the engine submit tick n + 1 first and collect tick n while n + 1 uploads (the read-back of
+ * n overlaps the upload of n + 1). Only the two most recent ticks can be waited for. */
+skgpu_rc skgpu_hub_wait_tick(skgpu_hub *hub, uint64_t tick);
 /* the session's packet of the last waited tick: F * channels samples (s16 or f32) inside the hub's pinned output arena,
  * valid until the next skgpu_hub_wait. *n_mixed = inputs that contributed a packet (0 = silence), *status = OR of the
  * inputs' chain status bits (skgpu_chain_result.status). Sessions opened after that tick was submitted report 0 / NULL. */

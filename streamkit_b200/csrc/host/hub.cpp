@@ -115,6 +115,11 @@ struct skgpu_hub {
     uint32_t cur = 0;                           // arena the next tick uploads
     int last = -1;                              // arena of the last submitted tick
     bool in_flight = false;
+    bool out_ready = false;                     // host_out[last] holds a finished tick
+    uint64_t epoch = 1;                         // bumped by every table rebuild
+    uint64_t arena_epoch[2] = {0, 0};           // table epoch the tick in each output arena was submitted with
+    std::vector<int64_t> first_by_arena[2];     // per session: first table input of that tick (-1: not part of it)
+    std::vector<uint32_t> count_by_arena[2];
     uint64_t ticks = 0;
     uint32_t n_live_sessions = 0, n_live_streams = 0;
     explicit skgpu_hub(uint32_t n_streams) : pushed(n_streams) {}
@@ -150,6 +155,7 @@ static skgpu_rc rebuild_tables(skgpu_hub *h) {
     }
     PASS(skgpu_plan_update_chain(h->plan, h->op, h->groups.data(), (uint32_t)h->groups.size(), h->inputs.data(), (uint32_t)h->inputs.size()));
     h->tables_dirty = false;
+    h->epoch += 1;
     return SKGPU_OK;
 }
 
@@ -445,7 +451,16 @@ extern "C" skgpu_rc skgpu_hub_tick(skgpu_hub *h) {
         h->gains_dirty = false;
     }
     PASS(skgpu_tick_submit(h->plan, in_cur, h->host_out[h->cur], SKGPU_SUBMIT_GRAPH | SKGPU_SUBMIT_OVERLAP_D2H));
-    h->last = (int)h->cur;
+    if (h->last == (int)h->cur) h->out_ready = false;   // this tick reuses the arena the collected results lived in
+    if (h->arena_epoch[h->cur] != h->epoch) {           // remember which table rows this tick's results belong to
+        auto &fa = h->first_by_arena[h->cur];
+        auto &ca = h->count_by_arena[h->cur];
+        fa.assign(h->sessions.size(), -1);
+        ca.assign(h->sessions.size(), 0);
+        for (size_t si = 0; si < h->sessions.size(); ++si)
+            if (h->sessions[si].live) { fa[si] = h->sessions[si].tab_first; ca[si] = (uint32_t)h->sessions[si].streams.size(); }
+        h->arena_epoch[h->cur] = h->epoch;
+    }
     h->cur ^= 1u;
     h->in_flight = true;
     h->ticks += 1;
@@ -456,21 +471,33 @@ extern "C" skgpu_rc skgpu_hub_wait(skgpu_hub *h, skgpu_tick_timing *timing) {
     if (!h) return hub_fail(SKGPU_ERR_INVALID, "null hub");
     PASS(skgpu_tick_wait(h->plan, timing));
     h->in_flight = false;
+    h->out_ready = h->ticks > 0;
+    if (h->ticks > 0) h->last = (int)((h->ticks - 1) & 1u);
+    return SKGPU_OK;
+}
+
+extern "C" skgpu_rc skgpu_hub_wait_tick(skgpu_hub *h, uint64_t tick) {
+    if (!h) return hub_fail(SKGPU_ERR_INVALID, "null hub");
+    if (tick == 0 || tick > h->ticks || tick + 1 < h->ticks) return hub_fail(SKGPU_ERR_INVALID, "tick %llu is not one of the two most recent ticks", (unsigned long long)tick);
+    PASS(skgpu_tick_wait_for(h->plan, tick));
+    h->last = (int)((tick - 1) & 1u);          // tick k uploaded from / read back into arena (k - 1) & 1
+    h->in_flight = tick < h->ticks;           // a later tick may still be running
+    h->out_ready = true;
     return SKGPU_OK;
 }
 
 extern "C" skgpu_rc skgpu_hub_session_output(skgpu_hub *h, uint32_t si, const void **samples, uint32_t *n_mixed, uint32_t *status) {
     Session *s = live_session(h, si);
     if (!s) return hub_fail(SKGPU_ERR_INVALID, "session %u is not open", si);
-    if (h->in_flight) return hub_fail(SKGPU_ERR_STATE, "a tick is in flight: call skgpu_hub_wait first");
+    if (!h->out_ready) return hub_fail(SKGPU_ERR_STATE, "no finished tick: call skgpu_hub_wait / skgpu_hub_wait_tick first");
     if (samples) *samples = nullptr;
     if (n_mixed) *n_mixed = 0;
     if (status) *status = 0;
-    if (h->last < 0 || s->tab_first < 0) return SKGPU_OK;   // opened after the last tick was submitted
+    if (h->last < 0 || si >= h->first_by_arena[h->last].size() || h->first_by_arena[h->last][si] < 0) return SKGPU_OK;   // not part of that tick
     const uint8_t *o = h->host_out[h->last];
-    const skgpu_chain_result *res = reinterpret_cast<const skgpu_chain_result *>(o) + s->tab_first;
+    const skgpu_chain_result *res = reinterpret_cast<const skgpu_chain_result *>(o) + h->first_by_arena[h->last][si];
     uint32_t nm = 0, stt = 0;
-    for (size_t i = 0; i < s->streams.size(); ++i) { nm += res[i].emitted; stt |= res[i].status; }
+    for (uint32_t i = 0; i < h->count_by_arena[h->last][si]; ++i) { nm += res[i].emitted; stt |= res[i].status; }
     if (samples) *samples = o + (h->out_off - h->res_off) + (uint64_t)si * h->out_stride;
     if (n_mixed) *n_mixed = nm;
     if (status) *status = stt;

@@ -332,6 +332,7 @@ struct skgpu_plan {
     cudaGraphExec_t graph_exec = nullptr;
     cudaEvent_t e0 = nullptr, e1 = nullptr, e2 = nullptr, e3 = nullptr;
     cudaEvent_t ev_kernels_done = nullptr, ev_d2h_done = nullptr;  // cross-stream ordering for overlapped read-back
+    cudaEvent_t ev_tick_done[2] = {nullptr, nullptr};              // completion of tick k (everything incl. read-back), by k & 1
     bool d2h_pending = false;
     bool timing_valid = false;
 };
@@ -384,6 +385,8 @@ extern "C" skgpu_rc skgpu_plan_create(skgpu_ctx *c, size_t arena_bytes, skgpu_pl
     CU(cudaEventCreate(&p->e0)); CU(cudaEventCreate(&p->e1)); CU(cudaEventCreate(&p->e2)); CU(cudaEventCreate(&p->e3));
     CU(cudaEventCreateWithFlags(&p->ev_kernels_done, cudaEventDisableTiming));
     CU(cudaEventCreateWithFlags(&p->ev_d2h_done, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&p->ev_tick_done[0], cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&p->ev_tick_done[1], cudaEventDisableTiming));
     CU(cudaMalloc((void **)&p->d_tick, 16));
     CU(cudaMemset(p->d_tick, 0, 16));
     *out = p;
@@ -411,6 +414,7 @@ extern "C" void skgpu_plan_destroy(skgpu_plan *p) {
     cudaFree(p->arena);
     cudaFree(p->d_tick);
     cudaEventDestroy(p->ev_kernels_done); cudaEventDestroy(p->ev_d2h_done);
+    cudaEventDestroy(p->ev_tick_done[0]); cudaEventDestroy(p->ev_tick_done[1]);
     cudaEventDestroy(p->e0); cudaEventDestroy(p->e1); cudaEventDestroy(p->e2); cudaEventDestroy(p->e3);
     delete p;
 }
@@ -1200,12 +1204,22 @@ extern "C" skgpu_rc skgpu_tick_submit(skgpu_plan *p, const void *host_in, void *
         CU(cudaMemcpyAsync(host_out, p->arena + p->d2h_off, p->d2h_bytes, cudaMemcpyDeviceToHost, c->stream_d2h));
         CU(cudaEventRecord(p->ev_d2h_done, c->stream_d2h));
         CU(cudaEventRecord(p->e3, c->stream_d2h));
+        CU(cudaEventRecord(p->ev_tick_done[p->tick & 1ull], c->stream_d2h));
         p->d2h_pending = true;
     } else {
         if (do_d2h) CU(cudaMemcpyAsync(host_out, p->arena + p->d2h_off, p->d2h_bytes, cudaMemcpyDeviceToHost, s));
         CU(cudaEventRecord(p->e3, s));
+        CU(cudaEventRecord(p->ev_tick_done[p->tick & 1ull], s));
     }
     p->timing_valid = true;
+    return SKGPU_OK;
+}
+
+extern "C" skgpu_rc skgpu_tick_wait_for(skgpu_plan *p, uint64_t tick) {
+    if (!p) return fail(SKGPU_ERR_INVALID, "null plan");
+    if (tick == 0 || tick > p->tick || tick + 1 < p->tick) return fail(SKGPU_ERR_INVALID, "tick %llu is not one of the two most recent ticks (%llu submitted)", (unsigned long long)tick, (unsigned long long)p->tick);
+    CU(cudaSetDevice(p->ctx->device));
+    CU(cudaEventSynchronize(p->ev_tick_done[tick & 1ull]));
     return SKGPU_OK;
 }
 

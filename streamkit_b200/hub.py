@@ -17,7 +17,7 @@ EXPORTS = [
     "skgpu_hub_set_input_gain", "skgpu_hub_set_master_gain", "skgpu_hub_chunk_frames", "skgpu_hub_push", "skgpu_hub_push_batch",
     "skgpu_hub_acquire", "skgpu_hub_commit", "skgpu_hub_commit_all",
     "skgpu_hub_tick",
-    "skgpu_hub_wait", "skgpu_hub_session_output", "skgpu_hub_live_sessions", "skgpu_hub_live_streams", "skgpu_hub_ticks",
+    "skgpu_hub_wait", "skgpu_hub_wait_tick", "skgpu_hub_session_output", "skgpu_hub_live_sessions", "skgpu_hub_live_streams", "skgpu_hub_ticks",
 ]
 
 
@@ -62,6 +62,7 @@ def load() -> C.CDLL:
     lib.skgpu_hub_commit_all.argtypes = [vp]
     lib.skgpu_hub_tick.argtypes = [vp]
     lib.skgpu_hub_wait.argtypes = [vp, C.POINTER(L.TickTiming)]
+    lib.skgpu_hub_wait_tick.argtypes = [vp, C.c_uint64]
     lib.skgpu_hub_session_output.argtypes = [vp, u32, C.POINTER(vp), C.POINTER(u32), C.POINTER(u32)]
     for n in ("skgpu_hub_live_sessions", "skgpu_hub_live_streams"):
         getattr(lib, n).argtypes = [vp]
@@ -150,6 +151,13 @@ class Hub:
         t = L.TickTiming()
         _chk(self.lib.skgpu_hub_wait(self.h, C.byref(t)))
         return t
+
+    def wait_tick(self, tick: int):
+        _chk(self.lib.skgpu_hub_wait_tick(self.h, tick))
+
+    @property
+    def ticks(self) -> int:
+        return self.lib.skgpu_hub_ticks(self.h)
 
     def output(self, session: int):
         """(samples copy or None, n_mixed, status) of the last waited tick"""

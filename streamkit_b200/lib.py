@@ -59,7 +59,7 @@ EXPORTS = [
     "skgpu_plan_add_chain_cap",
     "skgpu_plan_update_convert", "skgpu_plan_update_resample", "skgpu_plan_update_mix", "skgpu_plan_update_chain",
     "skgpu_plan_set_io", "skgpu_plan_set_banks", "skgpu_plan_tick_count",
-    "skgpu_plan_set_gains", "skgpu_plan_set_present", "skgpu_plan_finalize", "skgpu_tick_submit", "skgpu_tick_wait",
+    "skgpu_plan_set_gains", "skgpu_plan_set_present", "skgpu_plan_finalize", "skgpu_tick_submit", "skgpu_tick_wait", "skgpu_tick_wait_for",
     "skgpu_plan_op_time", "skgpu_plan_reset_op_times", "skgpu_plan_launches_per_tick", "skgpu_arena_upload",
     "skgpu_arena_download", "skgpu_arena_fill", "skgpu_timer_start", "skgpu_timer_stop", "skgpu_timer_elapsed_ms",
     "skgpu_ctx_sync", "skgpu_ctx_flush_l2",
@@ -98,6 +98,7 @@ def load() -> C.CDLL:
         "skgpu_plan_add_resample": (i32, [vp, vp, u32, u64, C.POINTER(u32)]),
         "skgpu_plan_add_mix": (i32, [vp, vp, u32, vp, u32, C.POINTER(u32)]),
         "skgpu_plan_add_chain": (i32, [vp, vp, u32, vp, u32, u32, u64, C.POINTER(u32)]),
+        "skgpu_tick_wait_for": (i32, [vp, C.c_uint64]),
         "skgpu_plan_add_chain_cap": (i32, [vp, vp, u32, vp, u32, u32, u32, u32, u32, u64, C.POINTER(u32)]),
         "skgpu_plan_update_chain": (i32, [vp, u32, vp, u32, vp, u32]),
         "skgpu_plan_set_banks": (i32, [vp, u64]),

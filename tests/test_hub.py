@@ -27,7 +27,7 @@ def test_hub_library_exports_every_declared_symbol():
     src = open(os.path.join(ROOT, "include", "skgpu_hub.h")).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
     names = sorted(set(re.findall(r"\b(skgpu_hub_[a-z0-9_]+)\s*\(", src)))
-    assert len(names) >= 19
+    assert len(names) >= 20
     out = subprocess.check_output(["nm", "-D", "--defined-only", H.HUB_LIB_PATH], text=True)
     exported = {ln.split()[-1] for ln in out.splitlines() if " T " in ln}
     assert not [n for n in names if n not in exported]
@@ -136,6 +136,41 @@ def test_hub_sessions_match_oracle_with_churn_absences_and_gain_updates():
                 assert got is not None and np.array_equal(got, w), f"tick {t} session {sid}: {(got != w).sum()} samples differ"
         assert hub.live_sessions == len(live)
         assert hub.live_streams == sum(len(o.rates) for o, _, _ in live.values())
+    finally:
+        hub.close()
+
+
+@pytest.mark.gpu
+def test_hub_pipelined_collection_matches_oracle():
+    """submit tick n + 1 first, then collect tick n (skgpu_hub_wait_tick): same bytes as the oracle, one tick late"""
+    hub = H.Hub(max_sessions=4, max_streams=8, in_rates=[44100, 32000], max_inputs_per_session=2)
+    try:
+        rates = [[44100, 32000], [44100], [32000, 32000]]
+        sids = [hub.session_open(r) for r in rates]
+        osess = [_OracleSession(r, 2, 960) for r in rates]
+        pending = None   # (tick number, {sid: (want, n)})
+        for t in range(12):
+            want = {}
+            for sid, o, r in zip(sids, osess, rates):
+                for i, rate in enumerate(r):
+                    x = _chunk(100 + sid * 4 + i, t, rate, rate * 960 // 48000, 2)
+                    hub.push(sid, i, x)
+                    o.push(i, x)
+                want[sid] = o.tick()
+            hub.tick()
+            k = hub.ticks
+            if pending is not None:
+                hub.wait_tick(pending[0])          # tick n while tick n + 1 is in flight
+                for sid, (w, n) in pending[1].items():
+                    got, n_mixed, status = hub.output(sid)
+                    assert status == 0 and n_mixed == n and np.array_equal(got, w), (t, sid)
+            pending = (k, want)
+        hub.wait_tick(pending[0])
+        for sid, (w, n) in pending[1].items():
+            got, n_mixed, status = hub.output(sid)
+            assert status == 0 and n_mixed == n and np.array_equal(got, w)
+        with pytest.raises(H.HubError):
+            hub.wait_tick(hub.ticks - 2)           # only the two most recent ticks can be waited for
     finally:
         hub.close()
 
