@@ -166,7 +166,7 @@ def run_hub_e2e(S: int, steps: int, warmup: int, device: int, threads: int) -> d
                 f = frames[s * K_INPUTS + i]
                 f["session"], f["input"], f["n_frames"] = sid, i, chunk
         frames["samples"] = pool.ctypes.data + (np.arange(frames.size, dtype=np.uint64) % 256) * np.uint64(pool.strides[0])
-        for _ in range(max(2, warmup)):
+        for _ in range(max(4, warmup)):   # also fills every arena of the input ring
             hub.push_batch(frames, threads)
             hub.tick()
             hub.wait()

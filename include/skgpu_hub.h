@@ -51,6 +51,8 @@ typedef struct skgpu_hub_config {
     uint16_t flags;                  /* SKGPU_HUB_OUT_S16 */
     const uint32_t *in_rates;        /* every input sample rate sessions may use; a chunk is in_rate * F / out_rate frames */
     uint32_t n_in_rates;
+    uint32_t jitter_frames;          /* chunks an input may queue ahead (ClockedMixerConfig.jitter_buffer_frames, default 3 in
+                                      * the reference, mixer.rs:46-55); 0 = 1. Costs jitter_frames + 2 pinned input arenas. */
 } skgpu_hub_config;
 
 /* message of the last error on the calling thread (borrowed, like skgpu_last_error) */
@@ -67,9 +69,9 @@ skgpu_rc skgpu_hub_set_master_gain(skgpu_hub *hub, uint32_t session, float gain)
 /* frames a chunk of this input must have (in_rate * F / out_rate) */
 skgpu_rc skgpu_hub_chunk_frames(skgpu_hub *hub, uint32_t session, uint32_t input, uint32_t *frames_out);
 
-/* one chunk (interleaved f32, n_frames == chunk frames of the input) for the NEXT tick; copied into the pinned arena.
- * A second push for the same input before the tick replaces the first (the clocked mixer's overwrite-oldest ring,
- * mixer.rs:1195-1201, with depth 1). */
+/* one chunk (interleaved f32, n_frames == chunk frames of the input), copied into the pinned arena of the first tick
+ * that has no chunk of this input yet: an input may queue up to jitter_frames chunks, every tick consumes one; a push
+ * into a full queue drops the oldest chunk (the clocked mixer's InputRingBuffer, mixer.rs:1185-1206). */
 skgpu_rc skgpu_hub_push(skgpu_hub *hub, uint32_t session, uint32_t input, const float *samples, uint32_t n_frames);
 
 /* zero-copy variant: *dst_out is the stream's slot in the pinned arena of the NEXT tick (chunk frames x channels f32);

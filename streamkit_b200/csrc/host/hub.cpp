@@ -100,19 +100,22 @@ struct skgpu_hub {
     uint32_t op = 0;
     uint32_t C = 2, F = 960, ob = 2;
     uint64_t in_stride = 0, in_bytes = 0, bank_stride = 0, res_off = 0, res_bytes = 0, out_off = 0, out_stride = 0, d2h_bytes = 0;
-    uint8_t *host_in[2] = {nullptr, nullptr};
+    static constexpr uint32_t MAX_RING = 10;    // jitter_frames (<= 8) + 2
+    uint8_t *host_in[MAX_RING] = {};            // ring of pinned input arenas: tick k uploads host_in[k % R]
+    uint32_t J = 1, R = 3;                      // queue depth per input (mixer.rs:1185-1206 InputRingBuffer) and ring size J + 2
     uint8_t *host_out[2] = {nullptr, nullptr};
     std::vector<Stream> streams;
     std::vector<Session> sessions;
     std::vector<uint32_t> free_streams, free_sessions;
-    std::vector<std::atomic<uint8_t>> pushed;   // per stream: a chunk for the NEXT tick sits in host_in[cur]
+    std::vector<std::atomic<uint8_t>> pushed;   // per stream: chunks queued for the next ticks (0..J); chunk i of the queue
+                                                // sits in the input arena of tick (ticks + 1 + i)
     std::vector<float> gains;                   // [stream gains | master gains]
     bool gains_dirty = true, tables_dirty = true;
     std::vector<skgpu_chain_group> groups;
     std::vector<skgpu_chain_input> inputs;
     std::vector<uint32_t> tab_stream;           // table input index -> hub stream id
     std::vector<uint8_t> present;
-    uint32_t cur = 0;                           // arena the next tick uploads
+    uint32_t cur = 0;                           // OUTPUT arena the next tick reads back into (ping-pong)
     int last = -1;                              // arena of the last submitted tick
     bool in_flight = false;
     bool out_ready = false;                     // host_out[last] holds a finished tick
@@ -124,6 +127,24 @@ struct skgpu_hub {
     uint32_t n_live_sessions = 0, n_live_streams = 0;
     explicit skgpu_hub(uint32_t n_streams) : pushed(n_streams) {}
 };
+
+// input arena of the tick that is `ahead` ticks after the next one to be submitted
+static inline uint8_t *in_arena(skgpu_hub *h, uint32_t ahead) { return h->host_in[(h->ticks + ahead) % h->R]; }
+
+// queue one chunk of stream sid (skgpu_hub_push and friends). Thread-safe for distinct streams.
+// copy == nullptr: only reserve the slot (zero-copy acquire). Returns the slot to write.
+static uint8_t *enqueue_slot(skgpu_hub *h, uint32_t sid) {
+    const uint64_t off = (uint64_t)sid * h->in_stride;
+    const size_t bytes = (size_t)h->streams[sid].chunk * h->C * 4u;
+    uint32_t q = h->pushed[sid].load(std::memory_order_relaxed);
+    if (q >= h->J) {
+        // queue full: the oldest chunk is dropped, the rest move up (overwrite-oldest, mixer.rs:1195-1201); rare
+        for (uint32_t i = 0; i + 1 < h->J; ++i) memcpy(in_arena(h, i) + off, in_arena(h, i + 1) + off, bytes);
+        q = h->J - 1;
+        h->pushed[sid].store((uint8_t)q, std::memory_order_relaxed);
+    }
+    return in_arena(h, q) + off;
+}
 
 static bool valid_gain(float g) { return std::isfinite(g) && g >= 0.0f && g <= 4.0f; }   // gain.rs:50-66
 
@@ -167,6 +188,7 @@ extern "C" skgpu_rc skgpu_hub_create(int32_t device, const skgpu_hub_config *cfg
     if (cfg->channels != 1 && cfg->channels != 2) return hub_fail(SKGPU_ERR_INVALID, "channels must be 1 or 2");
     if (cfg->max_inputs_per_session < 1 || cfg->max_inputs_per_session > 64) return hub_fail(SKGPU_ERR_INVALID, "max_inputs_per_session must be 1..64");
     if (cfg->n_in_rates > 64) return hub_fail(SKGPU_ERR_INVALID, "at most 64 distinct input rates");
+    if (cfg->jitter_frames > 8) return hub_fail(SKGPU_ERR_INVALID, "jitter_frames must be 0 (= 1) .. 8");
     uint32_t max_chunk = 0;
     for (uint32_t i = 0; i < cfg->n_in_rates; ++i) {
         const uint64_t num = (uint64_t)cfg->in_rates[i] * cfg->out_frames;
@@ -202,11 +224,16 @@ extern "C" skgpu_rc skgpu_hub_create(int32_t device, const skgpu_hub_config *cfg
     if (rc0 != SKGPU_OK) return bail(hub_pass(rc0));   // no CUDA device: SKGPU_ERR_NODEVICE, there is no CPU fallback
     rc0 = skgpu_plan_create(h->ctx, arena, &h->plan);
     if (rc0 != SKGPU_OK) return bail(hub_pass(rc0));
-    for (int b = 0; b < 2; ++b) {
+    h->J = cfg->jitter_frames ? cfg->jitter_frames : 1u;
+    h->R = h->J + 2u;   // J queued ticks + up to two ticks in flight (pipelined collection)
+    for (uint32_t b = 0; b < h->R; ++b) {
         void *p = nullptr;
         if (skgpu_pinned_alloc(h->ctx, h->in_bytes, &p) != SKGPU_OK) return bail(hub_pass(SKGPU_ERR_NOMEM));
         h->host_in[b] = (uint8_t *)p;
         memset(p, 0, h->in_bytes);
+    }
+    for (int b = 0; b < 2; ++b) {
+        void *p = nullptr;
         if (skgpu_pinned_alloc(h->ctx, h->d2h_bytes, &p) != SKGPU_OK) return bail(hub_pass(SKGPU_ERR_NOMEM));
         h->host_out[b] = (uint8_t *)p;
         memset(p, 0, h->d2h_bytes);
@@ -261,10 +288,10 @@ extern "C" void skgpu_hub_destroy(skgpu_hub *h) {
     if (!h) return;
     if (h->plan && h->in_flight) skgpu_tick_wait(h->plan, nullptr);
     if (h->ctx) {
-        for (int b = 0; b < 2; ++b) {
+        for (uint32_t b = 0; b < skgpu_hub::MAX_RING; ++b)
             if (h->host_in[b]) skgpu_pinned_free(h->ctx, h->host_in[b]);
+        for (int b = 0; b < 2; ++b)
             if (h->host_out[b]) skgpu_pinned_free(h->ctx, h->host_out[b]);
-        }
     }
     if (h->plan) skgpu_plan_destroy(h->plan);
     if (h->ctx) skgpu_ctx_destroy(h->ctx);
@@ -365,9 +392,9 @@ extern "C" skgpu_rc skgpu_hub_push(skgpu_hub *h, uint32_t si, uint32_t input, co
     const uint32_t sid = s->streams[input];
     const Stream &st = h->streams[sid];
     if (n_frames != st.chunk) return hub_fail(SKGPU_ERR_INVALID, "chunk of %u frames, the stream delivers %u per tick", n_frames, st.chunk);
-    stream_copy(h->host_in[h->cur] + (uint64_t)sid * h->in_stride, reinterpret_cast<const uint8_t *>(samples), (size_t)n_frames * h->C * 4u);
+    stream_copy(enqueue_slot(h, sid), reinterpret_cast<const uint8_t *>(samples), (size_t)n_frames * h->C * 4u);
     stream_fence();
-    h->pushed[sid].store(1, std::memory_order_release);
+    h->pushed[sid].fetch_add(1, std::memory_order_release);
     return SKGPU_OK;
 }
 
@@ -375,7 +402,7 @@ extern "C" skgpu_rc skgpu_hub_acquire(skgpu_hub *h, uint32_t si, uint32_t input,
     Session *s = live_session(h, si);
     if (!s || input >= s->streams.size() || !dst_out) return hub_fail(SKGPU_ERR_INVALID, "no such session / input");
     const uint32_t sid = s->streams[input];
-    *dst_out = reinterpret_cast<float *>(h->host_in[h->cur] + (uint64_t)sid * h->in_stride);
+    *dst_out = reinterpret_cast<float *>(enqueue_slot(h, sid));
     if (n_frames_out) *n_frames_out = h->streams[sid].chunk;
     return SKGPU_OK;
 }
@@ -383,14 +410,15 @@ extern "C" skgpu_rc skgpu_hub_acquire(skgpu_hub *h, uint32_t si, uint32_t input,
 extern "C" skgpu_rc skgpu_hub_commit(skgpu_hub *h, uint32_t si, uint32_t input) {
     Session *s = live_session(h, si);
     if (!s || input >= s->streams.size()) return hub_fail(SKGPU_ERR_INVALID, "no such session / input");
-    h->pushed[s->streams[input]].store(1, std::memory_order_release);
+    const uint32_t sid = s->streams[input];
+    if (h->pushed[sid].load(std::memory_order_relaxed) < h->J) h->pushed[sid].fetch_add(1, std::memory_order_release);
     return SKGPU_OK;
 }
 
 extern "C" skgpu_rc skgpu_hub_commit_all(skgpu_hub *h) {
     if (!h) return hub_fail(SKGPU_ERR_INVALID, "null hub");
     for (uint32_t sid = 0; sid < h->streams.size(); ++sid)
-        if (h->streams[sid].live) h->pushed[sid].store(1, std::memory_order_relaxed);
+        if (h->streams[sid].live && h->pushed[sid].load(std::memory_order_relaxed) == 0) h->pushed[sid].store(1, std::memory_order_relaxed);
     return SKGPU_OK;
 }
 
@@ -403,12 +431,11 @@ extern "C" skgpu_rc skgpu_hub_push_batch(skgpu_hub *h, const skgpu_hub_frame *fr
         if (frames[i].n_frames != h->streams[s->streams[frames[i].input]].chunk)
             return hub_fail(SKGPU_ERR_INVALID, "frame %u: chunk of %u frames, the stream delivers %u per tick", i, frames[i].n_frames, h->streams[s->streams[frames[i].input]].chunk);
     }
-    uint8_t *dst = h->host_in[h->cur];
     auto work = [&](uint32_t lo, uint32_t hi) {
         for (uint32_t i = lo; i < hi; ++i) {
             const uint32_t sid = h->sessions[frames[i].session].streams[frames[i].input];
-            stream_copy(dst + (uint64_t)sid * h->in_stride, reinterpret_cast<const uint8_t *>(frames[i].samples), (size_t)frames[i].n_frames * h->C * 4u);
-            h->pushed[sid].store(1, std::memory_order_relaxed);
+            stream_copy(enqueue_slot(h, sid), reinterpret_cast<const uint8_t *>(frames[i].samples), (size_t)frames[i].n_frames * h->C * 4u);
+            h->pushed[sid].fetch_add(1, std::memory_order_relaxed);
         }
         stream_fence();
     };
@@ -429,13 +456,14 @@ extern "C" skgpu_rc skgpu_hub_tick(skgpu_hub *h) {
         if (rc != SKGPU_OK) return rc;
     }
     const uint32_t n_in = (uint32_t)h->tab_stream.size();
-    uint8_t *in_cur = h->host_in[h->cur], *in_prev = h->host_in[h->cur ^ 1u];
+    uint8_t *in_cur = in_arena(h, 0), *in_prev = h->host_in[(h->ticks + h->R - 1u) % h->R];   // this tick's arena, the previous tick's
     for (uint32_t i = 0; i < n_in; ++i) {
         const uint32_t sid = h->tab_stream[i];
         Stream &st = h->streams[sid];
         // pushes for this tick happened-before this call (the engine's tick thread decides the cut): plain load + store
-        const bool got = h->pushed[sid].load(std::memory_order_acquire) != 0;
-        if (got) h->pushed[sid].store(0, std::memory_order_relaxed);
+        const uint32_t q = h->pushed[sid].load(std::memory_order_acquire);
+        const bool got = q != 0;   // the head of the stream's queue sits in this tick's arena
+        if (got) h->pushed[sid].store((uint8_t)(q - 1u), std::memory_order_relaxed);
         h->present[i] = got ? 1 : 0;
         if (got) {
             st.ever_pushed = true;

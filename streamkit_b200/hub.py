@@ -24,7 +24,7 @@ EXPORTS = [
 class HubConfig(C.Structure):
     _fields_ = [("max_sessions", C.c_uint32), ("max_streams", C.c_uint32), ("max_inputs_per_session", C.c_uint32),
                 ("out_rate", C.c_uint32), ("out_frames", C.c_uint32), ("channels", C.c_uint16), ("flags", C.c_uint16),
-                ("in_rates", C.POINTER(C.c_uint32)), ("n_in_rates", C.c_uint32)]
+                ("in_rates", C.POINTER(C.c_uint32)), ("n_in_rates", C.c_uint32), ("jitter_frames", C.c_uint32)]
 
 
 class HubFrame(C.Structure):
@@ -88,12 +88,12 @@ class Hub:
     """One GPU's frame-batching layer: sessions of n resampled inputs -> gain -> clocked mix -> gain -> s16."""
 
     def __init__(self, max_sessions: int, max_streams: int, in_rates, max_inputs_per_session: int = 8, out_rate: int = 48000,
-                 out_frames: int = 960, channels: int = 2, s16: bool = True, device: int = 0):
+                 out_frames: int = 960, channels: int = 2, s16: bool = True, device: int = 0, jitter_frames: int = 1):
         self.lib = load()
         rates = (C.c_uint32 * len(in_rates))(*in_rates)
         self._rates = rates
         cfg = HubConfig(max_sessions, max_streams, max_inputs_per_session, out_rate, out_frames, channels, OUT_S16 if s16 else 0,
-                        C.cast(rates, C.POINTER(C.c_uint32)), len(in_rates))
+                        C.cast(rates, C.POINTER(C.c_uint32)), len(in_rates), jitter_frames)
         self.h = C.c_void_p()
         _chk(self.lib.skgpu_hub_create(device, C.byref(cfg), C.byref(self.h)))
         self.F, self.C, self.s16 = out_frames, channels, s16

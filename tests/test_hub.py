@@ -176,6 +176,45 @@ def test_hub_pipelined_collection_matches_oracle():
 
 
 @pytest.mark.gpu
+def test_hub_jitter_queue_matches_the_clocked_mixer_ring():
+    """bursty arrival: an input may deliver 0..4 chunks between two ticks. With jitter_frames = 3 the hub queues up to three
+    chunks per input, consumes one per tick and drops the OLDEST on overflow -- InputRingBuffer of the clocked mixer
+    (mixer.rs:1185-1206, jitter_buffer_frames default 3). The oracle models exactly that with a deque(maxlen=3)."""
+    J = 3
+    rng = np.random.default_rng(21)
+    rates = [[44100, 44100], [32000]]
+    hub = H.Hub(max_sessions=2, max_streams=4, in_rates=[44100, 32000], max_inputs_per_session=2, jitter_frames=J)
+    try:
+        sids = [hub.session_open(r) for r in rates]
+        osess = [_OracleSession(r, 2, 960) for r in rates]
+        rings = [[collections.deque(maxlen=J) for _ in r] for r in rates]
+        sent = [[0] * len(r) for r in rates]
+        for t in range(30):
+            for a, (sid, r) in enumerate(zip(sids, rates)):
+                for i, rate in enumerate(r):
+                    burst = int(rng.choice([0, 1, 1, 1, 2, 4])) if t >= 2 else 1
+                    for _ in range(burst):
+                        x = _chunk(300 + a * 4 + i, sent[a][i], rate, rate * 960 // 48000, 2)
+                        sent[a][i] += 1
+                        hub.push(sid, i, x)
+                        rings[a][i].append(x)          # maxlen: the oldest chunk falls out
+            want = []
+            for a, o in enumerate(osess):
+                for i in range(len(rates[a])):
+                    if rings[a][i]:
+                        o.push(i, rings[a][i].popleft())   # one chunk per input per tick reaches the resampler
+                want.append(o.tick())
+            hub.tick()
+            hub.wait()
+            for sid, (w, n) in zip(sids, want):
+                got, n_mixed, status = hub.output(sid)
+                assert status == 0 and n_mixed == n, (t, sid, n_mixed, n)
+                assert np.array_equal(got, w), f"tick {t} session {sid}: {(got != w).sum()} samples differ"
+    finally:
+        hub.close()
+
+
+@pytest.mark.gpu
 def test_hub_rejects_what_the_fused_chain_cannot_do():
     with pytest.raises(H.HubError) as e:
         H.Hub(4, 8, [48000])                    # equal rates: the reference bypasses the resampler (resampler.rs:299-373)
