@@ -223,6 +223,8 @@ def test_hub_rejects_what_the_fused_chain_cannot_do():
         H.Hub(4, 8, [44101])                    # 20 ms of 44101 Hz is not a whole number of frames
     hub = H.Hub(2, 4, [44100], max_inputs_per_session=2)
     try:
+        hub.tick()                              # a tick with no session at all is a no-op, not an error
+        hub.wait()
         with pytest.raises(H.HubError):
             hub.session_open([22050])           # rate not declared at creation
         with pytest.raises(H.HubError):
@@ -234,6 +236,11 @@ def test_hub_rejects_what_the_fused_chain_cannot_do():
         with pytest.raises(H.HubError):
             hub.push(a, 0, np.zeros(100 * 2, np.float32))   # wrong chunk length
         hub.session_close(b)
-        hub.session_open([44100])
+        c = hub.session_open([44100])
+        hub.tick()                              # sessions that never pushed anything: silence, nothing mixed
+        hub.wait()
+        for sid in (a, c):
+            got, n_mixed, status = hub.output(sid)
+            assert n_mixed == 0 and status == 0 and got is not None and not np.any(got)
     finally:
         hub.close()
