@@ -71,11 +71,15 @@ skgpu_rc skgpu_hub_chunk_frames(skgpu_hub *hub, uint32_t session, uint32_t input
 
 /* one chunk (interleaved f32, n_frames == chunk frames of the input), copied into the pinned arena of the first tick
  * that has no chunk of this input yet: an input may queue up to jitter_frames chunks, every tick consumes one; a push
- * into a full queue drops the oldest chunk (the clocked mixer's InputRingBuffer, mixer.rs:1185-1206). */
+ * into a full queue drops the oldest chunk (the clocked mixer's InputRingBuffer, mixer.rs:1185-1206).
+ * Threading: push / push_batch / acquire / commit may be called from any thread, concurrently with each other (distinct
+ * streams) AND with skgpu_hub_tick: the hub serialises them against the tick's cut, so a racing chunk lands either in this
+ * tick or in the next one, never in an arena that is being uploaded. Everything else is the tick thread's. */
 skgpu_rc skgpu_hub_push(skgpu_hub *hub, uint32_t session, uint32_t input, const float *samples, uint32_t n_frames);
 
 /* zero-copy variant: *dst_out is the stream's slot in the pinned arena of the NEXT tick (chunk frames x channels f32);
- * the producer (e.g. a decoder) writes its samples there and calls skgpu_hub_commit. This is how the pinned arenas
+ * the producer (e.g. a decoder) writes its samples there and calls skgpu_hub_commit BEFORE the next skgpu_hub_tick
+ * (a commit after a tick intervened fails with SKGPU_ERR_STATE and the chunk is dropped). This is how the pinned arenas
  * replace AudioFramePool buffers (crates/core/src/frame_pool.rs:302-317) on the batched path: no gather copy at all.
  * The pointer is valid until the next skgpu_hub_tick. */
 skgpu_rc skgpu_hub_acquire(skgpu_hub *hub, uint32_t session, uint32_t input, float **dst_out, uint32_t *n_frames_out);
@@ -104,6 +108,24 @@ skgpu_rc skgpu_hub_wait_tick(skgpu_hub *hub, uint64_t tick);
  * valid until the next skgpu_hub_wait. *n_mixed = inputs that contributed a packet (0 = silence), *status = OR of the
  * inputs' chain status bits (skgpu_chain_result.status). Sessions opened after that tick was submitted report 0 / NULL. */
 skgpu_rc skgpu_hub_session_output(skgpu_hub *hub, uint32_t session, const void **samples, uint32_t *n_mixed, uint32_t *status);
+
+/* NodeStatsTracker counters (crates/core/src/stats.rs:131-152) of the batched nodes, summed over the hub:
+ *   received   chunks consumed by ticks (a resampler node's stats.received(), resampler.rs:283)
+ *   sent       mixed packets produced (one per live session per tick, mixer.rs:1011 stats.sent())
+ *   discarded  chunks dropped by overwrite-oldest when an input's jitter queue was full (mixer.rs:1195-1201)
+ *   errored    rejected gain updates (gain.rs:157-171 stats.errored()), rejected pushes, ticks that failed on the device */
+typedef struct skgpu_hub_stats {
+    uint64_t received, sent, discarded, errored;
+} skgpu_hub_stats;
+skgpu_rc skgpu_hub_get_stats(skgpu_hub *hub, skgpu_hub_stats *out);
+
+/* node state of the hub as a whole (crates/core/src/state.rs:122-186): 1 = Running, 2 = Degraded (a sync-mode session
+ * timed out on a slow input this tick), 3 = Failed (a CUDA error surfaced; every later call returns SKGPU_ERR_STATE and
+ * the engine must emit NodeState::Failed{reason} for the sessions of this hub). */
+#define SKGPU_HUB_RUNNING 1u
+#define SKGPU_HUB_DEGRADED 2u
+#define SKGPU_HUB_FAILED 3u
+uint32_t skgpu_hub_state(const skgpu_hub *hub, const char **reason_out);
 
 /* counters for logs / tests */
 uint32_t skgpu_hub_live_sessions(const skgpu_hub *hub);

@@ -6,7 +6,7 @@
 // packet's frame index j in [0, F) that the mixing kernel can execute without searching anything:
 //
 //   run segment       x_j = fma((double)(j - j0), delta, x0)         exact (all values in one binade, see phase_runs.h);
-//                     FAST: the binade is [2^e, 2^(e+1)) with 0 <= e <= 17, so floor(x) and x - floor(x) come from
+//                     FAST: the binade is [2^e, 2^(e+1)) with 0 <= e <= 16, so floor(x) and x - floor(x) come from
 //                     integer operations on the high word of the double (mask, shift and offset precomputed)
 //   explicit segment  (buffer offset, f32 fraction) stored per frame: prefix / gap / tiny-run elements and the packet's
 //                     tail, whose frames are produced by the CURRENT chunk (appended one tick later)
@@ -26,11 +26,11 @@
 #define SKC_ST_OVERFLOW 2u        // status bit1: a table of the record overflowed
 #define SKC_ST_UNSUPPORTED 4u     // status bit2: the packet needs frames the kernel does not stage
 #define SKC_KIND_E 0u             // ChainSeg.himask: explicit segment
-#define SKC_KIND_SLOW 1u          // ChainSeg.himask: run segment outside [1, 2^18): floor / fraction by real conversions
+#define SKC_KIND_SLOW 1u          // ChainSeg.himask: run segment outside [1, 2^17): floor / fraction by real conversions
                                   // any other value: FAST run segment, the mask that clears the fraction bits of the high word
 
 // One segment = two 16-byte shared-memory loads in the consumer. FAST run segments lie in one binade [2^e, 2^(e+1)),
-// 0 <= e <= 17, so with hi = high word of x:  floor(x) as a double = {hi & himask, 0}  and the byte offset of buffer
+// 0 <= e <= 16, so with hi = high word of x:  floor(x) as a double = {hi & himask, 0}  and the byte offset of buffer
 // frame floor(x) is ((hi & himask) >> sh) - cs   (sh = 20 - e - log2(frame_bytes), cs = (1022 + e) << (20 - sh)).
 struct alignas(32) ChainSeg {
     double x0, delta;   // run: x_j = fma((double)(j - j0), delta, x0)
@@ -220,7 +220,7 @@ struct SkcStream {
             const double xs = sk_dfma((double)(k - k0), delta, x0);
             const uint32_t hi = (uint32_t)(sk_d2bits(xs) >> 32);
             uint32_t himask = SKC_KIND_SLOW, cs = 0, sh = 0;
-            if ((hi - 0x3FF00000u) < (18u << 20)) {   // positive, exponent e in 0..17, shared by the whole run
+            if ((hi - 0x3FF00000u) < (17u << 20)) {   // positive, exponent e in 0..16 (shift >= 1), shared by the whole run
                 const uint32_t e = (hi >> 20) - 1023u;
                 const uint32_t lfb = b.frame_bytes == 8u ? 3u : 2u;
                 himask = 0xFFFFFFFFu << (20u - e);

@@ -16,6 +16,8 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <mutex>
+#include <shared_mutex>
 #include <string>
 #include <thread>
 #include <vector>
@@ -82,6 +84,7 @@ struct Stream {
     uint32_t in_rate = 0;
     bool live = false;
     bool ever_pushed = false;
+    uint64_t acq_tick = ~0ull;   // value of `ticks` when the zero-copy slot was handed out (skgpu_hub_acquire)
 };
 
 struct Session {
@@ -123,13 +126,23 @@ struct skgpu_hub {
     uint64_t arena_epoch[2] = {0, 0};           // table epoch the tick in each output arena was submitted with
     std::vector<int64_t> first_by_arena[2];     // per session: first table input of that tick (-1: not part of it)
     std::vector<uint32_t> count_by_arena[2];
-    uint64_t ticks = 0;
+    std::atomic<uint64_t> ticks{0};             // ticks submitted; pushers read it (under the shared lock) to find their arena
+    uint64_t waited = 0;                        // highest tick number known to have finished (read-back included)
+    // THE CUT between "this tick" and "the next one": pushers (push / acquire / commit / push_batch, any thread) hold the lock
+    // shared, skgpu_hub_tick holds it exclusively while it consumes the queue counters, copies absent streams and advances
+    // `ticks`. A push that races with a tick therefore lands entirely before the cut (mixed by this tick) or entirely after
+    // it (queued in the next tick's arena) -- never in the arena that is being uploaded.
+    std::shared_mutex cut;
+    std::atomic<uint64_t> n_discarded{0}, n_errored{0};   // bumped from pusher threads
+    std::string fail_reason;                    // non-empty: the hub is Failed (state.rs:122-186)
+    bool degraded = false;
+    skgpu_hub_stats stats{};                    // NodeStatsTracker counters of the batched nodes (crates/core/src/stats.rs:131-152)
     uint32_t n_live_sessions = 0, n_live_streams = 0;
     explicit skgpu_hub(uint32_t n_streams) : pushed(n_streams) {}
 };
 
 // input arena of the tick that is `ahead` ticks after the next one to be submitted
-static inline uint8_t *in_arena(skgpu_hub *h, uint32_t ahead) { return h->host_in[(h->ticks + ahead) % h->R]; }
+static inline uint8_t *in_arena(skgpu_hub *h, uint32_t ahead) { return h->host_in[(h->ticks.load(std::memory_order_relaxed) + ahead) % h->R]; }
 
 // queue one chunk of stream sid (skgpu_hub_push and friends). Thread-safe for distinct streams.
 // copy == nullptr: only reserve the slot (zero-copy acquire). Returns the slot to write.
@@ -142,6 +155,7 @@ static uint8_t *enqueue_slot(skgpu_hub *h, uint32_t sid) {
         for (uint32_t i = 0; i + 1 < h->J; ++i) memcpy(in_arena(h, i) + off, in_arena(h, i + 1) + off, bytes);
         q = h->J - 1;
         h->pushed[sid].store((uint8_t)q, std::memory_order_relaxed);
+        h->n_discarded.fetch_add(1, std::memory_order_relaxed);
     }
     return in_arena(h, q) + off;
 }
@@ -357,6 +371,8 @@ extern "C" skgpu_rc skgpu_hub_session_close(skgpu_hub *h, uint32_t si) {
     h->n_live_streams -= (uint32_t)s->streams.size();
     h->n_live_sessions -= 1;
     *s = Session{};
+    for (int a = 0; a < 2; ++a)   // a session index that is reused must not see the closed session's packets
+        if (si < h->first_by_arena[a].size()) h->first_by_arena[a][si] = -1;
     h->free_sessions.push_back(si);
     h->tables_dirty = true;
     return SKGPU_OK;
@@ -365,7 +381,7 @@ extern "C" skgpu_rc skgpu_hub_session_close(skgpu_hub *h, uint32_t si) {
 extern "C" skgpu_rc skgpu_hub_set_input_gain(skgpu_hub *h, uint32_t si, uint32_t input, float gain) {
     Session *s = live_session(h, si);
     if (!s || input >= s->streams.size()) return hub_fail(SKGPU_ERR_INVALID, "no such session / input");
-    if (!valid_gain(gain)) return hub_fail(SKGPU_ERR_INVALID, "gain must be a finite number between 0.0 and 4.0");   // gain.rs:50-66; the old gain stays
+    if (!valid_gain(gain)) { h->n_errored.fetch_add(1, std::memory_order_relaxed); return hub_fail(SKGPU_ERR_INVALID, "gain must be a finite number between 0.0 and 4.0"); }   // gain.rs:50-66, :157-171; the old gain stays
     h->gains[s->streams[input]] = gain;
     h->gains_dirty = true;
     return SKGPU_OK;
@@ -373,7 +389,7 @@ extern "C" skgpu_rc skgpu_hub_set_input_gain(skgpu_hub *h, uint32_t si, uint32_t
 
 extern "C" skgpu_rc skgpu_hub_set_master_gain(skgpu_hub *h, uint32_t si, float gain) {
     if (!live_session(h, si)) return hub_fail(SKGPU_ERR_INVALID, "session %u is not open", si);
-    if (!valid_gain(gain)) return hub_fail(SKGPU_ERR_INVALID, "gain must be a finite number between 0.0 and 4.0");
+    if (!valid_gain(gain)) { h->n_errored.fetch_add(1, std::memory_order_relaxed); return hub_fail(SKGPU_ERR_INVALID, "gain must be a finite number between 0.0 and 4.0"); }
     h->gains[h->cfg.max_streams + si] = gain;
     h->gains_dirty = true;
     return SKGPU_OK;
@@ -392,6 +408,7 @@ extern "C" skgpu_rc skgpu_hub_push(skgpu_hub *h, uint32_t si, uint32_t input, co
     const uint32_t sid = s->streams[input];
     const Stream &st = h->streams[sid];
     if (n_frames != st.chunk) return hub_fail(SKGPU_ERR_INVALID, "chunk of %u frames, the stream delivers %u per tick", n_frames, st.chunk);
+    std::shared_lock<std::shared_mutex> lk(h->cut);
     stream_copy(enqueue_slot(h, sid), reinterpret_cast<const uint8_t *>(samples), (size_t)n_frames * h->C * 4u);
     stream_fence();
     h->pushed[sid].fetch_add(1, std::memory_order_release);
@@ -402,7 +419,9 @@ extern "C" skgpu_rc skgpu_hub_acquire(skgpu_hub *h, uint32_t si, uint32_t input,
     Session *s = live_session(h, si);
     if (!s || input >= s->streams.size() || !dst_out) return hub_fail(SKGPU_ERR_INVALID, "no such session / input");
     const uint32_t sid = s->streams[input];
+    std::shared_lock<std::shared_mutex> lk(h->cut);
     *dst_out = reinterpret_cast<float *>(enqueue_slot(h, sid));
+    h->streams[sid].acq_tick = h->ticks.load(std::memory_order_relaxed);
     if (n_frames_out) *n_frames_out = h->streams[sid].chunk;
     return SKGPU_OK;
 }
@@ -411,12 +430,20 @@ extern "C" skgpu_rc skgpu_hub_commit(skgpu_hub *h, uint32_t si, uint32_t input) 
     Session *s = live_session(h, si);
     if (!s || input >= s->streams.size()) return hub_fail(SKGPU_ERR_INVALID, "no such session / input");
     const uint32_t sid = s->streams[input];
+    std::shared_lock<std::shared_mutex> lk(h->cut);
+    if (h->streams[sid].acq_tick != ~0ull && h->streams[sid].acq_tick != h->ticks.load(std::memory_order_relaxed)) {
+        h->streams[sid].acq_tick = ~0ull;
+        h->n_errored.fetch_add(1, std::memory_order_relaxed);
+        return hub_fail(SKGPU_ERR_STATE, "commit after a tick: the slot handed out by skgpu_hub_acquire belonged to an earlier tick; chunk dropped");
+    }
+    h->streams[sid].acq_tick = ~0ull;
     if (h->pushed[sid].load(std::memory_order_relaxed) < h->J) h->pushed[sid].fetch_add(1, std::memory_order_release);
     return SKGPU_OK;
 }
 
 extern "C" skgpu_rc skgpu_hub_commit_all(skgpu_hub *h) {
     if (!h) return hub_fail(SKGPU_ERR_INVALID, "null hub");
+    std::shared_lock<std::shared_mutex> lk(h->cut);
     for (uint32_t sid = 0; sid < h->streams.size(); ++sid)
         if (h->streams[sid].live && h->pushed[sid].load(std::memory_order_relaxed) == 0) h->pushed[sid].store(1, std::memory_order_relaxed);
     return SKGPU_OK;
@@ -432,6 +459,7 @@ extern "C" skgpu_rc skgpu_hub_push_batch(skgpu_hub *h, const skgpu_hub_frame *fr
             return hub_fail(SKGPU_ERR_INVALID, "frame %u: chunk of %u frames, the stream delivers %u per tick", i, frames[i].n_frames, h->streams[s->streams[frames[i].input]].chunk);
     }
     auto work = [&](uint32_t lo, uint32_t hi) {
+        std::shared_lock<std::shared_mutex> lk(h->cut);
         for (uint32_t i = lo; i < hi; ++i) {
             const uint32_t sid = h->sessions[frames[i].session].streams[frames[i].input];
             stream_copy(enqueue_slot(h, sid), reinterpret_cast<const uint8_t *>(frames[i].samples), (size_t)frames[i].n_frames * h->C * 4u);
@@ -450,24 +478,28 @@ extern "C" skgpu_rc skgpu_hub_push_batch(skgpu_hub *h, const skgpu_hub_frame *fr
 
 extern "C" skgpu_rc skgpu_hub_tick(skgpu_hub *h) {
     if (!h) return hub_fail(SKGPU_ERR_INVALID, "null hub");
+    const uint64_t t0 = h->ticks.load(std::memory_order_relaxed);
+    // at most two unfinished ticks: the input ring (J + 2 arenas) and the two output arenas are sized for exactly that
+    // (a third submit would let pushes overwrite an arena whose upload is pending and reuse host_out[cur])
+    if (t0 >= 2 && h->waited + 2 <= t0) {
+        PASS(skgpu_tick_wait_for(h->plan, t0 - 1));
+        h->waited = t0 - 1;
+    }
     if (h->tables_dirty) {
-        if (h->in_flight) { PASS(skgpu_tick_wait(h->plan, nullptr)); h->in_flight = false; }
+        if (h->in_flight) { PASS(skgpu_tick_wait(h->plan, nullptr)); h->in_flight = false; h->waited = t0; }
         skgpu_rc rc = rebuild_tables(h);
         if (rc != SKGPU_OK) return rc;
     }
+    // ---- the cut: from here to the advance of `ticks` no push can interleave
+    std::unique_lock<std::shared_mutex> cut(h->cut);
     const uint32_t n_in = (uint32_t)h->tab_stream.size();
-    uint8_t *in_cur = in_arena(h, 0), *in_prev = h->host_in[(h->ticks + h->R - 1u) % h->R];   // this tick's arena, the previous tick's
+    uint8_t *in_cur = in_arena(h, 0), *in_prev = h->host_in[(t0 + h->R - 1u) % h->R];   // this tick's arena, the previous tick's
     for (uint32_t i = 0; i < n_in; ++i) {
         const uint32_t sid = h->tab_stream[i];
-        Stream &st = h->streams[sid];
-        // pushes for this tick happened-before this call (the engine's tick thread decides the cut): plain load + store
-        const uint32_t q = h->pushed[sid].load(std::memory_order_acquire);
-        const bool got = q != 0;   // the head of the stream's queue sits in this tick's arena
-        if (got) h->pushed[sid].store((uint8_t)(q - 1u), std::memory_order_relaxed);
+        const Stream &st = h->streams[sid];
+        const bool got = h->pushed[sid].load(std::memory_order_acquire) != 0;   // the head of the stream's queue sits in this tick's arena
         h->present[i] = got ? 1 : 0;
-        if (got) {
-            st.ever_pushed = true;
-        } else if (st.ever_pushed) {
+        if (!got && st.ever_pushed) {
             // absent this tick: the other input bank must keep holding the stream's previous chunk (skgpu_batch.h, chain protocol)
             const uint64_t off = (uint64_t)sid * h->in_stride;
             memcpy(in_cur + off, in_prev + off, (size_t)st.chunk * h->C * 4u);
@@ -479,6 +511,15 @@ extern "C" skgpu_rc skgpu_hub_tick(skgpu_hub *h) {
         h->gains_dirty = false;
     }
     PASS(skgpu_tick_submit(h->plan, in_cur, h->host_out[h->cur], SKGPU_SUBMIT_GRAPH | SKGPU_SUBMIT_OVERLAP_D2H));
+    // only a tick that was really submitted consumes the queues (a failed submit keeps every queued chunk)
+    for (uint32_t i = 0; i < n_in; ++i) {
+        if (!h->present[i]) continue;
+        const uint32_t sid = h->tab_stream[i];
+        h->pushed[sid].fetch_sub(1, std::memory_order_relaxed);
+        h->streams[sid].ever_pushed = true;
+        h->stats.received += 1;
+    }
+    h->stats.sent += h->groups.size();
     if (h->last == (int)h->cur) h->out_ready = false;   // this tick reuses the arena the collected results lived in
     if (h->arena_epoch[h->cur] != h->epoch) {           // remember which table rows this tick's results belong to
         auto &fa = h->first_by_arena[h->cur];
@@ -491,7 +532,7 @@ extern "C" skgpu_rc skgpu_hub_tick(skgpu_hub *h) {
     }
     h->cur ^= 1u;
     h->in_flight = true;
-    h->ticks += 1;
+    h->ticks.store(t0 + 1, std::memory_order_release);
     return SKGPU_OK;
 }
 
@@ -499,6 +540,7 @@ extern "C" skgpu_rc skgpu_hub_wait(skgpu_hub *h, skgpu_tick_timing *timing) {
     if (!h) return hub_fail(SKGPU_ERR_INVALID, "null hub");
     PASS(skgpu_tick_wait(h->plan, timing));
     h->in_flight = false;
+    h->waited = h->ticks;
     h->out_ready = h->ticks > 0;
     if (h->ticks > 0) h->last = (int)((h->ticks - 1) & 1u);
     return SKGPU_OK;
@@ -508,6 +550,7 @@ extern "C" skgpu_rc skgpu_hub_wait_tick(skgpu_hub *h, uint64_t tick) {
     if (!h) return hub_fail(SKGPU_ERR_INVALID, "null hub");
     if (tick == 0 || tick > h->ticks || tick + 1 < h->ticks) return hub_fail(SKGPU_ERR_INVALID, "tick %llu is not one of the two most recent ticks", (unsigned long long)tick);
     PASS(skgpu_tick_wait_for(h->plan, tick));
+    h->waited = std::max(h->waited, tick);
     h->last = (int)((tick - 1) & 1u);          // tick k uploaded from / read back into arena (k - 1) & 1
     h->in_flight = tick < h->ticks;           // a later tick may still be running
     h->out_ready = true;
@@ -532,6 +575,21 @@ extern "C" skgpu_rc skgpu_hub_session_output(skgpu_hub *h, uint32_t si, const vo
     return SKGPU_OK;
 }
 
+extern "C" skgpu_rc skgpu_hub_get_stats(skgpu_hub *h, skgpu_hub_stats *out) {
+    if (!h || !out) return hub_fail(SKGPU_ERR_INVALID, "null argument");
+    *out = h->stats;
+    out->discarded += h->n_discarded.load(std::memory_order_relaxed);
+    out->errored += h->n_errored.load(std::memory_order_relaxed);
+    return SKGPU_OK;
+}
+
+extern "C" uint32_t skgpu_hub_state(const skgpu_hub *h, const char **reason_out) {
+    if (reason_out) *reason_out = (h && !h->fail_reason.empty()) ? h->fail_reason.c_str() : nullptr;
+    if (!h) return SKGPU_HUB_FAILED;
+    if (!h->fail_reason.empty()) return SKGPU_HUB_FAILED;
+    return h->degraded ? SKGPU_HUB_DEGRADED : SKGPU_HUB_RUNNING;
+}
+
 extern "C" uint32_t skgpu_hub_live_sessions(const skgpu_hub *h) { return h ? h->n_live_sessions : 0; }
 extern "C" uint32_t skgpu_hub_live_streams(const skgpu_hub *h) { return h ? h->n_live_streams : 0; }
-extern "C" uint64_t skgpu_hub_ticks(const skgpu_hub *h) { return h ? h->ticks : 0; }
+extern "C" uint64_t skgpu_hub_ticks(const skgpu_hub *h) { return h ? h->ticks.load(std::memory_order_relaxed) : 0; }

@@ -36,7 +36,9 @@
 
 namespace skgpu {
 
-constexpr int CH_CONSUMERS = 256;                 // 8 consumer warps
+constexpr int CH_CWARPS = 4;                      // consumer warps
+constexpr int CH_NB = 8;                          // consecutive 32-frame blocks a consumer warp owns per iteration (256 frames)
+constexpr int CH_CONSUMERS = CH_CWARPS * 32;
 constexpr int CH_THREADS = CH_CONSUMERS + 32;     // + producer warp (warp 0)
 constexpr int CH_MAX_STAGES = 4;                  // pipeline depth is a launch parameter (2..4)
 constexpr int CH_HEAD = 32;                       // frames of the CURRENT chunk staged behind the previous one
@@ -74,7 +76,7 @@ struct __align__(16) ChainTail {   // per staged input: what the end-of-batch hi
 struct __align__(16) ChainStage {   // header of one pipeline stage (shared memory)
     uint32_t nb;            // inputs in this batch           } one 16-byte load
     uint32_t first, last;   // first / last batch of the session
-    uint32_t has_base;      // bit0: the first input of the first batch is the base frame (mixer.rs:960-972);
+    uint32_t has_base;      // bit0: the first input of the first batch is the base frame (mixer.rs:960-972); bit1: every staged input is stereo;
                             // bits 8-10: block-ownership rotation of this session (load balance, see the consumers)
     uint64_t out_off;
     float master_gain;      // 1.0 when the session has no master audio::gain
@@ -150,7 +152,7 @@ __device__ __forceinline__ unsigned long long chain_frame(uint32_t addr, float f
 
 // rare run segments outside [1, 2^18) (negative positions right after a stream starts, very long chunks): real conversions.
 // Out of line so that the hot loop carries none of its instructions; returns (byte offset from buffer position 16, fraction).
-__device__ __noinline__ unsigned long long chain_split_slow(double x, uint32_t frame_bytes) {
+__device__ __forceinline__ unsigned long long chain_split_slow(double x, uint32_t frame_bytes) {
     int32_t fl;
     float frac;
     skc_split(x, &fl, &frac);
@@ -159,77 +161,131 @@ __device__ __noinline__ unsigned long long chain_split_slow(double x, uint32_t f
     return r;
 }
 
-// acc += v where `active` (packed f32x2, in place; see add2 for the fma-with-one form)
-__device__ __forceinline__ void acc_add2(unsigned long long &acc, unsigned long long v, unsigned long long one2, bool active) {
-    asm("{\n.reg .pred p;\nsetp.ne.u32 p, %2, 0;\n@p fma.rn.f32x2 %0, %1, %3, %0;\n}" : "+l"(acc) : "l"(v), "r"((uint32_t)active), "l"(one2));
+// acc += v (packed f32x2, in place; see add2 for the fma-with-one form)
+__device__ __forceinline__ void acc_add(unsigned long long &acc, unsigned long long v, unsigned long long one2) {
+    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(v), "l"(one2));
 }
 
-// Executes the frame program of one staged input for the 128 frames (4 blocks of 32) this warp owns per iteration:
-// segment-major -- a segment is decoded once (two 16-byte loads) and applied to every owned block it touches.
+// run cache of a consumer warp (registers, warp-uniform except xl): the FAST run segment the warp is inside of
+struct RunCache {
+    uint32_t j0, j1;      // packet frames the run covers (j1 = 0: nothing cached)
+    uint32_t himask;      // clears the fraction bits of the high word
+    uint32_t sh;          // byte offset of buffer frame floor(x) = (flh >> sh) - cs
+    uint32_t kc;          // shared-memory address of buffer frame 0 of the run's binade offset: a_chunk - cs
+    double xl;            // per lane: phase of this lane's frame in the block processed last
+    double dl32;          // 32 * delta (exact: a power-of-two multiple)
+};
+
+// floor / fraction of a phase inside a FAST run (one binade [2^e, 2^(e+1)), 0 <= e <= 16): integer operations on the high word
+__device__ __forceinline__ void fast_split(double x, uint32_t himask, uint32_t &flh, float &frac) {
+    flh = (uint32_t)__double2hiint(x) & himask;                                   // floor(x) as a double = {flh, 0}
+    frac = __double2float_rn(__dsub_rn(x, __hiloint2double((int)flh, 0)));        // T::coerce(idx - idx.floor())
+}
+
+// Executes the frame program of one staged input for the CH_NB consecutive blocks (256 frames) this warp owns per
+// iteration. Lane l owns frame (block start + l). A block that lies inside the cached FAST run takes the straight-line
+// path: the lane's phase advances by 32 * delta (exact, phase_runs.h) -- no segment decode, no search, no predicate.
+// Any other block (a binade boundary inside it, explicit frames, the packet's head and tail: ~7 of 30) takes the general
+// path: every lane finds ITS segment (short divergent walk from the block map's first entry) and evaluates it.
 //   prog    shared-memory address of the program record; a_hist: of the 16-frame history (buffer position 0)
 template <int OC, int SC, int ITERS>
-__device__ __forceinline__ void chain_consume(unsigned long long (&acc)[ITERS][4], uint32_t prog, uint32_t a_hist, const ChainProgDims &pd,
-                                              uint32_t cw, uint32_t lane, float gain, unsigned long long one2) {
+__device__ __forceinline__ void chain_consume(unsigned long long (&acc)[ITERS][CH_NB], uint32_t prog, uint32_t a_hist, const ChainProgDims &pd,
+                                              uint32_t F, uint32_t cw, uint32_t lane, float gain, unsigned long long one2) {
     const uint32_t segs = prog + skc_seg_off(pd);
     const uint32_t a_chunk = a_hist + 16u * SC * 4u;   // buffer position 16: floor(idx) == 0
+    RunCache rc;
+    rc.j0 = 0; rc.j1 = 0; rc.himask = 0; rc.sh = 0; rc.kc = 0; rc.xl = 0.0; rc.dl32 = 0.0;
 #pragma unroll
     for (int it = 0; it < ITERS; ++it) {
-        const uint32_t b0 = ((uint32_t)it * 8u + cw) * 4u;   // warp-uniform: first owned block
-        if (b0 >= pd.nblk) continue;
-        uint32_t e_first, e_last;
-        asm volatile("ld.shared.u16 %0, [%1];" : "=r"(e_first) : "r"(prog + b0 * 2u));
-        asm volatile("ld.shared.u16 %0, [%1];" : "=r"(e_last) : "r"(prog + min(b0 + 3u, pd.nblk - 1u) * 2u));
-        const uint32_t s_last = e_last >> 8;
-        const uint32_t jb = b0 * 32u, jw = jb + lane;
-#pragma unroll 1
-        for (uint32_t s = e_first & 0xFFu; s <= s_last; ++s) {
-            const uint32_t sa = segs + s * 32u;
-            uint32_t jj, himask, aux, sh;
-            asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4+16];" : "=r"(jj), "=r"(himask), "=r"(aux), "=r"(sh) : "r"(sa));
-            const uint32_t j0 = jj & 0xFFFFu, j1 = jj >> 16, lenm1 = j1 - j0 - 1u;
-            const uint32_t relw = jw - j0;   // frame f of this lane is element relw + 32 f of the segment (lanes outside are dropped)
-            if (himask > SKC_KIND_SLOW) {
-                // ---- FAST run segment (almost everything)
-                double x0, dl;
-                asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(x0), "=d"(dl) : "r"(sa));
-                const uint32_t k_chunk = a_chunk - aux;
+        if (ITERS > 1) rc.j1 = 0;   // the warp's next block is not adjacent
 #pragma unroll
-                for (int f = 0; f < 4; ++f) {
-                    const uint32_t jf = jb + (uint32_t)f * 32u;
-                    if (jf < j1 && jf + 32u > j0) {                     // warp-uniform: block f touches this segment
-                        const uint32_t rel_raw = relw + (uint32_t)f * 32u;
-                        const uint32_t rel = min(rel_raw, lenm1);       // lanes outside compute a valid frame and drop it
-                        const double x = __fma_rn((double)rel, dl, x0);    // exact inside a run (phase_runs.h)
-                        const uint32_t flh = (uint32_t)__double2hiint(x) & himask;                       // floor(x) as a double = {flh, 0}
-                        const float frac = __double2float_rn(__dsub_rn(x, __hiloint2double((int)flh, 0)));   // T::coerce(idx - idx.floor())
-                        const unsigned long long v = chain_frame<OC, SC>((flh >> sh) + k_chunk, frac, gain, one2);   // a_chunk + floor(x) * frame bytes
-                        acc_add2(acc[it][f], v, one2, rel_raw <= lenm1);
+        for (int f = 0; f < CH_NB; ++f) {
+            const uint32_t blk = ((uint32_t)it * CH_CWARPS + cw) * CH_NB + (uint32_t)f;
+            const uint32_t jb = blk * 32u;
+            bool pure = jb >= rc.j0 && jb + 32u <= rc.j1;
+            uint32_t e = 0;
+            if (!pure) {
+                if (jb >= F) continue;                                   // warp-uniform (a pure block never lies past the packet)
+                asm volatile("ld.shared.u16 %0, [%1];" : "=r"(e) : "r"(prog + blk * 2u));
+                if ((e & 0xFFu) == (e >> 8)) {
+                    // one segment covers the block (the warp's first block of an input, typically): if it is a FAST run, enter it
+                    const uint32_t sa = segs + (e & 0xFFu) * 32u;
+                    uint32_t ljj, lhimask, laux, lsh;
+                    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4+16];" : "=r"(ljj), "=r"(lhimask), "=r"(laux), "=r"(lsh) : "r"(sa));
+                    if (lhimask > SKC_KIND_SLOW && (ljj >> 16) >= jb + 32u) {
+                        double x0, dl;
+                        asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(x0), "=d"(dl) : "r"(sa));
+                        rc.j0 = ljj & 0xFFFFu;
+                        rc.j1 = ljj >> 16;
+                        rc.himask = lhimask;
+                        rc.sh = lsh;
+                        rc.kc = a_chunk - laux;
+                        rc.dl32 = __dmul_rn(dl, 32.0);
+                        // the lane's frame one block EARLIER on the run's lattice (a multiple of the binade's unit below 2^(e+1),
+                        // hence exact, also when it extrapolates below the run's start); the straight-line path adds 32 delta
+                        rc.xl = __fma_rn((double)((int)(jb + lane) - (int)rc.j0 - 32), dl, x0);
+                        pure = true;
                     }
                 }
+            }
+            if (pure) {
+                // ---- straight line: the whole block lies inside the cached run
+                rc.xl = __dadd_rn(rc.xl, rc.dl32);
+                uint32_t flh;
+                float frac;
+                fast_split(rc.xl, rc.himask, flh, frac);
+                acc_add(acc[it][f], chain_frame<OC, SC>((flh >> rc.sh) + rc.kc, frac, gain, one2), one2);   // a_chunk + floor(x) * frame bytes
             } else {
-                // ---- explicit frames / slow run segments
-                double x0 = 0.0, dl = 0.0;
-                if (himask == SKC_KIND_SLOW) asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(x0), "=d"(dl) : "r"(sa));
-#pragma unroll
-                for (int f = 0; f < 4; ++f) {
-                    const uint32_t jf = jb + (uint32_t)f * 32u;
-                    if (jf < j1 && jf + 32u > j0) {
-                        const uint32_t rel_raw = relw + (uint32_t)f * 32u;
-                        const uint32_t rel = min(rel_raw, lenm1);
-                        uint32_t addr;
-                        float frac;
-                        if (himask == SKC_KIND_E) {
-                            uint32_t aoff;
-                            asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(aoff), "=f"(frac) : "r"(prog + aux + rel * 8u));
-                            addr = a_hist + aoff;
-                        } else {
-                            const unsigned long long pf = chain_split_slow(__fma_rn((double)rel, dl, x0), SC * 4u);
-                            uint32_t off;
-                            asm("mov.b64 {%0, %1}, %2;" : "=r"(off), "=f"(frac) : "l"(pf));
-                            addr = a_chunk + off;
-                        }
-                        const unsigned long long v = chain_frame<OC, SC>(addr, frac, gain, one2);
-                        acc_add2(acc[it][f], v, one2, rel_raw <= lenm1);
+                uint32_t addr;
+                float frac;
+                // ---- general: per-lane segment walk
+                const uint32_t j = min(jb + lane, F - 1u);               // lanes past the packet's end recompute its last frame
+                uint32_t sa = segs + (e & 0xFFu) * 32u;
+                const uint32_t sa_last = segs + (e >> 8) * 32u;
+                uint32_t jj, himask, aux, sh;
+                asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4+16];" : "=r"(jj), "=r"(himask), "=r"(aux), "=r"(sh) : "r"(sa));
+                while ((jj >> 16) <= j && sa < sa_last) {
+                    sa += 32u;
+                    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4+16];" : "=r"(jj), "=r"(himask), "=r"(aux), "=r"(sh) : "r"(sa));
+                }
+                const uint32_t rel = j - (jj & 0xFFFFu);
+                if (himask == SKC_KIND_E) {
+                    uint32_t aoff;
+                    asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(aoff), "=f"(frac) : "r"(prog + aux + rel * 8u));
+                    addr = a_hist + aoff;
+                } else {
+                    double x0, dl;
+                    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(x0), "=d"(dl) : "r"(sa));
+                    const double x = __fma_rn((double)rel, dl, x0);     // exact inside a run (phase_runs.h)
+                    if (himask != SKC_KIND_SLOW) {
+                        uint32_t flh;
+                        fast_split(x, himask, flh, frac);
+                        addr = (flh >> sh) + a_chunk - aux;
+                    } else {
+                        const unsigned long long pf = chain_split_slow(x, SC * 4u);
+                        uint32_t off;
+                        asm("mov.b64 {%0, %1}, %2;" : "=r"(off), "=f"(frac) : "l"(pf));
+                        addr = a_chunk + off;
+                    }
+                }
+                acc_add(acc[it][f], chain_frame<OC, SC>(addr, frac, gain, one2), one2);
+                // ---- refresh the run cache from the block's last segment when that is a FAST run reaching past the block
+                rc.j1 = 0;
+                if (f + 1 < CH_NB) {
+                    uint32_t ljj, lhimask, laux, lsh;
+                    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4+16];" : "=r"(ljj), "=r"(lhimask), "=r"(laux), "=r"(lsh) : "r"(sa_last));
+                    if (lhimask > SKC_KIND_SLOW && (ljj >> 16) >= jb + 64u) {   // warp-uniform
+                        double x0, dl;
+                        asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(x0), "=d"(dl) : "r"(sa_last));
+                        rc.j0 = ljj & 0xFFFFu;
+                        rc.j1 = ljj >> 16;
+                        rc.himask = lhimask;
+                        rc.sh = lsh;
+                        rc.kc = a_chunk - laux;
+                        rc.dl32 = __dmul_rn(dl, 32.0);
+                        // this lane's frame of THIS block on the run's lattice (lanes before the run's start extrapolate below
+                        // the binade: still a multiple of the binade's unit, so every later + 32 delta step is exact)
+                        rc.xl = __fma_rn((double)((int)(jb + lane) - (int)rc.j0), dl, x0);
                     }
                 }
             }
@@ -330,13 +386,14 @@ __global__ void __launch_bounds__(PHASE_CHAIN_THREADS, 14) k_phase_chain(const O
 }
 
 template <int OC, int ITERS>  // output channels (1 | 2); ITERS = ceil(F / 1024)
-__global__ void __launch_bounds__(CH_THREADS, 4) k_chain(const OpHeader *__restrict__ hdr, const skgpu_chain_group *__restrict__ groups,
+__global__ void __launch_bounds__(CH_THREADS, 5) k_chain(const OpHeader *__restrict__ hdr, const skgpu_chain_group *__restrict__ groups,
                                                          const ChainRec *__restrict__ recs, const float *__restrict__ gains, SlotTables st,
                                                          uint8_t *__restrict__ arena, uint32_t F, ChainDims dm) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t bar_full[CH_MAX_STAGES], bar_empty[CH_MAX_STAGES];
     __shared__ __align__(16) ChainStage s_stage[CH_MAX_STAGES];
     __shared__ uint8_t s_order[CH_MAX_INPUTS];
+    __shared__ float s_one;   // 1.0f in a place ptxas cannot see through (add2): a register value, not a constant-bank operand
 
     // dynamic smem: nstages x kb input slots, then the producer's scratch for sessions that need several batches
     const uint32_t kb = dm.kb, nstages = dm.nstages;
@@ -348,6 +405,7 @@ __global__ void __launch_bounds__(CH_THREADS, 4) k_chain(const OpHeader *__restr
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
 
     if (threadIdx.x == 0) {
+        s_one = dm.one;
         for (uint32_t s = 0; s < nstages; ++s) {
             mbar_init(&bar_full[s], 1);
             mbar_init(&bar_empty[s], CH_CONSUMERS / 32);
@@ -430,6 +488,7 @@ __global__ void __launch_bounds__(CH_THREADS, 4) k_chain(const OpHeader *__restr
             const uint32_t elig_mask = __ballot_sync(0xffffffffu, elig);
             const uint32_t uniq_mask = __ballot_sync(0xffffffffu, elig && (r.flags & CR_UNIQUE));
             const uint32_t unal_mask = __ballot_sync(0xffffffffu, emit && (r.flags & CR_UNALIGNED));
+            const uint32_t mono_mask = __ballot_sync(0xffffffffu, emit && r.cons.sc != 2u);
             uint32_t m = __popc(emit_mask);
             if (K <= 32u && m <= kb && unal_mask == 0u) {
                 // ---- common path. max_by_key((unique, idx)): the last unique full-shape frame, else the last full-shape frame
@@ -452,7 +511,7 @@ __global__ void __launch_bounds__(CH_THREADS, 4) k_chain(const OpHeader *__restr
                 }
                 __syncwarp();
                 if (lane == 0) {
-                    stage_header(S, grp, m, true, true, base_lane >= 0 ? 1u : 0u, (n * 3u) & 7u);
+                    stage_header(S, grp, m, true, true, (base_lane >= 0 ? 1u : 0u) | (mono_mask == 0u ? 2u : 0u), (n * 3u) & (CH_CWARPS - 1u));
                     // one thread issues the 3 bulk copies of every input, in summation order, from the prefetched records
                     uint8_t *dst = smem_raw + (size_t)stage * stage_bytes;
                     uint32_t bytes = 0;
@@ -509,7 +568,7 @@ __global__ void __launch_bounds__(CH_THREADS, 4) k_chain(const OpHeader *__restr
                     }
 #pragma unroll
                     for (int o = 16; o > 0; o >>= 1) bytes += __shfl_xor_sync(0xffffffffu, bytes, o);
-                    if (lane == 0) stage_header(S, grp, nb, b == 0u, b + 1u == n_batches, has_base, (n * 3u) & 7u);
+                    if (lane == 0) stage_header(S, grp, nb, b == 0u, b + 1u == n_batches, has_base, (n * 3u) & (CH_CWARPS - 1u));
                     __syncwarp();
                     if (lane == 0) mbar_expect_tx(&bar_full[stage], bytes);
                     if (++stage == nstages) { stage = 0; ephase ^= 1u; }
@@ -532,8 +591,10 @@ __global__ void __launch_bounds__(CH_THREADS, 4) k_chain(const OpHeader *__restr
     // segments (the binades below 128) and the last ones its explicit tail, so a fixed assignment would make the same
     // warp the slowest of every session while a stage is only released when all eight are done.
     const uint32_t ct = threadIdx.x - 32u;
-    unsigned long long acc[ITERS][4];   // (left, right) packed f32x2 per owned frame (mono: low half)
-    const unsigned long long one2 = pack2(dm.one, dm.one);   // 1.0f the compiler cannot see (add2)
+    unsigned long long acc[ITERS][CH_NB];   // (left, right) packed f32x2 per owned frame (mono: low half)
+    float one_r;
+    asm volatile("ld.volatile.shared.f32 %0, [%1];" : "=f"(one_r) : "r"(smem_u32(&s_one)));
+    const unsigned long long one2 = pack2(one_r, one_r);   // 1.0f the compiler cannot see (add2)
     uint32_t stage = 0, fphase = 0;
     for (;;) {
         mbar_wait(&bar_full[stage], fphase);
@@ -542,7 +603,7 @@ __global__ void __launch_bounds__(CH_THREADS, 4) k_chain(const OpHeader *__restr
         if (S->stop) break;
         const uint32_t sm = smem_u32(smem_raw) + stage * stage_bytes;
         const uint32_t nb = (dm.debug & 1u) ? 0u : hd.x;
-        const uint32_t cw = (warp - 1u + (hd.w >> 8)) & 7u;   // this session's block group of the warp
+        const uint32_t cw = (warp - 1u + (hd.w >> 8)) & (CH_CWARPS - 1u);   // this session's block group of the warp
         if (hd.y != 0) {
             // the base frame IS the accumulator (mixer.rs:969-972): start from -0.0, the additive identity of every f32
             // (-0.0 + v == v bit for bit, also for v == -0.0); without a base frame the mix starts from vec![0.0; n]
@@ -550,20 +611,28 @@ __global__ void __launch_bounds__(CH_THREADS, 4) k_chain(const OpHeader *__restr
 #pragma unroll
             for (int it = 0; it < ITERS; ++it)
 #pragma unroll
-                for (int f = 0; f < 4; ++f) acc[it][f] = init;
+                for (int f = 0; f < CH_NB; ++f) acc[it][f] = init;
         }
-        for (uint32_t q = 0; q < nb; ++q) {
-            const ChainCons c = S->cons[q];
-            const uint32_t prog = sm + q * in_bytes;
-            if (c.sc == 2u) chain_consume<OC, 2, ITERS>(acc, prog, prog + prog_cap, dm.prog, cw, lane, c.gain, one2);
-            else chain_consume<OC, 1, ITERS>(acc, prog, prog + prog_cap + SK_SIDE_HIST - 64u, dm.prog, cw, lane, c.gain, one2);
+        if (hd.w & 2u) {
+            // every input of the batch is stereo (the common session): one code variant inside the loop
+            for (uint32_t q = 0; q < nb; ++q) {
+                const uint32_t prog = sm + q * in_bytes;
+                chain_consume<OC, 2, ITERS>(acc, prog, prog + prog_cap, dm.prog, F, cw, lane, S->cons[q].gain, one2);
+            }
+        } else {
+            for (uint32_t q = 0; q < nb; ++q) {
+                const ChainCons c = S->cons[q];
+                const uint32_t prog = sm + q * in_bytes;
+                if (c.sc == 2u) chain_consume<OC, 2, ITERS>(acc, prog, prog + prog_cap, dm.prog, F, cw, lane, c.gain, one2);
+                else chain_consume<OC, 1, ITERS>(acc, prog, prog + prog_cap + SK_SIDE_HIST - 64u, dm.prog, F, cw, lane, c.gain, one2);
+            }
         }
         if (hd.z != 0) {
             // ---- epilogue: master gain, then clip + s16 pack (or f32); a warp stores 32 consecutive frames per instruction
             const float mg = S->master_gain;   // audio::gain after the mixer (1.0 when there is none: x * 1.0 == x)
             const uint32_t flags = S->flags;
             uint8_t *out_base = arena + S->out_off;
-            const uint32_t jw = cw * 128u + lane;
+            const uint32_t jw = cw * (CH_NB * 32u) + lane;
             if (flags & SKGPU_MIX_OUT_S16) {
                 // s16 = cvt.rni.sat(fl(a * g) * 32768). The power-of-two scale commutes with the rounding of a * g, so one
                 // multiply by g * 32768 gives the same integer (a subnormal a * g rounds to 0 either way, overflow saturates).
@@ -572,8 +641,8 @@ __global__ void __launch_bounds__(CH_THREADS, 4) k_chain(const OpHeader *__restr
 #pragma unroll
                 for (int it = 0; it < ITERS; ++it) {
 #pragma unroll
-                    for (int f = 0; f < 4; ++f) {
-                        const uint32_t j = jw + (uint32_t)it * 1024u + (uint32_t)f * 32u;
+                    for (int f = 0; f < CH_NB; ++f) {
+                        const uint32_t j = jw + (uint32_t)it * (CH_CWARPS * CH_NB * 32u) + (uint32_t)f * 32u;
                         if (j >= F) continue;
                         float a0, a1;
                         unpack2(mul2v(acc[it][f], mgs2), a0, a1);
@@ -589,8 +658,8 @@ __global__ void __launch_bounds__(CH_THREADS, 4) k_chain(const OpHeader *__restr
 #pragma unroll
                 for (int it = 0; it < ITERS; ++it) {
 #pragma unroll
-                    for (int f = 0; f < 4; ++f) {
-                        const uint32_t j = jw + (uint32_t)it * 1024u + (uint32_t)f * 32u;
+                    for (int f = 0; f < CH_NB; ++f) {
+                        const uint32_t j = jw + (uint32_t)it * (CH_CWARPS * CH_NB * 32u) + (uint32_t)f * 32u;
                         if (j >= F) continue;
                         float a0, a1;
                         unpack2(mul2v(acc[it][f], mg2), a0, a1);

@@ -18,7 +18,12 @@ EXPORTS = [
     "skgpu_hub_acquire", "skgpu_hub_commit", "skgpu_hub_commit_all",
     "skgpu_hub_tick",
     "skgpu_hub_wait", "skgpu_hub_wait_tick", "skgpu_hub_session_output", "skgpu_hub_live_sessions", "skgpu_hub_live_streams", "skgpu_hub_ticks",
+    "skgpu_hub_get_stats", "skgpu_hub_state",
 ]
+
+
+class HubStats(C.Structure):
+    _fields_ = [("received", C.c_uint64), ("sent", C.c_uint64), ("discarded", C.c_uint64), ("errored", C.c_uint64)]
 
 
 class HubConfig(C.Structure):
@@ -69,6 +74,9 @@ def load() -> C.CDLL:
         getattr(lib, n).restype = u32
     lib.skgpu_hub_ticks.argtypes = [vp]
     lib.skgpu_hub_ticks.restype = C.c_uint64
+    lib.skgpu_hub_get_stats.argtypes = [vp, C.POINTER(HubStats)]
+    lib.skgpu_hub_state.argtypes = [vp, C.POINTER(C.c_char_p)]
+    lib.skgpu_hub_state.restype = u32
     _lib = lib
     return lib
 
@@ -171,6 +179,16 @@ class Hub:
         else:
             buf = np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_float)), shape=(cnt,)).copy()
         return buf, n.value, st.value
+
+    def stats(self) -> dict:
+        st = HubStats()
+        _chk(self.lib.skgpu_hub_get_stats(self.h, C.byref(st)))
+        return {"received": st.received, "sent": st.sent, "discarded": st.discarded, "errored": st.errored}
+
+    def state(self):
+        reason = C.c_char_p()
+        code = self.lib.skgpu_hub_state(self.h, C.byref(reason))
+        return code, (reason.value.decode() if reason.value else None)
 
     @property
     def live_sessions(self) -> int:

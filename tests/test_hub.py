@@ -244,3 +244,116 @@ def test_hub_rejects_what_the_fused_chain_cannot_do():
             assert n_mixed == 0 and status == 0 and got is not None and not np.any(got)
     finally:
         hub.close()
+
+
+@pytest.mark.gpu
+def test_hub_pushes_racing_with_ticks_are_never_torn_or_misplaced():
+    """ADVICE r1 (hub.cpp:132): pusher threads run freely while the tick thread ticks. Every stream's chunks carry a
+    per-chunk constant k = 1, 2, 3, ... in every sample (input rate = output rate / 2 exactly: 24 kHz -> 48 kHz, so a
+    constant chunk resamples to that constant away from the chunk edges). Whatever the interleaving, each session's
+    output must show its chunk values in ORDER, each at most once, never a mixture inside the packet's interior -- a chunk
+    written into an arena that is already being uploaded would show up as a torn or repeated packet."""
+    import threading
+
+    S, T = 48, 60
+    hub = H.Hub(max_sessions=S, max_streams=S, in_rates=[24000], max_inputs_per_session=1, jitter_frames=3, s16=False)
+    try:
+        sids = [hub.session_open([24000]) for _ in range(S)]
+        n = hub.chunk_frames(sids[0], 0)
+        stop = threading.Event()
+        sent = [0] * S
+
+        def pusher(lo, hi):
+            k = 0
+            while not stop.is_set():
+                for a in range(lo, hi):
+                    sent[a] += 1
+                    hub.push(sids[a], 0, np.full(n * 2, np.float32(sent[a]) / np.float32(1024.0), np.float32))
+                k += 1
+                if k % 3 == 0:
+                    stop.wait(0.0005)
+
+        threads = [threading.Thread(target=pusher, args=(i * S // 4, (i + 1) * S // 4)) for i in range(4)]
+        for th in threads:
+            th.start()
+        seen = [[] for _ in range(S)]
+        try:
+            for _ in range(T):
+                hub.tick()
+                hub.wait()
+                for a, sid in enumerate(sids):
+                    got, n_mixed, status = hub.output(sid)
+                    assert status == 0
+                    if n_mixed:
+                        mid = got.reshape(960, 2)[200:700]          # interior of the packet: one chunk's constant
+                        v = float(mid[0, 0]) * 1024.0
+                        assert np.all(mid == mid[0, 0]), f"session {a}: torn packet"
+                        assert abs(v - round(v)) < 1e-3
+                        seen[a].append(int(round(v)))
+        finally:
+            stop.set()
+            for th in threads:
+                th.join()
+        for a in range(S):
+            s = seen[a]
+            assert len(s) > T // 4
+            assert all(y > x for x, y in zip(s, s[1:])), f"session {a}: chunks out of order or repeated: {s[:20]}"
+            assert s[-1] <= sent[a]
+        assert hub.stats()["received"] >= sum(len(s) for s in seen)   # + the chunks that only filled a stream's first packet
+    finally:
+        hub.close()
+
+
+@pytest.mark.gpu
+def test_hub_reopened_session_index_does_not_see_the_closed_sessions_audio():
+    """ADVICE r1 (hub.cpp:347): close A, open B (same session index), collect before B's first tick: 0 / NULL, not A's packet."""
+    hub = H.Hub(max_sessions=2, max_streams=4, in_rates=[44100], max_inputs_per_session=2)
+    try:
+        a = hub.session_open([44100])
+        for t in range(3):
+            hub.push(a, 0, _chunk(1, t, 44100, 882, 2))
+            hub.tick()
+            hub.wait()
+        got, n_mixed, _ = hub.output(a)
+        assert n_mixed == 1 and np.any(got)
+        hub.session_close(a)
+        b = hub.session_open([44100])
+        assert b == a                                   # the index is reused
+        got, n_mixed, status = hub.output(b)
+        assert got is None and n_mixed == 0 and status == 0
+        hub.tick()
+        hub.wait()
+        got, n_mixed, _ = hub.output(b)
+        assert n_mixed == 0 and got is not None and not np.any(got)   # B's own first tick: silence
+    finally:
+        hub.close()
+
+
+@pytest.mark.gpu
+def test_hub_stats_and_bounded_ticks_in_flight():
+    """NodeStatsTracker counters (stats.rs:131-152) and the two-ticks-in-flight bound (hub.cpp:494)."""
+    hub = H.Hub(max_sessions=2, max_streams=2, in_rates=[44100], max_inputs_per_session=1, jitter_frames=2)
+    try:
+        a, b = hub.session_open([44100]), hub.session_open([44100])
+        assert hub.state() == (1, None)
+        for t in range(6):                               # never waited for explicitly: the hub itself bounds the pipeline
+            hub.push(a, 0, _chunk(2, t, 44100, 882, 2))
+            if t % 2 == 0:
+                hub.push(b, 0, _chunk(3, t // 2, 44100, 882, 2))
+            hub.tick()
+        hub.wait()
+        for _ in range(4):
+            hub.push(a, 0, _chunk(2, 9, 44100, 882, 2))  # queue depth 2: two of these overwrite the oldest
+        with pytest.raises(H.HubError):
+            hub.set_master_gain(a, 5.0)
+        st = hub.stats()
+        assert st["received"] == 6 + 3 and st["sent"] == 12 and st["discarded"] == 2 and st["errored"] == 1
+        dst = hub.acquire(b, 0)
+        dst[:] = 0
+        hub.tick()
+        with pytest.raises(H.HubError) as e:             # a tick intervened between acquire and commit
+            hub.commit(b, 0)
+        assert e.value.rc == -4
+        hub.wait()
+    finally:
+        hub.close()
