@@ -1,23 +1,30 @@
 #!/usr/bin/env python
-"""bench.py -- headline benchmark of streamkit_b200 (driver contract in the task statement).
+"""bench.py -- benchmark of streamkit_b200 (driver contract in the task statement).
 
-Workload (BASELINE.json configs[4], the configuration the metric is quoted on; fits one GPU):
+Default workload (--config 5 = BASELINE.json configs[4], the configuration the metric is quoted on; fits one GPU):
     full chain resample 44.1k->48k -> per-input gain -> ordered mix -> master gain -> clip -> s16,
-    K = 2 stereo f32 inputs per session, SESSIONS_PER_GPU sessions per GPU, one 20 ms tick per step.
-Metric: concurrent real-time 48 kHz stereo sessions = session-ticks processed per second / 50.
+    K (--k, default 2) stereo f32 inputs per session, --sessions per GPU, one 20 ms tick per step.
+Metric: concurrent real-time 48 kHz stereo sessions per GPU whose 20 ms tick costs <= 2 ms of device time.
 
-  value : device-resident (inputs already in HBM when the timed region starts), CUDA events, max over ranks
-  e2e   : the same tick submitted through the C ABI with HOST (pinned) buffers: H2D of every input frame and
-          D2H of every s16 result inside the timed region
-  roofline     : dominant kernel (k_chain; k_resample with --unfused), algorithmic bytes / CUDA-event time vs measured HBM peak
-  cpu_baseline : the oracle's reference-shaped CPU chain (oracle/sk_chain.c) on the box's host cores
+  value        device-resident (inputs already in HBM when the timed region starts), CUDA events, max over ranks:
+               sessions x 2 ms / ms_per_step. `capacity_check` then RUNS that many sessions and reports the measured p99.
+  e2e          the same tick through the C ABI with HOST (pinned) buffers, SLICED (skgpu_plan_auto_slices): upload, kernels and
+               read-back of consecutive slices overlap on three streams, two ticks in flight. H2D of every input frame and D2H
+               of every s16 result are inside the timed region. `e2e.latency` = per slice upload-done -> read-back-done
+               (SURVEY 8d's added device latency), worst slice of each tick, p50 / p99 over --latency-ticks ticks.
+  roofline     dominant kernel, algorithmic bytes / CUDA-event time vs the measured HBM peak; `traffic` is read from the
+               committed ncu capture of the same workload (profiles/r2_ncu_full_summary.csv), not a constant in this file
+  parity       sampled sessions of the last end-to-end tick compared with the CPU chain (oracle/sk_chain.c) after the same
+               number of ticks -- the oracle is the checker here, never the thing measured
+  cpu_baseline the oracle's reference-shaped CPU run of the same workload on the box's host cores
 
-`--impl reference` times that CPU chain as the reference arm (the reference is Rust and cannot be built in this
-image: DESIGN.md "Oracle"; the C restatement is the port).
+--config 2 | 3 | 4 run the standalone node workloads (BASELINE configs[1..3]) with the same JSON contract.
+`--impl reference` times the CPU arm (the reference is Rust and cannot be built in this image: DESIGN.md "Oracle").
 """
 from __future__ import annotations
 
 import argparse
+import csv
 import json
 import os
 import statistics
@@ -31,26 +38,21 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-IN_RATE, OUT_RATE, CHANNELS, K_INPUTS = 44100, 48000, 2, 2
-TICK_MS = 20.0
-# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture
-# (profiles/r1_ncu_full_summary.csv: 1.100923 GB read + 252.77 MB written at 65,536 sessions x 2 inputs), or None
-TRAFFIC_NCU: dict = {"k_chain<2>": 1100923000 + 252765952}
-METRIC = "concurrent real-time 48 kHz stereo sessions (resample->mix->gain->s16, 20 ms ticks)"
+IN_RATE, OUT_RATE, CHANNELS = 44100, 48000, 2
+TICK_MS, BUDGET_MS = 20.0, 2.0
+METRIC = "concurrent real-time 48 kHz stereo sessions per GPU within the 2 ms device budget per 20 ms tick (resample->mix->gain->s16)"
 UNIT = "sessions"
 
 
-def workload_config(sessions_per_gpu: int, n_gpus: int) -> dict:
+def chain_config(sessions_per_gpu: int, n_gpus: int, k: int) -> dict:
     return {
-        "workload": "BASELINE configs[4]: full chain resample 44.1k->48k -> gain -> %d-input ordered mix -> gain -> clip -> s16"
-                    % K_INPUTS,
-        "sessions_per_gpu": sessions_per_gpu,
-        "inputs_per_session": K_INPUTS,
-        "in_rate": IN_RATE, "out_rate": OUT_RATE, "channels": CHANNELS, "tick_ms": TICK_MS,
+        "workload": "BASELINE configs[4]: full chain resample 44.1k->48k -> gain -> %d-input ordered mix -> gain -> clip -> s16" % k,
+        "sessions_per_gpu": sessions_per_gpu, "inputs_per_session": k,
+        "in_rate": IN_RATE, "out_rate": OUT_RATE, "channels": CHANNELS, "tick_ms": TICK_MS, "device_budget_ms": BUDGET_MS,
         "chunk_frames": IN_RATE // 50, "output_frame_size": 960,
         "sharding": "sessions split evenly across %d GPU(s) by session id, no collective" % n_gpus,
         "l2": "inputs are %.0f MB per tick per GPU (> 126 MB L2): no flush needed" %
-              (sessions_per_gpu * K_INPUTS * (IN_RATE // 50) * CHANNELS * 4 / 1e6),
+              (sessions_per_gpu * k * (IN_RATE // 50) * CHANNELS * 4 / 1e6),
     }
 
 
@@ -106,18 +108,79 @@ class ClockSampler:
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def hbm_peak():
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        return float(json.load(open(peaks_path))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (of measured)"
+    return 6650.0, "B200_PROFILING.md fallback 6.65 TB/s (of fallback)"
+
+
+def ncu_traffic(kernel_substr: str, grid_hint: str | None = None):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the kernel from the committed `ncu --set full` capture of THIS bench
+    command (profiles/r2_ncu_full_summary.csv, written by tools/export_profiles.sh). Returns (bytes per launch, source) or
+    (None, why)."""
+    path = os.path.join(ROOT, "profiles", "r2_ncu_full_summary.csv")
+    if not os.path.exists(path):
+        return None, "no committed capture (profiles/r2_ncu_full_summary.csv)"
+    rows = list(csv.reader(open(path)))
+    hdr, units = rows[0], rows[1]
+    for r in rows[2:]:
+        d = dict(zip(hdr, r))
+        if kernel_substr in d.get("Kernel Name", ""):
+            u = dict(zip(hdr, units))
+            scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+            try:
+                tot = float(d["dram__bytes_read.sum"]) * scale[u["dram__bytes_read.sum"]] + float(d["dram__bytes_write.sum"]) * scale[u["dram__bytes_write.sum"]]
+            except (KeyError, ValueError):
+                return None, "capture lacks dram__bytes"
+            return int(tot), "profiles/r2_ncu_full_summary.csv (ncu --set full, per launch)"
+    return None, "kernel not in the committed capture"
+
+
 # ---------------------------------------------------------------------------------------------- CPU arm
 
-def cpu_chain(n_sessions: int, ticks: int, threads: int, seed: int = 0):
-    """the oracle's reference-shaped chain on host cores; returns seconds for `ticks` ticks of n_sessions"""
+def cpu_chain(n_sessions: int, k: int, ticks: int, threads: int, seed: int = 0, pool=None, ig=None, mg=None, want_last=False):
+    """the oracle's reference-shaped chain on host cores; returns (seconds for `ticks` ticks of n_sessions, last outputs)"""
     from oracle import sko
     from streamkit_b200 import synth
 
-    pool = synth.noise_streams(seed, 0, 256, IN_RATE // 50, CHANNELS)
-    ig = synth.gains(seed, n_sessions * K_INPUTS, 0.25, 1.5)
-    mg = synth.gains(seed + 1, n_sessions, 0.5, 2.0)
-    sec, _cs, _ = sko.chain_bench(n_sessions, K_INPUTS, ticks, IN_RATE, CHANNELS, pool, ig, mg, threads)
-    return sec
+    if pool is None:
+        pool = synth.noise_streams(seed, 0, 256, IN_RATE // 50, CHANNELS)
+        ig = synth.gains(seed, n_sessions * k, 0.25, 1.5)
+        mg = synth.gains(seed + 1, n_sessions, 0.5, 2.0)
+    sec, _cs, last = sko.chain_bench(n_sessions, k, ticks, IN_RATE, CHANNELS, pool, ig, mg, threads, want_last=want_last)
+    return sec, last
+
+
+def cpu_node(config: int, units: int, iters: int, threads: int):
+    """reference-shaped CPU run of a standalone node workload; returns seconds"""
+    from oracle import sko
+
+    rng = np.random.default_rng(3)
+    if config == 2:
+        pool = (rng.random((512, 1920), dtype=np.float32) * 2 - 1).astype(np.float32)
+        return sko.node_bench(0, units, iters, pool, rng.random(units, dtype=np.float32) * 4, threads)[0]
+    if config == 3:
+        pool = (rng.random((2048, 1920), dtype=np.float32) * 2 - 1).astype(np.float32)
+        return sko.node_bench(1, units, iters, pool, rng.random(units, dtype=np.float32), threads, k_inputs=64)[0]
+    pool = (rng.random((256, 882 * 2), dtype=np.float32) - 0.5).astype(np.float32)
+    return sko.node_bench(2, units, iters, pool, None, threads, in_rate=IN_RATE, out_rate=OUT_RATE, cap=1000)[0]
+
+
+NODE_META = {
+    2: ("concurrent real-time 48 kHz stereo sessions per GPU within the 2 ms device budget (gain + f32->s16)", "sessions", 512 * 16),
+    3: ("64-input mix groups per 20 ms tick per GPU within the 2 ms device budget (ordered sum + gain + clip + s16)", "mix groups", 256),
+    4: ("concurrent real-time stereo resampler streams 44.1k->48k per GPU within the 2 ms device budget", "streams", 8192),
+}
+
+
+def node_config(config: int, n_gpus: int) -> dict:
+    w = {2: "BASELINE configs[1]: gain + f32<->s16 conversion over 4,096 concurrent 48 kHz stereo sessions, 20 ms frames",
+         3: "BASELINE configs[2]: N-input mixer (64 inputs per mix, with clip) x 1,024 mix groups per tick",
+         4: "BASELINE configs[3]: batched resampling 44.1k->48k over 16,384 stereo streams (48k->16k: --rs-down)"}[config]
+    return {"workload": w, "tick_ms": TICK_MS, "device_budget_ms": BUDGET_MS,
+            "sharding": "units split evenly across %d GPU(s), no collective" % n_gpus,
+            "l2": "device working set > 126 MB L2 (8 rotated tick buffers for configs[1]): no flush needed"}
 
 
 def run_reference(args) -> None:
@@ -125,20 +188,29 @@ def run_reference(args) -> None:
     if rank != 0:
         return
     cores = len(os.sched_getaffinity(0))
-    n_sessions = args.ref_sessions
-    # one "step" = one 20 ms tick of the bounded session sample; state carries across steps inside one call
-    cpu_chain(n_sessions, max(args.warmup, 1), cores)
-    sec = cpu_chain(n_sessions, args.steps, cores)
-    ms_per_step = sec * 1e3 / args.steps
-    value = n_sessions * TICK_MS / ms_per_step
-    sample = "%d sessions x %d ticks on %d host threads (oracle/sk_chain.c, reference-shaped per-packet nodes)" % (
-        n_sessions, args.steps, cores)
+    if args.config == 5:
+        n = args.ref_sessions
+        cpu_chain(n, args.k, max(args.warmup, 1), cores)
+        sec, _ = cpu_chain(n, args.k, args.steps, cores)
+        ms_per_step = sec * 1e3 / args.steps
+        value = n * TICK_MS / ms_per_step       # sessions the host cores sustain in real time (the CPU has no 2 ms device budget)
+        metric, unit, cfg = METRIC, UNIT, chain_config(args.sessions, args.gpus, args.k)
+        sample = ("bounded sample: %d sessions x %d ticks on %d host threads (oracle/sk_chain.c, reference-shaped per-packet nodes); value = "
+                  "sessions sustained in real time (20 ms per tick)") % (n, args.steps, cores)
+    else:
+        metric, unit, n = NODE_META[args.config]
+        cpu_node(args.config, n, max(args.warmup, 1), cores)
+        sec = cpu_node(args.config, n, args.steps, cores)
+        ms_per_step = sec * 1e3 / args.steps
+        value = n * TICK_MS / ms_per_step
+        cfg = node_config(args.config, args.gpus)
+        sample = "bounded sample: %d %s x %d passes on %d host threads (oracle/sk_chain.c sko_node_bench); value = units sustained in real time" % (n, unit, args.steps, cores)
     line = {
-        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "impl": "reference", "metric": metric, "value": value, "unit": unit, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic", "config": workload_config(args.sessions, args.gpus),
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
-        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "dtype": "f32", "data": "synthetic", "config": cfg,
+        "cpu_baseline": {"value": value, "unit": unit, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
         "note": "reference is Rust (no toolchain in this image): timed arm is the C restatement of its nodes; tokio scheduling"
                 " and channel hops of the real engine are not included (optimistic for the reference)",
@@ -148,24 +220,31 @@ def run_reference(args) -> None:
 
 # ---------------------------------------------------------------------------------------------- frame-batching layer
 
-def run_hub_e2e(S: int, steps: int, warmup: int, device: int, threads: int) -> dict:
+def run_hub_e2e(S: int, k: int, steps: int, warmup: int, device: int, threads: int) -> dict:
     """The same workload driven through the frame-batching layer (include/skgpu_hub.h): per tick the chunks of all
-    S x K streams are gathered from separate host buffers into the hub's pinned arena by `threads` worker threads
-    (skgpu_hub_push_batch), then one asynchronous tick; the gather of tick n + 1 overlaps tick n on the GPU.
+    S x K streams are gathered from DISTINCT host buffers (one private chunk per stream: the whole ~0.9 GB tick is read
+    from host memory every tick, nothing is cache resident) into the hub's pinned arena by `threads` worker threads
+    (skgpu_hub_push_batch), then one asynchronous sliced tick; the gather of tick n + 1 overlaps tick n on the GPU.
     Wall-clock time (it includes host work), results read back every tick."""
     from streamkit_b200 import hub as H, synth
 
     chunk = IN_RATE // 50
-    hub = H.Hub(max_sessions=S, max_streams=S * K_INPUTS, in_rates=[IN_RATE], max_inputs_per_session=K_INPUTS, channels=CHANNELS, device=device)
+    hub = H.Hub(max_sessions=S, max_streams=S * k, in_rates=[IN_RATE], max_inputs_per_session=k, channels=CHANNELS, device=device)
     try:
-        pool = np.ascontiguousarray(synth.noise_streams(4242, 0, 256, chunk, CHANNELS))   # 256 distinct chunks, reused round-robin
-        frames = np.zeros(S * K_INPUTS, dtype=H.FRAME_DT)
+        n = S * k
+        src = np.empty((n, chunk * CHANNELS), dtype=np.float32)        # every stream's own frame buffer (pageable, like decoder output)
+        blk = synth.noise_streams(4242, 0, 4096, chunk, CHANNELS)
+        for b in range(0, n, 4096):
+            m = min(4096, n - b)
+            src[b:b + m] = blk[:m]
+            src[b:b + m, 0] += np.arange(b, b + m, dtype=np.float32) * np.float32(1e-7)
+        frames = np.zeros(n, dtype=H.FRAME_DT)
         for s in range(S):
-            sid = hub.session_open([IN_RATE] * K_INPUTS)
-            for i in range(K_INPUTS):
-                f = frames[s * K_INPUTS + i]
+            sid = hub.session_open([IN_RATE] * k)
+            for i in range(k):
+                f = frames[s * k + i]
                 f["session"], f["input"], f["n_frames"] = sid, i, chunk
-        frames["samples"] = pool.ctypes.data + (np.arange(frames.size, dtype=np.uint64) % 256) * np.uint64(pool.strides[0])
+        frames["samples"] = src.ctypes.data + np.arange(n, dtype=np.uint64) * np.uint64(src.strides[0])
         for _ in range(max(4, warmup)):   # also fills every arena of the input ring
             hub.push_batch(frames, threads)
             hub.tick()
@@ -202,7 +281,8 @@ def run_hub_e2e(S: int, steps: int, warmup: int, device: int, threads: int) -> d
         return {"value": S * TICK_MS / ms, "zero_copy": {"value": S * TICK_MS / ms_zc, "ms_per_step": ms_zc,
                                                         "what": "producers write in place (skgpu_hub_acquire / commit), pipelined collection (skgpu_hub_wait_tick)"}, "unit": UNIT, "ms_per_step": ms, "gather_threads": threads, "sessions": S,
                 "host_ms": {"gather": t_push * 1e3 / max(steps - 1, 1), "wait": t_wait * 1e3 / max(steps - 1, 1), "tick_call": t_tick * 1e3 / max(steps - 1, 1)},
-                "what": "skgpu_hub: multi-threaded gather into pinned arena + H2D + kernels + D2H per tick, wall clock",
+                "what": "skgpu_hub: multi-threaded gather of %.0f MB of distinct per-stream frames into the pinned arena + H2D + kernels + D2H per tick, wall clock" % (src.nbytes / 1e6),
+                "stats": hub.stats(),
                 "check": {"n_mixed": int(n_mixed), "status": int(status), "nonzero": bool(out is not None and np.any(out != 0))}}
     finally:
         hub.close()
@@ -210,45 +290,87 @@ def run_hub_e2e(S: int, steps: int, warmup: int, device: int, threads: int) -> d
 
 # ---------------------------------------------------------------------------------------------- GPU arm
 
-def run_gpu(args) -> None:
-    import torch
+class Dist:
+    def __init__(self):
+        import torch
+        self.torch = torch
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py: no CUDA device; streamkit_b200 has no CPU fallback (use --impl reference for the CPU arm)")
+        torch.cuda.set_device(self.local_rank)
+        self.dist = None
+        if self.world > 1:
+            import torch.distributed as dist  # plumbing only: barrier + max-reduce of the timings (no data-path collective)
 
-    from streamkit_b200 import chain, lib as L, synth
+            if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+                os.environ["NCCL_DEBUG"] = "WARN"   # keep NCCL's version banner off stdout: rank 0 prints exactly one JSON line
+            dist.init_process_group("nccl", device_id=torch.device("cuda", self.local_rank))
+            self.dist = dist
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device; streamkit_b200 has no CPU fallback (use --impl reference for the CPU arm)")
-    torch.cuda.set_device(local_rank)
-    dist = None
-    if world > 1:
-        import torch.distributed as dist  # plumbing only: barrier + max-reduce of the timings (no data-path collective)
+    def barrier(self):
+        if self.dist is not None:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
 
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"   # keep NCCL's version banner off stdout: rank 0 prints exactly one JSON line
-
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-
-    def barrier():
-        if dist is not None:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def max_over_ranks(x: float) -> float:
-        if dist is None:
+    def max(self, x: float) -> float:
+        if self.dist is None:
             return x
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        t = self.torch.tensor([x], dtype=self.torch.float64, device="cuda")
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
         return float(t.item())
 
-    S = args.sessions
-    ct = chain.ChainTick(S, K_INPUTS, in_rate=IN_RATE, channels=CHANNELS, device=local_rank, seed=rank, fused=not args.unfused)
+    def close(self):
+        if self.dist is not None:
+            self.dist.destroy_process_group()
+
+
+def pct(v, q):
+    v = sorted(v)
+    return v[min(len(v) - 1, int(len(v) * q))]
+
+
+def capacity_check(S2: int, k: int, device: int, ticks: int = 60) -> dict:
+    """run S2 sessions (the claimed `value`) device-resident, tick by tick, and report the measured per-tick device time"""
+    from streamkit_b200 import chain, lib as L, synth
+
+    ct = chain.ChainTick(S2, k, in_rate=IN_RATE, channels=CHANNELS, device=device, seed=5, alloc_host=False)
+    try:
+        blk = synth.noise_streams(77, 0, 8192, ct.chunk, CHANNELS)
+        tile = np.zeros((8192, ct.in_stride // 4), np.float32)
+        tile[:, : blk.shape[1]] = blk
+        for bank in (0, ct.bank_stride):
+            for b in range(0, ct.n_streams, 8192):
+                m = min(8192, ct.n_streams - b)
+                ct.plan.upload(bank + b * ct.in_stride, tile[:m])
+        flags = L.SUBMIT_NO_H2D | L.SUBMIT_NO_D2H | L.SUBMIT_GRAPH
+        for _ in range(3):
+            ct.plan.submit(None, None, flags)
+        ct.plan.wait()
+        lat = []
+        for _ in range(ticks):
+            ct.plan.submit(None, None, flags)
+            lat.append(ct.plan.wait().kernels_ms)
+        res = ct.results()
+        return {"sessions": S2, "ticks": ticks, "p50_ms": pct(lat, 0.5), "p99_ms": pct(lat, 0.99), "max_ms": max(lat),
+                "within_budget": pct(lat, 0.99) <= BUDGET_MS, "all_emitted": bool(np.all(res["emitted"] == 1) and np.all(res["status"] == 0)),
+                "what": "the claimed session count run for real: device time of one whole tick's kernels, tick by tick"}
+    finally:
+        ct.close()
+
+
+def run_chain(args, D: Dist) -> None:
+    from streamkit_b200 import chain, lib as L, synth
+
+    world, rank, local_rank = D.world, D.rank, D.local_rank
+    S, K = args.sessions, args.k
+    ct = chain.ChainTick(S, K, in_rate=IN_RATE, channels=CHANNELS, device=local_rank, seed=rank, fused=not args.unfused)
     plan, ctx = ct.plan, ct.ctx
-    # synthetic input: a tick of noise for every stream of every session on this rank
+    ctx.bind_thread()
+    # synthetic input: a tick of noise for every stream of every session on this rank (all streams distinct)
     x = synth.noise_streams(1000 + rank, 0, ct.n_streams, ct.chunk, CHANNELS)
-    ct.host_in[:] = x.reshape(-1)
-    del x
+    ct.host_in.reshape(ct.n_streams, ct.in_stride // 4)[:, : x.shape[1]] = x
     plan.upload(0, ct.host_in)  # resident in HBM for the device-timed region
     if ct.fused:
         plan.upload(ct.bank_stride, ct.host_in)  # both input banks (the fused kernel reads the previous tick's bank)
@@ -262,118 +384,315 @@ def run_gpu(args) -> None:
     clocks = ClockSampler(local_rank)
     clocks.start()
     time.sleep(0.25)
-    barrier()
+    D.barrier()
     t_wall0 = time.time()
     ctx.timer_start()
     for _ in range(args.steps):
         plan.submit(None, None, dev_flags)
     ctx.timer_stop()
     dev_ms = ctx.timer_ms()
-    barrier()
-    dev_ms = max_over_ranks(dev_ms)
+    D.barrier()
+    dev_ms = D.max(dev_ms)
     ms_per_step = dev_ms / args.steps
     if ct.fused:
         phase_ms, _ = plan.op_time(ct.op_chain, 0)
         main_ms, n_main = plan.op_time(ct.op_chain, 1)
-        kernels_ms = {"k_phase": phase_ms, "k_chain": main_ms}
+        kernels_ms = {"k_phase_chain": phase_ms, "k_chain": main_ms}
     else:
         phase_ms, _ = plan.op_time(ct.op_rs, 0)
         main_ms, n_main = plan.op_time(ct.op_rs, 1)
         mix_ms, _ = plan.op_time(ct.op_mix, 0)
-        kernels_ms = {"k_phase": phase_ms, "k_resample": main_ms, "k_mix+k_fifo_commit": mix_ms}
-
-    # ---- per-tick device latency (added latency per 20 ms tick, p99 over >= 500 ticks): one tick at a time,
-    # kernels only (upload-done -> results ready for the read-back), CUDA events inside the library
+        kernels_ms = {"k_phase_prog": phase_ms, "k_resample_prog": main_ms, "k_mix+k_fifo_commit": mix_ms}
+    # the same ticks submitted and awaited one by one through the captured graph (what a 20 ms tick loop sees)
     lat = []
-    for _ in range(args.latency_ticks):
-        plan.submit(None, None, L.SUBMIT_NO_H2D | L.SUBMIT_NO_D2H)
+    for _ in range(min(args.latency_ticks, 200)):
+        plan.submit(None, None, L.SUBMIT_NO_H2D | L.SUBMIT_NO_D2H | L.SUBMIT_GRAPH)
         lat.append(plan.wait().kernels_ms)
-    lat.sort()
-    latency = {"ticks": len(lat), "p50_ms": lat[len(lat) // 2], "p99_ms": lat[min(len(lat) - 1, int(len(lat) * 0.99))], "max_ms": lat[-1],
-               "what": "device time of one tick's kernels at sessions_per_gpu sessions, submitted and awaited tick by tick"} if lat else None
+    tick_lat = {"ticks": len(lat), "p50_ms": pct(lat, 0.5), "p99_ms": pct(lat, 0.99), "max_ms": max(lat),
+                "what": "device time of one whole tick's kernels (CUDA graph), submitted and awaited tick by tick"} if lat else None
 
-    # ---- end-to-end region: every step copies its inputs from pinned host memory and reads the s16 result back
-    for _ in range(max(1, min(args.warmup, 3))):
-        plan.submit(ct.host_in, ct.host_out, 0)
-    plan.wait()
-    barrier()
-    ctx.timer_start()
-    for _ in range(args.steps):
-        plan.submit(ct.host_in, ct.host_out, L.SUBMIT_GRAPH | L.SUBMIT_OVERLAP_D2H)
-    ctx.timer_stop()
-    e2e_ms = ctx.timer_ms()
-    timing = plan.wait()
-    barrier()
+    # ---- end-to-end region: SLICED ticks, two in flight; every step uploads its inputs from pinned host memory and reads
+    # every s16 result back
+    e2e = {}
+    if ct.fused:
+        n_sl = max(1, min(args.slices, S))
+        plan.auto_slices(ct.op_chain, n_sl)
+        ins = [ct.host_in, ctx.pinned(ct.in_bytes, np.float32)]
+        outs = [ct.host_out, ctx.pinned(ct.out_bytes, np.int16)]
+        ins[1][:] = ins[0]
+        fl = L.SUBMIT_SLICED
+
+        def pipelined(n_ticks, collect):
+            first = plan.tick_count()
+            for t in range(n_ticks):
+                plan.submit(ins[t & 1], outs[t & 1], fl)
+                if t >= 1:
+                    plan.wait_for(first + t)              # the previous tick: collected while this one uploads
+                    if collect is not None:
+                        collect(plan.slice_timing(first + t))
+            plan.wait()
+            if collect is not None:
+                collect(plan.slice_timing(first + n_ticks))
+
+        pipelined(max(3, min(args.warmup, 4)), None)
+        D.barrier()
+        ctx.timer_start()
+        pipelined(args.steps, None)
+        ctx.timer_stop()
+        e2e_ms = ctx.timer_ms()
+        D.barrier()
+        e2e_ms = D.max(e2e_ms)
+        worst, kern, updone = [], [], []
+
+        def collect(tm):
+            worst.append(max(t[2] for t in tm))
+            kern.append(max(t[1] for t in tm))
+            updone.append(tm[-1][0])
+
+        if args.latency_ticks > 0:
+            pipelined(args.latency_ticks, collect)
+        last_out = outs[(args.latency_ticks - 1) & 1] if args.latency_ticks > 0 else outs[(args.steps - 1) & 1]
+        e2e_ms_per_step = e2e_ms / args.steps
+        e2e = {"ms_per_step": e2e_ms_per_step, "slices": n_sl, "ticks_in_flight": 2,
+               "h2d_gbs_per_gpu": ct.in_bytes / (e2e_ms_per_step * 1e-3) / 1e9, "d2h_gbs_per_gpu": ct.out_bytes / (e2e_ms_per_step * 1e-3) / 1e9,
+               "latency": {"ticks": len(worst), "p50_ms": pct(worst, 0.5), "p99_ms": pct(worst, 0.99), "max_ms": max(worst),
+                           "kernels_p99_ms": pct(kern, 0.99), "upload_of_whole_tick_ms_p50": pct(updone, 0.5),
+                           "budget_ms": BUDGET_MS, "within_budget": pct(worst, 0.99) <= BUDGET_MS,
+                           "what": "per slice: its upload done -> its results in host memory (kernels + read-back, SURVEY 8d added device "
+                                   "latency); worst slice of each tick; CUDA events"} if worst else None,
+               "host_in_to_host_out_ms": {"first_slice": (pct(updone, 0.5) / n_sl + pct(worst, 0.5)) if worst else None,
+                                          "last_slice": (pct(updone, 0.5) + pct(worst, 0.5)) if worst else None,
+                                          "what": "a frame handed over at the start of the tick's upload is back in host memory after this long "
+                                                  "(its slice's share of the upload + the slice latency)"}}
+    else:
+        for _ in range(3):
+            plan.submit(ct.host_in, ct.host_out, 0)
+        plan.wait()
+        D.barrier()
+        ctx.timer_start()
+        for _ in range(args.steps):
+            plan.submit(ct.host_in, ct.host_out, L.SUBMIT_GRAPH | L.SUBMIT_OVERLAP_D2H)
+        ctx.timer_stop()
+        e2e_ms = D.max(ctx.timer_ms())
+        plan.wait()
+        e2e_ms_per_step = e2e_ms / args.steps
+        e2e = {"ms_per_step": e2e_ms_per_step}
+        last_out = ct.host_out
+    D.barrier()
     t_wall1 = time.time()
-    e2e_ms = max_over_ranks(e2e_ms)
-    e2e_ms_per_step = e2e_ms / args.steps
     clk = clocks.stop(t_wall0, t_wall1)
+
+    # ---- parity of the bytes the timed run produced: sampled sessions vs the CPU chain after the same number of ticks
+    parity = None
+    if rank == 0 and ct.fused and args.parity_sessions > 0:
+        n_ticks = int(plan.tick_count())
+        ids = np.unique(np.concatenate([np.arange(min(64, S)), np.arange(max(0, S - 64), S),
+                                        np.random.default_rng(1).integers(0, S, args.parity_sessions)]))
+        streams = (ids[:, None] * K + np.arange(K)[None, :]).reshape(-1)
+        pool = np.ascontiguousarray(x[streams])
+        _sec, want = cpu_chain(len(ids), K, n_ticks, len(os.sched_getaffinity(0)), pool=pool, ig=ct.in_gains[streams], mg=ct.master_gains[ids], want_last=True)
+        got = np.asarray(last_out).reshape(S, -1)[ids]
+        bad = int(np.count_nonzero(np.any(got != want, axis=1)))
+        parity = {"sessions_checked": int(len(ids)), "ticks": n_ticks, "sessions_differing": bad, "bit_exact": bad == 0,
+                  "nonzero_samples_frac": float(np.count_nonzero(got)) / got.size,
+                  "what": "s16 bytes of the last end-to-end tick vs oracle/sk_chain.c run for the same number of ticks on the same inputs"}
+        if bad:
+            print("bench.py: PARITY FAILURE: %d of %d sampled sessions differ from the CPU chain" % (bad, len(ids)), file=sys.stderr)
 
     launches_per_tick = plan.launches_per_tick()
     dev_name, dev_sms, dev_cc_ma, dev_cc_mi = ctx.device_info()
-    ct.close()   # frees the arenas before the frame-batching layer allocates its own
-    hub_e2e = None
-    if args.hub:
-        try:
-            hub_e2e = run_hub_e2e(S, max(5, min(args.steps, 20)), 2, local_rank, max(1, len(os.sched_getaffinity(0)) // max(world, 1)))
-            if dist is not None:
-                hub_e2e["ms_per_step"] = max_over_ranks(hub_e2e["ms_per_step"])
-                hub_e2e["value"] = S * world * TICK_MS / hub_e2e["ms_per_step"]
-        except Exception as e:  # the layer is an extra: never lose the main line
-            hub_e2e = {"error": str(e)[:200]}
+    numa = {"gpu_node": ctx.numa_node(), "pinned_node": getattr(ctx, "last_pinned_node", -1)}
+    chain_bytes = ct.algorithmic_bytes_per_tick()
+    in_bytes, out_bytes, n_streams, in_stride = ct.in_bytes, ct.out_bytes, ct.n_streams, ct.in_stride
+    fused = ct.fused
+    ct.close()   # frees the arenas before the next legs allocate their own
+    del x
 
     total_sessions = S * world
-    value = total_sessions * TICK_MS / ms_per_step
-    e2e_value = total_sessions * TICK_MS / e2e_ms_per_step
+    value = total_sessions * BUDGET_MS / ms_per_step
+    cap = None
+    if args.capacity_check and fused:
+        S2 = int(S * BUDGET_MS / ms_per_step * 0.97) // 1024 * 1024
+        try:
+            cap = capacity_check(S2, K, local_rank)
+            cap["p99_ms"] = D.max(cap["p99_ms"])
+        except Exception as e:  # an extra: never lose the main line
+            cap = {"error": str(e)[:200], "sessions": S2}
+    hub_e2e = None
+    if args.hub and fused:
+        try:
+            hub_e2e = run_hub_e2e(S, K, max(5, min(args.steps, 20)), 2, local_rank, max(1, len(os.sched_getaffinity(0)) // max(world, 1)))
+            if D.dist is not None:
+                hub_e2e["ms_per_step"] = D.max(hub_e2e["ms_per_step"])
+                hub_e2e["value"] = S * world * TICK_MS / hub_e2e["ms_per_step"]
+        except Exception as e:
+            hub_e2e = {"error": str(e)[:200]}
 
+    e2e_value = total_sessions * TICK_MS / e2e["ms_per_step"]
     if rank == 0:
-        peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
-        if os.path.exists(peaks_path):
-            peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (of measured)"
-        else:
-            peak, peak_src = 6650.0, "B200_PROFILING.md fallback 6.65 TB/s (of fallback)"
-        chain_bytes = ct.algorithmic_bytes_per_tick()
-        if ct.fused:
+        peak, peak_src = hbm_peak()
+        if fused:
             # dominant kernel = k_chain: the fully fused algorithmic bytes of SURVEY 8(d) / BASELINE.md:
             # per session-tick K x (7056 in + 272 state r/w) + 3840 s16 out = 18,496 B (K = 2)
-            dom_name, dom_bytes = "k_chain<2>", chain_bytes
+            dom_name, dom_bytes = "k_chain<2,1>", chain_bytes
+            traffic, traffic_src = ncu_traffic("k_chain<") if (S == 65536 and K == 2) else (None, "the committed capture is of 65,536 sessions x 2 inputs")
         else:
-            # dominant kernel = k_resample: in + out + state r/w per stream-tick (15,008 B for 44.1k->48k stereo)
-            dom_name, dom_bytes = "k_resample<2>", ct.n_streams * (ct.in_stride + 960 * CHANNELS * 4 + 2 * (8 + 16 * CHANNELS * 4))
+            dom_name, dom_bytes = "k_resample_prog<2>", n_streams * (in_stride + 960 * CHANNELS * 4 + 2 * (8 + 16 * CHANNELS * 4))
+            traffic, traffic_src = None, "no capture of the unfused path"
         achieved = dom_bytes / (main_ms * 1e-3) / 1e9 if main_ms > 0 else 0.0
         cores = len(os.sched_getaffinity(0))
         cpu_sessions, cpu_ticks = args.ref_sessions, 50
-        cpu_chain(cpu_sessions, 2, cores)
-        cpu_sec = cpu_chain(cpu_sessions, cpu_ticks, cores)
+        cpu_chain(cpu_sessions, K, 2, cores)
+        cpu_sec, _ = cpu_chain(cpu_sessions, K, cpu_ticks, cores)
         cpu_value = cpu_sessions * TICK_MS / (cpu_sec * 1e3 / cpu_ticks)
-        name, sms, cc_ma, cc_mi = dev_name, dev_sms, dev_cc_ma, dev_cc_mi
+        e2e_line = {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": in_bytes * world, "d2h_bytes_per_step": out_bytes * world,
+                    "what": "sessions sustained in real time (20 ms per tick) with every input uploaded from and every result read back to host memory"}
+        e2e_line.update(e2e)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-            "data": "synthetic", "config": dict(workload_config(S, world), path="fused k_chain" if ct.fused else "unfused k_resample + k_mix"),
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": ct.in_bytes * world, "d2h_bytes_per_step": ct.out_bytes * world,
-                    "ms_per_step": e2e_ms_per_step, "last_tick_ms": {"h2d": timing.h2d_ms, "kernels": timing.kernels_ms, "d2h": timing.d2h_ms},
-                    "h2d_gbs_per_gpu": ct.in_bytes / (timing.h2d_ms * 1e-3) / 1e9 if timing.h2d_ms > 0 else None,
-                    "d2h_gbs_per_gpu": ct.out_bytes / (timing.d2h_ms * 1e-3) / 1e9 if timing.d2h_ms > 0 else None},
+            "data": "synthetic", "config": chain_config(S, world, K),
+            "value_definition": "sessions_per_gpu x n_gpus x 2 ms / ms_per_step: sessions whose whole tick (all kernels, inputs resident in HBM) "
+                                "fits the 2 ms device budget; capacity_check runs that many for real. Real-time capacity at 20 ms per tick is 10x that.",
+            "path": "fused k_phase_chain + k_chain" if fused else "unfused k_resample_prog + k_mix",
+            "device_realtime_sessions_20ms": total_sessions * TICK_MS / ms_per_step,
+            "capacity_check": cap,
+            "e2e": e2e_line,
             "e2e_hub": hub_e2e,
-            "gpu_launches": launches_per_tick * args.steps * 2,
+            "parity": parity,
+            "gpu_launches": launches_per_tick * args.steps + (2 * e2e.get("slices", 0) + 1) * args.steps,
             "clocks": clk,
             "roofline": {"bound": "hbm", "kernel": dom_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "frac_of_nominal_8000_gbs": achieved / 8000.0,
-                         "traffic": TRAFFIC_NCU.get(dom_name) if (S == 65536 and K_INPUTS == 2) else None,
+                         "traffic": traffic, "traffic_source": traffic_src,
                          "algorithmic_bytes_per_launch": dom_bytes,
                          "avg_launch_ms": main_ms, "launches_timed": n_main, "peak_source": peak_src},
             "kernels_ms": kernels_ms,
             "chain": {"algorithmic_bytes_per_tick": chain_bytes, "achieved_gbs": chain_bytes / (ms_per_step * 1e-3) / 1e9,
                       "frac_of_peak": chain_bytes / (ms_per_step * 1e-3) / 1e9 / peak,
-                      "device_ms_per_tick": ms_per_step, "latency_budget_ms": 2.0, "latency": latency},
+                      "device_ms_per_tick": ms_per_step, "tick_latency": tick_lat},
             "cpu_baseline": {"value": cpu_value, "unit": UNIT, "cores": cores, "kind": "port",
-                             "sample": "%d sessions x %d ticks on %d host threads (oracle/sk_chain.c)" % (cpu_sessions, cpu_ticks, cores)},
-            "device": {"name": name, "sms": sms, "cc": "%d.%d" % (cc_ma, cc_mi)},
+                             "sample": "%d sessions x %d ticks on %d host threads (oracle/sk_chain.c); sessions sustained in real time" % (cpu_sessions, cpu_ticks, cores)},
+            "host": {"cpus": cores, "numa": numa},
+            "device": {"name": dev_name, "sms": dev_sms, "cc": "%d.%d" % (dev_cc_ma, dev_cc_mi)},
         }
         print(json.dumps(line), flush=True)
-    if dist is not None:
-        dist.destroy_process_group()
+
+
+def run_node(args, D: Dist) -> None:
+    """BASELINE configs[1..3]: the standalone node kernels, same JSON contract"""
+    from oracle import sko
+    from streamkit_b200 import lib as L, workloads as W
+
+    world, rank, local_rank = D.world, D.rank, D.local_rank
+    ctx = None
+    if args.config == 2:
+        ctx = L.Context(device=local_rank, max_streams=16, max_channels=2)
+        w = W.GainS16(ctx, L.CVT_F32_TO_S16)
+    elif args.config == 3:
+        ctx = L.Context(device=local_rank, max_streams=16, max_channels=2)
+        w = W.Mix64(ctx, s16=True)
+    else:
+        w = W.Resample(48000, 16000, 16384, local_rank) if args.rs_down else W.Resample(IN_RATE, OUT_RATE, 16384, local_rank)
+    plan, wctx = w.plan, w.ctx
+    metric, unit, cpu_units = NODE_META[args.config]
+    host_in = wctx.pinned(w.in_bytes, np.uint8)
+    host_out = wctx.pinned(w.out_bytes, np.uint8)
+    w.fill_host(host_in)
+    plan.upload(0, host_in)
+    dev_flags = L.SUBMIT_NO_H2D | L.SUBMIT_NO_D2H | L.SUBMIT_TIME_OPS
+    for _ in range(args.warmup):
+        plan.submit(None, None, dev_flags)
+    plan.wait()
+    plan.reset_op_times()
+    clocks = ClockSampler(local_rank)
+    clocks.start()
+    time.sleep(0.25)
+    D.barrier()
+    t_wall0 = time.time()
+    wctx.timer_start()
+    for _ in range(args.steps):
+        plan.submit(None, None, dev_flags)
+    wctx.timer_stop()
+    ms_per_step = D.max(wctx.timer_ms()) / args.steps
+    kernels_ms = {name: plan.op_time(op, sub)[0] for op, sub, name in w.ops}
+    main_ms, n_main = plan.op_time(w.ops[0][0], w.ops[0][1])
+    # end to end: host buffers, upload + kernels + read-back every step
+    for _ in range(3):
+        plan.submit(host_in, host_out, 0)
+    plan.wait()
+    D.barrier()
+    wctx.timer_start()
+    for _ in range(args.steps):
+        plan.submit(host_in, host_out, L.SUBMIT_GRAPH | L.SUBMIT_OVERLAP_D2H)
+    wctx.timer_stop()
+    e2e_ms_per_step = D.max(wctx.timer_ms()) / args.steps
+    timing = plan.wait()
+    D.barrier()
+    clk = clocks.stop(t_wall0, time.time())
+    # parity of what the timed run produced (rank 0): every unit of a sample against the oracle
+    parity = None
+    if rank == 0:
+        cores = len(os.sched_getaffinity(0))
+        if args.config == 2:
+            n = w.units_per_launch
+            _s, want, _ = sko.node_bench(0, n, 1, w.pool, w.gains, cores, want_last=True)
+            got = host_out.view(np.int16).reshape(n, 1920)
+        elif args.config == 3:
+            n = w.G
+            _s, want, _ = sko.node_bench(1, n, 1, w.pool, w.master, cores, k_inputs=64, want_last=True)
+            got = host_out.view(np.int16)[: n * 1920].reshape(n, 1920)
+        else:
+            n = w.S
+            ticks = int(plan.tick_count())
+            _s, want_f, cnt = sko.node_bench(2, n, ticks, w.base, None, cores, in_rate=w.in_rate, out_rate=w.out_rate, want_last=True, cap=w.cap)
+            res = host_out[: 8 * n].view(L.RS_RESULT_DT)
+            o0 = w.out_off - w.res_off
+            outs = host_out[o0: o0 + n * w.out_stride].reshape(n, w.out_stride)[:, : w.cap * 8].copy().view(np.float32)
+            m = int(cnt.min())
+            got = np.concatenate([res["out_frames"].astype(np.uint32)[:, None], outs[:, : m * 2].view(np.uint32)], axis=1)
+            want = np.concatenate([cnt[:, None], want_f[:, : m * 2].view(np.uint32)], axis=1)
+        bad = int(np.count_nonzero(np.any(got != want, axis=1)))
+        parity = {"units_checked": int(n), "units_differing": bad, "bit_exact": bad == 0,
+                  "what": "every unit of the last end-to-end step vs the oracle (oracle/sk_chain.c sko_node_bench) on the same inputs"}
+    units = w.units_per_launch if args.config != 2 else w.S * w.rot
+    total_units = units * world
+    value = total_units * BUDGET_MS / ms_per_step
+    if rank == 0:
+        peak, peak_src = hbm_peak()
+        achieved = w.algorithmic_bytes / (main_ms * 1e-3) / 1e9
+        traffic, traffic_src = ncu_traffic({2: "k_convert<1", 3: "k_mix", 4: "k_resample_prog<2"}[args.config]) if not args.rs_down else (None, "no capture of 48k->16k")
+        cpu_node(args.config, cpu_units, 2, cores)
+        cpu_iters = 20
+        cpu_sec = cpu_node(args.config, cpu_units, cpu_iters, cores)
+        cpu_value = cpu_units * TICK_MS / (cpu_sec * 1e3 / cpu_iters)
+        line = {
+            "metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": node_config(args.config, world),
+            "value_definition": "%s per launch (%d) x n_gpus x 2 ms / ms_per_step; the BASELINE size (%s) takes %.1f us" % (
+                unit, units, {2: "4,096 sessions", 3: "1,024 groups", 4: "16,384 streams"}[args.config],
+                ms_per_step * 1e3 * {2: 4096, 3: 1024, 4: 16384}[args.config] / units),
+            "workload_detail": w.name,
+            "e2e": {"value": total_units * TICK_MS / e2e_ms_per_step, "unit": unit, "h2d_bytes_per_step": w.in_bytes * world,
+                    "d2h_bytes_per_step": w.out_bytes * world, "ms_per_step": e2e_ms_per_step,
+                    "last_step_ms": {"h2d": timing.h2d_ms, "kernels": timing.kernels_ms, "d2h": timing.d2h_ms},
+                    "what": "units sustained in real time (20 ms per tick) with host buffers: upload + kernels + read-back every step"},
+            "parity": parity,
+            "gpu_launches": plan.launches_per_tick() * args.steps * 2,
+            "clocks": clk,
+            "roofline": {"bound": "hbm", "kernel": w.ops[0][2], "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "frac_of_nominal_8000_gbs": achieved / 8000.0, "traffic": traffic, "traffic_source": traffic_src,
+                         "algorithmic_bytes_per_launch": w.algorithmic_bytes, "avg_launch_ms": main_ms, "launches_timed": n_main,
+                         "peak_source": peak_src},
+            "kernels_ms": kernels_ms,
+            "cpu_baseline": {"value": cpu_value, "unit": unit, "cores": cores, "kind": "port",
+                             "sample": "%d %s x %d passes on %d host threads (oracle/sk_chain.c sko_node_bench); units sustained in real time" % (cpu_units, unit, cpu_iters, cores)},
+        }
+        print(json.dumps(line), flush=True)
+    w.close()
+    if ctx is not None:
+        ctx.close()
 
 
 def main() -> None:
@@ -382,18 +701,31 @@ def main() -> None:
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", type=int, default=5, choices=[2, 3, 4, 5], help="BASELINE.json config number (1-based): 5 = full chain (default)")
     ap.add_argument("--sessions", type=int, default=65536, help="sessions per GPU (weak scaling)")
-    ap.add_argument("--unfused", action="store_true", help="use the general unfused ops (k_resample -> ring -> k_mix)")
+    ap.add_argument("--k", type=int, default=2, choices=[1, 2, 3, 4], help="inputs per session (SURVEY 8d: K = 1 and K = 2)")
+    ap.add_argument("--slices", type=int, default=16, help="slices per end-to-end tick")
+    ap.add_argument("--unfused", action="store_true", help="use the general unfused ops (k_resample_prog -> ring -> k_mix)")
+    ap.add_argument("--rs-down", action="store_true", help="--config 4: 48k->16k instead of 44.1k->48k")
     ap.add_argument("--ref-sessions", type=int, default=8192, help="bounded session sample of the CPU arm")
+    ap.add_argument("--parity-sessions", type=int, default=256, help="sessions of the timed run compared with the CPU chain (0 = skip)")
     ap.add_argument("--no-hub", dest="hub", action="store_false", help="skip the frame-batching-layer end-to-end measurement")
-    ap.add_argument("--latency-ticks", type=int, default=500, help="ticks of the per-tick latency measurement (0 = skip)")
+    ap.add_argument("--no-capacity-check", dest="capacity_check", action="store_false")
+    ap.add_argument("--latency-ticks", type=int, default=500, help="ticks of the per-slice latency measurement (0 = skip)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
     if args.impl == "reference":
         run_reference(args)
-    else:
-        run_gpu(args)
+        return
+    D = Dist()
+    try:
+        if args.config == 5:
+            run_chain(args, D)
+        else:
+            run_node(args, D)
+    finally:
+        D.close()
 
 
 if __name__ == "__main__":

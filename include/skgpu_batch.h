@@ -64,6 +64,19 @@ skgpu_rc skgpu_ctx_device_info(skgpu_ctx *ctx, char *name, size_t name_len, int3
  * Replaces AudioFramePool buckets (crates/core/src/frame_pool.rs:302-317) on the batched path. */
 skgpu_rc skgpu_pinned_alloc(skgpu_ctx *ctx, size_t bytes, void **out);
 skgpu_rc skgpu_pinned_free(skgpu_ctx *ctx, void *p);
+/* Placement-aware variant ("one pinned arena pair per GPU, NUMA-pin each to the GPU's socket"). The pages are
+ * mapped on the host NUMA node the GPU hangs off (sysfs numa_node of its PCI function; mbind MPOL_BIND before the pages
+ * are touched), transparent huge pages are requested, then the range is registered with CUDA (cudaHostRegister).
+ * SKGPU_PIN_WRITE_COMBINED (input arenas only: the CPU never reads them back) uses cudaHostAllocWriteCombined instead.
+ * skgpu_pinned_alloc == skgpu_pinned_alloc_ex(flags = SKGPU_PIN_NUMA_LOCAL). *node_out (may be NULL) receives the node the
+ * pages were bound to, -1 when the platform exposes none (single-node VM) and the default policy was kept. */
+#define SKGPU_PIN_NUMA_LOCAL 1u
+#define SKGPU_PIN_WRITE_COMBINED 2u
+skgpu_rc skgpu_pinned_alloc_ex(skgpu_ctx *ctx, size_t bytes, uint32_t flags, void **out, int32_t *node_out);
+/* host NUMA node of the context's GPU (-1 unknown) and the CPUs of that node as a bitmask string for logs ("0-15") */
+int32_t skgpu_ctx_numa_node(skgpu_ctx *ctx);
+/* pins the CALLING thread to the CPUs of the GPU's NUMA node (the submit / gather thread of this GPU); no-op when unknown */
+skgpu_rc skgpu_ctx_bind_thread(skgpu_ctx *ctx);
 
 /* ------------------------------------------------------------------ resampler stream slots
  * One slot = one rubato::FastFixedIn<f32>(Linear) instance (resampler.rs:232-238): last_index (f64) and
@@ -228,6 +241,33 @@ skgpu_rc skgpu_plan_set_banks(skgpu_plan *plan, uint64_t bank_stride);
 /* number of ticks submitted so far (bank of the NEXT tick = result & 1) */
 uint64_t skgpu_plan_tick_count(const skgpu_plan *plan);
 
+/* ---- sliced ticks (chain op). A tick of tens of thousands of sessions is ~1 GB up and ~250 MB down: submitted as one
+ * upload -> kernels -> read-back sequence, the first result leaves the device only after the LAST input byte arrived
+ * (17 ms + 0.4 ms + 4.4 ms at 65,536 sessions). With slices the tables are cut into n consecutive pieces; slice i's kernels
+ * start as soon as ITS inputs are uploaded and its results are read back while slice i + 1 still uploads (three streams,
+ * PCIe is full duplex). Per slice the added device latency -- upload-done -> results-in-host-memory -- is
+ * (kernels + read-back) / n. Requirements: the plan's only op is the chain op; slices are consecutive, cover the tables,
+ * and a slice's inputs lie below its h2d_end inside the H2D range (groups sorted by input offset do that). */
+typedef struct skgpu_slice {
+    uint32_t group_end;   /* this slice runs groups [previous group_end, group_end) */
+    uint32_t input_end;   /* ... which own inputs [previous input_end, input_end) */
+    uint64_t h2d_end;     /* its kernels wait for host_in[0 .. h2d_end) (byte offset inside the H2D range, non-decreasing) */
+    uint64_t d2h_off[2];  /* up to two byte ranges of the D2H range that are final after this slice (results rows, output rows) */
+    uint64_t d2h_bytes[2];
+} skgpu_slice;
+skgpu_rc skgpu_plan_set_slices(skgpu_plan *plan, uint32_t chain_op, const skgpu_slice *slices, uint32_t n);
+/* even split of the CURRENT tables into n slices (tables in input-offset order, outputs in group order, results rows first
+ * then outputs inside the D2H range -- the layout streamkit_b200's own hosts use); re-run after skgpu_plan_update_chain */
+skgpu_rc skgpu_plan_auto_slices(skgpu_plan *plan, uint32_t chain_op, uint32_t n);
+
+typedef struct skgpu_slice_timing { /* CUDA events of one slice of a finished sliced tick */
+    float upload_done_ms;   /* since the tick's first upload started */
+    float kernels_ms;       /* upload-done -> kernels-done (includes waiting for the previous slice's kernels) */
+    float latency_ms;       /* upload-done -> read-back-done: the slice's added device latency */
+} skgpu_slice_timing;
+/* timings of tick number `tick` (one of the two most recent, finished); returns the number of slices in *n_out */
+skgpu_rc skgpu_tick_slice_timing(skgpu_plan *plan, uint64_t tick, skgpu_slice_timing *out, uint32_t cap, uint32_t *n_out);
+
 /* per-tick dynamic parameters, snapshotted at submit (gain.rs:151: control messages are drained before
  * each packet, so a new gain applies from the next frame on). present[i] != 0 <=> input i of mix or chain op
  * `mix_op` delivered a frame this tick; absent inputs are silence (mixer.rs:999-1009, :1354-1367). */
@@ -241,6 +281,8 @@ skgpu_rc skgpu_plan_finalize(skgpu_plan *plan);
 #define SKGPU_SUBMIT_NO_D2H 2u
 #define SKGPU_SUBMIT_GRAPH 4u    /* replay the captured CUDA graph instead of individual launches */
 #define SKGPU_SUBMIT_TIME_OPS 8u /* record a CUDA event pair around every op (stream mode only) */
+#define SKGPU_SUBMIT_SLICED 32u   /* run the tick slice by slice (skgpu_plan_set_slices): upload, kernels and read-back of
+                                   * consecutive slices overlap on three streams; implies the overlapped read-back */
 #define SKGPU_SUBMIT_OVERLAP_D2H 16u /* read results back on a second stream so the copy overlaps the NEXT tick's upload
                                       * (host_out must stay untouched until the next skgpu_tick_wait) */
 

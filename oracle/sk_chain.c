@@ -149,3 +149,101 @@ double sko_chain_bench(uint32_t n_sessions, uint32_t k_inputs, uint32_t ticks, u
     free(jobs);
     return (double)(t1.tv_sec - t0.tv_sec) + 1e-9 * (double)(t1.tv_nsec - t0.tv_nsec);
 }
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * CPU runners of the standalone node workloads (BASELINE configs 2-4), reference-shaped: one node object per
+ * stream / mixer, one 20 ms packet per call, output in a freshly written buffer. `unit` u plays input
+ * pool[(u * stride) % pool_units]. Returns the wall seconds of `iters` passes over `n_units` units on `threads` pthreads.
+ * kind: 0 = audio::gain -> f32->s16 (1920 samples), 1 = audio::mixer 64 stereo inputs (clocked, 960) -> gain -> s16,
+ *       2 = audio::resampler chunk = in_rate/50, variable-length output. */
+typedef struct node_job {
+    int kind;
+    uint32_t u_begin, u_end, iters, in_rate, out_rate, k_inputs, pool_units;
+    const float *pool;
+    const float *gains;
+    int16_t *out_s16;   /* kind 0/1: [n_units][1920] of the last pass, or NULL */
+    float *out_f32;     /* kind 2: [n_units][cap*2] of the last pass, or NULL */
+    uint32_t *out_n;    /* kind 2: frames per unit of the last pass */
+    uint32_t cap;
+    pthread_barrier_t *start, *stop;
+} node_job;
+
+static void *node_worker(void *arg) {
+    node_job *j = (node_job *)arg;
+    const size_t N = 1920;
+    const uint32_t nu = j->u_end - j->u_begin;
+    int16_t *s16 = (int16_t *)malloc(N * sizeof(int16_t));
+    float *mixed = (float *)malloc(N * sizeof(float));
+    sko_ffi **rs = NULL;
+    float *rs_out = NULL;
+    const uint32_t chunk = j->in_rate / 50;
+    if (j->kind == 2) {
+        rs = (sko_ffi **)calloc(nu + 1, sizeof(*rs));
+        for (uint32_t u = 0; u < nu; u++) rs[u] = sko_ffi_new((double)j->out_rate / (double)j->in_rate, chunk, 2);
+        rs_out = (float *)malloc((size_t)j->cap * 2 * sizeof(float));
+    }
+    pthread_barrier_wait(j->start);
+    for (uint32_t it = 0; it < j->iters; it++) {
+        for (uint32_t u = 0; u < nu; u++) {
+            const uint32_t gu = j->u_begin + u;
+            if (j->kind == 0) {
+                const float *x = j->pool + (size_t)(gu % j->pool_units) * N;
+                sko_gain_f32_to_s16_buf(x, s16, N, j->gains[gu]);
+                if (j->out_s16 && it + 1 == j->iters) memcpy(j->out_s16 + (size_t)gu * N, s16, N * sizeof(int16_t));
+            } else if (j->kind == 1) {
+                sko_frame fr[64];
+                for (uint32_t i = 0; i < j->k_inputs; i++) {
+                    fr[i].samples = j->pool + (size_t)(((size_t)gu * 37 + (size_t)i * 101) % j->pool_units) * N;
+                    fr[i].n_samples = (uint32_t)N; fr[i].channels = 2; fr[i].unique = 1;
+                }
+                sko_mix_clocked(fr, j->k_inputs, 2, N / 2, mixed, N);
+                sko_gain_f32_to_s16_buf(mixed, s16, N, j->gains[gu]);
+                if (j->out_s16 && it + 1 == j->iters) memcpy(j->out_s16 + (size_t)gu * N, s16, N * sizeof(int16_t));
+            } else {
+                const float *x = j->pool + (size_t)(gu % j->pool_units) * chunk * 2;
+                const size_t n = sko_ffi_process_interleaved(rs[u], x, rs_out, j->cap);
+                if (j->out_f32 && it + 1 == j->iters) {
+                    memcpy(j->out_f32 + (size_t)gu * j->cap * 2, rs_out, n * 2 * sizeof(float));
+                    j->out_n[gu] = (uint32_t)n;
+                }
+            }
+        }
+    }
+    pthread_barrier_wait(j->stop);
+    if (rs) { for (uint32_t u = 0; u < nu; u++) sko_ffi_free(rs[u]); free(rs); }
+    free(rs_out); free(s16); free(mixed);
+    return NULL;
+}
+
+double sko_node_bench(int kind, uint32_t n_units, uint32_t iters, uint32_t in_rate, uint32_t out_rate, uint32_t k_inputs,
+                      const float *pool, uint32_t pool_units, const float *gains, int threads, int16_t *out_s16, float *out_f32,
+                      uint32_t *out_n, uint32_t cap) {
+    if (threads < 1) threads = 1;
+    if ((uint32_t)threads > n_units) threads = (int)(n_units ? n_units : 1);
+    pthread_t *th = (pthread_t *)calloc((size_t)threads, sizeof(*th));
+    node_job *jobs = (node_job *)calloc((size_t)threads, sizeof(*jobs));
+    pthread_barrier_t start, stop;
+    pthread_barrier_init(&start, NULL, (unsigned)threads + 1);
+    pthread_barrier_init(&stop, NULL, (unsigned)threads + 1);
+    struct timespec t0, t1;
+    for (int i = 0; i < threads; i++) {
+        jobs[i].kind = kind;
+        jobs[i].u_begin = (uint32_t)((uint64_t)n_units * i / threads);
+        jobs[i].u_end = (uint32_t)((uint64_t)n_units * (i + 1) / threads);
+        jobs[i].iters = iters; jobs[i].in_rate = in_rate; jobs[i].out_rate = out_rate; jobs[i].k_inputs = k_inputs;
+        jobs[i].pool = pool; jobs[i].pool_units = pool_units; jobs[i].gains = gains;
+        jobs[i].out_s16 = out_s16; jobs[i].out_f32 = out_f32; jobs[i].out_n = out_n; jobs[i].cap = cap;
+        jobs[i].start = &start; jobs[i].stop = &stop;
+        pthread_create(&th[i], NULL, node_worker, &jobs[i]);
+    }
+    pthread_barrier_wait(&start);
+    clock_gettime(CLOCK_MONOTONIC, &t0);
+    pthread_barrier_wait(&stop);
+    clock_gettime(CLOCK_MONOTONIC, &t1);
+    for (int i = 0; i < threads; i++) pthread_join(th[i], NULL);
+    pthread_barrier_destroy(&start);
+    pthread_barrier_destroy(&stop);
+    free(th);
+    free(jobs);
+    return (double)(t1.tv_sec - t0.tv_sec) + 1e-9 * (double)(t1.tv_nsec - t0.tv_nsec);
+}

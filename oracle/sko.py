@@ -76,6 +76,9 @@ def load() -> C.CDLL:
     lib.sko_chain_bench.restype = C.c_double
     lib.sko_chain_bench.argtypes = [C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint16, vp, C.c_uint32, vp, vp, C.c_int, vp,
                                     C.POINTER(C.c_uint64)]
+    lib.sko_node_bench.restype = C.c_double
+    lib.sko_node_bench.argtypes = [C.c_int, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, vp, C.c_uint32, vp, C.c_int, vp, vp, vp,
+                                   C.c_uint32]
     _lib = lib
     return lib
 
@@ -246,3 +249,19 @@ def chain_bench(n_sessions: int, k_inputs: int, ticks: int, in_rate: int, channe
     sec = load().sko_chain_bench(n_sessions, k_inputs, ticks, in_rate, channels, _p(pool), pool.shape[0], _p(ig), _p(mg), threads,
                                  _p(last) if want_last else None, C.byref(cs))
     return sec, cs.value, last
+
+
+def node_bench(kind: int, n_units: int, iters: int, pool: np.ndarray, gains: np.ndarray | None, threads: int, in_rate: int = 48000,
+               out_rate: int = 48000, k_inputs: int = 64, want_last: bool = False, cap: int = 0):
+    """multi-threaded, reference-shaped CPU run of a standalone node workload (sk_chain.c sko_node_bench):
+    kind 0 gain->s16, 1 mixer(64)->gain->s16, 2 resampler. Returns (seconds, last_out, last_counts)."""
+    pool = np.ascontiguousarray(pool, dtype=np.float32)
+    g = np.ascontiguousarray(gains if gains is not None else np.ones(n_units, np.float32), dtype=np.float32)
+    assert g.size >= n_units
+    out_s16 = np.zeros((n_units, 1920), np.int16) if (want_last and kind in (0, 1)) else None
+    out_f32 = np.zeros((n_units, cap * 2), np.float32) if (want_last and kind == 2) else None
+    out_n = np.zeros(n_units, np.uint32) if (want_last and kind == 2) else None
+    sec = load().sko_node_bench(kind, n_units, iters, in_rate, out_rate, k_inputs, _p(pool), pool.shape[0], _p(g), threads,
+                                _p(out_s16) if out_s16 is not None else None, _p(out_f32) if out_f32 is not None else None,
+                                _p(out_n) if out_n is not None else None, cap)
+    return sec, (out_s16 if kind in (0, 1) else out_f32), out_n

@@ -25,7 +25,7 @@ def _align(x: int, a: int = 256) -> int:
 
 class ChainTick:
     def __init__(self, n_sessions: int, k_inputs: int, in_rate: int = 44100, channels: int = 2, device: int = 0,
-                 seed: int = 0, chunk_frames: int | None = None, fused: bool = True, out_frames: int = OUT_FRAMES):
+                 seed: int = 0, chunk_frames: int | None = None, fused: bool = True, out_frames: int = OUT_FRAMES, alloc_host: bool = True):
         """fused=True: one k_chain launch per tick (double-banked input, lagged recompute, no HBM intermediates);
         fused=False: the general unfused ops (k_resample -> device re-framing ring -> k_mix)."""
         self.fused = fused
@@ -69,8 +69,9 @@ class ChainTick:
             self.op_chain = self.plan.add_chain(cg, cin, self.F, self.res_off)
             self.op_rs = self.op_mix = None
             self.plan.finalize()
-            self.host_in = self.ctx.pinned(self.in_bytes, np.float32)
-            self.host_out = self.ctx.pinned(self.out_bytes, np.int16)
+            if alloc_host:
+                self.host_in = self.ctx.pinned(self.in_bytes, np.float32)
+                self.host_out = self.ctx.pinned(self.out_bytes, np.int16)
             return
         items = np.zeros(self.n_streams, dtype=L.RS_ITEM_DT)
         items["in_off"] = np.arange(self.n_streams, dtype=np.uint64) * self.in_stride

@@ -19,7 +19,8 @@ namespace skgpu {
 struct OpHeader {       // lives in device memory so a captured graph sees table-size updates
     uint32_t count;     // live entries (<= capacity the grid was sized for)
     uint32_t count2;    // second table (mix / chain inputs)
-    uint32_t pad[2];
+    uint32_t first;     // chain op, sliced ticks: this launch covers groups [first, first + count) ...
+    uint32_t first2;    // ... and inputs [first2, first2 + count2) of the op's tables (0 for a whole-tick launch)
 };
 
 struct __align__(16) SlotRec {  // everything a kernel needs to know about one resampler stream: ONE 64-byte load

@@ -44,6 +44,7 @@ constexpr int CH_MAX_STAGES = 4;                  // pipeline depth is a launch 
 constexpr int CH_HEAD = 32;                       // frames of the CURRENT chunk staged behind the previous one
 constexpr int CH_MAX_INPUTS = 64;                 // inputs per session
 constexpr int CH_MAX_KB = 4;                      // inputs staged per batch
+constexpr int CH_PF = 8;                          // inputs per session whose records the producer prefetches (more: general path)
 constexpr uint32_t CH_PROG_MAX = SK_SIDE_STRIDE - SK_SIDE_HIST;   // side record = [frame program (prog_cap bytes) | 128-byte history field]
 
 struct __align__(8) ChainCons {   // what a consumer needs per input
@@ -188,9 +189,121 @@ __device__ __forceinline__ void fast_split(double x, uint32_t himask, uint32_t &
 // Any other block (a binade boundary inside it, explicit frames, the packet's head and tail: ~7 of 30) takes the general
 // path: every lane finds ITS segment (short divergent walk from the block map's first entry) and evaluates it.
 //   prog    shared-memory address of the program record; a_hist: of the 16-frame history (buffer position 0)
+// N consecutive blocks that lie inside the cached run, as ONE basic block: the N dependency chains (DADD -> split -> LDS ->
+// 5 packed operations) interleave, which is what hides their fixed latencies with only ~6 warps per scheduler
+template <int OC, int SC, int N>
+__device__ __forceinline__ void chain_pure(unsigned long long *acc, RunCache &rc, float gain, unsigned long long one2) {
+    double x[N];
+    uint32_t flh[N];
+    float frac[N];
+#pragma unroll
+    for (int n = 0; n < N; ++n) x[n] = __dadd_rn(n ? x[n - 1] : rc.xl, rc.dl32);
+    rc.xl = x[N - 1];
+#pragma unroll
+    for (int n = 0; n < N; ++n) fast_split(x[n], rc.himask, flh[n], frac[n]);
+#pragma unroll
+    for (int n = 0; n < N; ++n) acc_add(acc[n], chain_frame<OC, SC>((flh[n] >> rc.sh) + rc.kc, frac[n], gain, one2), one2);   // a_chunk + floor(x) * frame bytes
+}
+
+// one block, any shape: straight line when it lies inside the cached run (possibly after entering the run that covers it),
+// else the per-lane segment walk; `refresh`: the next block belongs to this warp too, so try to cache the block's last run
+template <int OC, int SC>
+__device__ __forceinline__ void chain_block(unsigned long long &acc, RunCache &rc, uint32_t blk, bool refresh, uint32_t prog, uint32_t segs, uint32_t a_hist,
+                                            uint32_t a_chunk, uint32_t F, uint32_t lane, float gain, unsigned long long one2) {
+    const uint32_t jb = blk * 32u;
+    bool pure = jb >= rc.j0 && jb + 32u <= rc.j1;
+    uint32_t e = 0;
+    if (!pure) {
+        if (jb >= F) return;                                   // warp-uniform (a pure block never lies past the packet)
+        asm volatile("ld.shared.u16 %0, [%1];" : "=r"(e) : "r"(prog + blk * 2u));
+        if ((e & 0xFFu) == (e >> 8)) {
+            // one segment covers the block (the warp's first block of an input, typically): if it is a FAST run, enter it
+            const uint32_t sa = segs + (e & 0xFFu) * 32u;
+            uint32_t ljj, lhimask, laux, lsh;
+            asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4+16];" : "=r"(ljj), "=r"(lhimask), "=r"(laux), "=r"(lsh) : "r"(sa));
+            if (lhimask > SKC_KIND_SLOW && (ljj >> 16) >= jb + 32u) {
+                double x0, dl;
+                asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(x0), "=d"(dl) : "r"(sa));
+                rc.j0 = ljj & 0xFFFFu;
+                rc.j1 = ljj >> 16;
+                rc.himask = lhimask;
+                rc.sh = lsh;
+                rc.kc = a_chunk - laux;
+                rc.dl32 = __dmul_rn(dl, 32.0);
+                // the lane's frame one block EARLIER on the run's lattice (a multiple of the binade's unit below 2^(e+1),
+                // hence exact, also when it extrapolates below the run's start); the straight-line path adds 32 delta
+                rc.xl = __fma_rn((double)((int)(jb + lane) - (int)rc.j0 - 32), dl, x0);
+                pure = true;
+            }
+        }
+    }
+    if (pure) {
+        // ---- straight line: the whole block lies inside the cached run
+        rc.xl = __dadd_rn(rc.xl, rc.dl32);
+        uint32_t flh;
+        float frac;
+        fast_split(rc.xl, rc.himask, flh, frac);
+        acc_add(acc, chain_frame<OC, SC>((flh >> rc.sh) + rc.kc, frac, gain, one2), one2);   // a_chunk + floor(x) * frame bytes
+    } else {
+        uint32_t addr;
+        float frac;
+        // ---- general: per-lane segment walk
+        const uint32_t j = min(jb + lane, F - 1u);               // lanes past the packet's end recompute its last frame
+        uint32_t sa = segs + (e & 0xFFu) * 32u;
+        const uint32_t sa_last = segs + (e >> 8) * 32u;
+        uint32_t jj, himask, aux, sh;
+        asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4+16];" : "=r"(jj), "=r"(himask), "=r"(aux), "=r"(sh) : "r"(sa));
+        while ((jj >> 16) <= j && sa < sa_last) {
+            sa += 32u;
+            asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4+16];" : "=r"(jj), "=r"(himask), "=r"(aux), "=r"(sh) : "r"(sa));
+        }
+        const uint32_t rel = j - (jj & 0xFFFFu);
+        if (himask == SKC_KIND_E) {
+            uint32_t aoff;
+            asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(aoff), "=f"(frac) : "r"(prog + aux + rel * 8u));
+            addr = a_hist + aoff;
+        } else {
+            double x0, dl;
+            asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(x0), "=d"(dl) : "r"(sa));
+            const double x = __fma_rn((double)rel, dl, x0);     // exact inside a run (phase_runs.h)
+            if (himask != SKC_KIND_SLOW) {
+                uint32_t flh;
+                fast_split(x, himask, flh, frac);
+                addr = (flh >> sh) + a_chunk - aux;
+            } else {
+                const unsigned long long pf = chain_split_slow(x, SC * 4u);
+                uint32_t off;
+                asm("mov.b64 {%0, %1}, %2;" : "=r"(off), "=f"(frac) : "l"(pf));
+                addr = a_chunk + off;
+            }
+        }
+        acc_add(acc, chain_frame<OC, SC>(addr, frac, gain, one2), one2);
+        // ---- refresh the run cache from the block's last segment when that is a FAST run reaching past the block
+        rc.j1 = 0;
+        if (refresh) {
+            uint32_t ljj, lhimask, laux, lsh;
+            asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4+16];" : "=r"(ljj), "=r"(lhimask), "=r"(laux), "=r"(lsh) : "r"(sa_last));
+            if (lhimask > SKC_KIND_SLOW && (ljj >> 16) >= jb + 64u) {   // warp-uniform
+                double x0, dl;
+                asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(x0), "=d"(dl) : "r"(sa_last));
+                rc.j0 = ljj & 0xFFFFu;
+                rc.j1 = ljj >> 16;
+                rc.himask = lhimask;
+                rc.sh = lsh;
+                rc.kc = a_chunk - laux;
+                rc.dl32 = __dmul_rn(dl, 32.0);
+                // this lane's frame of THIS block on the run's lattice (lanes before the run's start extrapolate below
+                // the binade: still a multiple of the binade's unit, so every later + 32 delta step is exact)
+                rc.xl = __fma_rn((double)((int)(jb + lane) - (int)rc.j0), dl, x0);
+            }
+        }
+    }
+}
+
 template <int OC, int SC, int ITERS>
 __device__ __forceinline__ void chain_consume(unsigned long long (&acc)[ITERS][CH_NB], uint32_t prog, uint32_t a_hist, const ChainProgDims &pd,
                                               uint32_t F, uint32_t cw, uint32_t lane, float gain, unsigned long long one2) {
+    static_assert(CH_NB % 4 == 0, "blocks are processed in aligned groups of four");
     const uint32_t segs = prog + skc_seg_off(pd);
     const uint32_t a_chunk = a_hist + 16u * SC * 4u;   // buffer position 16: floor(idx) == 0
     RunCache rc;
@@ -198,94 +311,21 @@ __device__ __forceinline__ void chain_consume(unsigned long long (&acc)[ITERS][C
 #pragma unroll
     for (int it = 0; it < ITERS; ++it) {
         if (ITERS > 1) rc.j1 = 0;   // the warp's next block is not adjacent
+        const uint32_t blk0 = ((uint32_t)it * CH_CWARPS + cw) * CH_NB;
 #pragma unroll
-        for (int f = 0; f < CH_NB; ++f) {
-            const uint32_t blk = ((uint32_t)it * CH_CWARPS + cw) * CH_NB + (uint32_t)f;
-            const uint32_t jb = blk * 32u;
-            bool pure = jb >= rc.j0 && jb + 32u <= rc.j1;
-            uint32_t e = 0;
-            if (!pure) {
-                if (jb >= F) continue;                                   // warp-uniform (a pure block never lies past the packet)
-                asm volatile("ld.shared.u16 %0, [%1];" : "=r"(e) : "r"(prog + blk * 2u));
-                if ((e & 0xFFu) == (e >> 8)) {
-                    // one segment covers the block (the warp's first block of an input, typically): if it is a FAST run, enter it
-                    const uint32_t sa = segs + (e & 0xFFu) * 32u;
-                    uint32_t ljj, lhimask, laux, lsh;
-                    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4+16];" : "=r"(ljj), "=r"(lhimask), "=r"(laux), "=r"(lsh) : "r"(sa));
-                    if (lhimask > SKC_KIND_SLOW && (ljj >> 16) >= jb + 32u) {
-                        double x0, dl;
-                        asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(x0), "=d"(dl) : "r"(sa));
-                        rc.j0 = ljj & 0xFFFFu;
-                        rc.j1 = ljj >> 16;
-                        rc.himask = lhimask;
-                        rc.sh = lsh;
-                        rc.kc = a_chunk - laux;
-                        rc.dl32 = __dmul_rn(dl, 32.0);
-                        // the lane's frame one block EARLIER on the run's lattice (a multiple of the binade's unit below 2^(e+1),
-                        // hence exact, also when it extrapolates below the run's start); the straight-line path adds 32 delta
-                        rc.xl = __fma_rn((double)((int)(jb + lane) - (int)rc.j0 - 32), dl, x0);
-                        pure = true;
-                    }
-                }
-            }
-            if (pure) {
-                // ---- straight line: the whole block lies inside the cached run
-                rc.xl = __dadd_rn(rc.xl, rc.dl32);
-                uint32_t flh;
-                float frac;
-                fast_split(rc.xl, rc.himask, flh, frac);
-                acc_add(acc[it][f], chain_frame<OC, SC>((flh >> rc.sh) + rc.kc, frac, gain, one2), one2);   // a_chunk + floor(x) * frame bytes
+        for (int f4 = 0; f4 < CH_NB; f4 += 4) {
+            const uint32_t jb4 = (blk0 + (uint32_t)f4) * 32u;
+            if (jb4 >= rc.j0 && jb4 + 128u <= rc.j1) {
+                chain_pure<OC, SC, 4>(&acc[it][f4], rc, gain, one2);
             } else {
-                uint32_t addr;
-                float frac;
-                // ---- general: per-lane segment walk
-                const uint32_t j = min(jb + lane, F - 1u);               // lanes past the packet's end recompute its last frame
-                uint32_t sa = segs + (e & 0xFFu) * 32u;
-                const uint32_t sa_last = segs + (e >> 8) * 32u;
-                uint32_t jj, himask, aux, sh;
-                asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4+16];" : "=r"(jj), "=r"(himask), "=r"(aux), "=r"(sh) : "r"(sa));
-                while ((jj >> 16) <= j && sa < sa_last) {
-                    sa += 32u;
-                    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4+16];" : "=r"(jj), "=r"(himask), "=r"(aux), "=r"(sh) : "r"(sa));
-                }
-                const uint32_t rel = j - (jj & 0xFFFFu);
-                if (himask == SKC_KIND_E) {
-                    uint32_t aoff;
-                    asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(aoff), "=f"(frac) : "r"(prog + aux + rel * 8u));
-                    addr = a_hist + aoff;
-                } else {
-                    double x0, dl;
-                    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(x0), "=d"(dl) : "r"(sa));
-                    const double x = __fma_rn((double)rel, dl, x0);     // exact inside a run (phase_runs.h)
-                    if (himask != SKC_KIND_SLOW) {
-                        uint32_t flh;
-                        fast_split(x, himask, flh, frac);
-                        addr = (flh >> sh) + a_chunk - aux;
+#pragma unroll
+                for (int f2 = f4; f2 < f4 + 4; f2 += 2) {
+                    const uint32_t jb2 = (blk0 + (uint32_t)f2) * 32u;
+                    if (jb2 >= rc.j0 && jb2 + 64u <= rc.j1) {
+                        chain_pure<OC, SC, 2>(&acc[it][f2], rc, gain, one2);
                     } else {
-                        const unsigned long long pf = chain_split_slow(x, SC * 4u);
-                        uint32_t off;
-                        asm("mov.b64 {%0, %1}, %2;" : "=r"(off), "=f"(frac) : "l"(pf));
-                        addr = a_chunk + off;
-                    }
-                }
-                acc_add(acc[it][f], chain_frame<OC, SC>(addr, frac, gain, one2), one2);
-                // ---- refresh the run cache from the block's last segment when that is a FAST run reaching past the block
-                rc.j1 = 0;
-                if (f + 1 < CH_NB) {
-                    uint32_t ljj, lhimask, laux, lsh;
-                    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4+16];" : "=r"(ljj), "=r"(lhimask), "=r"(laux), "=r"(lsh) : "r"(sa_last));
-                    if (lhimask > SKC_KIND_SLOW && (ljj >> 16) >= jb + 64u) {   // warp-uniform
-                        double x0, dl;
-                        asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(x0), "=d"(dl) : "r"(sa_last));
-                        rc.j0 = ljj & 0xFFFFu;
-                        rc.j1 = ljj >> 16;
-                        rc.himask = lhimask;
-                        rc.sh = lsh;
-                        rc.kc = a_chunk - laux;
-                        rc.dl32 = __dmul_rn(dl, 32.0);
-                        // this lane's frame of THIS block on the run's lattice (lanes before the run's start extrapolate below
-                        // the binade: still a multiple of the binade's unit, so every later + 32 delta step is exact)
-                        rc.xl = __fma_rn((double)((int)(jb + lane) - (int)rc.j0), dl, x0);
+                        chain_block<OC, SC>(acc[it][f2], rc, blk0 + (uint32_t)f2, true, prog, segs, a_hist, a_chunk, F, lane, gain, one2);
+                        chain_block<OC, SC>(acc[it][f2 + 1], rc, blk0 + (uint32_t)f2 + 1u, f2 + 2 < CH_NB, prog, segs, a_hist, a_chunk, F, lane, gain, one2);
                     }
                 }
             }
@@ -300,8 +340,9 @@ __global__ void __launch_bounds__(PHASE_CHAIN_THREADS, 14) k_phase_chain(const O
                                                                      const uint8_t *__restrict__ present, const float *__restrict__ gains, SlotTables st,
                                                                      uint8_t *__restrict__ arena, const uint32_t *__restrict__ tick, uint64_t bank_stride,
                                                                      uint32_t F, uint64_t results_off, ChainDims dm, ChainRec *__restrict__ recs) {
-    const uint32_t i = blockIdx.x * PHASE_CHAIN_THREADS + threadIdx.x;
-    if (i >= hdr->count2) return;
+    const uint32_t il = blockIdx.x * PHASE_CHAIN_THREADS + threadIdx.x;
+    if (il >= hdr->count2) return;
+    const uint32_t i = il + hdr->first2;   // a sliced tick launches this kernel once per slice of the tables
     const skgpu_chain_input in = inputs[i];
     const uint32_t slot = in.slot;
     SlotRec *recp = st.rec + slot;
@@ -386,7 +427,7 @@ __global__ void __launch_bounds__(PHASE_CHAIN_THREADS, 14) k_phase_chain(const O
 }
 
 template <int OC, int ITERS>  // output channels (1 | 2); ITERS = ceil(F / 1024)
-__global__ void __launch_bounds__(CH_THREADS, 5) k_chain(const OpHeader *__restrict__ hdr, const skgpu_chain_group *__restrict__ groups,
+__global__ void __launch_bounds__(CH_THREADS, 6) k_chain(const OpHeader *__restrict__ hdr, const skgpu_chain_group *__restrict__ groups,
                                                          const ChainRec *__restrict__ recs, const float *__restrict__ gains, SlotTables st,
                                                          uint8_t *__restrict__ arena, uint32_t F, ChainDims dm) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
@@ -402,6 +443,7 @@ __global__ void __launch_bounds__(CH_THREADS, 5) k_chain(const OpHeader *__restr
     const uint32_t stage_bytes = kb * in_bytes;
     ChainRec *s_res = reinterpret_cast<ChainRec *>(smem_raw + (size_t)stage_bytes * nstages);
     const uint32_t n_groups = hdr->count;
+    groups += hdr->first;                  // a sliced tick launches this kernel once per slice of the tables
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
 
     if (threadIdx.x == 0) {
@@ -417,7 +459,7 @@ __global__ void __launch_bounds__(CH_THREADS, 5) k_chain(const OpHeader *__restr
     if (warp == 0) {
         // =============================================================== producer warp
         __shared__ __align__(16) skgpu_chain_group pf_grp[4];
-        __shared__ __align__(16) ChainRec pf_rec[2][32];
+        __shared__ __align__(16) ChainRec pf_rec[2][CH_PF];
         const uint32_t gstep = gridDim.x;
         uint32_t stage = 0, ephase = 1;  // waiting on parity 1 of a fresh mbarrier returns immediately
         auto sess = [&](uint32_t n) -> uint32_t { return blockIdx.x + n * gstep; };
@@ -427,7 +469,7 @@ __global__ void __launch_bounds__(CH_THREADS, 5) k_chain(const OpHeader *__restr
         auto issue_rec = [&](uint32_t n) {
             if (sess(n) >= n_groups) return;
             const skgpu_chain_group &g = pf_grp[n & 3u];
-            if (lane < min(g.n_inputs, 32u)) {
+            if (lane < min(g.n_inputs, (uint32_t)CH_PF)) {
                 const uint8_t *src = reinterpret_cast<const uint8_t *>(recs + g.first_input + lane);
                 uint8_t *dst = reinterpret_cast<uint8_t *>(&pf_rec[n & 1u][lane]);
 #pragma unroll
@@ -479,7 +521,8 @@ __global__ void __launch_bounds__(CH_THREADS, 5) k_chain(const OpHeader *__restr
             ChainRec r;
             r.flags = 0;
             r.cons.sc = 0;
-            if (lane < min(K, 32u)) r = pf_rec[n & 1u][lane];
+            if (lane < min(K, (uint32_t)CH_PF)) r = pf_rec[n & 1u][lane];
+            else if (lane < min(K, 32u)) r = recs[grp.first_input + lane];   // big sessions: straight from HBM
             const bool emit = (r.flags & CR_EMIT) != 0;
             const bool elig = emit && r.cons.sc == (uint32_t)OC;   // packet already has the output shape
             // ---- summation order over the inputs that deliver a packet: base selection + swap_remove (mixer.rs:960-980),
@@ -490,7 +533,7 @@ __global__ void __launch_bounds__(CH_THREADS, 5) k_chain(const OpHeader *__restr
             const uint32_t unal_mask = __ballot_sync(0xffffffffu, emit && (r.flags & CR_UNALIGNED));
             const uint32_t mono_mask = __ballot_sync(0xffffffffu, emit && r.cons.sc != 2u);
             uint32_t m = __popc(emit_mask);
-            if (K <= 32u && m <= kb && unal_mask == 0u) {
+            if (K <= (uint32_t)CH_PF && m <= kb && unal_mask == 0u) {
                 // ---- common path. max_by_key((unique, idx)): the last unique full-shape frame, else the last full-shape frame
                 const int base_lane = uniq_mask ? 31 - __clz(uniq_mask) : (elig_mask ? 31 - __clz(elig_mask) : -1);
                 const uint32_t rank = __popc(emit_mask & ((1u << lane) - 1u));

@@ -7,14 +7,22 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <cctype>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
+#include <mutex>
 #include <new>
 #include <string>
 #include <vector>
+
+#include <sched.h>
+#include <sys/mman.h>
+#include <sys/syscall.h>
+#include <unistd.h>
 
 #include "kernels.cuh"
 
@@ -52,6 +60,12 @@ struct skgpu_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
     cudaStream_t stream_d2h = nullptr;   // result read-back runs here so it overlaps the next tick's upload (PCIe is full duplex)
+    cudaStream_t stream_k = nullptr;     // sliced ticks: kernels run here, uploads stay on `stream`
+    int numa_node = -1;                  // host NUMA node of the GPU's PCI function (-1: unknown / single node)
+    std::vector<int> node_cpus;          // CPUs of that node
+    struct PinnedBlock { size_t bytes; int kind; };   // kind 0: cudaHostAlloc, 1: mmap + cudaHostRegister
+    std::map<void *, PinnedBlock> pinned;
+    std::mutex pinned_mu;
     cudaEvent_t tm0 = nullptr, tm1 = nullptr;
     skgpu_ctx_config cfg{};
     SlotTables st{};
@@ -102,6 +116,8 @@ static skgpu_rc ctx_flush(skgpu_ctx *c) {
     return SKGPU_OK;
 }
 
+static void detect_numa(skgpu_ctx *c);
+
 extern "C" skgpu_rc skgpu_ctx_create(int32_t device_ordinal, const skgpu_ctx_config *cfg, skgpu_ctx **out) {
     if (!cfg || !out) return fail(SKGPU_ERR_INVALID, "skgpu_ctx_create: null argument");
     if (cfg->max_streams == 0) return fail(SKGPU_ERR_INVALID, "max_streams must be > 0");
@@ -124,6 +140,8 @@ extern "C" skgpu_rc skgpu_ctx_create(int32_t device_ordinal, const skgpu_ctx_con
     c->sm_count = prop.multiProcessorCount;
     CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     CU(cudaStreamCreateWithFlags(&c->stream_d2h, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&c->stream_k, cudaStreamNonBlocking));
+    detect_numa(c);
     CU(cudaEventCreate(&c->tm0));
     CU(cudaEventCreate(&c->tm1));
     const size_t S = cfg->max_streams;
@@ -162,6 +180,11 @@ extern "C" void skgpu_ctx_destroy(skgpu_ctx *c) {
     if (c->d_reset) cudaFree(c->d_reset);
     if (c->l2buf) cudaFree(c->l2buf);
     cudaEventDestroy(c->tm0); cudaEventDestroy(c->tm1);
+    for (auto &kv : c->pinned) {
+        if (kv.second.kind == 1) { cudaHostUnregister(kv.first); munmap(kv.first, kv.second.bytes); }
+        else cudaFreeHost(kv.first);
+    }
+    cudaStreamDestroy(c->stream_k);
     cudaStreamDestroy(c->stream_d2h);
     cudaStreamDestroy(c->stream);
     delete c;
@@ -178,15 +201,107 @@ extern "C" skgpu_rc skgpu_ctx_device_info(skgpu_ctx *c, char *name, size_t name_
     return SKGPU_OK;
 }
 
-extern "C" skgpu_rc skgpu_pinned_alloc(skgpu_ctx *c, size_t bytes, void **out) {
-    if (!c || !out) return fail(SKGPU_ERR_INVALID, "null argument");
-    CU(cudaSetDevice(c->device));
-    CU(cudaHostAlloc(out, bytes ? bytes : 16, cudaHostAllocDefault));
+// ---- NUMA placement of the pinned tick arenas. No libnuma in the image: sysfs + the mbind syscall.
+static void detect_numa(skgpu_ctx *c) {
+    char bus[32] = {0};
+    if (cudaDeviceGetPCIBusId(bus, sizeof bus, c->device) != cudaSuccess) { cudaGetLastError(); return; }
+    for (char *p = bus; *p; ++p) *p = (char)tolower(*p);
+    char path[128];
+    snprintf(path, sizeof path, "/sys/bus/pci/devices/%s/numa_node", bus);
+    FILE *f = fopen(path, "r");
+    if (!f) return;
+    int node = -1;
+    if (fscanf(f, "%d", &node) != 1) node = -1;
+    fclose(f);
+    if (node < 0) return;
+    snprintf(path, sizeof path, "/sys/devices/system/node/node%d/cpulist", node);
+    f = fopen(path, "r");
+    if (!f) return;
+    char buf[4096] = {0};
+    if (!fgets(buf, sizeof buf, f)) buf[0] = 0;
+    fclose(f);
+    cpu_set_t allowed;
+    CPU_ZERO(&allowed);
+    sched_getaffinity(0, sizeof allowed, &allowed);
+    for (char *tok = strtok(buf, ",\n"); tok; tok = strtok(nullptr, ",\n")) {
+        int a = 0, b = 0;
+        if (sscanf(tok, "%d-%d", &a, &b) == 2) { for (int k = a; k <= b; ++k) if (k < CPU_SETSIZE && CPU_ISSET(k, &allowed)) c->node_cpus.push_back(k); }
+        else if (sscanf(tok, "%d", &a) == 1) { if (a < CPU_SETSIZE && CPU_ISSET(a, &allowed)) c->node_cpus.push_back(a); }
+    }
+    c->numa_node = node;
+}
+
+extern "C" int32_t skgpu_ctx_numa_node(skgpu_ctx *c) { return c ? c->numa_node : -1; }
+
+extern "C" skgpu_rc skgpu_ctx_bind_thread(skgpu_ctx *c) {
+    if (!c) return fail(SKGPU_ERR_INVALID, "null context");
+    if (c->node_cpus.empty()) return SKGPU_OK;
+    cpu_set_t set;
+    CPU_ZERO(&set);
+    for (int k : c->node_cpus) CPU_SET(k, &set);
+    if (sched_setaffinity(0, sizeof set, &set) != 0) return fail(SKGPU_ERR_STATE, "sched_setaffinity to NUMA node %d failed", c->numa_node);
     return SKGPU_OK;
 }
+
+extern "C" skgpu_rc skgpu_pinned_alloc_ex(skgpu_ctx *c, size_t bytes, uint32_t flags, void **out, int32_t *node_out) {
+    if (!c || !out) return fail(SKGPU_ERR_INVALID, "null argument");
+    CU(cudaSetDevice(c->device));
+    if (node_out) *node_out = -1;
+    if (bytes == 0) bytes = 16;
+    if ((flags & SKGPU_PIN_NUMA_LOCAL) && c->numa_node >= 0 && !(flags & SKGPU_PIN_WRITE_COMBINED)) {
+        // map, bind to the GPU's node BEFORE the first touch, ask for huge pages, then pin: cudaHostRegister faults the
+        // pages in under the MPOL_BIND policy, so every page of the arena is local to the GPU's PCIe root
+        const size_t len = (bytes + (2u << 20) - 1) & ~((size_t)(2u << 20) - 1);
+        void *p = mmap(nullptr, len, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
+        if (p != MAP_FAILED) {
+            unsigned long mask[16] = {0};
+            mask[c->numa_node / (8 * sizeof(unsigned long))] |= 1ul << (c->numa_node % (8 * sizeof(unsigned long)));
+            const long rc = syscall(SYS_mbind, p, len, 2 /* MPOL_BIND */, mask, sizeof(mask) * 8, 0);
+            madvise(p, len, MADV_HUGEPAGE);
+            if (cudaHostRegister(p, len, cudaHostRegisterPortable) == cudaSuccess) {
+                std::lock_guard<std::mutex> lk(c->pinned_mu);
+                c->pinned[p] = {len, 1};
+                *out = p;
+                if (node_out) *node_out = rc == 0 ? c->numa_node : -1;
+                return SKGPU_OK;
+            }
+            cudaGetLastError();
+            munmap(p, len);   // fall through to the plain allocation
+        }
+    }
+    // plain path: first touch on a thread bound to the GPU's node keeps the pages local under the default policy
+    cpu_set_t saved;
+    bool rebound = false;
+    if ((flags & SKGPU_PIN_NUMA_LOCAL) && !c->node_cpus.empty() && sched_getaffinity(0, sizeof saved, &saved) == 0) {
+        cpu_set_t set;
+        CPU_ZERO(&set);
+        for (int k : c->node_cpus) CPU_SET(k, &set);
+        rebound = sched_setaffinity(0, sizeof set, &set) == 0;
+    }
+    const cudaError_t e = cudaHostAlloc(out, bytes, (flags & SKGPU_PIN_WRITE_COMBINED) ? cudaHostAllocWriteCombined : cudaHostAllocDefault);
+    if (rebound) sched_setaffinity(0, sizeof saved, &saved);
+    if (e != cudaSuccess) return fail(SKGPU_ERR_NOMEM, "cudaHostAlloc(%zu) failed: %s", bytes, cudaGetErrorString(e));
+    {
+        std::lock_guard<std::mutex> lk(c->pinned_mu);
+        c->pinned[*out] = {bytes, 0};
+    }
+    if (node_out && rebound) *node_out = c->numa_node;
+    return SKGPU_OK;
+}
+extern "C" skgpu_rc skgpu_pinned_alloc(skgpu_ctx *c, size_t bytes, void **out) { return skgpu_pinned_alloc_ex(c, bytes, SKGPU_PIN_NUMA_LOCAL, out, nullptr); }
 extern "C" skgpu_rc skgpu_pinned_free(skgpu_ctx *c, void *p) {
     if (!c) return fail(SKGPU_ERR_INVALID, "null context");
-    if (p) CU(cudaFreeHost(p));
+    if (!p) return SKGPU_OK;
+    skgpu_ctx::PinnedBlock blk{0, 0};
+    {
+        std::lock_guard<std::mutex> lk(c->pinned_mu);
+        auto it = c->pinned.find(p);
+        if (it == c->pinned.end()) return fail(SKGPU_ERR_INVALID, "pointer was not allocated by skgpu_pinned_alloc on this context");
+        blk = it->second;
+        c->pinned.erase(it);
+    }
+    if (blk.kind == 1) { CU(cudaHostUnregister(p)); munmap(p, blk.bytes); }
+    else CU(cudaFreeHost(p));
     return SKGPU_OK;
 }
 
@@ -312,6 +427,12 @@ struct Op {
     ChainRec *d_rec = nullptr;    // chain: per-input records written by k_phase_chain every tick
     uint32_t chain_grid = 0;      // chain: persistent grid size (CTAs per SM x SMs)
     DynTable present;             // mix / chain: per-input presence
+    // sliced ticks (chain op)
+    std::vector<skgpu_slice> slices;
+    std::vector<uint32_t> last_reader;   // per slice i: the last slice whose kernels read bytes of upload piece i
+    OpHeader *d_hdr_sl = nullptr, *h_hdr_sl = nullptr;   // one launch header per slice
+    uint32_t hdr_sl_cap = 0;
+    bool slices_dirty = false;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev[2];
     uint32_t ev_used[2] = {0, 0};
 };
@@ -335,6 +456,11 @@ struct skgpu_plan {
     cudaEvent_t ev_tick_done[2] = {nullptr, nullptr};              // completion of tick k (everything incl. read-back), by k & 1
     bool d2h_pending = false;
     bool timing_valid = false;
+    // sliced ticks: events per (tick parity, slice); *_n = slices of the tick submitted with that parity
+    std::vector<cudaEvent_t> ev_up[2], ev_k[2], ev_done[2];
+    cudaEvent_t ev_t0[2] = {nullptr, nullptr}, ev_tables = nullptr, ev_k_all = nullptr;
+    uint32_t sl_n[2] = {0, 0};
+    bool sliced_pending = false;   // the previous submit was sliced (its kernels ran on stream_k)
 };
 
 static skgpu_rc dyn_alloc(DynTable &t, size_t bytes) {
@@ -394,7 +520,8 @@ extern "C" skgpu_rc skgpu_plan_create(skgpu_ctx *c, size_t arena_bytes, skgpu_pl
 }
 
 static void op_free(Op &op) {
-    cudaFree(op.d_tab); cudaFree(op.d_tab2); cudaFree(op.d_hdr); cudaFree(op.d_rec);
+    cudaFree(op.d_tab); cudaFree(op.d_tab2); cudaFree(op.d_hdr); cudaFree(op.d_rec); cudaFree(op.d_hdr_sl);
+    if (op.h_hdr_sl) cudaFreeHost(op.h_hdr_sl);
     if (op.h_tab) cudaFreeHost(op.h_tab);
     if (op.h_tab2) cudaFreeHost(op.h_tab2);
     if (op.h_hdr) cudaFreeHost(op.h_hdr);
@@ -407,6 +534,8 @@ extern "C" void skgpu_plan_destroy(skgpu_plan *p) {
     if (!p) return;
     cudaSetDevice(p->ctx->device);
     cudaStreamSynchronize(p->ctx->stream);
+    cudaStreamSynchronize(p->ctx->stream_k);
+    cudaStreamSynchronize(p->ctx->stream_d2h);
     for (auto &op : p->ops) op_free(op);
     dyn_free(p->gains);
     if (p->graph_exec) cudaGraphExecDestroy(p->graph_exec);
@@ -416,6 +545,14 @@ extern "C" void skgpu_plan_destroy(skgpu_plan *p) {
     cudaEventDestroy(p->ev_kernels_done); cudaEventDestroy(p->ev_d2h_done);
     cudaEventDestroy(p->ev_tick_done[0]); cudaEventDestroy(p->ev_tick_done[1]);
     cudaEventDestroy(p->e0); cudaEventDestroy(p->e1); cudaEventDestroy(p->e2); cudaEventDestroy(p->e3);
+    for (int a = 0; a < 2; ++a) {
+        for (auto e : p->ev_up[a]) cudaEventDestroy(e);
+        for (auto e : p->ev_k[a]) cudaEventDestroy(e);
+        for (auto e : p->ev_done[a]) cudaEventDestroy(e);
+        if (p->ev_t0[a]) cudaEventDestroy(p->ev_t0[a]);
+    }
+    if (p->ev_tables) cudaEventDestroy(p->ev_tables);
+    if (p->ev_k_all) cudaEventDestroy(p->ev_k_all);
     delete p;
 }
 
@@ -1005,7 +1142,104 @@ extern "C" skgpu_rc skgpu_plan_update_chain(skgpu_plan *p, uint32_t opi, const s
     op.n = ng;
     op.n2 = ni;
     op.dirty = true;
+    op.slices.clear();   // the cut points referred to the old tables: set them again (skgpu_plan_set_slices / _auto_slices)
     return SKGPU_OK;
+}
+
+// ---- slices
+
+extern "C" skgpu_rc skgpu_plan_set_slices(skgpu_plan *p, uint32_t opi, const skgpu_slice *sl, uint32_t n) {
+    if (!p || opi >= p->ops.size() || p->ops[opi].kind != OP_CHAIN) return fail(SKGPU_ERR_INVALID, "not a chain op");
+    if (p->ops.size() != 1) return fail(SKGPU_ERR_INVALID, "sliced ticks need a plan whose only op is the chain op");
+    Op &op = p->ops[opi];
+    if (n == 0) { op.slices.clear(); return SKGPU_OK; }
+    if (!sl || n > 4096) return fail(SKGPU_ERR_INVALID, "invalid slice table");
+    const skgpu_ctx *c = p->ctx;
+    const skgpu_chain_group *g = (const skgpu_chain_group *)op.h_tab;
+    const skgpu_chain_input *in = (const skgpu_chain_input *)op.h_tab2;
+    std::vector<uint32_t> last_reader(n);
+    uint32_t g0 = 0, i0 = 0;
+    uint64_t up0 = 0;
+    for (uint32_t k = 0; k < n; ++k) {
+        if (sl[k].group_end < g0 || sl[k].group_end > op.n || sl[k].input_end < i0 || sl[k].input_end > op.n2) return fail(SKGPU_ERR_INVALID, "slice %u: table ranges must be consecutive and inside the tables", k);
+        if (sl[k].h2d_end < up0 || sl[k].h2d_end > p->h2d_bytes) return fail(SKGPU_ERR_INVALID, "slice %u: h2d_end must be non-decreasing and inside the H2D range", k);
+        for (int r = 0; r < 2; ++r)
+            if (sl[k].d2h_off[r] > p->d2h_bytes || sl[k].d2h_bytes[r] > p->d2h_bytes - sl[k].d2h_off[r]) return fail(SKGPU_ERR_INVALID, "slice %u: read-back range outside the D2H range", k);
+        for (uint32_t q = g0; q < sl[k].group_end; ++q)
+            if (g[q].first_input < i0 || (uint64_t)g[q].first_input + g[q].n_inputs > sl[k].input_end) return fail(SKGPU_ERR_INVALID, "slice %u: group %u owns inputs outside the slice", k, q);
+        last_reader[k] = k;
+        g0 = sl[k].group_end; i0 = sl[k].input_end; up0 = sl[k].h2d_end;
+    }
+    if (g0 != op.n || i0 != op.n2) return fail(SKGPU_ERR_INVALID, "slices do not cover the tables (%u of %u groups, %u of %u inputs)", g0, op.n, i0, op.n2);
+    if (sl[n - 1].h2d_end != p->h2d_bytes) return fail(SKGPU_ERR_INVALID, "the last slice must end the H2D range");
+    // every input must be uploaded by its own slice's h2d_end; remember which slice reads each upload piece last (the next
+    // tick's upload into the other bank overwrites what THIS tick's kernels read as the previous chunk)
+    i0 = 0;
+    for (uint32_t k = 0; k < n; ++k) {
+        for (uint32_t q = i0; q < sl[k].input_end; ++q) {
+            if (in[q].in_off < p->h2d_off) return fail(SKGPU_ERR_INVALID, "input %u lies below the H2D range", q);
+            const uint64_t b0 = in[q].in_off - p->h2d_off;
+            const uint64_t b1 = b0 + (uint64_t)c->h_chunk[in[q].slot] * c->h_ch[in[q].slot] * 4u;
+            if (b1 > sl[k].h2d_end) return fail(SKGPU_ERR_INVALID, "slice %u: input %u ends at byte %llu of the H2D range, beyond the slice's h2d_end %llu (sort the tables by input offset)", k, q, (unsigned long long)b1, (unsigned long long)sl[k].h2d_end);
+            for (uint32_t u = 0; u <= k; ++u) {   // upload pieces [h2d_end[u-1], h2d_end[u]) the input overlaps
+                const uint64_t lo = u ? sl[u - 1].h2d_end : 0, hi = sl[u].h2d_end;
+                if (b0 < hi && b1 > lo) last_reader[u] = std::max(last_reader[u], k);
+                if (hi >= b1) break;
+            }
+        }
+        i0 = sl[k].input_end;
+    }
+    CU(cudaSetDevice(p->ctx->device));
+    if (n > op.hdr_sl_cap) {
+        CU(cudaStreamSynchronize(p->ctx->stream));
+        CU(cudaStreamSynchronize(p->ctx->stream_k));
+        if (op.d_hdr_sl) cudaFree(op.d_hdr_sl);
+        if (op.h_hdr_sl) cudaFreeHost(op.h_hdr_sl);
+        op.hdr_sl_cap = std::max(n, 64u);
+        CU(cudaMalloc((void **)&op.d_hdr_sl, op.hdr_sl_cap * sizeof(OpHeader)));
+        CU(cudaHostAlloc((void **)&op.h_hdr_sl, op.hdr_sl_cap * sizeof(OpHeader), cudaHostAllocDefault));
+    }
+    op.slices.assign(sl, sl + n);
+    op.last_reader = last_reader;
+    op.slices_dirty = true;
+    return SKGPU_OK;
+}
+
+extern "C" skgpu_rc skgpu_plan_auto_slices(skgpu_plan *p, uint32_t opi, uint32_t n) {
+    if (!p || opi >= p->ops.size() || p->ops[opi].kind != OP_CHAIN) return fail(SKGPU_ERR_INVALID, "not a chain op");
+    Op &op = p->ops[opi];
+    if (n == 0 || op.n == 0) return skgpu_plan_set_slices(p, opi, nullptr, 0);
+    n = std::min(n, op.n);
+    const skgpu_ctx *c = p->ctx;
+    const skgpu_chain_group *g = (const skgpu_chain_group *)op.h_tab;
+    const skgpu_chain_input *in = (const skgpu_chain_input *)op.h_tab2;
+    const uint64_t out_bytes = (uint64_t)op.chain_F * (uint32_t)op.chain_oc;
+    std::vector<skgpu_slice> sl(n);
+    uint32_t g0 = 0, i0 = 0;
+    uint64_t up = 0;
+    for (uint32_t k = 0; k < n; ++k) {
+        const uint32_t g1 = (uint32_t)((uint64_t)op.n * (k + 1) / n);
+        uint32_t i1 = i0;
+        uint64_t lo = ~0ull, hi = 0;
+        for (uint32_t q = g0; q < g1; ++q) {
+            i1 = std::max(i1, g[q].first_input + g[q].n_inputs);
+            const uint64_t ob = out_bytes * ((g[q].flags & SKGPU_MIX_OUT_S16) ? 2u : 4u);
+            lo = std::min(lo, g[q].out_off); hi = std::max(hi, g[q].out_off + ob);
+        }
+        for (uint32_t q = i0; q < i1; ++q) {
+            if (in[q].in_off < p->h2d_off) return fail(SKGPU_ERR_INVALID, "input %u lies below the H2D range", q);
+            up = std::max(up, in[q].in_off - p->h2d_off + (uint64_t)c->h_chunk[in[q].slot] * c->h_ch[in[q].slot] * 4u);
+        }
+        if (k + 1 == n) up = p->h2d_bytes;
+        sl[k].group_end = g1; sl[k].input_end = i1; sl[k].h2d_end = std::min<uint64_t>(up, p->h2d_bytes);
+        // read-back: the slice's result rows, then its output rows (skipped when they lie outside the D2H range)
+        sl[k].d2h_off[0] = sl[k].d2h_bytes[0] = sl[k].d2h_off[1] = sl[k].d2h_bytes[1] = 0;
+        const uint64_t r0 = op.results_off + (uint64_t)i0 * sizeof(skgpu_chain_result), r1 = op.results_off + (uint64_t)i1 * sizeof(skgpu_chain_result);
+        if (r0 >= p->d2h_off && r1 <= p->d2h_off + p->d2h_bytes && r1 > r0) { sl[k].d2h_off[0] = r0 - p->d2h_off; sl[k].d2h_bytes[0] = r1 - r0; }
+        if (lo != ~0ull && lo >= p->d2h_off && hi <= p->d2h_off + p->d2h_bytes) { sl[k].d2h_off[1] = lo - p->d2h_off; sl[k].d2h_bytes[1] = hi - lo; }
+        g0 = g1; i0 = i1;
+    }
+    return skgpu_plan_set_slices(p, opi, sl.data(), n);
 }
 
 // ---- launch
@@ -1053,6 +1287,25 @@ static chain_kernel_t chain_kernel(int oc, int iters) {
     return iters == 1 ? k_chain<1, 1> : iters == 2 ? k_chain<1, 2> : k_chain<1, 3>;
 }
 
+// the two kernels of the chain op over the table range a launch header describes (the whole tables, or one slice)
+static skgpu_rc launch_chain(skgpu_plan *p, Op &op, const OpHeader *d_hdr, uint32_t n_groups, uint32_t n_inputs, cudaStream_t s, bool time_ops) {
+    skgpu_ctx *c = p->ctx;
+    const float *gains = (const float *)p->gains.dev;
+    const uint8_t *present = op.present.valid ? (const uint8_t *)op.present.dev : nullptr;
+    const skgpu_chain_input *cin = (const skgpu_chain_input *)op.d_tab2;
+    if (time_ops) { skgpu_rc rc = op_event(op, 0, false, s); if (rc) return rc; }
+    k_phase_chain<<<(std::max(n_inputs, 1u) + PHASE_CHAIN_THREADS - 1) / PHASE_CHAIN_THREADS, PHASE_CHAIN_THREADS, 0, s>>>(
+        d_hdr, cin, present, gains, c->st, p->arena, p->d_tick, p->bank_stride, op.chain_F, op.results_off, op.chain_dm, op.d_rec);
+    CU(cudaGetLastError());
+    if (time_ops) { skgpu_rc rc = op_event(op, 0, true, s); if (rc) return rc; rc = op_event(op, 1, false, s); if (rc) return rc; }
+    const uint32_t grid = std::max(1u, std::min<uint32_t>(n_groups, op.chain_grid));
+    auto kfn = chain_kernel(op.chain_oc, op.chain_iters);
+    kfn<<<grid, CH_THREADS, op.smem_bytes, s>>>(d_hdr, (const skgpu_chain_group *)op.d_tab, op.d_rec, gains, c->st, p->arena, op.chain_F, op.chain_dm);
+    CU(cudaGetLastError());
+    if (time_ops) { skgpu_rc rc = op_event(op, 1, true, s); if (rc) return rc; }
+    return SKGPU_OK;
+}
+
 static skgpu_rc launch_ops(skgpu_plan *p, bool time_ops) {
     skgpu_ctx *c = p->ctx;
     cudaStream_t s = c->stream;
@@ -1083,20 +1336,8 @@ static skgpu_rc launch_ops(skgpu_plan *p, bool time_ops) {
             CU(cudaGetLastError());
             if (time_ops) { skgpu_rc rc = op_event(op, 1, true, s); if (rc) return rc; }
         } else if (op.kind == OP_CHAIN) {
-            const uint8_t *present = op.present.valid ? (const uint8_t *)op.present.dev : nullptr;
-            const skgpu_chain_input *cin = (const skgpu_chain_input *)op.d_tab2;
-            if (time_ops) { skgpu_rc rc = op_event(op, 0, false, s); if (rc) return rc; }
-            k_phase_chain<<<(op.cap2 + PHASE_CHAIN_THREADS - 1) / PHASE_CHAIN_THREADS, PHASE_CHAIN_THREADS, 0, s>>>(
-                op.d_hdr, cin, present, gains, c->st, p->arena, p->d_tick, p->bank_stride, op.chain_F, op.results_off, op.chain_dm, op.d_rec);
-            CU(cudaGetLastError());
-            if (time_ops) { skgpu_rc rc = op_event(op, 0, true, s); if (rc) return rc; rc = op_event(op, 1, false, s); if (rc) return rc; }
-            {
-                const uint32_t grid = std::min<uint32_t>(op.cap, op.chain_grid);
-                auto kfn = chain_kernel(op.chain_oc, op.chain_iters);
-                kfn<<<grid, CH_THREADS, op.smem_bytes, s>>>(op.d_hdr, (const skgpu_chain_group *)op.d_tab, op.d_rec, gains, c->st, p->arena, op.chain_F, op.chain_dm);
-            }
-            CU(cudaGetLastError());
-            if (time_ops) { skgpu_rc rc = op_event(op, 1, true, s); if (rc) return rc; }
+            skgpu_rc rc = launch_chain(p, op, op.d_hdr, op.cap, op.cap2, s, time_ops);
+            if (rc) return rc;
         } else {
             const uint8_t *present = op.present.valid ? (const uint8_t *)op.present.dev : nullptr;
             if (time_ops) { skgpu_rc rc = op_event(op, 0, false, s); if (rc) return rc; }
@@ -1169,6 +1410,104 @@ extern "C" skgpu_rc skgpu_plan_finalize(skgpu_plan *p) {
     return SKGPU_OK;
 }
 
+// One tick, slice by slice, on three streams: uploads on the context stream, kernels on stream_k, read-backs on stream_d2h.
+//   upload(i)  waits for the previous tick's kernels that read the same bytes of the OTHER bank as "previous chunk"
+//   kernels(i) wait for upload(i) and for the previous tick's read-back of the rows they overwrite
+//   read-back(i) waits for kernels(i)
+// so slice i's results are in host memory while slice i + 1 .. n still upload (SURVEY 8d latency: upload-done -> read-back-done).
+static skgpu_rc submit_sliced(skgpu_plan *p, const void *host_in, void *host_out, bool do_h2d, bool do_d2h) {
+    skgpu_ctx *c = p->ctx;
+    cudaStream_t s = c->stream, sk = c->stream_k, sd = c->stream_d2h;
+    if (p->ops.size() != 1 || p->ops[0].kind != OP_CHAIN) return fail(SKGPU_ERR_STATE, "sliced ticks need a plan whose only op is the chain op");
+    Op &op = p->ops[0];
+    if (op.slices.empty()) return fail(SKGPU_ERR_STATE, "no slices set (skgpu_plan_set_slices / skgpu_plan_auto_slices; table updates clear them)");
+    const uint32_t n = (uint32_t)op.slices.size();
+    if (!p->ev_tables) {
+        CU(cudaEventCreateWithFlags(&p->ev_tables, cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&p->ev_k_all, cudaEventDisableTiming));
+        CU(cudaEventCreate(&p->ev_t0[0]));
+        CU(cudaEventCreate(&p->ev_t0[1]));
+    }
+    const uint32_t par = (uint32_t)((p->tick + 1) & 1ull), opar = par ^ 1u;   // parity of THIS tick's number / of the previous tick
+    for (int a = 0; a < 2; ++a)
+        while (p->ev_up[a].size() < n) {
+            cudaEvent_t e1, e2, e3;
+            CU(cudaEventCreate(&e1)); CU(cudaEventCreate(&e2)); CU(cudaEventCreate(&e3));
+            p->ev_up[a].push_back(e1); p->ev_k[a].push_back(e2); p->ev_done[a].push_back(e3);
+        }
+    if (op.slices_dirty) {
+        uint32_t g0 = 0, i0 = 0;
+        // the staging buffer may still be read by an earlier upload: slices change only with the tables (rare), so just wait
+        CU(cudaStreamSynchronize(s));
+        for (uint32_t k = 0; k < n; ++k) {
+            op.h_hdr_sl[k].count = op.slices[k].group_end - g0;
+            op.h_hdr_sl[k].count2 = op.slices[k].input_end - i0;
+            op.h_hdr_sl[k].first = g0;
+            op.h_hdr_sl[k].first2 = i0;
+            g0 = op.slices[k].group_end; i0 = op.slices[k].input_end;
+        }
+        CU(cudaMemcpyAsync(op.d_hdr_sl, op.h_hdr_sl, n * sizeof(OpHeader), cudaMemcpyHostToDevice, s));
+        op.slices_dirty = false;
+    }
+    const bool prev_sliced = p->sliced_pending && p->sl_n[opar] > 0;
+    CU(cudaEventRecord(p->ev_tables, s));             // tables, gains, presence (and any unsliced tick before) are on s
+    CU(cudaStreamWaitEvent(sk, p->ev_tables, 0));
+    CU(cudaEventRecord(p->ev_t0[par], s));
+    uint8_t *bank = p->arena + p->h2d_off + (p->tick & 1ull) * p->bank_stride;
+    uint64_t up0 = 0;
+    uint32_t g0 = 0, i0 = 0;
+    for (uint32_t k = 0; k < n; ++k) {
+        const skgpu_slice &sl = op.slices[k];
+        if (do_h2d && sl.h2d_end > up0) {
+            if (prev_sliced) CU(cudaStreamWaitEvent(s, p->ev_k[opar][std::min(op.last_reader[k], p->sl_n[opar] - 1u)], 0));
+            CU(cudaMemcpyAsync(bank + up0, (const uint8_t *)host_in + up0, sl.h2d_end - up0, cudaMemcpyHostToDevice, s));
+        }
+        up0 = std::max(up0, sl.h2d_end);
+        CU(cudaEventRecord(p->ev_up[par][k], s));
+        CU(cudaStreamWaitEvent(sk, p->ev_up[par][k], 0));
+        if (prev_sliced && do_d2h && k < p->sl_n[opar]) CU(cudaStreamWaitEvent(sk, p->ev_done[opar][k], 0));
+        else if (p->d2h_pending && k == 0) CU(cudaStreamWaitEvent(sk, p->ev_d2h_done, 0));
+        skgpu_rc rc = launch_chain(p, op, op.d_hdr_sl + k, sl.group_end - g0, sl.input_end - i0, sk, false);
+        if (rc) return rc;
+        if (k + 1 == n) {   // bank parity of the next tick, after the last slice's kernels
+            k_tick_advance<<<1, 1, 0, sk>>>(p->d_tick);
+            CU(cudaGetLastError());
+        }
+        CU(cudaEventRecord(p->ev_k[par][k], sk));
+        CU(cudaStreamWaitEvent(sd, p->ev_k[par][k], 0));
+        if (do_d2h)
+            for (int r = 0; r < 2; ++r)
+                if (sl.d2h_bytes[r]) CU(cudaMemcpyAsync((uint8_t *)host_out + sl.d2h_off[r], p->arena + p->d2h_off + sl.d2h_off[r], sl.d2h_bytes[r], cudaMemcpyDeviceToHost, sd));
+        CU(cudaEventRecord(p->ev_done[par][k], sd));
+        g0 = sl.group_end; i0 = sl.input_end;
+    }
+    p->tick++;
+    CU(cudaEventRecord(p->ev_k_all, sk));
+    CU(cudaEventRecord(p->ev_d2h_done, sd));
+    CU(cudaEventRecord(p->ev_tick_done[p->tick & 1ull], sd));
+    p->sl_n[par] = n;
+    p->sliced_pending = true;
+    p->d2h_pending = do_d2h;
+    p->timing_valid = false;
+    return SKGPU_OK;
+}
+
+extern "C" skgpu_rc skgpu_tick_slice_timing(skgpu_plan *p, uint64_t tick, skgpu_slice_timing *out, uint32_t cap, uint32_t *n_out) {
+    if (!p || !n_out) return fail(SKGPU_ERR_INVALID, "null argument");
+    if (tick == 0 || tick > p->tick || tick + 1 < p->tick) return fail(SKGPU_ERR_INVALID, "tick %llu is not one of the two most recent ticks", (unsigned long long)tick);
+    const uint32_t par = (uint32_t)(tick & 1ull), n = p->sl_n[par];
+    if (n == 0) return fail(SKGPU_ERR_STATE, "tick %llu was not a sliced tick", (unsigned long long)tick);
+    CU(cudaSetDevice(p->ctx->device));
+    CU(cudaEventSynchronize(p->ev_done[par][n - 1]));
+    *n_out = n;
+    for (uint32_t k = 0; k < n && k < cap; ++k) {
+        CU(cudaEventElapsedTime(&out[k].upload_done_ms, p->ev_t0[par], p->ev_up[par][k]));
+        CU(cudaEventElapsedTime(&out[k].kernels_ms, p->ev_up[par][k], p->ev_k[par][k]));
+        CU(cudaEventElapsedTime(&out[k].latency_ms, p->ev_up[par][k], p->ev_done[par][k]));
+    }
+    return SKGPU_OK;
+}
+
 extern "C" skgpu_rc skgpu_tick_submit(skgpu_plan *p, const void *host_in, void *host_out, uint32_t flags) {
     if (!p) return fail(SKGPU_ERR_INVALID, "null plan");
     if (!p->finalized) return fail(SKGPU_ERR_STATE, "plan not finalized");
@@ -1183,6 +1522,11 @@ extern "C" skgpu_rc skgpu_tick_submit(skgpu_plan *p, const void *host_in, void *
     if (rc) return rc;
     rc = upload_dirty(p);
     if (rc) return rc;
+    if (flags & SKGPU_SUBMIT_SLICED) return submit_sliced(p, host_in, host_out, do_h2d, do_d2h);
+    if (p->sliced_pending) {   // the previous tick's kernels ran on the kernel stream: this tick's upload / kernels follow them
+        CU(cudaStreamWaitEvent(s, p->ev_k_all, 0));
+        p->sliced_pending = false;
+    }
     const bool overlap = (flags & SKGPU_SUBMIT_OVERLAP_D2H) != 0 && do_d2h;
     CU(cudaEventRecord(p->e0, s));
     if (do_h2d) CU(cudaMemcpyAsync(p->arena + p->h2d_off + (p->tick & 1ull) * p->bank_stride, host_in, p->h2d_bytes, cudaMemcpyHostToDevice, s));
@@ -1227,8 +1571,10 @@ extern "C" skgpu_rc skgpu_tick_wait(skgpu_plan *p, skgpu_tick_timing *t) {
     if (!p) return fail(SKGPU_ERR_INVALID, "null plan");
     CU(cudaSetDevice(p->ctx->device));
     CU(cudaStreamSynchronize(p->ctx->stream));
+    CU(cudaStreamSynchronize(p->ctx->stream_k));
     CU(cudaStreamSynchronize(p->ctx->stream_d2h));
     p->d2h_pending = false;
+    p->sliced_pending = false;
     if (t) {
         memset(t, 0, sizeof(*t));
         if (p->timing_valid) {
@@ -1318,6 +1664,7 @@ extern "C" skgpu_rc skgpu_ctx_sync(skgpu_ctx *c) {
     if (!c) return fail(SKGPU_ERR_INVALID, "null context");
     CU(cudaSetDevice(c->device));
     CU(cudaStreamSynchronize(c->stream));
+    CU(cudaStreamSynchronize(c->stream_k));
     CU(cudaStreamSynchronize(c->stream_d2h));
     return SKGPU_OK;
 }

@@ -19,7 +19,8 @@ CVT_F32_TO_F32, CVT_F32_TO_S16, CVT_S16_TO_F32 = 0, 1, 2
 RS_TO_FIFO = 1
 MIX_IN_UNIQUE, MIX_IN_FIFO = 1, 2
 MIX_OUT_S16 = 1
-SUBMIT_NO_H2D, SUBMIT_NO_D2H, SUBMIT_GRAPH, SUBMIT_TIME_OPS, SUBMIT_OVERLAP_D2H = 1, 2, 4, 8, 16
+SUBMIT_NO_H2D, SUBMIT_NO_D2H, SUBMIT_GRAPH, SUBMIT_TIME_OPS, SUBMIT_OVERLAP_D2H, SUBMIT_SLICED = 1, 2, 4, 8, 16, 32
+PIN_NUMA_LOCAL, PIN_WRITE_COMBINED = 1, 2
 
 
 class CtxConfig(C.Structure):
@@ -29,6 +30,10 @@ class CtxConfig(C.Structure):
 class StreamCfg(C.Structure):
     _fields_ = [("in_rate", C.c_uint32), ("out_rate", C.c_uint32), ("chunk_frames", C.c_uint32), ("channels", C.c_uint16),
                 ("reserved", C.c_uint16)]
+
+
+class SliceTiming(C.Structure):
+    _fields_ = [("upload_done_ms", C.c_float), ("kernels_ms", C.c_float), ("latency_ms", C.c_float)]
 
 
 class TickTiming(C.Structure):
@@ -48,6 +53,8 @@ CHAIN_INPUT_DT = np.dtype([("in_off", "<u8"), ("slot", "<u4"), ("gain_idx", "<u4
 CHAIN_GROUP_DT = np.dtype([("out_off", "<u8"), ("first_input", "<u4"), ("n_inputs", "<u4"), ("gain_idx", "<u4"),
                            ("out_channels", "<u2"), ("flags", "<u2")], align=True)
 CHAIN_RESULT_DT = np.dtype([("emitted", "<u4"), ("status", "<u4")], align=True)
+SLICE_DT = np.dtype([("group_end", "<u4"), ("input_end", "<u4"), ("h2d_end", "<u8"), ("d2h_off", "<u8", (2,)), ("d2h_bytes", "<u8", (2,))], align=True)
+assert SLICE_DT.itemsize == 48
 assert CHAIN_INPUT_DT.itemsize == 24 and CHAIN_GROUP_DT.itemsize == 24
 assert SEG_DT.itemsize == 24 and RS_ITEM_DT.itemsize == 32 and MIX_INPUT_DT.itemsize == 24 and MIX_GROUP_DT.itemsize == 32
 
@@ -63,6 +70,8 @@ EXPORTS = [
     "skgpu_plan_op_time", "skgpu_plan_reset_op_times", "skgpu_plan_launches_per_tick", "skgpu_arena_upload",
     "skgpu_arena_download", "skgpu_arena_fill", "skgpu_timer_start", "skgpu_timer_stop", "skgpu_timer_elapsed_ms",
     "skgpu_ctx_sync", "skgpu_ctx_flush_l2",
+    "skgpu_pinned_alloc_ex", "skgpu_ctx_numa_node", "skgpu_ctx_bind_thread", "skgpu_plan_set_slices", "skgpu_plan_auto_slices",
+    "skgpu_tick_slice_timing",
 ]
 
 _lib = None
@@ -123,6 +132,12 @@ def load() -> C.CDLL:
         "skgpu_timer_elapsed_ms": (i32, [vp, C.POINTER(C.c_float)]),
         "skgpu_ctx_sync": (i32, [vp]),
         "skgpu_ctx_flush_l2": (i32, [vp]),
+        "skgpu_pinned_alloc_ex": (i32, [vp, C.c_size_t, u32, C.POINTER(vp), C.POINTER(i32)]),
+        "skgpu_ctx_numa_node": (i32, [vp]),
+        "skgpu_ctx_bind_thread": (i32, [vp]),
+        "skgpu_plan_set_slices": (i32, [vp, u32, vp, u32]),
+        "skgpu_plan_auto_slices": (i32, [vp, u32, u32]),
+        "skgpu_tick_slice_timing": (i32, [vp, u64, C.POINTER(SliceTiming), u32, C.POINTER(u32)]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)
@@ -171,9 +186,17 @@ class Context:
         _chk(self.lib.skgpu_ctx_device_info(self.h, name, 128, C.byref(sm), C.byref(ma), C.byref(mi)))
         return name.value.decode(), sm.value, ma.value, mi.value
 
-    def pinned(self, nbytes: int, dtype=np.uint8) -> np.ndarray:
+    def numa_node(self) -> int:
+        return self.lib.skgpu_ctx_numa_node(self.h)
+
+    def bind_thread(self):
+        _chk(self.lib.skgpu_ctx_bind_thread(self.h))
+
+    def pinned(self, nbytes: int, dtype=np.uint8, flags: int = PIN_NUMA_LOCAL) -> np.ndarray:
         p = C.c_void_p()
-        _chk(self.lib.skgpu_pinned_alloc(self.h, nbytes, C.byref(p)))
+        node = C.c_int32()
+        _chk(self.lib.skgpu_pinned_alloc_ex(self.h, nbytes, flags, C.byref(p), C.byref(node)))
+        self.last_pinned_node = node.value
         buf = (C.c_uint8 * max(nbytes, 1)).from_address(p.value)
         arr = np.frombuffer(buf, dtype=np.uint8, count=nbytes)
         self._pinned.append((p, arr))
@@ -278,6 +301,23 @@ class Plan:
         groups = np.ascontiguousarray(groups, dtype=CHAIN_GROUP_DT)
         inputs = np.ascontiguousarray(inputs, dtype=CHAIN_INPUT_DT)
         _chk(self.lib.skgpu_plan_update_chain(self.h, op, _ptr(groups), groups.size, _ptr(inputs), inputs.size))
+
+    def set_slices(self, op: int, slices: np.ndarray):
+        sl = np.ascontiguousarray(slices, dtype=SLICE_DT)
+        _chk(self.lib.skgpu_plan_set_slices(self.h, op, _ptr(sl), sl.size))
+
+    def auto_slices(self, op: int, n: int):
+        _chk(self.lib.skgpu_plan_auto_slices(self.h, op, n))
+
+    def slice_timing(self, tick: int):
+        """[(upload_done_ms, kernels_ms, latency_ms)] of a finished sliced tick (one of the two most recent)"""
+        buf = (SliceTiming * 4096)()
+        n = C.c_uint32()
+        _chk(self.lib.skgpu_tick_slice_timing(self.h, tick, buf, 4096, C.byref(n)))
+        return [(buf[i].upload_done_ms, buf[i].kernels_ms, buf[i].latency_ms) for i in range(n.value)]
+
+    def wait_for(self, tick: int):
+        _chk(self.lib.skgpu_tick_wait_for(self.h, tick))
 
     def set_banks(self, bank_stride: int):
         _chk(self.lib.skgpu_plan_set_banks(self.h, bank_stride))

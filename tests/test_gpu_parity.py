@@ -620,3 +620,94 @@ def test_invalid_configs_are_rejected(ctx):
         plan.add_convert(L.CVT_F32_TO_F32, segs)
     assert "outside" in e.value.msg
     plan.destroy()
+
+
+# ------------------------------------------------------------------ sliced ticks
+
+@pytest.mark.parametrize("n_slices", [1, 3, 8, 64])
+def test_sliced_tick_equals_whole_tick(n_slices):
+    """SKGPU_SUBMIT_SLICED (upload / kernels / read-back of consecutive table slices overlapped on three streams) must give
+    the same bytes as the plain submit, tick after tick, also when sliced and plain ticks alternate and ticks are pipelined."""
+    S, K, T = 53, 2, 9
+    a = chain.ChainTick(S, K, seed=13)
+    b = chain.ChainTick(S, K, seed=13)
+    try:
+        b.plan.auto_slices(b.op_chain, n_slices)
+        for t in range(T):
+            x = synth.tone_streams(13, t, a.n_streams, a.chunk, 2, 44100)
+            want = a.tick(x)
+            sliced = (t % 4) != 3
+            got = b.tick(x, L.SUBMIT_SLICED if sliced else L.SUBMIT_GRAPH)
+            assert np.array_equal(got, want), f"tick {t}"
+            if sliced:
+                tm = b.plan.slice_timing(b.plan.tick_count())
+                assert len(tm) == min(n_slices, S) and all(lat >= ker >= 0 for _, ker, lat in tm)
+        res = b.results()
+        assert np.all(res["status"] == 0) and np.all(res["emitted"] == 1)
+    finally:
+        a.close()
+        b.close()
+
+
+def test_sliced_ticks_pipelined_two_in_flight():
+    """two sliced ticks in flight (submit n + 1 before collecting n, two host output buffers): the cross-tick ordering --
+    uploads into the other bank wait for the kernels that still read it, kernels wait for the read-back of the rows they
+    overwrite -- keeps every tick's bytes equal to the one-at-a-time run"""
+    S, K, T = 300, 2, 10
+    a = chain.ChainTick(S, K, seed=21)
+    b = chain.ChainTick(S, K, seed=21)
+    try:
+        b.plan.auto_slices(b.op_chain, 7)
+        xs = [synth.tone_streams(21, t, a.n_streams, a.chunk, 2, 44100) for t in range(T)]
+        want = [a.tick(x) for x in xs]
+        ins = [b.ctx.pinned(b.in_bytes, np.float32) for _ in range(2)]
+        outs = [b.ctx.pinned(b.out_bytes, np.int16) for _ in range(2)]
+        got = []
+        for t in range(T):
+            ins[t & 1].reshape(b.n_streams, b.in_stride // 4)[:, : xs[t].shape[1]] = xs[t]
+            b.plan.submit(ins[t & 1], outs[t & 1], L.SUBMIT_SLICED)
+            if t >= 1:
+                b.plan.wait_for(t)                                  # tick number t = the previous submit
+                got.append(outs[(t - 1) & 1].reshape(S, -1).copy())
+        b.plan.wait()
+        got.append(outs[(T - 1) & 1].reshape(S, -1).copy())
+        for t in range(T):
+            assert np.array_equal(got[t], want[t]), f"tick {t}"
+    finally:
+        a.close()
+        b.close()
+
+
+def test_slices_are_validated():
+    ct = chain.ChainTick(8, 2, seed=1)
+    try:
+        sl = np.zeros(2, dtype=L.SLICE_DT)
+        sl["group_end"] = [4, 8]
+        sl["input_end"] = [8, 16]
+        sl["h2d_end"] = [ct.in_bytes // 2, ct.in_bytes]
+        ct.plan.set_slices(ct.op_chain, sl)
+        bad = sl.copy()
+        bad["h2d_end"][0] = 16                                       # slice 0's inputs are not uploaded by then
+        with pytest.raises(L.SkgpuError) as e:
+            ct.plan.set_slices(ct.op_chain, bad)
+        assert "beyond the slice's h2d_end" in e.value.msg
+        bad = sl.copy()
+        bad["group_end"][1] = 7
+        with pytest.raises(L.SkgpuError):
+            ct.plan.set_slices(ct.op_chain, bad)
+        ct.plan.set_slices(ct.op_chain, sl[:0])                      # clears
+        with pytest.raises(L.SkgpuError) as e:
+            ct.plan.submit(ct.host_in, ct.host_out, L.SUBMIT_SLICED)
+        assert "no slices set" in e.value.msg
+    finally:
+        ct.close()
+
+
+def test_pinned_alloc_placement_flags(ctx):
+    a = ctx.pinned(1 << 20, np.uint8)                               # NUMA-local (default): bound to the GPU's node when the box has nodes
+    assert ctx.last_pinned_node in (-1, ctx.numa_node())
+    b = ctx.pinned(1 << 20, np.uint8, flags=L.PIN_WRITE_COMBINED)
+    a[:] = 7
+    b[:] = 9
+    assert a[-1] == 7
+    ctx.bind_thread()                                               # no-op on a single-node box
