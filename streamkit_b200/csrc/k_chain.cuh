@@ -427,7 +427,7 @@ __global__ void __launch_bounds__(PHASE_CHAIN_THREADS, 14) k_phase_chain(const O
 }
 
 template <int OC, int ITERS>  // output channels (1 | 2); ITERS = ceil(F / 1024)
-__global__ void __launch_bounds__(CH_THREADS, 6) k_chain(const OpHeader *__restrict__ hdr, const skgpu_chain_group *__restrict__ groups,
+__global__ void __launch_bounds__(CH_THREADS, 5) k_chain(const OpHeader *__restrict__ hdr, const skgpu_chain_group *__restrict__ groups,
                                                          const ChainRec *__restrict__ recs, const float *__restrict__ gains, SlotTables st,
                                                          uint8_t *__restrict__ arena, uint32_t F, ChainDims dm) {
     extern __shared__ __align__(16) uint8_t smem_raw[];

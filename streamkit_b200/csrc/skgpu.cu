@@ -60,7 +60,8 @@ struct skgpu_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
     cudaStream_t stream_d2h = nullptr;   // result read-back runs here so it overlaps the next tick's upload (PCIe is full duplex)
-    cudaStream_t stream_k = nullptr;     // sliced ticks: kernels run here, uploads stay on `stream`
+    cudaStream_t stream_k = nullptr;     // sliced ticks: k_chain runs here, uploads stay on `stream`
+    cudaStream_t stream_p = nullptr;     // sliced ticks: k_phase_chain (data independent) runs here, ahead of / next to k_chain
     int numa_node = -1;                  // host NUMA node of the GPU's PCI function (-1: unknown / single node)
     std::vector<int> node_cpus;          // CPUs of that node
     struct PinnedBlock { size_t bytes; int kind; };   // kind 0: cudaHostAlloc, 1: mmap + cudaHostRegister
@@ -141,6 +142,7 @@ extern "C" skgpu_rc skgpu_ctx_create(int32_t device_ordinal, const skgpu_ctx_con
     CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     CU(cudaStreamCreateWithFlags(&c->stream_d2h, cudaStreamNonBlocking));
     CU(cudaStreamCreateWithFlags(&c->stream_k, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&c->stream_p, cudaStreamNonBlocking));
     detect_numa(c);
     CU(cudaEventCreate(&c->tm0));
     CU(cudaEventCreate(&c->tm1));
@@ -185,6 +187,7 @@ extern "C" void skgpu_ctx_destroy(skgpu_ctx *c) {
         else cudaFreeHost(kv.first);
     }
     cudaStreamDestroy(c->stream_k);
+    cudaStreamDestroy(c->stream_p);
     cudaStreamDestroy(c->stream_d2h);
     cudaStreamDestroy(c->stream);
     delete c;
@@ -458,7 +461,10 @@ struct skgpu_plan {
     bool timing_valid = false;
     // sliced ticks: events per (tick parity, slice); *_n = slices of the tick submitted with that parity
     std::vector<cudaEvent_t> ev_up[2], ev_k[2], ev_done[2];
-    cudaEvent_t ev_t0[2] = {nullptr, nullptr}, ev_tables = nullptr, ev_k_all = nullptr;
+    cudaEvent_t ev_t0[2] = {nullptr, nullptr}, ev_tables = nullptr, ev_k_all = nullptr, ev_fork = nullptr;
+    std::vector<cudaEvent_t> ev_p;   // phase(i) done
+    cudaGraph_t sl_graph = nullptr;           // kernels of a sliced tick without transfers
+    cudaGraphExec_t sl_graph_exec = nullptr;
     uint32_t sl_n[2] = {0, 0};
     bool sliced_pending = false;   // the previous submit was sliced (its kernels ran on stream_k)
 };
@@ -553,6 +559,10 @@ extern "C" void skgpu_plan_destroy(skgpu_plan *p) {
     }
     if (p->ev_tables) cudaEventDestroy(p->ev_tables);
     if (p->ev_k_all) cudaEventDestroy(p->ev_k_all);
+    if (p->ev_fork) cudaEventDestroy(p->ev_fork);
+    for (auto e : p->ev_p) cudaEventDestroy(e);
+    if (p->sl_graph_exec) cudaGraphExecDestroy(p->sl_graph_exec);
+    if (p->sl_graph) cudaGraphDestroy(p->sl_graph);
     delete p;
 }
 
@@ -1410,35 +1420,59 @@ extern "C" skgpu_rc skgpu_plan_finalize(skgpu_plan *p) {
     return SKGPU_OK;
 }
 
-// One tick, slice by slice, on three streams: uploads on the context stream, kernels on stream_k, read-backs on stream_d2h.
-//   upload(i)  waits for the previous tick's kernels that read the same bytes of the OTHER bank as "previous chunk"
-//   kernels(i) wait for upload(i) and for the previous tick's read-back of the rows they overwrite
-//   read-back(i) waits for kernels(i)
-// so slice i's results are in host memory while slice i + 1 .. n still upload (SURVEY 8d latency: upload-done -> read-back-done).
-static skgpu_rc submit_sliced(skgpu_plan *p, const void *host_in, void *host_out, bool do_h2d, bool do_d2h) {
+// the two kernels of the chain op, separately (sliced ticks run them on different streams)
+static skgpu_rc launch_chain_phase(skgpu_plan *p, Op &op, const OpHeader *d_hdr, uint32_t n_inputs, cudaStream_t s) {
     skgpu_ctx *c = p->ctx;
-    cudaStream_t s = c->stream, sk = c->stream_k, sd = c->stream_d2h;
-    if (p->ops.size() != 1 || p->ops[0].kind != OP_CHAIN) return fail(SKGPU_ERR_STATE, "sliced ticks need a plan whose only op is the chain op");
-    Op &op = p->ops[0];
-    if (op.slices.empty()) return fail(SKGPU_ERR_STATE, "no slices set (skgpu_plan_set_slices / skgpu_plan_auto_slices; table updates clear them)");
-    const uint32_t n = (uint32_t)op.slices.size();
+    const uint8_t *present = op.present.valid ? (const uint8_t *)op.present.dev : nullptr;
+    k_phase_chain<<<(std::max(n_inputs, 1u) + PHASE_CHAIN_THREADS - 1) / PHASE_CHAIN_THREADS, PHASE_CHAIN_THREADS, 0, s>>>(
+        d_hdr, (const skgpu_chain_input *)op.d_tab2, present, (const float *)p->gains.dev, c->st, p->arena, p->d_tick, p->bank_stride, op.chain_F,
+        op.results_off, op.chain_dm, op.d_rec);
+    CU(cudaGetLastError());
+    return SKGPU_OK;
+}
+static skgpu_rc launch_chain_main(skgpu_plan *p, Op &op, const OpHeader *d_hdr, uint32_t n_groups, cudaStream_t s) {
+    skgpu_ctx *c = p->ctx;
+    const uint32_t grid = std::max(1u, std::min<uint32_t>(n_groups, op.chain_grid));
+    auto kfn = chain_kernel(op.chain_oc, op.chain_iters);
+    kfn<<<grid, CH_THREADS, op.smem_bytes, s>>>(d_hdr, (const skgpu_chain_group *)op.d_tab, op.d_rec, (const float *)p->gains.dev, c->st, p->arena,
+                                                 op.chain_F, op.chain_dm);
+    CU(cudaGetLastError());
+    return SKGPU_OK;
+}
+
+// One tick, slice by slice, on four streams: uploads on the context stream, k_phase_chain on stream_p, k_chain on stream_k,
+// read-backs on stream_d2h.
+//   phase(i)   is data independent (stream state + presence only): all slices' phase kernels are issued at the start of the
+//              tick and run while the first slice still uploads; with inputs resident they overlap the previous slice's k_chain
+//   upload(i)  follows the previous tick's kernels (they read the other bank as "previous chunk", and the per-tick tables)
+//   chain(i)   waits for phase(i), upload(i) and the previous tick's read-back of the rows it overwrites
+//   read-back(i) waits for chain(i)
+// so slice i's results are in host memory while slice i + 1 .. n still upload (SURVEY 8d latency: upload-done -> read-back-done).
+static skgpu_rc sliced_prepare(skgpu_plan *p, Op &op, uint32_t n) {
+    skgpu_ctx *c = p->ctx;
     if (!p->ev_tables) {
         CU(cudaEventCreateWithFlags(&p->ev_tables, cudaEventDisableTiming));
         CU(cudaEventCreateWithFlags(&p->ev_k_all, cudaEventDisableTiming));
         CU(cudaEventCreate(&p->ev_t0[0]));
         CU(cudaEventCreate(&p->ev_t0[1]));
     }
-    const uint32_t par = (uint32_t)((p->tick + 1) & 1ull), opar = par ^ 1u;   // parity of THIS tick's number / of the previous tick
     for (int a = 0; a < 2; ++a)
         while (p->ev_up[a].size() < n) {
             cudaEvent_t e1, e2, e3;
             CU(cudaEventCreate(&e1)); CU(cudaEventCreate(&e2)); CU(cudaEventCreate(&e3));
             p->ev_up[a].push_back(e1); p->ev_k[a].push_back(e2); p->ev_done[a].push_back(e3);
         }
+    while (p->ev_p.size() < n) {
+        cudaEvent_t e;
+        CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        p->ev_p.push_back(e);
+    }
     if (op.slices_dirty) {
         uint32_t g0 = 0, i0 = 0;
         // the staging buffer may still be read by an earlier upload: slices change only with the tables (rare), so just wait
-        CU(cudaStreamSynchronize(s));
+        CU(cudaStreamSynchronize(c->stream));
+        CU(cudaStreamSynchronize(c->stream_p));
+        CU(cudaStreamSynchronize(c->stream_k));
         for (uint32_t k = 0; k < n; ++k) {
             op.h_hdr_sl[k].count = op.slices[k].group_end - g0;
             op.h_hdr_sl[k].count2 = op.slices[k].input_end - i0;
@@ -1446,28 +1480,117 @@ static skgpu_rc submit_sliced(skgpu_plan *p, const void *host_in, void *host_out
             op.h_hdr_sl[k].first2 = i0;
             g0 = op.slices[k].group_end; i0 = op.slices[k].input_end;
         }
-        CU(cudaMemcpyAsync(op.d_hdr_sl, op.h_hdr_sl, n * sizeof(OpHeader), cudaMemcpyHostToDevice, s));
+        CU(cudaMemcpyAsync(op.d_hdr_sl, op.h_hdr_sl, n * sizeof(OpHeader), cudaMemcpyHostToDevice, c->stream));
         op.slices_dirty = false;
+        if (p->sl_graph_exec) { cudaGraphExecDestroy(p->sl_graph_exec); p->sl_graph_exec = nullptr; }
+        if (p->sl_graph) { cudaGraphDestroy(p->sl_graph); p->sl_graph = nullptr; }
     }
-    const bool prev_sliced = p->sliced_pending && p->sl_n[opar] > 0;
-    CU(cudaEventRecord(p->ev_tables, s));             // tables, gains, presence (and any unsliced tick before) are on s
-    CU(cudaStreamWaitEvent(sk, p->ev_tables, 0));
-    CU(cudaEventRecord(p->ev_t0[par], s));
-    uint8_t *bank = p->arena + p->h2d_off + (p->tick & 1ull) * p->bank_stride;
-    uint64_t up0 = 0;
+    return SKGPU_OK;
+}
+
+// kernels of one sliced tick as a fork / join between stream_k and stream_p (used directly, and captured as a CUDA graph for
+// ticks without transfers): phase(i + 1) runs next to chain(i)
+static skgpu_rc sliced_kernels(skgpu_plan *p, Op &op, uint32_t n, cudaEvent_t fork) {
+    skgpu_ctx *c = p->ctx;
+    cudaStream_t sk = c->stream_k, sp = c->stream_p;
+    CU(cudaEventRecord(fork, sk));
+    CU(cudaStreamWaitEvent(sp, fork, 0));
     uint32_t g0 = 0, i0 = 0;
     for (uint32_t k = 0; k < n; ++k) {
         const skgpu_slice &sl = op.slices[k];
-        if (do_h2d && sl.h2d_end > up0) {
-            if (prev_sliced) CU(cudaStreamWaitEvent(s, p->ev_k[opar][std::min(op.last_reader[k], p->sl_n[opar] - 1u)], 0));
-            CU(cudaMemcpyAsync(bank + up0, (const uint8_t *)host_in + up0, sl.h2d_end - up0, cudaMemcpyHostToDevice, s));
+        skgpu_rc rc = launch_chain_phase(p, op, op.d_hdr_sl + k, sl.input_end - i0, sp);
+        if (rc) return rc;
+        CU(cudaEventRecord(p->ev_p[k], sp));
+        CU(cudaStreamWaitEvent(sk, p->ev_p[k], 0));
+        rc = launch_chain_main(p, op, op.d_hdr_sl + k, sl.group_end - g0, sk);
+        if (rc) return rc;
+        g0 = sl.group_end; i0 = sl.input_end;
+    }
+    k_tick_advance<<<1, 1, 0, sk>>>(p->d_tick);
+    CU(cudaGetLastError());
+    return SKGPU_OK;
+}
+
+static skgpu_rc submit_sliced(skgpu_plan *p, const void *host_in, void *host_out, bool do_h2d, bool do_d2h, uint32_t flags) {
+    skgpu_ctx *c = p->ctx;
+    cudaStream_t s = c->stream, sk = c->stream_k, sp = c->stream_p, sd = c->stream_d2h;
+    if (p->ops.size() != 1 || p->ops[0].kind != OP_CHAIN) return fail(SKGPU_ERR_STATE, "sliced ticks need a plan whose only op is the chain op");
+    Op &op = p->ops[0];
+    if (op.slices.empty()) return fail(SKGPU_ERR_STATE, "no slices set (skgpu_plan_set_slices / skgpu_plan_auto_slices; table updates clear them)");
+    const uint32_t n = (uint32_t)op.slices.size();
+    skgpu_rc rc = sliced_prepare(p, op, n);
+    if (rc) return rc;
+    const uint32_t par = (uint32_t)((p->tick + 1) & 1ull), opar = par ^ 1u;   // parity of THIS tick's number / of the previous tick
+    const bool prev_sliced = p->sliced_pending && p->sl_n[opar] > 0;
+    // the previous tick's kernels read the per-tick tables and, as "previous chunk", the bank this tick uploads into
+    if (p->sliced_pending) CU(cudaStreamWaitEvent(s, p->ev_k_all, 0));
+    rc = upload_dirty(p);
+    if (rc) return rc;
+    CU(cudaEventRecord(p->ev_tables, s));             // tables, gains, presence (and any unsliced tick before) are on s
+    CU(cudaStreamWaitEvent(sk, p->ev_tables, 0));
+    CU(cudaEventRecord(p->ev_t0[par], s));
+    if (!do_h2d && !do_d2h) {
+        // ---- inputs resident, nothing read back: the kernel network alone, replayed as one CUDA graph
+        if ((flags & SKGPU_SUBMIT_GRAPH) != 0) {
+            if (!p->sl_graph_exec) {
+                if (!p->ev_fork) CU(cudaEventCreateWithFlags(&p->ev_fork, cudaEventDisableTiming));
+                CU(cudaStreamSynchronize(sk));
+                CU(cudaStreamSynchronize(sp));
+                CU(cudaStreamBeginCapture(sk, cudaStreamCaptureModeThreadLocal));
+                rc = sliced_kernels(p, op, n, p->ev_fork);
+                const cudaError_t e = cudaStreamEndCapture(sk, &p->sl_graph);
+                if (rc) return rc;
+                if (e != cudaSuccess) return fail(SKGPU_ERR_CUDA, "capture of the sliced tick failed: %s", cudaGetErrorString(e));
+                CU(cudaGraphInstantiate(&p->sl_graph_exec, p->sl_graph, 0));
+            }
+            CU(cudaGraphLaunch(p->sl_graph_exec, sk));
+        } else {
+            if (!p->ev_fork) CU(cudaEventCreateWithFlags(&p->ev_fork, cudaEventDisableTiming));
+            rc = sliced_kernels(p, op, n, p->ev_fork);
+            if (rc) return rc;
         }
+        p->tick++;
+        CU(cudaEventRecord(p->ev_k_all, sk));
+        CU(cudaStreamWaitEvent(sd, p->ev_k_all, 0));
+        for (uint32_t k = 0; k < n; ++k) {   // keep the per-slice events defined (timing of such a tick is not meaningful)
+            CU(cudaEventRecord(p->ev_up[par][k], s));
+            CU(cudaEventRecord(p->ev_k[par][k], sk));
+            CU(cudaEventRecord(p->ev_done[par][k], sd));
+        }
+        CU(cudaEventRecord(p->ev_d2h_done, sd));
+        CU(cudaEventRecord(p->ev_tick_done[p->tick & 1ull], sd));
+        p->sl_n[par] = n;
+        p->sliced_pending = true;
+        p->d2h_pending = false;
+        p->timing_valid = false;
+        return SKGPU_OK;
+    }
+    // ---- all phase kernels first (stream_p): they need no input byte of this tick (but they rewrite the result rows the
+    // previous tick's read-back may still be copying)
+    CU(cudaStreamWaitEvent(sp, p->ev_tables, 0));
+    if (p->d2h_pending) CU(cudaStreamWaitEvent(sp, p->ev_d2h_done, 0));
+    {
+        uint32_t i0 = 0;
+        for (uint32_t k = 0; k < n; ++k) {
+            rc = launch_chain_phase(p, op, op.d_hdr_sl + k, op.slices[k].input_end - i0, sp);
+            if (rc) return rc;
+            CU(cudaEventRecord(p->ev_p[k], sp));
+            i0 = op.slices[k].input_end;
+        }
+    }
+    uint8_t *bank = p->arena + p->h2d_off + (p->tick & 1ull) * p->bank_stride;
+    uint64_t up0 = 0;
+    uint32_t g0 = 0;
+    for (uint32_t k = 0; k < n; ++k) {
+        const skgpu_slice &sl = op.slices[k];
+        if (do_h2d && sl.h2d_end > up0) CU(cudaMemcpyAsync(bank + up0, (const uint8_t *)host_in + up0, sl.h2d_end - up0, cudaMemcpyHostToDevice, s));
         up0 = std::max(up0, sl.h2d_end);
         CU(cudaEventRecord(p->ev_up[par][k], s));
         CU(cudaStreamWaitEvent(sk, p->ev_up[par][k], 0));
-        if (prev_sliced && do_d2h && k < p->sl_n[opar]) CU(cudaStreamWaitEvent(sk, p->ev_done[opar][k], 0));
+        CU(cudaStreamWaitEvent(sk, p->ev_p[k], 0));
+        if (prev_sliced && k < p->sl_n[opar]) CU(cudaStreamWaitEvent(sk, p->ev_done[opar][k], 0));
         else if (p->d2h_pending && k == 0) CU(cudaStreamWaitEvent(sk, p->ev_d2h_done, 0));
-        skgpu_rc rc = launch_chain(p, op, op.d_hdr_sl + k, sl.group_end - g0, sl.input_end - i0, sk, false);
+        rc = launch_chain_main(p, op, op.d_hdr_sl + k, sl.group_end - g0, sk);
         if (rc) return rc;
         if (k + 1 == n) {   // bank parity of the next tick, after the last slice's kernels
             k_tick_advance<<<1, 1, 0, sk>>>(p->d_tick);
@@ -1479,7 +1602,7 @@ static skgpu_rc submit_sliced(skgpu_plan *p, const void *host_in, void *host_out
             for (int r = 0; r < 2; ++r)
                 if (sl.d2h_bytes[r]) CU(cudaMemcpyAsync((uint8_t *)host_out + sl.d2h_off[r], p->arena + p->d2h_off + sl.d2h_off[r], sl.d2h_bytes[r], cudaMemcpyDeviceToHost, sd));
         CU(cudaEventRecord(p->ev_done[par][k], sd));
-        g0 = sl.group_end; i0 = sl.input_end;
+        g0 = sl.group_end;
     }
     p->tick++;
     CU(cudaEventRecord(p->ev_k_all, sk));
@@ -1520,13 +1643,13 @@ extern "C" skgpu_rc skgpu_tick_submit(skgpu_plan *p, const void *host_in, void *
     if (do_d2h && !host_out) return fail(SKGPU_ERR_INVALID, "host_out is null");
     skgpu_rc rc = ctx_flush(c);
     if (rc) return rc;
-    rc = upload_dirty(p);
-    if (rc) return rc;
-    if (flags & SKGPU_SUBMIT_SLICED) return submit_sliced(p, host_in, host_out, do_h2d, do_d2h);
+    if (flags & SKGPU_SUBMIT_SLICED) return submit_sliced(p, host_in, host_out, do_h2d, do_d2h, flags);
     if (p->sliced_pending) {   // the previous tick's kernels ran on the kernel stream: this tick's upload / kernels follow them
         CU(cudaStreamWaitEvent(s, p->ev_k_all, 0));
         p->sliced_pending = false;
     }
+    rc = upload_dirty(p);
+    if (rc) return rc;
     const bool overlap = (flags & SKGPU_SUBMIT_OVERLAP_D2H) != 0 && do_d2h;
     CU(cudaEventRecord(p->e0, s));
     if (do_h2d) CU(cudaMemcpyAsync(p->arena + p->h2d_off + (p->tick & 1ull) * p->bank_stride, host_in, p->h2d_bytes, cudaMemcpyHostToDevice, s));
@@ -1571,6 +1694,7 @@ extern "C" skgpu_rc skgpu_tick_wait(skgpu_plan *p, skgpu_tick_timing *t) {
     if (!p) return fail(SKGPU_ERR_INVALID, "null plan");
     CU(cudaSetDevice(p->ctx->device));
     CU(cudaStreamSynchronize(p->ctx->stream));
+    CU(cudaStreamSynchronize(p->ctx->stream_p));
     CU(cudaStreamSynchronize(p->ctx->stream_k));
     CU(cudaStreamSynchronize(p->ctx->stream_d2h));
     p->d2h_pending = false;
@@ -1664,6 +1788,7 @@ extern "C" skgpu_rc skgpu_ctx_sync(skgpu_ctx *c) {
     if (!c) return fail(SKGPU_ERR_INVALID, "null context");
     CU(cudaSetDevice(c->device));
     CU(cudaStreamSynchronize(c->stream));
+    CU(cudaStreamSynchronize(c->stream_p));
     CU(cudaStreamSynchronize(c->stream_k));
     CU(cudaStreamSynchronize(c->stream_d2h));
     return SKGPU_OK;

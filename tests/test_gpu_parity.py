@@ -711,3 +711,33 @@ def test_pinned_alloc_placement_flags(ctx):
     b[:] = 9
     assert a[-1] == 7
     ctx.bind_thread()                                               # no-op on a single-node box
+
+
+@pytest.mark.parametrize("graph", [False, True])
+def test_resident_sliced_kernel_network_equals_whole_tick(graph):
+    """inputs resident, nothing read back: the sliced tick is a fork / join of k_phase_chain (stream_p) and k_chain (stream_k)
+    launches -- optionally one captured CUDA graph -- in which phase(i + 1) overlaps chain(i). Same bytes as whole-tick launches."""
+    S, K, T = 97, 2, 7
+    a = chain.ChainTick(S, K, seed=29)
+    b = chain.ChainTick(S, K, seed=29)
+    try:
+        b.plan.auto_slices(b.op_chain, 5)
+        x = synth.tone_streams(29, 0, a.n_streams, a.chunk, 2, 44100)
+        hin = np.zeros(a.in_bytes // 4, np.float32)
+        hin.reshape(a.n_streams, a.in_stride // 4)[:, : x.shape[1]] = x
+        for ct in (a, b):
+            ct.plan.upload(0, hin)
+            ct.plan.upload(ct.bank_stride, hin)
+        for t in range(T):
+            a.plan.submit(None, None, L.SUBMIT_NO_H2D | L.SUBMIT_NO_D2H)
+            b.plan.submit(None, None, L.SUBMIT_NO_H2D | L.SUBMIT_NO_D2H | L.SUBMIT_SLICED | (L.SUBMIT_GRAPH if graph else 0))
+            a.plan.wait()
+            b.plan.wait()
+            want = a.plan.download(a.out_off, a.out_bytes, np.int16)
+            got = b.plan.download(b.out_off, b.out_bytes, np.int16)
+            assert np.array_equal(got, want), f"tick {t}"
+        assert np.any(want != 0)
+        assert np.array_equal(a.results(), b.results())
+    finally:
+        a.close()
+        b.close()
