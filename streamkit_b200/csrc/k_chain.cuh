@@ -205,152 +205,79 @@ __device__ __forceinline__ void chain_pure(unsigned long long *acc, RunCache &rc
     for (int n = 0; n < N; ++n) acc_add(acc[n], chain_frame<OC, SC>((flh[n] >> rc.sh) + rc.kc, frac[n], gain, one2), one2);   // a_chunk + floor(x) * frame bytes
 }
 
-__device__ __forceinline__ uint4 lds_v4(uint32_t addr) {
-    uint4 v;
-    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
-    return v;
-}
-__device__ __forceinline__ void lds_run(uint32_t sa, double &x0, double &dl) {
-    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(x0), "=d"(dl) : "r"(sa));
-}
-__device__ __forceinline__ void cache_run(RunCache &rc, const uint4 &h, double dl, uint32_t a_chunk) {   // h = (jj, himask, aux, sh) of a FAST run
-    rc.j0 = h.x & 0xFFFFu;
-    rc.j1 = h.x >> 16;
-    rc.himask = h.y;
-    rc.sh = h.w;
-    rc.kc = a_chunk - h.z;
-    rc.dl32 = __dmul_rn(dl, 32.0);
-}
-
-// the general path of a block: every lane walks the segment list from the block map's first entry to ITS segment and
-// evaluates it (explicit frame, FAST run or SLOW run). Needed for blocks with several short segments (unusual ratios,
-// negative positions right after a stream starts); out of line so the hot code stays compact.
+// one block, any shape: straight line when it lies inside the cached run (possibly after entering the run that covers it),
+// else the per-lane segment walk; `refresh`: the next block belongs to this warp too, so try to cache the block's last run
 template <int OC, int SC>
-__device__ __forceinline__ unsigned long long chain_block_walk(uint32_t e, uint32_t jb, uint32_t prog, uint32_t segs, uint32_t a_hist,
-                                              uint32_t a_chunk, uint32_t F, uint32_t lane, float gain, unsigned long long one2) {
-    uint32_t addr;
-    float frac;
-    const uint32_t j = min(jb + lane, F - 1u);               // lanes past the packet's end recompute its last frame
-    uint32_t sa = segs + (e & 0xFFu) * 32u;
-    const uint32_t sa_last = segs + (e >> 8) * 32u;
-    uint4 h = lds_v4(sa + 16u);
-    while ((h.x >> 16) <= j && sa < sa_last) {
-        sa += 32u;
-        h = lds_v4(sa + 16u);
-    }
-    const uint32_t rel = j - (h.x & 0xFFFFu);
-    if (h.y == SKC_KIND_E) {
-        uint32_t aoff;
-        asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(aoff), "=f"(frac) : "r"(prog + h.z + rel * 8u));
-        addr = a_hist + aoff;
-    } else {
-        double x0, dl;
-        lds_run(sa, x0, dl);
-        const double x = __fma_rn((double)rel, dl, x0);     // exact inside a run (phase_runs.h)
-        if (h.y != SKC_KIND_SLOW) {
-            uint32_t flh;
-            fast_split(x, h.y, flh, frac);
-            addr = (flh >> h.w) + a_chunk - h.z;
-        } else {
-            const unsigned long long pf = chain_split_slow(x, SC * 4u);
-            uint32_t off;
-            asm("mov.b64 {%0, %1}, %2;" : "=r"(off), "=f"(frac) : "l"(pf));
-            addr = a_chunk + off;
-        }
-    }
-    return chain_frame<OC, SC>(addr, frac, gain, one2);   // the value to add
-}
-
-// One block, any shape.
-//   pure      the block lies inside the cached FAST run (or inside the single FAST run that covers it): straight line
-//   boundary  [run A | explicit frames | run B] with any part possibly empty -- a binade boundary of the phase recurrence
-//             (the few true chain elements between two runs are stored explicitly), the packet's head (explicit frames,
-//             then the first long run) and its tail (last run, then the frames of the current chunk). No search: the
-//             roles follow from the headers of the block's first, middle and last segment; every lane evaluates ITS role
-//             with selects, and run B becomes the cached run of the following blocks.
-//   anything else takes the per-lane segment walk.
-// `refresh`: the next block belongs to this warp too.
-template <int OC, int SC>
-__device__ __forceinline__ void chain_block(unsigned long long &acc, RunCache &rc, uint32_t blk, bool refresh, uint32_t prog, uint32_t segs, uint32_t a_hist,
-                                            uint32_t a_chunk, uint32_t F, uint32_t lane, float gain, unsigned long long one2) {
+__device__ __forceinline__ unsigned long long chain_block(RunCache &rc, uint32_t blk, bool refresh, uint32_t prog, uint32_t segs, uint32_t a_hist,
+                                                          uint32_t a_chunk, uint32_t F, uint32_t lane, float gain, unsigned long long one2) {
     const uint32_t jb = blk * 32u;
-    if (jb >= rc.j0 && jb + 32u <= rc.j1) {
-        chain_pure<OC, SC, 1>(&acc, rc, gain, one2);
-        return;
+    bool pure = jb >= rc.j0 && jb + 32u <= rc.j1;
+    uint32_t e = 0;
+    if (!pure) {
+        if (jb >= F) return 0x8000000080000000ull;             // warp-uniform: past the packet, add -0.0 (the identity)
+        asm volatile("ld.shared.u16 %0, [%1];" : "=r"(e) : "r"(prog + blk * 2u));
     }
-    if (jb >= F) return;                                       // warp-uniform (a pure block never lies past the packet)
-    uint32_t e;
-    asm volatile("ld.shared.u16 %0, [%1];" : "=r"(e) : "r"(prog + blk * 2u));
-    const uint32_t first = e & 0xFFu, nseg1 = (e >> 8) - first;   // segments of the block, minus one
-    const uint32_t saF = segs + first * 32u, saL = segs + (e >> 8) * 32u;
-    const uint4 hF = lds_v4(saF + 16u);                        // (j0 | j1 << 16, kind / himask, aux, sh)
-    uint4 hL = hF, hE = hF;
-    bool hasA = false, hasB = false, hasE = false, ok = nseg1 <= 2u;
-    const bool fastF = hF.y > SKC_KIND_SLOW;
-    if (nseg1 == 0u) {
-        if (fastF) {
-            // one FAST run covers the block (typically the warp's first block of an input): enter it
-            double x0, dl;
-            lds_run(saF, x0, dl);
-            cache_run(rc, hF, dl, a_chunk);
-            // the lane's frame one block EARLIER on the run's lattice (a multiple of the binade's unit below 2^(e+1), hence
-            // exact, also when it extrapolates below the run's start); the straight-line path adds 32 delta
-            rc.xl = __fma_rn((double)((int)(jb + lane) - (int)rc.j0 - 32), dl, x0);
-            chain_pure<OC, SC, 1>(&acc, rc, gain, one2);
-            return;
+    if (pure) {
+        // ---- straight line: the whole block lies inside the cached run
+        rc.xl = __dadd_rn(rc.xl, rc.dl32);
+        uint32_t flh;
+        float frac;
+        fast_split(rc.xl, rc.himask, flh, frac);
+        return chain_frame<OC, SC>((flh >> rc.sh) + rc.kc, frac, gain, one2);   // a_chunk + floor(x) * frame bytes
+    } else {
+        uint32_t addr;
+        float frac;
+        // ---- general: per-lane segment walk
+        const uint32_t j = min(jb + lane, F - 1u);               // lanes past the packet's end recompute its last frame
+        uint32_t sa = segs + (e & 0xFFu) * 32u;
+        const uint32_t sa_last = segs + (e >> 8) * 32u;
+        uint32_t jj, himask, aux, sh;
+        asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4+16];" : "=r"(jj), "=r"(himask), "=r"(aux), "=r"(sh) : "r"(sa));
+        while ((jj >> 16) <= j && sa < sa_last) {
+            sa += 32u;
+            asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4+16];" : "=r"(jj), "=r"(himask), "=r"(aux), "=r"(sh) : "r"(sa));
         }
-        hasE = hF.y == SKC_KIND_E;
-        ok = hasE;
-    } else if (ok) {
-        hL = lds_v4(saL + 16u);
-        const bool fastL = hL.y > SKC_KIND_SLOW;
-        if (nseg1 == 1u) {
-            hasA = fastF;
-            hasB = fastL;
-            if (!fastF) { hasE = hF.y == SKC_KIND_E; ok = hasE && fastL; }
-            else if (!fastL) { hasE = hL.y == SKC_KIND_E; hE = hL; ok = hasE; }
+        const uint32_t rel = j - (jj & 0xFFFFu);
+        if (himask == SKC_KIND_E) {
+            uint32_t aoff;
+            asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(aoff), "=f"(frac) : "r"(prog + aux + rel * 8u));
+            addr = a_hist + aoff;
         } else {
-            hE = lds_v4(saF + 48u);
-            hasA = hasB = hasE = true;
-            ok = fastF && fastL && hE.y == SKC_KIND_E;
+            double x0, dl;
+            asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(x0), "=d"(dl) : "r"(sa));
+            const double x = __fma_rn((double)rel, dl, x0);     // exact inside a run (phase_runs.h)
+            if (himask != SKC_KIND_SLOW) {
+                uint32_t flh;
+                fast_split(x, himask, flh, frac);
+                addr = (flh >> sh) + a_chunk - aux;
+            } else {
+                const unsigned long long pf = chain_split_slow(x, SC * 4u);
+                uint32_t off;
+                asm("mov.b64 {%0, %1}, %2;" : "=r"(off), "=f"(frac) : "l"(pf));
+                addr = a_chunk + off;
+            }
         }
-    }
-    if (!ok) {
-        acc_add(acc, chain_block_walk<OC, SC>(e, jb, prog, segs, a_hist, a_chunk, F, lane, gain, one2), one2);
+        const unsigned long long v = chain_frame<OC, SC>(addr, frac, gain, one2);
+        // ---- refresh the run cache from the block's last segment when that is a FAST run reaching past the block
         rc.j1 = 0;
-        return;
-    }
-    // ---- boundary block
-    const uint32_t j = min(jb + lane, F - 1u);                   // lanes past the packet's end recompute its last frame
-    const bool inA = hasA && j < (hF.x >> 16);
-    const bool inB = hasB && j >= (hL.x & 0xFFFFu);
-    double x = 0.0, xB = 0.0, dlB = 0.0;
-    if (hasA) {
-        double x0, dl;
-        lds_run(saF, x0, dl);
-        x = __fma_rn((double)(j - (hF.x & 0xFFFFu)), dl, x0);    // exact inside the run; lanes outside A drop it
-    }
-    if (hasB) {
-        double x0;
-        lds_run(saL, x0, dlB);
-        xB = __fma_rn((double)((int)j - (int)(hL.x & 0xFFFFu)), dlB, x0);   // lanes before B extrapolate (exact, see above)
-    }
-    x = inB ? xB : x;
-    const uint32_t himask = inB ? hL.y : hF.y, sh = inB ? hL.w : hF.w, aux = inB ? hL.z : hF.z;
-    uint32_t flh, addr;
-    float frac;
-    fast_split(x, himask, flh, frac);
-    addr = (flh >> sh) + a_chunk - aux;
-    if (!(inA || inB)) {                                          // the explicit frames between / before / after the runs
-        uint32_t aoff;
-        asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(aoff), "=f"(frac) : "r"(prog + hE.z + (j - (hE.x & 0xFFFFu)) * 8u));
-        addr = a_hist + aoff;
-    }
-    acc_add(acc, chain_frame<OC, SC>(addr, frac, gain, one2), one2);
-    rc.j1 = 0;
-    if (refresh && hasB && (hL.x >> 16) >= jb + 64u) {            // run B reaches past the next block: it is the cached run now
-        cache_run(rc, hL, dlB, a_chunk);
-        rc.xl = xB;                                              // this lane's frame of THIS block on B's lattice
+        if (refresh) {
+            uint32_t ljj, lhimask, laux, lsh;
+            asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4+16];" : "=r"(ljj), "=r"(lhimask), "=r"(laux), "=r"(lsh) : "r"(sa_last));
+            if (lhimask > SKC_KIND_SLOW && (ljj >> 16) >= jb + 64u) {   // warp-uniform
+                double x0, dl;
+                asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(x0), "=d"(dl) : "r"(sa_last));
+                rc.j0 = ljj & 0xFFFFu;
+                rc.j1 = ljj >> 16;
+                rc.himask = lhimask;
+                rc.sh = lsh;
+                rc.kc = a_chunk - laux;
+                rc.dl32 = __dmul_rn(dl, 32.0);
+                // this lane's frame of THIS block on the run's lattice (lanes before the run's start extrapolate below
+                // the binade: still a multiple of the binade's unit, so every later + 32 delta step is exact)
+                rc.xl = __fma_rn((double)((int)(jb + lane) - (int)rc.j0), dl, x0);
+            }
+        }
+        return v;
     }
 }
 
@@ -364,23 +291,44 @@ __device__ __forceinline__ void chain_consume(unsigned long long (&acc)[ITERS][C
     rc.j0 = 0; rc.j1 = 0; rc.himask = 0; rc.sh = 0; rc.kc = 0; rc.xl = 0.0; rc.dl32 = 0.0;
 #pragma unroll
     for (int it = 0; it < ITERS; ++it) {
-        if (ITERS > 1) rc.j1 = 0;   // the warp's next block is not adjacent
+        rc.j1 = 0;   // nothing cached: the warp's first block of this input / iteration is not adjacent to its last one
         const uint32_t blk0 = ((uint32_t)it * CH_CWARPS + cw) * CH_NB;
+        if (blk0 * 32u < F) {
+            // enter the run that covers the warp's first block, if one FAST run does (else the block takes the general path)
+            uint32_t e;
+            asm volatile("ld.shared.u16 %0, [%1];" : "=r"(e) : "r"(prog + blk0 * 2u));
+            const uint32_t sa = segs + (e & 0xFFu) * 32u;
+            uint32_t ljj, lhimask, laux, lsh;
+            asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4+16];" : "=r"(ljj), "=r"(lhimask), "=r"(laux), "=r"(lsh) : "r"(sa));
+            if ((e & 0xFFu) == (e >> 8) && lhimask > SKC_KIND_SLOW && (ljj >> 16) >= blk0 * 32u + 32u) {
+                double x0, dl;
+                asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(x0), "=d"(dl) : "r"(sa));
+                rc.j0 = ljj & 0xFFFFu;
+                rc.j1 = ljj >> 16;
+                rc.himask = lhimask;
+                rc.sh = lsh;
+                rc.kc = a_chunk - laux;
+                rc.dl32 = __dmul_rn(dl, 32.0);
+                // the lane's frame one block EARLIER on the run's lattice (a multiple of the binade's unit below 2^(e+1), hence
+                // exact, also when it extrapolates below the run's start); the straight-line paths add 32 delta per block
+                rc.xl = __fma_rn((double)((int)(blk0 * 32u + lane) - (int)rc.j0 - 32), dl, x0);
+            }
+        }
 #pragma unroll
         for (int f4 = 0; f4 < CH_NB; f4 += 4) {
             const uint32_t jb4 = (blk0 + (uint32_t)f4) * 32u;
             if (jb4 >= rc.j0 && jb4 + 128u <= rc.j1) {
                 chain_pure<OC, SC, 4>(&acc[it][f4], rc, gain, one2);
             } else {
-#pragma unroll
-                for (int f2 = f4; f2 < f4 + 4; f2 += 2) {
-                    const uint32_t jb2 = (blk0 + (uint32_t)f2) * 32u;
-                    if (jb2 >= rc.j0 && jb2 + 64u <= rc.j1) {
-                        chain_pure<OC, SC, 2>(&acc[it][f2], rc, gain, one2);
-                    } else {
-                        chain_block<OC, SC>(acc[it][f2], rc, blk0 + (uint32_t)f2, true, prog, segs, a_hist, a_chunk, F, lane, gain, one2);
-                        chain_block<OC, SC>(acc[it][f2 + 1], rc, blk0 + (uint32_t)f2 + 1u, f2 + 2 < CH_NB, prog, segs, a_hist, a_chunk, F, lane, gain, one2);
-                    }
+                // one copy of the single-block code per group of four (a real loop): the kernel's instruction footprint matters
+#pragma unroll 1
+                for (uint32_t i = 0; i < 4u; ++i) {
+                    const unsigned long long v = chain_block<OC, SC>(rc, blk0 + (uint32_t)f4 + i, (uint32_t)f4 + i + 1u < (uint32_t)CH_NB, prog, segs, a_hist,
+                                                                     a_chunk, F, lane, gain, one2);
+                    if (i == 0u) acc_add(acc[it][f4], v, one2);
+                    else if (i == 1u) acc_add(acc[it][f4 + 1], v, one2);
+                    else if (i == 2u) acc_add(acc[it][f4 + 2], v, one2);
+                    else acc_add(acc[it][f4 + 3], v, one2);
                 }
             }
         }
@@ -480,7 +428,9 @@ __global__ void __launch_bounds__(PHASE_CHAIN_THREADS, 14) k_phase_chain(const O
                  "r"(head * fb), "r"(flags), "r"((N - 16u) * ch), "r"(0u), "r"(0u) : "memory");
 }
 
-template <int OC, int ITERS>  // output channels (1 | 2); ITERS = ceil(F / 1024)
+// OC output channels (1 | 2); ITERS = ceil(F / 1024); UNIFORM: every input of the op has OC channels (the common case gets a
+// kernel with ONE copy of the consumer code: the instruction footprint matters), else inputs may be mono or stereo
+template <int OC, int ITERS, bool UNIFORM>
 __global__ void __launch_bounds__(CH_THREADS, 5) k_chain(const OpHeader *__restrict__ hdr, const skgpu_chain_group *__restrict__ groups,
                                                          const ChainRec *__restrict__ recs, const float *__restrict__ gains, SlotTables st,
                                                          uint8_t *__restrict__ arena, uint32_t F, ChainDims dm) {
@@ -710,11 +660,10 @@ __global__ void __launch_bounds__(CH_THREADS, 5) k_chain(const OpHeader *__restr
 #pragma unroll
                 for (int f = 0; f < CH_NB; ++f) acc[it][f] = init;
         }
-        if (hd.w & 2u) {
-            // every input of the batch is stereo (the common session): one code variant inside the loop
+        if (UNIFORM) {
             for (uint32_t q = 0; q < nb; ++q) {
                 const uint32_t prog = sm + q * in_bytes;
-                chain_consume<OC, 2, ITERS>(acc, prog, prog + prog_cap, dm.prog, F, cw, lane, S->cons[q].gain, one2);
+                chain_consume<OC, OC, ITERS>(acc, prog, prog + prog_cap + (OC == 2 ? 0u : SK_SIDE_HIST - 64u), dm.prog, F, cw, lane, S->cons[q].gain, one2);
             }
         } else {
             for (uint32_t q = 0; q < nb; ++q) {

@@ -426,6 +426,7 @@ struct Op {
     uint32_t chain_buf_floats = 0;  // chain: floats per staging buffer
     int chain_oc = 2;             // chain: output channels specialisation
     int chain_iters = 1;          // chain: ceil(F / 1024)
+    bool chain_uniform = false;   // chain: every input has the output's channel count (single-variant kernel)
     ChainDims chain_dm{};         // chain: staging-ring geometry passed to the kernel
     ChainRec *d_rec = nullptr;    // chain: per-input records written by k_phase_chain every tick
     uint32_t chain_grid = 0;      // chain: persistent grid size (CTAs per SM x SMs)
@@ -979,7 +980,7 @@ static bool prog_bounds(double t, int32_t end_idx, uint32_t N, uint32_t F, uint3
 }
 
 static skgpu_rc validate_chain(const skgpu_plan *p, const skgpu_chain_group *g, uint32_t ng, const skgpu_chain_input *in, uint32_t ni,
-                               uint32_t F, uint32_t *max_k, uint32_t *max_buf_floats, int *oc_out, uint32_t *cap_seg, uint32_t *cap_exp) {
+                               uint32_t F, uint32_t *max_k, uint32_t *max_buf_floats, int *oc_out, uint32_t *cap_seg, uint32_t *cap_exp, bool *uniform_out) {
     uint32_t need_seg = 0, need_exp = 0;
     double last_t = -1.0;
     int32_t last_end = 0;
@@ -1030,6 +1031,11 @@ static skgpu_rc validate_chain(const skgpu_plan *p, const skgpu_chain_group *g, 
     *max_k = mk;
     *max_buf_floats = (mb + 15u) & ~15u;
     *oc_out = oc < 0 ? 2 : oc;
+    {
+        bool uni = true;
+        for (uint32_t i = 0; i < ni; ++i) uni = uni && (int)c->h_ch[in[i].slot] == *oc_out;
+        *uniform_out = uni;
+    }
     // margin for phases the sampling did not hit; even counts keep every staged array a multiple of 16 bytes
     *cap_seg = (need_seg + 5u) & ~1u;
     *cap_exp = (need_exp + 9u) & ~1u;
@@ -1100,7 +1106,8 @@ extern "C" skgpu_rc skgpu_plan_add_chain_cap(skgpu_plan *p, const skgpu_chain_gr
     CU(cudaSetDevice(p->ctx->device));
     uint32_t mk = 0, mb = 0, cnp = 0, cnr = 0;
     int oc = 2;
-    skgpu_rc rc = validate_chain(p, groups, ng, inputs, ni, output_frame_size, &mk, &mb, &oc, &cnp, &cnr);
+    bool uniform = true;
+    skgpu_rc rc = validate_chain(p, groups, ng, inputs, ni, output_frame_size, &mk, &mb, &oc, &cnp, &cnr, &uniform);
     if (rc) return rc;
     mk = std::max(mk, max_inputs_per_group);
     rc = check_range(p, results_off, (uint64_t)std::max(cap_inputs, 1u) * sizeof(skgpu_chain_result), "chain results");
@@ -1116,6 +1123,7 @@ extern "C" skgpu_rc skgpu_plan_add_chain_cap(skgpu_plan *p, const skgpu_chain_gr
     op.n2 = ni;
     op.chain_F = output_frame_size;
     op.chain_oc = oc;
+    op.chain_uniform = uniform && ni > 0;
     op.chain_iters = (int)((output_frame_size + 1023u) / 1024u);
     op.results_off = results_off;
     chain_size_smem(op, mk, std::max(mb, 64u), cnp, cnr);
@@ -1140,9 +1148,11 @@ extern "C" skgpu_rc skgpu_plan_update_chain(skgpu_plan *p, uint32_t opi, const s
     if (ng > op.cap || ni > op.cap2) return fail(SKGPU_ERR_INVALID, "update exceeds capacity");
     uint32_t mk = 0, mb = 0, cnp = 0, cnr = 0;
     int oc = 2;
-    skgpu_rc rc = validate_chain(p, groups, ng, inputs, ni, op.chain_F, &mk, &mb, &oc, &cnp, &cnr);
+    bool uniform = true;
+    skgpu_rc rc = validate_chain(p, groups, ng, inputs, ni, op.chain_F, &mk, &mb, &oc, &cnp, &cnr, &uniform);
     if (rc) return rc;
     if (ng && oc != op.chain_oc) return fail(SKGPU_ERR_INVALID, "update changes the op's output channel count");
+    if (op.chain_uniform && !uniform) return fail(SKGPU_ERR_INVALID, "update adds an input whose channel count differs from the output's to an op created with uniform inputs (include such a stream in the initial tables)");
     if (mb > op.chain_buf_floats) return fail(SKGPU_ERR_INVALID, "update has a longer chunk than the op was sized for");
     if (mk > op.chain_dm.max_k) return fail(SKGPU_ERR_INVALID, "update has a session with more inputs (%u) than the op was sized for (%u)", mk, op.chain_dm.max_k);
     if (cnp > op.chain_dm.prog.cap_seg || cnr > op.chain_dm.prog.cap_exp) return fail(SKGPU_ERR_INVALID, "update adds a resampling ratio whose phase tables exceed the op's staging capacity");
@@ -1292,9 +1302,13 @@ static skgpu_rc op_event(Op &op, int sub, bool second, cudaStream_t s) {
 }
 
 typedef void (*chain_kernel_t)(const OpHeader *, const skgpu_chain_group *, const ChainRec *, const float *, SlotTables, uint8_t *, uint32_t, ChainDims);
-static chain_kernel_t chain_kernel(int oc, int iters) {
-    if (oc == 2) return iters == 1 ? k_chain<2, 1> : iters == 2 ? k_chain<2, 2> : k_chain<2, 3>;
-    return iters == 1 ? k_chain<1, 1> : iters == 2 ? k_chain<1, 2> : k_chain<1, 3>;
+static chain_kernel_t chain_kernel(int oc, int iters, bool uniform) {
+    if (uniform) {
+        if (oc == 2) return iters == 1 ? k_chain<2, 1, true> : iters == 2 ? k_chain<2, 2, true> : k_chain<2, 3, true>;
+        return iters == 1 ? k_chain<1, 1, true> : iters == 2 ? k_chain<1, 2, true> : k_chain<1, 3, true>;
+    }
+    if (oc == 2) return iters == 1 ? k_chain<2, 1, false> : iters == 2 ? k_chain<2, 2, false> : k_chain<2, 3, false>;
+    return iters == 1 ? k_chain<1, 1, false> : iters == 2 ? k_chain<1, 2, false> : k_chain<1, 3, false>;
 }
 
 // the two kernels of the chain op over the table range a launch header describes (the whole tables, or one slice)
@@ -1309,7 +1323,7 @@ static skgpu_rc launch_chain(skgpu_plan *p, Op &op, const OpHeader *d_hdr, uint3
     CU(cudaGetLastError());
     if (time_ops) { skgpu_rc rc = op_event(op, 0, true, s); if (rc) return rc; rc = op_event(op, 1, false, s); if (rc) return rc; }
     const uint32_t grid = std::max(1u, std::min<uint32_t>(n_groups, op.chain_grid));
-    auto kfn = chain_kernel(op.chain_oc, op.chain_iters);
+    auto kfn = chain_kernel(op.chain_oc, op.chain_iters, op.chain_uniform);
     kfn<<<grid, CH_THREADS, op.smem_bytes, s>>>(d_hdr, (const skgpu_chain_group *)op.d_tab, op.d_rec, gains, c->st, p->arena, op.chain_F, op.chain_dm);
     CU(cudaGetLastError());
     if (time_ops) { skgpu_rc rc = op_event(op, 1, true, s); if (rc) return rc; }
@@ -1396,7 +1410,7 @@ extern "C" skgpu_rc skgpu_plan_finalize(skgpu_plan *p) {
     }
     for (auto &op : p->ops) {
         if (op.kind == OP_CHAIN) {
-            auto kfn = chain_kernel(op.chain_oc, op.chain_iters);
+            auto kfn = chain_kernel(op.chain_oc, op.chain_iters, op.chain_uniform);
             CU(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)op.smem_bytes));
             int per_sm = 0;
             CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kfn, CH_THREADS, op.smem_bytes));
@@ -1433,7 +1447,7 @@ static skgpu_rc launch_chain_phase(skgpu_plan *p, Op &op, const OpHeader *d_hdr,
 static skgpu_rc launch_chain_main(skgpu_plan *p, Op &op, const OpHeader *d_hdr, uint32_t n_groups, cudaStream_t s) {
     skgpu_ctx *c = p->ctx;
     const uint32_t grid = std::max(1u, std::min<uint32_t>(n_groups, op.chain_grid));
-    auto kfn = chain_kernel(op.chain_oc, op.chain_iters);
+    auto kfn = chain_kernel(op.chain_oc, op.chain_iters, op.chain_uniform);
     kfn<<<grid, CH_THREADS, op.smem_bytes, s>>>(d_hdr, (const skgpu_chain_group *)op.d_tab, op.d_rec, (const float *)p->gains.dev, c->st, p->arena,
                                                  op.chain_F, op.chain_dm);
     CU(cudaGetLastError());
