@@ -320,15 +320,15 @@ __device__ __forceinline__ void chain_consume(unsigned long long (&acc)[ITERS][C
             if (jb4 >= rc.j0 && jb4 + 128u <= rc.j1) {
                 chain_pure<OC, SC, 4>(&acc[it][f4], rc, gain, one2);
             } else {
-                // one copy of the single-block code per group of four (a real loop): the kernel's instruction footprint matters
-#pragma unroll 1
-                for (uint32_t i = 0; i < 4u; ++i) {
-                    const unsigned long long v = chain_block<OC, SC>(rc, blk0 + (uint32_t)f4 + i, (uint32_t)f4 + i + 1u < (uint32_t)CH_NB, prog, segs, a_hist,
-                                                                     a_chunk, F, lane, gain, one2);
-                    if (i == 0u) acc_add(acc[it][f4], v, one2);
-                    else if (i == 1u) acc_add(acc[it][f4 + 1], v, one2);
-                    else if (i == 2u) acc_add(acc[it][f4 + 2], v, one2);
-                    else acc_add(acc[it][f4 + 3], v, one2);
+#pragma unroll
+                for (int f2 = f4; f2 < f4 + 4; f2 += 2) {
+                    const uint32_t jb2 = (blk0 + (uint32_t)f2) * 32u;
+                    if (jb2 >= rc.j0 && jb2 + 64u <= rc.j1) {
+                        chain_pure<OC, SC, 2>(&acc[it][f2], rc, gain, one2);
+                    } else {
+                        acc_add(acc[it][f2], chain_block<OC, SC>(rc, blk0 + (uint32_t)f2, true, prog, segs, a_hist, a_chunk, F, lane, gain, one2), one2);
+                        acc_add(acc[it][f2 + 1], chain_block<OC, SC>(rc, blk0 + (uint32_t)f2 + 1u, f2 + 2 < CH_NB, prog, segs, a_hist, a_chunk, F, lane, gain, one2), one2);
+                    }
                 }
             }
         }
