@@ -433,7 +433,7 @@ __global__ void __launch_bounds__(PHASE_CHAIN_THREADS, 14) k_phase_chain(const O
 template <int OC, int ITERS, bool UNIFORM>
 __global__ void __launch_bounds__(CH_THREADS, 5) k_chain(const OpHeader *__restrict__ hdr, const skgpu_chain_group *__restrict__ groups,
                                                          const ChainRec *__restrict__ recs, const float *__restrict__ gains, SlotTables st,
-                                                         uint8_t *__restrict__ arena, uint32_t F, ChainDims dm) {
+                                                         uint8_t *__restrict__ arena, uint32_t F, ChainDims dm, uint32_t *tick_advance) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t bar_full[CH_MAX_STAGES], bar_empty[CH_MAX_STAGES];
     __shared__ __align__(16) ChainStage s_stage[CH_MAX_STAGES];
@@ -629,6 +629,8 @@ __global__ void __launch_bounds__(CH_THREADS, 5) k_chain(const OpHeader *__restr
         if (lane == 0) {
             s_stage[stage].stop = 1;
             mbar_expect_tx(&bar_full[stage], 0);
+            // bank parity of the next tick (k_phase_chain of THIS tick has finished; nothing in this kernel reads the counter)
+            if (tick_advance && blockIdx.x == 0) tick_advance[0] += 1u;
         }
         return;
     }

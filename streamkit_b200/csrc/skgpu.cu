@@ -1301,7 +1301,7 @@ static skgpu_rc op_event(Op &op, int sub, bool second, cudaStream_t s) {
     return SKGPU_OK;
 }
 
-typedef void (*chain_kernel_t)(const OpHeader *, const skgpu_chain_group *, const ChainRec *, const float *, SlotTables, uint8_t *, uint32_t, ChainDims);
+typedef void (*chain_kernel_t)(const OpHeader *, const skgpu_chain_group *, const ChainRec *, const float *, SlotTables, uint8_t *, uint32_t, ChainDims, uint32_t *);
 static chain_kernel_t chain_kernel(int oc, int iters, bool uniform) {
     if (uniform) {
         if (oc == 2) return iters == 1 ? k_chain<2, 1, true> : iters == 2 ? k_chain<2, 2, true> : k_chain<2, 3, true>;
@@ -1324,7 +1324,8 @@ static skgpu_rc launch_chain(skgpu_plan *p, Op &op, const OpHeader *d_hdr, uint3
     if (time_ops) { skgpu_rc rc = op_event(op, 0, true, s); if (rc) return rc; rc = op_event(op, 1, false, s); if (rc) return rc; }
     const uint32_t grid = std::max(1u, std::min<uint32_t>(n_groups, op.chain_grid));
     auto kfn = chain_kernel(op.chain_oc, op.chain_iters, op.chain_uniform);
-    kfn<<<grid, CH_THREADS, op.smem_bytes, s>>>(d_hdr, (const skgpu_chain_group *)op.d_tab, op.d_rec, gains, c->st, p->arena, op.chain_F, op.chain_dm);
+    kfn<<<grid, CH_THREADS, op.smem_bytes, s>>>(d_hdr, (const skgpu_chain_group *)op.d_tab, op.d_rec, gains, c->st, p->arena, op.chain_F, op.chain_dm,
+                                                 p->ops.size() == 1 ? p->d_tick : nullptr);   // a chain-only plan: the kernel advances the bank parity itself
     CU(cudaGetLastError());
     if (time_ops) { skgpu_rc rc = op_event(op, 1, true, s); if (rc) return rc; }
     return SKGPU_OK;
@@ -1374,7 +1375,7 @@ static skgpu_rc launch_ops(skgpu_plan *p, bool time_ops) {
             if (time_ops) { skgpu_rc rc = op_event(op, 0, true, s); if (rc) return rc; }
         }
     }
-    if (p->bank_stride) {  // bank parity of the next tick
+    if (p->bank_stride && p->ops.size() != 1) {  // bank parity of the next tick (a chain-only plan advances it inside k_chain)
         k_tick_advance<<<1, 1, 0, s>>>(p->d_tick);
         CU(cudaGetLastError());
     }
@@ -1385,7 +1386,7 @@ extern "C" uint32_t skgpu_plan_launches_per_tick(const skgpu_plan *p) {
     if (!p) return 0;
     uint32_t n = 0;
     for (auto &op : p->ops) n += (op.kind == OP_RESAMPLE || op.kind == OP_CHAIN) ? 2 : (op.kind == OP_MIX && op.has_fifo_inputs) ? 2 : 1;
-    if (p->bank_stride) n += 1;
+    if (p->bank_stride && p->ops.size() != 1) n += 1;
     return n;
 }
 
@@ -1444,12 +1445,12 @@ static skgpu_rc launch_chain_phase(skgpu_plan *p, Op &op, const OpHeader *d_hdr,
     CU(cudaGetLastError());
     return SKGPU_OK;
 }
-static skgpu_rc launch_chain_main(skgpu_plan *p, Op &op, const OpHeader *d_hdr, uint32_t n_groups, cudaStream_t s) {
+static skgpu_rc launch_chain_main(skgpu_plan *p, Op &op, const OpHeader *d_hdr, uint32_t n_groups, cudaStream_t s, bool advance) {
     skgpu_ctx *c = p->ctx;
     const uint32_t grid = std::max(1u, std::min<uint32_t>(n_groups, op.chain_grid));
     auto kfn = chain_kernel(op.chain_oc, op.chain_iters, op.chain_uniform);
     kfn<<<grid, CH_THREADS, op.smem_bytes, s>>>(d_hdr, (const skgpu_chain_group *)op.d_tab, op.d_rec, (const float *)p->gains.dev, c->st, p->arena,
-                                                 op.chain_F, op.chain_dm);
+                                                 op.chain_F, op.chain_dm, advance ? p->d_tick : nullptr);
     CU(cudaGetLastError());
     return SKGPU_OK;
 }
@@ -1516,12 +1517,10 @@ static skgpu_rc sliced_kernels(skgpu_plan *p, Op &op, uint32_t n, cudaEvent_t fo
         if (rc) return rc;
         CU(cudaEventRecord(p->ev_p[k], sp));
         CU(cudaStreamWaitEvent(sk, p->ev_p[k], 0));
-        rc = launch_chain_main(p, op, op.d_hdr_sl + k, sl.group_end - g0, sk);
+        rc = launch_chain_main(p, op, op.d_hdr_sl + k, sl.group_end - g0, sk, k + 1 == n);   // the last slice advances the bank parity
         if (rc) return rc;
         g0 = sl.group_end; i0 = sl.input_end;
     }
-    k_tick_advance<<<1, 1, 0, sk>>>(p->d_tick);
-    CU(cudaGetLastError());
     return SKGPU_OK;
 }
 
@@ -1604,12 +1603,8 @@ static skgpu_rc submit_sliced(skgpu_plan *p, const void *host_in, void *host_out
         CU(cudaStreamWaitEvent(sk, p->ev_p[k], 0));
         if (prev_sliced && k < p->sl_n[opar]) CU(cudaStreamWaitEvent(sk, p->ev_done[opar][k], 0));
         else if (p->d2h_pending && k == 0) CU(cudaStreamWaitEvent(sk, p->ev_d2h_done, 0));
-        rc = launch_chain_main(p, op, op.d_hdr_sl + k, sl.group_end - g0, sk);
+        rc = launch_chain_main(p, op, op.d_hdr_sl + k, sl.group_end - g0, sk, k + 1 == n);   // the last slice advances the bank parity
         if (rc) return rc;
-        if (k + 1 == n) {   // bank parity of the next tick, after the last slice's kernels
-            k_tick_advance<<<1, 1, 0, sk>>>(p->d_tick);
-            CU(cudaGetLastError());
-        }
         CU(cudaEventRecord(p->ev_k[par][k], sk));
         CU(cudaStreamWaitEvent(sd, p->ev_k[par][k], 0));
         if (do_d2h)
