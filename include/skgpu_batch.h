@@ -82,13 +82,21 @@ skgpu_rc skgpu_ctx_bind_thread(skgpu_ctx *ctx);
  * One slot = one rubato::FastFixedIn<f32>(Linear) instance (resampler.rs:232-238): last_index (f64) and
  * a 16-frame history live in HBM for the lifetime of the stream. */
 
+/* stream flags */
+#define SKGPU_STREAM_S16 1u  /* chain op only: the stream's chunks arrive as interleaved s16 (x = s / 32768, exact) -- half the
+                              * PCIe bytes of f32 for natively 16-bit sources; expanded to f32 in shared memory */
 typedef struct skgpu_stream_cfg {
     uint32_t in_rate;           /* Hz, from the first packet (resampler.rs:206-209) */
     uint32_t out_rate;          /* AudioResamplerConfig.target_sample_rate (resampler.rs:22-27) */
     uint32_t chunk_frames;      /* AudioResamplerConfig.chunk_frames, input frames per process() */
     uint16_t channels;          /* 1..max_channels */
-    uint16_t reserved;
+    uint16_t flags;             /* SKGPU_STREAM_* */
 } skgpu_stream_cfg;
+/* in_rate == out_rate opens a BYPASS stream: the reference's resampler node does no DSP for such inputs and forwards /
+ * re-frames the packets untouched (resampler.rs:299-373). In a chain op a bypass stream delivers exactly one packet of
+ * output_frame_size frames per tick (chunk_frames == output_frame_size) that enters the mix as it is -- the path of the
+ * 48 kHz mono frames an Opus decoder emits (crates/nodes/src/audio/codecs/opus.rs:103,122-131; moq_mixing.yml has no
+ * resampler at all). No arithmetic is applied to it (not a frac = 0 interpolation). Resample ops reject bypass streams. */
 
 skgpu_rc skgpu_stream_open(skgpu_ctx *ctx, const skgpu_stream_cfg *cfg, uint32_t *slot_out);
 /* bulk open of n identical streams (session ramp-up); slots_out[n] */
@@ -175,7 +183,9 @@ typedef struct skgpu_mix_group {
  *  - eligible streams: channels 1 or 2, chunk_frames >= 16, chunk_frames * out_rate / in_rate == F (a packet
  *    never spans more than two chunks). Everything else uses the unfused resample + mix ops. */
 typedef struct skgpu_chain_input {
-    uint64_t in_off;      /* byte offset of the stream's chunk inside bank 0 (bank 1 = + bank_stride), 16-byte aligned */
+    uint64_t in_off;      /* byte offset of the stream's chunk inside bank 0 (bank 1 = + bank_stride), 16-byte aligned; the chunk
+                           * is chunk_frames x channels f32 (s16 with SKGPU_STREAM_S16: then chunk_frames x channels must be even
+                           * and at most 4096, and 16 bytes past the chunk's end must still lie inside the arena) */
     uint32_t slot;        /* resampler stream slot (state in HBM) */
     uint32_t gain_idx;    /* per-input audio::gain, or SKGPU_NO_GAIN */
     uint32_t flags;       /* SKGPU_MIX_IN_UNIQUE */

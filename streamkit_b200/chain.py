@@ -1,12 +1,16 @@
 """Host-side builder of the full-chain tick (BASELINE config #5) on top of the batch C ABI:
 
-    per input i of a session:  audio::resampler{target 48000, chunk_frames = in frames/tick, output_frame_size 960}
+    per input i of a session:  audio::resampler{target 48000, chunk_frames = in frames/tick, output_frame_size F}
                                -> audio::gain{g_i}
-    audio::mixer (clocked 48 kHz / 960, inputs in pin order) -> audio::gain{master} -> f32 -> s16
+    audio::mixer (clocked 48 kHz / F, inputs in pin order) -> audio::gain{master} -> f32 -> s16
 
 Sessions are the unit of sharding: every session's streams live on one GPU, no collective.
 This is what a frame-batching layer does each tick: gather all sessions' 20 ms frames into one pinned
 arena, one submit, scatter the s16 results.
+
+Input kinds per input index: `in_rate` may be a list (one rate per input of a session); a rate equal to
+48000 is a BYPASS input (the reference's resampler forwards such packets untouched, resampler.rs:299-373); `s16` (bool or
+list) makes an input arrive as interleaved s16 on PCIe (x = s / 32768).
 """
 from __future__ import annotations
 
@@ -24,18 +28,28 @@ def _align(x: int, a: int = 256) -> int:
 
 
 class ChainTick:
-    def __init__(self, n_sessions: int, k_inputs: int, in_rate: int = 44100, channels: int = 2, device: int = 0,
-                 seed: int = 0, chunk_frames: int | None = None, fused: bool = True, out_frames: int = OUT_FRAMES, alloc_host: bool = True):
+    def __init__(self, n_sessions: int, k_inputs: int, in_rate=44100, channels: int = 2, device: int = 0,
+                 seed: int = 0, chunk_frames: int | None = None, fused: bool = True, out_frames: int = OUT_FRAMES, alloc_host: bool = True,
+                 s16=False, out_rate: int = OUT_RATE):
         """fused=True: one k_chain launch per tick (double-banked input, lagged recompute, no HBM intermediates);
         fused=False: the general unfused ops (k_resample -> device re-framing ring -> k_mix)."""
         self.fused = fused
         self.F = out_frames   # output_frame_size of the resampler nodes = frame_samples_per_channel of the clocked mixer
         self.S, self.K, self.C = n_sessions, k_inputs, channels
-        self.in_rate = in_rate
-        self.chunk = chunk_frames if chunk_frames is not None else in_rate // 50  # frames per 20 ms tick
+        self.out_rate = out_rate
+        rates = list(in_rate) if isinstance(in_rate, (list, tuple)) else [in_rate] * k_inputs
+        fmts = list(s16) if isinstance(s16, (list, tuple)) else [bool(s16)] * k_inputs
+        assert len(rates) == k_inputs and len(fmts) == k_inputs
+        self.rates, self.fmts = rates, fmts
+        self.in_rate = rates[0]
+        # frames per tick of every input index: a tick is F / out_rate seconds
+        self.chunks = [chunk_frames if chunk_frames is not None else r * out_frames // out_rate for r in rates]
+        self.chunk = self.chunks[0]
         self.n_streams = n_sessions * k_inputs
         self.ctx = L.Context(device=device, max_streams=self.n_streams, max_channels=channels, fifo_frames=0 if fused else 2048)
-        self.in_stride = _align(self.chunk * channels * 4, 16)
+        # one arena row per stream; the row stride is the largest chunk of the session shape (+ 16 bytes of slack after s16 rows)
+        self.row_bytes = [c * channels * (2 if f else 4) for c, f in zip(self.chunks, fmts)]
+        self.in_stride = _align(max(b + (16 if f else 0) for b, f in zip(self.row_bytes, fmts)), 16)
         self.out_stride = self.F * channels * 2
         self.in_bytes = self.n_streams * self.in_stride
         self.bank_stride = _align(self.in_bytes) if fused else 0
@@ -49,7 +63,9 @@ class ChainTick:
         self.in_gains = synth.gains(seed, self.n_streams, 0.25, 1.5)
         self.master_gains = synth.gains(seed + 1, n_sessions, 0.5, 2.0)
         self.plan.set_gains(np.concatenate([self.in_gains, self.master_gains]))
-        slots = self.ctx.stream_open_many(in_rate, OUT_RATE, self.chunk, channels, self.n_streams)
+        slots = np.zeros(self.n_streams, dtype=np.uint32)
+        for i in range(k_inputs):   # stream (session s, input i) = s * K + i
+            slots[i::k_inputs] = self.ctx.stream_open_many(rates[i], out_rate, self.chunks[i], channels, n_sessions, L.STREAM_S16 if fmts[i] else 0)
         self.slots = slots
         if fused:
             self.plan.set_io(0, self.in_bytes, self.out_off, self.out_bytes)
@@ -73,6 +89,7 @@ class ChainTick:
                 self.host_in = self.ctx.pinned(self.in_bytes, np.float32)
                 self.host_out = self.ctx.pinned(self.out_bytes, np.int16)
             return
+        assert not any(fmts) and all(r != out_rate for r in rates), "the unfused ops take f32 chunks of resampled streams"
         items = np.zeros(self.n_streams, dtype=L.RS_ITEM_DT)
         items["in_off"] = np.arange(self.n_streams, dtype=np.uint64) * self.in_stride
         items["slot"] = slots
@@ -98,15 +115,24 @@ class ChainTick:
         self.host_in = self.ctx.pinned(self.in_bytes, np.float32)
         self.host_out = self.ctx.pinned(self.out_bytes, np.int16)
 
-    # algorithmic bytes: per session-tick K*(in + state r/w) + s16 out
+    # algorithmic bytes: per session-tick K*(in + state r/w) + s16 out; a bypass input has no resampler state
     def algorithmic_bytes_per_tick(self) -> int:
-        per_stream = self.in_stride + 2 * (8 + 16 * self.C * 4)
-        return self.S * (self.K * per_stream + self.out_stride)
+        per_session = sum(b + (0 if r == self.out_rate else 2 * (8 + 16 * self.C * 4)) for b, r in zip(self.row_bytes, self.rates))
+        return self.S * (per_session + self.out_stride)
 
-    def tick(self, inputs: np.ndarray, flags: int = 0) -> np.ndarray:
-        """inputs: float32 [n_streams, chunk*channels]; returns int16 [n_sessions, 960*channels]"""
-        x = np.ascontiguousarray(inputs, dtype=np.float32).reshape(self.n_streams, -1)
-        self.host_in.reshape(self.n_streams, self.in_stride // 4)[:, : x.shape[1]] = x
+    def fill_rows(self, host_in: np.ndarray, inputs):
+        """inputs: per input index i an array [n_sessions, chunk_i * channels] (float32, or int16 for s16 inputs) -- or one
+        float32 array [n_streams, chunk * channels] when every input has the same shape"""
+        rows = host_in.view(np.uint8).reshape(self.n_streams, self.in_stride)
+        if isinstance(inputs, np.ndarray):
+            inputs = [inputs.reshape(self.S, self.K, -1)[:, i] for i in range(self.K)]
+        for i, x in enumerate(inputs):
+            x = np.ascontiguousarray(x, dtype=np.int16 if self.fmts[i] else np.float32).reshape(self.S, -1)
+            rows[i::self.K, : self.row_bytes[i]] = x.view(np.uint8).reshape(self.S, -1)
+
+    def tick(self, inputs, flags: int = 0) -> np.ndarray:
+        """inputs: see fill_rows; returns int16 [n_sessions, F*channels]"""
+        self.fill_rows(self.host_in, inputs)
         self.plan.submit(self.host_in, self.host_out, flags)
         self.plan.wait()
         return self.host_out.reshape(self.S, self.F * self.C).copy()

@@ -35,14 +35,16 @@ struct __align__(16) SlotRec {  // everything a kernel needs to know about one r
     uint16_t n_runs[2];
     int32_t end_idx;       // chunk - 9 - ceil(t)                                   (host config)
     uint32_t overflow;     // bit (chunk number & 1): phase table overflowed
-    uint32_t pad;
+    uint32_t flags;        // SLOT_*                                                (host config)
 };
+constexpr uint32_t SLOT_BYPASS = 1u, SLOT_S16 = 2u;
 static_assert(sizeof(SlotRec) == 64, "SlotRec must be one 64-byte record");
 
 struct SlotCfgUpload {     // host -> device (re)configuration of one slot (k_config_slots)
     double t_ratio;
     uint32_t slot, chunk, channels;
     int32_t end_idx;
+    uint32_t flags, pad;
 };
 
 constexpr uint32_t SK_SIDE_STRIDE = 2048u;   // >= sizeof(SkPhaseTable); fused chain: frame program (<= 1920 B) + 128 B history
@@ -232,7 +234,7 @@ __global__ void k_config_slots(const SlotCfgUpload *__restrict__ cfgs, uint32_t 
         r.n_runs[0] = r.n_runs[1] = 0;
         r.end_idx = c.end_idx;
         r.overflow = 0;
-        r.pad = 0;
+        r.flags = c.flags;
         st.rec[slot] = r;
         if (st.fifo_w) { st.fifo_w[slot] = 0ull; st.fifo_r[slot] = 0ull; }
     }

@@ -47,9 +47,13 @@ constexpr int CH_MAX_KB = 4;                      // inputs staged per batch
 constexpr int CH_PF = 8;                          // inputs per session whose records the producer prefetches (more: general path)
 constexpr uint32_t CH_PROG_MAX = SK_SIDE_STRIDE - SK_SIDE_HIST;   // side record = [frame program (prog_cap bytes) | 128-byte history field]
 
-struct __align__(8) ChainCons {   // what a consumer needs per input
+constexpr uint32_t CK_BYPASS = 0x100u, CK_S16 = 0x200u;   // ChainCons.sc kind bits
+struct __align__(16) ChainCons {   // what a consumer needs per input
     float gain;             // 1.0 when the input has no audio::gain in front of the mixer (x * 1.0 == x)
-    uint32_t sc;            // source channels
+    uint32_t sc;            // source channels (low byte) | CK_BYPASS: the staged chunk IS the packet (resampler.rs:299-373)
+                            //                            | CK_S16: the staged chunk is s16, expand it in place before use
+    uint32_t n_prev;        // s16: samples of the first staged piece (previous chunk; bypass: the packet)
+    uint32_t n_head;        // s16: samples of the second staged piece (head of the current chunk)
 };
 
 // per-input record written by k_phase_chain every tick, consumed by k_chain's producer (64 bytes, one per chain input):
@@ -61,11 +65,10 @@ struct __align__(16) ChainRec {
     const float *prev_g;      // previous chunk (other input bank)
     const float *cur_g;       // current chunk
     float *hist_dst;          // where the last 16 frames of the previous chunk go (history field of the current chunk's record)
-    uint32_t chunk_bytes;     // N * channels * 4
+    uint32_t chunk_bytes;     // bytes of the first staged piece (s16 streams: padded to whole 16-byte units)
     uint32_t head_bytes;      // staged frames of the current chunk, bytes
     uint32_t flags;           // CR_*
     uint32_t tail_off;        // (N - 16) * channels: float offset of those 16 frames inside the chunk
-    uint32_t pad[2];
 };
 static_assert(sizeof(ChainRec) == 64, "ChainRec is one 64-byte record");
 
@@ -94,7 +97,7 @@ struct ChainDims {          // launch-time geometry of the staging ring (host: c
     ChainProgDims prog;     // frame-program capacities
     uint32_t nstages;
     uint32_t max_k;         // largest n_inputs of any session (sizes the producer scratch)
-    uint32_t debug;         // profiling only: bit0 = consumers skip the arithmetic (isolates the load pipeline)
+    uint32_t reserved;
     float one;              // 1.0f, deliberately a run-time value (see add2)
 };
 // shared-memory slot of one staged input:  [frame program | history field 128 B | previous chunk | head of current]
@@ -165,6 +168,63 @@ __device__ __forceinline__ unsigned long long chain_split_slow(double x, uint32_
 // acc += v (packed f32x2, in place; see add2 for the fma-with-one form)
 __device__ __forceinline__ void acc_add(unsigned long long &acc, unsigned long long v, unsigned long long one2) {
     asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(v), "l"(one2));
+}
+
+// one frame of a BYPASS input (input rate == mixer rate): the frame enters the mix as it is -- the input's audio::gain and
+// the mixer's channel mapping only; no interpolation arithmetic (resampler.rs:299-373 forwards such packets untouched)
+template <int OC, int SC>
+__device__ __forceinline__ unsigned long long chain_pass(uint32_t addr, float gain) {
+    if (SC == 2) {
+        unsigned long long y;
+        asm volatile("ld.shared.b64 %0, [%1];" : "=l"(y) : "r"(addr));
+        const unsigned long long r = mul2(y, gain);
+        if (OC == 2) return r;
+        float a, b;
+        unpack2(r, a, b);
+        return pack2(__fmul_rn(__fadd_rn(a, b), 0.5f), 0.0f);   // stereo -> mono: average
+    } else {
+        const float v = __fmul_rn(lds_f32(addr), gain);
+        return pack2(v, OC == 2 ? v : 0.0f);                    // mono -> stereo: duplicate
+    }
+}
+template <int OC, int SC, int ITERS>
+__device__ __forceinline__ void chain_consume_pass(unsigned long long (&acc)[ITERS][CH_NB], uint32_t a_chunk, uint32_t F, uint32_t cw, uint32_t lane,
+                                                   float gain, unsigned long long one2) {
+#pragma unroll
+    for (int it = 0; it < ITERS; ++it) {
+#pragma unroll
+        for (int f = 0; f < CH_NB; ++f) {
+            const uint32_t jb = (((uint32_t)it * CH_CWARPS + cw) * CH_NB + (uint32_t)f) * 32u;
+            if (jb < F) acc_add(acc[it][f], chain_pass<OC, SC>(a_chunk + min(jb + lane, F - 1u) * (SC * 4u), gain), one2);
+        }
+    }
+}
+
+// s16 ingest (SKGPU_STREAM_S16): the staged pieces are s16 (x = s / 32768, exact); the four consumer warps expand them to f32 in
+// place before the input is consumed. All reads of a round happen before its writes (named barrier), rounds run from the top
+// down, so the growing f32 image never overwrites s16 samples that are still unread.
+__device__ __forceinline__ void chain_expand_s16(uint32_t chunk_sm, uint32_t n_prev, uint32_t n_head, uint32_t ct) {
+    const uint32_t off_head = (n_prev * 2u + 15u) & ~15u;      // the head piece starts on the next 16-byte unit
+    const uint32_t T = n_prev + n_head;                         // both even
+    for (int r = (int)((T + 2047u) / 2048u) - 1; r >= 0; --r) {
+        uint32_t w[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const uint32_t idx = (((uint32_t)r * CH_CONSUMERS + ct) * 8u + (uint32_t)k) * 2u;
+            w[k] = 0u;
+            if (idx < T) asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w[k]) : "r"(chunk_sm + (idx < n_prev ? idx * 2u : off_head + (idx - n_prev) * 2u)));
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(CH_CONSUMERS) : "memory");
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const uint32_t idx = (((uint32_t)r * CH_CONSUMERS + ct) * 8u + (uint32_t)k) * 2u;
+            if (idx < T) {
+                const float lo = s16_to_f32((int)(short)(w[k] & 0xFFFFu)), hi = s16_to_f32((int)w[k] >> 16);
+                asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(chunk_sm + idx * 4u), "f"(lo), "f"(hi) : "memory");
+            }
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(CH_CONSUMERS) : "memory");
+    }
 }
 
 // run cache of a consumer warp (registers, warp-uniform except xl): the FAST run segment the warp is inside of
@@ -351,6 +411,28 @@ __global__ void __launch_bounds__(PHASE_CHAIN_THREADS, 14) k_phase_chain(const O
     SlotRec rec = *recp;
     const bool pres = present ? (present[i] != 0) : true;
     const uint32_t ch = rec.channels, N = rec.chunk, fb = ch * 4u;
+    const bool s16 = (rec.flags & SLOT_S16) != 0;
+    const uint32_t sbytes = s16 ? ch * 2u : fb;          // bytes of one frame in the input arena
+    const uint32_t parity = tick[0] & 1u;
+    const uint8_t *cur_b = arena + in.in_off + (uint64_t)parity * bank_stride;
+    const uint8_t *prev_b = arena + in.in_off + (uint64_t)(1u - parity) * bank_stride;
+    const float gain = in.gain_idx != SKGPU_NO_GAIN ? gains[in.gain_idx] : 1.0f;
+    uint32_t *dst = reinterpret_cast<uint32_t *>(recs + i);
+    if (rec.flags & SLOT_BYPASS) {
+        // ---- input rate == mixer rate: no resampler state, no program; this tick's chunk is the packet (resampler.rs:299-373)
+        skgpu_chain_result res;
+        res.emitted = pres ? 1u : 0u;
+        res.status = 0;
+        reinterpret_cast<skgpu_chain_result *>(arena + results_off)[i] = res;
+        const uint64_t a_prog = (uint64_t)(uintptr_t)slot_side(st, slot, 0), a_cur = (uint64_t)(uintptr_t)cur_b;
+        const uint32_t bytes = (N * sbytes + 15u) & ~15u;
+        const uint32_t flags = (pres ? CR_EMIT : 0u) | ((in.flags & SKGPU_MIX_IN_UNIQUE) ? CR_UNIQUE : 0u) | (((N * sbytes) & 15u) && !s16 ? CR_UNALIGNED : 0u);
+        asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(dst), "r"(__float_as_uint(gain)), "r"(ch | CK_BYPASS | (s16 ? CK_S16 : 0u)),
+                     "r"(N * ch), "r"(0u), "r"((uint32_t)a_prog), "r"((uint32_t)(a_prog >> 32)), "r"((uint32_t)a_cur), "r"((uint32_t)(a_cur >> 32)) : "memory");
+        asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(dst + 8), "r"((uint32_t)a_cur), "r"((uint32_t)(a_cur >> 32)), "r"((uint32_t)a_prog),
+                     "r"((uint32_t)(a_prog >> 32)), "r"(s16 ? bytes : N * sbytes), "r"(0u), "r"(flags), "r"(0u) : "memory");
+        return;
+    }
     const uint32_t head = min((uint32_t)CH_HEAD, N);
     // slot record fields reused by the chain op: n_prefix[par] = explicit entries of the record's part 1, n_runs[par] = segments
     const uint32_t count0 = rec.chunk_count;
@@ -398,34 +480,38 @@ __global__ void __launch_bounds__(PHASE_CHAIN_THREADS, 14) k_phase_chain(const O
         asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(rw), "r"(__double2loint(rec.t_ratio)), "r"(__double2hiint(rec.t_ratio)),
                      "r"(__double2loint(li)), "r"(__double2hiint(li)), "r"(rec.chunk), "r"(rec.channels), "r"(count0 + 1u), "r"(new_carry) : "memory");
         asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(rw + 8), "r"(n_out0), "r"(n_out1), "r"(np01), "r"(nr01),
-                     "r"((uint32_t)rec.end_idx), "r"(ovfl), "r"(0u), "r"(0u) : "memory");
+                     "r"((uint32_t)rec.end_idx), "r"(ovfl), "r"(rec.flags), "r"(0u) : "memory");
     }
     skgpu_chain_result res;
     res.emitted = emit;
     res.status = status;
     reinterpret_cast<skgpu_chain_result *>(arena + results_off)[i] = res;
 
-    const uint32_t parity = tick[0] & 1u;
-    const float *cur_g = reinterpret_cast<const float *>(arena + in.in_off + (uint64_t)parity * bank_stride);
-    const float *prev_g = reinterpret_cast<const float *>(arena + in.in_off + (uint64_t)(1u - parity) * bank_stride);
+    const float *cur_g = reinterpret_cast<const float *>(cur_b);
+    const float *prev_g = reinterpret_cast<const float *>(prev_b);
     // a present input that emits nothing still retires its previous chunk: the history before the current chunk
     // (= last 16 frames of the previous one) goes into the current chunk's side record. Emitting inputs get it from
     // k_chain's consumers, which have the previous chunk in shared memory anyway.
     const uint32_t prog_cap = skc_prog_cap(dm.prog);
     float *hist_dst = reinterpret_cast<float *>(slot_side(st, slot, par_new) + prog_cap + SK_SIDE_HIST) - 16u * ch;
     if (pres && !emit && count0 >= 1u) {
-        for (uint32_t e = 0; e < 16u * ch; ++e) hist_dst[e] = prev_g[(size_t)(N - 16u) * ch + e];
+        if (s16) {
+            const short *ps = reinterpret_cast<const short *>(prev_b);
+            for (uint32_t e = 0; e < 16u * ch; ++e) hist_dst[e] = s16_to_f32((int)ps[(size_t)(N - 16u) * ch + e]);
+        } else {
+            for (uint32_t e = 0; e < 16u * ch; ++e) hist_dst[e] = prev_g[(size_t)(N - 16u) * ch + e];
+        }
     }
     // the 64-byte ChainRec, written with two 256-bit stores (the kernel is bound by scattered store requests)
-    const float gain = in.gain_idx != SKGPU_NO_GAIN ? gains[in.gain_idx] : 1.0f;
     const uint64_t a_prog = (uint64_t)(uintptr_t)slot_side(st, slot, par_old), a_prev = (uint64_t)(uintptr_t)prev_g,
                    a_cur = (uint64_t)(uintptr_t)cur_g, a_hist = (uint64_t)(uintptr_t)hist_dst;
-    const uint32_t flags = (emit ? CR_EMIT : 0u) | ((in.flags & SKGPU_MIX_IN_UNIQUE) ? CR_UNIQUE : 0u) | ((((N * fb) | (head * fb)) & 15u) ? CR_UNALIGNED : 0u);
-    uint32_t *dst = reinterpret_cast<uint32_t *>(recs + i);
-    asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(dst), "r"(__float_as_uint(gain)), "r"(ch), "r"((uint32_t)a_prog),
-                 "r"((uint32_t)(a_prog >> 32)), "r"((uint32_t)a_prev), "r"((uint32_t)(a_prev >> 32)), "r"((uint32_t)a_cur), "r"((uint32_t)(a_cur >> 32)) : "memory");
-    asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(dst + 8), "r"((uint32_t)a_hist), "r"((uint32_t)(a_hist >> 32)), "r"(N * fb),
-                 "r"(head * fb), "r"(flags), "r"((N - 16u) * ch), "r"(0u), "r"(0u) : "memory");
+    // staged pieces: previous chunk, head of the current one (s16 streams: copied in whole 16-byte units)
+    const uint32_t cb = s16 ? ((N * sbytes + 15u) & ~15u) : N * fb, hb = s16 ? ((head * sbytes + 15u) & ~15u) : head * fb;
+    const uint32_t flags = (emit ? CR_EMIT : 0u) | ((in.flags & SKGPU_MIX_IN_UNIQUE) ? CR_UNIQUE : 0u) | (((cb | hb) & 15u) ? CR_UNALIGNED : 0u);
+    asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(dst), "r"(__float_as_uint(gain)), "r"(ch | (s16 ? CK_S16 : 0u)), "r"(N * ch), "r"(head * ch),
+                 "r"((uint32_t)a_prog), "r"((uint32_t)(a_prog >> 32)), "r"((uint32_t)a_prev), "r"((uint32_t)(a_prev >> 32)) : "memory");
+    asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(dst + 8), "r"((uint32_t)a_cur), "r"((uint32_t)(a_cur >> 32)), "r"((uint32_t)a_hist),
+                 "r"((uint32_t)(a_hist >> 32)), "r"(cb), "r"(hb), "r"(flags), "r"((N - 16u) * ch) : "memory");
 }
 
 // OC output channels (1 | 2); ITERS = ceil(F / 1024); UNIFORM: every input of the op has OC channels (the common case gets a
@@ -484,7 +570,7 @@ __global__ void __launch_bounds__(CH_THREADS, 5) k_chain(const OpHeader *__restr
         auto stage_input = [&](const ChainRec &r, uint32_t q, ChainStage *S, uint8_t *sm, uint64_t *bar) -> uint32_t {
             S->cons[q] = r.cons;
             ChainTail tl;
-            tl.hist_dst = r.hist_dst; tl.tail_off = r.tail_off; tl.n = 16u * r.cons.sc;
+            tl.hist_dst = r.hist_dst; tl.tail_off = r.tail_off; tl.n = (r.cons.sc & CK_BYPASS) ? 0u : 16u * (r.cons.sc & 0xFFu);
             S->tail[q] = tl;
             uint8_t *slot_sm = sm + (size_t)q * in_bytes;
             uint8_t *chunk_sm = slot_sm + prog_cap + SK_SIDE_HIST;
@@ -493,7 +579,7 @@ __global__ void __launch_bounds__(CH_THREADS, 5) k_chain(const OpHeader *__restr
             tma_bulk_g2s(slot_sm, r.prog_src, prog_cap + SK_SIDE_HIST, bar);   // frame program + the 16 frames before the previous chunk
             if (!(r.flags & CR_UNALIGNED)) {
                 tma_bulk_g2s(chunk_sm, r.prev_g, cb, bar);
-                tma_bulk_g2s(chunk_sm + cb, r.cur_g, hb, bar);
+                if (hb) tma_bulk_g2s(chunk_sm + cb, r.cur_g, hb, bar);
                 bytes += cb + hb;
             } else {   // chunk size not a multiple of 16 bytes (e.g. mono 882 frames): no bulk copy, this lane copies
                 float *dst = reinterpret_cast<float *>(chunk_sm);
@@ -528,14 +614,14 @@ __global__ void __launch_bounds__(CH_THREADS, 5) k_chain(const OpHeader *__restr
             if (lane < min(K, (uint32_t)CH_PF)) r = pf_rec[n & 1u][lane];
             else if (lane < min(K, 32u)) r = recs[grp.first_input + lane];   // big sessions: straight from HBM
             const bool emit = (r.flags & CR_EMIT) != 0;
-            const bool elig = emit && r.cons.sc == (uint32_t)OC;   // packet already has the output shape
+            const bool elig = emit && (r.cons.sc & 0xFFu) == (uint32_t)OC;   // packet already has the output shape
             // ---- summation order over the inputs that deliver a packet: base selection + swap_remove (mixer.rs:960-980),
             // computed by every lane from three ballots
             const uint32_t emit_mask = __ballot_sync(0xffffffffu, emit);
             const uint32_t elig_mask = __ballot_sync(0xffffffffu, elig);
             const uint32_t uniq_mask = __ballot_sync(0xffffffffu, elig && (r.flags & CR_UNIQUE));
             const uint32_t unal_mask = __ballot_sync(0xffffffffu, emit && (r.flags & CR_UNALIGNED));
-            const uint32_t mono_mask = __ballot_sync(0xffffffffu, emit && r.cons.sc != 2u);
+            const uint32_t mono_mask = __ballot_sync(0xffffffffu, emit && (r.cons.sc & 0xFFu) != 2u);
             uint32_t m = __popc(emit_mask);
             if (K <= (uint32_t)CH_PF && m <= kb && unal_mask == 0u) {
                 // ---- common path. max_by_key((unique, idx)): the last unique full-shape frame, else the last full-shape frame
@@ -552,7 +638,7 @@ __global__ void __launch_bounds__(CH_THREADS, 5) k_chain(const OpHeader *__restr
                 if (emit) {   // the lanes fill the consumer-side records of their inputs in parallel
                     S->cons[pos] = r.cons;
                     ChainTail tl;
-                    tl.hist_dst = r.hist_dst; tl.tail_off = r.tail_off; tl.n = 16u * r.cons.sc;
+                    tl.hist_dst = r.hist_dst; tl.tail_off = r.tail_off; tl.n = (r.cons.sc & CK_BYPASS) ? 0u : 16u * (r.cons.sc & 0xFFu);
                     S->tail[pos] = tl;
                     s_order[pos] = (uint8_t)lane;
                 }
@@ -567,7 +653,7 @@ __global__ void __launch_bounds__(CH_THREADS, 5) k_chain(const OpHeader *__restr
                         const uint32_t cb = rr->chunk_bytes, hb = rr->head_bytes;
                         tma_bulk_g2s(dst, rr->prog_src, prog_cap + SK_SIDE_HIST, &bar_full[stage]);
                         tma_bulk_g2s(dst + prog_cap + SK_SIDE_HIST, rr->prev_g, cb, &bar_full[stage]);
-                        tma_bulk_g2s(dst + prog_cap + SK_SIDE_HIST + cb, rr->cur_g, hb, &bar_full[stage]);
+                        if (hb) tma_bulk_g2s(dst + prog_cap + SK_SIDE_HIST + cb, rr->cur_g, hb, &bar_full[stage]);
                         bytes += prog_cap + SK_SIDE_HIST + cb + hb;
                     }
                     mbar_expect_tx(&bar_full[stage], bytes);   // arrive: the smem writes above are ordered before it
@@ -584,7 +670,7 @@ __global__ void __launch_bounds__(CH_THREADS, 5) k_chain(const OpHeader *__restr
                     int base = -1, base_unique = -1;
                     for (uint32_t j = 0; j < K; ++j) {
                         if (!(s_res[j].flags & CR_EMIT)) continue;
-                        if (s_res[j].cons.sc == (uint32_t)OC) {
+                        if ((s_res[j].cons.sc & 0xFFu) == (uint32_t)OC) {
                             const int u = (s_res[j].flags & CR_UNIQUE) ? 1 : 0;
                             if (u >= base_unique) { base = (int)m; base_unique = u; }
                         }
@@ -651,7 +737,7 @@ __global__ void __launch_bounds__(CH_THREADS, 5) k_chain(const OpHeader *__restr
         const uint4 hd = *reinterpret_cast<const uint4 *>(&S->nb);   // nb, first, last, has_base (one broadcast load)
         if (S->stop) break;
         const uint32_t sm = smem_u32(smem_raw) + stage * stage_bytes;
-        const uint32_t nb = (dm.debug & 1u) ? 0u : hd.x;
+        const uint32_t nb = hd.x;
         const uint32_t cw = (warp - 1u + (hd.w >> 8)) & (CH_CWARPS - 1u);   // this session's block group of the warp
         if (hd.y != 0) {
             // the base frame IS the accumulator (mixer.rs:969-972): start from -0.0, the additive identity of every f32
@@ -662,17 +748,19 @@ __global__ void __launch_bounds__(CH_THREADS, 5) k_chain(const OpHeader *__restr
 #pragma unroll
                 for (int f = 0; f < CH_NB; ++f) acc[it][f] = init;
         }
-        if (UNIFORM) {
-            for (uint32_t q = 0; q < nb; ++q) {
-                const uint32_t prog = sm + q * in_bytes;
-                chain_consume<OC, OC, ITERS>(acc, prog, prog + prog_cap + (OC == 2 ? 0u : SK_SIDE_HIST - 64u), dm.prog, F, cw, lane, S->cons[q].gain, one2);
-            }
-        } else {
-            for (uint32_t q = 0; q < nb; ++q) {
-                const ChainCons c = S->cons[q];
-                const uint32_t prog = sm + q * in_bytes;
-                if (c.sc == 2u) chain_consume<OC, 2, ITERS>(acc, prog, prog + prog_cap, dm.prog, F, cw, lane, c.gain, one2);
-                else chain_consume<OC, 1, ITERS>(acc, prog, prog + prog_cap + SK_SIDE_HIST - 64u, dm.prog, F, cw, lane, c.gain, one2);
+        for (uint32_t q = 0; q < nb; ++q) {
+            const ChainCons c = S->cons[q];
+            const uint32_t prog = sm + q * in_bytes, a_chunk = prog + prog_cap + SK_SIDE_HIST;   // program record; staged chunk pieces
+            if (c.sc & CK_S16) chain_expand_s16(a_chunk, c.n_prev, c.n_head, ct);
+            if (UNIFORM) {
+                if (c.sc & CK_BYPASS) chain_consume_pass<OC, OC, ITERS>(acc, a_chunk, F, cw, lane, c.gain, one2);
+                else chain_consume<OC, OC, ITERS>(acc, prog, a_chunk - 16u * OC * 4u, dm.prog, F, cw, lane, c.gain, one2);
+            } else if ((c.sc & 0xFFu) == 2u) {
+                if (c.sc & CK_BYPASS) chain_consume_pass<OC, 2, ITERS>(acc, a_chunk, F, cw, lane, c.gain, one2);
+                else chain_consume<OC, 2, ITERS>(acc, prog, a_chunk - 128u, dm.prog, F, cw, lane, c.gain, one2);
+            } else {
+                if (c.sc & CK_BYPASS) chain_consume_pass<OC, 1, ITERS>(acc, a_chunk, F, cw, lane, c.gain, one2);
+                else chain_consume<OC, 1, ITERS>(acc, prog, a_chunk - 64u, dm.prog, F, cw, lane, c.gain, one2);
             }
         }
         if (hd.z != 0) {

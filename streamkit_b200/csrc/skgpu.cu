@@ -73,7 +73,7 @@ struct skgpu_ctx {
     // host mirrors of slot configuration
     std::vector<double> h_t;
     std::vector<int32_t> h_end;
-    std::vector<uint32_t> h_chunk, h_ch;
+    std::vector<uint32_t> h_chunk, h_ch, h_flags;   // h_flags: SLOT_*
     std::vector<uint8_t> used;
     std::vector<uint32_t> free_list;
     uint32_t next_fresh = 0;
@@ -102,6 +102,8 @@ static skgpu_rc ctx_flush(skgpu_ctx *c) {
             up[i].chunk = c->h_chunk[slot];
             up[i].channels = c->h_ch[slot];
             up[i].end_idx = c->h_end[slot];
+            up[i].flags = c->h_flags[slot];
+            up[i].pad = 0;
         }
         if (n > c->d_reset_cap) {
             if (c->d_reset) cudaFree(c->d_reset);
@@ -167,6 +169,7 @@ extern "C" skgpu_rc skgpu_ctx_create(int32_t device_ordinal, const skgpu_ctx_con
     c->h_end.assign(S, 0);
     c->h_chunk.assign(S, 0);
     c->h_ch.assign(S, 0);
+    c->h_flags.assign(S, 0);
     c->used.assign(S, 0);
     *out = c;
     return SKGPU_OK;
@@ -318,6 +321,9 @@ static skgpu_rc validate_stream_cfg(const skgpu_ctx *c, const skgpu_stream_cfg *
     if (s->chunk_frames > (1u << 20)) return fail(SKGPU_ERR_INVALID, "chunk_frames too large");
     if (s->channels == 0 || s->channels > c->cfg.max_channels)
         return fail(SKGPU_ERR_INVALID, "channels %u outside 1..%u", (unsigned)s->channels, c->cfg.max_channels);
+    if (s->flags & ~(uint32_t)SKGPU_STREAM_S16) return fail(SKGPU_ERR_INVALID, "unknown stream flags 0x%x", (unsigned)s->flags);
+    if ((s->flags & SKGPU_STREAM_S16) && (((uint64_t)s->chunk_frames * s->channels) % 2u || (uint64_t)(s->chunk_frames + 32u) * s->channels > 4096u || s->channels > 2))
+        return fail(SKGPU_ERR_INVALID, "s16 streams need mono / stereo chunks of an even number of samples, at most 4096 samples with the 32-frame head");
     const double ratio = (double)s->out_rate / (double)s->in_rate;
     if (!(ratio >= 1.0 / 256.0 && ratio <= 256.0)) return fail(SKGPU_ERR_INVALID, "resample ratio %g outside [1/256, 256]", ratio);
     return SKGPU_OK;
@@ -330,6 +336,7 @@ static void slot_configure(skgpu_ctx *c, uint32_t slot, const skgpu_stream_cfg *
     c->h_end[slot] = (int32_t)s->chunk_frames - 9 - (int32_t)std::ceil(t);  // chunk - (POLYNOMIAL_LEN + 1) - ceil(t)
     c->h_chunk[slot] = s->chunk_frames;
     c->h_ch[slot] = s->channels;
+    c->h_flags[slot] = (s->in_rate == s->out_rate ? SLOT_BYPASS : 0u) | ((s->flags & SKGPU_STREAM_S16) ? SLOT_S16 : 0u);
     c->used[slot] = 1;
     c->reset_list.push_back(slot);
 }
@@ -655,6 +662,8 @@ static skgpu_rc validate_rs(const skgpu_plan *p, const skgpu_rs_item *items, uin
         const uint32_t slot = items[i].slot;
         if (slot >= c->cfg.max_streams || !c->used[slot]) return fail(SKGPU_ERR_INVALID, "resample item %u: slot %u is not open", i, slot);
         const uint32_t N = c->h_chunk[slot], C = c->h_ch[slot];
+        if (c->h_flags[slot] & SLOT_BYPASS) return fail(SKGPU_ERR_INVALID, "resample item %u: the stream's input rate equals its target rate: the reference bypasses the resampler for such inputs (resampler.rs:299-373); mix them directly or use the chain op", i);
+        if (c->h_flags[slot] & SLOT_S16) return fail(SKGPU_ERR_INVALID, "resample item %u: s16 streams are a chain-op feature (convert with SKGPU_CVT_S16_TO_F32 first)", i);
         skgpu_rc rc = check_range(p, items[i].in_off, (uint64_t)N * C * 4, "resample input");
         if (rc) return rc;
         if (items[i].in_off % 4) return fail(SKGPU_ERR_INVALID, "resample item %u: misaligned input", i);
@@ -737,7 +746,9 @@ static void rs_size_smem(const skgpu_ctx *c, Op &op) {
     // the program-driven kernels need the staged path and mono / stereo streams
     if (op.rs_prog && (op.smem_frames == 0 || (op.rs_channels != 1 && op.rs_channels != 2))) op.rs_prog = false;
     if (op.rs_prog) op.smem_bytes += skc_prog_cap(op.rs_pd);
+#ifdef SKGPU_TUNING_KNOBS
     if (std::getenv("SKGPU_RS_TABLE")) op.rs_prog = false;   // profiling knob: force the table-driven kernels
+#endif
 }
 
 extern "C" skgpu_rc skgpu_plan_add_resample(skgpu_plan *p, const skgpu_rs_item *items, uint32_t n, uint64_t results_off, uint32_t *op_out) {
@@ -994,15 +1005,18 @@ static skgpu_rc validate_chain(const skgpu_plan *p, const skgpu_chain_group *g, 
         const uint32_t N = c->h_chunk[slot], C = c->h_ch[slot];
         if (C != 1 && C != 2) return fail(SKGPU_ERR_INVALID, "chain input %u: %u channels (the fused chain handles mono and stereo)", i, C);
         if (N < 16) return fail(SKGPU_ERR_INVALID, "chain input %u: chunk_frames %u < 16", i, N);
+        const bool bypass = (c->h_flags[slot] & SLOT_BYPASS) != 0, s16 = (c->h_flags[slot] & SLOT_S16) != 0;
         // nominal frames per chunk must equal the packet size: a packet then never spans more than two chunks
         const double nominal = (double)N / c->h_t[slot];
-        if (std::fabs(nominal - (double)F) > 0.5)
+        if (bypass ? N != F : std::fabs(nominal - (double)F) > 0.5)
             return fail(SKGPU_ERR_INVALID, "chain input %u: chunk of %u frames yields %.2f output frames, not output_frame_size %u (use the unfused ops)", i, N, nominal, F);
         if (in[i].in_off % 16) return fail(SKGPU_ERR_INVALID, "chain input %u: in_off must be 16-byte aligned", i);
-        skgpu_rc rc = check_range(p, in[i].in_off + p->bank_stride, (uint64_t)N * C * 4, "chain input (bank 1)");
+        // s16 chunks are copied in whole 16-byte units: up to 16 bytes past the chunk's end are read (and ignored)
+        skgpu_rc rc = check_range(p, in[i].in_off + p->bank_stride, s16 ? (((uint64_t)N * C * 2 + 15u) & ~15ull) : (uint64_t)N * C * 4, "chain input (bank 1)");
         if (rc) return rc;
         if (in[i].gain_idx != SKGPU_NO_GAIN && in[i].gain_idx >= p->n_gains) return fail(SKGPU_ERR_INVALID, "chain input %u: gain_idx out of range", i);
-        mb = std::max(mb, (N + (uint32_t)CH_HEAD) * C * 4u);   // bytes: previous chunk + staged head of the current one
+        mb = std::max(mb, (N + (uint32_t)CH_HEAD) * C * 4u + 32u);   // bytes: previous chunk + staged head of the current one (+ s16 copy slack)
+        if (bypass) continue;                                        // no phase, no program
         if (c->h_t[slot] != last_t || c->h_end[slot] != last_end || N != last_N) {   // streams of one op usually share a handful of configurations
             uint32_t a = 0, b = 0;
             if (!prog_bounds(c->h_t[slot], c->h_end[slot], N, F, &a, &b))
@@ -1072,14 +1086,16 @@ static void chain_size_smem(Op &op, uint32_t max_k, uint32_t chunk_cap, uint32_t
         const uint64_t per_cta = stage * ns + scratch + static_smem + cta_overhead;
         if (per_cta * 4u <= sm_smem) best_ns = ns;
     }
-    if (const char *e = std::getenv("SKGPU_CHAIN_STAGES")) {   // tuning knob (profiling only)
+#ifdef SKGPU_TUNING_KNOBS   // never in the product build: environment variables must not change what the library computes or how
+    if (const char *e = std::getenv("SKGPU_CHAIN_STAGES")) {
         const int v = std::atoi(e);
         if (v >= 2 && v <= CH_MAX_STAGES) best_ns = (uint32_t)v;
     }
+#endif
     dm.kb = kb;
     dm.one = 1.0f;
     dm.nstages = best_ns;
-    dm.debug = std::getenv("SKGPU_CHAIN_DEBUG") ? (uint32_t)std::atoi(std::getenv("SKGPU_CHAIN_DEBUG")) : 0u;
+    dm.reserved = 0;
     op.chain_kb = kb;
     op.chain_buf_floats = chunk_cap;
     op.chain_dm = dm;
@@ -1168,6 +1184,10 @@ extern "C" skgpu_rc skgpu_plan_update_chain(skgpu_plan *p, uint32_t opi, const s
 
 // ---- slices
 
+static uint64_t chunk_bytes_of(const skgpu_ctx *c, uint32_t slot) {
+    return (uint64_t)c->h_chunk[slot] * c->h_ch[slot] * ((c->h_flags[slot] & SLOT_S16) ? 2u : 4u);
+}
+
 extern "C" skgpu_rc skgpu_plan_set_slices(skgpu_plan *p, uint32_t opi, const skgpu_slice *sl, uint32_t n) {
     if (!p || opi >= p->ops.size() || p->ops[opi].kind != OP_CHAIN) return fail(SKGPU_ERR_INVALID, "not a chain op");
     if (p->ops.size() != 1) return fail(SKGPU_ERR_INVALID, "sliced ticks need a plan whose only op is the chain op");
@@ -1199,7 +1219,7 @@ extern "C" skgpu_rc skgpu_plan_set_slices(skgpu_plan *p, uint32_t opi, const skg
         for (uint32_t q = i0; q < sl[k].input_end; ++q) {
             if (in[q].in_off < p->h2d_off) return fail(SKGPU_ERR_INVALID, "input %u lies below the H2D range", q);
             const uint64_t b0 = in[q].in_off - p->h2d_off;
-            const uint64_t b1 = b0 + (uint64_t)c->h_chunk[in[q].slot] * c->h_ch[in[q].slot] * 4u;
+            const uint64_t b1 = b0 + chunk_bytes_of(c, in[q].slot);
             if (b1 > sl[k].h2d_end) return fail(SKGPU_ERR_INVALID, "slice %u: input %u ends at byte %llu of the H2D range, beyond the slice's h2d_end %llu (sort the tables by input offset)", k, q, (unsigned long long)b1, (unsigned long long)sl[k].h2d_end);
             for (uint32_t u = 0; u <= k; ++u) {   // upload pieces [h2d_end[u-1], h2d_end[u]) the input overlaps
                 const uint64_t lo = u ? sl[u - 1].h2d_end : 0, hi = sl[u].h2d_end;
@@ -1248,7 +1268,7 @@ extern "C" skgpu_rc skgpu_plan_auto_slices(skgpu_plan *p, uint32_t opi, uint32_t
         }
         for (uint32_t q = i0; q < i1; ++q) {
             if (in[q].in_off < p->h2d_off) return fail(SKGPU_ERR_INVALID, "input %u lies below the H2D range", q);
-            up = std::max(up, in[q].in_off - p->h2d_off + (uint64_t)c->h_chunk[in[q].slot] * c->h_ch[in[q].slot] * 4u);
+            up = std::max(up, in[q].in_off - p->h2d_off + chunk_bytes_of(c, in[q].slot));
         }
         if (k + 1 == n) up = p->h2d_bytes;
         sl[k].group_end = g1; sl[k].input_end = i1; sl[k].h2d_end = std::min<uint64_t>(up, p->h2d_bytes);

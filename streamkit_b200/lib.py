@@ -21,6 +21,7 @@ MIX_IN_UNIQUE, MIX_IN_FIFO = 1, 2
 MIX_OUT_S16 = 1
 SUBMIT_NO_H2D, SUBMIT_NO_D2H, SUBMIT_GRAPH, SUBMIT_TIME_OPS, SUBMIT_OVERLAP_D2H, SUBMIT_SLICED = 1, 2, 4, 8, 16, 32
 PIN_NUMA_LOCAL, PIN_WRITE_COMBINED = 1, 2
+STREAM_S16 = 1
 
 
 class CtxConfig(C.Structure):
@@ -29,7 +30,7 @@ class CtxConfig(C.Structure):
 
 class StreamCfg(C.Structure):
     _fields_ = [("in_rate", C.c_uint32), ("out_rate", C.c_uint32), ("chunk_frames", C.c_uint32), ("channels", C.c_uint16),
-                ("reserved", C.c_uint16)]
+                ("flags", C.c_uint16)]
 
 
 class SliceTiming(C.Structure):
@@ -202,14 +203,14 @@ class Context:
         self._pinned.append((p, arr))
         return arr.view(dtype)
 
-    def stream_open(self, in_rate: int, out_rate: int, chunk_frames: int, channels: int) -> int:
-        cfg = StreamCfg(in_rate, out_rate, chunk_frames, channels, 0)
+    def stream_open(self, in_rate: int, out_rate: int, chunk_frames: int, channels: int, flags: int = 0) -> int:
+        cfg = StreamCfg(in_rate, out_rate, chunk_frames, channels, flags)
         slot = C.c_uint32()
         _chk(self.lib.skgpu_stream_open(self.h, C.byref(cfg), C.byref(slot)))
         return slot.value
 
-    def stream_open_many(self, in_rate: int, out_rate: int, chunk_frames: int, channels: int, n: int) -> np.ndarray:
-        cfg = StreamCfg(in_rate, out_rate, chunk_frames, channels, 0)
+    def stream_open_many(self, in_rate: int, out_rate: int, chunk_frames: int, channels: int, n: int, flags: int = 0) -> np.ndarray:
+        cfg = StreamCfg(in_rate, out_rate, chunk_frames, channels, flags)
         slots = np.zeros(n, dtype=np.uint32)
         _chk(self.lib.skgpu_stream_open_many(self.h, C.byref(cfg), n, _ptr(slots)))
         return slots

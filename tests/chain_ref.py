@@ -41,3 +41,40 @@ def run_chain_oracle(n_sessions: int, k_inputs: int, ticks: int, seed: int, in_r
             out[g] = sko.gain_f32_to_s16(mixed, float(master[g]))     # master gain -> clip -> s16
         outs.append(out)
     return outs
+
+
+class MixedChainOracle:
+    """sessions whose inputs differ in kind: per input index a sample rate (== out_rate: the resampler node's
+    bypass, resampler.rs:299-373) and a wire format (s16 inputs are converted with x = s / 32768 first). Driven tick by
+    tick with the same per-input arrays streamkit_b200.chain.ChainTick.tick takes."""
+
+    def __init__(self, n_sessions, rates, s16, channels, seed, out_frames=OUT_FRAMES, out_rate=OUT_RATE):
+        self.S, self.K, self.C, self.F = n_sessions, len(rates), channels, out_frames
+        self.rates, self.s16, self.out_rate = list(rates), list(s16), out_rate
+        n_streams = self.S * self.K
+        self.in_gains = synth.gains(seed, n_streams, 0.25, 1.5)
+        self.master = synth.gains(seed + 1, self.S, 0.5, 2.0)
+        self.nodes = [[sko.ResamplerNode(out_rate, chunk_frames=r * out_frames // out_rate, output_frame_size=out_frames) for r in rates]
+                      for _ in range(self.S)]
+        self.queues = [[collections.deque() for _ in rates] for _ in range(self.S)]
+
+    def tick(self, inputs, present=None):
+        """inputs[i]: [n_sessions, chunk_i * channels]; present[s][i] False = the input delivers nothing this tick"""
+        out = np.zeros((self.S, self.F * self.C), dtype=np.int16)
+        for s in range(self.S):
+            frames = []
+            for i in range(self.K):
+                if present is None or present[s][i]:
+                    x = inputs[i][s]
+                    if self.s16[i]:
+                        x = sko.s16_to_f32(np.ascontiguousarray(x, dtype=np.int16))
+                    n = self.nodes[s][i]
+                    n.out.clear()
+                    n.push(self.rates[i], self.C, np.ascontiguousarray(x, dtype=np.float32))
+                    for pkt in n.out:
+                        self.queues[s][i].append(sko.gain(pkt["samples"], float(self.in_gains[s * self.K + i])))
+                q = self.queues[s][i]
+                if q:
+                    frames.append((q.popleft(), self.C, True))
+            out[s] = sko.gain_f32_to_s16(sko.mix_clocked(frames, self.C, self.F), float(self.master[s]))
+        return out

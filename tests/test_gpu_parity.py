@@ -741,3 +741,101 @@ def test_resident_sliced_kernel_network_equals_whole_tick(graph):
     finally:
         a.close()
         b.close()
+
+
+# ------------------------------------------------------------------ input kinds of real pipelines
+
+def _kind_inputs(rng, ct, t, seed):
+    xs = []
+    for i, (r, c, f) in enumerate(zip(ct.rates, ct.chunks, ct.fmts)):
+        x = synth.tone_streams(seed + 17 * i, t, ct.S, c, ct.C, r)
+        if t % 5 == 3:
+            x[rng.integers(0, ct.S), rng.integers(0, x.shape[1])] = np.float32(-0.0)   # signed zero must survive a bypass input
+        xs.append(np.clip(np.rint(x * 32767.0), -32768, 32767).astype(np.int16) if f else x)
+    return xs
+
+
+@pytest.mark.parametrize("rates,s16,channels", [
+    ([48000], [False], 1),                         # one Opus-decoded participant: 48 kHz mono, untouched (opus.rs:103,122-131)
+    ([48000, 48000, 48000], [False] * 3, 1),       # samples/pipelines/dynamic/moq_mixing.yml: decoders -> gain -> clocked mixer, no resampler
+    ([48000, 48000], [False, False], 2),
+    ([44100, 48000], [False, False], 2),           # a resampled and a bypass participant in one mix
+    ([48000, 44100, 16000], [False, False, False], 1),
+    ([44100, 44100], [True, True], 2),             # s16 ingest: half the PCIe bytes
+    ([44100, 48000], [True, True], 2),
+    ([48000, 44100], [True, False], 1),
+    ([32000], [True], 2),
+])
+def test_chain_input_kinds_bypass_mono_s16(rates, s16, channels):
+    S, T, seed = 9, 8, 41
+    ct = chain.ChainTick(S, len(rates), in_rate=rates, channels=channels, seed=seed, s16=s16)
+    ref = chain_ref.MixedChainOracle(S, rates, s16, channels, seed)
+    rng = np.random.default_rng(3)
+    try:
+        for t in range(T):
+            xs = _kind_inputs(rng, ct, t, seed)
+            got = ct.tick(xs, L.SUBMIT_GRAPH if t % 2 else 0)
+            want = ref.tick(xs)
+            assert np.array_equal(got, want), f"tick {t}: {(got != want).sum()} s16 samples differ"
+            res = ct.results()
+            assert np.all(res["status"] == 0)
+        assert np.any(got != 0)
+    finally:
+        ct.close()
+
+
+def test_bypass_input_is_not_interpolated():
+    """(1 - 0) * y0 + 0 * y1 is NOT y0 when y1 is not finite or y0 is -0.0; a bypass input must come through untouched"""
+    S = 3
+    ct = chain.ChainTick(S, 1, in_rate=[48000], channels=1, seed=2)
+    try:
+        ct.plan.set_gains(np.ones(S + S, np.float32))              # unit gains: the packet itself reaches the s16 stage
+        x = np.zeros((S, 960), np.float32)
+        x[0, 10] = np.inf                                           # 0 * inf would poison frame 9 under interpolation
+        x[0, 9] = 0.25
+        x[1, :] = -0.0
+        x[2, 100] = 1.0
+        got = ct.tick([x])
+        assert got[0, 9] == 8192 and got[0, 10] == 32767 and got[0, 11] == 0
+        assert not np.any(got[1]) and got[2, 100] == 32767 and np.count_nonzero(got[2]) == 1
+    finally:
+        ct.close()
+
+
+def test_bypass_and_s16_absent_streams():
+    S, T, seed = 7, 10, 43
+    rates, s16 = [48000, 44100], [True, True]
+    ct = chain.ChainTick(S, 2, in_rate=rates, channels=2, seed=seed, s16=s16)
+    ref = chain_ref.MixedChainOracle(S, rates, s16, 2, seed)
+    rng = np.random.default_rng(5)
+    last = None
+    try:
+        for t in range(T):
+            xs = _kind_inputs(rng, ct, t, seed)
+            present = (rng.random((S, 2)) < 0.7) if t >= 2 else np.ones((S, 2), bool)
+            if last is not None:                                     # the host repeats an absent stream's previous chunk bytes
+                for i in range(2):
+                    xs[i][~present[:, i]] = last[i][~present[:, i]]
+            ct.plan.set_present(ct.op_chain, present.reshape(-1).astype(np.uint8))
+            got = ct.tick(xs)
+            want = ref.tick(xs, present)
+            assert np.array_equal(got, want), f"tick {t}"
+            last = xs
+    finally:
+        ct.close()
+
+
+def test_resample_op_rejects_bypass_streams(ctx):
+    slot = ctx.stream_open(48000, 48000, 960, 2)
+    plan = L.Plan(ctx, 1 << 20)
+    try:
+        items = np.zeros(1, dtype=L.RS_ITEM_DT)
+        items["slot"] = slot
+        items["out_off"] = 65536
+        items["out_cap_frames"] = 1000
+        with pytest.raises(L.SkgpuError) as e:
+            plan.add_resample(items, 32768)
+        assert "bypasses the resampler" in e.value.msg
+    finally:
+        plan.destroy()
+        ctx.stream_close(slot)
