@@ -12,7 +12,8 @@
  * One hub = one GPU. A SESSION is one instance of the chain
  *     n x [ audio::resampler{target 48 kHz, chunk = 20 ms, output_frame_size F} -> audio::gain ]
  *       -> audio::mixer{clocked, F frames} -> audio::gain -> f32->s16
- * (samples/pipelines/dynamic/moq_mixing.yml:63-74 is this shape with n = 2). Per 20 ms tick the engine pushes at most
+ * (samples/pipelines/dynamic/moq_mixing.yml:63-74 is this shape with n = 2 and 48 kHz decoder outputs: bypass inputs, no
+ * resampler work at all). Per 20 ms tick the engine pushes at most
  * one chunk per input, calls skgpu_hub_tick (asynchronous: upload, one fused kernel pass, read-back) and collects
  * every session's mixed packet after skgpu_hub_wait.
  *
@@ -40,6 +41,8 @@ extern "C" {
 typedef struct skgpu_hub skgpu_hub;
 
 #define SKGPU_HUB_OUT_S16 1u /* sessions deliver s16 (clip + pack); without it f32 */
+#define SKGPU_HUB_IN_S16 2u  /* inputs arrive as interleaved s16 (x = s / 32768, exact): half the PCIe bytes for natively 16-bit
+                              * sources; push / acquire then take and hand out int16_t samples */
 
 typedef struct skgpu_hub_config {
     uint32_t max_sessions;           /* capacity: concurrently open sessions */
@@ -49,10 +52,16 @@ typedef struct skgpu_hub_config {
     uint32_t out_frames;             /* F: output_frame_size = frame_samples_per_channel, e.g. 960 */
     uint16_t channels;               /* 1 | 2, inputs and output */
     uint16_t flags;                  /* SKGPU_HUB_OUT_S16 */
-    const uint32_t *in_rates;        /* every input sample rate sessions may use; a chunk is in_rate * F / out_rate frames */
+    const uint32_t *in_rates;        /* every input sample rate sessions may use; a chunk is in_rate * F / out_rate frames. A rate
+                                      * equal to out_rate is a BYPASS input: its F-frame packets enter the mix untouched, as the
+                                      * reference's resampler node forwards them (resampler.rs:299-373) -- the 48 kHz frames an
+                                      * Opus decoder emits (opus.rs:103,122-131) need no resampler in front of a 48 kHz mixer */
     uint32_t n_in_rates;
     uint32_t jitter_frames;          /* chunks an input may queue ahead (ClockedMixerConfig.jitter_buffer_frames, default 3 in
                                       * the reference, mixer.rs:46-55); 0 = 1. Costs jitter_frames + 2 pinned input arenas. */
+    uint32_t slices;                 /* a tick runs as this many slices (upload / kernels / read-back overlapped, skgpu_batch.h
+                                      * "sliced ticks"): the first sessions' packets are back in host memory while the last ones
+                                      * still upload. 0 = 16; 1 = whole-tick submit */
 } skgpu_hub_config;
 
 /* message of the last error on the calling thread (borrowed, like skgpu_last_error) */
@@ -69,20 +78,20 @@ skgpu_rc skgpu_hub_set_master_gain(skgpu_hub *hub, uint32_t session, float gain)
 /* frames a chunk of this input must have (in_rate * F / out_rate) */
 skgpu_rc skgpu_hub_chunk_frames(skgpu_hub *hub, uint32_t session, uint32_t input, uint32_t *frames_out);
 
-/* one chunk (interleaved f32, n_frames == chunk frames of the input), copied into the pinned arena of the first tick
+/* one chunk (interleaved f32 -- int16_t with SKGPU_HUB_IN_S16 --, n_frames == chunk frames of the input), copied into the pinned arena of the first tick
  * that has no chunk of this input yet: an input may queue up to jitter_frames chunks, every tick consumes one; a push
  * into a full queue drops the oldest chunk (the clocked mixer's InputRingBuffer, mixer.rs:1185-1206).
  * Threading: push / push_batch / acquire / commit may be called from any thread, concurrently with each other (distinct
  * streams) AND with skgpu_hub_tick: the hub serialises them against the tick's cut, so a racing chunk lands either in this
  * tick or in the next one, never in an arena that is being uploaded. Everything else is the tick thread's. */
-skgpu_rc skgpu_hub_push(skgpu_hub *hub, uint32_t session, uint32_t input, const float *samples, uint32_t n_frames);
+skgpu_rc skgpu_hub_push(skgpu_hub *hub, uint32_t session, uint32_t input, const void *samples, uint32_t n_frames);
 
 /* zero-copy variant: *dst_out is the stream's slot in the pinned arena of the NEXT tick (chunk frames x channels f32);
  * the producer (e.g. a decoder) writes its samples there and calls skgpu_hub_commit BEFORE the next skgpu_hub_tick
  * (a commit after a tick intervened fails with SKGPU_ERR_STATE and the chunk is dropped). This is how the pinned arenas
  * replace AudioFramePool buffers (crates/core/src/frame_pool.rs:302-317) on the batched path: no gather copy at all.
  * The pointer is valid until the next skgpu_hub_tick. */
-skgpu_rc skgpu_hub_acquire(skgpu_hub *hub, uint32_t session, uint32_t input, float **dst_out, uint32_t *n_frames_out);
+skgpu_rc skgpu_hub_acquire(skgpu_hub *hub, uint32_t session, uint32_t input, void **dst_out, uint32_t *n_frames_out);
 skgpu_rc skgpu_hub_commit(skgpu_hub *hub, uint32_t session, uint32_t input);
 /* every live stream delivered its chunk in place (producers that always write their slot) */
 skgpu_rc skgpu_hub_commit_all(skgpu_hub *hub);
@@ -90,7 +99,7 @@ skgpu_rc skgpu_hub_commit_all(skgpu_hub *hub);
 /* many chunks at once, copied by n_threads worker threads (the gather of a whole tick is ~1 GB at 65 k sessions:
  * one thread cannot keep up with PCIe). frames[i] must name distinct (session, input) pairs. */
 typedef struct skgpu_hub_frame {
-    const float *samples;
+    const void *samples;   /* f32, or int16_t with SKGPU_HUB_IN_S16 */
     uint32_t session, input, n_frames, reserved;
 } skgpu_hub_frame;
 skgpu_rc skgpu_hub_push_batch(skgpu_hub *hub, const skgpu_hub_frame *frames, uint32_t n, uint32_t n_threads);

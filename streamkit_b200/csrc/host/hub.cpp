@@ -101,7 +101,9 @@ struct skgpu_hub {
     skgpu_ctx *ctx = nullptr;
     skgpu_plan *plan = nullptr;
     uint32_t op = 0;
-    uint32_t C = 2, F = 960, ob = 2;
+    uint32_t C = 2, F = 960, ob = 2, ib = 4;   // ib: bytes per input sample (2 with SKGPU_HUB_IN_S16)
+    uint32_t n_slices = 16;
+    bool slices_dirty = true;
     uint64_t in_stride = 0, in_bytes = 0, bank_stride = 0, res_off = 0, res_bytes = 0, out_off = 0, out_stride = 0, d2h_bytes = 0;
     static constexpr uint32_t MAX_RING = 10;    // jitter_frames (<= 8) + 2
     uint8_t *host_in[MAX_RING] = {};            // ring of pinned input arenas: tick k uploads host_in[k % R]
@@ -148,7 +150,7 @@ static inline uint8_t *in_arena(skgpu_hub *h, uint32_t ahead) { return h->host_i
 // copy == nullptr: only reserve the slot (zero-copy acquire). Returns the slot to write.
 static uint8_t *enqueue_slot(skgpu_hub *h, uint32_t sid) {
     const uint64_t off = (uint64_t)sid * h->in_stride;
-    const size_t bytes = (size_t)h->streams[sid].chunk * h->C * 4u;
+    const size_t bytes = (size_t)h->streams[sid].chunk * h->C * h->ib;
     uint32_t q = h->pushed[sid].load(std::memory_order_relaxed);
     if (q >= h->J) {
         // queue full: the oldest chunk is dropped, the rest move up (overwrite-oldest, mixer.rs:1195-1201); rare
@@ -190,6 +192,7 @@ static skgpu_rc rebuild_tables(skgpu_hub *h) {
     }
     PASS(skgpu_plan_update_chain(h->plan, h->op, h->groups.data(), (uint32_t)h->groups.size(), h->inputs.data(), (uint32_t)h->inputs.size()));
     h->tables_dirty = false;
+    h->slices_dirty = true;
     h->epoch += 1;
     return SKGPU_OK;
 }
@@ -206,9 +209,6 @@ extern "C" skgpu_rc skgpu_hub_create(int32_t device, const skgpu_hub_config *cfg
     uint32_t max_chunk = 0;
     for (uint32_t i = 0; i < cfg->n_in_rates; ++i) {
         const uint64_t num = (uint64_t)cfg->in_rates[i] * cfg->out_frames;
-        if (cfg->in_rates[i] == cfg->out_rate)
-            return hub_fail(SKGPU_ERR_INVALID, "input rate %u equals the output rate: the reference bypasses the resampler for such inputs (resampler.rs:299-373); "
-                            "mix them with the unfused ops", cfg->in_rates[i]);
         if (!cfg->in_rates[i] || num % cfg->out_rate) return hub_fail(SKGPU_ERR_INVALID, "input rate %u does not give whole chunks of %u output frames at %u Hz", cfg->in_rates[i], cfg->out_frames, cfg->out_rate);
         max_chunk = std::max<uint32_t>(max_chunk, (uint32_t)(num / cfg->out_rate));
     }
@@ -219,7 +219,11 @@ extern "C" skgpu_rc skgpu_hub_create(int32_t device, const skgpu_hub_config *cfg
     h->C = cfg->channels;
     h->F = cfg->out_frames;
     h->ob = (cfg->flags & SKGPU_HUB_OUT_S16) ? 2u : 4u;
-    h->in_stride = align_up((uint64_t)max_chunk * h->C * 4u, 16);
+    h->ib = (cfg->flags & SKGPU_HUB_IN_S16) ? 2u : 4u;
+    h->n_slices = cfg->slices ? cfg->slices : 16u;
+    if (h->ib == 2u && (((uint64_t)max_chunk * h->C) % 2u || (uint64_t)(max_chunk + 32u) * h->C > 4096u))
+        { delete h; return hub_fail(SKGPU_ERR_INVALID, "s16 inputs need chunks of an even number of samples, at most 4096 with the 32-frame head"); }
+    h->in_stride = align_up((uint64_t)max_chunk * h->C * h->ib + (h->ib == 2u ? 16u : 0u), 16);   // s16 rows are copied in whole 16-byte units
     h->in_bytes = (uint64_t)cfg->max_streams * h->in_stride;
     h->bank_stride = align_up(h->in_bytes, 256);
     h->res_off = 2 * h->bank_stride;
@@ -269,6 +273,7 @@ extern "C" skgpu_rc skgpu_hub_create(int32_t device, const skgpu_hub_config *cfg
         sc.out_rate = cfg->out_rate;
         sc.chunk_frames = (uint32_t)((uint64_t)cfg->in_rates[i] * cfg->out_frames / cfg->out_rate);
         sc.channels = (uint16_t)h->C;
+        sc.flags = h->ib == 2u ? SKGPU_STREAM_S16 : 0u;
         if (skgpu_stream_open(h->ctx, &sc, &probe_slots[i]) != SKGPU_OK) return bail(hub_pass(SKGPU_ERR_INVALID));
         pin[i] = skgpu_chain_input{};
         pin[i].in_off = 0;
@@ -331,6 +336,7 @@ extern "C" skgpu_rc skgpu_hub_session_open(skgpu_hub *h, uint32_t n_inputs, cons
         sc.out_rate = h->cfg.out_rate;
         sc.chunk_frames = (uint32_t)((uint64_t)in_rates[i] * h->F / h->cfg.out_rate);
         sc.channels = (uint16_t)h->C;
+        sc.flags = h->ib == 2u ? SKGPU_STREAM_S16 : 0u;
         uint32_t slot = 0;
         const skgpu_rc rc = skgpu_stream_open(h->ctx, &sc, &slot);
         if (rc != SKGPU_OK) {
@@ -402,25 +408,25 @@ extern "C" skgpu_rc skgpu_hub_chunk_frames(skgpu_hub *h, uint32_t si, uint32_t i
     return SKGPU_OK;
 }
 
-extern "C" skgpu_rc skgpu_hub_push(skgpu_hub *h, uint32_t si, uint32_t input, const float *samples, uint32_t n_frames) {
+extern "C" skgpu_rc skgpu_hub_push(skgpu_hub *h, uint32_t si, uint32_t input, const void *samples, uint32_t n_frames) {
     Session *s = live_session(h, si);
     if (!s || input >= s->streams.size() || !samples) return hub_fail(SKGPU_ERR_INVALID, "no such session / input");
     const uint32_t sid = s->streams[input];
     const Stream &st = h->streams[sid];
     if (n_frames != st.chunk) return hub_fail(SKGPU_ERR_INVALID, "chunk of %u frames, the stream delivers %u per tick", n_frames, st.chunk);
     std::shared_lock<std::shared_mutex> lk(h->cut);
-    stream_copy(enqueue_slot(h, sid), reinterpret_cast<const uint8_t *>(samples), (size_t)n_frames * h->C * 4u);
+    stream_copy(enqueue_slot(h, sid), reinterpret_cast<const uint8_t *>(samples), (size_t)n_frames * h->C * h->ib);
     stream_fence();
     h->pushed[sid].fetch_add(1, std::memory_order_release);
     return SKGPU_OK;
 }
 
-extern "C" skgpu_rc skgpu_hub_acquire(skgpu_hub *h, uint32_t si, uint32_t input, float **dst_out, uint32_t *n_frames_out) {
+extern "C" skgpu_rc skgpu_hub_acquire(skgpu_hub *h, uint32_t si, uint32_t input, void **dst_out, uint32_t *n_frames_out) {
     Session *s = live_session(h, si);
     if (!s || input >= s->streams.size() || !dst_out) return hub_fail(SKGPU_ERR_INVALID, "no such session / input");
     const uint32_t sid = s->streams[input];
     std::shared_lock<std::shared_mutex> lk(h->cut);
-    *dst_out = reinterpret_cast<float *>(enqueue_slot(h, sid));
+    *dst_out = enqueue_slot(h, sid);
     h->streams[sid].acq_tick = h->ticks.load(std::memory_order_relaxed);
     if (n_frames_out) *n_frames_out = h->streams[sid].chunk;
     return SKGPU_OK;
@@ -462,7 +468,7 @@ extern "C" skgpu_rc skgpu_hub_push_batch(skgpu_hub *h, const skgpu_hub_frame *fr
         std::shared_lock<std::shared_mutex> lk(h->cut);
         for (uint32_t i = lo; i < hi; ++i) {
             const uint32_t sid = h->sessions[frames[i].session].streams[frames[i].input];
-            stream_copy(enqueue_slot(h, sid), reinterpret_cast<const uint8_t *>(frames[i].samples), (size_t)frames[i].n_frames * h->C * 4u);
+            stream_copy(enqueue_slot(h, sid), reinterpret_cast<const uint8_t *>(frames[i].samples), (size_t)frames[i].n_frames * h->C * h->ib);
             h->pushed[sid].fetch_add(1, std::memory_order_relaxed);
         }
         stream_fence();
@@ -502,7 +508,7 @@ extern "C" skgpu_rc skgpu_hub_tick(skgpu_hub *h) {
         if (!got && st.ever_pushed) {
             // absent this tick: the other input bank must keep holding the stream's previous chunk (skgpu_batch.h, chain protocol)
             const uint64_t off = (uint64_t)sid * h->in_stride;
-            memcpy(in_cur + off, in_prev + off, (size_t)st.chunk * h->C * 4u);
+            memcpy(in_cur + off, in_prev + off, (size_t)st.chunk * h->C * h->ib);
         }
     }
     PASS(skgpu_plan_set_present(h->plan, h->op, h->present.data(), n_in));
@@ -510,7 +516,12 @@ extern "C" skgpu_rc skgpu_hub_tick(skgpu_hub *h) {
         PASS(skgpu_plan_set_gains(h->plan, h->gains.data(), (uint32_t)h->gains.size()));
         h->gains_dirty = false;
     }
-    PASS(skgpu_tick_submit(h->plan, in_cur, h->host_out[h->cur], SKGPU_SUBMIT_GRAPH | SKGPU_SUBMIT_OVERLAP_D2H));
+    const bool sliced = h->n_slices > 1u && !h->groups.empty();
+    if (sliced && h->slices_dirty) {
+        PASS(skgpu_plan_auto_slices(h->plan, h->op, h->n_slices));
+        h->slices_dirty = false;
+    }
+    PASS(skgpu_tick_submit(h->plan, in_cur, h->host_out[h->cur], sliced ? SKGPU_SUBMIT_SLICED : (SKGPU_SUBMIT_GRAPH | SKGPU_SUBMIT_OVERLAP_D2H)));
     // only a tick that was really submitted consumes the queues (a failed submit keeps every queued chunk)
     for (uint32_t i = 0; i < n_in; ++i) {
         if (!h->present[i]) continue;

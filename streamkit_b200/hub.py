@@ -10,7 +10,7 @@ import numpy as np
 from . import lib as L
 
 HUB_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc", "libskgpu_hub.so")
-OUT_S16 = 1
+OUT_S16, IN_S16 = 1, 2
 
 EXPORTS = [
     "skgpu_hub_last_error", "skgpu_hub_create", "skgpu_hub_destroy", "skgpu_hub_session_open", "skgpu_hub_session_close",
@@ -29,7 +29,7 @@ class HubStats(C.Structure):
 class HubConfig(C.Structure):
     _fields_ = [("max_sessions", C.c_uint32), ("max_streams", C.c_uint32), ("max_inputs_per_session", C.c_uint32),
                 ("out_rate", C.c_uint32), ("out_frames", C.c_uint32), ("channels", C.c_uint16), ("flags", C.c_uint16),
-                ("in_rates", C.POINTER(C.c_uint32)), ("n_in_rates", C.c_uint32), ("jitter_frames", C.c_uint32)]
+                ("in_rates", C.POINTER(C.c_uint32)), ("n_in_rates", C.c_uint32), ("jitter_frames", C.c_uint32), ("slices", C.c_uint32)]
 
 
 class HubFrame(C.Structure):
@@ -96,12 +96,14 @@ class Hub:
     """One GPU's frame-batching layer: sessions of n resampled inputs -> gain -> clocked mix -> gain -> s16."""
 
     def __init__(self, max_sessions: int, max_streams: int, in_rates, max_inputs_per_session: int = 8, out_rate: int = 48000,
-                 out_frames: int = 960, channels: int = 2, s16: bool = True, device: int = 0, jitter_frames: int = 1):
+                 out_frames: int = 960, channels: int = 2, s16: bool = True, device: int = 0, jitter_frames: int = 1, in_s16: bool = False,
+                 slices: int = 0):
         self.lib = load()
         rates = (C.c_uint32 * len(in_rates))(*in_rates)
         self._rates = rates
-        cfg = HubConfig(max_sessions, max_streams, max_inputs_per_session, out_rate, out_frames, channels, OUT_S16 if s16 else 0,
-                        C.cast(rates, C.POINTER(C.c_uint32)), len(in_rates), jitter_frames)
+        cfg = HubConfig(max_sessions, max_streams, max_inputs_per_session, out_rate, out_frames, channels,
+                        (OUT_S16 if s16 else 0) | (IN_S16 if in_s16 else 0), C.cast(rates, C.POINTER(C.c_uint32)), len(in_rates), jitter_frames, slices)
+        self.in_dtype = np.int16 if in_s16 else np.float32
         self.h = C.c_void_p()
         _chk(self.lib.skgpu_hub_create(device, C.byref(cfg), C.byref(self.h)))
         self.F, self.C, self.s16 = out_frames, channels, s16
@@ -132,14 +134,15 @@ class Hub:
         return n.value
 
     def push(self, session: int, inp: int, samples: np.ndarray):
-        x = np.ascontiguousarray(samples, dtype=np.float32).reshape(-1)
+        x = np.ascontiguousarray(samples, dtype=self.in_dtype).reshape(-1)
         _chk(self.lib.skgpu_hub_push(self.h, session, inp, x.ctypes.data_as(C.c_void_p), x.size // self.C))
 
     def acquire(self, session: int, inp: int) -> np.ndarray:
-        """zero-copy: a writable float32 view of the stream's pinned slot for the next tick; fill it, then commit()"""
+        """zero-copy: a writable float32 (int16 for s16 hubs) view of the stream's pinned slot for the next tick; fill it, then commit()"""
         p, n = C.c_void_p(), C.c_uint32()
         _chk(self.lib.skgpu_hub_acquire(self.h, session, inp, C.byref(p), C.byref(n)))
-        return np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_float)), shape=(n.value * self.C,))
+        ct = C.c_int16 if self.in_dtype == np.int16 else C.c_float
+        return np.ctypeslib.as_array(C.cast(p, C.POINTER(ct)), shape=(n.value * self.C,))
 
     def commit(self, session: int, inp: int):
         _chk(self.lib.skgpu_hub_commit(self.h, session, inp))
