@@ -44,15 +44,25 @@ METRIC = "concurrent real-time 48 kHz stereo sessions per GPU within the 2 ms de
 UNIT = "sessions"
 
 
+S16_IN = False
+
+
 def chain_config(sessions_per_gpu: int, n_gpus: int, k: int) -> dict:
+    if IN_RATE == OUT_RATE:
+        wl = ("Opus-shaped variant of BASELINE configs[4] (samples/pipelines/dynamic/moq_mixing.yml): %d x 48 kHz %s decoder outputs -> gain -> "
+              "%d-input ordered mix -> gain -> clip -> s16; the resampler node bypasses rate-equal inputs (resampler.rs:299-373)") % (
+            k, "mono" if CHANNELS == 1 else "stereo", k)
+    else:
+        wl = "BASELINE configs[4]: full chain resample %.1fk->48k -> gain -> %d-input ordered mix -> gain -> clip -> s16" % (IN_RATE / 1e3, k)
+    mb = sessions_per_gpu * k * (IN_RATE // 50) * CHANNELS * (2 if S16_IN else 4) / 1e6
     return {
-        "workload": "BASELINE configs[4]: full chain resample 44.1k->48k -> gain -> %d-input ordered mix -> gain -> clip -> s16" % k,
+        "workload": wl + (" (inputs arrive as s16 on PCIe)" if S16_IN else ""),
         "sessions_per_gpu": sessions_per_gpu, "inputs_per_session": k,
         "in_rate": IN_RATE, "out_rate": OUT_RATE, "channels": CHANNELS, "tick_ms": TICK_MS, "device_budget_ms": BUDGET_MS,
-        "chunk_frames": IN_RATE // 50, "output_frame_size": 960,
+        "chunk_frames": IN_RATE // 50, "output_frame_size": 960, "input_format": "s16" if S16_IN else "f32",
         "sharding": "sessions split evenly across %d GPU(s) by session id, no collective" % n_gpus,
-        "l2": "inputs are %.0f MB per tick per GPU (> 126 MB L2): no flush needed" %
-              (sessions_per_gpu * k * (IN_RATE // 50) * CHANNELS * 4 / 1e6),
+        "l2": ("inputs are %.0f MB per tick per GPU (> 126 MB L2): no flush needed" % mb) if mb > 126 else
+              ("inputs are %.0f MB per tick per GPU, double-banked (two ticks' worth alternate) -- may partly stay in the 126 MB L2" % mb),
     }
 
 
@@ -229,15 +239,17 @@ def run_hub_e2e(S: int, k: int, steps: int, warmup: int, device: int, threads: i
     from streamkit_b200 import hub as H, synth
 
     chunk = IN_RATE // 50
-    hub = H.Hub(max_sessions=S, max_streams=S * k, in_rates=[IN_RATE], max_inputs_per_session=k, channels=CHANNELS, device=device)
+    hub = H.Hub(max_sessions=S, max_streams=S * k, in_rates=[IN_RATE], max_inputs_per_session=k, channels=CHANNELS, device=device, in_s16=S16_IN)
     try:
         n = S * k
-        src = np.empty((n, chunk * CHANNELS), dtype=np.float32)        # every stream's own frame buffer (pageable, like decoder output)
+        src = np.empty((n, chunk * CHANNELS), dtype=np.int16 if S16_IN else np.float32)   # every stream's own frame buffer (pageable, like decoder output)
         blk = synth.noise_streams(4242, 0, 4096, chunk, CHANNELS)
+        if S16_IN:
+            blk = np.rint(blk * 32767.0).astype(np.int16)
         for b in range(0, n, 4096):
             m = min(4096, n - b)
             src[b:b + m] = blk[:m]
-            src[b:b + m, 0] += np.arange(b, b + m, dtype=np.float32) * np.float32(1e-7)
+            src[b:b + m, 0] += (np.arange(b, b + m) % 97).astype(src.dtype)
         frames = np.zeros(n, dtype=H.FRAME_DT)
         for s in range(S):
             sid = hub.session_open([IN_RATE] * k)
@@ -335,11 +347,12 @@ def capacity_check(S2: int, k: int, device: int, kslices: int, ticks: int = 60) 
     """run S2 sessions (the claimed `value`) device-resident, tick by tick, and report the measured per-tick device time"""
     from streamkit_b200 import chain, lib as L, synth
 
-    ct = chain.ChainTick(S2, k, in_rate=IN_RATE, channels=CHANNELS, device=device, seed=5, alloc_host=False)
+    ct = chain.ChainTick(S2, k, in_rate=IN_RATE, channels=CHANNELS, device=device, seed=5, alloc_host=False, s16=S16_IN)
     try:
         blk = synth.noise_streams(77, 0, 8192, ct.chunk, CHANNELS)
-        tile = np.zeros((8192, ct.in_stride // 4), np.float32)
-        tile[:, : blk.shape[1]] = blk
+        tile = np.zeros((8192, ct.in_stride), np.uint8)
+        src = np.rint(blk * 32767.0).astype(np.int16) if S16_IN else blk
+        tile[:, : src.shape[1] * src.itemsize] = src.view(np.uint8).reshape(8192, -1)
         for bank in (0, ct.bank_stride):
             for b in range(0, ct.n_streams, 8192):
                 m = min(8192, ct.n_streams - b)
@@ -371,12 +384,18 @@ def run_chain(args, D: Dist) -> None:
 
     world, rank, local_rank = D.world, D.rank, D.local_rank
     S, K = args.sessions, args.k
-    ct = chain.ChainTick(S, K, in_rate=IN_RATE, channels=CHANNELS, device=local_rank, seed=rank, fused=not args.unfused)
+    ct = chain.ChainTick(S, K, in_rate=IN_RATE, channels=CHANNELS, device=local_rank, seed=rank, fused=not args.unfused, s16=S16_IN)
     plan, ctx = ct.plan, ct.ctx
     ctx.bind_thread()
     # synthetic input: a tick of noise for every stream of every session on this rank (all streams distinct)
     x = synth.noise_streams(1000 + rank, 0, ct.n_streams, ct.chunk, CHANNELS)
-    ct.host_in.reshape(ct.n_streams, ct.in_stride // 4)[:, : x.shape[1]] = x
+    if S16_IN:
+        from oracle import sko as _sko   # only to derive the CPU checker's input from the s16 data (x = s / 32768)
+        xi = np.rint(x * 32767.0).astype(np.int16)
+        ct.fill_rows(ct.host_in, xi)
+        x = _sko.s16_to_f32(xi.reshape(-1)).reshape(xi.shape)
+    else:
+        ct.fill_rows(ct.host_in, x)
     plan.upload(0, ct.host_in)  # resident in HBM for the device-timed region
     if ct.fused:
         plan.upload(ct.bank_stride, ct.host_in)  # both input banks (the fused kernel reads the previous tick's bank)
@@ -562,8 +581,9 @@ def run_chain(args, D: Dist) -> None:
         if fused:
             # dominant kernel = k_chain: the fully fused algorithmic bytes of SURVEY 8(d) / BASELINE.md:
             # per session-tick K x (7056 in + 272 state r/w) + 3840 s16 out = 18,496 B (K = 2)
-            dom_name, dom_bytes = "k_chain<2,1>", chain_bytes
-            traffic, traffic_src = ncu_traffic("k_chain<") if (S == 65536 and K == 2) else (None, "the committed capture is of 65,536 sessions x 2 inputs")
+            dom_name, dom_bytes = "k_chain<%d,1,uniform>" % CHANNELS, chain_bytes
+            std = S == 65536 and K == 2 and IN_RATE == 44100 and CHANNELS == 2 and not S16_IN
+            traffic, traffic_src = ncu_traffic("k_chain<") if std else (None, "the committed capture is of 65,536 sessions x 2 stereo f32 44.1 kHz inputs")
         else:
             dom_name, dom_bytes = "k_resample_prog<2>", n_streams * (in_stride + 960 * CHANNELS * 4 + 2 * (8 + 16 * CHANNELS * 4))
             traffic, traffic_src = None, "no capture of the unfused path"
@@ -734,6 +754,9 @@ def main() -> None:
     ap.add_argument("--config", type=int, default=5, choices=[2, 3, 4, 5], help="BASELINE.json config number (1-based): 5 = full chain (default)")
     ap.add_argument("--sessions", type=int, default=65536, help="sessions per GPU (weak scaling)")
     ap.add_argument("--k", type=int, default=2, choices=[1, 2, 3, 4], help="inputs per session (SURVEY 8d: K = 1 and K = 2)")
+    ap.add_argument("--in-rate", type=int, default=44100, help="input sample rate; 48000 = bypass inputs (Opus-decoder shaped, SURVEY 8f #3)")
+    ap.add_argument("--channels", type=int, default=2, choices=[1, 2])
+    ap.add_argument("--s16-in", action="store_true", help="inputs arrive as s16 on PCIe (x = s / 32768), half the upload")
     ap.add_argument("--slices", type=int, default=16, help="slices per end-to-end tick")
     ap.add_argument("--kslices", type=int, default=8, help="slices of the device-resident tick (phase / chain kernel overlap); 1 = whole-tick launches")
     ap.add_argument("--unfused", action="store_true", help="use the general unfused ops (k_resample_prog -> ring -> k_mix)")
@@ -746,6 +769,8 @@ def main() -> None:
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
+    global IN_RATE, CHANNELS, S16_IN
+    IN_RATE, CHANNELS, S16_IN = args.in_rate, args.channels, args.s16_in
     if args.impl == "reference":
         run_reference(args)
         return
