@@ -25,6 +25,7 @@ from __future__ import annotations
 
 import argparse
 import csv
+import ctypes as C
 import json
 import os
 import statistics
@@ -298,6 +299,50 @@ def run_hub_e2e(S: int, k: int, steps: int, warmup: int, device: int, threads: i
                 "check": {"n_mixed": int(n_mixed), "status": int(status), "nonzero": bool(out is not None and np.any(out != 0))}}
     finally:
         hub.close()
+
+
+def run_router_e2e(S: int, k: int, n_gpus: int, steps: int) -> dict:
+    """ONE process driving all n_gpus GPUs through the session router (include/skgpu_router.h): S x n_gpus sessions opened by
+    UUID, routed by fnv1a64(id) % n_gpus, one NUMA-pinned tick thread + NUMA-bound pinned arenas per GPU, zero-copy producers
+    (skgpu_hub_acquire / commit), sliced ticks, pipelined collection. Wall clock of the slowest GPU's tick loop."""
+    import uuid
+
+    from streamkit_b200 import hub as H, router as R, synth
+
+    chunk = IN_RATE // 50
+    r = R.Router(list(range(n_gpus)), max_sessions=int(S * 1.08) + 64, max_streams=(int(S * 1.08) + 64) * k, in_rates=[IN_RATE],
+                 max_inputs_per_session=k, channels=CHANNELS, in_s16=S16_IN)
+    try:
+        per_gpu = [[] for _ in range(n_gpus)]
+        for i in range(S * n_gpus):
+            h = r.session_open(str(uuid.UUID(int=i * 2654435761 + 12345)), [IN_RATE] * k)
+            per_gpu[h >> 32].append(h & 0xFFFFFFFF)
+        blk = synth.noise_streams(31337, 0, 4096, chunk, CHANNELS)
+        if S16_IN:
+            blk = np.rint(blk * 32767.0).astype(np.int16)
+        hl = H.load()
+        for g in range(n_gpus):            # fill every arena of each hub's input ring once (the producers own the slots afterwards)
+            ns = len(per_gpu[g])
+            frames = np.zeros(ns * k, dtype=H.FRAME_DT)
+            frames["session"] = np.repeat(np.asarray(per_gpu[g], dtype=np.uint32), k)
+            frames["input"] = np.tile(np.arange(k, dtype=np.uint32), ns)
+            frames["n_frames"] = chunk
+            frames["samples"] = blk.ctypes.data + (np.arange(frames.size, dtype=np.uint64) % 4096) * np.uint64(blk.strides[0])
+            for _ in range(3):
+                rc = hl.skgpu_hub_push_batch(r.hub_handle(g), frames.ctypes.data_as(C.c_void_p), frames.size, 8)
+                assert rc == 0
+                r.tick()
+                r.wait()
+        r.run_ticks(3)
+        ms = r.run_ticks(steps)
+        out, n_mixed, status = r.output((0 << 32) | per_gpu[0][0])
+        return {"value": S * n_gpus * TICK_MS / ms, "unit": UNIT, "ms_per_step": ms, "n_gpus": n_gpus, "sessions": S * n_gpus,
+                "sessions_per_gpu": [len(x) for x in per_gpu], "numa_nodes": r.numa_nodes(),
+                "what": "single process, skgpu_router: fnv1a64 session routing, one NUMA-pinned tick thread and NUMA-bound pinned arenas per GPU, "
+                        "zero-copy producers, sliced ticks, pipelined collection; wall clock per tick of the slowest GPU",
+                "check": {"n_mixed": int(n_mixed), "status": int(status), "nonzero": bool(out is not None and np.any(out != 0))}}
+    finally:
+        r.close()
 
 
 # ---------------------------------------------------------------------------------------------- GPU arm
@@ -576,6 +621,15 @@ def run_chain(args, D: Dist) -> None:
             hub_e2e = {"error": str(e)[:200]}
 
     e2e_value = total_sessions * TICK_MS / e2e["ms_per_step"]
+    router_e2e = None
+    if args.router and fused:
+        # every rank is done with its own GPU: rank 0 alone now drives ALL the GPUs of the box from one process
+        D.barrier()
+        if rank == 0:
+            try:
+                router_e2e = run_router_e2e(S, K, world, max(5, min(args.steps, 20)))
+            except Exception as e:
+                router_e2e = {"error": str(e)[:300]}
     if rank == 0:
         peak, peak_src = hbm_peak()
         if fused:
@@ -607,6 +661,7 @@ def run_chain(args, D: Dist) -> None:
             "capacity_check": cap,
             "e2e": e2e_line,
             "e2e_hub": hub_e2e,
+            "e2e_router": router_e2e,
             "parity": parity,
             "gpu_launches": launches_per_tick * args.steps + (2 * e2e.get("slices", 0) + 1) * args.steps,
             "clocks": clk,
@@ -764,6 +819,7 @@ def main() -> None:
     ap.add_argument("--ref-sessions", type=int, default=8192, help="bounded session sample of the CPU arm")
     ap.add_argument("--parity-sessions", type=int, default=256, help="sessions of the timed run compared with the CPU chain (0 = skip)")
     ap.add_argument("--no-hub", dest="hub", action="store_false", help="skip the frame-batching-layer end-to-end measurement")
+    ap.add_argument("--no-router", dest="router", action="store_false", help="skip the single-process multi-GPU router measurement")
     ap.add_argument("--no-capacity-check", dest="capacity_check", action="store_false")
     ap.add_argument("--latency-ticks", type=int, default=500, help="ticks of the per-slice latency measurement (0 = skip)")
     args = ap.parse_args()

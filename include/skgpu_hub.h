@@ -136,6 +136,10 @@ skgpu_rc skgpu_hub_get_stats(skgpu_hub *hub, skgpu_hub_stats *out);
 #define SKGPU_HUB_FAILED 3u
 uint32_t skgpu_hub_state(const skgpu_hub *hub, const char **reason_out);
 
+/* pins the CALLING thread to the CPUs of the hub GPU's NUMA node (the thread that ticks / gathers for this hub); returns the
+ * node, or -1 when the platform exposes none */
+int32_t skgpu_hub_bind_thread(skgpu_hub *hub);
+
 /* counters for logs / tests */
 uint32_t skgpu_hub_live_sessions(const skgpu_hub *hub);
 uint32_t skgpu_hub_live_streams(const skgpu_hub *hub);

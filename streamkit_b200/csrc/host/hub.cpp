@@ -601,6 +601,12 @@ extern "C" uint32_t skgpu_hub_state(const skgpu_hub *h, const char **reason_out)
     return h->degraded ? SKGPU_HUB_DEGRADED : SKGPU_HUB_RUNNING;
 }
 
+extern "C" int32_t skgpu_hub_bind_thread(skgpu_hub *h) {
+    if (!h || !h->ctx) return -1;
+    if (skgpu_ctx_bind_thread(h->ctx) != SKGPU_OK) return -1;
+    return skgpu_ctx_numa_node(h->ctx);
+}
+
 extern "C" uint32_t skgpu_hub_live_sessions(const skgpu_hub *h) { return h ? h->n_live_sessions : 0; }
 extern "C" uint32_t skgpu_hub_live_streams(const skgpu_hub *h) { return h ? h->n_live_streams : 0; }
 extern "C" uint64_t skgpu_hub_ticks(const skgpu_hub *h) { return h ? h->ticks.load(std::memory_order_relaxed) : 0; }
