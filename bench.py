@@ -349,6 +349,11 @@ def run_router_e2e(S: int, k: int, n_gpus: int, steps: int) -> dict:
 
 class Dist:
     def __init__(self):
+        # rank 0 prints exactly ONE line on stdout. NCCL (and anything else written from C) goes to fd 1 whenever it likes, so the
+        # real stdout is parked on a spare descriptor and fd 1 points at stderr until the JSON line is ready (emit()).
+        sys.stdout.flush()
+        self._real_stdout = os.dup(1)
+        os.dup2(2, 1)
         import torch
         self.torch = torch
         self.world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -377,6 +382,44 @@ class Dist:
         t = self.torch.tensor([x], dtype=self.torch.float64, device="cuda")
         self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
         return float(t.item())
+
+    def emit(self, line: dict):
+        sys.stdout.flush()
+        os.write(self._real_stdout, (json.dumps(line) + "\n").encode())
+
+    def pcie_ceiling(self, mb: int = 512, reps: int = 6) -> dict:
+        """what the BOX allows, measured in the same run: plain cudaMemcpyAsync from / to pinned memory on every rank at the same time
+        (upload and read-back concurrently, 4 : 1 like the workload, no kernels, nothing of streamkit_b200 involved)"""
+        torch = self.torch
+        h_in = torch.empty(mb << 20, dtype=torch.uint8, pin_memory=True)
+        h_out = torch.empty((mb << 20) // 4, dtype=torch.uint8, pin_memory=True)
+        d_in = torch.empty(mb << 20, dtype=torch.uint8, device="cuda")
+        d_out = torch.empty((mb << 20) // 4, dtype=torch.uint8, device="cuda")
+        s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+        for _ in range(2):
+            with torch.cuda.stream(s1):
+                d_in.copy_(h_in, non_blocking=True)
+            with torch.cuda.stream(s2):
+                h_out.copy_(d_out, non_blocking=True)
+        self.barrier()
+        with torch.cuda.stream(s1):
+            ev[0].record()
+            for _ in range(reps):
+                d_in.copy_(h_in, non_blocking=True)
+            ev[1].record()
+        with torch.cuda.stream(s2):
+            ev[2].record()
+            for _ in range(reps):
+                h_out.copy_(d_out, non_blocking=True)
+            ev[3].record()
+        torch.cuda.synchronize()
+        h2d = (mb << 20) * reps / (ev[0].elapsed_time(ev[1]) * 1e-3) / 1e9
+        d2h = ((mb << 20) // 4) * reps / (ev[2].elapsed_time(ev[3]) * 1e-3) / 1e9
+        h2d_min = -self.max(-h2d)
+        self.barrier()
+        return {"h2d_gbs_per_gpu_min": h2d_min, "h2d_gbs_this_gpu": h2d, "d2h_gbs_this_gpu": d2h, "ranks_copying_at_once": self.world,
+                "what": "plain cudaMemcpyAsync pinned->device (and device->pinned, a quarter of the bytes) on all ranks simultaneously"}
 
     def close(self):
         if self.dist is not None:
@@ -621,6 +664,14 @@ def run_chain(args, D: Dist) -> None:
             hub_e2e = {"error": str(e)[:200]}
 
     e2e_value = total_sessions * TICK_MS / e2e["ms_per_step"]
+    ceiling = None
+    try:
+        ceiling = D.pcie_ceiling()
+        per_session = in_bytes / S
+        ceiling["sessions_per_gpu_at_that_upload_rate"] = ceiling["h2d_gbs_per_gpu_min"] * 1e9 / (per_session * (1e3 / TICK_MS))
+        ceiling["e2e_fraction_of_ceiling"] = (e2e_value / world) / ceiling["sessions_per_gpu_at_that_upload_rate"]
+    except Exception as e:
+        ceiling = {"error": str(e)[:200]}
     router_e2e = None
     if args.router and fused:
         # every rank is done with its own GPU: rank 0 alone now drives ALL the GPUs of the box from one process
@@ -650,6 +701,7 @@ def run_chain(args, D: Dist) -> None:
         e2e_line = {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": in_bytes * world, "d2h_bytes_per_step": out_bytes * world,
                     "what": "sessions sustained in real time (20 ms per tick) with every input uploaded from and every result read back to host memory"}
         e2e_line.update(e2e)
+        e2e_line["pcie_ceiling"] = ceiling
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
@@ -681,7 +733,7 @@ def run_chain(args, D: Dist) -> None:
             "host": {"cpus": cores, "numa": numa},
             "device": {"name": dev_name, "sms": dev_sms, "cc": "%d.%d" % (dev_cc_ma, dev_cc_mi)},
         }
-        print(json.dumps(line), flush=True)
+        D.emit(line)
 
 
 def run_node(args, D: Dist) -> None:
@@ -794,7 +846,7 @@ def run_node(args, D: Dist) -> None:
             "cpu_baseline": {"value": cpu_value, "unit": unit, "cores": cores, "kind": "port",
                              "sample": "%d %s x %d passes on %d host threads (oracle/sk_chain.c sko_node_bench); units sustained in real time" % (cpu_units, unit, cpu_iters, cores)},
         }
-        print(json.dumps(line), flush=True)
+        D.emit(line)
     w.close()
     if ctx is not None:
         ctx.close()
