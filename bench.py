@@ -467,6 +467,65 @@ def capacity_check(S2: int, k: int, device: int, kslices: int, ticks: int = 60) 
         ct.close()
 
 
+def e2e_sliced(ct, args, D, latency_ticks=None):
+    """end-to-end through the C ABI with host buffers: SLICED ticks, two in flight; every step uploads its inputs from pinned host
+    memory and reads every s16 result back. Returns (dict, host buffer holding the last tick's outputs)."""
+    from streamkit_b200 import lib as L
+
+    plan, ctx, S = ct.plan, ct.ctx, ct.S
+    lt = args.latency_ticks if latency_ticks is None else latency_ticks
+    n_sl = max(1, min(args.slices, S))
+    plan.auto_slices(ct.op_chain, n_sl)
+    ins = [ct.host_in, ctx.pinned(ct.in_bytes, np.float32)]
+    outs = [ct.host_out, ctx.pinned(ct.out_bytes, np.int16)]
+    ins[1][:] = ins[0]
+    fl = L.SUBMIT_SLICED
+
+    def pipelined(n_ticks, collect):
+        first = plan.tick_count()
+        for t in range(n_ticks):
+            plan.submit(ins[t & 1], outs[t & 1], fl)
+            if t >= 1:
+                plan.wait_for(first + t)              # the previous tick: collected while this one uploads
+                if collect is not None:
+                    collect(plan.slice_timing(first + t))
+        plan.wait()
+        if collect is not None:
+            collect(plan.slice_timing(first + n_ticks))
+
+    pipelined(max(3, min(args.warmup, 4)), None)
+    D.barrier()
+    ctx.timer_start()
+    pipelined(args.steps, None)
+    ctx.timer_stop()
+    e2e_ms = ctx.timer_ms()
+    D.barrier()
+    e2e_ms = D.max(e2e_ms)
+    worst, kern, updone = [], [], []
+
+    def collect(tm):
+        worst.append(max(t[2] for t in tm))
+        kern.append(max(t[1] for t in tm))
+        updone.append(tm[-1][0])
+
+    if lt > 0:
+        pipelined(lt, collect)
+    last_out = outs[(lt - 1) & 1] if lt > 0 else outs[(args.steps - 1) & 1]
+    e2e_ms_per_step = e2e_ms / args.steps
+    e2e = {"ms_per_step": e2e_ms_per_step, "slices": n_sl, "ticks_in_flight": 2,
+           "h2d_gbs_per_gpu": ct.in_bytes / (e2e_ms_per_step * 1e-3) / 1e9, "d2h_gbs_per_gpu": ct.out_bytes / (e2e_ms_per_step * 1e-3) / 1e9,
+           "latency": {"ticks": len(worst), "p50_ms": pct(worst, 0.5), "p99_ms": pct(worst, 0.99), "max_ms": max(worst),
+                       "kernels_p99_ms": pct(kern, 0.99), "upload_of_whole_tick_ms_p50": pct(updone, 0.5),
+                       "budget_ms": BUDGET_MS, "within_budget": pct(worst, 0.99) <= BUDGET_MS,
+                       "what": "per slice: its upload done -> its results in host memory (kernels + read-back, SURVEY 8d added device "
+                               "latency); worst slice of each tick; CUDA events"} if worst else None,
+           "host_in_to_host_out_ms": {"first_slice": (pct(updone, 0.5) / n_sl + pct(worst, 0.5)) if worst else None,
+                                      "last_slice": (pct(updone, 0.5) + pct(worst, 0.5)) if worst else None,
+                                      "what": "a frame handed over at the start of the tick's upload is back in host memory after this long "
+                                              "(its slice's share of the upload + the slice latency)"}}
+    return e2e, last_out
+
+
 def run_chain(args, D: Dist) -> None:
     from streamkit_b200 import chain, lib as L, synth
 
@@ -550,55 +609,7 @@ def run_chain(args, D: Dist) -> None:
     # every s16 result back
     e2e = {}
     if ct.fused:
-        n_sl = max(1, min(args.slices, S))
-        plan.auto_slices(ct.op_chain, n_sl)
-        ins = [ct.host_in, ctx.pinned(ct.in_bytes, np.float32)]
-        outs = [ct.host_out, ctx.pinned(ct.out_bytes, np.int16)]
-        ins[1][:] = ins[0]
-        fl = L.SUBMIT_SLICED
-
-        def pipelined(n_ticks, collect):
-            first = plan.tick_count()
-            for t in range(n_ticks):
-                plan.submit(ins[t & 1], outs[t & 1], fl)
-                if t >= 1:
-                    plan.wait_for(first + t)              # the previous tick: collected while this one uploads
-                    if collect is not None:
-                        collect(plan.slice_timing(first + t))
-            plan.wait()
-            if collect is not None:
-                collect(plan.slice_timing(first + n_ticks))
-
-        pipelined(max(3, min(args.warmup, 4)), None)
-        D.barrier()
-        ctx.timer_start()
-        pipelined(args.steps, None)
-        ctx.timer_stop()
-        e2e_ms = ctx.timer_ms()
-        D.barrier()
-        e2e_ms = D.max(e2e_ms)
-        worst, kern, updone = [], [], []
-
-        def collect(tm):
-            worst.append(max(t[2] for t in tm))
-            kern.append(max(t[1] for t in tm))
-            updone.append(tm[-1][0])
-
-        if args.latency_ticks > 0:
-            pipelined(args.latency_ticks, collect)
-        last_out = outs[(args.latency_ticks - 1) & 1] if args.latency_ticks > 0 else outs[(args.steps - 1) & 1]
-        e2e_ms_per_step = e2e_ms / args.steps
-        e2e = {"ms_per_step": e2e_ms_per_step, "slices": n_sl, "ticks_in_flight": 2,
-               "h2d_gbs_per_gpu": ct.in_bytes / (e2e_ms_per_step * 1e-3) / 1e9, "d2h_gbs_per_gpu": ct.out_bytes / (e2e_ms_per_step * 1e-3) / 1e9,
-               "latency": {"ticks": len(worst), "p50_ms": pct(worst, 0.5), "p99_ms": pct(worst, 0.99), "max_ms": max(worst),
-                           "kernels_p99_ms": pct(kern, 0.99), "upload_of_whole_tick_ms_p50": pct(updone, 0.5),
-                           "budget_ms": BUDGET_MS, "within_budget": pct(worst, 0.99) <= BUDGET_MS,
-                           "what": "per slice: its upload done -> its results in host memory (kernels + read-back, SURVEY 8d added device "
-                                   "latency); worst slice of each tick; CUDA events"} if worst else None,
-               "host_in_to_host_out_ms": {"first_slice": (pct(updone, 0.5) / n_sl + pct(worst, 0.5)) if worst else None,
-                                          "last_slice": (pct(updone, 0.5) + pct(worst, 0.5)) if worst else None,
-                                          "what": "a frame handed over at the start of the tick's upload is back in host memory after this long "
-                                                  "(its slice's share of the upload + the slice latency)"}}
+        e2e, last_out = e2e_sliced(ct, args, D)
     else:
         for _ in range(3):
             plan.submit(ct.host_in, ct.host_out, 0)
@@ -645,6 +656,23 @@ def run_chain(args, D: Dist) -> None:
 
     total_sessions = S * world
     value = total_sessions * BUDGET_MS / ms_per_step
+    # ---- the same workload with the inputs as s16 on PCIe (natively 16-bit sources: x = s / 32768): half the upload
+    e2e_s16 = None
+    if args.s16_extra and fused and not S16_IN and (IN_RATE // 50 + 32) * CHANNELS <= 4096:
+        try:
+            ct2 = chain.ChainTick(S, K, in_rate=IN_RATE, channels=CHANNELS, device=local_rank, seed=rank, s16=True)
+            ct2.ctx.bind_thread()
+            blk = np.rint(synth.noise_streams(2000 + rank, 0, 8192, ct2.chunk, CHANNELS) * 32767.0).astype(np.int16)
+            ct2.fill_rows(ct2.host_in, np.tile(blk, ((ct2.n_streams + 8191) // 8192, 1))[: ct2.n_streams])
+            d, _ = e2e_sliced(ct2, args, D, latency_ticks=min(args.latency_ticks, 100))
+            d["value"] = total_sessions * TICK_MS / d["ms_per_step"]
+            d["unit"] = UNIT
+            d["h2d_bytes_per_step"], d["d2h_bytes_per_step"] = ct2.in_bytes * world, ct2.out_bytes * world
+            d["what"] = "the same sessions with s16 input frames (skgpu_stream_cfg.flags = SKGPU_STREAM_S16): expanded to f32 in shared memory"
+            e2e_s16 = d
+            ct2.close()
+        except Exception as e:
+            e2e_s16 = {"error": str(e)[:200]}
     cap = None
     if args.capacity_check and fused:
         S2 = int(S * BUDGET_MS / ms_per_step * 0.97) // 1024 * 1024
@@ -712,6 +740,7 @@ def run_chain(args, D: Dist) -> None:
             "device_realtime_sessions_20ms": total_sessions * TICK_MS / ms_per_step,
             "capacity_check": cap,
             "e2e": e2e_line,
+            "e2e_s16_ingest": e2e_s16,
             "e2e_hub": hub_e2e,
             "e2e_router": router_e2e,
             "parity": parity,
@@ -872,6 +901,7 @@ def main() -> None:
     ap.add_argument("--parity-sessions", type=int, default=256, help="sessions of the timed run compared with the CPU chain (0 = skip)")
     ap.add_argument("--no-hub", dest="hub", action="store_false", help="skip the frame-batching-layer end-to-end measurement")
     ap.add_argument("--no-router", dest="router", action="store_false", help="skip the single-process multi-GPU router measurement")
+    ap.add_argument("--no-s16-extra", dest="s16_extra", action="store_false", help="skip the s16-ingest end-to-end variant")
     ap.add_argument("--no-capacity-check", dest="capacity_check", action="store_false")
     ap.add_argument("--latency-ticks", type=int, default=500, help="ticks of the per-slice latency measurement (0 = skip)")
     args = ap.parse_args()

@@ -126,16 +126,21 @@ __device__ __forceinline__ void tma_bulk_g2s(void *dst_smem, const void *src_gme
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
+// Bounded wait: try_wait suspends the thread up to the hint (no issue slots while waiting). A barrier that never completes -- a
+// bulk copy that was lost, a byte count that does not match -- must not hang the context forever: after
+// ~2^21 expired hints (tens of seconds; a healthy wait is microseconds) the thread traps, the launch fails with a CUDA error,
+// and the host surfaces it as SKGPU_ERR_CUDA / NodeState::Failed instead of a silent hang.
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "WAIT_LOOP:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"   // suspends the thread (no issue slots) up to the hint
-        "@p bra DONE;\n"
-        "bra WAIT_LOOP;\n"
-        "DONE:\n"
-        "}\n" ::"r"(smem_u32(bar)), "r"(parity), "r"(20000u) : "memory");
+    uint32_t done = 0;
+    for (uint32_t spins = 0; !done; ++spins) {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n" : "=r"(done) : "r"(smem_u32(bar)), "r"(parity), "r"(20000u) : "memory");
+        if (!done && spins > (1u << 21)) asm volatile("trap;");
+    }
 }
 
 // ---- cp.async (LDGSTS): asynchronous global -> shared copies that need no destination registers

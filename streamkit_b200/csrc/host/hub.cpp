@@ -46,6 +46,17 @@ skgpu_rc hub_pass(skgpu_rc rc) {
         skgpu_rc rc__ = (call);             \
         if (rc__ != SKGPU_OK) return hub_pass(rc__); \
     } while (0)
+// same, inside tick / wait: a CUDA error is fatal for every session of the hub -- the node state becomes Failed{reason}
+// (crates/core/src/state.rs:122-186; wrapper.rs:468-483 does the same for a plugin whose process_packet fails)
+#define PASS_FATAL(h, call)                 \
+    do {                                    \
+        skgpu_rc rc__ = (call);             \
+        if (rc__ != SKGPU_OK) {             \
+            hub_pass(rc__);                 \
+            if (rc__ == SKGPU_ERR_CUDA) { (h)->fail_reason = g_err; (h)->stats.errored += 1; } \
+            return rc__;                    \
+        }                                   \
+    } while (0)
 
 uint64_t align_up(uint64_t x, uint64_t a) { return (x + a - 1) / a * a; }
 
@@ -484,6 +495,7 @@ extern "C" skgpu_rc skgpu_hub_push_batch(skgpu_hub *h, const skgpu_hub_frame *fr
 
 extern "C" skgpu_rc skgpu_hub_tick(skgpu_hub *h) {
     if (!h) return hub_fail(SKGPU_ERR_INVALID, "null hub");
+    if (!h->fail_reason.empty()) return hub_fail(SKGPU_ERR_STATE, "hub failed: %s", h->fail_reason.c_str());
     const uint64_t t0 = h->ticks.load(std::memory_order_relaxed);
     // at most two unfinished ticks: the input ring (J + 2 arenas) and the two output arenas are sized for exactly that
     // (a third submit would let pushes overwrite an arena whose upload is pending and reuse host_out[cur])
@@ -521,7 +533,7 @@ extern "C" skgpu_rc skgpu_hub_tick(skgpu_hub *h) {
         PASS(skgpu_plan_auto_slices(h->plan, h->op, h->n_slices));
         h->slices_dirty = false;
     }
-    PASS(skgpu_tick_submit(h->plan, in_cur, h->host_out[h->cur], sliced ? SKGPU_SUBMIT_SLICED : (SKGPU_SUBMIT_GRAPH | SKGPU_SUBMIT_OVERLAP_D2H)));
+    PASS_FATAL(h, skgpu_tick_submit(h->plan, in_cur, h->host_out[h->cur], sliced ? SKGPU_SUBMIT_SLICED : (SKGPU_SUBMIT_GRAPH | SKGPU_SUBMIT_OVERLAP_D2H)));
     // only a tick that was really submitted consumes the queues (a failed submit keeps every queued chunk)
     for (uint32_t i = 0; i < n_in; ++i) {
         if (!h->present[i]) continue;
@@ -549,7 +561,8 @@ extern "C" skgpu_rc skgpu_hub_tick(skgpu_hub *h) {
 
 extern "C" skgpu_rc skgpu_hub_wait(skgpu_hub *h, skgpu_tick_timing *timing) {
     if (!h) return hub_fail(SKGPU_ERR_INVALID, "null hub");
-    PASS(skgpu_tick_wait(h->plan, timing));
+    if (!h->fail_reason.empty()) return hub_fail(SKGPU_ERR_STATE, "hub failed: %s", h->fail_reason.c_str());
+    PASS_FATAL(h, skgpu_tick_wait(h->plan, timing));
     h->in_flight = false;
     h->waited = h->ticks;
     h->out_ready = h->ticks > 0;
@@ -560,7 +573,7 @@ extern "C" skgpu_rc skgpu_hub_wait(skgpu_hub *h, skgpu_tick_timing *timing) {
 extern "C" skgpu_rc skgpu_hub_wait_tick(skgpu_hub *h, uint64_t tick) {
     if (!h) return hub_fail(SKGPU_ERR_INVALID, "null hub");
     if (tick == 0 || tick > h->ticks || tick + 1 < h->ticks) return hub_fail(SKGPU_ERR_INVALID, "tick %llu is not one of the two most recent ticks", (unsigned long long)tick);
-    PASS(skgpu_tick_wait_for(h->plan, tick));
+    PASS_FATAL(h, skgpu_tick_wait_for(h->plan, tick));
     h->waited = std::max(h->waited, tick);
     h->last = (int)((tick - 1) & 1u);          // tick k uploaded from / read back into arena (k - 1) & 1
     h->in_flight = tick < h->ticks;           // a later tick may still be running

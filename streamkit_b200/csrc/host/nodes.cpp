@@ -32,8 +32,10 @@ GpuRuntime::~GpuRuntime() {
     if (ctx_) skgpu_ctx_destroy(ctx_);
 }
 GpuRuntime &GpuRuntime::get() {
-    static GpuRuntime rt;
-    return rt;
+    // deliberately leaked: the context must not be torn down from a static destructor at process exit, when the CUDA runtime
+    // may already be unloading; the OS reclaims it
+    static GpuRuntime *rt = new GpuRuntime();
+    return *rt;
 }
 
 void PlanHolder::reset() {

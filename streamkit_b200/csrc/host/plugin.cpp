@@ -7,6 +7,7 @@
 // at a time on pin "in" (wrapper.rs:398-457). Output packets are handed to the callback and may be freed as soon as
 // it returns: the host copies inside the callback (conversions.rs:340-346).
 #include <cstring>
+#include <memory>
 #include <string>
 #include <vector>
 
@@ -86,7 +87,8 @@ const sk_node_metadata *get_metadata() {
 
 sk_plugin_handle create_instance(const char *params_json, sk_log_callback log_cb, void *log_ud) {
     try {
-        auto *inst = new Instance();
+        // owned until every step has succeeded: a throw below (no GPU, out of memory) must not leak the instance
+        std::unique_ptr<Instance> inst(new Instance());
         inst->log_cb = log_cb;
         inst->log_ud = log_ud;
         StreamKitError err{StreamKitError::Configuration, ""};
@@ -99,12 +101,11 @@ sk_plugin_handle create_instance(const char *params_json, sk_log_callback log_cb
 #endif
         if (!inst->node) {
             inst->log(SK_LOG_ERROR, err.message);
-            delete inst;
             return nullptr;   // host: StreamKitError::Configuration("Plugin failed to create instance") (wrapper.rs:184-188)
         }
         GpuRuntime::get();    // fail at creation, not at the first packet, when there is no GPU
         inst->log(SK_LOG_INFO, std::string("created ") + kKind + " instance");
-        return inst;
+        return inst.release();
     } catch (const StreamKitError &e) {
         if (log_cb) log_cb(SK_LOG_ERROR, "streamkit_b200", e.message.c_str(), log_ud);
         return nullptr;
@@ -161,6 +162,8 @@ sk_result process_packet(sk_plugin_handle h, const char *pin, const sk_packet *p
         return fail(e.message);
     } catch (const std::exception &e) {
         return fail(e.what());
+    } catch (...) {
+        return fail("unknown exception");   // nothing may unwind across the C ABI into the Rust host
     }
 }
 
@@ -171,9 +174,15 @@ sk_result update_params(sk_plugin_handle h, const char *params_json) {
     return ok();   // audio::resampler has no tunable parameters
 #else
     auto *inst = static_cast<Instance *>(h);
-    if (auto bad = inst->node->update_params(params_json)) {
-        inst->log(SK_LOG_WARN, *bad);
-        return fail(*bad);   // host logs a warning and keeps running (wrapper.rs:297-299); the old gain stays in effect
+    try {
+        if (auto bad = inst->node->update_params(params_json)) {
+            inst->log(SK_LOG_WARN, *bad);
+            return fail(*bad);   // host logs a warning and keeps running (wrapper.rs:297-299); the old gain stays in effect
+        }
+    } catch (const std::exception &e) {
+        return fail(e.what());
+    } catch (...) {
+        return fail("unknown exception");
     }
     return ok();
 #endif
@@ -193,6 +202,10 @@ sk_result flush(sk_plugin_handle h, sk_output_callback cb, void *ud, sk_telemetr
         }
     } catch (const StreamKitError &e) {
         return fail(e.message);
+    } catch (const std::exception &e) {
+        return fail(e.what());
+    } catch (...) {
+        return fail("unknown exception");
     }
 #else
     (void)cb; (void)ud;
@@ -200,7 +213,9 @@ sk_result flush(sk_plugin_handle h, sk_output_callback cb, void *ud, sk_telemetr
     return ok();
 }
 
-void destroy_instance(sk_plugin_handle h) { delete static_cast<Instance *>(h); }
+void destroy_instance(sk_plugin_handle h) {
+    try { delete static_cast<Instance *>(h); } catch (...) {}
+}
 
 const sk_native_plugin_api kApi = {SK_NATIVE_PLUGIN_API_VERSION, get_metadata, create_instance, process_packet, update_params, flush, destroy_instance};
 

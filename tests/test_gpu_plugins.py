@@ -183,3 +183,80 @@ def test_mixer_node_mirror_reference_scenarios():
     o, oc = _mix(lib, h, 1, [F(0.75, 2)])
     assert np.all(np.abs(o - 0.75) < 1e-3)
     lib.skn_mixer_destroy(C.c_void_p(h))
+
+
+# ------------------------------------------------------------------ audio::resampler node: integer packet metadata
+
+class _SknMeta(C.Structure):
+    _fields_ = [("timestamp_us", C.c_uint64), ("duration_us", C.c_uint64), ("sequence", C.c_uint64), ("has_timestamp", C.c_uint8),
+                ("has_duration", C.c_uint8), ("has_sequence", C.c_uint8), ("pad", C.c_uint8)]
+
+
+_SKN_EMIT = C.CFUNCTYPE(None, C.c_void_p, C.c_uint32, C.c_uint16, C.POINTER(C.c_float), C.c_size_t, C.POINTER(_SknMeta))
+
+
+class _GpuResamplerNode:
+    def __init__(self, params: str):
+        lib = C.CDLL(os.path.join(CSRC, "libskgpu_nodes.so"))
+        lib.skn_resampler_create.restype = C.c_void_p
+        lib.skn_resampler_create.argtypes = [C.c_char_p]
+        lib.skn_resampler_destroy.argtypes = [C.c_void_p]
+        lib.skn_resampler_push.argtypes = [C.c_void_p, C.c_uint32, C.c_uint16, C.c_void_p, C.c_size_t, C.c_int, C.c_uint64, _SKN_EMIT, C.c_void_p]
+        lib.skn_resampler_finish.argtypes = [C.c_void_p, _SKN_EMIT, C.c_void_p]
+        lib.skn_last_error.restype = C.c_char_p
+        self.lib = lib
+        self.h = lib.skn_resampler_create(params.encode())
+        assert self.h, lib.skn_last_error()
+        self.out = []
+        self._cb = _SKN_EMIT(self._emit)
+
+    def _emit(self, ud, rate, ch, samples, n, meta):
+        m = meta.contents
+        self.out.append(dict(sample_rate=rate, channels=ch, samples=np.ctypeslib.as_array(samples, shape=(n,)).copy() if n else np.zeros(0, np.float32),
+                             timestamp_us=m.timestamp_us if m.has_timestamp else None, duration_us=m.duration_us if m.has_duration else None,
+                             sequence=m.sequence if m.has_sequence else None))
+
+    def push(self, rate, ch, x, timestamp_us=None):
+        x = np.ascontiguousarray(x, dtype=np.float32)
+        rc = self.lib.skn_resampler_push(C.c_void_p(self.h), rate, ch, x.ctypes.data_as(C.c_void_p), x.size, 0 if timestamp_us is None else 1,
+                                         0 if timestamp_us is None else timestamp_us, self._cb, None)
+        if rc != 0:
+            raise RuntimeError(self.lib.skn_last_error().decode())
+
+    def finish(self):
+        assert self.lib.skn_resampler_finish(C.c_void_p(self.h), self._cb, None) == 0
+
+    def close(self):
+        self.lib.skn_resampler_destroy(C.c_void_p(self.h))
+
+
+@pytest.mark.parametrize("in_rate,target,ch,ofs,packet,first_ts", [
+    (44100, 48000, 1, 960, 882, 1000), (48000, 16000, 2, 960, 960, 123456789), (44100, 48000, 2, 0, 1000, 7),
+    (48000, 48000, 2, 480, 700, 42), (22050, 48000, 1, 1920, 441, None),
+])
+def test_resampler_node_timestamp_duration_sequence_match_the_oracle(in_rate, target, ch, ofs, packet, first_ts):
+    """resampler.rs:286-297 / :108-116: the first input packet's timestamp seeds output_timestamp_us, every emitted packet
+    advances it by frames * 1_000_000 / rate (INTEGER division), sequence counts 0, 1, 2, ...; the flushed partial packet at EOF
+    carries the next sequence number WITHOUT incrementing it (:707-711). Integer metadata is a bit-exact requirement: samples
+    AND metadata of every packet equal the oracle node's (oracle/sk_oracle.c sko_rsnode_*)."""
+    node = _GpuResamplerNode('{"target_sample_rate": %d, "chunk_frames": 960, "output_frame_size": %d}' % (target, ofs))
+    ref = sko.ResamplerNode(target, 960, ofs)
+    try:
+        for c in range(11):
+            x = synth.tone_streams(9, c, 1, packet, ch, in_rate)[0]
+            ts = first_ts if (c == 0 and first_ts is not None) else (5 if first_ts is not None else None)   # later timestamps are ignored (:211-214)
+            node.push(in_rate, ch, x, timestamp_us=ts)
+            ref.push(in_rate, ch, x, timestamp_us=ts)
+        node.finish()
+        ref.finish()
+        assert len(node.out) == len(ref.out) and len(node.out) >= 2
+        for a, b in zip(node.out, ref.out):
+            assert (a["sample_rate"], a["channels"]) == (b["sample_rate"], b["channels"])
+            assert np.array_equal(a["samples"].view(np.uint32), b["samples"].view(np.uint32))
+            assert a["sequence"] == b["sequence"] and a["duration_us"] == b["duration_us"] and a["timestamp_us"] == b["timestamp_us"]
+        if first_ts is not None and in_rate != target and ofs:
+            assert node.out[0]["timestamp_us"] == first_ts
+            assert node.out[1]["timestamp_us"] == first_ts + sko.duration_us_for_frames(target, ofs)
+            assert [p["sequence"] for p in node.out[:-1]] == list(range(len(node.out) - 1))
+    finally:
+        node.close()
