@@ -18,7 +18,7 @@ EXPORTS = [
     "skgpu_hub_acquire", "skgpu_hub_commit", "skgpu_hub_commit_all",
     "skgpu_hub_tick",
     "skgpu_hub_wait", "skgpu_hub_wait_tick", "skgpu_hub_session_output", "skgpu_hub_live_sessions", "skgpu_hub_live_streams", "skgpu_hub_ticks",
-    "skgpu_hub_get_stats", "skgpu_hub_state",
+    "skgpu_hub_get_stats", "skgpu_hub_state", "skgpu_hub_bind_thread",
 ]
 
 
@@ -75,6 +75,8 @@ def load() -> C.CDLL:
     lib.skgpu_hub_ticks.argtypes = [vp]
     lib.skgpu_hub_ticks.restype = C.c_uint64
     lib.skgpu_hub_get_stats.argtypes = [vp, C.POINTER(HubStats)]
+    lib.skgpu_hub_bind_thread.argtypes = [vp]
+    lib.skgpu_hub_bind_thread.restype = i32
     lib.skgpu_hub_state.argtypes = [vp, C.POINTER(C.c_char_p)]
     lib.skgpu_hub_state.restype = u32
     _lib = lib
