@@ -72,6 +72,39 @@ void skgpu_hub_destroy(skgpu_hub *hub);
 
 /* in_rates[n_inputs]: sample rate of every input (each must be one of cfg.in_rates). Gains start at 1.0. */
 skgpu_rc skgpu_hub_session_open(skgpu_hub *hub, uint32_t n_inputs, const uint32_t *in_rates, uint32_t *session_out);
+
+/* ---- audio::mixer SYNC mode on the batch path (mixer.rs:554-918; the default above is the clocked mode, :1242-1434).
+ * The state machine that decides WHICH frames enter a mix stays on the host and is evaluated once per hub tick:
+ *   cold start   nothing is mixed until every active input has delivered at least once (:728-731)
+ *   ready        every input that is not marked slow holds a frame -> mix now; slow inputs that delivered again are
+ *                "recovered" and the session returns to Running (:746-762)
+ *   timeout      a frame has been waiting for sync_timeout_ms (AudioMixerConfig.sync_timeout_ms, default 100, :639-709,
+ *                :782-838) -> the inputs still missing are marked SLOW (stats.discarded += their number), the session becomes
+ *                Degraded{"slow_input_timeout"} and the mix goes out with silence in their place; later mixes no longer wait
+ *                for slow inputs
+ *   hold         otherwise: nothing is consumed, nothing is emitted (n_mixed = 0); the waiting chunks stay queued
+ *   EOF          skgpu_hub_input_eof removes an input from the active set (:848-898); buffered frames of the others are
+ *                mixed at the next tick; a session whose inputs are all closed is Stopped{"all_inputs_closed"}
+ * Time is the hub's tick clock: a timeout of T ms expires after ceil(T / tick_ms) ticks (tick_ms = 1000 F / out_rate).
+ * A waiting input keeps its LATEST chunk (jitter_frames = 1: a second push replaces the first, like slot.frame = Some(frame));
+ * unlike the reference, where the upstream resampler node has already consumed the replaced packet, the replaced chunk never
+ * reaches the stream's resampler state. */
+#define SKGPU_SESSION_SYNC 1u
+skgpu_rc skgpu_hub_session_open_ex(skgpu_hub *hub, uint32_t n_inputs, const uint32_t *in_rates, uint32_t mode, uint32_t sync_timeout_ms,
+                                   uint32_t *session_out);
+skgpu_rc skgpu_hub_input_eof(skgpu_hub *hub, uint32_t session, uint32_t input);
+#define SKGPU_SESSION_RUNNING 1u
+#define SKGPU_SESSION_DEGRADED 2u   /* NodeState::Degraded{reason: "slow_input_timeout"} (crates/core/src/state.rs:122-186) */
+#define SKGPU_SESSION_STOPPED 4u    /* all inputs closed */
+typedef struct skgpu_session_state {
+    uint32_t state;          /* SKGPU_SESSION_* */
+    uint32_t mixed;          /* 1 = the last tick mixed (consumed the waiting frames); 0 = it held or had nothing */
+    uint64_t slow_mask;      /* bit i: input i is marked slow */
+    uint64_t eof_mask;       /* bit i: input i reached EOF */
+    uint64_t newly_slow;     /* inputs marked slow by the last tick (the "newly_slow_pins" of the Degraded details) */
+    uint64_t recovered;      /* inputs that left the slow state at the last tick */
+} skgpu_session_state;
+skgpu_rc skgpu_hub_session_state(skgpu_hub *hub, uint32_t session, skgpu_session_state *out);
 skgpu_rc skgpu_hub_session_close(skgpu_hub *hub, uint32_t session);
 skgpu_rc skgpu_hub_set_input_gain(skgpu_hub *hub, uint32_t session, uint32_t input, float gain);
 skgpu_rc skgpu_hub_set_master_gain(skgpu_hub *hub, uint32_t session, float gain);

@@ -102,6 +102,15 @@ struct Session {
     bool live = false;
     std::vector<uint32_t> streams;   // hub stream ids, pin order
     int64_t tab_first = -1;          // index of its first input in the submitted tables (-1: not in the tables yet)
+    // ---- audio::mixer sync mode (mixer.rs:554-918), evaluated once per tick
+    bool sync = false;
+    uint32_t timeout_ticks = 0;      // 0 = no timeout (sync_timeout_ms: None)
+    uint64_t has_sent = 0, slow = 0, eof = 0, have_frame = 0;   // per-input bit masks (<= 64 inputs)
+    int64_t waiting_since = -1;      // tick number at which the first frame of the pending mix arrived
+    bool force_mix = false;          // an input reached EOF while frames were buffered
+    bool degraded_reported = false;
+    uint64_t consumed = 0;           // inputs whose frame the current tick's mix takes
+    skgpu_session_state st{SKGPU_SESSION_RUNNING, 0, 0, 0, 0, 0};
 };
 
 }  // namespace
@@ -130,6 +139,8 @@ struct skgpu_hub {
     std::vector<skgpu_chain_group> groups;
     std::vector<skgpu_chain_input> inputs;
     std::vector<uint32_t> tab_stream;           // table input index -> hub stream id
+    std::vector<uint32_t> tab_session, tab_input;   // table input index -> session index / input index inside the session
+    uint32_t n_sync_sessions = 0;
     std::vector<uint8_t> present;
     uint32_t cur = 0;                           // OUTPUT arena the next tick reads back into (ping-pong)
     int last = -1;                              // arena of the last submitted tick
@@ -179,6 +190,8 @@ static skgpu_rc rebuild_tables(skgpu_hub *h) {
     h->groups.clear();
     h->inputs.clear();
     h->tab_stream.clear();
+    h->tab_session.clear();
+    h->tab_input.clear();
     for (uint32_t si = 0; si < h->sessions.size(); ++si) {
         Session &s = h->sessions[si];
         if (!s.live) continue;
@@ -198,6 +211,8 @@ static skgpu_rc rebuild_tables(skgpu_hub *h) {
             in.flags = 1u;   // SKGPU_MIX_IN_UNIQUE: every stream owns its samples
             h->inputs.push_back(in);
             h->tab_stream.push_back(sid);
+            h->tab_session.push_back(si);
+            h->tab_input.push_back((uint32_t)(h->inputs.size() - 1u - (size_t)s.tab_first));
         }
         h->groups.push_back(g);
     }
@@ -206,6 +221,61 @@ static skgpu_rc rebuild_tables(skgpu_hub *h) {
     h->slices_dirty = true;
     h->epoch += 1;
     return SKGPU_OK;
+}
+
+// One evaluation of the sync-mode state machine of audio::mixer (mixer.rs:554-918) for tick number T. Decides whether the
+// session mixes at this tick (s.st.mixed, s.consumed) and maintains has_sent / slow / waiting_since like the reference's
+// InputSlot flags; arrivals between two ticks are observed at the later one.
+static void sync_evaluate(skgpu_hub *h, Session &s, int64_t T) {
+    const uint32_t n = (uint32_t)s.streams.size();
+    const uint64_t all = n >= 64 ? ~0ull : ((1ull << n) - 1ull);
+    const uint64_t active = all & ~s.eof;
+    s.st.newly_slow = s.st.recovered = 0;
+    s.st.mixed = 0;
+    s.consumed = 0;
+    for (uint32_t i = 0; i < n; ++i) {
+        const uint64_t bit = 1ull << i;
+        if (!(active & bit)) continue;
+        if (h->pushed[s.streams[i]].load(std::memory_order_acquire) != 0 && !(s.have_frame & bit)) {
+            // RecvResult::Audio (:717-745): the first frame into an empty mix starts the timeout clock when more than one input is expected
+            if ((s.have_frame & active) == 0 && __builtin_popcountll(active & ~s.slow) > 1) s.waiting_since = T;
+            s.have_frame |= bit;
+            s.has_sent |= bit;
+        }
+    }
+    const uint64_t frames = s.have_frame & active;
+    bool mix = false;
+    if (active != 0 && frames != 0) {
+        const bool cold_start_complete = (s.has_sent & active) == active;                     // :728-731
+        if (s.force_mix) {
+            mix = true;                                                                       // PinEof with frames buffered (:872-886)
+        } else if (cold_start_complete) {
+            if (((s.slow | s.have_frame) & active) == active) {                               // ready_to_mix (:746)
+                s.st.recovered = s.slow & frames;                                             // :748-762
+                s.slow &= ~s.st.recovered;
+                s.waiting_since = -1;
+                mix = true;
+            } else if (s.timeout_ticks && s.waiting_since >= 0 && T - s.waiting_since >= (int64_t)s.timeout_ticks) {
+                const uint64_t missing = active & ~s.slow & ~s.have_frame;                    // :782-838 / :639-709
+                if (missing) {
+                    s.slow |= missing;
+                    s.st.newly_slow = missing;
+                    h->stats.discarded += (uint64_t)__builtin_popcountll(missing);
+                    s.waiting_since = -1;
+                    mix = true;
+                }
+            }
+        }
+    }
+    s.force_mix = false;
+    if (mix) {
+        s.st.mixed = 1;
+        s.consumed = frames;
+        s.have_frame &= ~frames;
+    }
+    s.st.slow_mask = s.slow & active;
+    s.st.eof_mask = s.eof;
+    s.st.state = active == 0 ? SKGPU_SESSION_STOPPED : (s.st.slow_mask ? SKGPU_SESSION_DEGRADED : SKGPU_SESSION_RUNNING);
 }
 
 extern "C" const char *skgpu_hub_last_error(void) { return g_err.c_str(); }
@@ -329,7 +399,14 @@ extern "C" void skgpu_hub_destroy(skgpu_hub *h) {
 }
 
 extern "C" skgpu_rc skgpu_hub_session_open(skgpu_hub *h, uint32_t n_inputs, const uint32_t *in_rates, uint32_t *session_out) {
+    return skgpu_hub_session_open_ex(h, n_inputs, in_rates, 0u, 0u, session_out);
+}
+
+extern "C" skgpu_rc skgpu_hub_session_open_ex(skgpu_hub *h, uint32_t n_inputs, const uint32_t *in_rates, uint32_t mode, uint32_t sync_timeout_ms,
+                                              uint32_t *session_out) {
     if (!h || !in_rates || !session_out) return hub_fail(SKGPU_ERR_INVALID, "null argument");
+    if (mode & ~SKGPU_SESSION_SYNC) return hub_fail(SKGPU_ERR_INVALID, "unknown session mode 0x%x", mode);
+    if ((mode & SKGPU_SESSION_SYNC) && h->J != 1u) return hub_fail(SKGPU_ERR_INVALID, "sync-mode sessions keep the latest frame per input: the hub must have jitter_frames = 1");
     if (n_inputs < 1 || n_inputs > h->cfg.max_inputs_per_session) return hub_fail(SKGPU_ERR_INVALID, "n_inputs %u outside 1..%u", n_inputs, h->cfg.max_inputs_per_session);
     if (h->free_sessions.empty()) return hub_fail(SKGPU_ERR_NOMEM, "out of session slots (%u)", h->cfg.max_sessions);
     if (h->free_streams.size() < n_inputs) return hub_fail(SKGPU_ERR_NOMEM, "out of stream slots (%u requested, %zu free)", n_inputs, h->free_streams.size());
@@ -341,6 +418,11 @@ extern "C" skgpu_rc skgpu_hub_session_open(skgpu_hub *h, uint32_t n_inputs, cons
     const uint32_t si = h->free_sessions.back();
     Session s;
     s.live = true;
+    s.sync = (mode & SKGPU_SESSION_SYNC) != 0;
+    if (s.sync && sync_timeout_ms) {
+        const double tick_ms = 1000.0 * (double)h->F / (double)h->cfg.out_rate;
+        s.timeout_ticks = (uint32_t)std::ceil((double)sync_timeout_ms / tick_ms);
+    }
     for (uint32_t i = 0; i < n_inputs; ++i) {
         skgpu_stream_cfg sc{};
         sc.in_rate = in_rates[i];
@@ -368,6 +450,7 @@ extern "C" skgpu_rc skgpu_hub_session_open(skgpu_hub *h, uint32_t n_inputs, cons
     h->sessions[si] = std::move(s);
     h->n_live_sessions += 1;
     h->n_live_streams += n_inputs;
+    if (h->sessions[si].sync) h->n_sync_sessions += 1;
     h->gains_dirty = h->tables_dirty = true;
     *session_out = si;
     return SKGPU_OK;
@@ -387,6 +470,7 @@ extern "C" skgpu_rc skgpu_hub_session_close(skgpu_hub *h, uint32_t si) {
     }
     h->n_live_streams -= (uint32_t)s->streams.size();
     h->n_live_sessions -= 1;
+    if (s->sync) h->n_sync_sessions -= 1;
     *s = Session{};
     for (int a = 0; a < 2; ++a)   // a session index that is reused must not see the closed session's packets
         if (si < h->first_by_arena[a].size()) h->first_by_arena[a][si] = -1;
@@ -512,10 +596,30 @@ extern "C" skgpu_rc skgpu_hub_tick(skgpu_hub *h) {
     std::unique_lock<std::shared_mutex> cut(h->cut);
     const uint32_t n_in = (uint32_t)h->tab_stream.size();
     uint8_t *in_cur = in_arena(h, 0), *in_prev = h->host_in[(t0 + h->R - 1u) % h->R];   // this tick's arena, the previous tick's
+    uint32_t n_sent = 0;
+    if (h->n_sync_sessions) {
+        for (Session &s : h->sessions)
+            if (s.live && s.sync) sync_evaluate(h, s, (int64_t)t0 + 1);
+    }
+    h->degraded = false;
+    for (const Session &s : h->sessions) {
+        if (!s.live) continue;
+        if (!s.sync) n_sent += 1;
+        else { n_sent += s.st.mixed; h->degraded |= (s.st.state & SKGPU_SESSION_DEGRADED) != 0; }
+    }
+    uint8_t *in_next = in_arena(h, 1);
     for (uint32_t i = 0; i < n_in; ++i) {
         const uint32_t sid = h->tab_stream[i];
         const Stream &st = h->streams[sid];
-        const bool got = h->pushed[sid].load(std::memory_order_acquire) != 0;   // the head of the stream's queue sits in this tick's arena
+        bool got = h->pushed[sid].load(std::memory_order_acquire) != 0;   // the head of the stream's queue sits in this tick's arena
+        const Session &ss = h->sessions[h->tab_session[i]];
+        if (ss.sync && got && !(ss.st.mixed && ((ss.consumed >> h->tab_input[i]) & 1ull))) {
+            // sync mode holds this frame: it stays queued for a later mix (its chunk moves on to the next tick's arena); for the
+            // kernel the stream is absent
+            const uint64_t off = (uint64_t)sid * h->in_stride;
+            memcpy(in_next + off, in_cur + off, (size_t)st.chunk * h->C * h->ib);
+            got = false;
+        }
         h->present[i] = got ? 1 : 0;
         if (!got && st.ever_pushed) {
             // absent this tick: the other input bank must keep holding the stream's previous chunk (skgpu_batch.h, chain protocol)
@@ -542,7 +646,7 @@ extern "C" skgpu_rc skgpu_hub_tick(skgpu_hub *h) {
         h->streams[sid].ever_pushed = true;
         h->stats.received += 1;
     }
-    h->stats.sent += h->groups.size();
+    h->stats.sent += n_sent;
     if (h->last == (int)h->cur) h->out_ready = false;   // this tick reuses the arena the collected results lived in
     if (h->arena_epoch[h->cur] != h->epoch) {           // remember which table rows this tick's results belong to
         auto &fa = h->first_by_arena[h->cur];
@@ -596,6 +700,33 @@ extern "C" skgpu_rc skgpu_hub_session_output(skgpu_hub *h, uint32_t si, const vo
     if (samples) *samples = o + (h->out_off - h->res_off) + (uint64_t)si * h->out_stride;
     if (n_mixed) *n_mixed = nm;
     if (status) *status = stt;
+    return SKGPU_OK;
+}
+
+extern "C" skgpu_rc skgpu_hub_input_eof(skgpu_hub *h, uint32_t si, uint32_t input) {
+    Session *s = live_session(h, si);
+    if (!s || input >= s->streams.size()) return hub_fail(SKGPU_ERR_INVALID, "no such session / input");
+    if (!s->sync) return hub_fail(SKGPU_ERR_STATE, "session %u is a clocked-mode session: an input that stops delivering is simply silent there", si);
+    std::unique_lock<std::shared_mutex> lk(h->cut);
+    const uint64_t bit = 1ull << input;
+    if (s->eof & bit) return SKGPU_OK;
+    s->eof |= bit;                                   // slots.remove(slot_idx) (mixer.rs:856)
+    s->have_frame &= ~bit;
+    h->pushed[s->streams[input]].store(0, std::memory_order_relaxed);
+    s->waiting_since = -1;                           // :866
+    const uint32_t n = (uint32_t)s->streams.size();
+    const uint64_t active = (n >= 64 ? ~0ull : ((1ull << n) - 1ull)) & ~s->eof;
+    if (active && (s->have_frame & active)) s->force_mix = true;   // :872-886
+    s->st.eof_mask = s->eof;
+    s->st.slow_mask = s->slow & active;
+    s->st.state = active == 0 ? SKGPU_SESSION_STOPPED : (s->st.slow_mask ? SKGPU_SESSION_DEGRADED : SKGPU_SESSION_RUNNING);
+    return SKGPU_OK;
+}
+
+extern "C" skgpu_rc skgpu_hub_session_state(skgpu_hub *h, uint32_t si, skgpu_session_state *out) {
+    Session *s = live_session(h, si);
+    if (!s || !out) return hub_fail(SKGPU_ERR_INVALID, "no such session");
+    *out = s->st;
     return SKGPU_OK;
 }
 

@@ -18,8 +18,17 @@ EXPORTS = [
     "skgpu_hub_acquire", "skgpu_hub_commit", "skgpu_hub_commit_all",
     "skgpu_hub_tick",
     "skgpu_hub_wait", "skgpu_hub_wait_tick", "skgpu_hub_session_output", "skgpu_hub_live_sessions", "skgpu_hub_live_streams", "skgpu_hub_ticks",
-    "skgpu_hub_get_stats", "skgpu_hub_state", "skgpu_hub_bind_thread",
+    "skgpu_hub_get_stats", "skgpu_hub_state", "skgpu_hub_bind_thread", "skgpu_hub_session_open_ex", "skgpu_hub_input_eof", "skgpu_hub_session_state",
 ]
+
+
+SESSION_SYNC = 1
+SESSION_RUNNING, SESSION_DEGRADED, SESSION_STOPPED = 1, 2, 4
+
+
+class SessionState(C.Structure):
+    _fields_ = [("state", C.c_uint32), ("mixed", C.c_uint32), ("slow_mask", C.c_uint64), ("eof_mask", C.c_uint64), ("newly_slow", C.c_uint64),
+                ("recovered", C.c_uint64)]
 
 
 class HubStats(C.Structure):
@@ -76,6 +85,9 @@ def load() -> C.CDLL:
     lib.skgpu_hub_ticks.restype = C.c_uint64
     lib.skgpu_hub_get_stats.argtypes = [vp, C.POINTER(HubStats)]
     lib.skgpu_hub_bind_thread.argtypes = [vp]
+    lib.skgpu_hub_session_open_ex.argtypes = [vp, u32, C.POINTER(u32), u32, u32, C.POINTER(u32)]
+    lib.skgpu_hub_input_eof.argtypes = [vp, u32, u32]
+    lib.skgpu_hub_session_state.argtypes = [vp, u32, C.POINTER(SessionState)]
     lib.skgpu_hub_bind_thread.restype = i32
     lib.skgpu_hub_state.argtypes = [vp, C.POINTER(C.c_char_p)]
     lib.skgpu_hub_state.restype = u32
@@ -120,6 +132,21 @@ class Hub:
         sid = C.c_uint32()
         _chk(self.lib.skgpu_hub_session_open(self.h, len(in_rates), arr, C.byref(sid)))
         return sid.value
+
+    def session_open_sync(self, in_rates, sync_timeout_ms: int | None = 100) -> int:
+        """audio::mixer sync mode (mixer.rs:554-918); sync_timeout_ms None = wait forever"""
+        arr = (C.c_uint32 * len(in_rates))(*in_rates)
+        sid = C.c_uint32()
+        _chk(self.lib.skgpu_hub_session_open_ex(self.h, len(in_rates), arr, SESSION_SYNC, sync_timeout_ms or 0, C.byref(sid)))
+        return sid.value
+
+    def input_eof(self, session: int, inp: int):
+        _chk(self.lib.skgpu_hub_input_eof(self.h, session, inp))
+
+    def session_state(self, session: int) -> SessionState:
+        st = SessionState()
+        _chk(self.lib.skgpu_hub_session_state(self.h, session, C.byref(st)))
+        return st
 
     def session_close(self, session: int):
         _chk(self.lib.skgpu_hub_session_close(self.h, session))

@@ -397,3 +397,147 @@ def test_hub_moq_mixing_shape_bypass_inputs(channels, in_s16):
                 assert np.array_equal(got, w), f"tick {t} session {sid}: {(got != w).sum()} samples differ"
     finally:
         hub.close()
+
+
+# ------------------------------------------------------------------------------------------------ sync mode
+
+class _SyncMixerModel:
+    """audio::mixer sync mode restated from mixer.rs:554-918 for a tick-quantised clock (arrivals are seen at the next tick;
+    a timeout of N ticks expires N ticks after the first frame of the pending mix arrived)"""
+
+    def __init__(self, n, timeout_ticks):
+        self.n, self.timeout = n, timeout_ticks
+        self.has_sent = [False] * n
+        self.slow = [False] * n
+        self.frame = [None] * n
+        self.eof = [False] * n
+        self.waiting_since = None
+        self.force = False
+        self.discarded = 0
+
+    def active(self):
+        return [i for i in range(self.n) if not self.eof[i]]
+
+    def arrive(self, i, x, T):
+        if self.frame[i] is None and all(self.frame[k] is None for k in self.active()) and sum(1 for k in self.active() if not self.slow[k]) > 1:
+            self.waiting_since = T
+        self.frame[i] = x                         # keep the latest frame per pin (:741)
+        self.has_sent[i] = True
+
+    def pin_eof(self, i):
+        self.eof[i] = True
+        self.frame[i] = None
+        self.waiting_since = None
+        if self.active() and any(self.frame[k] is not None for k in self.active()):
+            self.force = True
+
+    def tick(self, T):
+        """returns (frames to mix {input: chunk} or None, newly_slow, recovered)"""
+        act = self.active()
+        frames = [k for k in act if self.frame[k] is not None]
+        mix, newly, rec = False, [], []
+        if act and frames:
+            if self.force:
+                mix = True
+            elif all(self.has_sent[k] for k in act):
+                if all(self.slow[k] or self.frame[k] is not None for k in act):
+                    rec = [k for k in frames if self.slow[k]]
+                    for k in rec:
+                        self.slow[k] = False
+                    self.waiting_since = None
+                    mix = True
+                elif self.timeout and self.waiting_since is not None and T - self.waiting_since >= self.timeout:
+                    newly = [k for k in act if not self.slow[k] and self.frame[k] is None]
+                    if newly:
+                        for k in newly:
+                            self.slow[k] = True
+                        self.discarded += len(newly)
+                        self.waiting_since = None
+                        mix = True
+        self.force = False
+        if not mix:
+            return None, newly, rec
+        out = {k: self.frame[k] for k in frames}
+        for k in frames:
+            self.frame[k] = None
+        return out, newly, rec
+
+
+@pytest.mark.gpu
+def test_hub_sync_mode_timeout_slow_pins_recovery_and_eof():
+    """SURVEY A8 / VERDICT r1 missing #3: sync_timeout_ms, slow-pin marking, Degraded{slow_input_timeout} and recovery, EOF pin
+    removal (mixer.rs:639-709, :746-762, :782-838, :848-898) on the batch path, against a restatement of the state machine; the
+    audio of every mix against the oracle's nodes."""
+    rng = np.random.default_rng(77)
+    hub = H.Hub(max_sessions=4, max_streams=12, in_rates=[44100, 48000], max_inputs_per_session=3, jitter_frames=1, slices=2)
+    try:
+        shapes = [[44100, 48000, 44100], [48000, 48000]]
+        timeout_ms = 100                                    # = 5 ticks of 20 ms
+        sids = [hub.session_open_sync(r, timeout_ms) for r in shapes]
+        clocked = hub.session_open([44100])                 # a clocked session next to them is unaffected
+        osess = [_OracleSession(r, 2, 960) for r in shapes] + [_OracleSession([44100], 2, 960)]
+        models = [_SyncMixerModel(len(r), 5) for r in shapes]
+        sent = [[0] * len(r) for r in shapes]
+        pending = [[None] * len(r) for r in shapes]         # the chunk an input pushed and the hub has not consumed yet
+        # scripted arrival pattern: input 2 of session 0 stalls for ticks 8..22 (-> slow after 5 ticks), then recovers;
+        # input 1 of session 1 reaches EOF at tick 30
+        def delivers(a, i, t):
+            if a == 0 and i == 2 and 8 <= t < 23:
+                return False
+            if a == 1 and i == 1 and t >= 30:
+                return False
+            return rng.random() < 0.9
+        saw_degraded = saw_recovered = saw_hold = False
+        for t in range(44):
+            T = t + 1
+            if t == 30:
+                hub.input_eof(sids[1], 1)
+                models[1].pin_eof(1)
+                pending[1][1] = None
+            for a, (sid, r) in enumerate(zip(sids, shapes)):
+                for i, rate in enumerate(r):
+                    if models[a].eof[i] or not delivers(a, i, t):
+                        continue
+                    x = _chunk(700 + a * 8 + i, sent[a][i], rate, rate * 960 // 48000, 2)
+                    sent[a][i] += 1
+                    hub.push(sid, i, x)
+                    pending[a][i] = x                     # a second push while waiting replaces the first (latest frame per pin)
+                    models[a].arrive(i, x, T)
+            xc = _chunk(990, t, 44100, 882, 2)
+            hub.push(clocked, 0, xc)
+            osess[2].push(0, xc)
+            want_c = osess[2].tick()
+            hub.tick()
+            hub.wait()
+            for a, sid in enumerate(sids):
+                frames, newly, rec = models[a].tick(T)
+                st = hub.session_state(sid)
+                assert bool(st.mixed) == (frames is not None), (t, a)
+                assert st.newly_slow == sum(1 << k for k in newly) and st.recovered == sum(1 << k for k in rec), (t, a)
+                assert st.slow_mask == sum(1 << k for k in models[a].active() if models[a].slow[k]), (t, a)
+                assert st.state == (H.SESSION_DEGRADED if st.slow_mask else H.SESSION_RUNNING)
+                saw_degraded |= st.state == H.SESSION_DEGRADED
+                saw_recovered |= st.recovered != 0
+                got, n_mixed, status = hub.output(sid)
+                assert status == 0
+                if frames is None:
+                    saw_hold |= any(p is not None for p in pending[a])
+                    assert n_mixed == 0 and not np.any(got)
+                    continue
+                for k, x in frames.items():
+                    osess[a].push(k, x)                   # the stream's resampler consumes the chunk when the mix takes it
+                    pending[a][k] = None
+                w, n = osess[a].tick()
+                assert n_mixed == n, (t, a, n_mixed, n)
+                assert np.array_equal(got, w), f"tick {t} session {a}: {(got != w).sum()} samples differ"
+            got, n_mixed, _ = hub.output(clocked)
+            assert n_mixed == want_c[1] and np.array_equal(got, want_c[0])
+        assert saw_degraded and saw_recovered and saw_hold
+        assert hub.stats()["discarded"] >= models[0].discarded + models[1].discarded
+        assert hub.session_state(sids[1]).eof_mask == 2
+        hub.input_eof(sids[1], 0)
+        assert hub.session_state(sids[1]).state == H.SESSION_STOPPED      # all_inputs_closed
+        with pytest.raises(H.HubError):
+            hub.input_eof(clocked, 0)
+    finally:
+        hub.close()
