@@ -85,6 +85,7 @@ skgpu_rc skgpu_ctx_bind_thread(skgpu_ctx *ctx);
 /* stream flags */
 #define SKGPU_STREAM_S16 1u  /* chain op only: the stream's chunks arrive as interleaved s16 (x = s / 32768, exact) -- half the
                               * PCIe bytes of f32 for natively 16-bit sources; expanded to f32 in shared memory */
+#define SKGPU_STREAM_SINC 2u /* resample op only: windowed-sinc polyphase interpolation (skgpu_ctx_set_sinc) instead of rubato's Linear */
 typedef struct skgpu_stream_cfg {
     uint32_t in_rate;           /* Hz, from the first packet (resampler.rs:206-209) */
     uint32_t out_rate;          /* AudioResamplerConfig.target_sample_rate (resampler.rs:22-27) */
@@ -97,6 +98,21 @@ typedef struct skgpu_stream_cfg {
  * output_frame_size frames per tick (chunk_frames == output_frame_size) that enters the mix as it is -- the path of the
  * 48 kHz mono frames an Opus decoder emits (crates/nodes/src/audio/codecs/opus.rs:103,122-131; moq_mixing.yml has no
  * resampler at all). No arithmetic is applied to it (not a frac = 0 interpolation). Resample ops reject bypass streams. */
+
+/* Windowed-sinc polyphase mode (BASELINE.json north star: "a batched polyphase windowed-sinc resampler that keeps filter state per
+ * stream in HBM"). The reference resamples with rubato FastFixedIn / Linear (resampler.rs:232-238), so this mode has no reference
+ * implementation; its specification, in rubato's SincInterpolationParameters vocabulary:
+ *   sinc_len L (taps per phase, multiple of 8, <= 256), oversampling_factor O (<= 1024), f_cutoff (of the lower Nyquist),
+ *   window BlackmanHarris2 (4-term Blackman-Harris squared), interpolation Linear between the two nearest phases;
+ *   fc = f_cutoff * min(1, out_rate / in_rate);  g(tau) = fc sinc(fc tau) w((tau + L/2) / L);
+ *   T[p][n] = g(L/2 - 1 - n + p/O) / sum_n g(..) (f64 -> f32), p = 0..O;
+ *   per chunk of N frames: idx starts at last_index (-(L/2) for a new stream) and advances by 1/ratio (f64) while
+ *   idx < N - L/2 - 1 - ceil(1/ratio); output = (1 - q) dot(window, T[p]) + q dot(window, T[p + 1]) with p = floor(frac O),
+ *   q = f32(frac O - p), window = L input frames from floor(idx) - L/2 + 1 (zeros before the stream starts), every dot product a
+ *   sequential f32 fma chain in ascending tap order. State per stream in HBM: last_index (f64) + the last L + 8 input frames.
+ * The oracle restates this independently (oracle/sk_sinc.c, oracle/np_oracle.py). Call before opening SKGPU_STREAM_SINC streams;
+ * the parameters are fixed for the context's lifetime. */
+skgpu_rc skgpu_ctx_set_sinc(skgpu_ctx *ctx, uint32_t sinc_len, uint32_t oversampling_factor, double f_cutoff);
 
 skgpu_rc skgpu_stream_open(skgpu_ctx *ctx, const skgpu_stream_cfg *cfg, uint32_t *slot_out);
 /* bulk open of n identical streams (session ramp-up); slots_out[n] */

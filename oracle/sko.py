@@ -38,7 +38,7 @@ def load() -> C.CDLL:
     global _lib
     if _lib is not None:
         return _lib
-    srcs = [os.path.join(_HERE, f) for f in ("sk_oracle.c", "sk_chain.c", "sk_oracle.h")]
+    srcs = [os.path.join(_HERE, f) for f in ("sk_oracle.c", "sk_chain.c", "sk_sinc.c", "sk_oracle.h")]
     if not os.path.exists(LIB_PATH) or any(os.path.getmtime(f) > os.path.getmtime(LIB_PATH) for f in srcs):
         build()
     lib = C.CDLL(LIB_PATH)
@@ -76,6 +76,16 @@ def load() -> C.CDLL:
     lib.sko_chain_bench.restype = C.c_double
     lib.sko_chain_bench.argtypes = [C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint16, vp, C.c_uint32, vp, vp, C.c_int, vp,
                                     C.POINTER(C.c_uint64)]
+    lib.sko_sinc_new.restype = vp
+    lib.sko_sinc_new.argtypes = [C.c_double, C.c_size_t, C.c_size_t, C.c_size_t, C.c_size_t, C.c_double]
+    lib.sko_sinc_free.argtypes = [vp]
+    lib.sko_sinc_out_max.restype = C.c_size_t
+    lib.sko_sinc_out_max.argtypes = [vp]
+    lib.sko_sinc_last_index.restype = C.c_double
+    lib.sko_sinc_last_index.argtypes = [vp]
+    lib.sko_sinc_process_interleaved.restype = C.c_size_t
+    lib.sko_sinc_process_interleaved.argtypes = [vp, vp, vp, C.c_size_t]
+    lib.sko_sinc_taps.argtypes = [C.c_size_t, C.c_size_t, C.c_double, vp]
     lib.sko_node_bench.restype = C.c_double
     lib.sko_node_bench.argtypes = [C.c_int, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, vp, C.c_uint32, vp, C.c_int, vp, vp, vp,
                                    C.c_uint32]
@@ -265,3 +275,37 @@ def node_bench(kind: int, n_units: int, iters: int, pool: np.ndarray, gains: np.
                                 _p(out_s16) if out_s16 is not None else None, _p(out_f32) if out_f32 is not None else None,
                                 _p(out_n) if out_n is not None else None, cap)
     return sec, (out_s16 if kind in (0, 1) else out_f32), out_n
+
+
+class SincFixedIn:
+    """windowed-sinc polyphase resampler of the build's own spec (oracle/sk_sinc.c header; no reference implementation exists)"""
+
+    def __init__(self, in_rate: int, out_rate: int, chunk_frames: int, channels: int, sinc_len: int = 64, oversampling: int = 256,
+                 f_cutoff: float = 0.95):
+        self.lib = load()
+        self.channels, self.chunk = channels, chunk_frames
+        self.h = self.lib.sko_sinc_new(float(out_rate) / float(in_rate), chunk_frames, channels, sinc_len, oversampling, f_cutoff)
+        assert self.h
+        self.out_max = self.lib.sko_sinc_out_max(self.h)
+
+    def process(self, chunk: np.ndarray) -> np.ndarray:
+        chunk = np.ascontiguousarray(chunk, dtype=np.float32).ravel()
+        assert chunk.size == self.chunk * self.channels
+        out = np.empty(self.out_max * self.channels, dtype=np.float32)
+        n = self.lib.sko_sinc_process_interleaved(self.h, _p(chunk), _p(out), self.out_max)
+        return out[: n * self.channels].copy()
+
+    @property
+    def last_index(self) -> float:
+        return self.lib.sko_sinc_last_index(self.h)
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.lib.sko_sinc_free(self.h)
+            self.h = None
+
+
+def sinc_taps(sinc_len: int, oversampling: int, fc: float) -> np.ndarray:
+    out = np.empty((oversampling + 1, sinc_len), dtype=np.float32)
+    load().sko_sinc_taps(sinc_len, oversampling, fc, _p(out))
+    return out

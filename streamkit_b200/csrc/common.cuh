@@ -37,7 +37,7 @@ struct __align__(16) SlotRec {  // everything a kernel needs to know about one r
     uint32_t overflow;     // bit (chunk number & 1): phase table overflowed
     uint32_t flags;        // SLOT_*                                                (host config)
 };
-constexpr uint32_t SLOT_BYPASS = 1u, SLOT_S16 = 2u;
+constexpr uint32_t SLOT_BYPASS = 1u, SLOT_S16 = 2u, SLOT_SINC = 4u;   // bits 8-15: index of the stream's sinc tap table
 static_assert(sizeof(SlotRec) == 64, "SlotRec must be one 64-byte record");
 
 struct SlotCfgUpload {     // host -> device (re)configuration of one slot (k_config_slots)
@@ -45,6 +45,7 @@ struct SlotCfgUpload {     // host -> device (re)configuration of one slot (k_co
     uint32_t slot, chunk, channels;
     int32_t end_idx;
     uint32_t flags, pad;
+    double last_index0;    // rubato's initial last_index: -4.0 (FastFixedIn, POLYNOMIAL_LEN / 2), -(sinc_len / 2) in sinc mode
 };
 
 constexpr uint32_t SK_SIDE_STRIDE = 2048u;   // >= sizeof(SkPhaseTable); fused chain: frame program (<= 1920 B) + 128 B history
@@ -61,6 +62,10 @@ struct SlotTables {     // per-stream state + configuration, all device pointers
     unsigned long long *fifo_r;  // total frames ever consumed
     uint32_t max_channels;
     uint32_t fifo_frames;   // power of two
+    // windowed-sinc mode (k_sinc.cuh); null / 0 until skgpu_ctx_set_sinc
+    float *sinc_hist;                  // [slot][sinc_H * max_channels]: the last sinc_H input frames
+    const float *const *sinc_tabs;     // tap tables [(sinc_O + 1)][sinc_L], one per distinct cutoff
+    uint32_t sinc_L, sinc_O, sinc_H, sinc_pad;
 };
 
 // ------------------------------------------------------------------ small helpers
@@ -222,6 +227,8 @@ __global__ void k_config_slots(const SlotCfgUpload *__restrict__ cfgs, uint32_t 
     const SlotCfgUpload c = cfgs[i];
     const uint32_t slot = c.slot;
     for (uint32_t s = threadIdx.x; s < 16u * st.max_channels; s += blockDim.x) st.hist[(size_t)slot * 16u * st.max_channels + s] = 0.0f;
+    if ((c.flags & SLOT_SINC) && st.sinc_hist)
+        for (uint32_t s = threadIdx.x; s < st.sinc_H * st.max_channels; s += blockDim.x) st.sinc_hist[(size_t)slot * st.sinc_H * st.max_channels + s] = 0.0f;
     {   // both side records (phase tables / chain history) start zeroed
         uint4 *sd = reinterpret_cast<uint4 *>(slot_side(st, slot, 0));
         for (uint32_t s = threadIdx.x; s < 2u * SK_SIDE_STRIDE / 16u; s += blockDim.x) sd[s] = make_uint4(0u, 0u, 0u, 0u);
@@ -229,7 +236,7 @@ __global__ void k_config_slots(const SlotCfgUpload *__restrict__ cfgs, uint32_t 
     if (threadIdx.x == 0) {
         SlotRec r;
         r.t_ratio = c.t_ratio;
-        r.last_index = -4.0;
+        r.last_index = c.last_index0;
         r.chunk = c.chunk;
         r.channels = c.channels;
         r.chunk_count = 0;

@@ -6,9 +6,11 @@
 //   k_mix            ordered N-input sum, channel conversion, epilogue      (mixer.rs:944-1013, :1027-1078)
 //   k_fifo_commit    advances device re-framing ring read cursors           (resampler.rs:420-458 re-framing, unfused path)
 //   k_chain          all of the above fused per session, lagged recompute   (BASELINE config #5)
+//   k_resample_sinc  windowed-sinc polyphase mode (north star; own spec)    (skgpu_ctx_set_sinc)
 #pragma once
 #include "common.cuh"
 #include "k_convert.cuh"
 #include "k_resample.cuh"
 #include "k_mix.cuh"
 #include "k_chain.cuh"
+#include "k_sinc.cuh"

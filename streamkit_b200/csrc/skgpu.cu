@@ -74,6 +74,13 @@ struct skgpu_ctx {
     std::vector<double> h_t;
     std::vector<int32_t> h_end;
     std::vector<uint32_t> h_chunk, h_ch, h_flags;   // h_flags: SLOT_*
+    std::vector<double> h_li0;                      // initial last_index of the slot's resampler
+    // windowed-sinc mode
+    uint32_t sinc_L = 0, sinc_O = 0;
+    double sinc_cutoff = 0.0;
+    std::vector<double> sinc_fc;                    // cutoff of tap table i
+    std::vector<float *> sinc_tab_dev;
+    const float **d_sinc_tabs = nullptr;            // device array of the table pointers (capacity 256)
     std::vector<uint8_t> used;
     std::vector<uint32_t> free_list;
     uint32_t next_fresh = 0;
@@ -104,9 +111,13 @@ static skgpu_rc ctx_flush(skgpu_ctx *c) {
             up[i].end_idx = c->h_end[slot];
             up[i].flags = c->h_flags[slot];
             up[i].pad = 0;
+            up[i].last_index0 = c->h_li0[slot];
         }
         if (n > c->d_reset_cap) {
             if (c->d_reset) cudaFree(c->d_reset);
+    if (c->st.sinc_hist) cudaFree(c->st.sinc_hist);
+    for (float *t : c->sinc_tab_dev) cudaFree(t);
+    if (c->d_sinc_tabs) cudaFree(c->d_sinc_tabs);
             c->d_reset_cap = std::max<uint32_t>(n, 1024u);
             CU(dalloc(&c->d_reset, c->d_reset_cap));
         }
@@ -170,6 +181,7 @@ extern "C" skgpu_rc skgpu_ctx_create(int32_t device_ordinal, const skgpu_ctx_con
     c->h_chunk.assign(S, 0);
     c->h_ch.assign(S, 0);
     c->h_flags.assign(S, 0);
+    c->h_li0.assign(S, -4.0);
     c->used.assign(S, 0);
     *out = c;
     return SKGPU_OK;
@@ -183,6 +195,9 @@ extern "C" void skgpu_ctx_destroy(skgpu_ctx *c) {
     cudaFree(st.rec); cudaFree(st.hist); cudaFree(st.side);
     if (st.fifo) { cudaFree(st.fifo); cudaFree(st.fifo_w); cudaFree(st.fifo_r); }
     if (c->d_reset) cudaFree(c->d_reset);
+    if (c->st.sinc_hist) cudaFree(c->st.sinc_hist);
+    for (float *t : c->sinc_tab_dev) cudaFree(t);
+    if (c->d_sinc_tabs) cudaFree(c->d_sinc_tabs);
     if (c->l2buf) cudaFree(c->l2buf);
     cudaEventDestroy(c->tm0); cudaEventDestroy(c->tm1);
     for (auto &kv : c->pinned) {
@@ -311,6 +326,66 @@ extern "C" skgpu_rc skgpu_pinned_free(skgpu_ctx *c, void *p) {
     return SKGPU_OK;
 }
 
+// ------------------------------------------------------------------ windowed-sinc mode: parameters + tap tables
+
+// 4-term Blackman-Harris window, squared (rubato WindowFunction::BlackmanHarris2), on u in (0, 1)
+static double sinc_window(double u) {
+    const double two_pi = 6.283185307179586476925286766559;
+    const double w = 0.35875 - 0.48829 * std::cos(two_pi * u) + 0.14128 * std::cos(2.0 * two_pi * u) - 0.01168 * std::cos(3.0 * two_pi * u);
+    return w * w;
+}
+
+// index of the tap table for cutoff fc (built and uploaded on first use): T[p][n] = g(L/2 - 1 - n + p/O) / sum_n g, p = 0..O
+static int sinc_table_for(skgpu_ctx *c, double fc) {
+    for (size_t i = 0; i < c->sinc_fc.size(); ++i)
+        if (c->sinc_fc[i] == fc) return (int)i;
+    const uint32_t L = c->sinc_L, O = c->sinc_O;
+    const double pi = 3.14159265358979323846264338327950288;
+    std::vector<float> tab((size_t)(O + 1u) * L);
+    std::vector<double> g(L);
+    for (uint32_t p = 0; p <= O; ++p) {
+        double sum = 0.0;
+        for (uint32_t n = 0; n < L; ++n) {
+            const double tau = (double)L / 2.0 - 1.0 - (double)n + (double)p / (double)O;
+            const double z = fc * tau;
+            const double sc = z == 0.0 ? 1.0 : std::sin(pi * z) / (pi * z);
+            const double u = (tau + (double)L / 2.0) / (double)L;
+            const double w = (u <= 0.0 || u >= 1.0) ? 0.0 : sinc_window(u);
+            g[n] = fc * sc * w;
+            sum += g[n];
+        }
+        for (uint32_t n = 0; n < L; ++n) tab[(size_t)p * L + n] = (float)(g[n] / sum);
+    }
+    float *d = nullptr;
+    if (cudaMalloc((void **)&d, tab.size() * sizeof(float)) != cudaSuccess) return 0;
+    cudaMemcpy(d, tab.data(), tab.size() * sizeof(float), cudaMemcpyHostToDevice);
+    c->sinc_fc.push_back(fc);
+    c->sinc_tab_dev.push_back(d);
+    const float *dp = d;
+    cudaMemcpy(c->d_sinc_tabs + (c->sinc_fc.size() - 1), &dp, sizeof(dp), cudaMemcpyHostToDevice);
+    return (int)c->sinc_fc.size() - 1;
+}
+
+extern "C" skgpu_rc skgpu_ctx_set_sinc(skgpu_ctx *c, uint32_t sinc_len, uint32_t oversampling, double f_cutoff) {
+    if (!c) return fail(SKGPU_ERR_INVALID, "null context");
+    if (c->sinc_L) return fail(SKGPU_ERR_STATE, "sinc parameters are fixed for the context's lifetime");
+    if (sinc_len < 8 || sinc_len > 256 || sinc_len % 8) return fail(SKGPU_ERR_INVALID, "sinc_len must be a multiple of 8 in 8..256");
+    if (oversampling < 1 || oversampling > 1024) return fail(SKGPU_ERR_INVALID, "oversampling_factor must be in 1..1024");
+    if (!(f_cutoff > 0.0 && f_cutoff <= 1.0)) return fail(SKGPU_ERR_INVALID, "f_cutoff must be in (0, 1]");
+    CU(cudaSetDevice(c->device));
+    SlotTables &st = c->st;
+    const uint32_t H = sinc_len + 8u;
+    const size_t n = (size_t)c->cfg.max_streams * H * c->cfg.max_channels;
+    CU(dalloc(&st.sinc_hist, n));
+    CU(cudaMemset(st.sinc_hist, 0, n * sizeof(float)));
+    CU(cudaMalloc((void **)&c->d_sinc_tabs, 256 * sizeof(float *)));
+    CU(cudaMemset(c->d_sinc_tabs, 0, 256 * sizeof(float *)));
+    st.sinc_tabs = c->d_sinc_tabs;
+    st.sinc_L = sinc_len; st.sinc_O = oversampling; st.sinc_H = H;
+    c->sinc_L = sinc_len; c->sinc_O = oversampling; c->sinc_cutoff = f_cutoff;
+    return SKGPU_OK;
+}
+
 // ------------------------------------------------------------------ stream slots
 
 static skgpu_rc validate_stream_cfg(const skgpu_ctx *c, const skgpu_stream_cfg *s) {
@@ -321,7 +396,14 @@ static skgpu_rc validate_stream_cfg(const skgpu_ctx *c, const skgpu_stream_cfg *
     if (s->chunk_frames > (1u << 20)) return fail(SKGPU_ERR_INVALID, "chunk_frames too large");
     if (s->channels == 0 || s->channels > c->cfg.max_channels)
         return fail(SKGPU_ERR_INVALID, "channels %u outside 1..%u", (unsigned)s->channels, c->cfg.max_channels);
-    if (s->flags & ~(uint32_t)SKGPU_STREAM_S16) return fail(SKGPU_ERR_INVALID, "unknown stream flags 0x%x", (unsigned)s->flags);
+    if (s->flags & ~(uint32_t)(SKGPU_STREAM_S16 | SKGPU_STREAM_SINC)) return fail(SKGPU_ERR_INVALID, "unknown stream flags 0x%x", (unsigned)s->flags);
+    if (s->flags & SKGPU_STREAM_SINC) {
+        if (!c->sinc_L) return fail(SKGPU_ERR_STATE, "sinc streams need skgpu_ctx_set_sinc first");
+        if (s->flags & SKGPU_STREAM_S16) return fail(SKGPU_ERR_INVALID, "sinc streams take f32 chunks");
+        if (s->in_rate == s->out_rate) return fail(SKGPU_ERR_INVALID, "input rate equals the target rate: nothing to resample");
+        if (s->chunk_frames < c->sinc_L + 4u) return fail(SKGPU_ERR_INVALID, "chunk_frames %u too short for sinc_len %u", s->chunk_frames, c->sinc_L);
+        if (c->sinc_fc.size() >= 255) return fail(SKGPU_ERR_NOMEM, "too many distinct sinc cutoffs");
+    }
     if ((s->flags & SKGPU_STREAM_S16) && (((uint64_t)s->chunk_frames * s->channels) % 2u || (uint64_t)(s->chunk_frames + 32u) * s->channels > 4096u || s->channels > 2))
         return fail(SKGPU_ERR_INVALID, "s16 streams need mono / stereo chunks of an even number of samples, at most 4096 samples with the 32-frame head");
     const double ratio = (double)s->out_rate / (double)s->in_rate;
@@ -337,6 +419,13 @@ static void slot_configure(skgpu_ctx *c, uint32_t slot, const skgpu_stream_cfg *
     c->h_chunk[slot] = s->chunk_frames;
     c->h_ch[slot] = s->channels;
     c->h_flags[slot] = (s->in_rate == s->out_rate ? SLOT_BYPASS : 0u) | ((s->flags & SKGPU_STREAM_S16) ? SLOT_S16 : 0u);
+    c->h_li0[slot] = -4.0;                                            // rubato FastFixedIn: -(POLYNOMIAL_LEN / 2)
+    if (s->flags & SKGPU_STREAM_SINC) {
+        const int tab = sinc_table_for(c, c->sinc_cutoff * std::min(1.0, ratio));   // validated by the caller
+        c->h_flags[slot] |= SLOT_SINC | ((uint32_t)tab << 8);
+        c->h_end[slot] = (int32_t)s->chunk_frames - (int32_t)(c->sinc_L / 2u) - 1 - (int32_t)std::ceil(t);
+        c->h_li0[slot] = -(double)(c->sinc_L / 2u);
+    }
     c->used[slot] = 1;
     c->reset_list.push_back(slot);
 }
@@ -425,6 +514,7 @@ struct Op {
     int rs_channels = 0;          // resample: 1 / 2 specialisation, 0 = generic
     uint32_t mix_tpc = 1;         // mix: tiles one CTA handles (whole group for small groups)
     bool rs_prog = false;         // resample: program-driven kernels (k_phase_prog + k_resample_prog)
+    bool rs_sinc = false;         // resample: windowed-sinc streams (k_phase + k_resample_sinc)
     ChainProgDims rs_pd{};        // resample: frame-program capacities of the op
     uint64_t results_off = 0;
     bool has_fifo_inputs = false;
@@ -664,6 +754,8 @@ static skgpu_rc validate_rs(const skgpu_plan *p, const skgpu_rs_item *items, uin
         const uint32_t N = c->h_chunk[slot], C = c->h_ch[slot];
         if (c->h_flags[slot] & SLOT_BYPASS) return fail(SKGPU_ERR_INVALID, "resample item %u: the stream's input rate equals its target rate: the reference bypasses the resampler for such inputs (resampler.rs:299-373); mix them directly or use the chain op", i);
         if (c->h_flags[slot] & SLOT_S16) return fail(SKGPU_ERR_INVALID, "resample item %u: s16 streams are a chain-op feature (convert with SKGPU_CVT_S16_TO_F32 first)", i);
+        if (((c->h_flags[slot] & SLOT_SINC) != 0) != ((c->h_flags[items[0].slot] & SLOT_SINC) != 0)) return fail(SKGPU_ERR_INVALID, "resample item %u: linear and sinc streams cannot share one resample op", i);
+        if ((c->h_flags[slot] & SLOT_SINC) && (items[i].flags & SKGPU_RS_TO_FIFO)) return fail(SKGPU_ERR_INVALID, "resample item %u: sinc streams write to out_off, not to the device ring", i);
         skgpu_rc rc = check_range(p, items[i].in_off, (uint64_t)N * C * 4, "resample input");
         if (rc) return rc;
         if (items[i].in_off % 4) return fail(SKGPU_ERR_INVALID, "resample item %u: misaligned input", i);
@@ -772,8 +864,15 @@ extern "C" skgpu_rc skgpu_plan_add_resample(skgpu_plan *p, const skgpu_rs_item *
     op.max_unit = std::max(mx, 1u);
     op.rs_channels = ch;
     op.results_off = results_off;
-    op.rs_prog = n > 0 && rs_prog_dims(p->ctx, items, n, &op.rs_pd);
-    rs_size_smem(p->ctx, op);
+    op.rs_sinc = n > 0 && (p->ctx->h_flags[items[0].slot] & SLOT_SINC) != 0;
+    if (op.rs_sinc) {
+        if (ch != 1 && ch != 2) return fail(SKGPU_ERR_INVALID, "sinc resample op: mono or stereo streams of one channel count");
+        op.smem_bytes = (uint32_t)((((uint64_t)(op.max_unit + p->ctx->st.sinc_H) * (uint32_t)ch * 4u) + 15u) & ~15ull);
+        if (op.smem_bytes > 200u * 1024u) return fail(SKGPU_ERR_INVALID, "sinc resample op: chunk too large for shared-memory staging");
+    } else {
+        op.rs_prog = n > 0 && rs_prog_dims(p->ctx, items, n, &op.rs_pd);
+        rs_size_smem(p->ctx, op);
+    }
     if (op_out) *op_out = (uint32_t)p->ops.size();
     p->ops.push_back(op);
     return SKGPU_OK;
@@ -789,6 +888,8 @@ extern "C" skgpu_rc skgpu_plan_update_resample(skgpu_plan *p, uint32_t opi, cons
     skgpu_rc rc = validate_rs(p, items, n, &mx, &ch, &fifo);
     if (rc) return rc;
     if (n && ch != op.rs_channels && op.rs_channels != 0) return fail(SKGPU_ERR_INVALID, "update changes the op's channel specialisation (%d -> %d)", op.rs_channels, ch);
+    if (n && op.rs_sinc != ((p->ctx->h_flags[items[0].slot] & SLOT_SINC) != 0)) return fail(SKGPU_ERR_INVALID, "update changes the op's interpolation mode");
+    if (op.rs_sinc && mx > op.max_unit) return fail(SKGPU_ERR_INVALID, "update has a longer chunk (%u) than the op was sized for (%u)", mx, op.max_unit);
     if (op.smem_frames && mx + 16u > op.smem_frames) return fail(SKGPU_ERR_INVALID, "update has a longer chunk (%u) than the op was sized for (%u)", mx, op.smem_frames - 16u);
     if (op.rs_prog && n) {
         ChainProgDims d{};
@@ -1006,6 +1107,7 @@ static skgpu_rc validate_chain(const skgpu_plan *p, const skgpu_chain_group *g, 
         if (C != 1 && C != 2) return fail(SKGPU_ERR_INVALID, "chain input %u: %u channels (the fused chain handles mono and stereo)", i, C);
         if (N < 16) return fail(SKGPU_ERR_INVALID, "chain input %u: chunk_frames %u < 16", i, N);
         const bool bypass = (c->h_flags[slot] & SLOT_BYPASS) != 0, s16 = (c->h_flags[slot] & SLOT_S16) != 0;
+        if (c->h_flags[slot] & SLOT_SINC) return fail(SKGPU_ERR_INVALID, "chain input %u: sinc streams belong to a resample op (the fused chain reproduces the reference's linear interpolation)", i);
         // nominal frames per chunk must equal the packet size: a packet then never spans more than two chunks
         const double nominal = (double)N / c->h_t[slot];
         if (bypass ? N != F : std::fabs(nominal - (double)F) > 0.5)
@@ -1369,11 +1471,14 @@ static skgpu_rc launch_ops(skgpu_plan *p, bool time_ops) {
         } else if (op.kind == OP_RESAMPLE) {
             const skgpu_rs_item *items = (const skgpu_rs_item *)op.d_tab;
             if (time_ops) { skgpu_rc rc = op_event(op, 0, false, s); if (rc) return rc; }
-            if (op.rs_prog) k_phase_prog<<<(op.cap + PHASE_THREADS - 1) / PHASE_THREADS, PHASE_THREADS, 0, s>>>(op.d_hdr, items, c->st, p->arena, op.results_off, op.rs_pd);
+            if (op.rs_sinc) k_phase<<<(op.cap + PHASE_THREADS - 1) / PHASE_THREADS, PHASE_THREADS, 0, s>>>(op.d_hdr, items, c->st, p->arena, op.results_off);
+            else if (op.rs_prog) k_phase_prog<<<(op.cap + PHASE_THREADS - 1) / PHASE_THREADS, PHASE_THREADS, 0, s>>>(op.d_hdr, items, c->st, p->arena, op.results_off, op.rs_pd);
             else k_phase<<<(op.cap + PHASE_THREADS - 1) / PHASE_THREADS, PHASE_THREADS, 0, s>>>(op.d_hdr, items, c->st, p->arena, op.results_off);
             CU(cudaGetLastError());
             if (time_ops) { skgpu_rc rc = op_event(op, 0, true, s); if (rc) return rc; rc = op_event(op, 1, false, s); if (rc) return rc; }
-            if (op.rs_prog && op.rs_channels == 2) k_resample_prog<2><<<op.cap, RSP_THREADS, op.smem_bytes, s>>>(op.d_hdr, items, c->st, p->arena, op.smem_frames, op.rs_pd);
+            if (op.rs_sinc && op.rs_channels == 2) k_resample_sinc<2><<<op.cap, SINC_THREADS, op.smem_bytes, s>>>(op.d_hdr, items, c->st, p->arena);
+            else if (op.rs_sinc) k_resample_sinc<1><<<op.cap, SINC_THREADS, op.smem_bytes, s>>>(op.d_hdr, items, c->st, p->arena);
+            else if (op.rs_prog && op.rs_channels == 2) k_resample_prog<2><<<op.cap, RSP_THREADS, op.smem_bytes, s>>>(op.d_hdr, items, c->st, p->arena, op.smem_frames, op.rs_pd);
             else if (op.rs_prog) k_resample_prog<1><<<op.cap, RSP_THREADS, op.smem_bytes, s>>>(op.d_hdr, items, c->st, p->arena, op.smem_frames, op.rs_pd);
             else if (op.rs_channels == 2) k_resample<2><<<op.cap, RS_THREADS, op.smem_bytes, s>>>(op.d_hdr, items, c->st, p->arena, op.smem_frames);
             else if (op.rs_channels == 1) k_resample<1><<<op.cap, RS_THREADS, op.smem_bytes, s>>>(op.d_hdr, items, c->st, p->arena, op.smem_frames);
@@ -1422,7 +1527,9 @@ extern "C" skgpu_rc skgpu_plan_finalize(skgpu_plan *p) {
     }
     for (auto &op : p->ops) {
         if (op.kind == OP_RESAMPLE && op.smem_bytes > 48u * 1024u) {
-            if (op.rs_prog && op.rs_channels == 2) CU(cudaFuncSetAttribute(k_resample_prog<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)op.smem_bytes));
+            if (op.rs_sinc && op.rs_channels == 2) CU(cudaFuncSetAttribute(k_resample_sinc<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)op.smem_bytes));
+            else if (op.rs_sinc) CU(cudaFuncSetAttribute(k_resample_sinc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)op.smem_bytes));
+            else if (op.rs_prog && op.rs_channels == 2) CU(cudaFuncSetAttribute(k_resample_prog<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)op.smem_bytes));
             else if (op.rs_prog) CU(cudaFuncSetAttribute(k_resample_prog<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)op.smem_bytes));
             else if (op.rs_channels == 2) CU(cudaFuncSetAttribute(k_resample<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)op.smem_bytes));
             else if (op.rs_channels == 1) CU(cudaFuncSetAttribute(k_resample<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)op.smem_bytes));

@@ -21,7 +21,7 @@ MIX_IN_UNIQUE, MIX_IN_FIFO = 1, 2
 MIX_OUT_S16 = 1
 SUBMIT_NO_H2D, SUBMIT_NO_D2H, SUBMIT_GRAPH, SUBMIT_TIME_OPS, SUBMIT_OVERLAP_D2H, SUBMIT_SLICED = 1, 2, 4, 8, 16, 32
 PIN_NUMA_LOCAL, PIN_WRITE_COMBINED = 1, 2
-STREAM_S16 = 1
+STREAM_S16, STREAM_SINC = 1, 2
 
 
 class CtxConfig(C.Structure):
@@ -72,7 +72,7 @@ EXPORTS = [
     "skgpu_arena_download", "skgpu_arena_fill", "skgpu_timer_start", "skgpu_timer_stop", "skgpu_timer_elapsed_ms",
     "skgpu_ctx_sync", "skgpu_ctx_flush_l2",
     "skgpu_pinned_alloc_ex", "skgpu_ctx_numa_node", "skgpu_ctx_bind_thread", "skgpu_plan_set_slices", "skgpu_plan_auto_slices",
-    "skgpu_tick_slice_timing",
+    "skgpu_tick_slice_timing", "skgpu_ctx_set_sinc",
 ]
 
 _lib = None
@@ -139,6 +139,7 @@ def load() -> C.CDLL:
         "skgpu_plan_set_slices": (i32, [vp, u32, vp, u32]),
         "skgpu_plan_auto_slices": (i32, [vp, u32, u32]),
         "skgpu_tick_slice_timing": (i32, [vp, u64, C.POINTER(SliceTiming), u32, C.POINTER(u32)]),
+        "skgpu_ctx_set_sinc": (i32, [vp, u32, u32, C.c_double]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)
@@ -186,6 +187,10 @@ class Context:
         sm, ma, mi = C.c_int32(), C.c_int32(), C.c_int32()
         _chk(self.lib.skgpu_ctx_device_info(self.h, name, 128, C.byref(sm), C.byref(ma), C.byref(mi)))
         return name.value.decode(), sm.value, ma.value, mi.value
+
+    def set_sinc(self, sinc_len: int = 64, oversampling: int = 256, f_cutoff: float = 0.95):
+        """enable the windowed-sinc polyphase mode for STREAM_SINC streams (spec: include/skgpu_batch.h skgpu_ctx_set_sinc)"""
+        _chk(self.lib.skgpu_ctx_set_sinc(self.h, sinc_len, oversampling, f_cutoff))
 
     def numa_node(self) -> int:
         return self.lib.skgpu_ctx_numa_node(self.h)

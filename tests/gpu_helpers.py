@@ -17,9 +17,9 @@ def bits(a):
 class GpuResampler:
     """n_streams identical-configuration resampler streams driven chunk by chunk through a resample op"""
 
-    def __init__(self, ctx, in_rate, out_rate, chunk, channels, n_streams=1):
+    def __init__(self, ctx, in_rate, out_rate, chunk, channels, n_streams=1, flags=0):
         self.ctx, self.chunk, self.channels, self.n = ctx, chunk, channels, n_streams
-        self.slots = [ctx.stream_open(in_rate, out_rate, chunk, channels) for _ in range(n_streams)]
+        self.slots = [ctx.stream_open(in_rate, out_rate, chunk, channels, flags) for _ in range(n_streams)]
         cap = L.Context.max_out_frames(in_rate, out_rate, chunk, channels)
         self.in_stride = al(chunk * channels * 4, 16)
         self.out_stride = al(cap * channels * 4, 16)
