@@ -115,9 +115,6 @@ static skgpu_rc ctx_flush(skgpu_ctx *c) {
         }
         if (n > c->d_reset_cap) {
             if (c->d_reset) cudaFree(c->d_reset);
-    if (c->st.sinc_hist) cudaFree(c->st.sinc_hist);
-    for (float *t : c->sinc_tab_dev) cudaFree(t);
-    if (c->d_sinc_tabs) cudaFree(c->d_sinc_tabs);
             c->d_reset_cap = std::max<uint32_t>(n, 1024u);
             CU(dalloc(&c->d_reset, c->d_reset_cap));
         }
@@ -192,17 +189,22 @@ extern "C" void skgpu_ctx_destroy(skgpu_ctx *c) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     SlotTables &st = c->st;
-    cudaFree(st.rec); cudaFree(st.hist); cudaFree(st.side);
-    if (st.fifo) { cudaFree(st.fifo); cudaFree(st.fifo_w); cudaFree(st.fifo_r); }
-    if (c->d_reset) cudaFree(c->d_reset);
-    if (c->st.sinc_hist) cudaFree(c->st.sinc_hist);
-    for (float *t : c->sinc_tab_dev) cudaFree(t);
-    if (c->d_sinc_tabs) cudaFree(c->d_sinc_tabs);
-    if (c->l2buf) cudaFree(c->l2buf);
-    cudaEventDestroy(c->tm0); cudaEventDestroy(c->tm1);
+#define TEARDOWN(call)                                                                                                  \
+    do {                                                                                                                \
+        const cudaError_t e__ = (call);                                                                                 \
+        if (e__ != cudaSuccess) { fprintf(stderr, "streamkit_b200: %s failed during teardown: %s\n", #call, cudaGetErrorString(e__)); cudaGetLastError(); } \
+    } while (0)
+    TEARDOWN(cudaFree(st.rec)); TEARDOWN(cudaFree(st.hist)); TEARDOWN(cudaFree(st.side));
+    if (st.fifo) { TEARDOWN(cudaFree(st.fifo)); TEARDOWN(cudaFree(st.fifo_w)); TEARDOWN(cudaFree(st.fifo_r)); }
+    if (c->d_reset) TEARDOWN(cudaFree(c->d_reset));
+    if (st.sinc_hist) TEARDOWN(cudaFree(st.sinc_hist));
+    for (float *t : c->sinc_tab_dev) TEARDOWN(cudaFree(t));
+    if (c->d_sinc_tabs) TEARDOWN(cudaFree((void *)c->d_sinc_tabs));
+    if (c->l2buf) TEARDOWN(cudaFree(c->l2buf));
+    TEARDOWN(cudaEventDestroy(c->tm0)); TEARDOWN(cudaEventDestroy(c->tm1));
     for (auto &kv : c->pinned) {
-        if (kv.second.kind == 1) { cudaHostUnregister(kv.first); munmap(kv.first, kv.second.bytes); }
-        else cudaFreeHost(kv.first);
+        if (kv.second.kind == 1) { TEARDOWN(cudaHostUnregister(kv.first)); munmap(kv.first, kv.second.bytes); }
+        else TEARDOWN(cudaFreeHost(kv.first));
     }
     cudaStreamDestroy(c->stream_k);
     cudaStreamDestroy(c->stream_p);
@@ -644,6 +646,7 @@ extern "C" void skgpu_plan_destroy(skgpu_plan *p) {
     dyn_free(p->gains);
     if (p->graph_exec) cudaGraphExecDestroy(p->graph_exec);
     if (p->graph) cudaGraphDestroy(p->graph);
+    { cudaError_t e = cudaGetLastError(); if (e != cudaSuccess) fprintf(stderr, "skgpu_plan_destroy: stale CUDA error: %s\n", cudaGetErrorString(e)); }
     cudaFree(p->arena);
     cudaFree(p->d_tick);
     cudaEventDestroy(p->ev_kernels_done); cudaEventDestroy(p->ev_d2h_done);
