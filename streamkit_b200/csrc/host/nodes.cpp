@@ -476,19 +476,25 @@ bool AudioMixerNode::run(const std::vector<AudioFrame> &frames, uint16_t oc, siz
     }
     const size_t in_bytes = align_up(std::max<size_t>(off, 16), 256);
     const size_t out_bytes = out_frames * oc * 4;
-    skgpu_mix_group g{in_bytes, 0, (uint32_t)frames.size(), (uint32_t)out_frames, oc, 0, SKGPU_NO_GAIN, 0};
-    skgpu_plan *plan = nullptr;
-    if (skgpu_plan_create(rt.ctx(), align_up(in_bytes + std::max<size_t>(out_bytes, 16), 256), &plan) != SKGPU_OK) { if (err) *err = rt_err("skgpu_plan_create"); return false; }
-    std::vector<uint8_t> host_in(in_bytes, 0);
-    for (size_t i = 0; i < frames.size(); ++i) std::memcpy(host_in.data() + ins[i].in_off, frames[i].samples.data(), frames[i].samples.size() * 4);
+    // shape of this mix: reuse the compiled plan while it stays the same (the steady state of a pipeline)
+    std::vector<uint64_t> shape{(uint64_t)oc, (uint64_t)out_frames};
+    for (const AudioFrame &f : frames) shape.push_back(((uint64_t)f.samples.size() << 32) | ((uint64_t)f.channels << 8) | (f.unique ? 1u : 0u));
+    if (!ph_.plan || shape != shape_) {
+        ph_.reset();
+        skgpu_mix_group g{in_bytes, 0, (uint32_t)frames.size(), (uint32_t)out_frames, oc, 0, SKGPU_NO_GAIN, 0};
+        if (skgpu_plan_create(rt.ctx(), align_up(in_bytes + std::max<size_t>(out_bytes, 16), 256), &ph_.plan) != SKGPU_OK) { if (err) *err = rt_err("skgpu_plan_create"); return false; }
+        const bool built = skgpu_plan_add_mix(ph_.plan, &g, 1, ins.data(), (uint32_t)ins.size(), nullptr) == SKGPU_OK &&
+                           skgpu_plan_set_io(ph_.plan, 0, in_bytes, in_bytes, out_bytes) == SKGPU_OK && skgpu_plan_finalize(ph_.plan) == SKGPU_OK;
+        if (!built) { if (err) *err = rt_err("gpu mix plan"); ph_.reset(); return false; }
+        shape_ = shape;
+        host_in_.assign(in_bytes, 0);
+    }
+    for (size_t i = 0; i < frames.size(); ++i) std::memcpy(host_in_.data() + ins[i].in_off, frames[i].samples.data(), frames[i].samples.size() * 4);
     out.sample_rate = rate;
     out.channels = oc;
     out.samples.assign(out_frames * oc, 0.0f);
-    bool ok = skgpu_plan_add_mix(plan, &g, 1, ins.data(), (uint32_t)ins.size(), nullptr) == SKGPU_OK &&
-              skgpu_plan_set_io(plan, 0, in_bytes, in_bytes, out_bytes) == SKGPU_OK && skgpu_plan_finalize(plan) == SKGPU_OK &&
-              skgpu_tick_submit(plan, host_in.data(), out.samples.data(), 0) == SKGPU_OK && skgpu_tick_wait(plan, nullptr) == SKGPU_OK;
+    const bool ok = skgpu_tick_submit(ph_.plan, host_in_.data(), out.samples.data(), SKGPU_SUBMIT_GRAPH) == SKGPU_OK && skgpu_tick_wait(ph_.plan, nullptr) == SKGPU_OK;
     if (!ok && err) *err = rt_err("gpu mix");
-    skgpu_plan_destroy(plan);
     return ok;
 }
 

@@ -174,6 +174,11 @@ class AudioMixerNode {
     bool run(const std::vector<AudioFrame> &frames, uint16_t oc, size_t out_frames, uint32_t rate, AudioFrame &out, StreamKitError *err);
     AudioMixerConfig cfg_;
     uint16_t max_channels_seen_ = 0;
+    // the compiled tick of the current packet shape: a steady stream of equally shaped mixes is one submit each, not a
+    // plan build + graph capture + teardown per mix
+    PlanHolder ph_;
+    std::vector<uint64_t> shape_;
+    std::vector<uint8_t> host_in_;
 };
 
 uint64_t duration_us_for_frames(uint32_t sample_rate, size_t frames_per_channel);   // resampler.rs:108-116

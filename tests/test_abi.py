@@ -121,3 +121,17 @@ def test_plugin_libraries_export_the_entry_point_and_metadata_without_a_gpu():
         if not _gpu_present():
             with pytest.raises(ph.PluginError, match="failed to create instance"):
                 p.create('{"gain": 1.0, "target_sample_rate": 48000}')
+
+
+def test_abi_v3_header_compiles_as_c_and_v3_plugin_exports_version_3():
+    import tempfile
+    root = ROOT
+    with tempfile.TemporaryDirectory() as d:
+        open(os.path.join(d, "t.c"), "w").write('#include "streamkit_native_abi_v3.h"\nint main(void){ return sizeof(sk_native_plugin_api_v3) == 80 && sizeof(sk_packet_v3) == 32 ? 0 : 1; }\n')
+        subprocess.check_call(["gcc", "-std=c11", "-Wall", "-Werror", "-I", os.path.join(root, "include"), "-o", os.path.join(d, "t"), os.path.join(d, "t.c")])
+        assert subprocess.call([os.path.join(d, "t")]) == 0
+    lib = C.CDLL(os.path.join(ROOT, "streamkit_b200", "csrc", "libskgpu_plugin_mixer_v3.so"))
+    lib.streamkit_native_plugin_api.restype = C.POINTER(C.c_uint32)
+    assert lib.streamkit_native_plugin_api()[0] == 3
+
+

@@ -260,3 +260,67 @@ def test_resampler_node_timestamp_duration_sequence_match_the_oracle(in_rate, ta
             assert [p["sequence"] for p in node.out[:-1]] == list(range(len(node.out) - 1))
     finally:
         node.close()
+
+
+# ------------------------------------------------------------------ PROPOSED ABI v3: C host + GPU mixer plugin
+
+def _lcg_inputs(n_in, rounds, s16):
+    seed = np.uint32(12345)
+    outs = []
+    state = int(seed)
+    for _ in range(rounds):
+        per = []
+        for _i in range(n_in):
+            v = np.empty(1920, np.int32)
+            for k in range(1920):
+                state = (state * 1664525 + 1013904223) & 0xFFFFFFFF
+                v[k] = (state >> 16) - 32768
+            if s16:
+                per.append(sko.s16_to_f32(v.astype(np.int16)))
+            else:
+                per.append((v.astype(np.float32) * np.float32(1.0 / 32768.0) * np.float32(0.75)).astype(np.float32))
+        outs.append(per)
+    return outs
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n_in,in_fmt,out_fmt", [(3, "f32", "s16"), (2, "s16", "f32"), (1, "f32", "f32")])
+def test_abi_v3_c_host_drives_the_gpu_mixer_plugin(n_in, in_fmt, out_fmt, tmp_path):
+    """tests/host/host_v3.c (a C host, like crates/plugin-native loads plugins) against libskgpu_plugin_mixer_v3.so: dynamic pins,
+    batched process_packets, s16 payloads in / out, metadata passthrough; output bytes checked against the oracle's mixer."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "host_v3")
+    subprocess.check_call(["gcc", "-std=c11", "-O1", "-Wall", "-o", exe, os.path.join(root, "tests", "host", "host_v3.c"), "-ldl"])
+    rounds, gain = 3, 1.5
+    out_file = str(tmp_path / "out.bin")
+    res = subprocess.run([exe, os.path.join(CSRC, "libskgpu_plugin_mixer_v3.so"), '{"gain": %r, "output_format": "%s"}' % (gain, out_fmt), str(n_in), in_fmt,
+                          str(rounds), out_file], capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr
+    lines = res.stdout.strip().splitlines()
+    assert lines[0] == "kind gpu_mixer inputs 1 cardinality 1 prefix in accepts 2"
+    pk = [ln.split() for ln in lines if ln.startswith("packet ")]
+    assert len(pk) == rounds + 1 and lines[-1] == "packets %d" % (rounds + 1)
+    assert "update_params(gain 9.0) success 0" in lines
+    ins = _lcg_inputs(n_in, rounds, in_fmt == "s16")
+    raw = open(out_file, "rb").read()
+    bps = 2 if out_fmt == "s16" else 4
+    off = 0
+    for r in range(rounds + 1):
+        if r < rounds:
+            n_used = n_in - 1 if (r == rounds - 1 and n_in > 1) else n_in       # the removed pin's frame is not mixed
+            frames = [(ins[r][i], 2, True) for i in range(n_used)]
+            ts, seq = 1000000 + 20000 * r, 100 + r                               # the mix carries the FIRST frame's metadata (mixer.rs:994)
+        else:
+            first = (_lcg_inputs(n_in, rounds, False)[rounds - 1][0])           # the host re-sends the f32 buffer of input 0 (last round)
+            frames = [(first, 2, True)]
+            ts = seq = None
+        mixed, oc = sko.mix_sync(frames)
+        want = sko.gain_f32_to_s16(mixed, gain) if out_fmt == "s16" else sko.gain(mixed, gain)
+        got = np.frombuffer(raw[off: off + 1920 * bps], dtype=np.int16 if out_fmt == "s16" else np.float32)
+        off += 1920 * bps
+        assert np.array_equal(got.view(np.uint16 if out_fmt == "s16" else np.uint32), want.view(np.uint16 if out_fmt == "s16" else np.uint32)), f"packet {r}"
+        f = pk[r]
+        assert int(f[1]) == 1920 * bps and f[3] == "48000" and f[5] == "2" and f[7] == ("1" if out_fmt == "s16" else "0")
+        assert f[9] == (str(ts) if ts is not None else "-") and f[11] == (str(seq) if seq is not None else "-")
+    assert off == len(raw)
