@@ -765,6 +765,10 @@ def run_chain(args, D: Dist) -> None:
         D.emit(line)
 
 
+def sms_of(ctx) -> int:
+    return ctx.device_info()[1]
+
+
 def run_node(args, D: Dist) -> None:
     """BASELINE configs[1..3]: the standalone node kernels, same JSON contract"""
     from oracle import sko
@@ -779,7 +783,8 @@ def run_node(args, D: Dist) -> None:
         ctx = L.Context(device=local_rank, max_streams=16, max_channels=2)
         w = W.Mix64(ctx, s16=True)
     else:
-        w = W.Resample(48000, 16000, 16384, local_rank) if args.rs_down else W.Resample(IN_RATE, OUT_RATE, 16384, local_rank)
+        sinc = (64, 256, 0.95) if args.sinc else None
+        w = W.Resample(48000, 16000, 16384, local_rank, sinc=sinc) if args.rs_down else W.Resample(44100, OUT_RATE, 16384, local_rank, sinc=sinc)
     plan, wctx = w.plan, w.ctx
     metric, unit, cpu_units = NODE_META[args.config]
     host_in = wctx.pinned(w.in_bytes, np.uint8)
@@ -831,7 +836,18 @@ def run_node(args, D: Dist) -> None:
         else:
             n = w.S
             ticks = int(plan.tick_count())
-            _s, want_f, cnt = sko.node_bench(2, n, ticks, w.base, None, cores, in_rate=w.in_rate, out_rate=w.out_rate, want_last=True, cap=w.cap)
+            if args.sinc:   # the sinc oracle, stream class by stream class (256 distinct inputs tiled over the streams)
+                D_ = w.base.shape[0]
+                refs = [sko.SincFixedIn(w.in_rate, w.out_rate, w.chunk, 2, 64, 256, 0.95) for _ in range(D_)]
+                last = None
+                for _t in range(ticks):
+                    last = [r.process(w.base[i]) for i, r in enumerate(refs)]
+                cnt = np.array([last[i % D_].size // 2 for i in range(n)], dtype=np.uint32)
+                want_f = np.zeros((n, w.cap * 2), np.float32)
+                for i in range(n):
+                    want_f[i, : last[i % D_].size] = last[i % D_]
+            else:
+                _s, want_f, cnt = sko.node_bench(2, n, ticks, w.base, None, cores, in_rate=w.in_rate, out_rate=w.out_rate, want_last=True, cap=w.cap)
             res = host_out[: 8 * n].view(L.RS_RESULT_DT)
             o0 = w.out_off - w.res_off
             outs = host_out[o0: o0 + n * w.out_stride].reshape(n, w.out_stride)[:, : w.cap * 8].copy().view(np.float32)
@@ -847,7 +863,7 @@ def run_node(args, D: Dist) -> None:
     if rank == 0:
         peak, peak_src = hbm_peak()
         achieved = w.algorithmic_bytes / (main_ms * 1e-3) / 1e9
-        traffic, traffic_src = ncu_traffic({2: "k_convert<1", 3: "k_mix", 4: "k_resample_prog<2"}[args.config]) if not args.rs_down else (None, "no capture of 48k->16k")
+        traffic, traffic_src = ncu_traffic({2: "k_convert<1", 3: "k_mix", 4: "k_resample_sinc<2" if args.sinc else "k_resample_prog<2"}[args.config]) if not args.rs_down else (None, "no capture of 48k->16k")
         cpu_node(args.config, cpu_units, 2, cores)
         cpu_iters = 20
         cpu_sec = cpu_node(args.config, cpu_units, cpu_iters, cores)
@@ -875,6 +891,13 @@ def run_node(args, D: Dist) -> None:
             "cpu_baseline": {"value": cpu_value, "unit": unit, "cores": cores, "kind": "port",
                              "sample": "%d %s x %d passes on %d host threads (oracle/sk_chain.c sko_node_bench); units sustained in real time" % (cpu_units, unit, cpu_iters, cores)},
         }
+        if getattr(w, "fma_per_launch", None):
+            # the sinc mode is bound by the FMA / LSU pipes (16 fma per byte moved), not by HBM: say how far from the FP32 peak it runs
+            peak_fma = sms_of(wctx) * 128 * (clk.get("sm_mhz") or 1965.0) * 1e6
+            line["roofline"]["fma"] = {"fma_per_launch": w.fma_per_launch, "achieved_tfma_s": w.fma_per_launch / (main_ms * 1e-3) / 1e12,
+                                       "peak_tfma_s": peak_fma / 1e12, "frac": w.fma_per_launch / (main_ms * 1e-3) / peak_fma,
+                                       "what": "f32 fused multiply-adds of the two tap-row dot products vs SMs x 128 lanes x SM clock"}
+            line["cpu_baseline"]["note"] = "CPU arm of this line is the LINEAR resampler (the reference has no sinc mode)"
         D.emit(line)
     w.close()
     if ctx is not None:
@@ -897,6 +920,7 @@ def main() -> None:
     ap.add_argument("--kslices", type=int, default=8, help="slices of the device-resident tick (phase / chain kernel overlap); 1 = whole-tick launches")
     ap.add_argument("--unfused", action="store_true", help="use the general unfused ops (k_resample_prog -> ring -> k_mix)")
     ap.add_argument("--rs-down", action="store_true", help="--config 4: 48k->16k instead of 44.1k->48k")
+    ap.add_argument("--sinc", action="store_true", help="--config 4: the windowed-sinc polyphase mode (sinc_len 64, oversampling 256) instead of rubato's Linear")
     ap.add_argument("--ref-sessions", type=int, default=8192, help="bounded session sample of the CPU arm")
     ap.add_argument("--parity-sessions", type=int, default=256, help="sessions of the timed run compared with the CPU chain (0 = skip)")
     ap.add_argument("--no-hub", dest="hub", action="store_false", help="skip the frame-batching-layer end-to-end measurement")

@@ -44,7 +44,7 @@ struct SlotCfgUpload {     // host -> device (re)configuration of one slot (k_co
     double t_ratio;
     uint32_t slot, chunk, channels;
     int32_t end_idx;
-    uint32_t flags, pad;
+    uint32_t flags, aux;   // aux: sinc streams: the sub-phase period in outputs (kept in SlotRec.carry, which only chain streams use)
     double last_index0;    // rubato's initial last_index: -4.0 (FastFixedIn, POLYNOMIAL_LEN / 2), -(sinc_len / 2) in sinc mode
 };
 
@@ -64,7 +64,7 @@ struct SlotTables {     // per-stream state + configuration, all device pointers
     uint32_t fifo_frames;   // power of two
     // windowed-sinc mode (k_sinc.cuh); null / 0 until skgpu_ctx_set_sinc
     float *sinc_hist;                  // [slot][sinc_H * max_channels]: the last sinc_H input frames
-    const float *const *sinc_tabs;     // tap tables [(sinc_O + 1)][sinc_L], one per distinct cutoff
+    const float *const *sinc_tabs;     // tap tables [(sinc_O + 1)][sinc_L + 4], one per distinct cutoff
     uint32_t sinc_L, sinc_O, sinc_H, sinc_pad;
 };
 
@@ -240,7 +240,7 @@ __global__ void k_config_slots(const SlotCfgUpload *__restrict__ cfgs, uint32_t 
         r.chunk = c.chunk;
         r.channels = c.channels;
         r.chunk_count = 0;
-        r.carry = 0;
+        r.carry = (c.flags & SLOT_SINC) ? c.aux : 0u;
         r.n_out[0] = r.n_out[1] = 0;
         r.n_prefix[0] = r.n_prefix[1] = 0;
         r.n_runs[0] = r.n_runs[1] = 0;

@@ -235,122 +235,4 @@ __global__ void __launch_bounds__(PHASE_THREADS, 14) k_phase_prog(const OpHeader
     reinterpret_cast<skgpu_rs_result *>(arena + results_off)[i] = res;
 }
 
-template <int C>  // 1 | 2
-__global__ void __launch_bounds__(RSP_THREADS) k_resample_prog(const OpHeader *__restrict__ hdr, const skgpu_rs_item *__restrict__ items,
-                                                              SlotTables st, uint8_t *__restrict__ arena, uint32_t smem_frames, ChainProgDims pd) {
-    extern __shared__ __align__(16) uint8_t smem_raw[];   // [program (prog_cap) | 16 history frames | chunk]
-    __shared__ __align__(8) uint64_t bar;
-
-    const uint32_t i = blockIdx.x;
-    if (i >= hdr->count) return;
-    const skgpu_rs_item it = items[i];
-    const uint32_t slot = it.slot;
-    const SlotRec rec = st.rec[slot];
-    const uint32_t N = rec.chunk;
-    const bool to_fifo = (it.flags & SKGPU_RS_TO_FIFO) != 0;
-    const uint32_t par = (rec.chunk_count - 1u) & 1u;   // the chunk k_phase_prog just processed
-    const uint32_t n_total = par ? rec.n_out[1] : rec.n_out[0];
-    const uint32_t n_exp = par ? rec.n_prefix[1] : rec.n_prefix[0];
-    const bool prog_ok = ((rec.overflow >> par) & 1u) == 0u;
-
-    const uint32_t prog_cap = skc_prog_cap(pd);
-    float *buf = reinterpret_cast<float *>(smem_raw + prog_cap);  // [(16 + N) * C]: history then chunk, interleaved
-    float *hist_g = st.hist + (size_t)slot * 16u * st.max_channels;
-    const float *in_g = reinterpret_cast<const float *>(arena + it.in_off);
-    const uint32_t hist_bytes = 16u * C * 4u;
-    const uint32_t in_bytes = N * C * 4u;
-    const uint32_t prog_bytes = (skc_exp_off(pd) + n_exp * 8u + 15u) & ~15u;
-    const bool tma_ok = ((in_bytes & 15u) == 0) && ((((uintptr_t)in_g) & 15u) == 0);
-    if (threadIdx.x == 0) {
-        mbar_init(&bar, 1);
-        mbar_fence_init();
-        mbar_expect_tx(&bar, prog_bytes + hist_bytes + (tma_ok ? in_bytes : 0u));
-        tma_bulk_g2s(smem_raw, slot_side(st, slot, par), prog_bytes, &bar);
-        tma_bulk_g2s(buf, hist_g, hist_bytes, &bar);
-        if (tma_ok) tma_bulk_g2s(buf + 16u * C, in_g, in_bytes, &bar);
-    }
-    if (!tma_ok)
-        for (uint32_t s = threadIdx.x; s < N * C; s += RSP_THREADS) buf[16u * C + s] = in_g[s];
-    __syncthreads();
-    mbar_wait(&bar, 0);
-
-    const uint32_t n_out = prog_ok ? (to_fifo ? n_total : min(n_total, it.out_cap_frames)) : 0u;
-    float *out_g;
-    unsigned long long fifo_w = 0;
-    uint32_t fifo_mask = 0;
-    if (to_fifo) {
-        out_g = st.fifo + (size_t)slot * st.fifo_frames * st.max_channels;
-        fifo_w = st.fifo_w[slot];
-        fifo_mask = st.fifo_frames - 1u;
-    } else {
-        out_g = reinterpret_cast<float *>(arena + it.out_off);
-    }
-
-    const uint32_t prog = smem_u32(smem_raw), segs = prog + skc_seg_off(pd);
-    const uint32_t a_hist = smem_u32(buf), a_chunk = a_hist + 16u * C * 4u;
-    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
-    for (uint32_t b = warp; b * 32u < n_out; b += RSP_THREADS / 32) {
-        const uint32_t j = b * 32u + lane;
-        uint32_t ent;
-        asm volatile("ld.shared.u16 %0, [%1];" : "=r"(ent) : "r"(prog + b * 2u));
-        const uint32_t s_last = ent >> 8;
-        float o0 = 0.0f, o1 = 0.0f;
-#pragma unroll 1
-        for (uint32_t s = ent & 0xFFu; s <= s_last; ++s) {
-            const uint32_t sa = segs + s * 32u;
-            uint32_t jj, himask, aux, sh;
-            asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4+16];" : "=r"(jj), "=r"(himask), "=r"(aux), "=r"(sh) : "r"(sa));
-            const uint32_t j0 = jj & 0xFFFFu, lenm1 = (jj >> 16) - j0 - 1u;
-            const uint32_t rel_raw = j - j0;
-            const uint32_t rel = min(rel_raw, lenm1);   // lanes outside the segment compute a valid frame and drop it
-            uint32_t addr;
-            float frac;
-            if (himask == SKC_KIND_E) {
-                uint32_t aoff;
-                asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(aoff), "=f"(frac) : "r"(prog + aux + rel * 8u));
-                addr = a_hist + aoff;
-            } else {
-                double x0, dl;
-                asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(x0), "=d"(dl) : "r"(sa));
-                const double x = __fma_rn((double)rel, dl, x0);    // exact inside a run (phase_runs.h)
-                if (himask > SKC_KIND_SLOW) {
-                    const uint32_t flh = (uint32_t)__double2hiint(x) & himask;                          // floor(x) as a double = {flh, 0}
-                    frac = __double2float_rn(__dsub_rn(x, __hiloint2double((int)flh, 0)));              // T::coerce(idx - idx.floor())
-                    addr = (flh >> sh) + (a_chunk - aux);
-                } else {
-                    int32_t fl;
-                    skc_split(x, &fl, &frac);
-                    addr = a_chunk + (uint32_t)(fl * (int32_t)(C * 4));
-                }
-            }
-            float v0, v1 = 0.0f;
-            if (C == 2) {
-                float2 y0, y1;
-                asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(y0.x), "=f"(y0.y) : "r"(addr));
-                asm volatile("ld.shared.v2.f32 {%0, %1}, [%2+8];" : "=f"(y1.x), "=f"(y1.y) : "r"(addr));
-                v0 = interp_lin(frac, y0.x, y1.x);
-                v1 = interp_lin(frac, y0.y, y1.y);
-            } else {
-                float y0, y1;
-                asm volatile("ld.shared.f32 %0, [%1];" : "=f"(y0) : "r"(addr));
-                asm volatile("ld.shared.f32 %0, [%1+4];" : "=f"(y1) : "r"(addr));
-                v0 = interp_lin(frac, y0, y1);
-            }
-            if (rel_raw <= lenm1) { o0 = v0; o1 = v1; }   // every output frame belongs to exactly one segment
-        }
-        if (j < n_out) {
-            const uint32_t of = to_fifo ? (uint32_t)((fifo_w + j) & fifo_mask) : j;
-            if (C == 2) stg_stream_f2(reinterpret_cast<float2 *>(out_g) + of, make_float2(o0, o1));
-            else out_g[of] = o0;
-        }
-    }
-    // new history = buffer frames [N, N+16): the last 16 frames of (history ++ chunk)
-    float hv = 0.0f;
-    const bool hw = threadIdx.x < 16u * C;
-    if (hw) hv = buf[N * C + threadIdx.x];
-    __syncthreads();  // everyone is done with the staged buffer; the old history in HBM was only read by the bulk copy
-    if (hw) hist_g[threadIdx.x] = hv;
-    if (to_fifo && threadIdx.x == 0) st.fifo_w[slot] = fifo_w + n_total;
-}
-
 }  // namespace skgpu

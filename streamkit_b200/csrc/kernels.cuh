@@ -13,4 +13,5 @@
 #include "k_resample.cuh"
 #include "k_mix.cuh"
 #include "k_chain.cuh"
+#include "k_resample_prog.cuh"
 #include "k_sinc.cuh"

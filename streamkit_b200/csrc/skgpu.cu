@@ -74,6 +74,7 @@ struct skgpu_ctx {
     std::vector<double> h_t;
     std::vector<int32_t> h_end;
     std::vector<uint32_t> h_chunk, h_ch, h_flags;   // h_flags: SLOT_*
+    std::vector<uint32_t> h_pe;                     // sinc streams: outputs after which the sub-phase repeats (k_resample_sinc_tiled)
     std::vector<double> h_li0;                      // initial last_index of the slot's resampler
     // windowed-sinc mode
     uint32_t sinc_L = 0, sinc_O = 0;
@@ -110,7 +111,7 @@ static skgpu_rc ctx_flush(skgpu_ctx *c) {
             up[i].channels = c->h_ch[slot];
             up[i].end_idx = c->h_end[slot];
             up[i].flags = c->h_flags[slot];
-            up[i].pad = 0;
+            up[i].aux = c->h_pe[slot];
             up[i].last_index0 = c->h_li0[slot];
         }
         if (n > c->d_reset_cap) {
@@ -179,6 +180,7 @@ extern "C" skgpu_rc skgpu_ctx_create(int32_t device_ordinal, const skgpu_ctx_con
     c->h_ch.assign(S, 0);
     c->h_flags.assign(S, 0);
     c->h_li0.assign(S, -4.0);
+    c->h_pe.assign(S, 0u);
     c->used.assign(S, 0);
     *out = c;
     return SKGPU_OK;
@@ -343,7 +345,8 @@ static int sinc_table_for(skgpu_ctx *c, double fc) {
         if (c->sinc_fc[i] == fc) return (int)i;
     const uint32_t L = c->sinc_L, O = c->sinc_O;
     const double pi = 3.14159265358979323846264338327950288;
-    std::vector<float> tab((size_t)(O + 1u) * L);
+    const uint32_t LS = L + SINC_ROW_PAD;                       // padded row stride (k_sinc.cuh)
+    std::vector<float> tab((size_t)(O + 1u) * LS, 0.0f);
     std::vector<double> g(L);
     for (uint32_t p = 0; p <= O; ++p) {
         double sum = 0.0;
@@ -356,7 +359,7 @@ static int sinc_table_for(skgpu_ctx *c, double fc) {
             g[n] = fc * sc * w;
             sum += g[n];
         }
-        for (uint32_t n = 0; n < L; ++n) tab[(size_t)p * L + n] = (float)(g[n] / sum);
+        for (uint32_t n = 0; n < L; ++n) tab[(size_t)p * LS + n] = (float)(g[n] / sum);
     }
     float *d = nullptr;
     if (cudaMalloc((void **)&d, tab.size() * sizeof(float)) != cudaSuccess) return 0;
@@ -427,6 +430,14 @@ static void slot_configure(skgpu_ctx *c, uint32_t slot, const skgpu_stream_cfg *
         c->h_flags[slot] |= SLOT_SINC | ((uint32_t)tab << 8);
         c->h_end[slot] = (int32_t)s->chunk_frames - (int32_t)(c->sinc_L / 2u) - 1 - (int32_t)std::ceil(t);
         c->h_li0[slot] = -(double)(c->sinc_L / 2u);
+        // out_rate / gcd outputs later the sub-phase is the same again (up to the rounding of the f64 recurrence, which the
+        // kernel checks per output); a multiple >= 32 of it keeps a warp's lanes on consecutive outputs
+        uint32_t a = s->in_rate, b = s->out_rate;
+        while (b) { const uint32_t r = a % b; a = b; b = r; }
+        const uint32_t P = s->out_rate / a;
+        c->h_pe[slot] = P >= 32u ? P : P * ((32u + P - 1u) / P);
+    } else {
+        c->h_pe[slot] = 0u;
     }
     c->used[slot] = 1;
     c->reset_list.push_back(slot);
@@ -517,6 +528,9 @@ struct Op {
     uint32_t mix_tpc = 1;         // mix: tiles one CTA handles (whole group for small groups)
     bool rs_prog = false;         // resample: program-driven kernels (k_phase_prog + k_resample_prog)
     bool rs_sinc = false;         // resample: windowed-sinc streams (k_phase + k_resample_sinc)
+    bool rs_sinc_tiled = false;   // ... through the persistent tap-table-in-shared-memory kernel (one tap table, fits)
+    SincDims sinc_dm{};
+    const float *sinc_taps = nullptr;
     ChainProgDims rs_pd{};        // resample: frame-program capacities of the op
     uint64_t results_off = 0;
     bool has_fifo_inputs = false;
@@ -780,6 +794,36 @@ static skgpu_rc validate_rs(const skgpu_plan *p, const skgpu_rs_item *items, uin
     return SKGPU_OK;
 }
 
+// Geometry of the persistent sinc kernel for this op, or rs_sinc_tiled = false (the one-CTA-per-stream kernel then runs):
+// every stream must use the same tap table, and the table plus a 2-stage ring of at least one stream must fit.
+static void rs_sinc_dims(const skgpu_ctx *c, Op &op, const skgpu_rs_item *items, uint32_t n, int ch) {
+    op.rs_sinc_tiled = false;
+    if (!n) return;
+    const uint32_t tab = (c->h_flags[items[0].slot] >> 8) & 0xFFu;
+    uint32_t max_items = 1;
+    for (uint32_t i = 0; i < n; ++i) {
+        const uint32_t slot = items[i].slot;
+        if (((c->h_flags[slot] >> 8) & 0xFFu) != tab) return;
+        const uint32_t pe = std::max(c->h_pe[slot], 1u);
+        const uint32_t cap_out = (uint32_t)((double)c->h_chunk[slot] / c->h_t[slot] + 10.0) + 8u;   // skgpu_stream_max_out_frames
+        const uint32_t per_class = (cap_out + pe - 1u) / pe;
+        max_items = std::max(max_items, pe * ((per_class + SINC_RA - 1u) / SINC_RA));
+    }
+    SincDims d;
+    d.tab_bytes = (c->sinc_O + 1u) * (c->sinc_L + SINC_ROW_PAD) * 4u;
+    const uint32_t pt = ((uint32_t)sizeof(SkPhaseTable) + 15u) & ~15u;
+    d.stream_bytes = pt + c->st.sinc_H * (uint32_t)ch * 4u + (((op.max_unit * (uint32_t)ch * 4u) + 15u) & ~15u);
+    const uint32_t budget = 220u * 1024u;
+    if (d.tab_bytes >= (1u << 20) || d.tab_bytes + 2u * d.stream_bytes > budget) return;
+    uint32_t G = std::max(1u, (uint32_t)SINCT_THREADS / max_items);
+    G = std::min(G, (uint32_t)SINC_GMAX);
+    G = std::min(G, (budget - d.tab_bytes) / (2u * d.stream_bytes));
+    d.G = G;
+    op.sinc_dm = d;
+    op.sinc_taps = c->sinc_tab_dev[tab];
+    op.rs_sinc_tiled = true;
+}
+
 // Frame-program capacities of a resample op (k_resample_prog): the same generator + builder the phase kernel runs,
 // over the first chunks of every distinct stream configuration and a spread of steady-state phases. Returns false when
 // a program cannot be represented (the op then uses the table-driven kernels).
@@ -872,6 +916,7 @@ extern "C" skgpu_rc skgpu_plan_add_resample(skgpu_plan *p, const skgpu_rs_item *
         if (ch != 1 && ch != 2) return fail(SKGPU_ERR_INVALID, "sinc resample op: mono or stereo streams of one channel count");
         op.smem_bytes = (uint32_t)((((uint64_t)(op.max_unit + p->ctx->st.sinc_H) * (uint32_t)ch * 4u) + 15u) & ~15ull);
         if (op.smem_bytes > 200u * 1024u) return fail(SKGPU_ERR_INVALID, "sinc resample op: chunk too large for shared-memory staging");
+        rs_sinc_dims(p->ctx, op, items, n, ch);
     } else {
         op.rs_prog = n > 0 && rs_prog_dims(p->ctx, items, n, &op.rs_pd);
         rs_size_smem(p->ctx, op);
@@ -893,6 +938,12 @@ extern "C" skgpu_rc skgpu_plan_update_resample(skgpu_plan *p, uint32_t opi, cons
     if (n && ch != op.rs_channels && op.rs_channels != 0) return fail(SKGPU_ERR_INVALID, "update changes the op's channel specialisation (%d -> %d)", op.rs_channels, ch);
     if (n && op.rs_sinc != ((p->ctx->h_flags[items[0].slot] & SLOT_SINC) != 0)) return fail(SKGPU_ERR_INVALID, "update changes the op's interpolation mode");
     if (op.rs_sinc && mx > op.max_unit) return fail(SKGPU_ERR_INVALID, "update has a longer chunk (%u) than the op was sized for (%u)", mx, op.max_unit);
+    if (op.rs_sinc && op.rs_sinc_tiled && n) {
+        Op probe = op;
+        rs_sinc_dims(p->ctx, probe, items, n, op.rs_channels);
+        if (!probe.rs_sinc_tiled || probe.sinc_taps != op.sinc_taps) return fail(SKGPU_ERR_INVALID, "update changes the op's tap table (streams of one sinc op share one effective cutoff)");
+        if (probe.sinc_dm.G < op.sinc_dm.G) op.sinc_dm.G = probe.sinc_dm.G;   // more work items per stream: fewer streams per pass (same shared memory)
+    }
     if (op.smem_frames && mx + 16u > op.smem_frames) return fail(SKGPU_ERR_INVALID, "update has a longer chunk (%u) than the op was sized for (%u)", mx, op.smem_frames - 16u);
     if (op.rs_prog && n) {
         ChainProgDims d{};
@@ -1479,10 +1530,15 @@ static skgpu_rc launch_ops(skgpu_plan *p, bool time_ops) {
             else k_phase<<<(op.cap + PHASE_THREADS - 1) / PHASE_THREADS, PHASE_THREADS, 0, s>>>(op.d_hdr, items, c->st, p->arena, op.results_off);
             CU(cudaGetLastError());
             if (time_ops) { skgpu_rc rc = op_event(op, 0, true, s); if (rc) return rc; rc = op_event(op, 1, false, s); if (rc) return rc; }
-            if (op.rs_sinc && op.rs_channels == 2) k_resample_sinc<2><<<op.cap, SINC_THREADS, op.smem_bytes, s>>>(op.d_hdr, items, c->st, p->arena);
+            if (op.rs_sinc && op.rs_sinc_tiled) {
+                const uint32_t grid = std::min<uint32_t>((op.cap + op.sinc_dm.G - 1u) / op.sinc_dm.G, (uint32_t)c->sm_count);
+                const uint32_t sm = op.sinc_dm.tab_bytes + 2u * op.sinc_dm.G * op.sinc_dm.stream_bytes;
+                if (op.rs_channels == 2) k_resample_sinc_tiled<2><<<grid, SINCT_THREADS, sm, s>>>(op.d_hdr, items, c->st, p->arena, op.sinc_taps, op.sinc_dm);
+                else k_resample_sinc_tiled<1><<<grid, SINCT_THREADS, sm, s>>>(op.d_hdr, items, c->st, p->arena, op.sinc_taps, op.sinc_dm);
+            } else if (op.rs_sinc && op.rs_channels == 2) k_resample_sinc<2><<<op.cap, SINC_THREADS, op.smem_bytes, s>>>(op.d_hdr, items, c->st, p->arena);
             else if (op.rs_sinc) k_resample_sinc<1><<<op.cap, SINC_THREADS, op.smem_bytes, s>>>(op.d_hdr, items, c->st, p->arena);
-            else if (op.rs_prog && op.rs_channels == 2) k_resample_prog<2><<<op.cap, RSP_THREADS, op.smem_bytes, s>>>(op.d_hdr, items, c->st, p->arena, op.smem_frames, op.rs_pd);
-            else if (op.rs_prog) k_resample_prog<1><<<op.cap, RSP_THREADS, op.smem_bytes, s>>>(op.d_hdr, items, c->st, p->arena, op.smem_frames, op.rs_pd);
+            else if (op.rs_prog && op.rs_channels == 2) k_resample_prog<2><<<op.cap, RSP_THREADS, op.smem_bytes, s>>>(op.d_hdr, items, c->st, p->arena, op.smem_frames, op.rs_pd, 1.0f);
+            else if (op.rs_prog) k_resample_prog<1><<<op.cap, RSP_THREADS, op.smem_bytes, s>>>(op.d_hdr, items, c->st, p->arena, op.smem_frames, op.rs_pd, 1.0f);
             else if (op.rs_channels == 2) k_resample<2><<<op.cap, RS_THREADS, op.smem_bytes, s>>>(op.d_hdr, items, c->st, p->arena, op.smem_frames);
             else if (op.rs_channels == 1) k_resample<1><<<op.cap, RS_THREADS, op.smem_bytes, s>>>(op.d_hdr, items, c->st, p->arena, op.smem_frames);
             else k_resample<0><<<op.cap, RS_THREADS, op.smem_bytes, s>>>(op.d_hdr, items, c->st, p->arena, op.smem_frames);
@@ -1529,6 +1585,11 @@ extern "C" skgpu_rc skgpu_plan_finalize(skgpu_plan *p) {
         if (rc) return rc;
     }
     for (auto &op : p->ops) {
+        if (op.kind == OP_RESAMPLE && op.rs_sinc && op.rs_sinc_tiled) {
+            const int sm_fit = 220 * 1024;   // a cap, not a reservation (per function, shared by every plan of the process)
+            CU(cudaFuncSetAttribute(k_resample_sinc_tiled<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm_fit));
+            CU(cudaFuncSetAttribute(k_resample_sinc_tiled<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm_fit));
+        }
         if (op.kind == OP_RESAMPLE && op.smem_bytes > 48u * 1024u) {
             if (op.rs_sinc && op.rs_channels == 2) CU(cudaFuncSetAttribute(k_resample_sinc<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)op.smem_bytes));
             else if (op.rs_sinc) CU(cudaFuncSetAttribute(k_resample_sinc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)op.smem_bytes));

@@ -127,12 +127,17 @@ class Resample(Workload):
     unit = "streams"
     kernel = "k_resample_prog<2>"
 
-    def __init__(self, in_rate=44100, out_rate=48000, streams=16384, device=0):
+    def __init__(self, in_rate=44100, out_rate=48000, streams=16384, device=0, sinc=None):
+        """sinc: None = rubato Linear (the reference's mode); (sinc_len, oversampling, f_cutoff) = the windowed-sinc polyphase mode"""
         self.own_ctx = True
         self.in_rate, self.out_rate, self.S, self.C = in_rate, out_rate, streams, 2
         self.chunk = in_rate // 50
+        self.sinc = sinc
         self.ctx = L.Context(device=device, max_streams=streams, max_channels=2, fifo_frames=0)
-        slots = self.ctx.stream_open_many(in_rate, out_rate, self.chunk, self.C, streams)
+        if sinc:
+            self.ctx.set_sinc(*sinc)
+            self.kernel = "k_resample_sinc<2>"
+        slots = self.ctx.stream_open_many(in_rate, out_rate, self.chunk, self.C, streams, L.STREAM_SINC if sinc else 0)
         self.cap = L.Context.max_out_frames(in_rate, out_rate, self.chunk, self.C)
         self.in_stride, self.out_stride = al(self.chunk * self.C * 4, 16), al(self.cap * self.C * 4, 16)
         self.in_bytes = al(streams * self.in_stride)
@@ -154,7 +159,12 @@ class Resample(Workload):
         self.algorithmic_bytes = streams * (self.chunk * self.C * 4 + self.n_out * self.C * 4 + 2 * (8 + 16 * self.C * 4))
         self.name = "BASELINE configs[3]: batched resampling %d->%d Hz over %d stereo streams, 20 ms chunks (in+out %.0f MB > L2)" % (
             in_rate, out_rate, streams, streams * (self.chunk + self.n_out) * self.C * 4 / 1e6)
-        self.ops = [(self.op, 1, self.kernel), (self.op, 0, "k_phase_prog")]
+        self.ops = [(self.op, 1, self.kernel), (self.op, 0, "k_phase" if sinc else "k_phase_prog")]
+        if sinc:
+            hist = (sinc[0] + 8) * self.C * 4
+            self.algorithmic_bytes = streams * (self.chunk * self.C * 4 + self.n_out * self.C * 4 + 2 * (8 + hist))
+            self.fma_per_launch = streams * self.n_out * self.C * 2 * sinc[0]       # two tap rows x L taps per channel and output frame
+            self.name += " -- windowed-sinc polyphase mode (sinc_len %d, oversampling %d, cutoff %.2f, BlackmanHarris2, linear phase interpolation)" % sinc
 
     def fill_host(self, host_in: np.ndarray, seed=9):
         D = 256

@@ -117,3 +117,92 @@ def test_sinc_and_linear_streams_do_not_share_an_op_and_chain_rejects_sinc():
         plan.destroy()
     finally:
         ctx.close()
+
+
+def _run_sinc_op(ctx, cfgs, ticks, params, update_at=None):
+    """cfgs: list of (in_rate, out_rate, chunk, channels); one resample op over all of them, `ticks` chunks each, checked
+    bit for bit against one C-oracle resampler per stream. Returns the number of compared frames."""
+    from tests.gpu_helpers import al, bits
+    n = len(cfgs)
+    slots = [ctx.stream_open(i, o, c, ch, L.STREAM_SINC) for (i, o, c, ch) in cfgs]
+    caps = [L.Context.max_out_frames(i, o, c, ch) for (i, o, c, ch) in cfgs]
+    in_off, out_off, pos = [], [], 0
+    for (i, o, c, ch) in cfgs:
+        in_off.append(pos)
+        pos += al(c * ch * 4, 16)
+    in_bytes = al(pos)
+    res_off = in_bytes
+    pos = al(res_off + 8 * n)
+    for (i, o, c, ch), cap in zip(cfgs, caps):
+        out_off.append(pos)
+        pos += al(cap * ch * 4, 16)
+    total = al(pos)
+    plan = L.Plan(ctx, total)
+    items = np.zeros(n, dtype=L.RS_ITEM_DT)
+    items["in_off"], items["out_off"], items["slot"], items["out_cap_frames"] = in_off, out_off, slots, caps
+    plan.add_resample(items, res_off)
+    plan.set_io(0, in_bytes, res_off, total - res_off)
+    plan.finalize()
+    host_in, host_out = np.zeros(in_bytes, np.uint8), np.zeros(total - res_off, np.uint8)
+    refs = [sko.SincFixedIn(i, o, c, ch, *params) for (i, o, c, ch) in cfgs]
+    frames = 0
+    for t in range(ticks):
+        xs = []
+        for s, (i, o, c, ch) in enumerate(cfgs):
+            x = synth.tone_streams(1000 + s, t, 1, c, ch, i)[0]
+            xs.append(x)
+            host_in[in_off[s]: in_off[s] + x.size * 4] = x.view(np.uint8)
+        plan.submit(host_in, host_out, L.SUBMIT_GRAPH if t % 2 else 0)
+        plan.wait()
+        res = host_out[: 8 * n].view(L.RS_RESULT_DT)
+        for s, (i, o, c, ch) in enumerate(cfgs):
+            want = refs[s].process(xs[s])
+            assert res[s]["status"] == 0 and int(res[s]["out_frames"]) * ch == want.size, (t, s)
+            got = host_out[out_off[s] - res_off: out_off[s] - res_off + want.size * 4].view(np.float32)
+            assert np.array_equal(bits(got), bits(want)), (t, s, cfgs[s])
+            frames += want.size // ch
+    plan.destroy()
+    for sl in slots:
+        ctx.stream_close(sl)
+    return frames
+
+
+@pytest.mark.gpu
+def test_sinc_persistent_kernel_many_streams_more_passes_than_ctas():
+    """700 stereo 44.1k->48k streams = more passes than SMs: every CTA of the persistent kernel refills both ring stages"""
+    params = (64, 256, 0.95)
+    ctx = L.Context(device=0, max_streams=1024, max_channels=2)
+    try:
+        ctx.set_sinc(*params)
+        assert _run_sinc_op(ctx, [(44100, 48000, 882, 2)] * 700, 3, params) > 700 * 2700
+    finally:
+        ctx.close()
+
+
+@pytest.mark.gpu
+def test_sinc_one_op_with_mixed_up_sampling_ratios_channels_stay_per_op():
+    """up-sampling streams share the tap table (cutoff 0.95): different periods, chunk sizes and item counts in one op"""
+    params = (64, 256, 0.95)
+    ctx = L.Context(device=0, max_streams=256, max_channels=2)
+    try:
+        ctx.set_sinc(*params)
+        cfgs = [(44100, 48000, 882, 2), (16000, 48000, 320, 2), (22050, 48000, 441, 2), (8000, 48000, 160, 2), (32000, 48000, 640, 2),
+                (11025, 48000, 441, 2), (44100, 48000, 441, 2), (24000, 48000, 480, 2)] * 9
+        _run_sinc_op(ctx, cfgs, 4, params)
+        # mono, with a chunk that is not a 16-byte multiple (441 x 4 B): the cooperative copy path
+        _run_sinc_op(ctx, [(44100, 48000, 441, 1), (44100, 48000, 882, 1), (22050, 48000, 441, 1)] * 5, 4, params)
+    finally:
+        ctx.close()
+
+
+@pytest.mark.gpu
+def test_sinc_one_op_with_several_tap_tables_takes_the_per_stream_kernel():
+    """down-sampling scales the cutoff with the ratio: streams with different tables in one op still resample exactly"""
+    params = (64, 256, 0.95)
+    ctx = L.Context(device=0, max_streams=64, max_channels=2)
+    try:
+        ctx.set_sinc(*params)
+        _run_sinc_op(ctx, [(44100, 48000, 882, 2), (48000, 16000, 960, 2), (48000, 44100, 960, 2), (48000, 8000, 960, 2)] * 3, 4, params)
+        _run_sinc_op(ctx, [(48000, 16000, 960, 2)] * 40, 3, params)      # one down-sampling table: persistent kernel, every output one sub-phase
+    finally:
+        ctx.close()
