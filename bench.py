@@ -863,7 +863,7 @@ def run_node(args, D: Dist) -> None:
     if rank == 0:
         peak, peak_src = hbm_peak()
         achieved = w.algorithmic_bytes / (main_ms * 1e-3) / 1e9
-        traffic, traffic_src = ncu_traffic({2: "k_convert<1", 3: "k_mix", 4: "k_resample_sinc<2" if args.sinc else "k_resample_prog<2"}[args.config]) if not args.rs_down else (None, "no capture of 48k->16k")
+        traffic, traffic_src = ncu_traffic({2: "k_convert<1", 3: "k_mix", 4: "k_resample_sinc_tiled<2" if args.sinc else "k_resample_prog<2"}[args.config]) if not args.rs_down else (None, "no capture of 48k->16k")
         cpu_node(args.config, cpu_units, 2, cores)
         cpu_iters = 20
         cpu_sec = cpu_node(args.config, cpu_units, cpu_iters, cores)

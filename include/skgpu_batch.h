@@ -111,7 +111,11 @@ typedef struct skgpu_stream_cfg {
  *   q = f32(frac O - p), window = L input frames from floor(idx) - L/2 + 1 (zeros before the stream starts), every dot product a
  *   sequential f32 fma chain in ascending tap order. State per stream in HBM: last_index (f64) + the last L + 8 input frames.
  * The oracle restates this independently (oracle/sk_sinc.c, oracle/np_oracle.py). Call before opening SKGPU_STREAM_SINC streams;
- * the parameters are fixed for the context's lifetime. */
+ * the parameters are fixed for the context's lifetime.
+ * Performance note: a resample op whose sinc streams share ONE tap table (all up-sampling streams do: fc = f_cutoff; down-sampling
+ * streams of one ratio do) runs the persistent kernel that keeps the table in shared memory (k_resample_sinc_tiled); an op that
+ * mixes tables, or whose table does not fit beside two staged chunks, runs one CTA per stream with the taps read through L1. Same
+ * results either way. */
 skgpu_rc skgpu_ctx_set_sinc(skgpu_ctx *ctx, uint32_t sinc_len, uint32_t oversampling_factor, double f_cutoff);
 
 skgpu_rc skgpu_stream_open(skgpu_ctx *ctx, const skgpu_stream_cfg *cfg, uint32_t *slot_out);

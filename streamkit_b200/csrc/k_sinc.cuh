@@ -122,6 +122,7 @@ __global__ void __launch_bounds__(SINC_THREADS) k_resample_sinc(const OpHeader *
 constexpr int SINCT_THREADS = 512;
 constexpr int SINC_RA = 6;
 constexpr int SINC_GMAX = 8;
+constexpr uint32_t SINC_SLOW_CAP = 1024;
 
 struct __align__(16) SincStream {   // one stream of a pass: written by its loading lane, read by everyone after the stage's barrier
     float *out_g;
@@ -164,27 +165,60 @@ __device__ __forceinline__ unsigned long long sinc_fma2(unsigned long long a, un
 }
 __device__ __forceinline__ float sinc_mix(float q, float y0, float y1) { return __fadd_rn(__fmul_rn(__fsub_rn(1.0f, q), y0), __fmul_rn(q, y1)); }
 
-// one output frame, its own tap rows (shared-memory addresses): the reference form of the arithmetic
+// one output frame on its own tap rows (shared-memory addresses)
 template <int C>
 __device__ __forceinline__ void sinc_one(uint32_t w, uint32_t row, uint32_t LS4, uint32_t L, float q, float *out) {
-    float y0[C], y1[C];
+    if (C == 2) {
+        unsigned long long y0 = 0ull, y1 = 0ull;
+#pragma unroll 2
+        for (uint32_t n4 = 0; n4 < L / 4u; ++n4) {
+            const float4 a = sinc_lds128(row + n4 * 16u), b = sinc_lds128(row + LS4 + n4 * 16u);
+            const unsigned long long A[4] = {pack2(a.x, a.x), pack2(a.y, a.y), pack2(a.z, a.z), pack2(a.w, a.w)};
+            const unsigned long long B[4] = {pack2(b.x, b.x), pack2(b.y, b.y), pack2(b.z, b.z), pack2(b.w, b.w)};
 #pragma unroll
-    for (int c = 0; c < C; ++c) y0[c] = y1[c] = 0.0f;
-    for (uint32_t n4 = 0; n4 < L / 4u; ++n4) {
-        const float4 a = sinc_lds128(row + n4 * 16u), b = sinc_lds128(row + LS4 + n4 * 16u);
-        const float ta[4] = {a.x, a.y, a.z, a.w}, tb[4] = {b.x, b.y, b.z, b.w};
-#pragma unroll
-        for (int m = 0; m < 4; ++m) {
-#pragma unroll
-            for (int c = 0; c < C; ++c) {
-                const float xin = lds_f32(w + ((n4 * 4u + (uint32_t)m) * C + (uint32_t)c) * 4u);
-                y0[c] = __fmaf_rn(xin, ta[m], y0[c]);
-                y1[c] = __fmaf_rn(xin, tb[m], y1[c]);
+            for (int m = 0; m < 4; ++m) {
+                const unsigned long long xf = sinc_lds64(w + (n4 * 4u + (uint32_t)m) * 8u);
+                y0 = sinc_fma2(xf, A[m], y0);
+                y1 = sinc_fma2(xf, B[m], y1);
             }
         }
-    }
+        float l0, r0, l1, r1;
+        unpack2(y0, l0, r0);
+        unpack2(y1, l1, r1);
+        out[0] = sinc_mix(q, l0, l1);
+        out[C - 1] = sinc_mix(q, r0, r1);
+    } else {
+        float y0 = 0.0f, y1 = 0.0f;
+#pragma unroll 2
+        for (uint32_t n4 = 0; n4 < L / 4u; ++n4) {
+            const float4 a = sinc_lds128(row + n4 * 16u), b = sinc_lds128(row + LS4 + n4 * 16u);
+            const float ta[4] = {a.x, a.y, a.z, a.w}, tb[4] = {b.x, b.y, b.z, b.w};
 #pragma unroll
-    for (int c = 0; c < C; ++c) out[c] = sinc_mix(q, y0[c], y1[c]);
+            for (int m = 0; m < 4; ++m) {
+                const float xin = lds_f32(w + (n4 * 4u + (uint32_t)m) * 4u);
+                y0 = __fmaf_rn(xin, ta[m], y0);
+                y1 = __fmaf_rn(xin, tb[m], y1);
+            }
+        }
+        out[0] = sinc_mix(q, y0, y1);
+    }
+}
+
+// output k of a staged stream, evaluated on its own (phase -> rows -> two dot products -> store)
+template <int C>
+__device__ __forceinline__ void sinc_single(const SincStream &m, const SkPhaseTable *T, uint32_t a_buf, uint32_t a_tab, uint32_t k, uint32_t L, uint32_t O,
+                                            uint32_t H, uint32_t LS4) {
+    if (k >= m.n_out) return;
+    const double x = sinc_phase_eval(T, m.t, k);
+    const int fl = __double2int_rd(x);
+    const double fo = __dmul_rn(__dsub_rn(x, (double)fl), (double)O);
+    int p = __double2int_rd(fo);
+    p = min(p, (int)O - 1);
+    const float q = __double2float_rn(__dsub_rn(fo, (double)p));
+    float o[C];
+    sinc_one<C>(a_buf + (uint32_t)(fl - (int)(L / 2u) + 1 + (int)H) * (C * 4u), a_tab + (uint32_t)p * LS4, LS4, L, q, o);
+    if (C == 2) stg_stream_f2(reinterpret_cast<float2 *>(m.out_g) + k, make_float2(o[0], o[C - 1]));
+    else m.out_g[k] = o[0];
 }
 
 template <int C>
@@ -193,6 +227,7 @@ __global__ void __launch_bounds__(SINCT_THREADS, 1) k_resample_sinc_tiled(const 
     extern __shared__ __align__(16) uint8_t smem_raw[];   // [tap table | stage 0: G streams | stage 1: G streams]
     __shared__ __align__(8) uint64_t bar_tab, bar_full[2];
     __shared__ SincStream meta[2][SINC_GMAX];
+    __shared__ uint32_t slow_n, slow_q[SINC_SLOW_CAP];   // work items whose outputs do not share their tap rows (see below)
 
     const uint32_t count = hdr->count, G = dm.G;
     const uint32_t n_pass = (count + G - 1u) / G;
@@ -254,7 +289,9 @@ __global__ void __launch_bounds__(SINCT_THREADS, 1) k_resample_sinc_tiled(const 
     for (uint32_t q = blockIdx.x; q < n_pass; q += gridDim.x, ++it_n) {
         const uint32_t s = it_n & 1u;
         if (tid < G && q + gridDim.x < n_pass) load_stream(q + gridDim.x, s ^ 1u, tid);   // stage s ^ 1 was released by the barrier that ended the previous pass
+        if (tid == 0) slow_n = 0u;       // ordered before its first use by the barrier below (and after its last use by the pass-ending one)
         mbar_wait(&bar_full[s], (it_n >> 1) & 1u);
+        __syncthreads();
 
         // chunks that could not be bulk-copied (unaligned / odd sizes)
         bool any_coop = false;
@@ -354,22 +391,27 @@ __global__ void __launch_bounds__(SINCT_THREADS, 1) k_resample_sinc_tiled(const 
                     }
                 }
             } else {
-                // rare: recompute each output's phase (no register arrays indexed at run time) and evaluate it on its own rows
+                // The outputs of this item sit within rounding distance of a tap-row boundary ((x - floor x) * O is an integer in
+                // exact arithmetic: 1 class in 5 at 160/147), so the f64 recurrence puts them on either side of it. A lane that
+                // evaluated them one by one here would stall its whole warp: queue the item, all threads share the queue below.
+                const uint32_t at = atomicAdd(&slow_n, 1u);
+                if (at < SINC_SLOW_CAP) {
+                    slow_q[at] = (g << 24) | local;
+                } else {
 #pragma unroll 1
-                for (uint32_t a = 0; a < (uint32_t)SINC_RA; ++a) {
-                    const uint32_t k = k0 + a * pe;
-                    if (k >= n_out) break;
-                    const double x = sinc_phase_eval(T, m.t, k);
-                    const int fl = __double2int_rd(x);
-                    const double fo = __dmul_rn(__dsub_rn(x, (double)fl), (double)O);
-                    int p = __double2int_rd(fo);
-                    p = min(p, (int)O - 1);
-                    const float q = __double2float_rn(__dsub_rn(fo, (double)p));
-                    float o[C];
-                    sinc_one<C>(a_buf + (uint32_t)(fl - (int)(L / 2u) + 1 + (int)H) * (C * 4u), a_tab + (uint32_t)p * LS4, LS4, L, q, o);
-#pragma unroll
-                    for (int c = 0; c < C; ++c) out_g[(size_t)k * C + c] = o[c];
+                    for (uint32_t a = 0; a < (uint32_t)SINC_RA; ++a) sinc_single<C>(m, T, a_buf, a_tab, k0 + a * pe, L, O, H, LS4);
                 }
+            }
+        }
+        __syncthreads();
+        {   // queued items, one OUTPUT per thread
+            const uint32_t ns = min(slow_n, SINC_SLOW_CAP);
+            for (uint32_t u = tid; u < ns * SINC_RA; u += SINCT_THREADS) {
+                const uint32_t e = slow_q[u % ns], a = u / ns, g = e >> 24, local = e & 0xFFFFFFu;
+                const SincStream &m = meta[s][g];
+                const uint32_t k = (local % m.pe) + m.pe * ((local / m.pe) * SINC_RA + a);
+                const SkPhaseTable *T = reinterpret_cast<const SkPhaseTable *>(stage_p + (size_t)(s * G + g) * dm.stream_bytes);
+                sinc_single<C>(m, T, a_stage + (s * G + g) * dm.stream_bytes + PT_BYTES, a_tab, k, L, O, H, LS4);
             }
         }
         // new history = the last H frames of [history | chunk]

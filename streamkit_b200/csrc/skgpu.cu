@@ -805,8 +805,9 @@ static void rs_sinc_dims(const skgpu_ctx *c, Op &op, const skgpu_rs_item *items,
         const uint32_t slot = items[i].slot;
         if (((c->h_flags[slot] >> 8) & 0xFFu) != tab) return;
         const uint32_t pe = std::max(c->h_pe[slot], 1u);
-        const uint32_t cap_out = (uint32_t)((double)c->h_chunk[slot] / c->h_t[slot] + 10.0) + 8u;   // skgpu_stream_max_out_frames
-        const uint32_t per_class = (cap_out + pe - 1u) / pe;
+        // the NOMINAL output count sizes the pass (a chunk that yields one frame more costs its stream a second round of items)
+        const uint32_t nominal = std::max(1u, (uint32_t)((double)c->h_chunk[slot] / c->h_t[slot] + 0.5));
+        const uint32_t per_class = (nominal + pe - 1u) / pe;
         max_items = std::max(max_items, pe * ((per_class + SINC_RA - 1u) / SINC_RA));
     }
     SincDims d;

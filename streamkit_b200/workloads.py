@@ -136,7 +136,7 @@ class Resample(Workload):
         self.ctx = L.Context(device=device, max_streams=streams, max_channels=2, fifo_frames=0)
         if sinc:
             self.ctx.set_sinc(*sinc)
-            self.kernel = "k_resample_sinc<2>"
+            self.kernel = "k_resample_sinc_tiled<2>"
         slots = self.ctx.stream_open_many(in_rate, out_rate, self.chunk, self.C, streams, L.STREAM_SINC if sinc else 0)
         self.cap = L.Context.max_out_frames(in_rate, out_rate, self.chunk, self.C)
         self.in_stride, self.out_stride = al(self.chunk * self.C * 4, 16), al(self.cap * self.C * 4, 16)

@@ -40,6 +40,10 @@ def run(w):
 
 
 def main():
+    if os.environ.get("SK_ONLY") == "sinc":      # profiling helper: the sinc workloads alone
+        run(W.Resample(44100, 48000, 16384, sinc=(64, 256, 0.95)))
+        run(W.Resample(48000, 16000, 16384, sinc=(64, 256, 0.95)))
+        return
     ctx = L.Context(device=0, max_streams=16, max_channels=2)
     name, sms, *_ = ctx.device_info()
     print(json.dumps({"device": name, "sms": sms, "peak_gbs": PEAK, "iters": ITERS, "warmup": WARM}), flush=True)
