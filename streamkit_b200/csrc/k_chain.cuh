@@ -748,19 +748,25 @@ __global__ void __launch_bounds__(CH_THREADS, 5) k_chain(const OpHeader *__restr
 #pragma unroll
                 for (int f = 0; f < CH_NB; ++f) acc[it][f] = init;
         }
-        for (uint32_t q = 0; q < nb; ++q) {
-            const ChainCons c = S->cons[q];
-            const uint32_t prog = sm + q * in_bytes, a_chunk = prog + prog_cap + SK_SIDE_HIST;   // program record; staged chunk pieces
-            if (c.sc & CK_S16) chain_expand_s16(a_chunk, c.n_prev, c.n_head, ct);
-            if (UNIFORM) {
-                if (c.sc & CK_BYPASS) chain_consume_pass<OC, OC, ITERS>(acc, a_chunk, F, cw, lane, c.gain, one2);
-                else chain_consume<OC, OC, ITERS>(acc, prog, a_chunk - 16u * OC * 4u, dm.prog, F, cw, lane, c.gain, one2);
-            } else if ((c.sc & 0xFFu) == 2u) {
-                if (c.sc & CK_BYPASS) chain_consume_pass<OC, 2, ITERS>(acc, a_chunk, F, cw, lane, c.gain, one2);
-                else chain_consume<OC, 2, ITERS>(acc, prog, a_chunk - 128u, dm.prog, F, cw, lane, c.gain, one2);
-            } else {
-                if (c.sc & CK_BYPASS) chain_consume_pass<OC, 1, ITERS>(acc, a_chunk, F, cw, lane, c.gain, one2);
-                else chain_consume<OC, 1, ITERS>(acc, prog, a_chunk - 64u, dm.prog, F, cw, lane, c.gain, one2);
+        if (UNIFORM) {
+            // every input of the op is a resampled f32 stream with the output's channel count (host: validate_chain): this
+            // instantiation carries no input-kind code at all -- the consumer loop is sensitive to its instruction footprint
+            for (uint32_t q = 0; q < nb; ++q) {
+                const uint32_t prog = sm + q * in_bytes;
+                chain_consume<OC, OC, ITERS>(acc, prog, prog + prog_cap + (OC == 2 ? 0u : SK_SIDE_HIST - 64u), dm.prog, F, cw, lane, S->cons[q].gain, one2);
+            }
+        } else {
+            for (uint32_t q = 0; q < nb; ++q) {
+                const ChainCons c = S->cons[q];
+                const uint32_t prog = sm + q * in_bytes, a_chunk = prog + prog_cap + SK_SIDE_HIST;   // program record; staged chunk pieces
+                if (c.sc & CK_S16) chain_expand_s16(a_chunk, c.n_prev, c.n_head, ct);
+                if ((c.sc & 0xFFu) == 2u) {
+                    if (c.sc & CK_BYPASS) chain_consume_pass<OC, 2, ITERS>(acc, a_chunk, F, cw, lane, c.gain, one2);
+                    else chain_consume<OC, 2, ITERS>(acc, prog, a_chunk - 128u, dm.prog, F, cw, lane, c.gain, one2);
+                } else {
+                    if (c.sc & CK_BYPASS) chain_consume_pass<OC, 1, ITERS>(acc, a_chunk, F, cw, lane, c.gain, one2);
+                    else chain_consume<OC, 1, ITERS>(acc, prog, a_chunk - 64u, dm.prog, F, cw, lane, c.gain, one2);
+                }
             }
         }
         if (hd.z != 0) {

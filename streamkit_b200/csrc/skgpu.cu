@@ -539,7 +539,7 @@ struct Op {
     uint32_t chain_buf_floats = 0;  // chain: floats per staging buffer
     int chain_oc = 2;             // chain: output channels specialisation
     int chain_iters = 1;          // chain: ceil(F / 1024)
-    bool chain_uniform = false;   // chain: every input has the output's channel count (single-variant kernel)
+    bool chain_uniform = false;   // chain: every input is a resampled f32 stream with the output's channel count (single-variant kernel)
     ChainDims chain_dm{};         // chain: staging-ring geometry passed to the kernel
     ChainRec *d_rec = nullptr;    // chain: per-input records written by k_phase_chain every tick
     uint32_t chain_grid = 0;      // chain: persistent grid size (CTAs per SM x SMs)
@@ -1204,7 +1204,8 @@ static skgpu_rc validate_chain(const skgpu_plan *p, const skgpu_chain_group *g, 
     *oc_out = oc < 0 ? 2 : oc;
     {
         bool uni = true;
-        for (uint32_t i = 0; i < ni; ++i) uni = uni && (int)c->h_ch[in[i].slot] == *oc_out;
+        for (uint32_t i = 0; i < ni; ++i)   // plain inputs only: resampled f32 streams with the output's channel count
+            uni = uni && (int)c->h_ch[in[i].slot] == *oc_out && !(c->h_flags[in[i].slot] & (SLOT_BYPASS | SLOT_S16));
         *uniform_out = uni;
     }
     // margin for phases the sampling did not hit; even counts keep every staged array a multiple of 16 bytes
@@ -1325,7 +1326,7 @@ extern "C" skgpu_rc skgpu_plan_update_chain(skgpu_plan *p, uint32_t opi, const s
     skgpu_rc rc = validate_chain(p, groups, ng, inputs, ni, op.chain_F, &mk, &mb, &oc, &cnp, &cnr, &uniform);
     if (rc) return rc;
     if (ng && oc != op.chain_oc) return fail(SKGPU_ERR_INVALID, "update changes the op's output channel count");
-    if (op.chain_uniform && !uniform) return fail(SKGPU_ERR_INVALID, "update adds an input whose channel count differs from the output's to an op created with uniform inputs (include such a stream in the initial tables)");
+    if (op.chain_uniform && !uniform) return fail(SKGPU_ERR_INVALID, "update adds an input of another kind (channel count differing from the output's, rate-equal bypass or s16) to an op created with plain inputs only (include such a stream in the initial tables)");
     if (mb > op.chain_buf_floats) return fail(SKGPU_ERR_INVALID, "update has a longer chunk than the op was sized for");
     if (mk > op.chain_dm.max_k) return fail(SKGPU_ERR_INVALID, "update has a session with more inputs (%u) than the op was sized for (%u)", mk, op.chain_dm.max_k);
     if (cnp > op.chain_dm.prog.cap_seg || cnr > op.chain_dm.prog.cap_exp) return fail(SKGPU_ERR_INVALID, "update adds a resampling ratio whose phase tables exceed the op's staging capacity");
