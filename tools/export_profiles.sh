@@ -14,9 +14,11 @@ w=csv.writer(sys.stdout)
 for r in rows:
     if len(r)==len(hdr): w.writerow([r[i][:60] for i in keep])
 ' > ${OUT}_launches.csv
-for c in config2 config3 config4 config4_sinc; do [ -f gpurun_out/bench_${c}_$TAG.json ] && cp gpurun_out/bench_${c}_$TAG.json ${OUT}_bench_${c}.json; done
+for c in config2 config3 config4 config4_sinc config4_down k1 s16 opus opus_s16; do [ -f gpurun_out/bench_${c}_$TAG.json ] && cp gpurun_out/bench_${c}_$TAG.json ${OUT}_bench_${c}.json; done
 python tools/ncu_summary.py gpurun_out/prof_full_$TAG.ncu-rep $(ls gpurun_out/prof_nodes_$TAG.ncu-rep 2>/dev/null) > ${OUT}_ncu_full_summary.csv
 python tools/ncu_lines.py gpurun_out/prof_full_$TAG.ncu-rep k_chain 65536 > ${OUT}_k_chain_hot_lines.txt 2>&1
 python tools/ncu_lines.py gpurun_out/prof_full_$TAG.ncu-rep k_phase_chain 4096 > ${OUT}_k_phase_chain_hot_lines.txt 2>&1
+[ -f gpurun_out/prof_nodes_$TAG.ncu-rep ] && python tools/ncu_lines.py gpurun_out/prof_nodes_$TAG.ncu-rep k_resample_sinc_tiled 16384 > ${OUT}_k_resample_sinc_hot_lines.txt 2>&1
+[ -f gpurun_out/prof_nodes_$TAG.ncu-rep ] && python tools/ncu_lines.py gpurun_out/prof_nodes_$TAG.ncu-rep k_resample_prog 16384 > ${OUT}_k_resample_prog_hot_lines.txt 2>&1
 cuobjdump -sass streamkit_b200/csrc/libskgpu.so | grep -oE "UBLKCP[.A-Z0-9]*|SYNCS[.A-Z0-9]*|FFMA2|FMUL2|FADD2|LDGSTS[.A-Z0-9]*" | sort | uniq -c > ${OUT}_sass_mnemonics.txt
 ls -la profiles

@@ -32,9 +32,9 @@ def main():
         for r in rows[2:]:
             d = dict(zip(hdr, r))
             uu = dict(zip(hdr, u))
-            for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"):      # one unit per column across reports
-                if k in d and uu.get(k) != units.get(k):
-                    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+            scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "ns": 1e-9, "us": 1e-6, "usecond": 1e-6, "ms": 1e-3, "msecond": 1e-3, "s": 1.0, "second": 1.0, "nsecond": 1e-9}
+            for k in ("dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__time_duration.sum"):      # one unit per column across reports
+                if k in d and uu.get(k) != units.get(k) and uu.get(k) in scale and units.get(k) in scale:
                     d[k] = "%g" % (float(d[k].replace(",", "")) * scale[uu[k]] / scale[units[k]])
             d["Kernel Name"] = d.get("Kernel Name", "")[:90]
             out.append(d)

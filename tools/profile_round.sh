@@ -15,4 +15,11 @@ python tools/bench_kernels.py > gpurun_out/kernels_$TAG.jsonl 2> gpurun_out/kern
 SK_PROFILE=1 ncu --set full --clock-control none --import-source on -k regex:"k_convert|k_mix|k_resample_prog|k_resample_sinc" -o gpurun_out/prof_nodes_$TAG -f python tools/bench_kernels.py > gpurun_out/ncu_nodes_$TAG.log 2>&1
 for c in 2 3 4; do python bench.py --config $c --steps 30 --warmup 5 > gpurun_out/bench_config${c}_$TAG.json 2>> gpurun_out/bench_$TAG.err; done
 python bench.py --config 4 --sinc --steps 30 --warmup 5 > gpurun_out/bench_config4_sinc_$TAG.json 2>> gpurun_out/bench_$TAG.err
+python bench.py --config 4 --rs-down --steps 30 --warmup 5 > gpurun_out/bench_config4_down_$TAG.json 2>> gpurun_out/bench_$TAG.err
+# workload variants of the chain: one input per session, s16 ingest, Opus-decoder shaped (48 kHz mono inputs, bypass)
+V="--steps 30 --warmup 5 --no-hub --no-router --no-s16-extra --no-capacity-check"
+python bench.py $V --k 1 > gpurun_out/bench_k1_$TAG.json 2>> gpurun_out/bench_$TAG.err
+python bench.py $V --s16-in > gpurun_out/bench_s16_$TAG.json 2>> gpurun_out/bench_$TAG.err
+python bench.py $V --in-rate 48000 --channels 1 --k 3 > gpurun_out/bench_opus_$TAG.json 2>> gpurun_out/bench_$TAG.err
+python bench.py $V --in-rate 48000 --channels 1 --k 3 --s16-in > gpurun_out/bench_opus_s16_$TAG.json 2>> gpurun_out/bench_$TAG.err
 tail -c 600 gpurun_out/bench_$TAG.json
