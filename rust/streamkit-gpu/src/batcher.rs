@@ -57,6 +57,15 @@ fn rt_err(what: &str) -> StreamKitError {
 }
 
 impl GpuBatcher {
+    /// the rate every session is mixed at (the hubs' `out_rate`)
+    pub fn mixer_rate(&self) -> u32 {
+        self.out_rate
+    }
+    /// frames per packet and tick (the hubs' `out_frames`)
+    pub fn packet_frames(&self) -> u32 {
+        self.out_frames
+    }
+
     /// `devices`: CUDA ordinals of the box; capacities are per GPU. Fails (Configuration) when there is no GPU: there is no CPU
     /// fallback -- a deployment without GPUs keeps the built-in `audio::*` nodes.
     pub fn new(devices: &[i32], max_sessions_per_gpu: u32, max_inputs_per_session: u32, in_rates: &[u32]) -> Result<Arc<Self>, StreamKitError> {
