@@ -738,6 +738,9 @@ def run_chain(args, D: Dist) -> None:
                                 "fits the 2 ms device budget; capacity_check runs that many for real. Real-time capacity at 20 ms per tick is 10x that.",
             "path": "fused k_phase_chain + k_chain" if fused else "unfused k_resample_prog + k_mix",
             "device_realtime_sessions_20ms": total_sessions * TICK_MS / ms_per_step,
+            "samples_per_s": {"device": total_sessions * 960 * CHANNELS / (ms_per_step * 1e-3),
+                              "e2e": (e2e_line or {}).get("value", 0.0) * 960 * CHANNELS / (TICK_MS * 1e-3),
+                              "what": "output samples (48 kHz frames x channels) per second: device-resident kernels / end to end in real time"},
             "capacity_check": cap,
             "e2e": e2e_line,
             "e2e_s16_ingest": e2e_s16,
