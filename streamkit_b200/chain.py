@@ -146,9 +146,9 @@ class ChainTick:
 
 
 def run_chain_gpu(n_sessions: int, k_inputs: int, ticks: int, seed: int, in_rate: int = 44100, channels: int = 2,
-                  graph: bool = False, fused: bool = True, chunk_frames: int | None = None, out_frames: int = OUT_FRAMES):
+                  graph: bool = False, fused: bool = True, chunk_frames: int | None = None, out_frames: int = OUT_FRAMES, out_rate: int = OUT_RATE):
     ct = ChainTick(n_sessions, k_inputs, in_rate=in_rate, channels=channels, seed=seed, fused=fused, chunk_frames=chunk_frames,
-                   out_frames=out_frames)
+                   out_frames=out_frames, out_rate=out_rate)
     try:
         outs = []
         for t in range(ticks):

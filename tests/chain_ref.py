@@ -14,13 +14,17 @@ OUT_FRAMES = 960
 
 
 def run_chain_oracle(n_sessions: int, k_inputs: int, ticks: int, seed: int, in_rate: int = 44100, channels: int = 2,
-                     inputs_fn=None, chunk_frames: int | None = None, out_frames: int = OUT_FRAMES):
+                     inputs_fn=None, chunk_frames: int | None = None, out_frames: int = OUT_FRAMES, out_rate: int = OUT_RATE,
+                     node_chunk_frames: int | None = None):
+    """node_chunk_frames: the resampler nodes' own chunk_frames when it differs from the frames delivered per tick (a tick
+    that carries several node chunks, e.g. 60 ms ticks over 20 ms chunks)"""
     chunk = chunk_frames if chunk_frames is not None else in_rate // 50
     OUT_FRAMES = out_frames
+    OUT_RATE = out_rate
     n_streams = n_sessions * k_inputs
     in_gains = synth.gains(seed, n_streams, 0.25, 1.5)
     master = synth.gains(seed + 1, n_sessions, 0.5, 2.0)
-    nodes = [sko.ResamplerNode(OUT_RATE, chunk_frames=chunk, output_frame_size=OUT_FRAMES) for _ in range(n_streams)]
+    nodes = [sko.ResamplerNode(OUT_RATE, chunk_frames=node_chunk_frames or chunk, output_frame_size=OUT_FRAMES) for _ in range(n_streams)]
     queues = [collections.deque() for _ in range(n_streams)]
     outs = []
     for t in range(ticks):

@@ -495,6 +495,21 @@ def test_fused_chain_other_packet_sizes_and_ratios(in_rate, chunk, out_frames, c
     assert any(np.any(g != 0) for g in got)
 
 
+@pytest.mark.parametrize("channels,k_inputs", [(1, 1), (2, 1), (2, 2)])
+def test_fused_chain_config0_48k_to_16k_with_960_frame_packets(channels, k_inputs):
+    """BASELINE configs[0] / samples/pipelines/oneshot/speech_to_text.yml:14-18: audio::resampler 48k -> 16k, chunk_frames 960,
+    output_frame_size 960 (one packet per THREE chunks). Fused, this runs at the packet cadence: one 60 ms tick carries the
+    stream's three 20 ms chunks as one 2,880-frame chunk. t = 3.0 is exact, so every position of the f64 recurrence is an
+    integer whichever way the input is cut: the s16 bytes equal the reference-shaped nodes that process 960-frame chunks."""
+    S, T = 4, 8
+    got = chain.run_chain_gpu(S, k_inputs, T, seed=41, in_rate=48000, channels=channels, chunk_frames=2880, out_frames=960, out_rate=16000)
+    want = chain_ref.run_chain_oracle(S, k_inputs, T, seed=41, in_rate=48000, channels=channels, chunk_frames=2880, out_frames=960, out_rate=16000,
+                                      node_chunk_frames=960)
+    for t in range(T):
+        assert np.array_equal(got[t], want[t]), f"tick {t}: {(got[t] != want[t]).sum()} s16 samples differ"
+    assert any(np.any(g != 0) for g in got[1:])
+
+
 def test_fused_chain_long_run_stays_bit_exact():
     """400 ticks (8 s of audio): the f64 phase state, the carry bookkeeping and the alternating side records of the
     fused path must track the oracle tick for tick (a drifting phase would flip a packet boundary sooner or later)."""
