@@ -81,7 +81,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", os.environ.get("SK_BENCH_CLOCK_LMS", "100")], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
             self.proc = None
@@ -503,19 +503,27 @@ def e2e_sliced(ct, args, D, latency_ticks=None):
     e2e_ms = D.max(e2e_ms)
     worst, kern, updone = [], [], []
 
+    dbg = []
+
     def collect(tm):
+        if os.environ.get("SK_BENCH_LAT_DEBUG"):
+            i = max(range(len(tm)), key=lambda j: tm[j][2])
+            dbg.append((tm[i][2], len(dbg), i, tm[i][0], tm[i][1]))
         worst.append(max(t[2] for t in tm))
         kern.append(max(t[1] for t in tm))
         updone.append(tm[-1][0])
 
     if lt > 0:
         pipelined(lt, collect)
+    if dbg:
+        print("[lat debug] worst slices (latency ms, tick, slice, upload_done ms, kernels ms):", sorted(dbg, reverse=True)[:12], file=sys.stderr)
     last_out = outs[(lt - 1) & 1] if lt > 0 else outs[(args.steps - 1) & 1]
     e2e_ms_per_step = e2e_ms / args.steps
     e2e = {"ms_per_step": e2e_ms_per_step, "slices": n_sl, "ticks_in_flight": 2,
            "h2d_gbs_per_gpu": ct.in_bytes / (e2e_ms_per_step * 1e-3) / 1e9, "d2h_gbs_per_gpu": ct.out_bytes / (e2e_ms_per_step * 1e-3) / 1e9,
            "latency": {"ticks": len(worst), "p50_ms": pct(worst, 0.5), "p99_ms": pct(worst, 0.99), "max_ms": max(worst),
                        "kernels_p99_ms": pct(kern, 0.99), "upload_of_whole_tick_ms_p50": pct(updone, 0.5),
+                       "ticks_over_1ms": int(sum(1 for w in worst if w > 1.0)), "p90_ms": pct(worst, 0.9),
                        "budget_ms": BUDGET_MS, "within_budget": pct(worst, 0.99) <= BUDGET_MS,
                        "what": "per slice: its upload done -> its results in host memory (kernels + read-back, SURVEY 8d added device "
                                "latency); worst slice of each tick; CUDA events"} if worst else None,
