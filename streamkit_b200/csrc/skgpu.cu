@@ -1236,6 +1236,12 @@ static void chain_size_smem(Op &op, uint32_t max_k, uint32_t chunk_cap, uint32_t
     const uint64_t in_bytes = chain_in_bytes(dm);
     uint32_t kb = std::max(1u, std::min<uint32_t>(max_k, CH_MAX_KB));
     while (kb > 1 && 2ull * kb * in_bytes > 100u * 1024u) --kb;
+#ifdef SKGPU_TUNING_KNOBS
+    if (const char *e = std::getenv("SKGPU_CHAIN_KB")) {
+        const int v = std::atoi(e);
+        if (v >= 1 && v <= CH_MAX_KB) kb = (uint32_t)v;
+    }
+#endif
     const uint64_t stage = (uint64_t)kb * in_bytes;
     const uint64_t scratch = (uint64_t)dm.max_k * sizeof(ChainRec);
     const uint64_t static_smem = sizeof(ChainStage) * CH_MAX_STAGES + 5u * 1024u, sm_smem = 227u * 1024u, cta_overhead = 1024u;   // stage headers + prefetch slots
