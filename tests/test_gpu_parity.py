@@ -609,6 +609,38 @@ def test_chain_rejects_ineligible_streams(ctx):
         ctx.stream_close(slot)
 
 
+def test_chain_op_of_plain_inputs_rejects_another_input_kind_on_update(ctx):
+    """an op created from resampled f32 inputs of the output's channel count runs the instantiation without input-kind code;
+    a later table update must not smuggle a bypass / s16 / other-channel stream into it"""
+    a = ctx.stream_open(44100, 48000, 882, 2)
+    a2 = ctx.stream_open(44100, 48000, 882, 2)
+    b = ctx.stream_open(48000, 48000, 960, 2)          # rate-equal: bypass
+    c = ctx.stream_open(44100, 48000, 882, 2, L.STREAM_S16)
+    plan = L.Plan(ctx, 1 << 20)
+    try:
+        plan.set_io(0, 32768, 200000, 8192)
+        plan.set_banks(65536)
+        cin = np.zeros(2, dtype=L.CHAIN_INPUT_DT)
+        cin["slot"] = [a, a2]
+        cin["in_off"] = [0, 8192]
+        cin["gain_idx"] = L.SKGPU_NO_GAIN
+        cg = np.zeros(1, dtype=L.CHAIN_GROUP_DT)
+        cg["out_off"], cg["n_inputs"], cg["gain_idx"], cg["out_channels"] = 200000, 2, L.SKGPU_NO_GAIN, 2
+        op = plan.add_chain(cg, cin, 960, 150000)
+        plan.finalize()
+        for other in (b, c):
+            cin["slot"] = [a, other]
+            with pytest.raises(L.SkgpuError) as e:
+                plan.update_chain(op, cg, cin)
+            assert "another kind" in e.value.msg, e.value.msg
+        cin["slot"] = [a2, a]                              # the same kind in another order is fine
+        plan.update_chain(op, cg, cin)
+    finally:
+        plan.destroy()
+        for s_ in (a, a2, b, c):
+            ctx.stream_close(s_)
+
+
 def test_smoke_entry():
     import __graft_entry__ as g
 
