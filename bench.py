@@ -467,14 +467,25 @@ def capacity_check(S2: int, k: int, device: int, kslices: int, ticks: int = 60) 
         ct.close()
 
 
-def e2e_sliced(ct, args, D, latency_ticks=None):
+def auto_slices(ct, args, d2h_gbs) -> int:
+    """slices per end-to-end tick: --slices N, or (default) as many as keep ONE slice's read-back near 0.5 ms at the device->host
+    rate this box sustains with every rank copying (a slice's results cannot reach the host faster than that), at least 16"""
+    if args.slices > 0:
+        return max(1, min(args.slices, ct.S))
+    n = 16
+    if d2h_gbs and d2h_gbs > 0:
+        n = int(np.ceil(ct.out_bytes / (d2h_gbs * 1e9 * 0.5e-3)))
+    return max(16, min(n, 128, ct.S))
+
+
+def e2e_sliced(ct, args, D, latency_ticks=None, d2h_gbs=None):
     """end-to-end through the C ABI with host buffers: SLICED ticks, two in flight; every step uploads its inputs from pinned host
     memory and reads every s16 result back. Returns (dict, host buffer holding the last tick's outputs)."""
     from streamkit_b200 import lib as L
 
     plan, ctx, S = ct.plan, ct.ctx, ct.S
     lt = args.latency_ticks if latency_ticks is None else latency_ticks
-    n_sl = max(1, min(args.slices, S))
+    n_sl = auto_slices(ct, args, d2h_gbs)
     plan.auto_slices(ct.op_chain, n_sl)
     ins = [ct.host_in, ctx.pinned(ct.in_bytes, np.float32)]
     outs = [ct.host_out, ctx.pinned(ct.out_bytes, np.int16)]
@@ -616,8 +627,13 @@ def run_chain(args, D: Dist) -> None:
     # ---- end-to-end region: SLICED ticks, two in flight; every step uploads its inputs from pinned host memory and reads
     # every s16 result back
     e2e = {}
+    ceiling = None
     if ct.fused:
-        e2e, last_out = e2e_sliced(ct, args, D)
+        try:   # what the box allows (plain copies on every rank at once): also sizes the slices
+            ceiling = D.pcie_ceiling()
+        except Exception as e:
+            ceiling = {"error": str(e)[:200]}
+        e2e, last_out = e2e_sliced(ct, args, D, d2h_gbs=ceiling.get("d2h_gbs_this_gpu"))
     else:
         for _ in range(3):
             plan.submit(ct.host_in, ct.host_out, 0)
@@ -672,7 +688,7 @@ def run_chain(args, D: Dist) -> None:
             ct2.ctx.bind_thread()
             blk = np.rint(synth.noise_streams(2000 + rank, 0, 8192, ct2.chunk, CHANNELS) * 32767.0).astype(np.int16)
             ct2.fill_rows(ct2.host_in, np.tile(blk, ((ct2.n_streams + 8191) // 8192, 1))[: ct2.n_streams])
-            d, _ = e2e_sliced(ct2, args, D, latency_ticks=min(args.latency_ticks, 100))
+            d, _ = e2e_sliced(ct2, args, D, latency_ticks=min(args.latency_ticks, 100), d2h_gbs=(ceiling or {}).get("d2h_gbs_this_gpu"))
             d["value"] = total_sessions * TICK_MS / d["ms_per_step"]
             d["unit"] = UNIT
             d["h2d_bytes_per_step"], d["d2h_bytes_per_step"] = ct2.in_bytes * world, ct2.out_bytes * world
@@ -700,14 +716,10 @@ def run_chain(args, D: Dist) -> None:
             hub_e2e = {"error": str(e)[:200]}
 
     e2e_value = total_sessions * TICK_MS / e2e["ms_per_step"]
-    ceiling = None
-    try:
-        ceiling = D.pcie_ceiling()
+    if ceiling is not None and "error" not in ceiling:
         per_session = in_bytes / S
         ceiling["sessions_per_gpu_at_that_upload_rate"] = ceiling["h2d_gbs_per_gpu_min"] * 1e9 / (per_session * (1e3 / TICK_MS))
         ceiling["e2e_fraction_of_ceiling"] = (e2e_value / world) / ceiling["sessions_per_gpu_at_that_upload_rate"]
-    except Exception as e:
-        ceiling = {"error": str(e)[:200]}
     router_e2e = None
     if args.router and fused:
         # every rank is done with its own GPU: rank 0 alone now drives ALL the GPUs of the box from one process
@@ -927,7 +939,7 @@ def main() -> None:
     ap.add_argument("--in-rate", type=int, default=44100, help="input sample rate; 48000 = bypass inputs (Opus-decoder shaped, SURVEY 8f #3)")
     ap.add_argument("--channels", type=int, default=2, choices=[1, 2])
     ap.add_argument("--s16-in", action="store_true", help="inputs arrive as s16 on PCIe (x = s / 32768), half the upload")
-    ap.add_argument("--slices", type=int, default=16, help="slices per end-to-end tick")
+    ap.add_argument("--slices", type=int, default=0, help="slices per end-to-end tick; 0 = automatic (>= 16, more when the box's device->host rate is low)")
     ap.add_argument("--kslices", type=int, default=8, help="slices of the device-resident tick (phase / chain kernel overlap); 1 = whole-tick launches")
     ap.add_argument("--unfused", action="store_true", help="use the general unfused ops (k_resample_prog -> ring -> k_mix)")
     ap.add_argument("--rs-down", action="store_true", help="--config 4: 48k->16k instead of 44.1k->48k")
