@@ -219,7 +219,7 @@ def run_reference(args) -> None:
     line = {
         "impl": "reference", "metric": metric, "value": value, "unit": unit, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic", "config": cfg,
+        "dtype": "f32", "data": "synthetic", "config": dict(cfg, timed_sample=sample),   # the workload is the GPU arm's; the CPU times a bounded sample of it
         "cpu_baseline": {"value": value, "unit": unit, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
