@@ -1018,7 +1018,12 @@ extern "C" skgpu_rc skgpu_plan_add_mix(skgpu_plan *p, const skgpu_mix_group *gro
     {   // groups with few inputs: one CTA per group (the prologue costs more than the tile's loads); fixed at add time
         uint32_t max_k = 0;
         for (uint32_t i = 0; i < ng; ++i) max_k = std::max(max_k, groups[i].n_inputs);
-        op.mix_tpc = (ng >= 4096u && max_k <= 8u) ? std::min(op.tiles, 8u) : 1u;
+        // ... and with several groups per SM a CTA takes a whole group whatever its size: the prologue (descriptor loads, summation
+        // order) is paid once per group instead of once per tile (config #3, 1,024 groups x 64 inputs: 94.9 -> 89.0 us)
+        op.mix_tpc = (ng >= 4096u && max_k <= 8u) ? std::min(op.tiles, 8u) : (ng >= 4u * (uint32_t)p->ctx->sm_count ? std::min(op.tiles, 8u) : 1u);
+#ifdef SKGPU_TUNING_KNOBS
+        if (const char *e = std::getenv("SKGPU_MIX_TPC")) op.mix_tpc = (uint32_t)std::max(1, std::atoi(e));
+#endif
     }
     op.has_fifo_inputs = fifo;
     {   // presence table: every input present until skgpu_plan_set_present says otherwise

@@ -10,6 +10,8 @@ import json
 import os
 import sys
 
+import numpy as np
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from streamkit_b200 import lib as L, workloads as W  # noqa: E402
@@ -23,7 +25,11 @@ ITERS, WARM = (1, 1) if os.environ.get("SK_PROFILE") else (20, 3)      # SK_PROF
 
 def run(w):
     flags = L.SUBMIT_NO_H2D | L.SUBMIT_NO_D2H | L.SUBMIT_TIME_OPS
-    w.plan.fill(0, 0, w.in_bytes)
+    # real signal in the arena (seeded noise / tones, uploaded once): all-zero inputs time a few percent faster on this part
+    host_in = w.ctx.pinned(w.in_bytes, np.uint8)
+    w.fill_host(host_in)
+    w.plan.submit(host_in, None, L.SUBMIT_NO_D2H)
+    w.plan.wait()
     for _ in range(WARM):
         w.plan.submit(None, None, flags)
     w.plan.wait()
@@ -45,6 +51,10 @@ def main():
         run(W.Resample(48000, 16000, 16384, sinc=(64, 256, 0.95)))
         return
     ctx = L.Context(device=0, max_streams=16, max_channels=2)
+    if os.environ.get("SK_ONLY") == "mix":
+        run(W.Mix64(ctx, s16=True))
+        ctx.close()
+        return
     name, sms, *_ = ctx.device_info()
     print(json.dumps({"device": name, "sms": sms, "peak_gbs": PEAK, "iters": ITERS, "warmup": WARM}), flush=True)
     for mode in (L.CVT_F32_TO_F32, L.CVT_F32_TO_S16, L.CVT_S16_TO_F32):
