@@ -399,6 +399,47 @@ def test_hub_moq_mixing_shape_bypass_inputs(channels, in_s16):
         hub.close()
 
 
+@pytest.mark.gpu
+def test_hub_16k_mixer_with_960_frame_packets_ticks_at_the_packet_cadence():
+    """BASELINE configs[0] shape on the batch path (speech_to_text.yml:14-18: 48k -> 16k, output_frame_size 960): a 16 kHz /
+    960-frame hub ticks every 60 ms and asks each 48 kHz input for 2,880 frames per tick; the reference-shaped nodes consume the
+    same audio in 960-frame chunks (chunk_frames 960). Integer ratio: identical bytes. A 16 kHz participant bypasses."""
+    from oracle import sko
+    hub = H.Hub(max_sessions=4, max_streams=8, in_rates=[48000, 16000], max_inputs_per_session=2, out_rate=16000, out_frames=960, channels=1)
+    try:
+        shapes = [[48000], [48000, 48000], [48000, 16000]]
+        sids = [hub.session_open(r) for r in shapes]
+        assert hub.chunk_frames(sids[0], 0) == 2880 and hub.chunk_frames(sids[2], 1) == 960
+        nodes = [[sko.ResamplerNode(16000, chunk_frames=960, output_frame_size=960) for _ in r] for r in shapes]
+        queues = [[collections.deque() for _ in r] for r in shapes]
+        for t in range(7):
+            want = []
+            for a, r in enumerate(shapes):
+                frames = []
+                for i, rate in enumerate(r):
+                    n_in = rate * 960 // 16000
+                    x = _chunk(900 + a * 4 + i, t, rate, n_in, 1)
+                    hub.push(sids[a], i, x)
+                    nd = nodes[a][i]
+                    for c0 in range(0, n_in, 960):                 # the node sees 20 ms packets
+                        nd.out.clear()
+                        nd.push(rate, 1, x[c0:c0 + 960])
+                        for pkt in nd.out:
+                            queues[a][i].append(pkt["samples"])
+                    if queues[a][i]:
+                        frames.append((queues[a][i].popleft(), 1, True))
+                want.append((sko.gain_f32_to_s16(sko.mix_clocked(frames, 1, 960), 1.0), len(frames)))
+            hub.tick()
+            hub.wait()
+            for sid, (w, n) in zip(sids, want):
+                got, n_mixed, status = hub.output(sid)
+                assert status == 0 and n_mixed == n, (t, sid, n_mixed, n)
+                assert np.array_equal(got, w), f"tick {t} session {sid}: {(got != w).sum()} samples differ"
+        assert any(n for _w, n in want)
+    finally:
+        hub.close()
+
+
 # ------------------------------------------------------------------------------------------------ sync mode
 
 class _SyncMixerModel:
