@@ -150,10 +150,15 @@ extern "C" skgpu_rc skgpu_ctx_create(int32_t device_ordinal, const skgpu_ctx_con
     cudaDeviceProp prop;
     CU(cudaGetDeviceProperties(&prop, device_ordinal));
     c->sm_count = prop.multiProcessorCount;
-    CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
-    CU(cudaStreamCreateWithFlags(&c->stream_d2h, cudaStreamNonBlocking));
-    CU(cudaStreamCreateWithFlags(&c->stream_k, cudaStreamNonBlocking));
-    CU(cudaStreamCreateWithFlags(&c->stream_p, cudaStreamNonBlocking));
+    {   // sliced ticks: a slice's kernels and read-back are on the latency path, the bulk upload of the NEXT slices is not --
+        // give the device's scheduler that order of preference
+        int lo = 0, hi = 0;   // numerically lower = higher priority
+        CU(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        CU(cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, lo));
+        CU(cudaStreamCreateWithPriority(&c->stream_d2h, cudaStreamNonBlocking, hi));
+        CU(cudaStreamCreateWithPriority(&c->stream_k, cudaStreamNonBlocking, hi));
+        CU(cudaStreamCreateWithPriority(&c->stream_p, cudaStreamNonBlocking, hi));
+    }
     detect_numa(c);
     CU(cudaEventCreate(&c->tm0));
     CU(cudaEventCreate(&c->tm1));
