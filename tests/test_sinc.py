@@ -206,3 +206,31 @@ def test_sinc_one_op_with_several_tap_tables_takes_the_per_stream_kernel():
         _run_sinc_op(ctx, [(48000, 16000, 960, 2)] * 40, 3, params)      # one down-sampling table: persistent kernel, every output one sub-phase
     finally:
         ctx.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_sinc_random_rate_pairs_and_filter_shapes(seed):
+    """random common-rate pairs (up- and down-sampling mixed tables -> per-stream kernel; same-table groups -> persistent kernel),
+    random filter shapes: every output frame equals the C oracle's bit for bit"""
+    rng = np.random.default_rng(seed)
+    rates = [8000, 11025, 12000, 16000, 22050, 24000, 32000, 44100, 48000, 88200, 96000]
+    params = (int(rng.choice([16, 32, 64, 128])), int(rng.choice([32, 128, 256, 512])), float(rng.choice([0.8, 0.9, 0.95, 1.0])))
+    ch = int(rng.choice([1, 2]))
+    ctx = L.Context(device=0, max_streams=64, max_channels=2)
+    try:
+        ctx.set_sinc(*params)
+        def chunk_of(r):
+            c = max(r // 50, params[0] + 8)
+            return c + (c * ch) % 2                      # keep stereo / mono chunks a whole number of 8-byte units
+        ups, mixed = [], []
+        for _ in range(6):
+            i, o = (int(v) for v in rng.choice(rates, 2, replace=False))
+            (ups if o > i else mixed).append((i, o, chunk_of(i), ch))
+        mixed = mixed + ups[:2]
+        if ups:
+            _run_sinc_op(ctx, ups * 3, 3, params)        # one tap table (cutoff unscaled): the persistent kernel
+        if mixed:
+            _run_sinc_op(ctx, mixed, 3, params)          # several tables: one CTA per stream
+    finally:
+        ctx.close()
