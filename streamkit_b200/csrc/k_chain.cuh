@@ -514,9 +514,14 @@ __global__ void __launch_bounds__(PHASE_CHAIN_THREADS, 14) k_phase_chain(const O
                  "r"((uint32_t)(a_hist >> 32)), "r"(cb), "r"(hb), "r"(flags), "r"((N - 16u) * ch) : "memory");
 }
 
-// OC output channels (1 | 2); ITERS = ceil(F / 1024); UNIFORM: every input of the op has OC channels (the common case gets a
-// kernel with ONE copy of the consumer code: the instruction footprint matters), else inputs may be mono or stereo
-template <int OC, int ITERS, bool UNIFORM>
+// OC output channels (1 | 2); ITERS = ceil(F / 1024); KIND: what the op's inputs are (host: validate_chain) --
+//   CHAIN_PLAIN   every input is a resampled f32 stream with OC channels: ONE copy of the consumer code, no input-kind code
+//                 (the instruction footprint matters);
+//   CHAIN_BYPASS  every input is a rate-equal f32 stream with OC channels (Opus decoders into a 48 kHz mix,
+//                 samples/pipelines/dynamic/moq_mixing.yml): no frame programs at all, the staged chunk is the packet;
+//   CHAIN_ANY     anything the chain admits (mono and stereo, bypass, s16 ingest), in any mixture
+constexpr int CHAIN_ANY = 0, CHAIN_PLAIN = 1, CHAIN_BYPASS = 2;
+template <int OC, int ITERS, int KIND>
 __global__ void __launch_bounds__(CH_THREADS, 5) k_chain(const OpHeader *__restrict__ hdr, const skgpu_chain_group *__restrict__ groups,
                                                          const ChainRec *__restrict__ recs, const float *__restrict__ gains, SlotTables st,
                                                          uint8_t *__restrict__ arena, uint32_t F, ChainDims dm, uint32_t *tick_advance) {
@@ -575,8 +580,11 @@ __global__ void __launch_bounds__(CH_THREADS, 5) k_chain(const OpHeader *__restr
             uint8_t *slot_sm = sm + (size_t)q * in_bytes;
             uint8_t *chunk_sm = slot_sm + prog_cap + SK_SIDE_HIST;
             const uint32_t cb = r.chunk_bytes, hb = r.head_bytes;
-            uint32_t bytes = prog_cap + SK_SIDE_HIST;
-            tma_bulk_g2s(slot_sm, r.prog_src, prog_cap + SK_SIDE_HIST, bar);   // frame program + the 16 frames before the previous chunk
+            uint32_t bytes = 0;
+            if (KIND != CHAIN_BYPASS) {   // a bypass input has neither a program nor a history
+                bytes = prog_cap + SK_SIDE_HIST;
+                tma_bulk_g2s(slot_sm, r.prog_src, prog_cap + SK_SIDE_HIST, bar);   // frame program + the 16 frames before the previous chunk
+            }
             if (!(r.flags & CR_UNALIGNED)) {
                 tma_bulk_g2s(chunk_sm, r.prev_g, cb, bar);
                 if (hb) tma_bulk_g2s(chunk_sm + cb, r.cur_g, hb, bar);
@@ -651,10 +659,13 @@ __global__ void __launch_bounds__(CH_THREADS, 5) k_chain(const OpHeader *__restr
                     for (uint32_t q = 0; q < m; ++q, dst += in_bytes) {
                         const ChainRec *rr = &pf_rec[n & 1u][s_order[q]];
                         const uint32_t cb = rr->chunk_bytes, hb = rr->head_bytes;
-                        tma_bulk_g2s(dst, rr->prog_src, prog_cap + SK_SIDE_HIST, &bar_full[stage]);
+                        if (KIND != CHAIN_BYPASS) {   // a bypass input has neither a program nor a history
+                            tma_bulk_g2s(dst, rr->prog_src, prog_cap + SK_SIDE_HIST, &bar_full[stage]);
+                            bytes += prog_cap + SK_SIDE_HIST;
+                        }
                         tma_bulk_g2s(dst + prog_cap + SK_SIDE_HIST, rr->prev_g, cb, &bar_full[stage]);
                         if (hb) tma_bulk_g2s(dst + prog_cap + SK_SIDE_HIST + cb, rr->cur_g, hb, &bar_full[stage]);
-                        bytes += prog_cap + SK_SIDE_HIST + cb + hb;
+                        bytes += cb + hb;
                     }
                     mbar_expect_tx(&bar_full[stage], bytes);   // arrive: the smem writes above are ordered before it
                 }
@@ -748,7 +759,10 @@ __global__ void __launch_bounds__(CH_THREADS, 5) k_chain(const OpHeader *__restr
 #pragma unroll
                 for (int f = 0; f < CH_NB; ++f) acc[it][f] = init;
         }
-        if (UNIFORM) {
+        if (KIND == CHAIN_BYPASS) {
+            for (uint32_t q = 0; q < nb; ++q)
+                chain_consume_pass<OC, OC, ITERS>(acc, sm + q * in_bytes + prog_cap + SK_SIDE_HIST, F, cw, lane, S->cons[q].gain, one2);
+        } else if (KIND == CHAIN_PLAIN) {
             // every input of the op is a resampled f32 stream with the output's channel count (host: validate_chain): this
             // instantiation carries no input-kind code at all -- the consumer loop is sensitive to its instruction footprint
             for (uint32_t q = 0; q < nb; ++q) {

@@ -544,7 +544,7 @@ struct Op {
     uint32_t chain_buf_floats = 0;  // chain: floats per staging buffer
     int chain_oc = 2;             // chain: output channels specialisation
     int chain_iters = 1;          // chain: ceil(F / 1024)
-    bool chain_uniform = false;   // chain: every input is a resampled f32 stream with the output's channel count (single-variant kernel)
+    int chain_kind = CHAIN_ANY;   // chain: CHAIN_PLAIN / CHAIN_BYPASS when every input is of that one kind (specialised kernels), else CHAIN_ANY
     ChainDims chain_dm{};         // chain: staging-ring geometry passed to the kernel
     ChainRec *d_rec = nullptr;    // chain: per-input records written by k_phase_chain every tick
     uint32_t chain_grid = 0;      // chain: persistent grid size (CTAs per SM x SMs)
@@ -1157,7 +1157,7 @@ static bool prog_bounds(double t, int32_t end_idx, uint32_t N, uint32_t F, uint3
 }
 
 static skgpu_rc validate_chain(const skgpu_plan *p, const skgpu_chain_group *g, uint32_t ng, const skgpu_chain_input *in, uint32_t ni,
-                               uint32_t F, uint32_t *max_k, uint32_t *max_buf_floats, int *oc_out, uint32_t *cap_seg, uint32_t *cap_exp, bool *uniform_out) {
+                               uint32_t F, uint32_t *max_k, uint32_t *max_buf_floats, int *oc_out, uint32_t *cap_seg, uint32_t *cap_exp, int *kind_out) {
     uint32_t need_seg = 0, need_exp = 0;
     double last_t = -1.0;
     int32_t last_end = 0;
@@ -1213,10 +1213,13 @@ static skgpu_rc validate_chain(const skgpu_plan *p, const skgpu_chain_group *g, 
     *max_buf_floats = (mb + 15u) & ~15u;
     *oc_out = oc < 0 ? 2 : oc;
     {
-        bool uni = true;
-        for (uint32_t i = 0; i < ni; ++i)   // plain inputs only: resampled f32 streams with the output's channel count
-            uni = uni && (int)c->h_ch[in[i].slot] == *oc_out && !(c->h_flags[in[i].slot] & (SLOT_BYPASS | SLOT_S16));
-        *uniform_out = uni;
+        bool plain = ni > 0, bypass = ni > 0;   // one kind only: f32 streams with the output's channel count, all resampled or all rate-equal
+        for (uint32_t i = 0; i < ni; ++i) {
+            const bool shape = (int)c->h_ch[in[i].slot] == *oc_out && !(c->h_flags[in[i].slot] & SLOT_S16);
+            plain = plain && shape && !(c->h_flags[in[i].slot] & SLOT_BYPASS);
+            bypass = bypass && shape && (c->h_flags[in[i].slot] & SLOT_BYPASS);
+        }
+        *kind_out = plain ? CHAIN_PLAIN : bypass ? CHAIN_BYPASS : CHAIN_ANY;
     }
     // margin for phases the sampling did not hit; even counts keep every staged array a multiple of 16 bytes
     *cap_seg = (need_seg + 5u) & ~1u;
@@ -1296,8 +1299,8 @@ extern "C" skgpu_rc skgpu_plan_add_chain_cap(skgpu_plan *p, const skgpu_chain_gr
     CU(cudaSetDevice(p->ctx->device));
     uint32_t mk = 0, mb = 0, cnp = 0, cnr = 0;
     int oc = 2;
-    bool uniform = true;
-    skgpu_rc rc = validate_chain(p, groups, ng, inputs, ni, output_frame_size, &mk, &mb, &oc, &cnp, &cnr, &uniform);
+    int kind = CHAIN_ANY;
+    skgpu_rc rc = validate_chain(p, groups, ng, inputs, ni, output_frame_size, &mk, &mb, &oc, &cnp, &cnr, &kind);
     if (rc) return rc;
     mk = std::max(mk, max_inputs_per_group);
     rc = check_range(p, results_off, (uint64_t)std::max(cap_inputs, 1u) * sizeof(skgpu_chain_result), "chain results");
@@ -1313,7 +1316,7 @@ extern "C" skgpu_rc skgpu_plan_add_chain_cap(skgpu_plan *p, const skgpu_chain_gr
     op.n2 = ni;
     op.chain_F = output_frame_size;
     op.chain_oc = oc;
-    op.chain_uniform = uniform && ni > 0;
+    op.chain_kind = kind;
     op.chain_iters = (int)((output_frame_size + 1023u) / 1024u);
     op.results_off = results_off;
     chain_size_smem(op, mk, std::max(mb, 64u), cnp, cnr);
@@ -1338,11 +1341,11 @@ extern "C" skgpu_rc skgpu_plan_update_chain(skgpu_plan *p, uint32_t opi, const s
     if (ng > op.cap || ni > op.cap2) return fail(SKGPU_ERR_INVALID, "update exceeds capacity");
     uint32_t mk = 0, mb = 0, cnp = 0, cnr = 0;
     int oc = 2;
-    bool uniform = true;
-    skgpu_rc rc = validate_chain(p, groups, ng, inputs, ni, op.chain_F, &mk, &mb, &oc, &cnp, &cnr, &uniform);
+    int kind = CHAIN_ANY;
+    skgpu_rc rc = validate_chain(p, groups, ng, inputs, ni, op.chain_F, &mk, &mb, &oc, &cnp, &cnr, &kind);
     if (rc) return rc;
     if (ng && oc != op.chain_oc) return fail(SKGPU_ERR_INVALID, "update changes the op's output channel count");
-    if (op.chain_uniform && !uniform) return fail(SKGPU_ERR_INVALID, "update adds an input of another kind (channel count differing from the output's, rate-equal bypass or s16) to an op created with plain inputs only (include such a stream in the initial tables)");
+    if (op.chain_kind != CHAIN_ANY && ni && kind != op.chain_kind) return fail(SKGPU_ERR_INVALID, "update adds an input of another kind (channel count differing from the output's, resampled vs rate-equal bypass, s16) to an op created from inputs of one kind only (include such a stream in the initial tables)");
     if (mb > op.chain_buf_floats) return fail(SKGPU_ERR_INVALID, "update has a longer chunk than the op was sized for");
     if (mk > op.chain_dm.max_k) return fail(SKGPU_ERR_INVALID, "update has a session with more inputs (%u) than the op was sized for (%u)", mk, op.chain_dm.max_k);
     if (cnp > op.chain_dm.prog.cap_seg || cnr > op.chain_dm.prog.cap_exp) return fail(SKGPU_ERR_INVALID, "update adds a resampling ratio whose phase tables exceed the op's staging capacity");
@@ -1496,13 +1499,14 @@ static skgpu_rc op_event(Op &op, int sub, bool second, cudaStream_t s) {
 }
 
 typedef void (*chain_kernel_t)(const OpHeader *, const skgpu_chain_group *, const ChainRec *, const float *, SlotTables, uint8_t *, uint32_t, ChainDims, uint32_t *);
-static chain_kernel_t chain_kernel(int oc, int iters, bool uniform) {
-    if (uniform) {
-        if (oc == 2) return iters == 1 ? k_chain<2, 1, true> : iters == 2 ? k_chain<2, 2, true> : k_chain<2, 3, true>;
-        return iters == 1 ? k_chain<1, 1, true> : iters == 2 ? k_chain<1, 2, true> : k_chain<1, 3, true>;
-    }
-    if (oc == 2) return iters == 1 ? k_chain<2, 1, false> : iters == 2 ? k_chain<2, 2, false> : k_chain<2, 3, false>;
-    return iters == 1 ? k_chain<1, 1, false> : iters == 2 ? k_chain<1, 2, false> : k_chain<1, 3, false>;
+static chain_kernel_t chain_kernel(int oc, int iters, int kind) {
+#define SK_CHAIN_PICK(K)                                                                                                  \
+    if (oc == 2) return iters == 1 ? k_chain<2, 1, K> : iters == 2 ? k_chain<2, 2, K> : k_chain<2, 3, K>;                \
+    return iters == 1 ? k_chain<1, 1, K> : iters == 2 ? k_chain<1, 2, K> : k_chain<1, 3, K>;
+    if (kind == CHAIN_PLAIN) { SK_CHAIN_PICK(CHAIN_PLAIN) }
+    if (kind == CHAIN_BYPASS) { SK_CHAIN_PICK(CHAIN_BYPASS) }
+    SK_CHAIN_PICK(CHAIN_ANY)
+#undef SK_CHAIN_PICK
 }
 
 // the two kernels of the chain op over the table range a launch header describes (the whole tables, or one slice)
@@ -1517,7 +1521,7 @@ static skgpu_rc launch_chain(skgpu_plan *p, Op &op, const OpHeader *d_hdr, uint3
     CU(cudaGetLastError());
     if (time_ops) { skgpu_rc rc = op_event(op, 0, true, s); if (rc) return rc; rc = op_event(op, 1, false, s); if (rc) return rc; }
     const uint32_t grid = std::max(1u, std::min<uint32_t>(n_groups, op.chain_grid));
-    auto kfn = chain_kernel(op.chain_oc, op.chain_iters, op.chain_uniform);
+    auto kfn = chain_kernel(op.chain_oc, op.chain_iters, op.chain_kind);
     kfn<<<grid, CH_THREADS, op.smem_bytes, s>>>(d_hdr, (const skgpu_chain_group *)op.d_tab, op.d_rec, gains, c->st, p->arena, op.chain_F, op.chain_dm,
                                                  p->ops.size() == 1 ? p->d_tick : nullptr);   // a chain-only plan: the kernel advances the bank parity itself
     CU(cudaGetLastError());
@@ -1620,7 +1624,7 @@ extern "C" skgpu_rc skgpu_plan_finalize(skgpu_plan *p) {
     }
     for (auto &op : p->ops) {
         if (op.kind == OP_CHAIN) {
-            auto kfn = chain_kernel(op.chain_oc, op.chain_iters, op.chain_uniform);
+            auto kfn = chain_kernel(op.chain_oc, op.chain_iters, op.chain_kind);
             CU(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)op.smem_bytes));
             int per_sm = 0;
             CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kfn, CH_THREADS, op.smem_bytes));
@@ -1657,7 +1661,7 @@ static skgpu_rc launch_chain_phase(skgpu_plan *p, Op &op, const OpHeader *d_hdr,
 static skgpu_rc launch_chain_main(skgpu_plan *p, Op &op, const OpHeader *d_hdr, uint32_t n_groups, cudaStream_t s, bool advance) {
     skgpu_ctx *c = p->ctx;
     const uint32_t grid = std::max(1u, std::min<uint32_t>(n_groups, op.chain_grid));
-    auto kfn = chain_kernel(op.chain_oc, op.chain_iters, op.chain_uniform);
+    auto kfn = chain_kernel(op.chain_oc, op.chain_iters, op.chain_kind);
     kfn<<<grid, CH_THREADS, op.smem_bytes, s>>>(d_hdr, (const skgpu_chain_group *)op.d_tab, op.d_rec, (const float *)p->gains.dev, c->st, p->arena,
                                                  op.chain_F, op.chain_dm, advance ? p->d_tick : nullptr);
     CU(cudaGetLastError());
