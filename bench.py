@@ -734,7 +734,7 @@ def run_chain(args, D: Dist) -> None:
         if fused:
             # dominant kernel = k_chain: the fully fused algorithmic bytes of SURVEY 8(d) / BASELINE.md:
             # per session-tick K x (7056 in + 272 state r/w) + 3840 s16 out = 18,496 B (K = 2)
-            dom_name, dom_bytes = "k_chain<%d,1,%s>" % (CHANNELS, "any" if S16_IN else ("bypass" if IN_RATE == OUT_RATE else "plain")), chain_bytes
+            dom_name, dom_bytes = "k_chain<%d,1,%s>" % (CHANNELS, ("bypass" if IN_RATE == OUT_RATE else "plain") + ("_s16" if S16_IN else "")), chain_bytes
             std = S == 65536 and K == 2 and IN_RATE == 44100 and CHANNELS == 2 and not S16_IN
             traffic, traffic_src = ncu_traffic("k_chain<") if std else (None, "the committed capture is of 65,536 sessions x 2 stereo f32 44.1 kHz inputs")
         else:

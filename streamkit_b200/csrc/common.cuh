@@ -117,7 +117,12 @@ __device__ __forceinline__ uint32_t f32_to_s16_bits(float x) {
     return (uint32_t)r & 0xFFFFu;
 }
 __device__ __forceinline__ uint32_t pack_s16x2(float a, float b) { return f32_to_s16_bits(a) | (f32_to_s16_bits(b) << 16); }
-__device__ __forceinline__ float s16_to_f32(int s) { return __fmul_rn((float)s, 1.0f / 32768.0f); }
+// s / 32768 without an int->float conversion (I2F runs on the quarter-rate XU pipe): 0x4B400000 is 1.5 * 2^23, where one ulp is
+// 1.0, so adding s to the bit pattern yields exactly 12582912 + s; the subtraction and the power-of-two scaling are exact too --
+// bit-identical to (float)s * (1.0f / 32768.0f) for every 16-bit s (test_s16_to_f32_all_values_and_roundtrip)
+__device__ __forceinline__ float s16_to_f32(int s) {
+    return __fmul_rn(__fsub_rn(__int_as_float(0x4B400000 + s), 12582912.0f), 1.0f / 32768.0f);
+}
 
 // ---- mbarrier + TMA bulk copy (cp.async.bulk, SASS UBLKCP): one instruction moves a whole chunk into smem
 __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {

@@ -520,7 +520,8 @@ __global__ void __launch_bounds__(PHASE_CHAIN_THREADS, 14) k_phase_chain(const O
 //   CHAIN_BYPASS  every input is a rate-equal f32 stream with OC channels (Opus decoders into a 48 kHz mix,
 //                 samples/pipelines/dynamic/moq_mixing.yml): no frame programs at all, the staged chunk is the packet;
 //   CHAIN_ANY     anything the chain admits (mono and stereo, bypass, s16 ingest), in any mixture
-constexpr int CHAIN_ANY = 0, CHAIN_PLAIN = 1, CHAIN_BYPASS = 2;
+//   CHAIN_PLAIN_S16 / CHAIN_BYPASS_S16   the same two with every input arriving as s16 (expanded in shared memory first)
+constexpr int CHAIN_ANY = 0, CHAIN_PLAIN = 1, CHAIN_BYPASS = 2, CHAIN_PLAIN_S16 = 3, CHAIN_BYPASS_S16 = 4;
 template <int OC, int ITERS, int KIND>
 __global__ void __launch_bounds__(CH_THREADS, 5) k_chain(const OpHeader *__restrict__ hdr, const skgpu_chain_group *__restrict__ groups,
                                                          const ChainRec *__restrict__ recs, const float *__restrict__ gains, SlotTables st,
@@ -581,7 +582,7 @@ __global__ void __launch_bounds__(CH_THREADS, 5) k_chain(const OpHeader *__restr
             uint8_t *chunk_sm = slot_sm + prog_cap + SK_SIDE_HIST;
             const uint32_t cb = r.chunk_bytes, hb = r.head_bytes;
             uint32_t bytes = 0;
-            if (KIND != CHAIN_BYPASS) {   // a bypass input has neither a program nor a history
+            if (KIND != CHAIN_BYPASS && KIND != CHAIN_BYPASS_S16) {   // a bypass input has neither a program nor a history
                 bytes = prog_cap + SK_SIDE_HIST;
                 tma_bulk_g2s(slot_sm, r.prog_src, prog_cap + SK_SIDE_HIST, bar);   // frame program + the 16 frames before the previous chunk
             }
@@ -659,7 +660,7 @@ __global__ void __launch_bounds__(CH_THREADS, 5) k_chain(const OpHeader *__restr
                     for (uint32_t q = 0; q < m; ++q, dst += in_bytes) {
                         const ChainRec *rr = &pf_rec[n & 1u][s_order[q]];
                         const uint32_t cb = rr->chunk_bytes, hb = rr->head_bytes;
-                        if (KIND != CHAIN_BYPASS) {   // a bypass input has neither a program nor a history
+                        if (KIND != CHAIN_BYPASS && KIND != CHAIN_BYPASS_S16) {   // a bypass input has neither a program nor a history
                             tma_bulk_g2s(dst, rr->prog_src, prog_cap + SK_SIDE_HIST, &bar_full[stage]);
                             bytes += prog_cap + SK_SIDE_HIST;
                         }
@@ -759,9 +760,19 @@ __global__ void __launch_bounds__(CH_THREADS, 5) k_chain(const OpHeader *__restr
 #pragma unroll
                 for (int f = 0; f < CH_NB; ++f) acc[it][f] = init;
         }
-        if (KIND == CHAIN_BYPASS) {
-            for (uint32_t q = 0; q < nb; ++q)
-                chain_consume_pass<OC, OC, ITERS>(acc, sm + q * in_bytes + prog_cap + SK_SIDE_HIST, F, cw, lane, S->cons[q].gain, one2);
+        if (KIND == CHAIN_BYPASS || KIND == CHAIN_BYPASS_S16) {
+            for (uint32_t q = 0; q < nb; ++q) {
+                const uint32_t a_chunk = sm + q * in_bytes + prog_cap + SK_SIDE_HIST;
+                // (expanding two inputs behind one pair of barriers was measured slower: the per-input barriers let the warps drift)
+                if (KIND == CHAIN_BYPASS_S16) chain_expand_s16(a_chunk, S->cons[q].n_prev, S->cons[q].n_head, ct);
+                chain_consume_pass<OC, OC, ITERS>(acc, a_chunk, F, cw, lane, S->cons[q].gain, one2);
+            }
+        } else if (KIND == CHAIN_PLAIN_S16) {
+            for (uint32_t q = 0; q < nb; ++q) {
+                const uint32_t prog = sm + q * in_bytes, a_chunk = prog + prog_cap + SK_SIDE_HIST;
+                chain_expand_s16(a_chunk, S->cons[q].n_prev, S->cons[q].n_head, ct);
+                chain_consume<OC, OC, ITERS>(acc, prog, a_chunk - 16u * OC * 4u, dm.prog, F, cw, lane, S->cons[q].gain, one2);
+            }
         } else if (KIND == CHAIN_PLAIN) {
             // every input of the op is a resampled f32 stream with the output's channel count (host: validate_chain): this
             // instantiation carries no input-kind code at all -- the consumer loop is sensitive to its instruction footprint

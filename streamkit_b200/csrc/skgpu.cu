@@ -544,7 +544,7 @@ struct Op {
     uint32_t chain_buf_floats = 0;  // chain: floats per staging buffer
     int chain_oc = 2;             // chain: output channels specialisation
     int chain_iters = 1;          // chain: ceil(F / 1024)
-    int chain_kind = CHAIN_ANY;   // chain: CHAIN_PLAIN / CHAIN_BYPASS when every input is of that one kind (specialised kernels), else CHAIN_ANY
+    int chain_kind = CHAIN_ANY;   // chain: CHAIN_PLAIN / _BYPASS / _PLAIN_S16 / _BYPASS_S16 when every input is of that one kind (specialised kernels), else CHAIN_ANY
     ChainDims chain_dm{};         // chain: staging-ring geometry passed to the kernel
     ChainRec *d_rec = nullptr;    // chain: per-input records written by k_phase_chain every tick
     uint32_t chain_grid = 0;      // chain: persistent grid size (CTAs per SM x SMs)
@@ -1213,13 +1213,15 @@ static skgpu_rc validate_chain(const skgpu_plan *p, const skgpu_chain_group *g, 
     *max_buf_floats = (mb + 15u) & ~15u;
     *oc_out = oc < 0 ? 2 : oc;
     {
-        bool plain = ni > 0, bypass = ni > 0;   // one kind only: f32 streams with the output's channel count, all resampled or all rate-equal
+        bool plain = ni > 0, bypass = ni > 0, f32 = true, s16 = true;   // one kind only: streams with the output's channel count, all resampled or all rate-equal, all f32 or all s16
         for (uint32_t i = 0; i < ni; ++i) {
-            const bool shape = (int)c->h_ch[in[i].slot] == *oc_out && !(c->h_flags[in[i].slot] & SLOT_S16);
+            const bool shape = (int)c->h_ch[in[i].slot] == *oc_out;
             plain = plain && shape && !(c->h_flags[in[i].slot] & SLOT_BYPASS);
             bypass = bypass && shape && (c->h_flags[in[i].slot] & SLOT_BYPASS);
+            f32 = f32 && !(c->h_flags[in[i].slot] & SLOT_S16);
+            s16 = s16 && (c->h_flags[in[i].slot] & SLOT_S16);
         }
-        *kind_out = plain ? CHAIN_PLAIN : bypass ? CHAIN_BYPASS : CHAIN_ANY;
+        *kind_out = (plain && f32) ? CHAIN_PLAIN : (bypass && f32) ? CHAIN_BYPASS : (plain && s16) ? CHAIN_PLAIN_S16 : (bypass && s16) ? CHAIN_BYPASS_S16 : CHAIN_ANY;
     }
     // margin for phases the sampling did not hit; even counts keep every staged array a multiple of 16 bytes
     *cap_seg = (need_seg + 5u) & ~1u;
@@ -1505,6 +1507,8 @@ static chain_kernel_t chain_kernel(int oc, int iters, int kind) {
     return iters == 1 ? k_chain<1, 1, K> : iters == 2 ? k_chain<1, 2, K> : k_chain<1, 3, K>;
     if (kind == CHAIN_PLAIN) { SK_CHAIN_PICK(CHAIN_PLAIN) }
     if (kind == CHAIN_BYPASS) { SK_CHAIN_PICK(CHAIN_BYPASS) }
+    if (kind == CHAIN_PLAIN_S16) { SK_CHAIN_PICK(CHAIN_PLAIN_S16) }
+    if (kind == CHAIN_BYPASS_S16) { SK_CHAIN_PICK(CHAIN_BYPASS_S16) }
     SK_CHAIN_PICK(CHAIN_ANY)
 #undef SK_CHAIN_PICK
 }
