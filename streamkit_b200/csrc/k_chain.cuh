@@ -521,7 +521,9 @@ __global__ void __launch_bounds__(PHASE_CHAIN_THREADS, 14) k_phase_chain(const O
 //                 samples/pipelines/dynamic/moq_mixing.yml): no frame programs at all, the staged chunk is the packet;
 //   CHAIN_ANY     anything the chain admits (mono and stereo, bypass, s16 ingest), in any mixture
 //   CHAIN_PLAIN_S16 / CHAIN_BYPASS_S16   the same two with every input arriving as s16 (expanded in shared memory first)
-constexpr int CHAIN_ANY = 0, CHAIN_PLAIN = 1, CHAIN_BYPASS = 2, CHAIN_PLAIN_S16 = 3, CHAIN_BYPASS_S16 = 4;
+//   CHAIN_F32      f32 inputs of the output's channel count, resampled and rate-equal ones mixed (a 48 kHz mix with 44.1 kHz
+//                  and 48 kHz participants): the plain code plus the small pass-through loop, nothing else
+constexpr int CHAIN_ANY = 0, CHAIN_PLAIN = 1, CHAIN_BYPASS = 2, CHAIN_PLAIN_S16 = 3, CHAIN_BYPASS_S16 = 4, CHAIN_F32 = 5;
 template <int OC, int ITERS, int KIND>
 __global__ void __launch_bounds__(CH_THREADS, 5) k_chain(const OpHeader *__restrict__ hdr, const skgpu_chain_group *__restrict__ groups,
                                                          const ChainRec *__restrict__ recs, const float *__restrict__ gains, SlotTables st,
@@ -772,6 +774,13 @@ __global__ void __launch_bounds__(CH_THREADS, 5) k_chain(const OpHeader *__restr
                 const uint32_t prog = sm + q * in_bytes, a_chunk = prog + prog_cap + SK_SIDE_HIST;
                 chain_expand_s16(a_chunk, S->cons[q].n_prev, S->cons[q].n_head, ct);
                 chain_consume<OC, OC, ITERS>(acc, prog, a_chunk - 16u * OC * 4u, dm.prog, F, cw, lane, S->cons[q].gain, one2);
+            }
+        } else if (KIND == CHAIN_F32) {
+            for (uint32_t q = 0; q < nb; ++q) {
+                const ChainCons c = S->cons[q];
+                const uint32_t prog = sm + q * in_bytes, a_chunk = prog + prog_cap + SK_SIDE_HIST;
+                if (c.sc & CK_BYPASS) chain_consume_pass<OC, OC, ITERS>(acc, a_chunk, F, cw, lane, c.gain, one2);
+                else chain_consume<OC, OC, ITERS>(acc, prog, a_chunk - 16u * OC * 4u, dm.prog, F, cw, lane, c.gain, one2);
             }
         } else if (KIND == CHAIN_PLAIN) {
             // every input of the op is a resampled f32 stream with the output's channel count (host: validate_chain): this

@@ -1213,15 +1213,16 @@ static skgpu_rc validate_chain(const skgpu_plan *p, const skgpu_chain_group *g, 
     *max_buf_floats = (mb + 15u) & ~15u;
     *oc_out = oc < 0 ? 2 : oc;
     {
-        bool plain = ni > 0, bypass = ni > 0, f32 = true, s16 = true;   // one kind only: streams with the output's channel count, all resampled or all rate-equal, all f32 or all s16
+        bool plain = ni > 0, bypass = ni > 0, f32 = true, s16 = true, same_shape = ni > 0;   // one kind only: streams with the output's channel count, all resampled or all rate-equal, all f32 or all s16
         for (uint32_t i = 0; i < ni; ++i) {
             const bool shape = (int)c->h_ch[in[i].slot] == *oc_out;
+            same_shape = same_shape && shape;
             plain = plain && shape && !(c->h_flags[in[i].slot] & SLOT_BYPASS);
             bypass = bypass && shape && (c->h_flags[in[i].slot] & SLOT_BYPASS);
             f32 = f32 && !(c->h_flags[in[i].slot] & SLOT_S16);
             s16 = s16 && (c->h_flags[in[i].slot] & SLOT_S16);
         }
-        *kind_out = (plain && f32) ? CHAIN_PLAIN : (bypass && f32) ? CHAIN_BYPASS : (plain && s16) ? CHAIN_PLAIN_S16 : (bypass && s16) ? CHAIN_BYPASS_S16 : CHAIN_ANY;
+        *kind_out = (plain && f32) ? CHAIN_PLAIN : (bypass && f32) ? CHAIN_BYPASS : (plain && s16) ? CHAIN_PLAIN_S16 : (bypass && s16) ? CHAIN_BYPASS_S16 : (same_shape && f32) ? CHAIN_F32 : CHAIN_ANY;
     }
     // margin for phases the sampling did not hit; even counts keep every staged array a multiple of 16 bytes
     *cap_seg = (need_seg + 5u) & ~1u;
@@ -1347,7 +1348,9 @@ extern "C" skgpu_rc skgpu_plan_update_chain(skgpu_plan *p, uint32_t opi, const s
     skgpu_rc rc = validate_chain(p, groups, ng, inputs, ni, op.chain_F, &mk, &mb, &oc, &cnp, &cnr, &kind);
     if (rc) return rc;
     if (ng && oc != op.chain_oc) return fail(SKGPU_ERR_INVALID, "update changes the op's output channel count");
-    if (op.chain_kind != CHAIN_ANY && ni && kind != op.chain_kind) return fail(SKGPU_ERR_INVALID, "update adds an input of another kind (channel count differing from the output's, resampled vs rate-equal bypass, s16) to an op created from inputs of one kind only (include such a stream in the initial tables)");
+    const bool kind_ok = op.chain_kind == CHAIN_ANY || !ni || kind == op.chain_kind ||
+                         (op.chain_kind == CHAIN_F32 && (kind == CHAIN_PLAIN || kind == CHAIN_BYPASS));   // the mixed-f32 kernel runs either
+    if (!kind_ok) return fail(SKGPU_ERR_INVALID, "update adds an input of another kind (channel count differing from the output's, resampled vs rate-equal bypass, s16) to an op created from inputs of one kind only (include such a stream in the initial tables)");
     if (mb > op.chain_buf_floats) return fail(SKGPU_ERR_INVALID, "update has a longer chunk than the op was sized for");
     if (mk > op.chain_dm.max_k) return fail(SKGPU_ERR_INVALID, "update has a session with more inputs (%u) than the op was sized for (%u)", mk, op.chain_dm.max_k);
     if (cnp > op.chain_dm.prog.cap_seg || cnr > op.chain_dm.prog.cap_exp) return fail(SKGPU_ERR_INVALID, "update adds a resampling ratio whose phase tables exceed the op's staging capacity");
@@ -1509,6 +1512,7 @@ static chain_kernel_t chain_kernel(int oc, int iters, int kind) {
     if (kind == CHAIN_BYPASS) { SK_CHAIN_PICK(CHAIN_BYPASS) }
     if (kind == CHAIN_PLAIN_S16) { SK_CHAIN_PICK(CHAIN_PLAIN_S16) }
     if (kind == CHAIN_BYPASS_S16) { SK_CHAIN_PICK(CHAIN_BYPASS_S16) }
+    if (kind == CHAIN_F32) { SK_CHAIN_PICK(CHAIN_F32) }
     SK_CHAIN_PICK(CHAIN_ANY)
 #undef SK_CHAIN_PICK
 }
