@@ -712,6 +712,10 @@ def run_chain(args, D: Dist) -> None:
             if D.dist is not None:
                 hub_e2e["ms_per_step"] = D.max(hub_e2e["ms_per_step"])
                 hub_e2e["value"] = S * world * TICK_MS / hub_e2e["ms_per_step"]
+                zc = hub_e2e.get("zero_copy")
+                if zc:   # whole job, like every other figure of the line
+                    zc["ms_per_step"] = D.max(zc["ms_per_step"])
+                    zc["value"] = S * world * TICK_MS / zc["ms_per_step"]
         except Exception as e:
             hub_e2e = {"error": str(e)[:200]}
 
