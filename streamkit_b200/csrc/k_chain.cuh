@@ -22,14 +22,19 @@
 //                  a ready-made 64-byte ChainRec per input for k_chain's producer.
 //   k_chain        PERSISTENT, WARP-SPECIALISED CTAs (looping over sessions):
 //       warp 0  (producer)   prefetches ChainRecs with cp.async, derives the summation order (base selection +
-//                            swap_remove, mixer.rs:960-980) from warp ballots, and issues 4 TMA bulk copies per
-//                            input (frame program, history, previous chunk, head of the current chunk) into a
-//                            shared-memory ring guarded by full/empty mbarriers;
-//       warps 1-8 (consumers) execute the frame programs: a warp owns 32-frame blocks in which lane l owns frame
-//                            (block start + l) -- neighbouring lanes read neighbouring input frames, so the two
-//                            shared-memory loads of a frame are conflict free. Inputs are added SEQUENTIALLY in the
-//                            reference's order (f32 addition is not associative); master gain, clip +
-//                            s16 pack, one coalesced store per block.
+//                            swap_remove, mixer.rs:960-980) from warp ballots, and issues 3 TMA bulk copies per
+//                            input ([frame program | history], previous chunk, head of the current chunk) into a
+//                            2-stage shared-memory ring guarded by full/empty mbarriers;
+//       warps 1-4 (consumers) execute the frame programs: a warp owns EIGHT consecutive 32-frame blocks in which lane l
+//                            owns frame (block start + l) -- neighbouring lanes read neighbouring input frames, so the
+//                            two shared-memory loads of a frame are conflict free. A block inside the FAST run the warp
+//                            is already in (RunCache) is straight-line code; blocks holding a run boundary or explicit
+//                            frames walk the segments per lane. Inputs are added SEQUENTIALLY in the reference's order
+//                            (f32 addition is not associative); master gain, clip + s16 pack, one coalesced
+//                            store per block.
+// Input kinds: resampled f32 (the reference's path), rate-equal BYPASS (resampler.rs:299-373: the staged
+// chunk is the packet), s16 ingest (expanded to f32 in shared memory); the kernel is instantiated per mixture of kinds
+// (CHAIN_PLAIN ... CHAIN_ANY below) because the consumer loop is sensitive to its instruction footprint.
 #pragma once
 #include "chain_prog.h"
 #include "common.cuh"

@@ -10,9 +10,11 @@
 // The positions x follow the same f64 recurrence idx += 1/ratio as the linear mode, so k_phase (phase_runs.h) produces them
 // exactly and data-independently. Per stream the state in HBM is last_index (f64) and the last L + 8 input frames.
 //
+// Two kernels. k_resample_sinc_tiled (further down; persistent, tap table in shared memory, same-phase output tiles) runs ops whose
+// streams share one tap table; k_resample_sinc is the simple form and the fallback:
 // k_resample_sinc: one CTA per stream-chunk. The input window every output needs -- [history | chunk], 7.6 KB for a 20 ms
 // stereo chunk -- is staged in shared memory by two TMA bulk copies; each thread then owns whole output frames and walks the two
-// tap rows of its sub-phase with 128-bit loads (rows are L floats, 16-byte aligned; the (O + 1) x L table is 66 KB and lives in
+// tap rows of its sub-phase with 128-bit loads (rows are L + 4 floats apart, 16-byte aligned; the (O + 1) x (L + 4) table is 70 KB and lives in
 // L1 / L2: every CTA of the launch reads the same table). The dot products are sequential f32 fma chains in ascending tap order,
 // one chain per channel and row: bit-identical to a plain C fmaf loop. 256 fma per stereo frame at L = 64: the kernel is bound by
 // the FMA / LSU pipes, not by HBM (16 fma per byte moved).
