@@ -250,7 +250,11 @@ skgpu_rc skgpu_plan_add_chain(skgpu_plan *plan, const skgpu_chain_group *groups,
 
 /* same, with explicit table capacities (sessions come and go: skgpu_plan_update_chain may grow the tables up to these)
  * and the largest n_inputs any later group will have (0 = the initial tables' maximum). The initial inputs must cover
- * every stream configuration (rate pair, chunk size, channels) later updates will use: staging is sized from them. */
+ * every stream configuration (rate pair, chunk size, channels) later updates will use: staging is sized from them.
+ * They also fix which kernel the op runs: when every initial input is of ONE kind -- f32 resampled, f32 rate-equal, s16 resampled,
+ * s16 rate-equal, each with the group's channel count -- or an f32 mixture of resampled and rate-equal inputs of that shape, the op
+ * gets the instantiation specialised for it (faster), and a later update must stay within that kind
+ * (SKGPU_ERR_INVALID otherwise). Initial tables that already mix channel counts or formats get the general kernel. */
 skgpu_rc skgpu_plan_add_chain_cap(skgpu_plan *plan, const skgpu_chain_group *groups, uint32_t n_groups,
                                   const skgpu_chain_input *inputs, uint32_t n_inputs, uint32_t cap_groups, uint32_t cap_inputs,
                                   uint32_t max_inputs_per_group, uint32_t output_frame_size, uint64_t results_off, uint32_t *op_out);
