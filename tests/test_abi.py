@@ -6,7 +6,6 @@ import os
 import re
 import subprocess
 
-import numpy as np
 import pytest
 
 from streamkit_b200 import lib as L

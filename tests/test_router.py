@@ -8,7 +8,7 @@ import uuid
 import numpy as np
 import pytest
 
-from streamkit_b200 import router as R, shard, synth
+from streamkit_b200 import router as R, shard
 from tests.test_hub import _OracleSession, _chunk
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))

@@ -7,7 +7,6 @@ import pytest
 
 from oracle import np_oracle, sko
 from streamkit_b200 import lib as L, synth
-from tests import pins
 
 TOL = 2e-6    # north_star: f32 resample within 2e-6 max-abs
 

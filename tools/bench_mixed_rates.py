@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Device-resident kernel times of the fused chain for sessions that mix a resampled (44.1 kHz) and a rate-equal (48 kHz) input --
 the CHAIN_F32 instantiation -- next to the all-resampled shape (CHAIN_PLAIN). 65,536 sessions x 2 stereo inputs."""
-import sys, numpy as np
+import sys
 sys.path.insert(0, __import__('os').path.dirname(__import__('os').path.dirname(__import__('os').path.abspath(__file__))))
 from streamkit_b200 import chain, lib as L, synth
 for rates in ([44100, 48000], [44100, 44100]):
