@@ -41,3 +41,15 @@ def test_cuda_arm_fails_loudly_without_a_gpu():
     p, lines = _run("--steps", "1", "--warmup", "1", "--no-hub", "--no-router")
     assert p.returncode != 0
     assert not any(ln.lstrip().startswith("{") and '"value"' in ln for ln in lines)
+
+
+def test_reference_arm_under_torchrun_prints_from_rank_0_only():
+    """N > 1: the driver launches the reference arm under torchrun like the CUDA arm; rank 0 alone runs and prints, the others exit 0"""
+    p = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29541", os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "2", "--warmup", "1"],
+                       capture_output=True, text=True, timeout=900, cwd=ROOT)
+    assert p.returncode == 0, p.stderr[-800:]
+    lines = [ln for ln in p.stdout.splitlines() if ln.lstrip().startswith("{")]
+    assert len(lines) == 1, lines
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["n_gpus"] == 2
